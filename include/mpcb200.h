@@ -1,0 +1,260 @@
+/*
+ * mpcb200.h -- C ABI of the B200-native batched receding-horizon OCP solver.
+ *
+ * This is the drop-in boundary for the ONE hot path of rst-tu-dortmund/mpc_local_planner:
+ * everything below Controller::step() (reference: mpc_local_planner/include/mpc_local_planner/controller.h:61-104,
+ * mpc_local_planner/src/controller.cpp:102-179), i.e. the OCP transcription (FiniteDifferencesGridSE2::createEdges,
+ * src/optimal_control/finite_differences_grid_se2.cpp:36-152), the hypergraph derivative assembly and the
+ * interior-point solve that the reference delegates to control_box_rst + Ipopt (src/controller.cpp:380-421).
+ *
+ * Plain C, plain pointers and sizes; no C++/torch types cross this boundary. All floating point is IEEE double.
+ * All host arrays are row-major "[instance][k][component]" unless stated otherwise.
+ * A handle owns one CUDA device's workspace; it is NOT thread-safe (same contract as Controller::step,
+ * which is not re-entrant: src/controller.cpp:111-179 mutates the grid).  Functions return 0 on success and a
+ * negative MPCB200_E_* code on failure; they never throw and never abort (reference convention: bool return,
+ * no exception crosses step(), src/controller.cpp:114-123,172,178).
+ */
+#ifndef MPCB200_H_
+#define MPCB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB200_VERSION 100
+
+/* ---- enums (ints in the struct so that ctypes/cgo bindings are trivial) -------------------------------- */
+
+/* robot/type (src/controller.cpp:344-378) */
+#define MPCB200_ROBOT_UNICYCLE 0          /* inc/systems/unicycle_robot.h:59-68 */
+#define MPCB200_ROBOT_SIMPLE_CAR 1        /* inc/systems/simple_car.h:68-77  (rear wheel driving) */
+#define MPCB200_ROBOT_SIMPLE_CAR_FRONT 2  /* inc/systems/simple_car.h:131-141 */
+#define MPCB200_ROBOT_KIN_BICYCLE 3       /* inc/systems/kinematic_bicycle_model.h:65-77 */
+
+/* grid/collocation_method (src/controller.cpp:298-316) */
+#define MPCB200_COLLOC_FORWARD 0   /* inc/optimal_control/fd_collocation_se2.h:54-69 (default, every shipped config) */
+#define MPCB200_COLLOC_MIDPOINT 1  /* :91-108  -- not implemented in this round: create() returns E_UNSUPPORTED */
+#define MPCB200_COLLOC_CRANK_NICOLSON 2 /* :130-147 -- idem (see SURVEY App. C.1 for the reference quirk) */
+
+/* planning/objective/type (src/controller.cpp:551-641) */
+#define MPCB200_OBJ_MINIMUM_TIME 0            /* corbo::MinimumTime: J = (N-1)*dt */
+#define MPCB200_OBJ_QUADRATIC_FORM 1          /* QuadraticFormCostSE2, src/optimal_control/quadratic_cost_se2.cpp:31-52 */
+#define MPCB200_OBJ_MINIMUM_TIME_VIA_POINTS 2 /* src/optimal_control/min_time_via_points_cost.cpp:40-145 */
+
+/* footprint_model/type (src/mpc_local_planner_ros.cpp:890-1028) */
+#define MPCB200_FOOTPRINT_POINT 0
+#define MPCB200_FOOTPRINT_CIRCULAR 1    /* params[0] = radius */
+#define MPCB200_FOOTPRINT_TWO_CIRCLES 2 /* params = front_offset, front_radius, rear_offset, rear_radius */
+#define MPCB200_FOOTPRINT_LINE 3        /* params = start.x, start.y, end.x, end.y (robot frame) */
+#define MPCB200_FOOTPRINT_POLYGON 4     /* n_poly vertices in poly_xy (robot frame), closing edge implied */
+
+/* obstacle types (teb_local_planner obstacles) */
+#define MPCB200_OBST_POINT 0  /* params: x, y */
+#define MPCB200_OBST_CIRCLE 1 /* params: x, y, -, -, radius */
+#define MPCB200_OBST_LINE 2   /* params: x0, y0, x1, y1 */
+
+/* per-instance solver status written to status[] */
+#define MPCB200_STATUS_CONVERGED 0       /* scaled KKT error <= tol */
+#define MPCB200_STATUS_MAX_ITER 1        /* iteration cap hit (reference: EarlyTerminated => step() still returns true) */
+#define MPCB200_STATUS_NUMERICAL_ERROR 2 /* inertia correction or line search failed */
+#define MPCB200_STATUS_INVALID_INPUT 3   /* NaN/inf in the instance's inputs */
+
+/* error codes */
+#define MPCB200_OK 0
+#define MPCB200_E_INVALID -1     /* bad argument / config */
+#define MPCB200_E_UNSUPPORTED -2 /* feature of the reference that this build does not implement */
+#define MPCB200_E_CUDA -3        /* CUDA runtime error (message in mpcb200_last_error) */
+#define MPCB200_E_NOMEM -4
+#define MPCB200_E_NODEVICE -5    /* no CUDA device: there is NO CPU fallback */
+
+#define MPCB200_MAX_POLY 16
+#define MPCB200_OBST_STRIDE 5    /* doubles per obstacle in mpcb200_obstacles.params */
+#define MPCB200_INF 1e30         /* |bound| >= this means "no bound" (corbo CORBO_INF_DBL sentinel) */
+
+/*
+ * Solver/OCP configuration shared by all instances of a handle.  Field names and defaults follow the reference's
+ * ROS parameter keys (src/controller.cpp:225-805).  mpcb200_default_config() fills the in-code
+ * defaults of the reference.
+ */
+typedef struct mpcb200_config {
+    /* robot (src/controller.cpp:344-378, 494-549, 733-800) */
+    int robot_type;
+    double wheelbase;      /* simple_car/wheelbase (0.5) */
+    double length_rear;    /* kinematic_bicycle_vel_input/length_rear (1.0) */
+    double length_front;   /* kinematic_bicycle_vel_input/length_front (1.0) */
+    double u_lb[2];        /* control lower bounds: (-max_vel_x_backwards, -max_vel_theta | -max_steering_angle) */
+    double u_ub[2];        /* control upper bounds */
+    double du_lb[2];       /* control-rate lower bounds (-dec_lim_x, -acc_lim_theta|-max_steering_rate); <= -MPCB200_INF: off */
+    double du_ub[2];       /* control-rate upper bounds; >= MPCB200_INF: off */
+    /* grid (src/controller.cpp:225-342) */
+    int n;                 /* grid/grid_size_ref: number of grid points N (x_0 .. x_{N-1}) */
+    double dt_ref;         /* grid/dt_ref */
+    int variable_dt;       /* grid/variable_grid/enable: dt is a decision variable (one shared dt) */
+    double dt_lb, dt_ub;   /* grid/variable_grid/{min_dt,max_dt} */
+    int xf_fixed[3];       /* grid/xf_fixed */
+    int collocation;       /* grid/collocation_method */
+    int warm_start;        /* grid/warm_start (fixed-dt grid only; the variable grid disables the shift,
+                              inc/optimal_control/finite_differences_variable_grid_se2.h:85) */
+    /* objective (src/controller.cpp:551-674) */
+    int objective;
+    double Q[9], R[4];     /* quadratic_form state/control weights, row-major full matrices */
+    int terminal_cost;     /* planning/terminal_cost/type == "quadratic" */
+    double Qf[9];
+    double vp_position_weight;    /* minimum_time_via_points/position_weight */
+    double vp_orientation_weight; /* .../orientation_weight (linear in the wrapped angle) */
+    int vp_ordered;               /* .../via_points_ordered */
+    int vp_attraction_with_quadratic; /* EXTENSION (SURVEY 8d cfg 4 reading A): add the via-point attraction term to quadratic_form */
+    /* collision avoidance (src/controller.cpp:711-729) */
+    double min_obstacle_dist, force_inclusion_dist, cutoff_dist;
+    int footprint_type;
+    double footprint_params[4];
+    int n_poly;
+    double poly_xy[2 * MPCB200_MAX_POLY];
+    int k_max_obstacles_per_stage; /* fixed row budget K per stage on the device (masked rows are exact no-ops) */
+    /* solver (src/controller.cpp:380-421): the interior-point method replaces Ipopt */
+    int max_iter;          /* solver/ipopt/iterations (100) */
+    double tol;            /* scaled KKT error tolerance; "converged" <=> error <= tol */
+    double mu_init;        /* initial barrier parameter (Ipopt default 0.1) */
+    int outer_iterations;  /* controller/outer_ocp_iterations */
+} mpcb200_config;
+
+/* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]). */
+typedef struct mpcb200_obstacles {
+    int max_per_instance;
+    const int* count;      /* [B] */
+    const int* type;       /* [B*max_per_instance] MPCB200_OBST_* */
+    const double* params;  /* [B*max_per_instance*MPCB200_OBST_STRIDE]: x0, y0, x1, y1, radius */
+} mpcb200_obstacles;
+
+/* Per-instance via-points (teb PoseSE2 list handed to Controller::configure, inc/controller.h:61-63). */
+typedef struct mpcb200_viapoints {
+    int max_per_instance;
+    const int* count;      /* [B] */
+    const double* poses;   /* [B*max_per_instance*3]: x, y, theta */
+} mpcb200_viapoints;
+
+typedef struct mpcb200_handle mpcb200_handle;
+
+/* Fills *cfg with the reference's in-code defaults: unicycle, N=20, dt_ref=0.3, minimum_time ... */
+void mpcb200_default_config(mpcb200_config* cfg);
+
+/*
+ * Replaces Controller::configure (inc/controller.h:61-63, src/controller.cpp:58-100): validates the configuration,
+ * selects `device`, allocates the device workspace for up to max_batch instances.
+ */
+int mpcb200_create(const mpcb200_config* cfg, int max_batch, int device, mpcb200_handle** out);
+
+/*
+ * Replaces Controller::step (inc/controller.h:65-67, src/controller.cpp:111-179) for a batch of B independent
+ * instances.  Per instance: x0 = measured state (start pose), xf = goal pose, u_prev/u_prev_dt = previously applied
+ * control and its age (StructuredOptimalControlProblem::setPreviousControlInput, src/mpc_local_planner_ros.cpp:384).
+ *   x_init  optional [B][N][3] initial state guess (reference: _x_seq_init sampled at k*dt, src/controller.cpp:807-857);
+ *           NULL => straight line start->goal with angle-aware linear interpolation (what the reference produces for
+ *           a 2-pose plan).
+ *   reinit  optional [B]: non-zero forces a cold re-initialisation of that instance (grid->clear(), src/controller.cpp:152-158);
+ *           NULL => cold start on the first call after create/reset, warm start afterwards when cfg.warm_start.
+ * Outputs (any may be NULL): u_seq [B][N][2] (last control duplicated, full_discretization_grid_base_se2.cpp:591-614),
+ *   x_seq [B][N][3], dt_out [B], status [B], kkt_err [B] (final scaled KKT error), iters [B], solve_time_s [1]
+ *   (device time of the whole batch, the analogue of OptimalControlResult.cpu_time).
+ * Host pointers may be pageable or pinned; host<->device copies happen inside this call.
+ */
+int mpcb200_step_batch(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev,
+                       double u_prev_dt, const mpcb200_obstacles* obst, const mpcb200_viapoints* vp,
+                       const double* x_init, const unsigned char* reinit, double* u_seq, double* x_seq,
+                       double* dt_out, int* status, double* kkt_err, int* iters, double* solve_time_s);
+
+/* Replaces Controller::reset (inc/controller.h:104): which == NULL resets every instance, else those with which[b] != 0. */
+int mpcb200_reset(mpcb200_handle* h, const unsigned char* which, int B);
+
+void mpcb200_destroy(mpcb200_handle* h);
+
+/* Last error message of this handle (or of create() when h == NULL). Never NULL. */
+const char* mpcb200_last_error(const mpcb200_handle* h);
+
+/* ---- device-resident variant (inputs already in HBM; used by bench.py's kernel-only `value`) ----------- */
+
+/*
+ * Stage the inputs of a batch on the device once (same arguments as mpcb200_step_batch), then
+ * mpcb200_solve_resident() re-runs init + association + solve from those resident inputs without any
+ * host<->device traffic, and mpcb200_fetch_results() copies the results back.
+ */
+int mpcb200_upload_inputs(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev,
+                          double u_prev_dt, const mpcb200_obstacles* obst, const mpcb200_viapoints* vp,
+                          const double* x_init);
+int mpcb200_solve_resident(mpcb200_handle* h, int cold, double* solve_time_s);
+int mpcb200_fetch_results(mpcb200_handle* h, double* u_seq, double* x_seq, double* dt_out, int* status,
+                          double* kkt_err, int* iters);
+/* Device pointer of the packed optimal controls [B][N-1][2] (for the NCCL all-gather of u*) and its size. */
+int mpcb200_device_controls(mpcb200_handle* h, void** dev_ptr, long long* n_doubles);
+
+/* ---- kernel-level access: parity tests and the roofline measurement ------------------------------------ */
+
+/* Workspace fields, each stored per instance as [component][k] (k = stage index 0..N-1, fastest). */
+#define MPCB200_F_X 0      /* 3 x N   states */
+#define MPCB200_F_U 1      /* 2 x N   controls (k = N-1 unused) */
+#define MPCB200_F_NU 2     /* 3 x N   multipliers of the dynamics defects (k = N-1 unused) */
+#define MPCB200_F_S 3      /* RS x N  slacks of the inequality rows, RS = 8 + K */
+#define MPCB200_F_LAM 4    /* RS x N  multipliers of the inequality rows */
+#define MPCB200_F_KKT 5    /* 42 x N  condensed KKT stage records (see DESIGN.md "KKT record") */
+#define MPCB200_F_STEP 6   /* 8 x N   Newton step: dw (5), nu_plus (3) */
+#define MPCB200_F_SCAL 7   /* 16      per-instance scalars (see MPCB200_SC_*) */
+#define MPCB200_F_OBSIDX 8 /* K x N   associated obstacle index per row slot as double (-1 = empty) */
+#define MPCB200_KKT_WORDS 42
+/* offsets inside one KKT stage record (DESIGN.md "KKT record"); stage k = 0..N-2, terminal data at k = N-1 */
+#define MPCB200_K_H 0    /* 15: upper triangle (row-major) of the condensed 5x5 Hessian block of w_k = (x_k, u_k) */
+#define MPCB200_K_G 15   /* 5 : condensed gradient */
+#define MPCB200_K_A 20   /* 3 : dt * df/dtheta  (A_k = I + a e_theta^T) */
+#define MPCB200_K_B 23   /* 6 : dt * df/du, row-major 3x2 */
+#define MPCB200_K_E 29   /* 3 : defect e_k = x_k + dt f(x_k,u_k) - x_{k+1} */
+#define MPCB200_K_C 32   /* 2 : diagonal of the cross block d2L/du_{k-1} du_k (control-rate rows) */
+#define MPCB200_K_HB 34  /* 5 : border column d2L/dw_k d(dt) */
+#define MPCB200_K_D 39   /* 3 : de_k/d(dt) = f(x_k,u_k) */
+#define MPCB200_STEP_WORDS 8
+#define MPCB200_SCAL_WORDS 16
+/* indices into the SCAL field */
+#define MPCB200_SC_DT 0
+#define MPCB200_SC_MU 1
+#define MPCB200_SC_RHO 2
+#define MPCB200_SC_DELTA 3
+#define MPCB200_SC_HTT 4
+#define MPCB200_SC_GT 5
+#define MPCB200_SC_DDT 6
+#define MPCB200_SC_ERR0 7    /* scaled KKT error E_0 */
+#define MPCB200_SC_ERRMU 8   /* barrier-problem error E_mu */
+#define MPCB200_SC_ITER 9
+#define MPCB200_SC_STATUS 10
+#define MPCB200_SC_ALPHA 11
+#define MPCB200_SC_OBJ 12
+#define MPCB200_SC_INF 13    /* l1 infeasibility */
+#define MPCB200_SC_DELTA_LAST 14
+#define MPCB200_SC_NREG 15   /* number of inertia-correction refactorisations so far */
+
+int mpcb200_ws_count(const mpcb200_handle* h, int field);  /* number of components of a field (e.g. RS) */
+int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst);        /* dst: [B][count][N] (SCAL: [B][16]) */
+int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const double* src);
+
+/* phases of one solve, launchable one by one */
+#define MPCB200_PHASE_INIT 0       /* cold initial guess + slack/multiplier initialisation */
+#define MPCB200_PHASE_ASSOCIATE 1  /* obstacle / via-point association (StageInequalitySE2::update) */
+#define MPCB200_PHASE_EVAL 2       /* stage functions + derivatives -> condensed KKT records, KKT error */
+#define MPCB200_PHASE_KKT 3        /* block-tridiagonal Riccati factorisation + solve -> Newton step */
+#define MPCB200_PHASE_LINESEARCH 4 /* step lengths, merit line search, iterate + barrier update */
+#define MPCB200_NUM_PHASES 5
+int mpcb200_run_phase(mpcb200_handle* h, int phase, int B);
+/* Launch `phase` reps times back to back and report the mean device time per launch (CUDA events on the solver stream). */
+int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps, int flush_l2, double* ms_per_launch);
+
+/* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */
+typedef struct mpcb200_stats {
+    long long launches[MPCB200_NUM_PHASES];
+    double ms[MPCB200_NUM_PHASES];
+    long long launches_total;
+    long long h2d_bytes, d2h_bytes;
+} mpcb200_stats;
+int mpcb200_stats_get(const mpcb200_handle* h, mpcb200_stats* out);
+int mpcb200_stats_reset(mpcb200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB200_H_ */
