@@ -197,7 +197,7 @@ int mpcb200_device_controls(mpcb200_handle* h, void** dev_ptr, long long* n_doub
 #define MPCB200_F_LAM 4    /* RS x N  multipliers of the inequality rows */
 #define MPCB200_F_KKT 5    /* 42 x N  condensed KKT stage records (see DESIGN.md "KKT record") */
 #define MPCB200_F_STEP 6   /* 8 x N   Newton step: dw (5), nu_plus (3) */
-#define MPCB200_F_SCAL 7   /* 16      per-instance scalars (see MPCB200_SC_*) */
+#define MPCB200_F_SCAL 7   /* 24      per-instance scalars (see MPCB200_SC_*) */
 #define MPCB200_F_OBSIDX 8 /* K x N   associated obstacle index per row slot as double (-1 = empty) */
 #define MPCB200_KKT_WORDS 42
 /* offsets inside one KKT stage record (DESIGN.md "KKT record"); stage k = 0..N-2, terminal data at k = N-1 */
@@ -210,7 +210,7 @@ int mpcb200_device_controls(mpcb200_handle* h, void** dev_ptr, long long* n_doub
 #define MPCB200_K_HB 34  /* 5 : border column d2L/dw_k d(dt) */
 #define MPCB200_K_D 39   /* 3 : de_k/d(dt) = f(x_k,u_k) */
 #define MPCB200_STEP_WORDS 8
-#define MPCB200_SCAL_WORDS 16
+#define MPCB200_SCAL_WORDS 24
 /* indices into the SCAL field */
 #define MPCB200_SC_DT 0
 #define MPCB200_SC_MU 1
@@ -228,9 +228,13 @@ int mpcb200_device_controls(mpcb200_handle* h, void** dev_ptr, long long* n_doub
 #define MPCB200_SC_INF 13    /* l1 infeasibility */
 #define MPCB200_SC_DELTA_LAST 14
 #define MPCB200_SC_NREG 15   /* number of inertia-correction refactorisations so far */
+#define MPCB200_SC_BLOG 16   /* sum of log(slack) over active rows */
+#define MPCB200_SC_GLDT 17   /* dL/d(dt) */
+#define MPCB200_SC_NBT 18    /* line-search backtracks so far */
+#define MPCB200_SC_COLD 19   /* 1 until the instance has been solved once (cold start pending) */
 
 int mpcb200_ws_count(const mpcb200_handle* h, int field);  /* number of components of a field (e.g. RS) */
-int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst);        /* dst: [B][count][N] (SCAL: [B][16]) */
+int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst);        /* dst: [B][count][N] (SCAL: [B][24]) */
 int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const double* src);
 
 /* phases of one solve, launchable one by one */

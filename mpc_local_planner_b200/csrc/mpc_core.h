@@ -1,0 +1,358 @@
+// mpc_core.h -- host/device core of the sm_100a solver: workspace layout and the reference restatement of the
+// elementary OCP functions.  Everything here is `__host__ __device__` so that tests/emu can run the SAME code on a
+// CPU warp emulator (test infrastructure); the product only ever runs it inside the CUDA kernels of mpcb200.cu.
+//
+// Reference files restated here (R/ = mpc_local_planner/ in rst-tu-dortmund/mpc_local_planner):
+//   normalize_theta / interpolate_angle   R/include/mpc_local_planner/utils/math_utils.h:81-103
+//   robot dynamics                        R/include/mpc_local_planner/systems/{unicycle_robot.h:59-68,simple_car.h:68-77,131-141,
+//                                          kinematic_bicycle_model.h:65-77}
+//   footprint distances                   teb_local_planner RobotFootprintModel::calculateDistance semantics,
+//                                          used at R/src/optimal_control/stage_inequality_se2.cpp:109,173
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define HD __host__ __device__
+#else
+#define HD
+#endif
+
+#include "../../include/mpcb200.h"
+
+#define KW MPCB200_KKT_WORDS
+#define MAXSEG (MPCB200_MAX_POLY + 2)
+
+// ---- per-instance workspace layout (doubles).  Every array field is [component][k], k fastest, so that the
+//      lanes of the warp that owns the instance touch consecutive addresses (stage-contiguous, coalesced). ----
+struct WsLayout
+{
+    int N, K, RS, M, V;      // grid points, obstacle rows per stage, row slots, max obstacles, max via-points
+    int64_t stride;          // doubles per instance (multiple of 16 -> 128-byte aligned blocks)
+    int oX, oU, oNU, oS, oLAM, oKKT, oSTEP, oOBS, oSCAL, oDS, oDLAM, oRIC, oVPST;
+    int oIN;                 // x0(3) xf(3) u_prev(2) n_obst n_vp has_xinit reinit
+    int oOBST, oOTYPE, oVP, oXINIT;
+    int ricw;                // Riccati scratch words per stage
+};
+#define IN_X0 0
+#define IN_XF 3
+#define IN_UPREV 6
+#define IN_NOBST 8
+#define IN_NVP 9
+#define IN_HASXINIT 10
+#define IN_REINIT 11
+#define IN_WORDS 16
+
+// solver constants (same values as the oracle)
+#define KAPPA_EPS 10.0
+#define KAPPA_MU 0.2
+#define THETA_MU 1.5
+#define TAU_MIN 0.99
+#define SLACK_PUSH 1e-2
+#define ARMIJO 1e-4
+#define MAX_BACKTRACK 30
+#define KAPPA_SIGMA 1e10
+#define SMAX 100.0
+#define PROJ_MARGIN 0.05
+#define PROJ_SWEEPS 6
+#define INIT_SHRINK 0.9
+
+typedef mpcb200_config Cfg;
+
+// ---- elementary functions ----
+HD inline double normalize_theta(double theta)
+{
+    const double PI = 3.14159265358979323846;
+    if (theta >= -PI && theta < PI) return theta;
+    double multiplier = floor(theta / (2.0 * PI));
+    theta = theta - multiplier * 2.0 * PI;
+    if (theta >= PI) theta -= 2.0 * PI;
+    if (theta < -PI) theta += 2.0 * PI;
+    return theta;
+}
+HD inline double interpolate_angle(double a1, double a2, double factor)
+{
+    return normalize_theta(a1 + factor * normalize_theta(a2 - a1));
+}
+
+// f(x,u) and derivatives wrt q = (theta, u0, u1): J[j*3+i] = df_j/dq_i, Hc = sum_j nu_j Hess f_j packed (tt,t0,t1,00,01,11)
+HD inline void dynamics_derivs(const Cfg& c, double th, double v, double w, const double* nu, double* f, double* J,
+                                       double* Hc)
+{
+#pragma unroll
+    for (int i = 0; i < 9; ++i) J[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Hc[i] = 0.0;
+    if (c.robot_type != MPCB200_ROBOT_KIN_BICYCLE)
+    {
+        double s, co;
+        sincos(th, &s, &co);
+        f[0] = v * co; f[1] = v * s;
+        J[0] = -v * s; J[1] = co;
+        J[3] = v * co; J[4] = s;
+        Hc[0] = nu[0] * (-v * co) + nu[1] * (-v * s);
+        Hc[1] = nu[0] * (-s) + nu[1] * co;
+        if (c.robot_type == MPCB200_ROBOT_UNICYCLE)
+        {
+            f[2] = w; J[8] = 1.0;
+        }
+        else if (c.robot_type == MPCB200_ROBOT_SIMPLE_CAR)
+        {
+            const double L = c.wheelbase, t = tan(w), sec2 = 1.0 + t * t;
+            f[2] = v * t / L; J[7] = t / L; J[8] = v * sec2 / L;
+            Hc[4] += nu[2] * sec2 / L;
+            Hc[5] += nu[2] * 2.0 * v * t * sec2 / L;
+        }
+        else
+        {
+            const double L = c.wheelbase;
+            double sp, cp;
+            sincos(w, &sp, &cp);
+            f[2] = v * sp / L; J[7] = sp / L; J[8] = v * cp / L;
+            Hc[4] += nu[2] * cp / L;
+            Hc[5] += nu[2] * (-v * sp / L);
+        }
+    }
+    else
+    {
+        const double lr = c.length_rear, kap = lr / (c.length_front + lr);
+        const double t = tan(w), sec2 = 1.0 + t * t, den = 1.0 + kap * kap * t * t;
+        const double beta = atan(kap * t);
+        const double b1 = kap * sec2 / den;
+        const double b2 = 2.0 * kap * t * (1.0 - kap * kap) * sec2 / (den * den);
+        double s, co, sb, cb;
+        sincos(th + beta, &s, &co);
+        sincos(beta, &sb, &cb);
+        f[0] = v * co; f[1] = v * s; f[2] = v * sb / lr;
+        J[0] = -v * s; J[1] = co; J[2] = -v * s * b1;
+        J[3] = v * co; J[4] = s;  J[5] = v * co * b1;
+        J[6] = 0.0;    J[7] = sb / lr; J[8] = v * cb * b1 / lr;
+        Hc[0] += nu[0] * (-v * co) + nu[1] * (-v * s);
+        Hc[1] += nu[0] * (-s) + nu[1] * co;
+        Hc[2] += nu[0] * (-v * co * b1) + nu[1] * (-v * s * b1);
+        Hc[4] += nu[0] * (-s * b1) + nu[1] * (co * b1) + nu[2] * (cb * b1 / lr);
+        Hc[5] += nu[0] * (-v * co * b1 * b1 - v * s * b2) + nu[1] * (-v * s * b1 * b1 + v * co * b2) +
+                 nu[2] * (v * (-sb * b1 * b1 + cb * b2) / lr);
+    }
+}
+
+HD inline void dynamics_value(const Cfg& c, double th, double v, double w, double* f)
+{
+    if (c.robot_type != MPCB200_ROBOT_KIN_BICYCLE)
+    {
+        double s, co;
+        sincos(th, &s, &co);
+        f[0] = v * co; f[1] = v * s;
+        if (c.robot_type == MPCB200_ROBOT_UNICYCLE) f[2] = w;
+        else if (c.robot_type == MPCB200_ROBOT_SIMPLE_CAR) f[2] = v * tan(w) / c.wheelbase;
+        else f[2] = v * sin(w) / c.wheelbase;
+    }
+    else
+    {
+        double beta = atan(c.length_rear / (c.length_front + c.length_rear) * tan(w));
+        f[0] = v * cos(th + beta); f[1] = v * sin(th + beta); f[2] = v * sin(beta) / c.length_rear;
+    }
+}
+
+// ---- footprint geometry ----
+struct FpSeg { double ax, ay, bx, by, rad; };
+
+HD inline int footprint_segments(const Cfg& c, FpSeg* seg)
+{
+    switch (c.footprint_type)
+    {
+        case MPCB200_FOOTPRINT_POINT: seg[0] = FpSeg{0, 0, 0, 0, 0}; return 1;
+        case MPCB200_FOOTPRINT_CIRCULAR: seg[0] = FpSeg{0, 0, 0, 0, c.footprint_params[0]}; return 1;
+        case MPCB200_FOOTPRINT_TWO_CIRCLES:
+            seg[0] = FpSeg{c.footprint_params[0], 0, c.footprint_params[0], 0, c.footprint_params[1]};
+            seg[1] = FpSeg{-c.footprint_params[2], 0, -c.footprint_params[2], 0, c.footprint_params[3]};
+            return 2;
+        case MPCB200_FOOTPRINT_LINE:
+            seg[0] = FpSeg{c.footprint_params[0], c.footprint_params[1], c.footprint_params[2], c.footprint_params[3], 0};
+            return 1;
+        default:
+        {
+            int n = c.n_poly;
+            if (n == 1) { seg[0] = FpSeg{c.poly_xy[0], c.poly_xy[1], c.poly_xy[0], c.poly_xy[1], 0}; return 1; }
+            if (n == 2) { seg[0] = FpSeg{c.poly_xy[0], c.poly_xy[1], c.poly_xy[2], c.poly_xy[3], 0}; return 1; }
+            for (int i = 0; i < n; ++i)
+            {
+                int j = (i + 1) % n;
+                seg[i] = FpSeg{c.poly_xy[2 * i], c.poly_xy[2 * i + 1], c.poly_xy[2 * j], c.poly_xy[2 * j + 1], 0};
+            }
+            return n;
+        }
+    }
+}
+
+// distance footprint(pose) <-> point/circle obstacle; optional gradient (x,y,theta) and Hessian (xx,xy,xt,yy,yt,tt)
+template <bool WITH_GRAD, bool WITH_HESS>
+HD inline double footprint_distance(const Cfg& c, double px, double py, double pth, int obst_type, const double* op,
+                                            double* grad3, double* hess6)
+{
+    double s, co;
+    sincos(pth, &s, &co);
+    const double ox = op[0] - px, oy = op[1] - py;
+    const double qx = co * ox + s * oy, qy = -s * ox + co * oy;
+    double best = 1e300, bcx = 0, bcy = 0, brho = 0;
+    int bvert = 1;
+    // iterate the footprint features without materialising the segment list (register pressure)
+    int ns;
+    switch (c.footprint_type)
+    {
+        case MPCB200_FOOTPRINT_POINT:
+        case MPCB200_FOOTPRINT_CIRCULAR:
+        case MPCB200_FOOTPRINT_LINE: ns = 1; break;
+        case MPCB200_FOOTPRINT_TWO_CIRCLES: ns = 2; break;
+        default: ns = c.n_poly <= 2 ? 1 : c.n_poly;
+    }
+    for (int i = 0; i < ns; ++i)
+    {
+        double ax, ay, bx, by, rad = 0.0;
+        switch (c.footprint_type)
+        {
+            case MPCB200_FOOTPRINT_POINT: ax = ay = bx = by = 0.0; break;
+            case MPCB200_FOOTPRINT_CIRCULAR: ax = ay = bx = by = 0.0; rad = c.footprint_params[0]; break;
+            case MPCB200_FOOTPRINT_TWO_CIRCLES:
+                if (i == 0) { ax = bx = c.footprint_params[0]; ay = by = 0.0; rad = c.footprint_params[1]; }
+                else { ax = bx = -c.footprint_params[2]; ay = by = 0.0; rad = c.footprint_params[3]; }
+                break;
+            case MPCB200_FOOTPRINT_LINE:
+                ax = c.footprint_params[0]; ay = c.footprint_params[1]; bx = c.footprint_params[2]; by = c.footprint_params[3];
+                break;
+            default:
+            {
+                int n = c.n_poly;
+                int j = (n <= 2) ? (n - 1) : ((i + 1) % n);
+                ax = c.poly_xy[2 * i]; ay = c.poly_xy[2 * i + 1]; bx = c.poly_xy[2 * j]; by = c.poly_xy[2 * j + 1];
+            }
+        }
+        double dx = bx - ax, dy = by - ay;
+        double sq = dx * dx + dy * dy;
+        double t = 0.0;
+        if (sq > 0.0) t = ((qx - ax) * dx + (qy - ay) * dy) / sq;
+        int isv = 0;
+        if (!(sq > 0.0) || t <= 0.0) { t = 0.0; isv = 1; }
+        else if (t >= 1.0) { t = 1.0; isv = 1; }
+        double cx = ax + t * dx, cy = ay + t * dy;
+        double ex = qx - cx, ey = qy - cy;
+        double rho = sqrt(ex * ex + ey * ey);
+        double d = rho - rad;
+        if (d < best) { best = d; bcx = cx; bcy = cy; brho = rho; bvert = isv; }
+    }
+    double r_obst = (obst_type == MPCB200_OBST_CIRCLE) ? op[4] : 0.0;
+    double dist = best - r_obst;
+    if (WITH_GRAD)
+    {
+        double rho = brho > 1e-12 ? brho : 1e-12;
+        double nx = (qx - bcx) / rho, ny = (qy - bcy) / rho;
+        double J0[3] = {-co, -s, qy}, J1[3] = {s, -co, -qx};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grad3[i] = nx * J0[i] + ny * J1[i];
+        if (WITH_HESS)
+        {
+            double h00 = 0, h01 = 0, h11 = 0;
+            if (bvert) { h00 = (1 - nx * nx) / rho; h01 = -nx * ny / rho; h11 = (1 - ny * ny) / rho; }
+            double H[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    H[i][j] = J0[i] * (h00 * J0[j] + h01 * J1[j]) + J1[i] * (h01 * J0[j] + h11 * J1[j]);
+            double mx = nx * s + ny * co;
+            double my = -nx * co + ny * s;
+            H[0][2] += mx; H[2][0] += mx;
+            H[1][2] += my; H[2][1] += my;
+            H[2][2] += -(nx * qx + ny * qy);
+            hess6[0] = H[0][0]; hess6[1] = H[0][1]; hess6[2] = H[0][2];
+            hess6[3] = H[1][1]; hess6[4] = H[1][2]; hess6[5] = H[2][2];
+        }
+    }
+    return dist;
+}
+
+// ---- config predicates ----
+HD inline bool xf_all_fixed(const Cfg& c) { return c.xf_fixed[0] && c.xf_fixed[1] && c.xf_fixed[2]; }
+HD inline bool has_quadratic(const Cfg& c) { return c.objective == MPCB200_OBJ_QUADRATIC_FORM; }
+HD inline bool has_mintime(const Cfg& c)
+{
+    return c.objective == MPCB200_OBJ_MINIMUM_TIME || c.objective == MPCB200_OBJ_MINIMUM_TIME_VIA_POINTS;
+}
+HD inline bool has_viapoints(const Cfg& c)
+{
+    return c.objective == MPCB200_OBJ_MINIMUM_TIME_VIA_POINTS ||
+           (c.objective == MPCB200_OBJ_QUADRATIC_FORM && c.vp_attraction_with_quadratic);
+}
+HD inline bool has_terminal_cost(const Cfg& c) { return c.terminal_cost && !xf_all_fixed(c); }
+
+// ---- linear inequality rows (slots 0..7; see DESIGN.md "row slots") ----
+// slot < 4, k <= N-2: control bounds; k == N-1: dt bounds.  slot 4..7: control-rate rows of stage k.
+HD inline bool lin_row_active(const Cfg& c, int N, int k, int slot, double uprev_dt)
+{
+    if (slot < 4)
+    {
+        if (k <= N - 2)
+        {
+            int i = slot >> 1;
+            return (slot & 1) ? (c.u_ub[i] < MPCB200_INF) : (c.u_lb[i] > -MPCB200_INF);
+        }
+        if (!c.variable_dt) return false;
+        if (slot == 0) return c.dt_lb > -MPCB200_INF;
+        if (slot == 1) return c.dt_ub < MPCB200_INF;
+        return false;
+    }
+    int i = (slot - 4) >> 1, ub = (slot - 4) & 1;
+    if (k == 0 && uprev_dt == 0.0) return false;
+    return ub ? (c.du_ub[i] < MPCB200_INF) : (c.du_lb[i] > -MPCB200_INF);
+}
+
+// value of a linear row; gradient entries wrt u_k[i] (gu), u_{k-1}[i] (gum) and dt (gdt), i = component of the row.
+// uk / um: the two control values of component i (um = u_prev for k = 0; uk = u_ref = 0 for k = N-1)
+HD inline double lin_row(const Cfg& c, int N, int k, int slot, double uk, double um, double dt, double uprev_dt,
+                                          double& gu, double& gum, double& gdt)
+{
+    gu = gum = gdt = 0.0;
+    if (slot < 4)
+    {
+        if (k <= N - 2)
+        {
+            int i = slot >> 1;
+            if (slot & 1) { gu = 1.0; return uk - c.u_ub[i]; }
+            gu = -1.0;
+            return c.u_lb[i] - uk;
+        }
+        if (slot == 0) { gdt = -1.0; return c.dt_lb - dt; }
+        gdt = 1.0;
+        return dt - c.dt_ub;
+    }
+    int i = (slot - 4) >> 1, ub = (slot - 4) & 1;
+    double T = (k >= 1) ? dt : uprev_dt;
+    double sgn = ub ? 1.0 : -1.0;
+    double bnd = ub ? c.du_ub[i] : c.du_lb[i];
+    if (k <= N - 2) gu = sgn;
+    if (k >= 1) gum = -sgn;
+    if (k >= 1 && c.variable_dt) gdt = -sgn * bnd;
+    return sgn * ((uk - um) - bnd * T);
+}
+
+HD inline int hidx(int i, int j) { return i * 5 - (i * (i - 1)) / 2 + (j - i); }
+
+HD inline double scaled_error(double dual_inf, double prim_inf, double sl_max, double sl_min, double sum_nu,
+                                               double sum_lam, int m_eq, int m_ineq, double mu)
+{
+    double sd = (sum_nu + sum_lam) / (double)(m_eq + m_ineq > 0 ? m_eq + m_ineq : 1);
+    sd = (sd > SMAX ? sd : SMAX) / SMAX;
+    double sc = m_ineq > 0 ? sum_lam / (double)m_ineq : 0.0;
+    sc = (sc > SMAX ? sc : SMAX) / SMAX;
+    double compl_ = 0.0;
+    if (m_ineq > 0)
+    {
+        double a = sl_max - mu, b = mu - sl_min;
+        compl_ = a > b ? a : b;
+        if (compl_ < 0) compl_ = 0;
+    }
+    double e = dual_inf / sd;
+    if (prim_inf > e) e = prim_inf;
+    if (compl_ / sc > e) e = compl_ / sc;
+    return e;
+}

@@ -1,0 +1,800 @@
+// mpc_stage.h -- per-stage (= per-lane) bodies of the solver phases.  One warp owns one OCP instance; lane l handles
+// the stages k = l, l+32, ...  Each function below is the work of ONE stage; the kernels in mpcb200.cu (and the CPU
+// warp emulator in tests/emu, test infrastructure) loop over a lane's stages and combine the accumulators with warp
+// reductions.  All functions are host/device.
+//
+// Reference structure restated here:
+//   which term attaches to which stage      R/src/optimal_control/finite_differences_grid_se2.cpp:36-152
+//   quadratic costs                         R/src/optimal_control/quadratic_cost_se2.cpp:31-52, final_state_conditions_se2.cpp:31-52
+//   via-point cost                          R/src/optimal_control/min_time_via_points_cost.cpp:120-145
+//   obstacle / control-rate rows            R/src/optimal_control/stage_inequality_se2.cpp:164-222
+//   obstacle association                    R/src/optimal_control/stage_inequality_se2.cpp:50-162
+//   cold init / warm start                  R/src/optimal_control/full_discretization_grid_base_se2.cpp:192-339
+#pragma once
+#include "mpc_core.h"
+
+#define AX(c_, k_) W[L.oX + (c_) * N + (k_)]
+#define AU(c_, k_) W[L.oU + (c_) * N + (k_)]
+#define ANU(c_, k_) W[L.oNU + (c_) * N + (k_)]
+#define AS(c_, k_) W[L.oS + (c_) * N + (k_)]
+#define ALAM(c_, k_) W[L.oLAM + (c_) * N + (k_)]
+#define AKKT(c_, k_) W[L.oKKT + (c_) * N + (k_)]
+#define ASTEP(c_, k_) W[L.oSTEP + (c_) * N + (k_)]
+#define AOBS(c_, k_) W[L.oOBS + (c_) * N + (k_)]
+#define ADS(c_, k_) W[L.oDS + (c_) * N + (k_)]
+#define ADLAM(c_, k_) W[L.oDLAM + (c_) * N + (k_)]
+#define ASC(i_) W[L.oSCAL + (i_)]
+#define AIN(i_) W[L.oIN + (i_)]
+
+// ------------------------------------------------------------------------------------------------------
+// EVAL
+// ------------------------------------------------------------------------------------------------------
+struct EvalAcc
+{
+    double dual_inf, prim_inf, sl_max, sl_min;        // max / max / max / min
+    double sum_nu, sum_lam, inf1, blog, gt0, gt1, gldt, htt, obj;  // sums
+    double m_ineq, m_eq;                               // counts (as double so that one reduction routine serves all)
+};
+HD inline void evalacc_init(EvalAcc& a)
+{
+    a.dual_inf = 0; a.prim_inf = 0; a.sl_max = -1e300; a.sl_min = 1e300;
+    a.sum_nu = a.sum_lam = a.inf1 = a.blog = a.gt0 = a.gt1 = a.gldt = a.htt = a.obj = 0.0;
+    a.m_ineq = a.m_eq = 0.0;
+}
+HD inline void evalacc_merge(EvalAcc& a, const EvalAcc& b)
+{
+    a.dual_inf = fmax(a.dual_inf, b.dual_inf); a.prim_inf = fmax(a.prim_inf, b.prim_inf);
+    a.sl_max = fmax(a.sl_max, b.sl_max); a.sl_min = fmin(a.sl_min, b.sl_min);
+    a.sum_nu += b.sum_nu; a.sum_lam += b.sum_lam; a.inf1 += b.inf1; a.blog += b.blog; a.gt0 += b.gt0; a.gt1 += b.gt1;
+    a.gldt += b.gldt; a.htt += b.htt; a.obj += b.obj; a.m_ineq += b.m_ineq; a.m_eq += b.m_eq;
+}
+
+// bookkeeping of one inequality row (owner side): errors + barrier terms
+HD inline void row_stats(EvalAcc& acc, double r, double s, double lam)
+{
+    acc.prim_inf = fmax(acc.prim_inf, fabs(r));
+    acc.inf1 += fabs(r);
+    acc.sl_max = fmax(acc.sl_max, s * lam);
+    acc.sl_min = fmin(acc.sl_min, s * lam);
+    acc.sum_lam += fabs(lam);
+    acc.blog += log(s);
+    acc.m_ineq += 1.0;
+}
+
+// Stage functions + derivatives of stage k -> condensed KKT record (G holds the mu-independent part g0, the
+// coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
+HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int k, EvalAcc& acc)
+{
+    const int N = L.N, K = L.K;
+    const double dt = ASC(MPCB200_SC_DT);
+    double H[15], g0[5], g1[5], GL[5], a3[3], Bm[6], e[3], Cc[2], hb[5], dvec[3];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) H[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { g0[i] = 0; g1[i] = 0; GL[i] = 0; hb[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a3[i] = 0; e[i] = 0; dvec[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Bm[i] = 0;
+    Cc[0] = Cc[1] = 0.0;
+    const double x[3] = {AX(0, k), AX(1, k), AX(2, k)};
+    const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
+
+    if (k <= N - 2)
+    {
+        const double u[2] = {AU(0, k), AU(1, k)};
+        const double nu[3] = {ANU(0, k), ANU(1, k), ANU(2, k)};
+        double f[3], J[9], Hc[6];
+        dynamics_derivs(c, x[2], u[0], u[1], nu, f, J, Hc);
+        e[0] = x[0] + dt * f[0] - AX(0, k + 1);
+        e[1] = x[1] + dt * f[1] - AX(1, k + 1);
+        e[2] = dt * f[2] - normalize_theta(AX(2, k + 1) - x[2]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+            dvec[i] = f[i];
+            a3[i] = dt * J[i * 3 + 0];
+            Bm[2 * i] = dt * J[i * 3 + 1];
+            Bm[2 * i + 1] = dt * J[i * 3 + 2];
+            acc.prim_inf = fmax(acc.prim_inf, fabs(e[i]));
+            acc.inf1 += fabs(e[i]);
+            acc.sum_nu += fabs(nu[i]);
+        }
+        acc.m_eq += 3.0;
+        // quadratic running cost (k = 0 state term is a constant: its gradient is never used since x_0 is fixed)
+        if (has_quadratic(c))
+        {
+            double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double o = 0.0;
+            for (int i = 0; i < 3; ++i)
+            {
+                double gi = 0.0;
+                for (int j = 0; j < 3; ++j)
+                {
+                    gi += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j];
+                    o += d[i] * c.Q[i * 3 + j] * d[j];
+                    if (j >= i) H[hidx(i, j)] += c.Q[i * 3 + j] + c.Q[j * 3 + i];
+                }
+                g0[i] += gi; GL[i] += gi;
+            }
+            for (int i = 0; i < 2; ++i)
+            {
+                double gi = 0.0;
+                for (int j = 0; j < 2; ++j)
+                {
+                    gi += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j];
+                    o += u[i] * c.R[i * 2 + j] * u[j];
+                    if (j >= i) H[hidx(3 + i, 3 + j)] += c.R[i * 2 + j] + c.R[j * 2 + i];
+                }
+                g0[3 + i] += gi; GL[3 + i] += gi;
+            }
+            acc.obj += o;
+        }
+        // Lagrangian terms of nu_k^T e_k
+        const double fx_nu = nu[0] * J[0] + nu[1] * J[3] + nu[2] * J[6];
+        const double fu_nu0 = nu[0] * J[1] + nu[1] * J[4] + nu[2] * J[7];
+        const double fu_nu1 = nu[0] * J[2] + nu[1] * J[5] + nu[2] * J[8];
+        GL[0] += nu[0]; GL[1] += nu[1]; GL[2] += nu[2] + dt * fx_nu;
+        GL[3] += dt * fu_nu0; GL[4] += dt * fu_nu1;
+        acc.gldt += nu[0] * f[0] + nu[1] * f[1] + nu[2] * f[2];
+        H[hidx(2, 2)] += dt * Hc[0]; H[hidx(2, 3)] += dt * Hc[1]; H[hidx(2, 4)] += dt * Hc[2];
+        H[hidx(3, 3)] += dt * Hc[3]; H[hidx(3, 4)] += dt * Hc[4]; H[hidx(4, 4)] += dt * Hc[5];
+        if (c.variable_dt) { hb[2] += fx_nu; hb[3] += fu_nu0; hb[4] += fu_nu1; }
+        // ---- linear rows owned by stage k (bounds 0..3, rate rows 4..7) and the rate rows of stage k+1 (gather) ----
+        for (int pass = 0; pass < 2; ++pass)
+        {
+            const int kk = k + pass;           // owner stage of the rows
+            const int s0 = pass == 0 ? 0 : 4;  // next stage: rate rows only
+            for (int sl = s0; sl < 8; ++sl)
+            {
+                if (!lin_row_active(c, N, kk, sl, uprev_dt)) continue;
+                if (pass == 1 && kk > N - 1) continue;
+                const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
+                double uk, um;
+                if (pass == 0) { uk = u[i]; um = (k >= 1) ? AU(i, k - 1) : AIN(IN_UPREV + i); }
+                else { uk = (kk <= N - 2) ? AU(i, kk) : 0.0; um = u[i]; }
+                double gu, gum, gdt;
+                const double g = lin_row(c, N, kk, sl, uk, um, dt, uprev_dt, gu, gum, gdt);
+                const double s = AS(sl, kk), lam = ALAM(sl, kk);
+                const double r = g + s, sig = lam / s, c0 = sig * r, c1 = 1.0 / s;
+                const double gmine = (pass == 0) ? gu : gum;  // gradient entry on u_k[i]
+                if (gmine != 0.0)
+                {
+                    g0[3 + i] += c0 * gmine; g1[3 + i] += c1 * gmine; GL[3 + i] += lam * gmine;
+                    H[hidx(3 + i, 3 + i)] += sig * gmine * gmine;
+                    if (gdt != 0.0) hb[3 + i] += sig * gmine * gdt;
+                    if (pass == 0 && gum != 0.0) Cc[i] += sig * gu * gum;
+                }
+                if (pass == 0)
+                {
+                    row_stats(acc, r, s, lam);
+                    if (gdt != 0.0) { acc.gt0 += c0 * gdt; acc.gt1 += c1 * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt; }
+                }
+            }
+        }
+    }
+    else
+    {
+        // terminal stage k = N-1: terminal cost, dt-bound rows (slots 0,1), final control-rate rows (slots 4..7; their
+        // contribution to u_{N-2} is gathered by stage N-2 above), minimum-time term
+        if (has_terminal_cost(c))
+        {
+            double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double o = 0.0;
+            for (int i = 0; i < 3; ++i)
+            {
+                double gi = 0.0;
+                for (int j = 0; j < 3; ++j)
+                {
+                    gi += (c.Qf[i * 3 + j] + c.Qf[j * 3 + i]) * d[j];
+                    o += d[i] * c.Qf[i * 3 + j] * d[j];
+                    if (j >= i) H[hidx(i, j)] += c.Qf[i * 3 + j] + c.Qf[j * 3 + i];
+                }
+                g0[i] += gi; GL[i] += gi;
+            }
+            acc.obj += o;
+        }
+        if (has_mintime(c)) { acc.gt0 += (double)(N - 1); acc.gldt += (double)(N - 1); acc.obj += (double)(N - 1) * dt; }
+        for (int sl = 0; sl < 8; ++sl)
+        {
+            if (!lin_row_active(c, N, k, sl, uprev_dt)) continue;
+            const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
+            double gu, gum, gdt;
+            const double um = (sl >= 4) ? AU(i, k - 1) : 0.0;
+            const double g = lin_row(c, N, k, sl, 0.0, um, dt, uprev_dt, gu, gum, gdt);
+            const double s = AS(sl, k), lam = ALAM(sl, k);
+            const double r = g + s, sig = lam / s, c0 = sig * r, c1 = 1.0 / s;
+            row_stats(acc, r, s, lam);
+            if (gdt != 0.0) { acc.gt0 += c0 * gdt; acc.gt1 += c1 * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt; }
+        }
+    }
+    // multiplier of the previous defect: d/dx_k ( nu_{k-1}^T e_{k-1} ) = -nu_{k-1}
+    if (k >= 1) { GL[0] -= ANU(0, k - 1); GL[1] -= ANU(1, k - 1); GL[2] -= ANU(2, k - 1); }
+    // via-points attached to this stage
+    if (has_viapoints(c) && k >= 1 && k <= N - 2)
+    {
+        const int nvp = (int)AIN(IN_NVP);
+        for (int j = 0; j < nvp && j < L.V; ++j)
+        {
+            if ((int)W[L.oVPST + j] != k) continue;
+            const double w = c.vp_position_weight;
+            const double ex = W[L.oVP + 3 * j] - x[0], ey = W[L.oVP + 3 * j + 1] - x[1];
+            g0[0] += -2 * w * ex; GL[0] += -2 * w * ex;
+            g0[1] += -2 * w * ey; GL[1] += -2 * w * ey;
+            H[hidx(0, 0)] += 2 * w; H[hidx(1, 1)] += 2 * w;
+            acc.obj += w * (ex * ex + ey * ey);
+            if (c.vp_orientation_weight > 0)
+            {
+                g0[2] += -c.vp_orientation_weight; GL[2] += -c.vp_orientation_weight;
+                acc.obj += c.vp_orientation_weight * normalize_theta(W[L.oVP + 3 * j + 2] - x[2]);
+            }
+        }
+    }
+    // obstacle rows (k = 1..N-2)
+    if (k >= 1 && k <= N - 2)
+    {
+        for (int j = 0; j < K; ++j)
+        {
+            const int oi = (int)AOBS(j, k);
+            if (oi < 0) continue;
+            double gd[3], hd[6];
+            const double dist = footprint_distance<true, true>(c, x[0], x[1], x[2], (int)W[L.oOTYPE + oi],
+                                                               W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, hd);
+            const double g = c.min_obstacle_dist - dist;
+            const double s = AS(8 + j, k), lam = ALAM(8 + j, k);
+            const double r = g + s, sig = lam / s, c0 = sig * r, c1 = 1.0 / s;
+            row_stats(acc, r, s, lam);
+            double gr[3] = {-gd[0], -gd[1], -gd[2]};
+            int q = 0;
+            for (int i = 0; i < 3; ++i)
+            {
+                g0[i] += c0 * gr[i]; g1[i] += c1 * gr[i]; GL[i] += lam * gr[i];
+                for (int jj = i; jj < 3; ++jj, ++q) H[hidx(i, jj)] += lam * (-hd[q]) + sig * gr[i] * gr[jj];
+            }
+        }
+    }
+    // dual infeasibility over the free variables of this stage
+    for (int i = 0; i < 5; ++i)
+    {
+        if (i < 3 && k == 0) continue;
+        if (i < 3 && k == N - 1 && c.xf_fixed[i]) continue;
+        if (i >= 3 && k == N - 1) continue;
+        acc.dual_inf = fmax(acc.dual_inf, fabs(GL[i]));
+    }
+    // store the record
+#pragma unroll
+    for (int i = 0; i < 15; ++i) AKKT(MPCB200_K_H + i, k) = H[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { AKKT(MPCB200_K_G + i, k) = g0[i]; ASTEP(i, k) = g1[i]; AKKT(MPCB200_K_HB + i, k) = hb[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { AKKT(MPCB200_K_A + i, k) = a3[i]; AKKT(MPCB200_K_E + i, k) = e[i]; AKKT(MPCB200_K_D + i, k) = dvec[i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) AKKT(MPCB200_K_B + i, k) = Bm[i];
+    AKKT(MPCB200_K_C + 0, k) = Cc[0];
+    AKKT(MPCB200_K_C + 1, k) = Cc[1];
+}
+
+// After the warp reduction: convergence test, monotone barrier update (Ipopt's Fiacco-McCormick rule), scalars.
+// Returns the barrier parameter to finalise the gradients with; *finished is set when the instance terminates.
+HD inline double eval_finish(const Cfg& c, const WsLayout& L, double* W, const EvalAcc& a, bool write, int* finished)
+{
+    double mu = ASC(MPCB200_SC_MU);
+    const double tol = c.tol, mu_min = tol / 10.0;
+    const int m_eq = (int)a.m_eq, m_in = (int)a.m_ineq;
+    double dual_inf = a.dual_inf;
+    if (c.variable_dt) dual_inf = fmax(dual_inf, fabs(a.gldt));
+    const double e0 = scaled_error(dual_inf, a.prim_inf, a.sl_max, a.sl_min, a.sum_nu, a.sum_lam, m_eq, m_in, 0.0);
+    double emu = scaled_error(dual_inf, a.prim_inf, a.sl_max, a.sl_min, a.sum_nu, a.sum_lam, m_eq, m_in, mu);
+    const int iter = (int)ASC(MPCB200_SC_ITER);
+    int fin = 0, status = -1;
+    if (e0 <= tol) { fin = 1; status = MPCB200_STATUS_CONVERGED; }
+    else if (iter >= c.max_iter) { fin = 1; status = MPCB200_STATUS_MAX_ITER; }
+    if (!(e0 == e0)) { fin = 1; status = MPCB200_STATUS_NUMERICAL_ERROR; }
+    if (!fin)
+    {
+        while (emu <= KAPPA_EPS * mu && mu > mu_min)
+        {
+            double m1 = KAPPA_MU * mu, m2 = pow(mu, THETA_MU);
+            mu = m1 < m2 ? m1 : m2;
+            if (mu < mu_min) mu = mu_min;
+            emu = scaled_error(dual_inf, a.prim_inf, a.sl_max, a.sl_min, a.sum_nu, a.sum_lam, m_eq, m_in, mu);
+        }
+    }
+    if (write)
+    {
+        ASC(MPCB200_SC_MU) = mu;
+        ASC(MPCB200_SC_ERR0) = e0;
+        ASC(MPCB200_SC_ERRMU) = emu;
+        ASC(MPCB200_SC_HTT) = a.htt;
+        ASC(MPCB200_SC_GT) = a.gt0 + mu * a.gt1;
+        ASC(MPCB200_SC_GLDT) = a.gldt;
+        ASC(MPCB200_SC_OBJ) = a.obj;
+        ASC(MPCB200_SC_INF) = a.inf1;
+        ASC(MPCB200_SC_BLOG) = a.blog;
+        if (fin) ASC(MPCB200_SC_STATUS) = (double)status;
+    }
+    *finished = fin;
+    return mu;
+}
+HD inline void eval_finalize_stage(const WsLayout& L, double* W, int k, double mu)
+{
+    const int N = L.N;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) AKKT(MPCB200_K_G + i, k) += mu * ASTEP(i, k);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// LINE SEARCH
+// ------------------------------------------------------------------------------------------------------
+struct LsAcc
+{
+    double a_p, a_d;                 // min
+    double dphi_bar, curv, dJ;       // sums
+};
+HD inline void lsacc_init(LsAcc& a) { a.a_p = 1.0; a.a_d = 1.0; a.dphi_bar = a.curv = a.dJ = 0.0; }
+
+// slack / multiplier steps of the rows owned by stage k, fraction to the boundary, directional derivatives
+HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int k, LsAcc& acc)
+{
+    const int N = L.N, K = L.K;
+    const double dt = ASC(MPCB200_SC_DT), mu = ASC(MPCB200_SC_MU), ddt = ASC(MPCB200_SC_DDT);
+    const double delta = ASC(MPCB200_SC_DELTA);
+    const double tau = (1.0 - mu > TAU_MIN) ? 1.0 - mu : TAU_MIN;
+    const double x[3] = {AX(0, k), AX(1, k), AX(2, k)};
+    const double dx[3] = {ASTEP(0, k), ASTEP(1, k), ASTEP(2, k)};
+    const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
+    double du[2] = {0, 0};
+    if (k <= N - 2) { du[0] = ASTEP(3, k); du[1] = ASTEP(4, k); }
+    // rows
+    for (int sl = 0; sl < 8 + K; ++sl)
+    {
+        double g, gdz;
+        if (sl < 8)
+        {
+            if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; continue; }
+            const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
+            const double uk = (k <= N - 2) ? AU(i, k) : 0.0;
+            const double um = (sl >= 4) ? ((k >= 1) ? AU(i, k - 1) : AIN(IN_UPREV + i)) : 0.0;
+            double gu, gum, gdt;
+            g = lin_row(c, N, k, sl, uk, um, dt, uprev_dt, gu, gum, gdt);
+            gdz = gu * du[i] + gdt * ddt;
+            if (gum != 0.0) gdz += gum * ASTEP(3 + i, k - 1);
+        }
+        else
+        {
+            const int j = sl - 8;
+            const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(j, k) : -1;
+            if (oi < 0) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; continue; }
+            double gd[3];
+            const double dist = footprint_distance<true, false>(c, x[0], x[1], x[2], (int)W[L.oOTYPE + oi],
+                                                                W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, nullptr);
+            g = c.min_obstacle_dist - dist;
+            gdz = -(gd[0] * dx[0] + gd[1] * dx[1] + gd[2] * dx[2]);
+        }
+        const double s = AS(sl, k), lam = ALAM(sl, k);
+        const double ds = -(g + s) - gdz;
+        const double dl = mu / s - lam - (lam / s) * ds;
+        ADS(sl, k) = ds;
+        ADLAM(sl, k) = dl;
+        if (ds < 0) acc.a_p = fmin(acc.a_p, -tau * s / ds);
+        if (dl < 0) acc.a_d = fmin(acc.a_d, -tau * lam / dl);
+        acc.dphi_bar += -mu * ds / s;
+        acc.curv += (lam / s) * ds * ds;
+    }
+    // directional derivative of the objective
+    double dJ = 0.0;
+    if (k <= N - 2)
+    {
+        if (has_quadratic(c))
+        {
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            const double u[2] = {AU(0, k), AU(1, k)};
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) dJ += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j] * dx[i];
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j) dJ += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j] * du[i];
+        }
+    }
+    else
+    {
+        if (has_mintime(c)) dJ += (double)(N - 1) * ddt;
+        if (has_terminal_cost(c))
+        {
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) dJ += (c.Qf[i * 3 + j] + c.Qf[j * 3 + i]) * d[j] * dx[i];
+        }
+    }
+    if (has_viapoints(c) && k >= 1 && k <= N - 2)
+    {
+        const int nvp = (int)AIN(IN_NVP);
+        for (int j = 0; j < nvp && j < L.V; ++j)
+        {
+            if ((int)W[L.oVPST + j] != k) continue;
+            const double w = c.vp_position_weight;
+            dJ += -2 * w * (W[L.oVP + 3 * j] - x[0]) * dx[0];
+            dJ += -2 * w * (W[L.oVP + 3 * j + 1] - x[1]) * dx[1];
+            if (c.vp_orientation_weight > 0) dJ += -c.vp_orientation_weight * dx[2];
+        }
+    }
+    acc.dJ += dJ;
+    // curvature dz' H dz of this stage's block (+ cross block with stage k-1, + border)
+    {
+        const int nv = (k <= N - 2) ? 5 : 3;
+        double st[5] = {dx[0], dx[1], dx[2], du[0], du[1]};
+        double cv = 0.0;
+        for (int i = 0; i < nv; ++i)
+            for (int j = 0; j < nv; ++j)
+            {
+                const int a = i < j ? i : j, b = i < j ? j : i;
+                cv += st[i] * (AKKT(MPCB200_K_H + hidx(a, b), k) + (a == b ? delta : 0.0)) * st[j];
+            }
+        if (k >= 1 && k <= N - 2)
+            for (int i = 0; i < 2; ++i) cv += 2.0 * ASTEP(3 + i, k - 1) * AKKT(MPCB200_K_C + i, k) * du[i];
+        if (c.variable_dt && k <= N - 2)
+            for (int i = 0; i < 5; ++i) cv += 2.0 * ddt * AKKT(MPCB200_K_HB + i, k) * st[i];
+        if (c.variable_dt && k == N - 1) cv += ddt * ddt * (ASC(MPCB200_SC_HTT) + delta);
+        acc.curv += cv;
+    }
+}
+
+struct TrialAcc { double obj, inf1, blog; };
+// merit pieces of stage k at the trial point z + alpha dz, s + alpha ds
+HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, double uprev_dt, int k, double alpha, TrialAcc& acc)
+{
+    const int N = L.N, K = L.K;
+    const double dtt = ASC(MPCB200_SC_DT) + (c.variable_dt ? alpha * ASC(MPCB200_SC_DDT) : 0.0);
+    const double x[3] = {AX(0, k) + alpha * ASTEP(0, k), AX(1, k) + alpha * ASTEP(1, k), AX(2, k) + alpha * ASTEP(2, k)};
+    const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
+    double u[2] = {0, 0};
+    if (k <= N - 2)
+    {
+        u[0] = AU(0, k) + alpha * ASTEP(3, k);
+        u[1] = AU(1, k) + alpha * ASTEP(4, k);
+        double f[3];
+        dynamics_value(c, x[2], u[0], u[1], f);
+        const double xn[3] = {AX(0, k + 1) + alpha * ASTEP(0, k + 1), AX(1, k + 1) + alpha * ASTEP(1, k + 1),
+                              AX(2, k + 1) + alpha * ASTEP(2, k + 1)};
+        acc.inf1 += fabs(x[0] + dtt * f[0] - xn[0]) + fabs(x[1] + dtt * f[1] - xn[1]) +
+                    fabs(dtt * f[2] - normalize_theta(xn[2] - x[2]));
+        if (has_quadratic(c))
+        {
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double o = 0.0;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) o += d[i] * c.Q[i * 3 + j] * d[j];
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j) o += u[i] * c.R[i * 2 + j] * u[j];
+            acc.obj += o;
+        }
+    }
+    else
+    {
+        if (has_mintime(c)) acc.obj += (double)(N - 1) * dtt;
+        if (has_terminal_cost(c))
+        {
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double o = 0.0;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) o += d[i] * c.Qf[i * 3 + j] * d[j];
+            acc.obj += o;
+        }
+    }
+    if (has_viapoints(c) && k >= 1 && k <= N - 2)
+    {
+        const int nvp = (int)AIN(IN_NVP);
+        for (int j = 0; j < nvp && j < L.V; ++j)
+        {
+            if ((int)W[L.oVPST + j] != k) continue;
+            const double ex = W[L.oVP + 3 * j] - x[0], ey = W[L.oVP + 3 * j + 1] - x[1];
+            acc.obj += c.vp_position_weight * (ex * ex + ey * ey);
+            if (c.vp_orientation_weight > 0)
+                acc.obj += c.vp_orientation_weight * normalize_theta(W[L.oVP + 3 * j + 2] - x[2]);
+        }
+    }
+    for (int sl = 0; sl < 8 + K; ++sl)
+    {
+        double g;
+        if (sl < 8)
+        {
+            if (!lin_row_active(c, N, k, sl, uprev_dt)) continue;
+            const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
+            const double uk = (k <= N - 2) ? u[i] : 0.0;
+            const double um = (sl >= 4) ? ((k >= 1) ? AU(i, k - 1) + alpha * ASTEP(3 + i, k - 1) : AIN(IN_UPREV + i)) : 0.0;
+            double gu, gum, gdt;
+            g = lin_row(c, N, k, sl, uk, um, dtt, uprev_dt, gu, gum, gdt);
+        }
+        else
+        {
+            const int j = sl - 8;
+            const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(j, k) : -1;
+            if (oi < 0) continue;
+            const double dist = footprint_distance<false, false>(c, x[0], x[1], x[2], (int)W[L.oOTYPE + oi],
+                                                                 W + L.oOBST + oi * MPCB200_OBST_STRIDE, nullptr, nullptr);
+            g = c.min_obstacle_dist - dist;
+        }
+        const double s = AS(sl, k) + alpha * ADS(sl, k);
+        acc.inf1 += fabs(g + s);
+        acc.blog += log(s);
+    }
+}
+
+// accept the step: z, s, lambda, nu of stage k
+HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int k, double alpha, double a_dual)
+{
+    const int N = L.N, K = L.K;
+    const double mu = ASC(MPCB200_SC_MU);
+    // NOTE: reads STEP of stage k only -> safe to run lane-parallel after all trial evaluations are done
+    const double d0 = ASTEP(0, k), d1 = ASTEP(1, k), d2 = ASTEP(2, k);
+    AX(0, k) += alpha * d0; AX(1, k) += alpha * d1; AX(2, k) += alpha * d2;
+    if (k <= N - 2)
+    {
+        AU(0, k) += alpha * ASTEP(3, k);
+        AU(1, k) += alpha * ASTEP(4, k);
+        for (int i = 0; i < 3; ++i) ANU(i, k) += alpha * (ASTEP(5 + i, k) - ANU(i, k));
+    }
+    for (int sl = 0; sl < 8 + K; ++sl)
+    {
+        bool act;
+        if (sl < 8) act = lin_row_active(c, N, k, sl, uprev_dt);
+        else act = (k >= 1 && k <= N - 2) && AOBS(sl - 8, k) >= 0.0;
+        if (!act) continue;
+        double s = AS(sl, k) + alpha * ADS(sl, k);
+        double lam = ALAM(sl, k) + a_dual * ADLAM(sl, k);
+        const double lo = mu / (KAPPA_SIGMA * s), hi = KAPPA_SIGMA * mu / s;
+        if (lam < lo) lam = lo;
+        if (lam > hi) lam = hi;
+        AS(sl, k) = s;
+        ALAM(sl, k) = lam;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// INITIALISATION / ASSOCIATION
+// ------------------------------------------------------------------------------------------------------
+// cold initial guess of stage k
+HD inline void init_cold_stage(const Cfg& c, const WsLayout& L, double* W, int k)
+{
+    const int N = L.N;
+    const double* x0 = &AIN(IN_X0);
+    const double* xf = &AIN(IN_XF);
+    if (k == 0) { for (int i = 0; i < 3; ++i) AX(i, k) = x0[i]; }
+    else if (k == N - 1) { for (int i = 0; i < 3; ++i) AX(i, k) = xf[i]; }
+    else if (AIN(IN_HASXINIT) != 0.0) { for (int i = 0; i < 3; ++i) AX(i, k) = W[L.oXINIT + 3 * k + i]; }
+    else
+    {
+        const double frac = (double)k / (double)(N - 1);
+        AX(0, k) = x0[0] + frac * (xf[0] - x0[0]);
+        AX(1, k) = x0[1] + frac * (xf[1] - x0[1]);
+        AX(2, k) = interpolate_angle(x0[2], xf[2], frac);
+    }
+    AU(0, k) = 0.0;
+    AU(1, k) = 0.0;
+}
+
+// warm start shift (serial; run by one lane): FullDiscretizationGridBaseSE2::warmStartShifting + findNearestState
+HD inline void warm_shift_serial(const Cfg& c, const WsLayout& L, double* W)
+{
+    const int N = L.N;
+    const double* x0 = &AIN(IN_X0);
+    const double* xf = &AIN(IN_XF);
+    int num_shift = 0;
+    {
+        double d0 = 0;
+        for (int i = 0; i < 3; ++i) { double e = x0[i] - AX(i, 0); d0 += e * e; }
+        d0 = sqrt(d0);
+        if (fabs(d0) >= 1e-12)
+        {
+            const int num_interv = N - 1, lookahead = num_interv - 1 < 20 ? num_interv - 1 : 20;
+            double cache = d0;
+            for (int i = 1; i <= lookahead; ++i)
+            {
+                double d = 0;
+                for (int j = 0; j < 3; ++j) { double e = x0[j] - AX(j, i); d += e * e; }
+                d = sqrt(d);
+                if (d < cache) { cache = d; num_shift = i; }
+                else break;
+            }
+        }
+    }
+    if (num_shift > 0 && num_shift <= N - 2)
+    {
+        for (int i = 0; i < N - num_shift; ++i)
+        {
+            const int idx = i + num_shift;
+            for (int j = 0; j < 3; ++j) AX(j, i) = AX(j, idx);
+            if (idx != N - 1)
+                for (int j = 0; j < 2; ++j) AU(j, i) = AU(j, idx);
+        }
+        int idx = N - num_shift;
+        for (int i = 0; i < num_shift; ++i, ++idx)
+        {
+            for (int j = 0; j < 2; ++j) AX(j, idx) = AX(j, idx - 2) + 2.0 * (AX(j, idx - 1) - AX(j, idx - 2));
+            AX(2, idx) = interpolate_angle(AX(2, idx - 2), AX(2, idx - 1), 2.0);
+            for (int j = 0; j < 2; ++j) AU(j, idx - 1) = AU(j, idx - 2);
+        }
+    }
+    for (int i = 0; i < 3; ++i) AX(i, 0) = x0[i];
+    for (int i = 0; i < 3; ++i)
+        if (c.xf_fixed[i]) AX(i, N - 1) = xf[i];
+}
+
+// obstacle association of stage k
+HD inline void associate_stage(const Cfg& c, const WsLayout& L, double* W, int k)
+{
+    const int N = L.N, K = L.K;
+    for (int j = 0; j < K; ++j) AOBS(j, k) = -1.0;
+    if (k < 1 || k > N - 2 || K <= 0) return;
+    const double px = AX(0, k), py = AX(1, k), pth = AX(2, k);
+    const double ox = cos(pth), oy = sin(pth);
+    double left_min = 1e300, right_min = 1e300;
+    int left = -1, right = -1, cnt = 0;
+    double dists[16];
+    const int nobst = (int)AIN(IN_NOBST);
+    const int KK = K < 16 ? K : 16;
+    for (int pass = 0; pass < 3; ++pass)
+    {
+        // pass 0: forced inclusions in obstacle order; pass 1: left; pass 2: right (reference order)
+        const int jb = pass == 0 ? 0 : (pass == 1 ? left : right);
+        const int je = pass == 0 ? nobst : jb + 1;
+        if (pass > 0 && jb < 0) continue;
+        for (int j = jb; j < je; ++j)
+        {
+            const double* op = W + L.oOBST + j * MPCB200_OBST_STRIDE;
+            double dist;
+            if (pass == 0)
+            {
+                dist = footprint_distance<false, false>(c, px, py, pth, (int)W[L.oOTYPE + j], op, nullptr, nullptr);
+                if (!(dist < c.force_inclusion_dist))
+                {
+                    if (dist > c.cutoff_dist) continue;
+                    if (ox * op[1] - op[0] * oy > 0) { if (dist < left_min) { left_min = dist; left = j; } }
+                    else { if (dist < right_min) { right_min = dist; right = j; } }
+                    continue;
+                }
+            }
+            else dist = pass == 1 ? left_min : right_min;
+            // insert into the K-slot list (append; when full replace the farthest if nearer)
+            if (cnt < KK) { AOBS(cnt, k) = (double)j; dists[cnt] = dist; ++cnt; }
+            else
+            {
+                int far = 0;
+                for (int i = 1; i < KK; ++i)
+                    if (dists[i] > dists[far]) far = i;
+                if (dist < dists[far]) { AOBS(far, k) = (double)j; dists[far] = dist; }
+            }
+        }
+    }
+}
+
+// initial-guess repair of stage k: push the pose out of violated obstacle rows
+HD inline void project_stage(const Cfg& c, const WsLayout& L, double* W, int k)
+{
+    const int N = L.N, K = L.K;
+    if (k < 1 || k > N - 2) return;
+    for (int sweep = 0; sweep < PROJ_SWEEPS; ++sweep)
+    {
+        int moved = 0;
+        for (int j = 0; j < K; ++j)
+        {
+            const int oi = (int)AOBS(j, k);
+            if (oi < 0) continue;
+            double gd[3];
+            const double dist = footprint_distance<true, false>(c, AX(0, k), AX(1, k), AX(2, k), (int)W[L.oOTYPE + oi],
+                                                                W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, nullptr);
+            const double g = c.min_obstacle_dist - dist;
+            if (g <= -PROJ_MARGIN) continue;
+            double gx = -gd[0], gy = -gd[1];
+            double n2 = gx * gx + gy * gy;
+            if (n2 < 1e-16) { gx = 1.0; gy = 0.0; n2 = 1.0; }
+            const double step = (g + PROJ_MARGIN) / n2;
+            AX(0, k) -= step * gx;
+            AX(1, k) -= step * gy;
+            moved = 1;
+        }
+        if (!moved) break;
+    }
+}
+
+// initial controls of stage k by inverting the dynamics along the state guess, clipped inside the bounds
+HD inline void init_controls_stage(const Cfg& c, const WsLayout& L, double* W, int k)
+{
+    const int N = L.N;
+    if (k > N - 2) return;
+    const double dt = ASC(MPCB200_SC_DT);
+    const double th = AX(2, k);
+    const double dx = AX(0, k + 1) - AX(0, k), dy = AX(1, k + 1) - AX(1, k);
+    const double dth = normalize_theta(AX(2, k + 1) - th);
+    const double v = (dx * cos(th) + dy * sin(th)) / dt, w = dth / dt;
+    double u1 = 0.0;
+    switch (c.robot_type)
+    {
+        case MPCB200_ROBOT_UNICYCLE: u1 = w; break;
+        case MPCB200_ROBOT_SIMPLE_CAR: u1 = fabs(v) > 1e-3 ? atan(c.wheelbase * w / v) : 0.0; break;
+        case MPCB200_ROBOT_SIMPLE_CAR_FRONT:
+        {
+            double a = fabs(v) > 1e-3 ? c.wheelbase * w / v : 0.0;
+            u1 = asin(a > 1 ? 1 : (a < -1 ? -1 : a));
+            break;
+        }
+        default:
+        {
+            double a = fabs(v) > 1e-3 ? c.length_rear * w / v : 0.0;
+            double beta = asin(a > 0.99 ? 0.99 : (a < -0.99 ? -0.99 : a));
+            u1 = atan(tan(beta) * (c.length_front + c.length_rear) / c.length_rear);
+        }
+    }
+    double uu[2] = {v, u1};
+    for (int i = 0; i < 2; ++i)
+    {
+        const double l = c.u_lb[i] > -MPCB200_INF ? c.u_lb[i] : -1e6, h = c.u_ub[i] < MPCB200_INF ? c.u_ub[i] : 1e6;
+        const double mid = 0.5 * (l + h), half = 0.5 * (h - l) * INIT_SHRINK;
+        const double lo = mid - half, hi = mid + half;
+        AU(i, k) = uu[i] < lo ? lo : (uu[i] > hi ? hi : uu[i]);
+    }
+}
+// serial clipping of the controls into the control-rate rows (forward from u_prev, backward from u_ref = 0)
+HD inline void clip_rates_serial(const Cfg& c, const WsLayout& L, double* W, double uprev_dt)
+{
+    const int N = L.N;
+    const double dt = ASC(MPCB200_SC_DT);
+    for (int i = 0; i < 2; ++i)
+    {
+        const double dl = c.du_lb[i] > -MPCB200_INF ? c.du_lb[i] * INIT_SHRINK : -1e6;
+        const double dh = c.du_ub[i] < MPCB200_INF ? c.du_ub[i] * INIT_SHRINK : 1e6;
+        double prev = AIN(IN_UPREV + i), T = uprev_dt;
+        for (int k = 0; k <= N - 2; ++k)
+        {
+            if (!(k == 0 && T == 0.0))
+            {
+                const double a = prev + dl * T, b = prev + dh * T, u = AU(i, k);
+                AU(i, k) = u < a ? a : (u > b ? b : u);
+            }
+            prev = AU(i, k);
+            T = dt;
+        }
+        double next = 0.0;
+        for (int k = N - 2; k >= 0; --k)
+        {
+            const double a = next - dh * dt, b = next - dl * dt, u = AU(i, k);
+            AU(i, k) = u < a ? a : (u > b ? b : u);
+            next = AU(i, k);
+        }
+    }
+}
+
+// slack / multiplier initialisation of stage k
+HD inline void init_duals_stage(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int k, double mu)
+{
+    const int N = L.N, K = L.K;
+    const double dt = ASC(MPCB200_SC_DT);
+    for (int sl = 0; sl < 8 + K; ++sl)
+    {
+        double s = 1.0, lam = 0.0, g = 0.0;
+        bool act;
+        if (sl < 8)
+        {
+            act = lin_row_active(c, N, k, sl, uprev_dt);
+            if (act)
+            {
+                const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
+                const double uk = (k <= N - 2) ? AU(i, k) : 0.0;
+                const double um = (sl >= 4) ? ((k >= 1) ? AU(i, k - 1) : AIN(IN_UPREV + i)) : 0.0;
+                double gu, gum, gdt;
+                g = lin_row(c, N, k, sl, uk, um, dt, uprev_dt, gu, gum, gdt);
+            }
+        }
+        else
+        {
+            const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(sl - 8, k) : -1;
+            act = oi >= 0;
+            if (act)
+                g = c.min_obstacle_dist - footprint_distance<false, false>(c, AX(0, k), AX(1, k), AX(2, k), (int)W[L.oOTYPE + oi],
+                                                                           W + L.oOBST + oi * MPCB200_OBST_STRIDE, nullptr, nullptr);
+        }
+        if (act) { s = -g > SLACK_PUSH ? -g : SLACK_PUSH; lam = mu / s; }
+        AS(sl, k) = s;
+        ALAM(sl, k) = lam;
+    }
+    for (int i = 0; i < 3; ++i) ANU(i, k) = 0.0;
+}

@@ -1,0 +1,887 @@
+// mpcb200.cu -- sm_100a kernels + C-ABI host side of the batched receding-horizon OCP solver (include/mpcb200.h).
+//
+// One warp owns one OCP instance.  The instance's working set is one contiguous, 128-byte aligned block in HBM in
+// which every array is laid out [component][stage] (stage fastest): in the stage-parallel phases (EVAL, LINESEARCH,
+// INIT, ASSOCIATE) lane l handles stages l, l+32, ... so that the 32 lanes touch consecutive addresses; in the
+// sequential KKT phase the warp first stages the instance's condensed KKT records through shared memory with
+// coalesced loads and then runs the Riccati sweep out of shared memory (mpc_riccati.h).
+//
+// This file is the ONLY implementation of the hot path: there is no CPU fallback.  Every entry point fails with
+// MPCB200_E_NODEVICE / MPCB200_E_CUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "mpc_core.h"
+#include "mpc_riccati.h"
+#include "mpc_stage.h"
+#include "mpc_layout.h"
+
+#define FULLMASK 0xffffffffu
+#define WARPS_PER_CTA 4
+
+// ---- warp reductions (fp64 via two 32-bit shuffles each) ------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULLMASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, o));
+    return v;
+}
+
+struct InputPtrs
+{
+    const double* x0; const double* xf; const double* u_prev;      // [B][3],[B][3],[B][2]
+    const int* obst_count; const int* obst_type; const double* obst_params; int obst_max;
+    const int* vp_count; const double* vp_poses; int vp_max;
+    const double* x_init;                                          // [B][N][3] or null
+    const unsigned char* reinit;                                   // [B] or null
+};
+
+// ---- kernel: scatter the compact input arrays into the instance blocks -------------------------------------
+__global__ void scatter_inputs_kernel(WsLayout L, double* ws, int B, InputPtrs in)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    double* W = ws + (int64_t)warp * L.stride;
+    const int N = L.N;
+    if (lane < 3) { AIN(IN_X0 + lane) = in.x0[warp * 3 + lane]; AIN(IN_XF + lane) = in.xf[warp * 3 + lane]; }
+    if (lane < 2) AIN(IN_UPREV + lane) = in.u_prev ? in.u_prev[warp * 2 + lane] : 0.0;
+    int nob = 0, nvp = 0;
+    if (in.obst_count) nob = min(in.obst_count[warp], min(in.obst_max, L.M));
+    if (in.vp_count) nvp = min(in.vp_count[warp], min(in.vp_max, L.V));
+    if (lane == 0)
+    {
+        AIN(IN_NOBST) = (double)nob; AIN(IN_NVP) = (double)nvp;
+        AIN(IN_HASXINIT) = in.x_init ? 1.0 : 0.0;
+        AIN(IN_REINIT) = (in.reinit && in.reinit[warp]) ? 1.0 : 0.0;
+    }
+    for (int i = lane; i < nob * MPCB200_OBST_STRIDE; i += 32)
+        W[L.oOBST + i] = in.obst_params[(int64_t)warp * in.obst_max * MPCB200_OBST_STRIDE + i];
+    for (int i = lane; i < nob; i += 32) W[L.oOTYPE + i] = (double)in.obst_type[(int64_t)warp * in.obst_max + i];
+    for (int i = lane; i < nvp * 3; i += 32) W[L.oVP + i] = in.vp_poses[(int64_t)warp * in.vp_max * 3 + i];
+    if (in.x_init)
+        for (int i = lane; i < 3 * N; i += 32) W[L.oXINIT + i] = in.x_init[(int64_t)warp * 3 * N + i];
+}
+
+// ---- kernel: PHASE_INIT -- cold initial guess or warm-start shift ------------------------------------------
+__global__ void init_kernel(Cfg c, WsLayout L, double* ws, int B, int force_cold)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    double* W = ws + (int64_t)warp * L.stride;
+    const int N = L.N;
+    const bool cold = force_cold || ASC(MPCB200_SC_COLD) != 0.0 || AIN(IN_REINIT) != 0.0;
+    __syncwarp();
+    if (cold)
+    {
+        for (int k = lane; k < N; k += 32) init_cold_stage(c, L, W, k);
+        if (lane == 0) { ASC(MPCB200_SC_DT) = c.dt_ref; ASC(MPCB200_SC_COLD) = 2.0; /* 2: cold init done, repair pending */ }
+    }
+    else
+    {
+        if (lane == 0)
+        {
+            if (c.warm_start && !c.variable_dt) warm_shift_serial(c, L, W);
+            else
+            {
+                for (int i = 0; i < 3; ++i) AX(i, 0) = AIN(IN_X0 + i);
+                for (int i = 0; i < 3; ++i)
+                    if (c.xf_fixed[i]) AX(i, N - 1) = AIN(IN_XF + i);
+            }
+            ASC(MPCB200_SC_COLD) = 0.0;
+        }
+    }
+}
+
+// ---- kernel: PHASE_ASSOCIATE -- obstacle / via-point association, initial-guess repair, dual initialisation ----
+__global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt, int first_outer)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    double* W = ws + (int64_t)warp * L.stride;
+    const int N = L.N;
+    const bool repair = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
+    __syncwarp();
+    for (int k = lane; k < N; k += 32) associate_stage(c, L, W, k);
+    // via-points: MinTimeViaPointsCost::update with findClosestPose (argmin over the grid, first minimum wins)
+    if (has_viapoints(c))
+    {
+        const int nvp = (int)AIN(IN_NVP);
+        int start_idx = 0;
+        for (int j = 0; j < nvp && j < L.V; ++j)
+        {
+            const double vx = W[L.oVP + 3 * j], vy = W[L.oVP + 3 * j + 1];
+            double best = 1e300; int bidx = -1;
+            for (int i = start_idx + lane; i < N - 1; i += 32)
+            {
+                const double dx = AX(0, i) - vx, dy = AX(1, i) - vy;
+                const double d = sqrt(dx * dx + dy * dy);
+                if (d < best) { best = d; bidx = i; }
+            }
+            // warp argmin with smallest index on ties
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const double ob = __shfl_xor_sync(FULLMASK, best, o);
+                const int oi = __shfl_xor_sync(FULLMASK, bidx, o);
+                if (ob < best || (ob == best && oi >= 0 && (bidx < 0 || oi < bidx))) { best = ob; bidx = oi; }
+            }
+            {
+                const double dx = AX(0, N - 1) - vx, dy = AX(1, N - 1) - vy;
+                const double d = sqrt(dx * dx + dy * dy);
+                if (d < best) { best = d; bidx = N - 1; }
+            }
+            int idx = bidx;
+            if (c.vp_ordered) start_idx = idx + 2;
+            if (idx > N - 2) idx = N - 2;
+            if (idx < 1) idx = c.vp_ordered ? 1 : -1;
+            if (lane == 0) W[L.oVPST + j] = (double)idx;
+        }
+        for (int j = nvp + lane; j < L.V; j += 32) W[L.oVPST + j] = -1.0;
+    }
+    __syncwarp();
+    if (repair)
+    {
+        for (int k = lane; k < N; k += 32) project_stage(c, L, W, k);
+        __syncwarp();
+        for (int k = lane; k < N; k += 32) init_controls_stage(c, L, W, k);
+        __syncwarp();
+        if (lane == 0) clip_rates_serial(c, L, W, uprev_dt);
+        __syncwarp();
+    }
+    const double mu = c.mu_init > 0 ? c.mu_init : 0.1;
+    for (int k = lane; k < N; k += 32) init_duals_stage(c, L, W, uprev_dt, k, mu);
+    __syncwarp();
+    if (lane == 0)
+    {
+        ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
+        ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
+        ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0;
+        if (repair) ASC(MPCB200_SC_COLD) = 0.0;
+    }
+}
+
+// ---- kernel: PHASE_EVAL -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) eval_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt, int* n_active)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    double* W = ws + (int64_t)warp * L.stride;
+    const int N = L.N;
+    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;  // finished instance: exact no-op
+    EvalAcc a;
+    evalacc_init(a);
+    for (int k = lane; k < N; k += 32) eval_stage(c, L, W, uprev_dt, k, a);
+    a.dual_inf = warp_max(a.dual_inf); a.prim_inf = warp_max(a.prim_inf);
+    a.sl_max = warp_max(a.sl_max); a.sl_min = warp_min(a.sl_min);
+    a.sum_nu = warp_sum(a.sum_nu); a.sum_lam = warp_sum(a.sum_lam); a.inf1 = warp_sum(a.inf1); a.blog = warp_sum(a.blog);
+    a.gt0 = warp_sum(a.gt0); a.gt1 = warp_sum(a.gt1); a.gldt = warp_sum(a.gldt); a.htt = warp_sum(a.htt);
+    a.obj = warp_sum(a.obj); a.m_ineq = warp_sum(a.m_ineq); a.m_eq = warp_sum(a.m_eq);
+    double mu = 0.0;
+    int fin = 0;
+    if (lane == 0) mu = eval_finish(c, L, W, a, true, &fin);
+    mu = __shfl_sync(FULLMASK, mu, 0);
+    fin = __shfl_sync(FULLMASK, fin, 0);
+    if (fin) return;
+    if (lane == 0 && n_active) atomicAdd(n_active, 1);
+    for (int k = lane; k < N; k += 32) eval_finalize_stage(L, W, k, mu);
+}
+
+// ---- kernel: PHASE_KKT -- Riccati factorisation + solve with inertia-correcting regularisation --------------
+__device__ __forceinline__ int ric_src(int w)
+{
+    if (w < 15) return rP(w / 5, w % 5);
+    if (w < 30) return rPI((w - 15) / 5, (w - 15) % 5);
+    if (w < 40) return R_KG + (w - 30);
+    return R_KT + (w - 40);
+}
+
+__global__ void kkt_kernel(Cfg c, WsLayout L, double* ws, int B, int warps_per_cta)
+{
+    extern __shared__ double smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * warps_per_cta + wib;
+    if (warp >= B) return;
+    double* W = ws + (int64_t)warp * L.stride;
+    const int N = L.N;
+    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    const int per_warp = KW * N + R_WORDS + 8 * N;
+    double* rec = smem + (size_t)wib * per_warp;  // [42][N]
+    double* sm = rec + KW * N;                    // Riccati scratch
+    double* stepbuf = sm + R_WORDS;               // [8][N]
+    double* ric = W + L.oRIC;                     // [N][50] gains (global scratch, L2 resident)
+    // stage the instance's KKT records through shared memory (coalesced, stage-contiguous)
+    for (int i = lane; i < KW * N; i += 32) rec[i] = W[L.oKKT + i];
+    if (lane < 4) sm[R_ZERO + lane] = 0.0;
+    const double htt = ASC(MPCB200_SC_HTT), gt = ASC(MPCB200_SC_GT);
+    const double dlast = ASC(MPCB200_SC_DELTA_LAST);
+    const int dt_free = c.variable_dt;
+    // per-lane task tables (registers)
+    const RTask tA = rtask_A(lane), tB0 = rtask_B(lane), tB1 = rtask_B(lane + 32), tC = rtask_C(lane);
+    const RTask tD0 = rtask_D(lane), tD1 = rtask_D(lane + 32);
+    __syncwarp();
+    double delta = 0.0;
+    double th[5];
+    int ok = 0, nreg = 0;
+    for (int tries = 0; tries < 40; ++tries)
+    {
+        // ---- backward sweep ----
+        for (int idx = lane; idx < 75; idx += 32) sm[R_P + idx] = terminal_entry(c, rec, N, idx, delta, htt, gt);
+        __syncwarp();
+        int good = 1;
+        for (int k = N - 2; k >= 0; --k)
+        {
+            for (int idx = lane; idx < R_EXP_WORDS; idx += 32) sm[R_EXP + idx] = expand_entry(rec, N, k, idx, delta, dt_free);
+            __syncwarp();
+            run_task(sm, tA);
+            __syncwarp();
+            run_task(sm, tB0);
+            run_task(sm, tB1);
+            __syncwarp();
+            double lam4[4];
+            if (!lambda_from_mmvv(sm, lam4)) { good = 0; break; }  // warp-uniform: every lane reads the same values
+            if (lane < 4) sm[R_LAMB + lane] = lam4[lane];
+            __syncwarp();
+            run_task(sm, tC);
+            __syncwarp();
+            for (int w = lane; w < RIC_WORDS; w += 32) ric[k * RIC_WORDS + w] = sm[ric_src(w)];
+            __syncwarp();
+            run_task(sm, tD0);
+            run_task(sm, tD1);
+            __syncwarp();
+        }
+        if (good) good = root_solve(c, sm + R_TH, th);
+        if (good) { ok = 1; break; }
+        ++nreg;
+        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
+        else delta *= (dlast == 0.0 ? 100.0 : 8.0);
+        if (delta > 1e20) break;
+        __syncwarp();
+    }
+    if (!ok)
+    {
+        if (lane == 0) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; ASC(MPCB200_SC_NREG) += (double)nreg; }
+        return;
+    }
+    __syncwarp();
+    // ---- forward substitution (every lane carries the recursion; lanes 0..7 record the step) ----
+    double y[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k <= N - 2; ++k)
+    {
+        double a3[3], Bm[6], e[3], d[3], dw[5], nup[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { a3[i] = rec[(MPCB200_K_A + i) * N + k]; e[i] = rec[(MPCB200_K_E + i) * N + k]; d[i] = rec[(MPCB200_K_D + i) * N + k]; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Bm[i] = rec[(MPCB200_K_B + i) * N + k];
+        forward_stage(ric + k * RIC_WORDS, a3, Bm, e, d, dt_free, th, y, dw, nup);
+        double outv = dw[0];
+        outv = lane == 1 ? dw[1] : outv; outv = lane == 2 ? dw[2] : outv; outv = lane == 3 ? dw[3] : outv;
+        outv = lane == 4 ? dw[4] : outv; outv = lane == 5 ? nup[0] : outv; outv = lane == 6 ? nup[1] : outv;
+        outv = lane == 7 ? nup[2] : outv;
+        if (lane < 8) stepbuf[lane * N + k] = outv;
+    }
+    if (lane < 8) stepbuf[lane * N + (N - 1)] = lane < 3 ? (lane == 0 ? y[0] : (lane == 1 ? y[1] : y[2])) : 0.0;
+    __syncwarp();
+    for (int i = lane; i < 8 * N; i += 32) W[L.oSTEP + i] = stepbuf[i];
+    if (lane == 0)
+    {
+        ASC(MPCB200_SC_DDT) = th[1];
+        ASC(MPCB200_SC_DELTA) = delta;
+        if (delta > 0.0) ASC(MPCB200_SC_DELTA_LAST) = delta;
+        ASC(MPCB200_SC_NREG) += (double)nreg;
+    }
+}
+
+// ---- kernel: PHASE_LINESEARCH -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    double* W = ws + (int64_t)warp * L.stride;
+    const int N = L.N;
+    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    LsAcc a;
+    lsacc_init(a);
+    for (int k = lane; k < N; k += 32) ls_stage_steps(c, L, W, uprev_dt, k, a);
+    a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
+    a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
+    const double mu = ASC(MPCB200_SC_MU), inf1 = ASC(MPCB200_SC_INF), obj = ASC(MPCB200_SC_OBJ), blog = ASC(MPCB200_SC_BLOG);
+    const double ddt = ASC(MPCB200_SC_DDT), dt = ASC(MPCB200_SC_DT);
+    double rho = 1.0;
+    {
+        const double num = a.dJ + a.dphi_bar + 0.5 * (a.curv > 0 ? a.curv : 0.0);
+        if (inf1 > 1e-14)
+        {
+            const double rho_trial = num / ((1.0 - 0.1) * inf1);
+            if (rho < rho_trial) rho = rho_trial + 1.0;
+        }
+    }
+    const double phi0 = obj - mu * blog + rho * inf1;
+    const double dphi = a.dJ + a.dphi_bar - rho * inf1;
+    double alpha = a.a_p;
+    int nbt = 0;
+    __syncwarp();
+    for (int bt = 0; bt < MAX_BACKTRACK; ++bt)
+    {
+        TrialAcc t;
+        t.obj = t.inf1 = t.blog = 0.0;
+        for (int k = lane; k < N; k += 32) ls_stage_trial(c, L, W, uprev_dt, k, alpha, t);
+        t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
+        const double phi = t.obj - mu * t.blog + rho * t.inf1;
+        if (phi <= phi0 + ARMIJO * alpha * dphi || (bt > 0 && fabs(phi - phi0) <= 1e-13 * (1.0 + fabs(phi0)))) break;
+        alpha *= 0.5;
+        ++nbt;
+    }
+    const double a_dual = a.a_d > alpha ? alpha : a.a_d;
+    __syncwarp();
+    for (int k = lane; k < N; k += 32) ls_stage_update(c, L, W, uprev_dt, k, alpha, a_dual);
+    __syncwarp();
+    if (lane == 0)
+    {
+        if (c.variable_dt) ASC(MPCB200_SC_DT) = dt + alpha * ddt;
+        ASC(MPCB200_SC_ALPHA) = alpha;
+        ASC(MPCB200_SC_RHO) = rho;
+        ASC(MPCB200_SC_ITER) += 1.0;
+        ASC(MPCB200_SC_NBT) += (double)nbt;
+    }
+}
+
+// ---- kernel: gather results into compact arrays ----------------------------------------------------------------
+struct OutputPtrs { double* u_seq; double* x_seq; double* dt; int* status; double* kkt; int* iters; double* u_packed; };
+__global__ void gather_outputs_kernel(WsLayout L, const double* ws, int B, OutputPtrs o)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const double* W = ws + (int64_t)warp * L.stride;
+    const int N = L.N;
+    for (int k = lane; k < N; k += 32)
+    {
+        const int kk = k <= N - 2 ? k : N - 2;
+        o.u_seq[((int64_t)warp * N + k) * 2 + 0] = AU(0, kk);
+        o.u_seq[((int64_t)warp * N + k) * 2 + 1] = AU(1, kk);
+        o.x_seq[((int64_t)warp * N + k) * 3 + 0] = AX(0, k);
+        o.x_seq[((int64_t)warp * N + k) * 3 + 1] = AX(1, k);
+        o.x_seq[((int64_t)warp * N + k) * 3 + 2] = normalize_theta(AX(2, k));
+        if (k <= N - 2)
+        {
+            o.u_packed[((int64_t)warp * (N - 1) + k) * 2 + 0] = AU(0, k);
+            o.u_packed[((int64_t)warp * (N - 1) + k) * 2 + 1] = AU(1, k);
+        }
+    }
+    if (lane == 0)
+    {
+        o.dt[warp] = ASC(MPCB200_SC_DT);
+        const double st = ASC(MPCB200_SC_STATUS);
+        o.status[warp] = st < 0 ? MPCB200_STATUS_MAX_ITER : (int)st;
+        o.kkt[warp] = ASC(MPCB200_SC_ERR0);
+        o.iters[warp] = (int)ASC(MPCB200_SC_ITER);
+    }
+}
+
+__global__ void reset_kernel(WsLayout L, double* ws, int B, const unsigned char* which)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (which && !which[b]) return;
+    double* W = ws + (int64_t)b * L.stride;
+    ASC(MPCB200_SC_COLD) = 1.0;
+    ASC(MPCB200_SC_STATUS) = -1.0;
+}
+
+__global__ void flush_kernel(double* buf, size_t n)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = buf[i] * 0.999 + 1.0;
+}
+
+// =================================================================================================================
+// host side
+// =================================================================================================================
+struct mpcb200_handle
+{
+    Cfg cfg;
+    WsLayout L;
+    int max_batch, device, B;
+    double* ws;
+    cudaStream_t stream;
+    // compact device input / output staging
+    double *d_x0, *d_xf, *d_uprev, *d_obst, *d_vp, *d_xinit;
+    int *d_obst_count, *d_obst_type, *d_vp_count;
+    unsigned char* d_reinit;
+    double *d_useq, *d_xseq, *d_dt, *d_kkt, *d_upacked;
+    int *d_status, *d_iters, *d_nactive;
+    int* h_nactive;  // pinned
+    double* d_flush; size_t flush_n;
+    int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
+    double uprev_dt;
+    int kkt_wpc; size_t kkt_smem;
+    mpcb200_stats stats;
+    std::vector<cudaEvent_t> ev;  // pool of event pairs
+    std::vector<int> ev_phase;
+    size_t ev_used;
+    std::string err;
+};
+
+static std::string g_create_err = "";
+
+static int set_err(mpcb200_handle* h, int code, const std::string& msg)
+{
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            return set_err(h, MPCB200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+extern "C" void mpcb200_default_config(mpcb200_config* c)
+{
+    memset(c, 0, sizeof(*c));
+    c->robot_type = MPCB200_ROBOT_UNICYCLE;
+    c->wheelbase = 0.5; c->length_rear = 1.0; c->length_front = 1.0;
+    c->u_lb[0] = -0.2; c->u_lb[1] = -0.3; c->u_ub[0] = 0.4; c->u_ub[1] = 0.3;
+    c->du_lb[0] = c->du_lb[1] = -MPCB200_INF; c->du_ub[0] = c->du_ub[1] = MPCB200_INF;
+    c->n = 20; c->dt_ref = 0.3; c->variable_dt = 1; c->dt_lb = 0.0; c->dt_ub = 10.0;
+    c->xf_fixed[0] = c->xf_fixed[1] = c->xf_fixed[2] = 1;
+    c->collocation = MPCB200_COLLOC_FORWARD; c->warm_start = 1;
+    c->objective = MPCB200_OBJ_MINIMUM_TIME;
+    c->vp_position_weight = 1.0; c->vp_orientation_weight = 0.0;
+    c->min_obstacle_dist = 0.5; c->force_inclusion_dist = 0.5; c->cutoff_dist = 2.0;
+    c->footprint_type = MPCB200_FOOTPRINT_POINT;
+    c->k_max_obstacles_per_stage = 5;
+    c->max_iter = 100; c->tol = 1e-6; c->mu_init = 0.1; c->outer_iterations = 1;
+}
+
+static int validate_config(const mpcb200_config* c, std::string& why)
+{
+    if (c->n < 3 || c->n > 512) { why = "n must be in [3, 512]"; return MPCB200_E_INVALID; }
+    if (c->robot_type < 0 || c->robot_type > 3) { why = "unknown robot_type"; return MPCB200_E_INVALID; }
+    if (c->collocation != MPCB200_COLLOC_FORWARD)
+    { why = "only forward_differences collocation is implemented (midpoint / crank_nicolson: next round)"; return MPCB200_E_UNSUPPORTED; }
+    if (c->objective < 0 || c->objective > 2) { why = "unknown objective"; return MPCB200_E_INVALID; }
+    if (c->footprint_type < 0 || c->footprint_type > 4) { why = "unknown footprint_type"; return MPCB200_E_INVALID; }
+    if (c->footprint_type == MPCB200_FOOTPRINT_POLYGON && (c->n_poly < 1 || c->n_poly > MPCB200_MAX_POLY))
+    { why = "polygon footprint needs 1..16 vertices"; return MPCB200_E_INVALID; }
+    if (c->k_max_obstacles_per_stage < 0 || c->k_max_obstacles_per_stage > 16) { why = "k_max_obstacles_per_stage must be in [0,16]"; return MPCB200_E_INVALID; }
+    if (!(c->dt_ref > 0)) { why = "dt_ref must be > 0"; return MPCB200_E_INVALID; }
+    if (c->variable_dt && !(c->dt_ub > c->dt_lb)) { why = "dt_ub must exceed dt_lb"; return MPCB200_E_INVALID; }
+    if (has_mintime(*c) && !c->variable_dt) { why = "minimum_time objectives need variable_dt"; return MPCB200_E_INVALID; }
+    if (!(c->tol > 0) || c->max_iter < 1) { why = "tol > 0 and max_iter >= 1 required"; return MPCB200_E_INVALID; }
+    for (int i = 0; i < 2; ++i)
+        if (!(c->u_ub[i] > c->u_lb[i])) { why = "u_ub must exceed u_lb"; return MPCB200_E_INVALID; }
+    return 0;
+}
+
+
+extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int device, mpcb200_handle** out)
+{
+    mpcb200_handle* h = nullptr;
+    if (!cfg || !out || max_batch < 1) return set_err(nullptr, MPCB200_E_INVALID, "bad arguments");
+    std::string why;
+    int rc = validate_config(cfg, why);
+    if (rc) return set_err(nullptr, rc, why);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, MPCB200_E_NODEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) + "): this solver has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(nullptr, MPCB200_E_INVALID, "device index out of range");
+    h = new mpcb200_handle();
+    h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->ev_used = 0;
+    memset(&h->stats, 0, sizeof(h->stats));
+    make_layout(cfg, MAX_OBST, MAX_VP, h->L);
+    h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0;
+#define CKC(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e_); delete h; return set_err(nullptr, MPCB200_E_CUDA, m); } \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t B = (size_t)max_batch, N = (size_t)cfg->n;
+    CKC(cudaMalloc(&h->ws, B * h->L.stride * sizeof(double)));
+    CKC(cudaMemsetAsync(h->ws, 0, B * h->L.stride * sizeof(double), h->stream));
+    CKC(cudaMalloc(&h->d_x0, B * 3 * 8)); CKC(cudaMalloc(&h->d_xf, B * 3 * 8)); CKC(cudaMalloc(&h->d_uprev, B * 2 * 8));
+    CKC(cudaMalloc(&h->d_obst, B * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CKC(cudaMalloc(&h->d_obst_count, B * 4));
+    CKC(cudaMalloc(&h->d_obst_type, B * MAX_OBST * 4));
+    CKC(cudaMalloc(&h->d_vp, B * MAX_VP * 3 * 8)); CKC(cudaMalloc(&h->d_vp_count, B * 4));
+    CKC(cudaMalloc(&h->d_xinit, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_reinit, B));
+    CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
+    CKC(cudaMalloc(&h->d_kkt, B * 8)); CKC(cudaMalloc(&h->d_upacked, B * (N - 1) * 2 * 8));
+    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 4));
+    CKC(cudaMallocHost(&h->h_nactive, 4));
+    h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
+    CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
+    CKC(cudaMemsetAsync(h->d_flush, 0, h->flush_n * 8, h->stream));
+    // KKT kernel: shared memory per warp = records + scratch + step buffer
+    {
+        const size_t per_warp = ((size_t)KW * N + R_WORDS + 8 * N) * sizeof(double);
+        int wpc = (int)((200 * 1024) / per_warp);
+        if (wpc < 1) { delete h; return set_err(nullptr, MPCB200_E_UNSUPPORTED, "horizon too long for the shared-memory staged KKT kernel"); }
+        if (wpc > WARPS_PER_CTA) wpc = WARPS_PER_CTA;
+        h->kkt_wpc = wpc; h->kkt_smem = per_warp * wpc;
+        CKC(cudaFuncSetAttribute(kkt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->kkt_smem));
+    }
+    {
+        // all instances start cold
+        reset_kernel<<<(max_batch + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, max_batch, nullptr);
+        CKC(cudaGetLastError());
+    }
+    CKC(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return MPCB200_OK;
+}
+
+extern "C" void mpcb200_destroy(mpcb200_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->ws, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
+                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->h_nactive) cudaFreeHost(h->h_nactive);
+    for (auto& e : h->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* mpcb200_last_error(const mpcb200_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+static inline int grid_for(int B, int wpc) { return (B + wpc - 1) / wpc; }
+
+// event-pair pool: device time per phase launch (CUDA events on the solver stream)
+static int ev_begin(mpcb200_handle* h, int phase)
+{
+    if (h->ev_used + 2 > h->ev.size())
+    {
+        for (int i = 0; i < 256; ++i) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return -1; h->ev.push_back(e); }
+        h->ev_phase.resize(h->ev.size() / 2);
+    }
+    h->ev_phase[h->ev_used / 2] = phase;
+    cudaEventRecord(h->ev[h->ev_used], h->stream);
+    return 0;
+}
+static void ev_end(mpcb200_handle* h)
+{
+    cudaEventRecord(h->ev[h->ev_used + 1], h->stream);
+    h->ev_used += 2;
+}
+static void ev_collect(mpcb200_handle* h)
+{
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2)
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess)
+        {
+            const int p = h->ev_phase[i / 2];
+            h->stats.ms[p] += ms; h->stats.launches[p] += 1;
+        }
+    }
+    h->ev_used = 0;
+}
+
+static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int first_outer, bool timed)
+{
+    const int grid4 = grid_for(B, WARPS_PER_CTA);
+    if (timed && ev_begin(h, phase)) return set_err(h, MPCB200_E_CUDA, "cudaEventCreate failed");
+    switch (phase)
+    {
+        case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold); break;
+        case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer); break;
+        case MPCB200_PHASE_EVAL: eval_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, h->d_nactive); break;
+        case MPCB200_PHASE_KKT: kkt_kernel<<<grid_for(B, h->kkt_wpc), h->kkt_wpc * 32, h->kkt_smem, h->stream>>>(h->cfg, h->L, h->ws, B, h->kkt_wpc); break;
+        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt); break;
+        default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
+    }
+    if (timed) ev_end(h);
+    h->stats.launches_total += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int check_batch(mpcb200_handle* h, int B)
+{
+    if (!h) return MPCB200_E_INVALID;
+    if (B < 1 || B > h->max_batch) return set_err(h, MPCB200_E_INVALID, "batch size out of range");
+    return 0;
+}
+
+static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                         const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init, const unsigned char* reinit)
+{
+    if (!x0 || !xf) return set_err(h, MPCB200_E_INVALID, "x0 and xf are required");
+    const size_t N = (size_t)h->cfg.n;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_x0, x0, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_xf, xf, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (long long)B * 6 * 8;
+    if (u_prev) { CK(cudaMemcpyAsync(h->d_uprev, u_prev, (size_t)B * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)B * 16; }
+    else CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
+    h->uprev_dt = u_prev_dt;
+    h->has_obst = 0; h->obst_max = 0;
+    if (obst && obst->count && obst->max_per_instance > 0)
+    {
+        if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
+        const size_t M = (size_t)obst->max_per_instance;
+        for (size_t i = 0; i < (size_t)B * M; ++i)
+            if (obst->type[i] == MPCB200_OBST_LINE) return set_err(h, MPCB200_E_UNSUPPORTED, "line obstacles are not implemented in this round");
+        CK(cudaMemcpyAsync(h->d_obst_count, obst->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_obst_type, obst->type, (size_t)B * M * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_obst, obst->params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (long long)(B * 4 + B * M * 4 + B * M * MPCB200_OBST_STRIDE * 8);
+        h->has_obst = 1; h->obst_max = (int)M;
+    }
+    h->has_vp = 0; h->vp_max = 0;
+    if (vp && vp->count && vp->max_per_instance > 0)
+    {
+        if (vp->max_per_instance > MAX_VP) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 8 via-points per instance");
+        const size_t V = (size_t)vp->max_per_instance;
+        CK(cudaMemcpyAsync(h->d_vp_count, vp->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_vp, vp->poses, (size_t)B * V * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (long long)(B * 4 + B * V * 24);
+        h->has_vp = 1; h->vp_max = (int)V;
+    }
+    h->has_xinit = 0;
+    if (x_init) { CK(cudaMemcpyAsync(h->d_xinit, x_init, (size_t)B * N * 3 * 8, cudaMemcpyHostToDevice, h->stream)); h->has_xinit = 1; h->stats.h2d_bytes += (long long)(B * N * 24); }
+    h->has_reinit = 0;
+    if (reinit) { CK(cudaMemcpyAsync(h->d_reinit, reinit, (size_t)B, cudaMemcpyHostToDevice, h->stream)); h->has_reinit = 1; h->stats.h2d_bytes += B; }
+    InputPtrs in;
+    in.x0 = h->d_x0; in.xf = h->d_xf; in.u_prev = h->d_uprev;
+    in.obst_count = h->has_obst ? h->d_obst_count : nullptr; in.obst_type = h->d_obst_type; in.obst_params = h->d_obst; in.obst_max = h->obst_max;
+    in.vp_count = h->has_vp ? h->d_vp_count : nullptr; in.vp_poses = h->d_vp; in.vp_max = h->vp_max;
+    in.x_init = h->has_xinit ? h->d_xinit : nullptr;
+    in.reinit = h->has_reinit ? h->d_reinit : nullptr;
+    scatter_inputs_kernel<<<grid_for(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, h->stream>>>(h->L, h->ws, B, in);
+    h->stats.launches_total += 1;
+    CK(cudaGetLastError());
+    h->B = B;
+    return 0;
+}
+
+// the solve proper: INIT, then outer_iterations x (ASSOCIATE, interior-point iterations)
+static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_time_s)
+{
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, h->stream));
+    int rc = launch_phase(h, MPCB200_PHASE_INIT, B, force_cold, 0, true);
+    if (rc) return rc;
+    const int outer = h->cfg.outer_iterations > 0 ? h->cfg.outer_iterations : 1;
+    for (int oi = 0; oi < outer; ++oi)
+    {
+        if ((rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, oi == 0, true))) return rc;
+        for (int it = 0; it <= h->cfg.max_iter; ++it)
+        {
+            const bool poll = (it % 4 == 3) || it == h->cfg.max_iter;
+            if (poll) CK(cudaMemsetAsync(h->d_nactive, 0, 4, h->stream));
+            if ((rc = launch_phase(h, MPCB200_PHASE_EVAL, B, 0, 0, true))) return rc;
+            if (poll)
+            {
+                CK(cudaMemcpyAsync(h->h_nactive, h->d_nactive, 4, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                if (*h->h_nactive == 0) break;
+            }
+            if (it == h->cfg.max_iter) break;
+            if ((rc = launch_phase(h, MPCB200_PHASE_KKT, B, 0, 0, true))) return rc;
+            if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, true))) return rc;
+        }
+    }
+    OutputPtrs o{h->d_useq, h->d_xseq, h->d_dt, h->d_status, h->d_kkt, h->d_iters, h->d_upacked};
+    gather_outputs_kernel<<<grid_for(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, h->stream>>>(h->L, h->ws, B, o);
+    h->stats.launches_total += 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(t1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    if (solve_time_s) *solve_time_s = ms * 1e-3;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    ev_collect(h);
+    return 0;
+}
+
+static int fetch_results(mpcb200_handle* h, int B, double* u_seq, double* x_seq, double* dt_out, int* status, double* kkt_err, int* iters)
+{
+    const size_t N = (size_t)h->cfg.n;
+    if (u_seq) { CK(cudaMemcpyAsync(u_seq, h->d_useq, (size_t)B * N * 16, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(B * N * 16); }
+    if (x_seq) { CK(cudaMemcpyAsync(x_seq, h->d_xseq, (size_t)B * N * 24, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(B * N * 24); }
+    if (dt_out) { CK(cudaMemcpyAsync(dt_out, h->d_dt, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += B * 8; }
+    if (status) { CK(cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += B * 4; }
+    if (kkt_err) { CK(cudaMemcpyAsync(kkt_err, h->d_kkt, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += B * 8; }
+    if (iters) { CK(cudaMemcpyAsync(iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += B * 4; }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int mpcb200_step_batch(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                                  const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init,
+                                  const unsigned char* reinit, double* u_seq, double* x_seq, double* dt_out, int* status,
+                                  double* kkt_err, int* iters, double* solve_time_s)
+{
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if ((rc = upload_inputs(h, B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit))) return rc;
+    if ((rc = solve_device(h, B, 0, solve_time_s))) return rc;
+    return fetch_results(h, B, u_seq, x_seq, dt_out, status, kkt_err, iters);
+}
+
+extern "C" int mpcb200_upload_inputs(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                                     const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init)
+{
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if ((rc = upload_inputs(h, B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, nullptr))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int mpcb200_solve_resident(mpcb200_handle* h, int cold, double* solve_time_s)
+{
+    if (!h || h->B < 1) return set_err(h, MPCB200_E_INVALID, "no resident inputs: call mpcb200_upload_inputs first");
+    CK(cudaSetDevice(h->device));
+    return solve_device(h, h->B, cold ? 1 : 0, solve_time_s);
+}
+
+extern "C" int mpcb200_fetch_results(mpcb200_handle* h, double* u_seq, double* x_seq, double* dt_out, int* status, double* kkt_err, int* iters)
+{
+    if (!h || h->B < 1) return set_err(h, MPCB200_E_INVALID, "nothing to fetch");
+    CK(cudaSetDevice(h->device));
+    return fetch_results(h, h->B, u_seq, x_seq, dt_out, status, kkt_err, iters);
+}
+
+extern "C" int mpcb200_device_controls(mpcb200_handle* h, void** dev_ptr, long long* n_doubles)
+{
+    if (!h || h->B < 1) return set_err(h, MPCB200_E_INVALID, "no batch solved yet");
+    if (dev_ptr) *dev_ptr = h->d_upacked;
+    if (n_doubles) *n_doubles = (long long)h->B * (h->cfg.n - 1) * 2;
+    return 0;
+}
+
+extern "C" int mpcb200_reset(mpcb200_handle* h, const unsigned char* which, int B)
+{
+    if (!h) return MPCB200_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int n = which ? B : h->max_batch;
+    if (n < 1 || n > h->max_batch) return set_err(h, MPCB200_E_INVALID, "batch size out of range");
+    if (which) CK(cudaMemcpyAsync(h->d_reinit, which, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    reset_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, n, which ? h->d_reinit : nullptr);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- kernel-level access ------------------------------------------------------------------------------------
+static int field_info(const mpcb200_handle* h, int field, int* off, int* cnt)
+{
+    const WsLayout& L = h->L;
+    switch (field)
+    {
+        case MPCB200_F_X: *off = L.oX; *cnt = 3; return 0;
+        case MPCB200_F_U: *off = L.oU; *cnt = 2; return 0;
+        case MPCB200_F_NU: *off = L.oNU; *cnt = 3; return 0;
+        case MPCB200_F_S: *off = L.oS; *cnt = L.RS; return 0;
+        case MPCB200_F_LAM: *off = L.oLAM; *cnt = L.RS; return 0;
+        case MPCB200_F_KKT: *off = L.oKKT; *cnt = KW; return 0;
+        case MPCB200_F_STEP: *off = L.oSTEP; *cnt = 8; return 0;
+        case MPCB200_F_SCAL: *off = L.oSCAL; *cnt = MPCB200_SCAL_WORDS; return 0;
+        case MPCB200_F_OBSIDX: *off = L.oOBS; *cnt = L.K > 0 ? L.K : 1; return 0;
+    }
+    return -1;
+}
+
+extern "C" int mpcb200_ws_count(const mpcb200_handle* h, int field)
+{
+    int off, cnt;
+    if (!h || field_info(h, field, &off, &cnt)) return MPCB200_E_INVALID;
+    return cnt;
+}
+
+extern "C" int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst)
+{
+    int off, cnt, rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!dst || field_info(h, field, &off, &cnt)) return set_err(h, MPCB200_E_INVALID, "bad field");
+    CK(cudaSetDevice(h->device));
+    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * h->L.N;
+    CK(cudaMemcpy2DAsync(dst, words * 8, h->ws + off, (size_t)h->L.stride * 8, words * 8, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const double* src)
+{
+    int off, cnt, rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!src || field_info(h, field, &off, &cnt)) return set_err(h, MPCB200_E_INVALID, "bad field");
+    CK(cudaSetDevice(h->device));
+    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * h->L.N;
+    CK(cudaMemcpy2DAsync(h->ws + off, (size_t)h->L.stride * 8, src, words * 8, words * 8, (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int mpcb200_run_phase(mpcb200_handle* h, int phase, int B)
+{
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if ((rc = launch_phase(h, phase, B, phase == MPCB200_PHASE_INIT ? 0 : 0, 1, true))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    ev_collect(h);
+    return 0;
+}
+
+extern "C" int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps, int flush_l2, double* ms_per_launch)
+{
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (reps < 1) reps = 1;
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    double total = 0.0;
+    for (int r = 0; r < reps; ++r)
+    {
+        if (flush_l2) { flush_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_n); CK(cudaGetLastError()); }
+        CK(cudaEventRecord(a, h->stream));
+        if ((rc = launch_phase(h, phase, B, 0, 1, false))) return rc;
+        CK(cudaEventRecord(b, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        total += ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (ms_per_launch) *ms_per_launch = total / reps;
+    return 0;
+}
+
+extern "C" int mpcb200_stats_get(const mpcb200_handle* h, mpcb200_stats* out)
+{
+    if (!h || !out) return MPCB200_E_INVALID;
+    *out = h->stats;
+    return 0;
+}
+extern "C" int mpcb200_stats_reset(mpcb200_handle* h)
+{
+    if (!h) return MPCB200_E_INVALID;
+    memset(&h->stats, 0, sizeof(h->stats));
+    return 0;
+}

@@ -692,7 +692,7 @@ static double row_value(const orc_problem* p, const orc_ws* ws, int k, int slot,
 void orc_project_init(const orc_problem* p, orc_ws* ws)
 {
     const int N = ws->N, K = ws->K;
-    double margin = getenv("ORC_MARGIN") ? atof(getenv("ORC_MARGIN")) : ORC_PROJ_MARGIN;
+    const double margin = ORC_PROJ_MARGIN;
     for (int k = 1; k <= N - 2; ++k)
         for (int sweep = 0; sweep < ORC_PROJ_SWEEPS; ++sweep)
         {
@@ -817,9 +817,7 @@ void orc_init_duals(const orc_problem* p, orc_ws* ws)
             if (row_active(p, ws, k, sl))
             {
                 double g = row_value(p, ws, k, sl, ws->X, ws->U, dt, NULL, NULL);
-                double push = getenv("ORC_PUSH") ? atof(getenv("ORC_PUSH")) : ORC_SLACK_PUSH;
-                if (sl >= 8) push = ORC_SLACK_PUSH;
-                s = -g > push ? -g : push;
+                s = -g > ORC_SLACK_PUSH ? -g : ORC_SLACK_PUSH;
                 lam = mu / s;
             }
             ws->S[IX(sl, k)] = s;
@@ -853,7 +851,6 @@ typedef struct {
 } eval_info;
 
 static eval_info g_last_info;
-static __thread double* g_GR = NULL; /* experiment: sigma*r part of the condensed gradient (5N+1) */ /* oracle is used single-threaded per ws; batch driver keeps its own copy */
 
 static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double* G1 /*5xN + 1*/)
 {
@@ -865,7 +862,6 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
     memset(KKT, 0, sizeof(double) * KW * N);
     memset(GL, 0, sizeof(double) * 5 * N);
     memset(G1, 0, sizeof(double) * (5 * N + 1));
-    if (g_GR) memset(g_GR, 0, sizeof(double) * (5 * N + 1));
     double htt = 0.0, gt0 = 0.0, gl_dt = 0.0;
     double prim_inf = 0.0, inf1 = 0.0, sum_nu = 0.0;
     int m_eq = 0;
@@ -999,13 +995,12 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
                 for (int i = 0; i < 3; ++i)
                 {
                     KK(MPCB200_K_G + i, k) += c0 * grad[i];
-                    if (g_GR) g_GR[IX(i, k)] += c0 * grad[i];
                     G1[IX(i, k)] += c1 * grad[i];
                     GL[IX(i, k)] += lam * grad[i];
                 }
                 int q = 0;
                 for (int i = 0; i < 3; ++i)
-                    for (int j = i; j < 3; ++j, ++q) hadd(KKT, N, k, i, j, (getenv("ORC_GN") ? 0.0 : lam * h6[q]) + sig * grad[i] * grad[j]);
+                    for (int j = i; j < 3; ++j, ++q) hadd(KKT, N, k, i, j, lam * h6[q] + sig * grad[i] * grad[j]);
                 continue;
             }
             /* u_k part */
@@ -1014,7 +1009,6 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
                 double gi = grad[3 + i];
                 if (gi == 0.0 || k > N - 2) continue;
                 KK(MPCB200_K_G + 3 + i, k) += c0 * gi;
-                if (g_GR) g_GR[IX(3 + i, k)] += c0 * gi;
                 G1[IX(3 + i, k)] += c1 * gi;
                 GL[IX(3 + i, k)] += lam * gi;
                 hadd(KKT, N, k, 3 + i, 3 + i, sig * gi * gi);
@@ -1027,7 +1021,6 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
                 double gi = grad[5 + i];
                 if (gi == 0.0 || k < 1) continue;
                 KK(MPCB200_K_G + 3 + i, k - 1) += c0 * gi;
-                if (g_GR) g_GR[IX(3 + i, k - 1)] += c0 * gi;
                 G1[IX(3 + i, k - 1)] += c1 * gi;
                 GL[IX(3 + i, k - 1)] += lam * gi;
                 hadd(KKT, N, k - 1, 3 + i, 3 + i, sig * gi * gi);
@@ -1037,7 +1030,6 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
             if (grad[7] != 0.0)
             {
                 gt0 += c0 * grad[7];
-                if (g_GR) g_GR[5 * N] += c0 * grad[7];
                 gt1 += c1 * grad[7];
                 gl_dt += lam * grad[7];
                 htt += sig * grad[7] * grad[7];
@@ -1068,6 +1060,8 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
     info->obj = orc_objective(p, ws, ws->X, ws->U, dt);
     ws->SCAL[MPCB200_SC_OBJ] = info->obj;
     ws->SCAL[MPCB200_SC_INF] = inf1;
+    ws->SCAL[MPCB200_SC_BLOG] = blog;
+    ws->SCAL[MPCB200_SC_GLDT] = gl_dt;
 #undef KK
 }
 
@@ -1369,8 +1363,6 @@ int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
     int status = MPCB200_STATUS_MAX_ITER;
     int iter = 0, nreg = 0, nbt = 0;
     eval_info info;
-    double* GRbuf = (double*)malloc(sizeof(double) * (5 * N + 1));
-    g_GR = GRbuf;
     for (;;)
     {
         eval_and_update_mu(p, ws, &info, 1);
@@ -1393,64 +1385,6 @@ int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
         }
         if (!ok) { status = MPCB200_STATUS_NUMERICAL_ERROR; break; }
         if (delta > 0.0) ws->SCAL[MPCB200_SC_DELTA_LAST] = delta;
-        double kappa = 1.0;
-        if (getenv("ORC_COMPOSITE"))
-        {
-            /* composite step: full = tangential + normal; scale the normal part by kappa */
-            double* full = (double*)malloc(sizeof(double) * (8 * N + 1));
-            double* tang = (double*)malloc(sizeof(double) * (8 * N + 1));
-            double* Esave = (double*)malloc(sizeof(double) * 3 * N);
-            memcpy(full, ws->STEP, sizeof(double) * 8 * N); full[8 * N] = ws->SCAL[MPCB200_SC_DDT];
-            for (int k = 0; k < N; ++k)
-            {
-                for (int i = 0; i < 5; ++i) ws->KKT[(MPCB200_K_G + i) * N + k] -= g_GR[IX(i, k)];
-                for (int i = 0; i < 3; ++i) { Esave[IX(i, k)] = ws->KKT[(MPCB200_K_E + i) * N + k]; ws->KKT[(MPCB200_K_E + i) * N + k] = 0.0; }
-            }
-            ws->SCAL[MPCB200_SC_GT] -= g_GR[5 * N];
-            orc_kkt_solve(p, ws, delta);
-            memcpy(tang, ws->STEP, sizeof(double) * 8 * N); tang[8 * N] = ws->SCAL[MPCB200_SC_DDT];
-            for (int k = 0; k < N; ++k)
-            {
-                for (int i = 0; i < 5; ++i) ws->KKT[(MPCB200_K_G + i) * N + k] += g_GR[IX(i, k)];
-                for (int i = 0; i < 3; ++i) ws->KKT[(MPCB200_K_E + i) * N + k] = Esave[IX(i, k)];
-            }
-            ws->SCAL[MPCB200_SC_GT] += g_GR[5 * N];
-            /* choose kappa: maximise kappa * a_p(kappa) over a small grid, require a_p(kappa) >= 0.2 a_p(0) */
-            const double taus = (1.0 - mu > ORC_TAU_MIN) ? 1.0 - mu : ORC_TAU_MIN;
-            double best = -1.0, bestk = 1.0;
-            double ap0 = 0.0;
-            for (int pass = 0; pass < 2; ++pass)
-            for (int ik = (pass == 0 ? 12 : 0); ik <= 12; ++ik)
-            {
-                double kap = (ik == 12) ? 0.0 : pow(0.5, ik);
-                if (pass == 1 && ik == 12) continue;
-                double ap = 1.0;
-                for (int k = 0; k < N; ++k)
-                    for (int sl = 0; sl < RS; ++sl)
-                    {
-                        if (!row_active(p, ws, k, sl)) continue;
-                        double grad[8];
-                        double g = row_value(p, ws, k, sl, ws->X, ws->U, dt, grad, NULL);
-                        double gdz = 0.0;
-#define STP(i, kk) (tang[IX(i, kk)] + kap * (full[IX(i, kk)] - tang[IX(i, kk)]))
-                        for (int i = 0; i < 3; ++i) gdz += grad[i] * STP(i, k);
-                        if (k <= N - 2) for (int i = 0; i < 2; ++i) gdz += grad[3 + i] * STP(3 + i, k);
-                        if (k >= 1) for (int i = 0; i < 2; ++i) gdz += grad[5 + i] * STP(3 + i, k - 1);
-                        gdz += grad[7] * (tang[8 * N] + kap * (full[8 * N] - tang[8 * N]));
-                        double sv = ws->S[IX(sl, k)];
-                        double ds = -kap * (g + sv) - gdz;
-                        if (ds < 0 && -taus * sv / ds < ap) ap = -taus * sv / ds;
-                    }
-                if (pass == 0) { ap0 = ap; continue; }
-                double score = kap * ap;
-                if (ap >= 0.2 * ap0 && score > best) { best = score; bestk = kap; }
-            }
-            if (best < 0) bestk = 0.0;
-            kappa = bestk;
-            for (int i = 0; i < 8 * N; ++i) ws->STEP[i] = tang[i] + kappa * (full[i] - tang[i]);
-            ws->SCAL[MPCB200_SC_DDT] = tang[8 * N] + kappa * (full[8 * N] - tang[8 * N]);
-            free(full); free(tang); free(Esave);
-        }
         const double ddt = ws->SCAL[MPCB200_SC_DDT];
         /* ---- slack / multiplier steps and fraction to the boundary ---- */
         const double tau = (1.0 - mu > ORC_TAU_MIN) ? 1.0 - mu : ORC_TAU_MIN;
@@ -1469,11 +1403,11 @@ int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
                 if (k >= 1) for (int i = 0; i < 2; ++i) gdz += grad[5 + i] * ws->STEP[IX(3 + i, k - 1)];
                 gdz += grad[7] * ddt;
                 double s = ws->S[IX(sl, k)], lam = ws->LAM[IX(sl, k)];
-                double ds = -kappa * (g + s) - gdz;
+                double ds = -(g + s) - gdz;
                 double dl = mu / s - lam - (lam / s) * ds;
                 ws->DS[IX(sl, k)] = ds;
                 ws->DLAM[IX(sl, k)] = dl;
-                if (ds < 0 && -tau * s / ds < a_p) { a_p = -tau * s / ds; if (getenv("ORC_DEBUG2")) fprintf(stderr, "   a_p %.4f row k=%d slot=%d s=%.3e ds=%.3e g=%.3e lam=%.3e gdz=%.3e\n", a_p, k, sl, s, ds, g, lam, gdz); }
+                if (ds < 0 && -tau * s / ds < a_p) a_p = -tau * s / ds;
                 if (dl < 0 && -tau * lam / dl < a_d) a_d = -tau * lam / dl;
                 dphi_bar += -mu * ds / s;
                 curv += (lam / s) * ds * ds;
@@ -1533,18 +1467,18 @@ int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
             if (c->variable_dt) curv += ddt * ddt * (ws->SCAL[MPCB200_SC_HTT] + ws->SCAL[MPCB200_SC_DELTA]);
         }
         const double inf1 = info.inf1;
-        double rho = ws->SCAL[MPCB200_SC_RHO];
+        double rho = 1.0; /* memoryless penalty parameter: recomputed every iteration */
         {
             double num = dJ + dphi_bar + 0.5 * (curv > 0 ? curv : 0.0);
             if (inf1 > 1e-14)
             {
-                double rho_trial = num / ((1.0 - 0.1) * inf1 * (kappa > 1e-3 ? kappa : 1e-3));
+                double rho_trial = num / ((1.0 - 0.1) * inf1);
                 if (rho < rho_trial) rho = rho_trial + 1.0;
             }
         }
         ws->SCAL[MPCB200_SC_RHO] = rho;
         const double phi0 = info.obj - mu * info.barrier_log + rho * inf1;
-        const double dphi = dJ + dphi_bar - rho * kappa * inf1;
+        const double dphi = dJ + dphi_bar - rho * inf1;
         /* ---- backtracking line search ---- */
         double alpha = a_p;
         int accepted = 0;
@@ -1572,8 +1506,7 @@ int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
             /* tiny step: accept anyway (keeps the iteration going; counted) */
         }
         /* ---- update ---- */
-        double a_dual = a_d;
-        if (!getenv("ORC_SEPDUAL") && a_dual > alpha) a_dual = alpha;
+        double a_dual = a_d > alpha ? alpha : a_d; /* the multipliers never move further than the primal step taken */
         for (int k = 0; k < N; ++k)
         {
             for (int i = 0; i < 3; ++i) ws->X[IX(i, k)] += alpha * ws->STEP[IX(i, k)];
@@ -1587,8 +1520,7 @@ int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
                 if (!row_active(p, ws, k, sl)) continue;
                 double s = ws->S[IX(sl, k)] + alpha * ws->DS[IX(sl, k)];
                 double lam = ws->LAM[IX(sl, k)] + a_dual * ws->DLAM[IX(sl, k)];
-                double ksig = getenv("ORC_KSIG") ? atof(getenv("ORC_KSIG")) : ORC_KAPPA_SIGMA;
-                double lo = mu / (ksig * s), hi = ksig * mu / s;
+                double lo = mu / (ORC_KAPPA_SIGMA * s), hi = ORC_KAPPA_SIGMA * mu / s;
                 if (lam < lo) lam = lo;
                 if (lam > hi) lam = hi;
                 ws->S[IX(sl, k)] = s;
@@ -1598,12 +1530,10 @@ int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
         if (c->variable_dt) ws->SCAL[MPCB200_SC_DT] = dt + alpha * ddt;
         ws->SCAL[MPCB200_SC_ALPHA] = alpha;
         if (getenv("ORC_DEBUG"))
-            fprintf(stderr, "it %3d kap %.3f mu %.1e E0 %.2e Emu %.2e obj %.5f inf1 %.2e dinf %.2e delta %.1e a_p %.3f a_d %.3f alpha %.4f rho %.2e dphi %.2e acc %d dt %.4f\n",
-                    iter, kappa, mu, ws->SCAL[MPCB200_SC_ERR0], ws->SCAL[MPCB200_SC_ERRMU], info.obj, inf1, info.dual_inf, delta, a_p, a_d, alpha, rho, dphi, accepted, dt);
+            fprintf(stderr, "it %3d mu %.1e E0 %.2e Emu %.2e obj %.5f inf1 %.2e dinf %.2e delta %.1e a_p %.3f a_d %.3f alpha %.4f rho %.2e dphi %.2e acc %d dt %.4f\n",
+                    iter, mu, ws->SCAL[MPCB200_SC_ERR0], ws->SCAL[MPCB200_SC_ERRMU], info.obj, inf1, info.dual_inf, delta, a_p, a_d, alpha, rho, dphi, accepted, dt);
         ++iter;
     }
-    g_GR = NULL;
-    free(GRbuf);
     ws->SCAL[MPCB200_SC_STATUS] = (double)status;
     ws->SCAL[MPCB200_SC_NREG] = (double)nreg;
     if (res)
@@ -1625,7 +1555,8 @@ int orc_step(const orc_problem* p, orc_ws* ws, const double* x_init, int reinit,
              orc_result* res)
 {
     const int N = ws->N;
-    if (ws->cold || reinit) { orc_init_cold(p, x_init, ws); if (!getenv("ORC_NOUINIT")) orc_init_controls(p, ws); }
+    const int is_cold = (ws->cold || reinit);
+    if (is_cold) orc_init_cold(p, x_init, ws);
     else if (p->cfg->warm_start && !p->cfg->variable_dt) orc_warm_shift(p, ws);
     else
     {
@@ -1640,7 +1571,11 @@ int orc_step(const orc_problem* p, orc_ws* ws, const double* x_init, int reinit,
     for (int it = 0; it < outer; ++it)
     {
         orc_associate(p, ws);
-        if (it == 0 && (ws->cold || reinit) && !getenv("ORC_NOPROJ")) orc_project_init(p, ws);
+        if (it == 0 && is_cold)
+        {
+            orc_project_init(p, ws);
+            orc_init_controls(p, ws);
+        }
         orc_init_duals(p, ws);
         status = orc_solve(p, ws, &r);
         racc.iters += r.iters; racc.n_regularised += r.n_regularised; racc.n_backtracks += r.n_backtracks;

@@ -101,6 +101,10 @@ void orc_init_cold(const orc_problem* p, const double* x_init, orc_ws* ws);
 void orc_warm_shift(const orc_problem* p, orc_ws* ws);
 /* a12/a11: obstacle + via-point association from the current trajectory */
 void orc_associate(const orc_problem* p, orc_ws* ws);
+/* solver-side initial-guess repair (cold start only): push poses out of violated obstacle rows; seed the controls by
+   inverting the dynamics along the state guess, clipped inside bounds and rate rows */
+void orc_project_init(const orc_problem* p, orc_ws* ws);
+void orc_init_controls(const orc_problem* p, orc_ws* ws);
 void orc_init_duals(const orc_problem* p, orc_ws* ws);
 /* stage functions + derivatives -> KKT records, errors (SCAL[ERR0], SCAL[ERRMU]) */
 void orc_eval(const orc_problem* p, orc_ws* ws);

@@ -1,0 +1,344 @@
+// emu.cpp -- CPU WARP EMULATOR of the device code (TEST INFRASTRUCTURE, not product code).
+//
+// Compiles the SAME host/device headers that the CUDA kernels are made of (mpc_core.h, mpc_stage.h, mpc_riccati.h,
+// mpc_layout.h) with g++ and replays the kernels' warp-level orchestration (lane loops, reductions, passes) serially
+// for ONE instance.  Purpose: `-m "not gpu"` tests can check the device algorithm (stage bodies, Riccati task tables,
+// line search) against the oracle on a box without a GPU.  It is never loaded by the product package; the product
+// path exists only as CUDA kernels (mpcb200.cu) and fails loudly without a GPU.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../mpc_local_planner_b200/csrc/mpc_core.h"
+#include "../../mpc_local_planner_b200/csrc/mpc_riccati.h"
+#include "../../mpc_local_planner_b200/csrc/mpc_stage.h"
+#include "../../mpc_local_planner_b200/csrc/mpc_layout.h"
+
+extern "C" {
+
+long long emu_stride(const Cfg* c)
+{
+    WsLayout L;
+    make_layout(c, MAX_OBST, MAX_VP, L);
+    return (long long)L.stride;
+}
+
+int emu_field_offset(const Cfg* c, int field, int* cnt)
+{
+    WsLayout L;
+    make_layout(c, MAX_OBST, MAX_VP, L);
+    switch (field)
+    {
+        case MPCB200_F_X: *cnt = 3; return L.oX;
+        case MPCB200_F_U: *cnt = 2; return L.oU;
+        case MPCB200_F_NU: *cnt = 3; return L.oNU;
+        case MPCB200_F_S: *cnt = L.RS; return L.oS;
+        case MPCB200_F_LAM: *cnt = L.RS; return L.oLAM;
+        case MPCB200_F_KKT: *cnt = KW; return L.oKKT;
+        case MPCB200_F_STEP: *cnt = 8; return L.oSTEP;
+        case MPCB200_F_SCAL: *cnt = MPCB200_SCAL_WORDS; return L.oSCAL;
+        case MPCB200_F_OBSIDX: *cnt = L.K > 0 ? L.K : 1; return L.oOBS;
+    }
+    return -1;
+}
+
+void emu_scatter(const Cfg* c, double* W, const double* x0, const double* xf, const double* u_prev, int nobst, const int* types,
+                 const double* params, int nvp, const double* vp, const double* x_init, int reinit)
+{
+    WsLayout L;
+    make_layout(c, MAX_OBST, MAX_VP, L);
+    const int N = L.N;
+    (void)N;
+    for (int i = 0; i < 3; ++i) { AIN(IN_X0 + i) = x0[i]; AIN(IN_XF + i) = xf[i]; }
+    for (int i = 0; i < 2; ++i) AIN(IN_UPREV + i) = u_prev ? u_prev[i] : 0.0;
+    AIN(IN_NOBST) = nobst; AIN(IN_NVP) = nvp; AIN(IN_HASXINIT) = x_init ? 1.0 : 0.0; AIN(IN_REINIT) = reinit ? 1.0 : 0.0;
+    for (int i = 0; i < nobst * MPCB200_OBST_STRIDE; ++i) W[L.oOBST + i] = params[i];
+    for (int i = 0; i < nobst; ++i) W[L.oOTYPE + i] = (double)types[i];
+    for (int i = 0; i < nvp * 3; ++i) W[L.oVP + i] = vp[i];
+    if (x_init)
+        for (int i = 0; i < 3 * L.N; ++i) W[L.oXINIT + i] = x_init[i];
+}
+
+void emu_reset(const Cfg* c, double* W)
+{
+    WsLayout L;
+    make_layout(c, MAX_OBST, MAX_VP, L);
+    ASC(MPCB200_SC_COLD) = 1.0;
+    ASC(MPCB200_SC_STATUS) = -1.0;
+}
+
+void emu_init(const Cfg* cp, double* W, int force_cold)
+{
+    const Cfg& c = *cp;
+    WsLayout L;
+    make_layout(cp, MAX_OBST, MAX_VP, L);
+    const int N = L.N;
+    const bool cold = force_cold || ASC(MPCB200_SC_COLD) != 0.0 || AIN(IN_REINIT) != 0.0;
+    if (cold)
+    {
+        for (int k = 0; k < N; ++k) init_cold_stage(c, L, W, k);
+        ASC(MPCB200_SC_DT) = c.dt_ref;
+        ASC(MPCB200_SC_COLD) = 2.0;
+    }
+    else
+    {
+        if (c.warm_start && !c.variable_dt) warm_shift_serial(c, L, W);
+        else
+        {
+            for (int i = 0; i < 3; ++i) AX(i, 0) = AIN(IN_X0 + i);
+            for (int i = 0; i < 3; ++i)
+                if (c.xf_fixed[i]) AX(i, N - 1) = AIN(IN_XF + i);
+        }
+        ASC(MPCB200_SC_COLD) = 0.0;
+    }
+}
+
+void emu_associate(const Cfg* cp, double* W, double uprev_dt, int first_outer)
+{
+    const Cfg& c = *cp;
+    WsLayout L;
+    make_layout(cp, MAX_OBST, MAX_VP, L);
+    const int N = L.N;
+    const bool repair = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
+    for (int k = 0; k < N; ++k) associate_stage(c, L, W, k);
+    if (has_viapoints(c))
+    {
+        const int nvp = (int)AIN(IN_NVP);
+        int start_idx = 0;
+        for (int j = 0; j < nvp && j < L.V; ++j)
+        {
+            const double vx = W[L.oVP + 3 * j], vy = W[L.oVP + 3 * j + 1];
+            double best = 1e300;
+            int bidx = -1;
+            for (int i = start_idx; i < N - 1; ++i)
+            {
+                const double dx = AX(0, i) - vx, dy = AX(1, i) - vy, d = sqrt(dx * dx + dy * dy);
+                if (d < best) { best = d; bidx = i; }
+            }
+            {
+                const double dx = AX(0, N - 1) - vx, dy = AX(1, N - 1) - vy, d = sqrt(dx * dx + dy * dy);
+                if (d < best) { best = d; bidx = N - 1; }
+            }
+            int idx = bidx;
+            if (c.vp_ordered) start_idx = idx + 2;
+            if (idx > N - 2) idx = N - 2;
+            if (idx < 1) idx = c.vp_ordered ? 1 : -1;
+            W[L.oVPST + j] = (double)idx;
+        }
+        for (int j = nvp; j < L.V; ++j) W[L.oVPST + j] = -1.0;
+    }
+    if (repair)
+    {
+        for (int k = 0; k < N; ++k) project_stage(c, L, W, k);
+        for (int k = 0; k < N; ++k) init_controls_stage(c, L, W, k);
+        clip_rates_serial(c, L, W, uprev_dt);
+    }
+    const double mu = c.mu_init > 0 ? c.mu_init : 0.1;
+    for (int k = 0; k < N; ++k) init_duals_stage(c, L, W, uprev_dt, k, mu);
+    ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
+    ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
+    ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0;
+    if (repair) ASC(MPCB200_SC_COLD) = 0.0;
+}
+
+// lanes accumulate their own stages, then a tree reduction in the same xor order as the shuffles
+static void reduce_eval(EvalAcc* a)
+{
+    for (int o = 16; o > 0; o >>= 1)
+        for (int l = 0; l < 32; ++l)
+            if ((l & o) == 0) { EvalAcc t = a[l]; evalacc_merge(t, a[l ^ o]); a[l] = t; a[l ^ o] = t; }
+}
+
+int emu_eval(const Cfg* cp, double* W, double uprev_dt)
+{
+    const Cfg& c = *cp;
+    WsLayout L;
+    make_layout(cp, MAX_OBST, MAX_VP, L);
+    const int N = L.N;
+    if (ASC(MPCB200_SC_STATUS) >= 0.0) return 1;
+    EvalAcc a[32];
+    for (int l = 0; l < 32; ++l)
+    {
+        evalacc_init(a[l]);
+        for (int k = l; k < N; k += 32) eval_stage(c, L, W, uprev_dt, k, a[l]);
+    }
+    reduce_eval(a);
+    int fin = 0;
+    const double mu = eval_finish(c, L, W, a[0], true, &fin);
+    if (fin) return 1;
+    for (int k = 0; k < N; ++k) eval_finalize_stage(L, W, k, mu);
+    return 0;
+}
+
+static int ric_src(int w)
+{
+    if (w < 15) return rP(w / 5, w % 5);
+    if (w < 30) return rPI((w - 15) / 5, (w - 15) % 5);
+    if (w < 40) return R_KG + (w - 30);
+    return R_KT + (w - 40);
+}
+
+int emu_kkt(const Cfg* cp, double* W)
+{
+    const Cfg& c = *cp;
+    WsLayout L;
+    make_layout(cp, MAX_OBST, MAX_VP, L);
+    const int N = L.N;
+    if (ASC(MPCB200_SC_STATUS) >= 0.0) return 1;
+    double* rec = (double*)malloc(sizeof(double) * (KW * N + R_WORDS + 8 * N));
+    double* sm = rec + KW * N;
+    double* stepbuf = sm + R_WORDS;
+    double* ric = W + L.oRIC;
+    for (int i = 0; i < KW * N; ++i) rec[i] = W[L.oKKT + i];
+    for (int i = 0; i < R_WORDS; ++i) sm[i] = 0.0;
+    const double htt = ASC(MPCB200_SC_HTT), gt = ASC(MPCB200_SC_GT), dlast = ASC(MPCB200_SC_DELTA_LAST);
+    const int dt_free = c.variable_dt;
+    RTask tA[32], tB[64], tC[32], tD[64];
+    for (int l = 0; l < 32; ++l) { tA[l] = rtask_A(l); tC[l] = rtask_C(l); }
+    for (int l = 0; l < 64; ++l) { tB[l] = rtask_B(l); tD[l] = rtask_D(l); }
+    double delta = 0.0, th[5];
+    int ok = 0, nreg = 0;
+    for (int tries = 0; tries < 40; ++tries)
+    {
+        for (int idx = 0; idx < 75; ++idx) sm[R_P + idx] = terminal_entry(c, rec, N, idx, delta, htt, gt);
+        int good = 1;
+        for (int k = N - 2; k >= 0; --k)
+        {
+            for (int idx = 0; idx < R_EXP_WORDS; ++idx) sm[R_EXP + idx] = expand_entry(rec, N, k, idx, delta, dt_free);
+            // a pass must be hazard free: emulate "all lanes read, then all lanes write" by double buffering
+            double tmp[R_WORDS];
+            memcpy(tmp, sm, sizeof(tmp));
+            for (int l = 0; l < 32; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tA[l]); if (tA[l].out >= 0) { sm[tA[l].out] = s2[tA[l].out]; if (tA[l].out2 >= 0) sm[tA[l].out2] = s2[tA[l].out2]; } }
+            memcpy(tmp, sm, sizeof(tmp));
+            for (int l = 0; l < 64; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tB[l]); if (tB[l].out >= 0) { sm[tB[l].out] = s2[tB[l].out]; if (tB[l].out2 >= 0) sm[tB[l].out2] = s2[tB[l].out2]; } }
+            double lam4[4];
+            if (!lambda_from_mmvv(sm, lam4)) { good = 0; break; }
+            for (int i = 0; i < 4; ++i) sm[R_LAMB + i] = lam4[i];
+            memcpy(tmp, sm, sizeof(tmp));
+            for (int l = 0; l < 32; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tC[l]); if (tC[l].out >= 0) { sm[tC[l].out] = s2[tC[l].out]; if (tC[l].out2 >= 0) sm[tC[l].out2] = s2[tC[l].out2]; } }
+            for (int w = 0; w < RIC_WORDS; ++w) ric[k * RIC_WORDS + w] = sm[ric_src(w)];
+            memcpy(tmp, sm, sizeof(tmp));
+            for (int l = 0; l < 64; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tD[l]); if (tD[l].out >= 0) { sm[tD[l].out] = s2[tD[l].out]; if (tD[l].out2 >= 0) sm[tD[l].out2] = s2[tD[l].out2]; } }
+        }
+        if (good) good = root_solve(c, sm + R_TH, th);
+        if (good) { ok = 1; break; }
+        ++nreg;
+        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
+        else delta *= (dlast == 0.0 ? 100.0 : 8.0);
+        if (delta > 1e20) break;
+    }
+    if (!ok)
+    {
+        ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;
+        ASC(MPCB200_SC_NREG) += (double)nreg;
+        free(rec);
+        return 1;
+    }
+    double y[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k <= N - 2; ++k)
+    {
+        double a3[3], Bm[6], e[3], d[3], dw[5], nup[3];
+        for (int i = 0; i < 3; ++i) { a3[i] = rec[(MPCB200_K_A + i) * N + k]; e[i] = rec[(MPCB200_K_E + i) * N + k]; d[i] = rec[(MPCB200_K_D + i) * N + k]; }
+        for (int i = 0; i < 6; ++i) Bm[i] = rec[(MPCB200_K_B + i) * N + k];
+        forward_stage(ric + k * RIC_WORDS, a3, Bm, e, d, dt_free, th, y, dw, nup);
+        for (int i = 0; i < 5; ++i) stepbuf[i * N + k] = dw[i];
+        for (int i = 0; i < 3; ++i) stepbuf[(5 + i) * N + k] = nup[i];
+    }
+    for (int i = 0; i < 8; ++i) stepbuf[i * N + (N - 1)] = i < 3 ? y[i] : 0.0;
+    for (int i = 0; i < 8 * N; ++i) W[L.oSTEP + i] = stepbuf[i];
+    ASC(MPCB200_SC_DDT) = th[1];
+    ASC(MPCB200_SC_DELTA) = delta;
+    if (delta > 0.0) ASC(MPCB200_SC_DELTA_LAST) = delta;
+    ASC(MPCB200_SC_NREG) += (double)nreg;
+    free(rec);
+    return 0;
+}
+
+void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
+{
+    const Cfg& c = *cp;
+    WsLayout L;
+    make_layout(cp, MAX_OBST, MAX_VP, L);
+    const int N = L.N;
+    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    LsAcc a;
+    lsacc_init(a);
+    for (int l = 0; l < 32; ++l)
+    {
+        LsAcc t;
+        lsacc_init(t);
+        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, uprev_dt, k, t);
+        a.a_p = fmin(a.a_p, t.a_p); a.a_d = fmin(a.a_d, t.a_d);
+        a.dphi_bar += t.dphi_bar; a.curv += t.curv; a.dJ += t.dJ;
+    }
+    const double mu = ASC(MPCB200_SC_MU), inf1 = ASC(MPCB200_SC_INF), obj = ASC(MPCB200_SC_OBJ), blog = ASC(MPCB200_SC_BLOG);
+    const double ddt = ASC(MPCB200_SC_DDT), dt = ASC(MPCB200_SC_DT);
+    double rho = 1.0;
+    {
+        const double num = a.dJ + a.dphi_bar + 0.5 * (a.curv > 0 ? a.curv : 0.0);
+        if (inf1 > 1e-14)
+        {
+            const double rho_trial = num / ((1.0 - 0.1) * inf1);
+            if (rho < rho_trial) rho = rho_trial + 1.0;
+        }
+    }
+    const double phi0 = obj - mu * blog + rho * inf1;
+    const double dphi = a.dJ + a.dphi_bar - rho * inf1;
+    double alpha = a.a_p;
+    int nbt = 0;
+    for (int bt = 0; bt < MAX_BACKTRACK; ++bt)
+    {
+        TrialAcc t;
+        t.obj = t.inf1 = t.blog = 0.0;
+        for (int k = 0; k < N; ++k) ls_stage_trial(c, L, W, uprev_dt, k, alpha, t);
+        const double phi = t.obj - mu * t.blog + rho * t.inf1;
+        if (phi <= phi0 + ARMIJO * alpha * dphi || (bt > 0 && fabs(phi - phi0) <= 1e-13 * (1.0 + fabs(phi0)))) break;
+        alpha *= 0.5;
+        ++nbt;
+    }
+    const double a_dual = a.a_d > alpha ? alpha : a.a_d;
+    for (int k = 0; k < N; ++k) ls_stage_update(c, L, W, uprev_dt, k, alpha, a_dual);
+    if (c.variable_dt) ASC(MPCB200_SC_DT) = dt + alpha * ddt;
+    ASC(MPCB200_SC_ALPHA) = alpha;
+    ASC(MPCB200_SC_RHO) = rho;
+    ASC(MPCB200_SC_ITER) += 1.0;
+    ASC(MPCB200_SC_NBT) += (double)nbt;
+}
+
+// whole Controller::step of one instance, same launch sequence as solve_device() in mpcb200.cu
+int emu_solve(const Cfg* cp, double* W, double uprev_dt, int force_cold)
+{
+    const Cfg& c = *cp;
+    WsLayout L;
+    make_layout(cp, MAX_OBST, MAX_VP, L);
+    emu_init(cp, W, force_cold);
+    const int outer = c.outer_iterations > 0 ? c.outer_iterations : 1;
+    for (int oi = 0; oi < outer; ++oi)
+    {
+        emu_associate(cp, W, uprev_dt, oi == 0);
+        for (int it = 0; it <= c.max_iter; ++it)
+        {
+            if (emu_eval(cp, W, uprev_dt)) break;
+            if (it == c.max_iter) break;
+            if (emu_kkt(cp, W)) break;
+            emu_linesearch(cp, W, uprev_dt);
+        }
+    }
+    const double st = ASC(MPCB200_SC_STATUS);
+    return st < 0 ? MPCB200_STATUS_MAX_ITER : (int)st;
+}
+
+void emu_outputs(const Cfg* cp, const double* W, double* u_seq, double* x_seq)
+{
+    WsLayout L;
+    make_layout(cp, MAX_OBST, MAX_VP, L);
+    const int N = L.N;
+    for (int k = 0; k < N; ++k)
+    {
+        const int kk = k <= N - 2 ? k : N - 2;
+        u_seq[2 * k] = AU(0, kk); u_seq[2 * k + 1] = AU(1, kk);
+        x_seq[3 * k] = AX(0, k); x_seq[3 * k + 1] = AX(1, k); x_seq[3 * k + 2] = normalize_theta(AX(2, k));
+    }
+}
+
+}  // extern "C"
