@@ -186,6 +186,11 @@ int mpcb200_fetch_results(mpcb200_handle* h, double* u_seq, double* x_seq, doubl
                           double* kkt_err, int* iters);
 /* Device pointer of the packed optimal controls [B][N-1][2] (for the NCCL all-gather of u*) and its size. */
 int mpcb200_device_controls(mpcb200_handle* h, void** dev_ptr, long long* n_doubles);
+/* Device-to-device copy of the packed optimal controls into a caller-owned device buffer (e.g. the send buffer of the
+   NCCL all-gather).  dst must hold B*(N-1)*2 doubles on the handle's device. */
+int mpcb200_export_controls(mpcb200_handle* h, void* dst_dev);
+/* Evict the L2 cache (writes a 320 MB scratch buffer); used between timed launches by the benchmark. */
+int mpcb200_flush_l2(mpcb200_handle* h);
 
 /* ---- kernel-level access: parity tests and the roofline measurement ------------------------------------ */
 
@@ -232,6 +237,7 @@ int mpcb200_device_controls(mpcb200_handle* h, void** dev_ptr, long long* n_doub
 #define MPCB200_SC_GLDT 17   /* dL/d(dt) */
 #define MPCB200_SC_NBT 18    /* line-search backtracks so far */
 #define MPCB200_SC_COLD 19   /* 1 until the instance has been solved once (cold start pending) */
+#define MPCB200_SC_TINY 20   /* consecutive iterations with a step length below 1e-8 (2 => the instance is given up) */
 
 int mpcb200_ws_count(const mpcb200_handle* h, int field);  /* number of components of a field (e.g. RS) */
 int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst);        /* dst: [B][count][N] (SCAL: [B][24]) */
@@ -254,6 +260,8 @@ typedef struct mpcb200_stats {
     double ms[MPCB200_NUM_PHASES];
     long long launches_total;
     long long h2d_bytes, d2h_bytes;
+    long long kkt_instances; /* number of (instance, launch) pairs the KKT kernel actually factorised */
+    long long kkt_sweeps;    /* backward sweeps incl. inertia-correction refactorisations */
 } mpcb200_stats;
 int mpcb200_stats_get(const mpcb200_handle* h, mpcb200_stats* out);
 int mpcb200_stats_reset(mpcb200_handle* h);

@@ -31,7 +31,7 @@ PHASE_INIT, PHASE_ASSOCIATE, PHASE_EVAL, PHASE_KKT, PHASE_LINESEARCH = range(5)
 NUM_PHASES = 5
 K_H, K_G, K_A, K_B, K_E, K_C, K_HB, K_D = 0, 15, 20, 23, 29, 32, 34, 39
 (SC_DT, SC_MU, SC_RHO, SC_DELTA, SC_HTT, SC_GT, SC_DDT, SC_ERR0, SC_ERRMU, SC_ITER, SC_STATUS, SC_ALPHA, SC_OBJ,
- SC_INF, SC_DELTA_LAST, SC_NREG, SC_BLOG, SC_GLDT, SC_NBT, SC_COLD) = range(20)
+ SC_INF, SC_DELTA_LAST, SC_NREG, SC_BLOG, SC_GLDT, SC_NBT, SC_COLD, SC_TINY) = range(21)
 
 
 class Config(C.Structure):
@@ -93,7 +93,8 @@ class ViaPoints(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("launches", C.c_longlong * NUM_PHASES), ("ms", C.c_double * NUM_PHASES),
-                ("launches_total", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+                ("launches_total", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
+                ("kkt_instances", C.c_longlong), ("kkt_sweeps", C.c_longlong)]
 
 
 def default_config():
@@ -159,7 +160,7 @@ EXPORTS = [
     "mpcb200_default_config", "mpcb200_create", "mpcb200_step_batch", "mpcb200_reset", "mpcb200_destroy",
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
-    "mpcb200_time_phase", "mpcb200_stats_get", "mpcb200_stats_reset",
+    "mpcb200_time_phase", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
 ]
 
 
@@ -191,6 +192,8 @@ def load_library(path=None):
     lib.mpcb200_solve_resident.argtypes = [vp, C.c_int, dp]
     lib.mpcb200_fetch_results.argtypes = [vp, dp, dp, dp, ip, dp, ip]
     lib.mpcb200_device_controls.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
+    lib.mpcb200_export_controls.argtypes = [vp, vp]
+    lib.mpcb200_flush_l2.argtypes = [vp]
     lib.mpcb200_ws_count.argtypes = [vp, C.c_int]
     lib.mpcb200_ws_read.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.mpcb200_ws_write.argtypes = [vp, C.c_int, C.c_int, dp]
@@ -336,10 +339,17 @@ class BatchSolver:
         s = Stats()
         self._check(self.lib.mpcb200_stats_get(self.h, C.byref(s)), "mpcb200_stats_get")
         return dict(launches=list(s.launches), ms=list(s.ms), launches_total=s.launches_total,
-                    h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes)
+                    h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes, kkt_instances=s.kkt_instances,
+                    kkt_sweeps=s.kkt_sweeps)
 
     def stats_reset(self):
         self._check(self.lib.mpcb200_stats_reset(self.h), "mpcb200_stats_reset")
+
+    def export_controls(self, dst_dev_ptr):
+        self._check(self.lib.mpcb200_export_controls(self.h, C.c_void_p(int(dst_dev_ptr))), "mpcb200_export_controls")
+
+    def flush_l2(self):
+        self._check(self.lib.mpcb200_flush_l2(self.h), "mpcb200_flush_l2")
 
     def device_controls(self):
         p = C.c_void_p()

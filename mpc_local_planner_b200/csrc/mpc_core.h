@@ -50,7 +50,11 @@ struct WsLayout
 #define TAU_MIN 0.99
 #define SLACK_PUSH 1e-2
 #define ARMIJO 1e-4
-#define MAX_BACKTRACK 30
+#define MAX_BACKTRACK 8
+#define MAX_INERTIA_TRIES 12
+#define MAX_DELTA 1e8
+#define TINY_STEP 1e-8
+#define TINY_STEP_COUNT 2
 #define KAPPA_SIGMA 1e10
 #define SMAX 100.0
 #define PROJ_MARGIN 0.05

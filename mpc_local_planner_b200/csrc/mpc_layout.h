@@ -1,7 +1,7 @@
 // mpc_layout.h -- workspace layout of one OCP instance (shared by the CUDA library and the test-only CPU warp emulator)
 #pragma once
 #include "mpc_core.h"
-#include "mpc_riccati.h"
+#include "mpc_riccati_lane.h"
 
 #define MAX_OBST 64
 #define MAX_VP 8
@@ -16,11 +16,11 @@ static inline void make_layout(const mpcb200_config* c, int M, int V, WsLayout& 
     L.oIN = take(IN_WORDS);
     L.oX = take(3 * N); L.oU = take(2 * N); L.oNU = take(3 * N);
     L.oS = take(L.RS * N); L.oLAM = take(L.RS * N);
-    L.oKKT = take(KW * N); L.oSTEP = take(8 * N);
+    L.oKKT = -1; L.oSTEP = take(8 * N);  /* KKT records and Riccati gains live in 32-instance interleaved tiles */
     L.oOBS = take((L.K > 0 ? L.K : 1) * N);
     L.oDS = take(L.RS * N); L.oDLAM = take(L.RS * N);
-    L.ricw = RIC_WORDS;
-    L.oRIC = take(RIC_WORDS * N);
+    L.ricw = RICW_MAX;
+    L.oRIC = -1;
     L.oVPST = take(V > 0 ? V : 1);
     L.oOBST = take((M > 0 ? M : 1) * MPCB200_OBST_STRIDE);
     L.oOTYPE = take(M > 0 ? M : 1);

@@ -18,7 +18,7 @@
 #define ANU(c_, k_) W[L.oNU + (c_) * N + (k_)]
 #define AS(c_, k_) W[L.oS + (c_) * N + (k_)]
 #define ALAM(c_, k_) W[L.oLAM + (c_) * N + (k_)]
-#define AKKT(c_, k_) W[L.oKKT + (c_) * N + (k_)]
+#define AKKT(c_, k_) Kb[((size_t)(k_) * KW + (c_)) * 32]  /* 32-instance interleaved tile; Kb = tile base + slot of this instance */
 #define ASTEP(c_, k_) W[L.oSTEP + (c_) * N + (k_)]
 #define AOBS(c_, k_) W[L.oOBS + (c_) * N + (k_)]
 #define ADS(c_, k_) W[L.oDS + (c_) * N + (k_)]
@@ -63,7 +63,7 @@ HD inline void row_stats(EvalAcc& acc, double r, double s, double lam)
 
 // Stage functions + derivatives of stage k -> condensed KKT record (G holds the mu-independent part g0, the
 // coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
-HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int k, EvalAcc& acc)
+HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb, double uprev_dt, int k, EvalAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT);
@@ -316,7 +316,7 @@ HD inline double eval_finish(const Cfg& c, const WsLayout& L, double* W, const E
     *finished = fin;
     return mu;
 }
-HD inline void eval_finalize_stage(const WsLayout& L, double* W, int k, double mu)
+HD inline void eval_finalize_stage(const WsLayout& L, double* W, double* Kb, int k, double mu)
 {
     const int N = L.N;
 #pragma unroll
@@ -334,7 +334,7 @@ struct LsAcc
 HD inline void lsacc_init(LsAcc& a) { a.a_p = 1.0; a.a_d = 1.0; a.dphi_bar = a.curv = a.dJ = 0.0; }
 
 // slack / multiplier steps of the rows owned by stage k, fraction to the boundary, directional derivatives
-HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int k, LsAcc& acc)
+HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const double* Kb, double uprev_dt, int k, LsAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT), mu = ASC(MPCB200_SC_MU), ddt = ASC(MPCB200_SC_DDT);

@@ -3,8 +3,9 @@
 // One warp owns one OCP instance.  The instance's working set is one contiguous, 128-byte aligned block in HBM in
 // which every array is laid out [component][stage] (stage fastest): in the stage-parallel phases (EVAL, LINESEARCH,
 // INIT, ASSOCIATE) lane l handles stages l, l+32, ... so that the 32 lanes touch consecutive addresses; in the
-// sequential KKT phase the warp first stages the instance's condensed KKT records through shared memory with
-// coalesced loads and then runs the Riccati sweep out of shared memory (mpc_riccati.h).
+// sequential KKT phase ONE LANE owns one instance (mpc_riccati_lane.h): the condensed KKT stage records and the
+// Riccati gains live in 32-instance interleaved tiles so that the 32 lanes of a warp, sweeping 32 instances in
+// lock-step, touch 256 consecutive bytes per access.
 //
 // This file is the ONLY implementation of the hot path: there is no CPU fallback.  Every entry point fails with
 // MPCB200_E_NODEVICE / MPCB200_E_CUDA when no CUDA device is usable.
@@ -17,7 +18,7 @@
 #include <vector>
 
 #include "mpc_core.h"
-#include "mpc_riccati.h"
+#include "mpc_riccati_lane.h"
 #include "mpc_stage.h"
 #include "mpc_layout.h"
 
@@ -171,22 +172,23 @@ __global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double up
     {
         ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
         ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
-        ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0;
+        ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0;
         if (repair) ASC(MPCB200_SC_COLD) = 0.0;
     }
 }
 
 // ---- kernel: PHASE_EVAL -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) eval_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt, int* n_active)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, int B, double uprev_dt, int* n_active)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;  // finished instance: exact no-op
+    double* Kb = kkt_tiles + (size_t)(warp >> 5) * N * KW * TILE + (warp & 31);
     EvalAcc a;
     evalacc_init(a);
-    for (int k = lane; k < N; k += 32) eval_stage(c, L, W, uprev_dt, k, a);
+    for (int k = lane; k < N; k += 32) eval_stage(c, L, W, Kb, uprev_dt, k, a);
     a.dual_inf = warp_max(a.dual_inf); a.prim_inf = warp_max(a.prim_inf);
     a.sl_max = warp_max(a.sl_max); a.sl_min = warp_min(a.sl_min);
     a.sum_nu = warp_sum(a.sum_nu); a.sum_lam = warp_sum(a.sum_lam); a.inf1 = warp_sum(a.inf1); a.blog = warp_sum(a.blog);
@@ -199,125 +201,56 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) eval_kernel(Cfg c, WsLayou
     fin = __shfl_sync(FULLMASK, fin, 0);
     if (fin) return;
     if (lane == 0 && n_active) atomicAdd(n_active, 1);
-    for (int k = lane; k < N; k += 32) eval_finalize_stage(L, W, k, mu);
+    for (int k = lane; k < N; k += 32) eval_finalize_stage(L, W, Kb, k, mu);
 }
 
-// ---- kernel: PHASE_KKT -- Riccati factorisation + solve with inertia-correcting regularisation --------------
-__device__ __forceinline__ int ric_src(int w)
+// ---- kernel: PHASE_KKT -- Riccati factorisation + solve, ONE LANE PER INSTANCE ------------------------------------
+// warp w handles the instances of tile w (32 consecutive instances); every record / gain access is one coalesced
+// 256-byte transaction across the warp.  Lanes whose instance is finished (or beyond B) idle.
+struct StepOut
 {
-    if (w < 15) return rP(w / 5, w % 5);
-    if (w < 30) return rPI((w - 15) / 5, (w - 15) % 5);
-    if (w < 40) return R_KG + (w - 30);
-    return R_KT + (w - 40);
-}
+    double* W; int oSTEP; int N;
+    __device__ void operator()(int k, int c, double v) const { W[oSTEP + c * N + k] = v; }
+};
 
-__global__ void kkt_kernel(Cfg c, WsLayout L, double* ws, int B, int warps_per_cta)
+template <bool EXT>
+__global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, double* ric_tiles, int B,
+                                                       unsigned long long* counters)
 {
-    extern __shared__ double smem[];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warp = blockIdx.x * warps_per_cta + wib;
-    if (warp >= B) return;
-    double* W = ws + (int64_t)warp * L.stride;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int b = tile * TILE + lane;
+    if (b >= B) return;
+    double* W = ws + (int64_t)b * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
-    const int per_warp = KW * N + R_WORDS + 8 * N;
-    double* rec = smem + (size_t)wib * per_warp;  // [42][N]
-    double* sm = rec + KW * N;                    // Riccati scratch
-    double* stepbuf = sm + R_WORDS;               // [8][N]
-    double* ric = W + L.oRIC;                     // [N][50] gains (global scratch, L2 resident)
-    // stage the instance's KKT records through shared memory (coalesced, stage-contiguous)
-    for (int i = lane; i < KW * N; i += 32) rec[i] = W[L.oKKT + i];
-    if (lane < 4) sm[R_ZERO + lane] = 0.0;
-    const double htt = ASC(MPCB200_SC_HTT), gt = ASC(MPCB200_SC_GT);
-    const double dlast = ASC(MPCB200_SC_DELTA_LAST);
-    const int dt_free = c.variable_dt;
-    // per-lane task tables (registers)
-    const RTask tA = rtask_A(lane), tB0 = rtask_B(lane), tB1 = rtask_B(lane + 32), tC = rtask_C(lane);
-    const RTask tD0 = rtask_D(lane), tD1 = rtask_D(lane + 32);
-    __syncwarp();
-    double delta = 0.0;
-    double th[5];
-    int ok = 0, nreg = 0;
-    for (int tries = 0; tries < 40; ++tries)
-    {
-        // ---- backward sweep ----
-        for (int idx = lane; idx < 75; idx += 32) sm[R_P + idx] = terminal_entry(c, rec, N, idx, delta, htt, gt);
-        __syncwarp();
-        int good = 1;
-        for (int k = N - 2; k >= 0; --k)
-        {
-            for (int idx = lane; idx < R_EXP_WORDS; idx += 32) sm[R_EXP + idx] = expand_entry(rec, N, k, idx, delta, dt_free);
-            __syncwarp();
-            run_task(sm, tA);
-            __syncwarp();
-            run_task(sm, tB0);
-            run_task(sm, tB1);
-            __syncwarp();
-            double lam4[4];
-            if (!lambda_from_mmvv(sm, lam4)) { good = 0; break; }  // warp-uniform: every lane reads the same values
-            if (lane < 4) sm[R_LAMB + lane] = lam4[lane];
-            __syncwarp();
-            run_task(sm, tC);
-            __syncwarp();
-            for (int w = lane; w < RIC_WORDS; w += 32) ric[k * RIC_WORDS + w] = sm[ric_src(w)];
-            __syncwarp();
-            run_task(sm, tD0);
-            run_task(sm, tD1);
-            __syncwarp();
-        }
-        if (good) good = root_solve(c, sm + R_TH, th);
-        if (good) { ok = 1; break; }
-        ++nreg;
-        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
-        else delta *= (dlast == 0.0 ? 100.0 : 8.0);
-        if (delta > 1e20) break;
-        __syncwarp();
-    }
-    if (!ok)
-    {
-        if (lane == 0) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; ASC(MPCB200_SC_NREG) += (double)nreg; }
-        return;
-    }
-    __syncwarp();
-    // ---- forward substitution (every lane carries the recursion; lanes 0..7 record the step) ----
-    double y[5] = {0, 0, 0, 0, 0};
-    for (int k = 0; k <= N - 2; ++k)
-    {
-        double a3[3], Bm[6], e[3], d[3], dw[5], nup[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { a3[i] = rec[(MPCB200_K_A + i) * N + k]; e[i] = rec[(MPCB200_K_E + i) * N + k]; d[i] = rec[(MPCB200_K_D + i) * N + k]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Bm[i] = rec[(MPCB200_K_B + i) * N + k];
-        forward_stage(ric + k * RIC_WORDS, a3, Bm, e, d, dt_free, th, y, dw, nup);
-        double outv = dw[0];
-        outv = lane == 1 ? dw[1] : outv; outv = lane == 2 ? dw[2] : outv; outv = lane == 3 ? dw[3] : outv;
-        outv = lane == 4 ? dw[4] : outv; outv = lane == 5 ? nup[0] : outv; outv = lane == 6 ? nup[1] : outv;
-        outv = lane == 7 ? nup[2] : outv;
-        if (lane < 8) stepbuf[lane * N + k] = outv;
-    }
-    if (lane < 8) stepbuf[lane * N + (N - 1)] = lane < 3 ? (lane == 0 ? y[0] : (lane == 1 ? y[1] : y[2])) : 0.0;
-    __syncwarp();
-    for (int i = lane; i < 8 * N; i += 32) W[L.oSTEP + i] = stepbuf[i];
-    if (lane == 0)
-    {
-        ASC(MPCB200_SC_DDT) = th[1];
-        ASC(MPCB200_SC_DELTA) = delta;
-        if (delta > 0.0) ASC(MPCB200_SC_DELTA_LAST) = delta;
-        ASC(MPCB200_SC_NREG) += (double)nreg;
-    }
+    TileRec rec{kkt_tiles + (size_t)tile * N * KW * TILE + lane};
+    TileRic ric{ric_tiles + (size_t)tile * N * RICW_MAX * TILE + lane};
+    StepOut step{W, L.oSTEP, N};
+    double ddt = 0.0, delta = 0.0;
+    int nreg = 0;
+    const int ok = riccati_solve_lane<EXT>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST),
+                                           &ddt, &delta, &nreg);
+    if (counters) { atomicAdd(counters, 1ull); atomicAdd(counters + 1, (unsigned long long)(nreg + 1)); }
+    ASC(MPCB200_SC_NREG) += (double)nreg;
+    if (!ok) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; return; }
+    ASC(MPCB200_SC_DDT) = ddt;
+    ASC(MPCB200_SC_DELTA) = delta;
+    if (delta > 0.0) ASC(MPCB200_SC_DELTA_LAST) = delta;
 }
 
 // ---- kernel: PHASE_LINESEARCH -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, int B, double uprev_dt)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    const double* Kb = kkt_tiles + (size_t)(warp >> 5) * N * KW * TILE + (warp & 31);
     LsAcc a;
     lsacc_init(a);
-    for (int k = lane; k < N; k += 32) ls_stage_steps(c, L, W, uprev_dt, k, a);
+    for (int k = lane; k < N; k += 32) ls_stage_steps(c, L, W, Kb, uprev_dt, k, a);
     a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
     a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
     const double mu = ASC(MPCB200_SC_MU), inf1 = ASC(MPCB200_SC_INF), obj = ASC(MPCB200_SC_OBJ), blog = ASC(MPCB200_SC_BLOG);
@@ -358,6 +291,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, W
         ASC(MPCB200_SC_RHO) = rho;
         ASC(MPCB200_SC_ITER) += 1.0;
         ASC(MPCB200_SC_NBT) += (double)nbt;
+        const double tiny = alpha < TINY_STEP ? ASC(MPCB200_SC_TINY) + 1.0 : 0.0;
+        ASC(MPCB200_SC_TINY) = tiny;
+        if (tiny >= (double)TINY_STEP_COUNT) ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;  /* jammed: give up */
     }
 }
 
@@ -418,6 +354,7 @@ struct mpcb200_handle
     WsLayout L;
     int max_batch, device, B;
     double* ws;
+    double *kkt_tiles, *ric_tiles;
     cudaStream_t stream;
     // compact device input / output staging
     double *d_x0, *d_xf, *d_uprev, *d_obst, *d_vp, *d_xinit;
@@ -425,11 +362,11 @@ struct mpcb200_handle
     unsigned char* d_reinit;
     double *d_useq, *d_xseq, *d_dt, *d_kkt, *d_upacked;
     int *d_status, *d_iters, *d_nactive;
+    unsigned long long* d_counters;
     int* h_nactive;  // pinned
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
     double uprev_dt;
-    int kkt_wpc; size_t kkt_smem;
     mpcb200_stats stats;
     std::vector<cudaEvent_t> ev;  // pool of event pairs
     std::vector<int> ev_phase;
@@ -503,7 +440,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
         return set_err(nullptr, MPCB200_E_NODEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) + "): this solver has no CPU fallback");
     if (device < 0 || device >= ndev) return set_err(nullptr, MPCB200_E_INVALID, "device index out of range");
     h = new mpcb200_handle();
-    h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->ev_used = 0;
+    h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->kkt_tiles = nullptr; h->ric_tiles = nullptr; h->ev_used = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
     h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0;
@@ -517,6 +454,13 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     const size_t B = (size_t)max_batch, N = (size_t)cfg->n;
     CKC(cudaMalloc(&h->ws, B * h->L.stride * sizeof(double)));
     CKC(cudaMemsetAsync(h->ws, 0, B * h->L.stride * sizeof(double), h->stream));
+    {
+        const size_t ntiles = (B + TILE - 1) / TILE;
+        CKC(cudaMalloc(&h->kkt_tiles, ntiles * N * KW * TILE * sizeof(double)));
+        CKC(cudaMalloc(&h->ric_tiles, ntiles * N * RICW_MAX * TILE * sizeof(double)));
+        CKC(cudaMemsetAsync(h->kkt_tiles, 0, ntiles * N * KW * TILE * sizeof(double), h->stream));
+        CKC(cudaMemsetAsync(h->ric_tiles, 0, ntiles * N * RICW_MAX * TILE * sizeof(double), h->stream));
+    }
     CKC(cudaMalloc(&h->d_x0, B * 3 * 8)); CKC(cudaMalloc(&h->d_xf, B * 3 * 8)); CKC(cudaMalloc(&h->d_uprev, B * 2 * 8));
     CKC(cudaMalloc(&h->d_obst, B * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CKC(cudaMalloc(&h->d_obst_count, B * 4));
     CKC(cudaMalloc(&h->d_obst_type, B * MAX_OBST * 4));
@@ -525,19 +469,11 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
     CKC(cudaMalloc(&h->d_kkt, B * 8)); CKC(cudaMalloc(&h->d_upacked, B * (N - 1) * 2 * 8));
     CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 4));
+    CKC(cudaMalloc(&h->d_counters, 16)); CKC(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
     CKC(cudaMallocHost(&h->h_nactive, 4));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
     CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
     CKC(cudaMemsetAsync(h->d_flush, 0, h->flush_n * 8, h->stream));
-    // KKT kernel: shared memory per warp = records + scratch + step buffer
-    {
-        const size_t per_warp = ((size_t)KW * N + R_WORDS + 8 * N) * sizeof(double);
-        int wpc = (int)((200 * 1024) / per_warp);
-        if (wpc < 1) { delete h; return set_err(nullptr, MPCB200_E_UNSUPPORTED, "horizon too long for the shared-memory staged KKT kernel"); }
-        if (wpc > WARPS_PER_CTA) wpc = WARPS_PER_CTA;
-        h->kkt_wpc = wpc; h->kkt_smem = per_warp * wpc;
-        CKC(cudaFuncSetAttribute(kkt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->kkt_smem));
-    }
     {
         // all instances start cold
         reset_kernel<<<(max_batch + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, max_batch, nullptr);
@@ -553,8 +489,8 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->ws, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
-                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush};
+    void* ptrs[] = {h->ws, h->kkt_tiles, h->ric_tiles, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
+                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush, h->d_counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
@@ -605,9 +541,16 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
     {
         case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold); break;
         case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer); break;
-        case MPCB200_PHASE_EVAL: eval_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, h->d_nactive); break;
-        case MPCB200_PHASE_KKT: kkt_kernel<<<grid_for(B, h->kkt_wpc), h->kkt_wpc * 32, h->kkt_smem, h->stream>>>(h->cfg, h->L, h->ws, B, h->kkt_wpc); break;
-        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt); break;
+        case MPCB200_PHASE_EVAL: eval_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, B, h->uprev_dt, h->d_nactive); break;
+        case MPCB200_PHASE_KKT:
+        {
+            const bool ext = h->cfg.variable_dt || h->cfg.xf_fixed[0] || h->cfg.xf_fixed[1] || h->cfg.xf_fixed[2];
+            const int ntiles = (B + TILE - 1) / TILE;
+            if (ext) kkt_lane_kernel<true><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, B, h->d_counters);
+            else kkt_lane_kernel<false><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, B, h->d_counters);
+            break;
+        }
+        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, B, h->uprev_dt); break;
         default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
     }
     if (timed) ev_end(h);
@@ -798,7 +741,7 @@ static int field_info(const mpcb200_handle* h, int field, int* off, int* cnt)
         case MPCB200_F_NU: *off = L.oNU; *cnt = 3; return 0;
         case MPCB200_F_S: *off = L.oS; *cnt = L.RS; return 0;
         case MPCB200_F_LAM: *off = L.oLAM; *cnt = L.RS; return 0;
-        case MPCB200_F_KKT: *off = L.oKKT; *cnt = KW; return 0;
+        case MPCB200_F_KKT: *off = 0; *cnt = KW; return 0;
         case MPCB200_F_STEP: *off = L.oSTEP; *cnt = 8; return 0;
         case MPCB200_F_SCAL: *off = L.oSCAL; *cnt = MPCB200_SCAL_WORDS; return 0;
         case MPCB200_F_OBSIDX: *off = L.oOBS; *cnt = L.K > 0 ? L.K : 1; return 0;
@@ -819,7 +762,20 @@ extern "C" int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst)
     if (rc) return rc;
     if (!dst || field_info(h, field, &off, &cnt)) return set_err(h, MPCB200_E_INVALID, "bad field");
     CK(cudaSetDevice(h->device));
-    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * h->L.N;
+    const int N = h->L.N;
+    if (field == MPCB200_F_KKT)
+    {   // device layout: 32-instance interleaved tiles [tile][k][42][32]; the API presents [B][42][N]
+        const size_t ntiles = ((size_t)B + TILE - 1) / TILE, tw = (size_t)N * KW * TILE;
+        std::vector<double> tmp(ntiles * tw);
+        CK(cudaMemcpyAsync(tmp.data(), h->kkt_tiles, tmp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int b = 0; b < B; ++b)
+            for (int k = 0; k < N; ++k)
+                for (int f = 0; f < KW; ++f)
+                    dst[((size_t)b * KW + f) * N + k] = tmp[(size_t)(b / TILE) * tw + ((size_t)k * KW + f) * TILE + (b % TILE)];
+        return 0;
+    }
+    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * N;
     CK(cudaMemcpy2DAsync(dst, words * 8, h->ws + off, (size_t)h->L.stride * 8, words * 8, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -831,7 +787,20 @@ extern "C" int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const doubl
     if (rc) return rc;
     if (!src || field_info(h, field, &off, &cnt)) return set_err(h, MPCB200_E_INVALID, "bad field");
     CK(cudaSetDevice(h->device));
-    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * h->L.N;
+    const int N = h->L.N;
+    if (field == MPCB200_F_KKT)
+    {
+        const size_t ntiles = ((size_t)B + TILE - 1) / TILE, tw = (size_t)N * KW * TILE;
+        std::vector<double> tmp(ntiles * tw, 0.0);
+        for (int b = 0; b < B; ++b)
+            for (int k = 0; k < N; ++k)
+                for (int f = 0; f < KW; ++f)
+                    tmp[(size_t)(b / TILE) * tw + ((size_t)k * KW + f) * TILE + (b % TILE)] = src[((size_t)b * KW + f) * N + k];
+        CK(cudaMemcpyAsync(h->kkt_tiles, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * N;
     CK(cudaMemcpy2DAsync(h->ws + off, (size_t)h->L.stride * 8, src, words * 8, words * 8, (size_t)B, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -873,9 +842,16 @@ extern "C" int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps,
     return 0;
 }
 
-extern "C" int mpcb200_stats_get(const mpcb200_handle* h, mpcb200_stats* out)
+extern "C" int mpcb200_stats_get(const mpcb200_handle* hc, mpcb200_stats* out)
 {
+    mpcb200_handle* h = const_cast<mpcb200_handle*>(hc);
     if (!h || !out) return MPCB200_E_INVALID;
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(cnt, h->d_counters, 16, cudaMemcpyDeviceToHost));
+    h->stats.kkt_instances = (long long)cnt[0];
+    h->stats.kkt_sweeps = (long long)cnt[1];
     *out = h->stats;
     return 0;
 }
@@ -883,5 +859,25 @@ extern "C" int mpcb200_stats_reset(mpcb200_handle* h)
 {
     if (!h) return MPCB200_E_INVALID;
     memset(&h->stats, 0, sizeof(h->stats));
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int mpcb200_export_controls(mpcb200_handle* h, void* dst_dev)
+{
+    if (!h || h->B < 1 || !dst_dev) return set_err(h, MPCB200_E_INVALID, "nothing to export");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(dst_dev, h->d_upacked, (size_t)h->B * (h->cfg.n - 1) * 16, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int mpcb200_flush_l2(mpcb200_handle* h)
+{
+    if (!h) return MPCB200_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    flush_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -2,8 +2,6 @@ import sys, time, json; sys.path.insert(0,'.')
 import numpy as np
 from mpc_local_planner_b200 import capi, configs
 from oracle import oracle_py as orc
-import __graft_entry__ as g
-g.smoke()
 for cid,B,tol in ((2,1024,1e-6),(2,4096,1e-6),(3,1024,1e-6),(4,2048,1e-6)):
     cfg=configs.config_for(cid,tol=tol); data=configs.generate(cid,B)
     s=capi.BatchSolver(cfg,B)

@@ -1,6 +1,6 @@
 // emu.cpp -- CPU WARP EMULATOR of the device code (TEST INFRASTRUCTURE, not product code).
 //
-// Compiles the SAME host/device headers that the CUDA kernels are made of (mpc_core.h, mpc_stage.h, mpc_riccati.h,
+// Compiles the SAME host/device headers that the CUDA kernels are made of (mpc_core.h, mpc_stage.h, mpc_riccati_lane.h,
 // mpc_layout.h) with g++ and replays the kernels' warp-level orchestration (lane loops, reductions, passes) serially
 // for ONE instance.  Purpose: `-m "not gpu"` tests can check the device algorithm (stage bodies, Riccati task tables,
 // line search) against the oracle on a box without a GPU.  It is never loaded by the product package; the product
@@ -10,17 +10,22 @@
 #include <string.h>
 
 #include "../../mpc_local_planner_b200/csrc/mpc_core.h"
-#include "../../mpc_local_planner_b200/csrc/mpc_riccati.h"
+#include "../../mpc_local_planner_b200/csrc/mpc_riccati_lane.h"
 #include "../../mpc_local_planner_b200/csrc/mpc_stage.h"
 #include "../../mpc_local_planner_b200/csrc/mpc_layout.h"
 
+#define EMU_SLOT 5  /* the emulated instance sits in lane slot 5 of its tile (catches tile-indexing bugs) */
+static inline double* emu_kb(const WsLayout& L, double* W) { return W + L.stride + EMU_SLOT; }
+static inline double* emu_rb(const WsLayout& L, double* W) { return W + L.stride + (size_t)L.N * KW * TILE + EMU_SLOT; }
+
 extern "C" {
 
+// words of the emulator buffer: instance block + one KKT tile + one gains tile
 long long emu_stride(const Cfg* c)
 {
     WsLayout L;
     make_layout(c, MAX_OBST, MAX_VP, L);
-    return (long long)L.stride;
+    return (long long)L.stride + (long long)L.N * KW * TILE + (long long)L.N * RICW_MAX * TILE;
 }
 
 int emu_field_offset(const Cfg* c, int field, int* cnt)
@@ -34,7 +39,7 @@ int emu_field_offset(const Cfg* c, int field, int* cnt)
         case MPCB200_F_NU: *cnt = 3; return L.oNU;
         case MPCB200_F_S: *cnt = L.RS; return L.oS;
         case MPCB200_F_LAM: *cnt = L.RS; return L.oLAM;
-        case MPCB200_F_KKT: *cnt = KW; return L.oKKT;
+        case MPCB200_F_KKT: *cnt = KW; return (int)L.stride + EMU_SLOT;  /* tile: element (k,f) at ((k*42+f)*32) */
         case MPCB200_F_STEP: *cnt = 8; return L.oSTEP;
         case MPCB200_F_SCAL: *cnt = MPCB200_SCAL_WORDS; return L.oSCAL;
         case MPCB200_F_OBSIDX: *cnt = L.K > 0 ? L.K : 1; return L.oOBS;
@@ -137,7 +142,7 @@ void emu_associate(const Cfg* cp, double* W, double uprev_dt, int first_outer)
     for (int k = 0; k < N; ++k) init_duals_stage(c, L, W, uprev_dt, k, mu);
     ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
     ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
-    ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0;
+    ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0;
     if (repair) ASC(MPCB200_SC_COLD) = 0.0;
 }
 
@@ -160,23 +165,21 @@ int emu_eval(const Cfg* cp, double* W, double uprev_dt)
     for (int l = 0; l < 32; ++l)
     {
         evalacc_init(a[l]);
-        for (int k = l; k < N; k += 32) eval_stage(c, L, W, uprev_dt, k, a[l]);
+        for (int k = l; k < N; k += 32) eval_stage(c, L, W, emu_kb(L, W), uprev_dt, k, a[l]);
     }
     reduce_eval(a);
     int fin = 0;
     const double mu = eval_finish(c, L, W, a[0], true, &fin);
     if (fin) return 1;
-    for (int k = 0; k < N; ++k) eval_finalize_stage(L, W, k, mu);
+    for (int k = 0; k < N; ++k) eval_finalize_stage(L, W, emu_kb(L, W), k, mu);
     return 0;
 }
 
-static int ric_src(int w)
+struct EmuStep
 {
-    if (w < 15) return rP(w / 5, w % 5);
-    if (w < 30) return rPI((w - 15) / 5, (w - 15) % 5);
-    if (w < 40) return R_KG + (w - 30);
-    return R_KT + (w - 40);
-}
+    double* W; int oSTEP; int N;
+    void operator()(int k, int c, double v) const { W[oSTEP + c * N + k] = v; }
+};
 
 int emu_kkt(const Cfg* cp, double* W)
 {
@@ -185,72 +188,19 @@ int emu_kkt(const Cfg* cp, double* W)
     make_layout(cp, MAX_OBST, MAX_VP, L);
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return 1;
-    double* rec = (double*)malloc(sizeof(double) * (KW * N + R_WORDS + 8 * N));
-    double* sm = rec + KW * N;
-    double* stepbuf = sm + R_WORDS;
-    double* ric = W + L.oRIC;
-    for (int i = 0; i < KW * N; ++i) rec[i] = W[L.oKKT + i];
-    for (int i = 0; i < R_WORDS; ++i) sm[i] = 0.0;
-    const double htt = ASC(MPCB200_SC_HTT), gt = ASC(MPCB200_SC_GT), dlast = ASC(MPCB200_SC_DELTA_LAST);
-    const int dt_free = c.variable_dt;
-    RTask tA[32], tB[64], tC[32], tD[64];
-    for (int l = 0; l < 32; ++l) { tA[l] = rtask_A(l); tC[l] = rtask_C(l); }
-    for (int l = 0; l < 64; ++l) { tB[l] = rtask_B(l); tD[l] = rtask_D(l); }
-    double delta = 0.0, th[5];
-    int ok = 0, nreg = 0;
-    for (int tries = 0; tries < 40; ++tries)
-    {
-        for (int idx = 0; idx < 75; ++idx) sm[R_P + idx] = terminal_entry(c, rec, N, idx, delta, htt, gt);
-        int good = 1;
-        for (int k = N - 2; k >= 0; --k)
-        {
-            for (int idx = 0; idx < R_EXP_WORDS; ++idx) sm[R_EXP + idx] = expand_entry(rec, N, k, idx, delta, dt_free);
-            // a pass must be hazard free: emulate "all lanes read, then all lanes write" by double buffering
-            double tmp[R_WORDS];
-            memcpy(tmp, sm, sizeof(tmp));
-            for (int l = 0; l < 32; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tA[l]); if (tA[l].out >= 0) { sm[tA[l].out] = s2[tA[l].out]; if (tA[l].out2 >= 0) sm[tA[l].out2] = s2[tA[l].out2]; } }
-            memcpy(tmp, sm, sizeof(tmp));
-            for (int l = 0; l < 64; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tB[l]); if (tB[l].out >= 0) { sm[tB[l].out] = s2[tB[l].out]; if (tB[l].out2 >= 0) sm[tB[l].out2] = s2[tB[l].out2]; } }
-            double lam4[4];
-            if (!lambda_from_mmvv(sm, lam4)) { good = 0; break; }
-            for (int i = 0; i < 4; ++i) sm[R_LAMB + i] = lam4[i];
-            memcpy(tmp, sm, sizeof(tmp));
-            for (int l = 0; l < 32; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tC[l]); if (tC[l].out >= 0) { sm[tC[l].out] = s2[tC[l].out]; if (tC[l].out2 >= 0) sm[tC[l].out2] = s2[tC[l].out2]; } }
-            for (int w = 0; w < RIC_WORDS; ++w) ric[k * RIC_WORDS + w] = sm[ric_src(w)];
-            memcpy(tmp, sm, sizeof(tmp));
-            for (int l = 0; l < 64; ++l) { double s2[R_WORDS]; memcpy(s2, tmp, sizeof(s2)); run_task(s2, tD[l]); if (tD[l].out >= 0) { sm[tD[l].out] = s2[tD[l].out]; if (tD[l].out2 >= 0) sm[tD[l].out2] = s2[tD[l].out2]; } }
-        }
-        if (good) good = root_solve(c, sm + R_TH, th);
-        if (good) { ok = 1; break; }
-        ++nreg;
-        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
-        else delta *= (dlast == 0.0 ? 100.0 : 8.0);
-        if (delta > 1e20) break;
-    }
-    if (!ok)
-    {
-        ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;
-        ASC(MPCB200_SC_NREG) += (double)nreg;
-        free(rec);
-        return 1;
-    }
-    double y[5] = {0, 0, 0, 0, 0};
-    for (int k = 0; k <= N - 2; ++k)
-    {
-        double a3[3], Bm[6], e[3], d[3], dw[5], nup[3];
-        for (int i = 0; i < 3; ++i) { a3[i] = rec[(MPCB200_K_A + i) * N + k]; e[i] = rec[(MPCB200_K_E + i) * N + k]; d[i] = rec[(MPCB200_K_D + i) * N + k]; }
-        for (int i = 0; i < 6; ++i) Bm[i] = rec[(MPCB200_K_B + i) * N + k];
-        forward_stage(ric + k * RIC_WORDS, a3, Bm, e, d, dt_free, th, y, dw, nup);
-        for (int i = 0; i < 5; ++i) stepbuf[i * N + k] = dw[i];
-        for (int i = 0; i < 3; ++i) stepbuf[(5 + i) * N + k] = nup[i];
-    }
-    for (int i = 0; i < 8; ++i) stepbuf[i * N + (N - 1)] = i < 3 ? y[i] : 0.0;
-    for (int i = 0; i < 8 * N; ++i) W[L.oSTEP + i] = stepbuf[i];
-    ASC(MPCB200_SC_DDT) = th[1];
+    TileRec rec{emu_kb(L, W)};
+    TileRic ric{emu_rb(L, W)};
+    EmuStep step{W, L.oSTEP, N};
+    const bool ext = c.variable_dt || c.xf_fixed[0] || c.xf_fixed[1] || c.xf_fixed[2];
+    double ddt = 0.0, delta = 0.0;
+    int nreg = 0, ok;
+    if (ext) ok = riccati_solve_lane<true>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
+    else ok = riccati_solve_lane<false>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
+    ASC(MPCB200_SC_NREG) += (double)nreg;
+    if (!ok) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; return 1; }
+    ASC(MPCB200_SC_DDT) = ddt;
     ASC(MPCB200_SC_DELTA) = delta;
     if (delta > 0.0) ASC(MPCB200_SC_DELTA_LAST) = delta;
-    ASC(MPCB200_SC_NREG) += (double)nreg;
-    free(rec);
     return 0;
 }
 
@@ -267,7 +217,7 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
     {
         LsAcc t;
         lsacc_init(t);
-        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, uprev_dt, k, t);
+        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, emu_kb(L, W), uprev_dt, k, t);
         a.a_p = fmin(a.a_p, t.a_p); a.a_d = fmin(a.a_d, t.a_d);
         a.dphi_bar += t.dphi_bar; a.curv += t.curv; a.dJ += t.dJ;
     }
@@ -303,6 +253,9 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
     ASC(MPCB200_SC_RHO) = rho;
     ASC(MPCB200_SC_ITER) += 1.0;
     ASC(MPCB200_SC_NBT) += (double)nbt;
+    const double tiny = alpha < TINY_STEP ? ASC(MPCB200_SC_TINY) + 1.0 : 0.0;
+    ASC(MPCB200_SC_TINY) = tiny;
+    if (tiny >= (double)TINY_STEP_COUNT) ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;  /* jammed: give up */
 }
 
 // whole Controller::step of one instance, same launch sequence as solve_device() in mpcb200.cu
