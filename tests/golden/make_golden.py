@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures of tests/golden/ (committed; this script is the provenance).
+
+The reference ships no golden vectors and cannot be run here, so the known answers are produced by an
+INDEPENDENT algorithm -- scipy.optimize SLSQP (and trust-constr for the single-instance config) with numeric Jacobians --
+on the restated OCP functions (objective / dynamics defects / inequality rows evaluated through oracle/liboracle.so),
+from the same initial guess the solvers use.  The oracle's interior-point solver and the CUDA solver are then both
+tested against these fixtures (tests/test_oracle_golden.py, tests/test_gpu_parity.py).
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.json (a few minutes)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+from scipy.optimize import NonlinearConstraint, minimize
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from mpc_local_planner_b200 import capi, configs  # noqa: E402
+from oracle import oracle_py as orc  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def scipy_solve(cfg, data, b, method="SLSQP"):
+    inst = orc.instance_from_batch(cfg, data, b)
+    N = inst.N
+    inst.init_cold()
+    inst.associate()
+    inst.L.orc_project_init(orc.C.byref(inst.p), inst.ws)
+    inst.L.orc_init_controls(orc.C.byref(inst.p), inst.ws)
+    inst.init_duals()
+    X, U, SC = inst.arr("X"), inst.arr("U"), inst.arr("SCAL")
+    idx = []
+    for k in range(1, N):
+        for i in range(3):
+            if k == N - 1 and cfg.xf_fixed[i]:
+                continue
+            idx.append(("x", i, k))
+    for k in range(N - 1):
+        for i in range(2):
+            idx.append(("u", i, k))
+    if cfg.variable_dt:
+        idx.append(("dt", 0, 0))
+
+    def setz(z):
+        for v, (t, i, k) in zip(z, idx):
+            if t == "x":
+                X[i, k] = v
+            elif t == "u":
+                U[i, k] = v
+            else:
+                SC[capi.SC_DT] = v
+
+    def getz():
+        return np.array([X[i, k] if t == "x" else (U[i, k] if t == "u" else SC[capi.SC_DT]) for (t, i, k) in idx])
+
+    act = inst.arr("LAM") > 0
+
+    def fun(z):
+        setz(z); inst.eval(); return SC[capi.SC_OBJ]
+
+    def ceq(z):
+        setz(z); inst.eval(); return inst.arr("KKT")[capi.K_E:capi.K_E + 3, :N - 1].ravel().copy()
+
+    def cin(z):
+        setz(z); inst.eval(); return -(inst.arr("G")[act]).copy()
+
+    z0 = getz()
+    if method == "SLSQP":
+        res = minimize(fun, z0, method="SLSQP", constraints=[{"type": "eq", "fun": ceq}, {"type": "ineq", "fun": cin}],
+                       options=dict(maxiter=500, ftol=1e-12))
+    else:
+        res = minimize(fun, z0, method="trust-constr",
+                       constraints=[NonlinearConstraint(ceq, 0, 0), NonlinearConstraint(cin, 0, np.inf)],
+                       options=dict(maxiter=3000, gtol=1e-9, xtol=1e-12))
+    setz(res.x)
+    ce = float(np.abs(ceq(res.x)).max())
+    ci = float(min(cin(res.x).min(), 0))
+    return dict(f=float(res.fun), ceq=ce, cin=ci, nit=int(res.nit), U=U[:, :N - 1].T.copy().tolist(),
+                dt=float(SC[capi.SC_DT]), xN=X[:, N - 1].tolist())
+
+
+def main():
+    out = {}
+    # config 1 / scenario G1 (reference's only fixed scenario): two independent scipy algorithms
+    cfg = configs.cfg1(tol=1e-8)
+    data = configs.g1_instance()
+    t = time.time()
+    a = scipy_solve(cfg, data, 0, "SLSQP")
+    bb = scipy_solve(cfg, data, 0, "trust-constr")
+    print("G1 SLSQP dt %.8f trust-constr dt %.8f  |du| %.2e  (%.0fs)" % (
+        a["dt"], bb["dt"], np.abs(np.array(a["U"]) - np.array(bb["U"])).max(), time.time() - t))
+    out["g1"] = dict(config_id=1, slsqp=a, trust_constr=bb)
+    json.dump(out["g1"], open(os.path.join(HERE, "g1.json"), "w"), indent=1)
+    # config 2: a handful of seeded instances (obstacles + rate limits active)
+    cfg = configs.cfg2(tol=1e-8)
+    sel = [0, 2, 6, 10, 12, 18, 29, 33, 55, 58]
+    data = configs.generate(2, max(sel) + 1)
+    rows = []
+    for b in sel:
+        t = time.time()
+        r = scipy_solve(cfg, data, b)
+        r["instance"] = b
+        print("cfg2 inst %d f %.6f ceq %.1e cin %.1e nit %d (%.0fs)" % (b, r["f"], r["ceq"], r["cin"], r["nit"], time.time() - t))
+        if r["ceq"] < 1e-8 and r["cin"] > -1e-8:
+            rows.append(r)
+    json.dump(dict(config_id=2, instances=rows), open(os.path.join(HERE, "slsqp_cfg2.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,270 @@
+"""The CPU oracle's restatement of the reference's elementary functions + analytic derivatives (CPU, no GPU)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from mpc_local_planner_b200 import capi, configs
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def test_normalize_theta_matches_reference_rule(orc):
+    """math_utils.h:81-91: identity on [-pi, pi), else floor-mod then +-2pi."""
+    L = orc.lib()
+    for th in (-math.pi, -3.0, 0.0, 3.0, math.pi - 1e-12):
+        assert L.orc_normalize_theta(th) == th
+    assert L.orc_normalize_theta(math.pi) == pytest.approx(-math.pi)
+    rng = np.random.default_rng(0)
+    for th in rng.uniform(-50, 50, 200):
+        w = L.orc_normalize_theta(th)
+        assert -math.pi <= w < math.pi
+        assert math.isclose(math.sin(w), math.sin(th), abs_tol=1e-12) and math.isclose(math.cos(w), math.cos(th), abs_tol=1e-12)
+    assert L.orc_interpolate_angle(3.0, -3.0, 0.5) == pytest.approx(L.orc_normalize_theta(3.0 + 0.5 * (2 * math.pi - 6.0)))
+
+
+@pytest.mark.parametrize("robot", [capi.ROBOT_UNICYCLE, capi.ROBOT_SIMPLE_CAR, capi.ROBOT_SIMPLE_CAR_FRONT, capi.ROBOT_KIN_BICYCLE])
+def test_dynamics_values_and_derivatives(orc, robot):
+    """systems/*.h dynamics; analytic Jacobian/Hessian vs central differences."""
+    L = orc.lib()
+    cfg = capi.default_config()
+    cfg.robot_type = robot
+    cfg.wheelbase, cfg.length_rear, cfg.length_front = 0.4, 0.7, 0.9
+    rng = np.random.default_rng(robot)
+    for _ in range(10):
+        x = rng.uniform(-2, 2, 3); u = np.array([rng.uniform(-0.3, 0.5), rng.uniform(-1.0, 1.0)]); nu = rng.standard_normal(3)
+        f = np.zeros(3); J = np.zeros(9); Hc = np.zeros(6); f2 = np.zeros(3)
+        L.orc_dynamics(C.byref(cfg), _dp(x), _dp(u), _dp(f2))
+        L.orc_dynamics_derivs(C.byref(cfg), _dp(x), _dp(u), _dp(nu), _dp(f), _dp(J), _dp(Hc))
+        np.testing.assert_allclose(f, f2, atol=1e-15)
+        th, v, w = x[2], u[0], u[1]
+        if robot == capi.ROBOT_UNICYCLE:
+            np.testing.assert_allclose(f, [v * math.cos(th), v * math.sin(th), w], atol=1e-15)
+        elif robot == capi.ROBOT_SIMPLE_CAR:
+            np.testing.assert_allclose(f, [v * math.cos(th), v * math.sin(th), v * math.tan(w) / 0.4], atol=1e-14)
+        elif robot == capi.ROBOT_SIMPLE_CAR_FRONT:
+            np.testing.assert_allclose(f, [v * math.cos(th), v * math.sin(th), v * math.sin(w) / 0.4], atol=1e-14)
+        else:
+            beta = math.atan(0.7 / 1.6 * math.tan(w))
+            np.testing.assert_allclose(f, [v * math.cos(th + beta), v * math.sin(th + beta), v * math.sin(beta) / 0.7], atol=1e-14)
+
+        def fq(q):
+            xx = x.copy(); xx[2] = q[0]; uu = np.array([q[1], q[2]]); o = np.zeros(3)
+            L.orc_dynamics(C.byref(cfg), _dp(xx), _dp(uu), _dp(o)); return o
+        q0 = np.array([th, v, w]); h = 1e-6
+        Jfd = np.zeros((3, 3))
+        for i in range(3):
+            e = np.zeros(3); e[i] = h
+            Jfd[:, i] = (fq(q0 + e) - fq(q0 - e)) / (2 * h)
+        np.testing.assert_allclose(J.reshape(3, 3), Jfd, atol=1e-8)
+        # Hessian of nu^T f
+        def g(q): return nu @ fq(q)
+        H = np.zeros((3, 3)); hh = 1e-4
+        for i in range(3):
+            for j in range(3):
+                ei = np.zeros(3); ej = np.zeros(3); ei[i] = hh; ej[j] = hh
+                H[i, j] = (g(q0 + ei + ej) - g(q0 + ei - ej) - g(q0 - ei + ej) + g(q0 - ei - ej)) / (4 * hh * hh)
+        Hpk = np.array([[Hc[0], Hc[1], Hc[2]], [Hc[1], Hc[3], Hc[4]], [Hc[2], Hc[4], Hc[5]]])
+        np.testing.assert_allclose(Hpk, H, atol=2e-6)
+
+
+def test_defect_is_dt_times_reference_defect(orc):
+    """fd_collocation_se2.h:54-69 as coded (divides by dt) vs the multiplied form used by the solvers."""
+    L = orc.lib()
+    cfg = capi.default_config()
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        x1 = rng.uniform(-3, 3, 3); x2 = x1 + rng.uniform(-0.3, 0.3, 3); u = rng.uniform(-0.4, 0.4, 2); dt = rng.uniform(0.05, 1.0)
+        x2[2] += rng.integers(-2, 3) * 2 * math.pi  # periodic in theta
+        e_ref = np.zeros(3); e = np.zeros(3)
+        L.orc_defect_reference(C.byref(cfg), _dp(x1), _dp(u), _dp(x2), dt, _dp(e_ref))
+        L.orc_defect(C.byref(cfg), _dp(x1), _dp(u), _dp(x2), dt, _dp(e))
+        np.testing.assert_allclose(e, dt * e_ref, atol=1e-13)
+
+
+def _fp_cfg(kind):
+    c = capi.default_config()
+    c.footprint_type = kind
+    if kind == capi.FOOTPRINT_CIRCULAR:
+        c.footprint_params[0] = 0.25
+    elif kind == capi.FOOTPRINT_TWO_CIRCLES:
+        c.footprint_params[:] = [0.2, 0.15, 0.25, 0.2]
+    elif kind == capi.FOOTPRINT_LINE:
+        c.footprint_params[:] = [-0.1, 0.05, 0.4, -0.02]
+    elif kind == capi.FOOTPRINT_POLYGON:
+        c.n_poly = len(configs.CARLIKE_POLYGON)
+        for i, (x, y) in enumerate(configs.CARLIKE_POLYGON):
+            c.poly_xy[2 * i], c.poly_xy[2 * i + 1] = x, y
+    return c
+
+
+@pytest.mark.parametrize("kind", [capi.FOOTPRINT_POINT, capi.FOOTPRINT_CIRCULAR, capi.FOOTPRINT_TWO_CIRCLES, capi.FOOTPRINT_LINE,
+                                  capi.FOOTPRINT_POLYGON])
+def test_footprint_distance(orc, kind):
+    """teb RobotFootprintModel::calculateDistance semantics: values by brute force in the world frame,
+    gradient / Hessian of the active feature by finite differences."""
+    L = orc.lib()
+    cfg = _fp_cfg(kind)
+    rng = np.random.default_rng(kind)
+
+    def dist(pose, otype, op):
+        return L.orc_footprint_distance(C.byref(cfg), _dp(np.ascontiguousarray(pose)), otype, _dp(op), None, None)
+
+    def brute(pose, otype, op):
+        c, s = math.cos(pose[2]), math.sin(pose[2])
+        R = np.array([[c, -s], [s, c]])
+        o = op[:2]
+        def seg_d(a, b):
+            a = pose[:2] + R @ a; b = pose[:2] + R @ b
+            ab = b - a; sq = ab @ ab
+            t = 0.0 if sq == 0 else min(1.0, max(0.0, ((o - a) @ ab) / sq))
+            return np.linalg.norm(o - (a + t * ab))
+        if kind == capi.FOOTPRINT_POINT:
+            d = np.linalg.norm(o - pose[:2])
+        elif kind == capi.FOOTPRINT_CIRCULAR:
+            d = np.linalg.norm(o - pose[:2]) - 0.25
+        elif kind == capi.FOOTPRINT_TWO_CIRCLES:
+            h = np.array([c, s])
+            d = min(np.linalg.norm(o - (pose[:2] + 0.2 * h)) - 0.15, np.linalg.norm(o - (pose[:2] - 0.25 * h)) - 0.2)
+        elif kind == capi.FOOTPRINT_LINE:
+            d = seg_d(np.array([-0.1, 0.05]), np.array([0.4, -0.02]))
+        else:
+            P = np.array(configs.CARLIKE_POLYGON)
+            d = min(seg_d(P[i], P[(i + 1) % len(P)]) for i in range(len(P)))
+        return d - (op[4] if otype == capi.OBST_CIRCLE else 0.0)
+
+    for _ in range(40):
+        pose = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-3, 3)])
+        op = np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), 0, 0, rng.uniform(0.05, 0.3)])
+        otype = int(rng.integers(0, 2))
+        d = dist(pose, otype, op)
+        assert d == pytest.approx(brute(pose, otype, op), abs=1e-12)
+        g = np.zeros(3); H = np.zeros(6)
+        L.orc_footprint_distance(C.byref(cfg), _dp(pose), otype, _dp(op), _dp(g), _dp(H))
+        h = 1e-6
+        gfd = np.array([(dist(pose + h * e, otype, op) - dist(pose - h * e, otype, op)) / (2 * h) for e in np.eye(3)])
+        np.testing.assert_allclose(g, gfd, atol=1e-7)
+        hh = 1e-4
+        Hfd = np.zeros((3, 3))
+        for i in range(3):
+            for j in range(3):
+                ei, ej = np.eye(3)[i] * hh, np.eye(3)[j] * hh
+                Hfd[i, j] = (dist(pose + ei + ej, otype, op) - dist(pose + ei - ej, otype, op) - dist(pose - ei + ej, otype, op)
+                             + dist(pose - ei - ej, otype, op)) / (4 * hh * hh)
+        Hm = np.array([[H[0], H[1], H[2]], [H[1], H[3], H[4]], [H[2], H[4], H[5]]])
+        if np.abs(Hfd - Hm).max() > 1e-4:  # feature switch inside the FD stencil: skip (piecewise smooth distance)
+            continue
+        np.testing.assert_allclose(Hm, Hfd, atol=1e-4)
+
+
+def _random_iterate(orc, cid, b, seed):
+    cfg = configs.config_for(cid, tol=1e-8)
+    data = configs.g1_instance() if cid == 1 else configs.generate(cid, b + 1)
+    inst = orc.instance_from_batch(cfg, data, 0 if cid == 1 else b)
+    N = inst.N
+    inst.init_cold()
+    rng = np.random.default_rng(seed)
+    inst.arr("X")[:, 1:] += 0.05 * rng.standard_normal((3, N - 1))
+    inst.arr("U")[:] = 0.1 * rng.standard_normal((2, N)); inst.arr("U")[:, N - 1] = 0
+    inst.associate(); inst.init_duals()
+    inst.arr("NU")[:] = rng.standard_normal((3, N)); inst.arr("NU")[:, N - 1] = 0
+    act = inst.arr("LAM") > 0
+    inst.arr("LAM")[:] = np.where(act, rng.uniform(0.5, 2, act.shape), 0)
+    inst.arr("SCAL")[capi.SC_MU] = 0.1
+    return inst, cfg
+
+
+def _pack(inst):
+    return np.concatenate([inst.arr("X").ravel(), inst.arr("U").ravel(), [inst.arr("SCAL")[capi.SC_DT]]])
+
+
+def _unpack(inst, z):
+    N = inst.N
+    inst.arr("X")[:] = z[:3 * N].reshape(3, N); inst.arr("U")[:] = z[3 * N:5 * N].reshape(2, N); inst.arr("SCAL")[capi.SC_DT] = z[5 * N]
+
+
+def _lagrangian(inst):
+    inst.eval()
+    S = inst.arr("SCAL"); K = inst.arr("KKT"); N = inst.N
+    e = K[capi.K_E:capi.K_E + 3, :N - 1]
+    return S[capi.SC_OBJ] + (inst.arr("NU")[:, :N - 1] * e).sum() + (inst.arr("LAM") * (inst.arr("G") + inst.arr("S")) * (inst.arr("LAM") > 0)).sum()
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3, 4])
+def test_lagrangian_gradient_and_newton_step(orc, cid):
+    """Analytic Lagrangian gradient vs finite differences; the Riccati Newton step (incl. the dt border and the fixed
+    terminal state) vs a dense numpy solve of the full KKT system assembled by finite differences."""
+    inst, cfg = _random_iterate(orc, cid, 0, 0)
+    N = inst.N
+    z0 = _pack(inst)
+    n = len(z0)
+    inst.eval()
+    GL = inst.arr("GL").copy(); gl_dt = inst.ws.contents.gl_dt
+    h = 1e-6
+    g_fd = np.zeros(n)
+    for i in range(n):
+        zp = z0.copy(); zp[i] += h; _unpack(inst, zp); Lp = _lagrangian(inst)
+        zm = z0.copy(); zm[i] -= h; _unpack(inst, zm); Lm = _lagrangian(inst)
+        g_fd[i] = (Lp - Lm) / (2 * h)
+    _unpack(inst, z0)
+    gx = g_fd[:3 * N].reshape(3, N); gu = g_fd[3 * N:5 * N].reshape(2, N)
+    assert np.abs(gx[:, 1:] - GL[:3, 1:]).max() < 5e-6
+    assert np.abs(gu[:, :N - 1] - GL[3:5, :N - 1]).max() < 5e-6
+    if cfg.variable_dt:
+        assert abs(g_fd[5 * N] - gl_dt) < 5e-6 * max(1, abs(gl_dt))
+    # ---- dense KKT by finite differences of the analytic gradient ----
+    free = []
+    for k in range(1, N):
+        for i in range(3):
+            if k == N - 1 and cfg.xf_fixed[i]:
+                continue
+            free.append(i * N + k)
+    for k in range(N - 1):
+        for i in range(2):
+            free.append(3 * N + i * N + k)
+    if cfg.variable_dt:
+        free.append(5 * N)
+    free = np.array(free)
+
+    def grads(z):
+        _unpack(inst, z); inst.eval()
+        G_ = inst.arr("GL")
+        g = np.concatenate([G_[:3].ravel(), G_[3:5].ravel(), [inst.ws.contents.gl_dt]])
+        return g, inst.arr("KKT")[capi.K_E:capi.K_E + 3, :N - 1].T.ravel().copy(), inst.arr("G").copy()
+    m = 3 * (N - 1); RS = inst.RS
+    W = np.zeros((n, n)); Jc = np.zeros((m, n)); Jg = np.zeros((RS * N, n))
+    for i in range(n):
+        zp = z0.copy(); zp[i] += h; gp, ep, Gp = grads(zp)
+        zm = z0.copy(); zm[i] -= h; gm, em, Gm = grads(zm)
+        W[:, i] = (gp - gm) / (2 * h); Jc[:, i] = (ep - em) / (2 * h); Jg[:, i] = ((Gp - Gm) / (2 * h)).ravel()
+    _unpack(inst, z0); inst.eval()
+    S = inst.arr("S").ravel(); LAM = inst.arr("LAM").ravel(); G = inst.arr("G").ravel()
+    act = LAM > 0
+    sig = np.where(act, LAM / S, 0.0)
+    mu = inst.arr("SCAL")[capi.SC_MU]
+    Hc = W + Jg.T @ np.diag(sig) @ Jg
+    gl, _, _ = grads(z0)
+    nu = inst.arr("NU")[:, :N - 1].T.ravel()
+    gJ = gl - Jc.T @ nu - Jg.T @ np.where(act, LAM, 0)
+    r = np.where(act, G + S, 0)
+    gt = gJ + Jg.T @ (np.where(act, mu / S, 0) + sig * r)
+    e = inst.arr("KKT")[capi.K_E:capi.K_E + 3, :N - 1].T.ravel()
+    nf = len(free)
+    for delta in (0.0, 1e-2):
+        Kmat = np.zeros((nf + m, nf + m))
+        Kmat[:nf, :nf] = Hc[np.ix_(free, free)] + delta * np.eye(nf); Kmat[:nf, nf:] = Jc[:, free].T; Kmat[nf:, :nf] = Jc[:, free]
+        ev = np.linalg.eigvalsh(Kmat)
+        rc = inst.kkt_solve(delta)
+        if (ev > 0).sum() != nf or (ev < 0).sum() != m:
+            assert rc == 1  # wrong inertia must be detected
+            continue
+        assert rc == 0
+        sol = np.linalg.solve(Kmat, np.concatenate([-gt[free], -e]))
+        STEP = inst.arr("STEP"); ddt = inst.arr("SCAL")[capi.SC_DDT]
+        dz = np.zeros(n); dz[:3 * N] = STEP[:3].ravel(); dz[3 * N:5 * N] = STEP[3:5].ravel(); dz[5 * N] = ddt
+        nup = STEP[5:8, :N - 1].T.ravel()
+        assert np.abs(dz[free] - sol[:nf]).max() < 1e-5 * max(1.0, np.abs(sol[:nf]).max())
+        assert np.abs(nup - sol[nf:]).max() < 1e-5 * max(1.0, np.abs(sol[nf:]).max())
