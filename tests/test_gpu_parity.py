@@ -198,3 +198,32 @@ def test_error_paths(cuda_lib):
     with pytest.raises(capi.SolverError):
         capi.BatchSolver(bad, 4)
     s.close()
+
+
+def test_golden_g1_and_cfg2(cuda_lib):
+    """CUDA path against the committed scipy golden fixtures (tests/golden/, independent algorithms)."""
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = json.load(open(os.path.join(here, "g1.json")))
+    cfg = configs.cfg1(tol=1e-9)
+    data = configs.g1_instance()
+    s = _solver(cfg, 1)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"])
+    assert out["status"][0] == 0
+    assert abs(out["dt"][0] - 0.71287734) < 2e-8 and abs(out["dt"][0] - g["slsqp"]["dt"]) < 1e-7
+    assert np.abs(out["u_seq"][0][0] - np.array([0.4, 0.3])).max() < 1e-6
+    assert np.abs(out["u_seq"][0][:-1] - np.array(g["slsqp"]["U"])).max() < 2e-4
+    s.close()
+    g2 = json.load(open(os.path.join(here, "slsqp_cfg2.json")))
+    rows = g2["instances"]
+    B = max(r["instance"] for r in rows) + 1
+    cfg = configs.cfg2(tol=1e-9)
+    data = configs.generate(2, B)
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"])
+    for r in rows:
+        b = r["instance"]
+        assert out["status"][b] == 0
+        assert np.abs(out["u_seq"][b][:-1] - np.array(r["U"])).max() < 2e-4
+    s.close()
