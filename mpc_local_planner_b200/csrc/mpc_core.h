@@ -30,6 +30,7 @@ struct WsLayout
     int N, K, RS, M, V;      // grid points, obstacle rows per stage, row slots, max obstacles, max via-points
     int64_t stride;          // doubles per instance (multiple of 16 -> 128-byte aligned blocks)
     int oX, oU, oNU, oS, oLAM, oKKT, oSTEP, oOBS, oSCAL, oDS, oDLAM, oRIC, oVPST;
+    int oR0, oOG;            // row residuals at the current point (RS x N), obstacle row value + gradient (4K x N)
     int oIN;                 // x0(3) xf(3) u_prev(2) n_obst n_vp has_xinit reinit
     int oOBST, oOTYPE, oVP, oXINIT;
     int ricw;                // Riccati scratch words per stage
@@ -51,7 +52,7 @@ struct WsLayout
 #define SLACK_PUSH 1e-2
 #define ARMIJO 1e-4
 #define MAX_BACKTRACK 8
-#define MAX_INERTIA_TRIES 12
+#define MAX_INERTIA_TRIES 5
 #define MAX_DELTA 1e8
 #define TINY_STEP 1e-8
 #define TINY_STEP_COUNT 2
@@ -81,7 +82,7 @@ HD inline double interpolate_angle(double a1, double a2, double factor)
 
 // f(x,u) and derivatives wrt q = (theta, u0, u1): J[j*3+i] = df_j/dq_i, Hc = sum_j nu_j Hess f_j packed (tt,t0,t1,00,01,11)
 HD inline void dynamics_derivs(const Cfg& c, double th, double v, double w, const double* nu, double* f, double* J,
-                                       double* Hc)
+                                       double* Hc, const double* sc = nullptr)
 {
 #pragma unroll
     for (int i = 0; i < 9; ++i) J[i] = 0.0;
@@ -90,7 +91,8 @@ HD inline void dynamics_derivs(const Cfg& c, double th, double v, double w, cons
     if (c.robot_type != MPCB200_ROBOT_KIN_BICYCLE)
     {
         double s, co;
-        sincos(th, &s, &co);
+        if (sc) { s = sc[0]; co = sc[1]; }
+        else sincos(th, &s, &co);
         f[0] = v * co; f[1] = v * s;
         J[0] = -v * s; J[1] = co;
         J[3] = v * co; J[4] = s;
@@ -191,11 +193,23 @@ HD inline int footprint_segments(const Cfg& c, FpSeg* seg)
 
 // distance footprint(pose) <-> point/circle obstacle; optional gradient (x,y,theta) and Hessian (xx,xy,xt,yy,yt,tt)
 template <bool WITH_GRAD, bool WITH_HESS>
+HD inline double footprint_distance_sc(const Cfg& c, double px, double py, double s, double co, int obst_type, const double* op,
+                                       double* grad3, double* hess6);
+
+template <bool WITH_GRAD, bool WITH_HESS>
 HD inline double footprint_distance(const Cfg& c, double px, double py, double pth, int obst_type, const double* op,
                                             double* grad3, double* hess6)
 {
     double s, co;
     sincos(pth, &s, &co);
+    return footprint_distance_sc<WITH_GRAD, WITH_HESS>(c, px, py, s, co, obst_type, op, grad3, hess6);
+}
+
+// same with the sine / cosine of the heading supplied by the caller (one sincos per stage, shared by all rows)
+template <bool WITH_GRAD, bool WITH_HESS>
+HD inline double footprint_distance_sc(const Cfg& c, double px, double py, double s, double co, int obst_type, const double* op,
+                                       double* grad3, double* hess6)
+{
     const double ox = op[0] - px, oy = op[1] - py;
     const double qx = co * ox + s * oy, qy = -s * ox + co * oy;
     double best = 1e300, bcx = 0, bcy = 0, brho = 0;

@@ -19,6 +19,7 @@ static inline void make_layout(const mpcb200_config* c, int M, int V, WsLayout& 
     L.oKKT = -1; L.oSTEP = take(8 * N);  /* KKT records and Riccati gains live in 32-instance interleaved tiles */
     L.oOBS = take((L.K > 0 ? L.K : 1) * N);
     L.oDS = take(L.RS * N); L.oDLAM = take(L.RS * N);
+    L.oR0 = take(L.RS * N); L.oOG = take(4 * (L.K > 0 ? L.K : 1) * N);
     L.ricw = RICW_MAX;
     L.oRIC = -1;
     L.oVPST = take(V > 0 ? V : 1);

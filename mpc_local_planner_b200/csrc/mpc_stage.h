@@ -23,6 +23,8 @@
 #define AOBS(c_, k_) W[L.oOBS + (c_) * N + (k_)]
 #define ADS(c_, k_) W[L.oDS + (c_) * N + (k_)]
 #define ADLAM(c_, k_) W[L.oDLAM + (c_) * N + (k_)]
+#define AR0(c_, k_) W[L.oR0 + (c_) * N + (k_)]
+#define AOG(c_, k_) W[L.oOG + (c_) * N + (k_)]
 #define ASC(i_) W[L.oSCAL + (i_)]
 #define AIN(i_) W[L.oIN + (i_)]
 
@@ -49,16 +51,81 @@ HD inline void evalacc_merge(EvalAcc& a, const EvalAcc& b)
     a.gldt += b.gldt; a.htt += b.htt; a.obj += b.obj; a.m_ineq += b.m_ineq; a.m_eq += b.m_eq;
 }
 
-// bookkeeping of one inequality row (owner side): errors + barrier terms
-HD inline void row_stats(EvalAcc& acc, double r, double s, double lam)
+// bookkeeping of one inequality row (owner side): errors + barrier terms.  The barrier term sum(log s) is accumulated
+// as a running product that is flushed through one log() every few rows (fp64 log costs ~60 instructions).
+struct RowProd { double p; int n; };
+HD inline void rowprod_add(RowProd& rp, double s, double& blog)
+{
+    rp.p *= s;
+    if (++rp.n >= 4) { blog += log(rp.p); rp.p = 1.0; rp.n = 0; }
+}
+HD inline void rowprod_flush(RowProd& rp, double& blog)
+{
+    if (rp.n > 0) { blog += log(rp.p); rp.p = 1.0; rp.n = 0; }
+}
+HD inline void row_stats(EvalAcc& acc, RowProd& rp, double r, double s, double lam)
 {
     acc.prim_inf = fmax(acc.prim_inf, fabs(r));
     acc.inf1 += fabs(r);
     acc.sl_max = fmax(acc.sl_max, s * lam);
     acc.sl_min = fmin(acc.sl_min, s * lam);
     acc.sum_lam += fabs(lam);
-    acc.blog += log(s);
+    rowprod_add(rp, s, acc.blog);
     acc.m_ineq += 1.0;
+}
+
+// One linear row (control bound / control-rate row) seen from stage k's control component I.
+//   g: row value, (s, lam): slack / multiplier, gmine: d g / d u_k[I], gdt: d g / d(dt), own: the row belongs to stage k
+//   (bookkeeping of errors and dt terms is done once, by the owner), gcross: d g / d u_{k-1}[I] (own rate rows only).
+template <int I>
+HD inline void lin_row_accum(double g, double s, double lam, double gmine, double gdt, bool own, double gcross, double* H, double* g0,
+                             double* g1, double* GL, double* hb, double* Cc, EvalAcc& acc, RowProd& rp)
+{
+    const double rs = 1.0 / s;
+    const double r = g + s, sig = lam * rs, c0 = sig * r;
+    g0[3 + I] += c0 * gmine; g1[3 + I] += rs * gmine; GL[3 + I] += lam * gmine;
+    H[hidx(3 + I, 3 + I)] += sig * gmine * gmine;
+    hb[3 + I] += sig * gmine * gdt;
+    if (own)
+    {
+        Cc[I] += sig * gmine * gcross;
+        row_stats(acc, rp, r, s, lam);
+        acc.gt0 += c0 * gdt; acc.gt1 += rs * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt;
+    }
+}
+
+// all linear rows that touch control component I of stage k <= N-2: bounds (slots 2I, 2I+1), own rate rows
+// (slots 4+2I, 5+2I) and the rate rows of stage k+1 (gather: their derivative wrt u_k)
+template <int I>
+HD inline void lin_rows_component(const Cfg& c, const WsLayout& L, const double* W, double uprev_dt, int k, double dt, double u_i, double* H,
+                                  double* g0, double* g1, double* GL, double* hb, double* Cc, EvalAcc& acc, RowProd& rp)
+{
+    const int N = L.N;
+    // control bounds
+    if (c.u_lb[I] > -MPCB200_INF) lin_row_accum<I>(c.u_lb[I] - u_i, AS(2 * I, k), ALAM(2 * I, k), -1.0, 0.0, true, 0.0, H, g0, g1, GL, hb, Cc, acc, rp);
+    if (c.u_ub[I] < MPCB200_INF) lin_row_accum<I>(u_i - c.u_ub[I], AS(2 * I + 1, k), ALAM(2 * I + 1, k), 1.0, 0.0, true, 0.0, H, g0, g1, GL, hb, Cc, acc, rp);
+    const bool has_lb = c.du_lb[I] > -MPCB200_INF, has_ub = c.du_ub[I] < MPCB200_INF;
+    if (!has_lb && !has_ub) return;
+    // own rate rows: Delta = u_k - u_{k-1}; k = 0 uses (u_prev, dt_prev) and is absent when dt_prev == 0
+    if (!(k == 0 && uprev_dt == 0.0))
+    {
+        const double um = (k >= 1) ? AU(I, k - 1) : AIN(IN_UPREV + I);
+        const double T = (k >= 1) ? dt : uprev_dt;
+        const double delta = u_i - um;
+        const double cross = (k >= 1) ? 1.0 : 0.0;             // d/du_{k-1} exists only for k >= 1
+        const double dtf = (k >= 1 && c.variable_dt) ? 1.0 : 0.0;
+        if (has_lb) lin_row_accum<I>(-(delta - c.du_lb[I] * T), AS(4 + 2 * I, k), ALAM(4 + 2 * I, k), -1.0, dtf * c.du_lb[I], true, cross * 1.0, H, g0, g1, GL, hb, Cc, acc, rp);
+        if (has_ub) lin_row_accum<I>(delta - c.du_ub[I] * T, AS(5 + 2 * I, k), ALAM(5 + 2 * I, k), 1.0, -dtf * c.du_ub[I], true, cross * -1.0, H, g0, g1, GL, hb, Cc, acc, rp);
+    }
+    // rate rows of stage k+1: Delta' = u_{k+1} - u_k (u_{N-1} := u_ref = 0); derivative wrt u_k is -sgn
+    {
+        const int kk = k + 1;
+        const double un = (kk <= N - 2) ? AU(I, kk) : 0.0;
+        const double delta = un - u_i;
+        const double dtf = c.variable_dt ? 1.0 : 0.0;
+        if (has_lb) lin_row_accum<I>(-(delta - c.du_lb[I] * dt), AS(4 + 2 * I, kk), ALAM(4 + 2 * I, kk), 1.0, dtf * c.du_lb[I], false, 0.0, H, g0, g1, GL, hb, Cc, acc, rp);
+        if (has_ub) lin_row_accum<I>(delta - c.du_ub[I] * dt, AS(5 + 2 * I, kk), ALAM(5 + 2 * I, kk), -1.0, -dtf * c.du_ub[I], false, 0.0, H, g0, g1, GL, hb, Cc, acc, rp);
+    }
 }
 
 // Stage functions + derivatives of stage k -> condensed KKT record (G holds the mu-independent part g0, the
@@ -77,15 +144,18 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
 #pragma unroll
     for (int i = 0; i < 6; ++i) Bm[i] = 0;
     Cc[0] = Cc[1] = 0.0;
+    RowProd rp; rp.p = 1.0; rp.n = 0;
     const double x[3] = {AX(0, k), AX(1, k), AX(2, k)};
     const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
+    double sc[2];
+    sincos(x[2], &sc[0], &sc[1]);  // shared by the dynamics and every footprint distance of this stage
 
     if (k <= N - 2)
     {
         const double u[2] = {AU(0, k), AU(1, k)};
         const double nu[3] = {ANU(0, k), ANU(1, k), ANU(2, k)};
         double f[3], J[9], Hc[6];
-        dynamics_derivs(c, x[2], u[0], u[1], nu, f, J, Hc);
+        dynamics_derivs(c, x[2], u[0], u[1], nu, f, J, Hc, sc);
         e[0] = x[0] + dt * f[0] - AX(0, k + 1);
         e[1] = x[1] + dt * f[1] - AX(1, k + 1);
         e[2] = dt * f[2] - normalize_theta(AX(2, k + 1) - x[2]);
@@ -104,11 +174,13 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
         // quadratic running cost (k = 0 state term is a constant: its gradient is never used since x_0 is fixed)
         if (has_quadratic(c))
         {
-            double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             double o = 0.0;
+#pragma unroll
             for (int i = 0; i < 3; ++i)
             {
                 double gi = 0.0;
+#pragma unroll
                 for (int j = 0; j < 3; ++j)
                 {
                     gi += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j];
@@ -117,9 +189,11 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
                 }
                 g0[i] += gi; GL[i] += gi;
             }
+#pragma unroll
             for (int i = 0; i < 2; ++i)
             {
                 double gi = 0.0;
+#pragma unroll
                 for (int j = 0; j < 2; ++j)
                 {
                     gi += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j];
@@ -140,38 +214,9 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
         H[hidx(2, 2)] += dt * Hc[0]; H[hidx(2, 3)] += dt * Hc[1]; H[hidx(2, 4)] += dt * Hc[2];
         H[hidx(3, 3)] += dt * Hc[3]; H[hidx(3, 4)] += dt * Hc[4]; H[hidx(4, 4)] += dt * Hc[5];
         if (c.variable_dt) { hb[2] += fx_nu; hb[3] += fu_nu0; hb[4] += fu_nu1; }
-        // ---- linear rows owned by stage k (bounds 0..3, rate rows 4..7) and the rate rows of stage k+1 (gather) ----
-        for (int pass = 0; pass < 2; ++pass)
-        {
-            const int kk = k + pass;           // owner stage of the rows
-            const int s0 = pass == 0 ? 0 : 4;  // next stage: rate rows only
-            for (int sl = s0; sl < 8; ++sl)
-            {
-                if (!lin_row_active(c, N, kk, sl, uprev_dt)) continue;
-                if (pass == 1 && kk > N - 1) continue;
-                const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
-                double uk, um;
-                if (pass == 0) { uk = u[i]; um = (k >= 1) ? AU(i, k - 1) : AIN(IN_UPREV + i); }
-                else { uk = (kk <= N - 2) ? AU(i, kk) : 0.0; um = u[i]; }
-                double gu, gum, gdt;
-                const double g = lin_row(c, N, kk, sl, uk, um, dt, uprev_dt, gu, gum, gdt);
-                const double s = AS(sl, kk), lam = ALAM(sl, kk);
-                const double r = g + s, sig = lam / s, c0 = sig * r, c1 = 1.0 / s;
-                const double gmine = (pass == 0) ? gu : gum;  // gradient entry on u_k[i]
-                if (gmine != 0.0)
-                {
-                    g0[3 + i] += c0 * gmine; g1[3 + i] += c1 * gmine; GL[3 + i] += lam * gmine;
-                    H[hidx(3 + i, 3 + i)] += sig * gmine * gmine;
-                    if (gdt != 0.0) hb[3 + i] += sig * gmine * gdt;
-                    if (pass == 0 && gum != 0.0) Cc[i] += sig * gu * gum;
-                }
-                if (pass == 0)
-                {
-                    row_stats(acc, r, s, lam);
-                    if (gdt != 0.0) { acc.gt0 += c0 * gdt; acc.gt1 += c1 * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt; }
-                }
-            }
-        }
+        // linear rows touching u_k (own bounds, own rate rows, rate rows of stage k+1)
+        lin_rows_component<0>(c, L, W, uprev_dt, k, dt, u[0], H, g0, g1, GL, hb, Cc, acc, rp);
+        lin_rows_component<1>(c, L, W, uprev_dt, k, dt, u[1], H, g0, g1, GL, hb, Cc, acc, rp);
     }
     else
     {
@@ -179,11 +224,13 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
         // contribution to u_{N-2} is gathered by stage N-2 above), minimum-time term
         if (has_terminal_cost(c))
         {
-            double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             double o = 0.0;
+#pragma unroll
             for (int i = 0; i < 3; ++i)
             {
                 double gi = 0.0;
+#pragma unroll
                 for (int j = 0; j < 3; ++j)
                 {
                     gi += (c.Qf[i * 3 + j] + c.Qf[j * 3 + i]) * d[j];
@@ -203,9 +250,9 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
             const double um = (sl >= 4) ? AU(i, k - 1) : 0.0;
             const double g = lin_row(c, N, k, sl, 0.0, um, dt, uprev_dt, gu, gum, gdt);
             const double s = AS(sl, k), lam = ALAM(sl, k);
-            const double r = g + s, sig = lam / s, c0 = sig * r, c1 = 1.0 / s;
-            row_stats(acc, r, s, lam);
-            if (gdt != 0.0) { acc.gt0 += c0 * gdt; acc.gt1 += c1 * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt; }
+            const double rs = 1.0 / s, r = g + s, sig = lam * rs, c0 = sig * r;
+            row_stats(acc, rp, r, s, lam);
+            acc.gt0 += c0 * gdt; acc.gt1 += rs * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt;
         }
     }
     // multiplier of the previous defect: d/dx_k ( nu_{k-1}^T e_{k-1} ) = -nu_{k-1}
@@ -230,7 +277,7 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
             }
         }
     }
-    // obstacle rows (k = 1..N-2)
+    // obstacle rows (k = 1..N-2); value and gradient are kept for the line-search kernel
     if (k >= 1 && k <= N - 2)
     {
         for (int j = 0; j < K; ++j)
@@ -238,22 +285,27 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
             const int oi = (int)AOBS(j, k);
             if (oi < 0) continue;
             double gd[3], hd[6];
-            const double dist = footprint_distance<true, true>(c, x[0], x[1], x[2], (int)W[L.oOTYPE + oi],
-                                                               W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, hd);
+            const double dist = footprint_distance_sc<true, true>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
+                                                                  W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, hd);
             const double g = c.min_obstacle_dist - dist;
             const double s = AS(8 + j, k), lam = ALAM(8 + j, k);
-            const double r = g + s, sig = lam / s, c0 = sig * r, c1 = 1.0 / s;
-            row_stats(acc, r, s, lam);
-            double gr[3] = {-gd[0], -gd[1], -gd[2]};
+            const double rs = 1.0 / s, r = g + s, sig = lam * rs, c0 = sig * r;
+            row_stats(acc, rp, r, s, lam);
+            const double gr[3] = {-gd[0], -gd[1], -gd[2]};
+            AOG(4 * j + 0, k) = g; AOG(4 * j + 1, k) = gr[0]; AOG(4 * j + 2, k) = gr[1]; AOG(4 * j + 3, k) = gr[2];
             int q = 0;
+#pragma unroll
             for (int i = 0; i < 3; ++i)
             {
-                g0[i] += c0 * gr[i]; g1[i] += c1 * gr[i]; GL[i] += lam * gr[i];
+                g0[i] += c0 * gr[i]; g1[i] += rs * gr[i]; GL[i] += lam * gr[i];
+#pragma unroll
                 for (int jj = i; jj < 3; ++jj, ++q) H[hidx(i, jj)] += lam * (-hd[q]) + sig * gr[i] * gr[jj];
             }
         }
     }
+    rowprod_flush(rp, acc.blog);
     // dual infeasibility over the free variables of this stage
+#pragma unroll
     for (int i = 0; i < 5; ++i)
     {
         if (i < 3 && k == 0) continue;
@@ -345,13 +397,14 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const 
     const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
     double du[2] = {0, 0};
     if (k <= N - 2) { du[0] = ASTEP(3, k); du[1] = ASTEP(4, k); }
-    // rows
+    // rows: slack / multiplier steps.  Linear rows are re-evaluated (pure arithmetic); obstacle rows reuse the value and
+    // gradient stored by the EVAL kernel at this very point.  r0 = g + s is kept for the analytic trial evaluation.
     for (int sl = 0; sl < 8 + K; ++sl)
     {
         double g, gdz;
         if (sl < 8)
         {
-            if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; continue; }
+            if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; AR0(sl, k) = 0.0; continue; }
             const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
             const double uk = (k <= N - 2) ? AU(i, k) : 0.0;
             const double um = (sl >= 4) ? ((k >= 1) ? AU(i, k - 1) : AIN(IN_UPREV + i)) : 0.0;
@@ -364,22 +417,22 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const 
         {
             const int j = sl - 8;
             const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(j, k) : -1;
-            if (oi < 0) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; continue; }
-            double gd[3];
-            const double dist = footprint_distance<true, false>(c, x[0], x[1], x[2], (int)W[L.oOTYPE + oi],
-                                                                W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, nullptr);
-            g = c.min_obstacle_dist - dist;
-            gdz = -(gd[0] * dx[0] + gd[1] * dx[1] + gd[2] * dx[2]);
+            if (oi < 0) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; AR0(sl, k) = 0.0; continue; }
+            g = AOG(4 * j + 0, k);
+            gdz = AOG(4 * j + 1, k) * dx[0] + AOG(4 * j + 2, k) * dx[1] + AOG(4 * j + 3, k) * dx[2];
         }
         const double s = AS(sl, k), lam = ALAM(sl, k);
-        const double ds = -(g + s) - gdz;
-        const double dl = mu / s - lam - (lam / s) * ds;
+        const double rs = 1.0 / s;
+        const double r0 = g + s;
+        const double ds = -r0 - gdz;
+        const double dl = mu * rs - lam - (lam * rs) * ds;
         ADS(sl, k) = ds;
         ADLAM(sl, k) = dl;
+        AR0(sl, k) = r0;
         if (ds < 0) acc.a_p = fmin(acc.a_p, -tau * s / ds);
         if (dl < 0) acc.a_d = fmin(acc.a_d, -tau * lam / dl);
-        acc.dphi_bar += -mu * ds / s;
-        acc.curv += (lam / s) * ds * ds;
+        acc.dphi_bar += -mu * ds * rs;
+        acc.curv += (lam * rs) * ds * ds;
     }
     // directional derivative of the objective
     double dJ = 0.0;
@@ -439,20 +492,27 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const 
 }
 
 struct TrialAcc { double obj, inf1, blog; };
-// merit pieces of stage k at the trial point z + alpha dz, s + alpha ds
+// merit pieces of stage k at the trial point z + alpha dz, s + alpha ds.  Linear rows are exact in alpha:
+// g(alpha) + s(alpha) = (1 - alpha) r0, so only the dynamics defect, the objective and the obstacle rows are re-evaluated.
 HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, double uprev_dt, int k, double alpha, TrialAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dtt = ASC(MPCB200_SC_DT) + (c.variable_dt ? alpha * ASC(MPCB200_SC_DDT) : 0.0);
     const double x[3] = {AX(0, k) + alpha * ASTEP(0, k), AX(1, k) + alpha * ASTEP(1, k), AX(2, k) + alpha * ASTEP(2, k)};
     const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
-    double u[2] = {0, 0};
+    double sc[2];
+    sincos(x[2], &sc[0], &sc[1]);
     if (k <= N - 2)
     {
-        u[0] = AU(0, k) + alpha * ASTEP(3, k);
-        u[1] = AU(1, k) + alpha * ASTEP(4, k);
+        const double u[2] = {AU(0, k) + alpha * ASTEP(3, k), AU(1, k) + alpha * ASTEP(4, k)};
         double f[3];
-        dynamics_value(c, x[2], u[0], u[1], f);
+        if (c.robot_type == MPCB200_ROBOT_KIN_BICYCLE) dynamics_value(c, x[2], u[0], u[1], f);
+        else
+        {
+            f[0] = u[0] * sc[1]; f[1] = u[0] * sc[0];
+            f[2] = c.robot_type == MPCB200_ROBOT_UNICYCLE ? u[1]
+                 : (c.robot_type == MPCB200_ROBOT_SIMPLE_CAR ? u[0] * tan(u[1]) / c.wheelbase : u[0] * sin(u[1]) / c.wheelbase);
+        }
         const double xn[3] = {AX(0, k + 1) + alpha * ASTEP(0, k + 1), AX(1, k + 1) + alpha * ASTEP(1, k + 1),
                               AX(2, k + 1) + alpha * ASTEP(2, k + 1)};
         acc.inf1 += fabs(x[0] + dtt * f[0] - xn[0]) + fabs(x[1] + dtt * f[1] - xn[1]) +
@@ -461,9 +521,13 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
         {
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             double o = 0.0;
+#pragma unroll
             for (int i = 0; i < 3; ++i)
+#pragma unroll
                 for (int j = 0; j < 3; ++j) o += d[i] * c.Q[i * 3 + j] * d[j];
+#pragma unroll
             for (int i = 0; i < 2; ++i)
+#pragma unroll
                 for (int j = 0; j < 2; ++j) o += u[i] * c.R[i * 2 + j] * u[j];
             acc.obj += o;
         }
@@ -475,7 +539,9 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
         {
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             double o = 0.0;
+#pragma unroll
             for (int i = 0; i < 3; ++i)
+#pragma unroll
                 for (int j = 0; j < 3; ++j) o += d[i] * c.Qf[i * 3 + j] * d[j];
             acc.obj += o;
         }
@@ -492,31 +558,26 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
                 acc.obj += c.vp_orientation_weight * normalize_theta(W[L.oVP + 3 * j + 2] - x[2]);
         }
     }
-    for (int sl = 0; sl < 8 + K; ++sl)
+    RowProd rp; rp.p = 1.0; rp.n = 0;
+    const double oma = 1.0 - alpha;
+    for (int sl = 0; sl < 8; ++sl)
     {
-        double g;
-        if (sl < 8)
-        {
-            if (!lin_row_active(c, N, k, sl, uprev_dt)) continue;
-            const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
-            const double uk = (k <= N - 2) ? u[i] : 0.0;
-            const double um = (sl >= 4) ? ((k >= 1) ? AU(i, k - 1) + alpha * ASTEP(3 + i, k - 1) : AIN(IN_UPREV + i)) : 0.0;
-            double gu, gum, gdt;
-            g = lin_row(c, N, k, sl, uk, um, dtt, uprev_dt, gu, gum, gdt);
-        }
-        else
-        {
-            const int j = sl - 8;
-            const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(j, k) : -1;
-            if (oi < 0) continue;
-            const double dist = footprint_distance<false, false>(c, x[0], x[1], x[2], (int)W[L.oOTYPE + oi],
-                                                                 W + L.oOBST + oi * MPCB200_OBST_STRIDE, nullptr, nullptr);
-            g = c.min_obstacle_dist - dist;
-        }
-        const double s = AS(sl, k) + alpha * ADS(sl, k);
-        acc.inf1 += fabs(g + s);
-        acc.blog += log(s);
+        if (!lin_row_active(c, N, k, sl, uprev_dt)) continue;
+        acc.inf1 += fabs(oma * AR0(sl, k));
+        rowprod_add(rp, AS(sl, k) + alpha * ADS(sl, k), acc.blog);
     }
+    if (k >= 1 && k <= N - 2)
+        for (int j = 0; j < K; ++j)
+        {
+            const int oi = (int)AOBS(j, k);
+            if (oi < 0) continue;
+            const double dist = footprint_distance_sc<false, false>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
+                                                                    W + L.oOBST + oi * MPCB200_OBST_STRIDE, nullptr, nullptr);
+            const double sn = AS(8 + j, k) + alpha * ADS(8 + j, k);
+            acc.inf1 += fabs(c.min_obstacle_dist - dist + sn);
+            rowprod_add(rp, sn, acc.blog);
+        }
+    rowprod_flush(rp, acc.blog);
 }
 
 // accept the step: z, s, lambda, nu of stage k

@@ -177,15 +177,90 @@ __global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double up
     }
 }
 
+// ---- kernel: regroup -- assign tile slots so that instances in the same state share tiles ------------------------------
+// key 0: active, last factorisation needed no regularisation; key 1: active, regularised last time (will sweep more
+// than once); key 2: finished.  The lane-per-instance KKT kernel pays max-over-lanes per warp, so homogeneous tiles
+// remove most of the divergence (and tiles of finished instances exit immediately).  Results do not depend on the slot.
+__global__ void __launch_bounds__(1024) regroup_kernel(WsLayout L, const double* ws, int B, int* slot_of, int* inst_of_slot, int nslots)
+{
+    __shared__ int wcount[3][32];   // per-warp counts of the current chunk -> exclusive scan
+    __shared__ int chunk_total[3];
+    __shared__ int running[3];      // next free slot of each key class
+    __shared__ int total[3];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < 3) total[tid] = 0;
+    __syncthreads();
+    // pass 0: class sizes
+    for (int c0 = 0; c0 < B; c0 += 1024)
+    {
+        const int b = c0 + tid;
+        int key = -1;
+        if (b < B)
+        {
+            const double* W = ws + (int64_t)b * L.stride;
+            key = ASC(MPCB200_SC_STATUS) >= 0.0 ? 2 : (ASC(MPCB200_SC_DELTA_LAST) > 0.0 ? 1 : 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const unsigned m = __ballot_sync(FULLMASK, key == k);
+            if (lane == 0 && m) atomicAdd(&total[k], __popc(m));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { running[0] = 0; running[1] = total[0]; running[2] = total[0] + total[1]; }
+    __syncthreads();
+    // pass 1: deterministic slot assignment (instance order preserved inside a class)
+    for (int c0 = 0; c0 < B; c0 += 1024)
+    {
+        const int b = c0 + tid;
+        int key = -1;
+        if (b < B)
+        {
+            const double* W = ws + (int64_t)b * L.stride;
+            key = ASC(MPCB200_SC_STATUS) >= 0.0 ? 2 : (ASC(MPCB200_SC_DELTA_LAST) > 0.0 ? 1 : 0);
+        }
+        int myoff = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const unsigned m = __ballot_sync(FULLMASK, key == k);
+            if (key == k) myoff = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) wcount[k][wid] = __popc(m);
+        }
+        __syncthreads();
+        if (wid < 3)
+        {
+            const int v = wcount[wid][lane];
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+            wcount[wid][lane] = incl - v;
+            if (lane == 31) chunk_total[wid] = incl;
+        }
+        __syncthreads();
+        if (key >= 0)
+        {
+            const int sidx = running[key] + wcount[key][wid] + myoff;
+            slot_of[b] = sidx;
+            inst_of_slot[sidx] = b;
+        }
+        __syncthreads();
+        if (tid < 3) running[tid] += chunk_total[tid];
+        __syncthreads();
+    }
+    for (int sidx = B + tid; sidx < nslots; sidx += 1024) inst_of_slot[sidx] = -1;
+}
+
 // ---- kernel: PHASE_EVAL -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, int B, double uprev_dt, int* n_active)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, const int* slot_of, int B, double uprev_dt, int* n_active)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;  // finished instance: exact no-op
-    double* Kb = kkt_tiles + (size_t)(warp >> 5) * N * KW * TILE + (warp & 31);
+    const int slot = slot_of[warp];
+    double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
     EvalAcc a;
     evalacc_init(a);
     for (int k = lane; k < N; k += 32) eval_stage(c, L, W, Kb, uprev_dt, k, a);
@@ -214,13 +289,13 @@ struct StepOut
 };
 
 template <bool EXT>
-__global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, double* ric_tiles, int B,
+__global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, double* ric_tiles, const int* inst_of_slot, int B,
                                                        unsigned long long* counters)
 {
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
-    const int b = tile * TILE + lane;
-    if (b >= B) return;
+    const int b = inst_of_slot[tile * TILE + lane];
+    if (b < 0) return;
     double* W = ws + (int64_t)b * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
@@ -240,14 +315,15 @@ __global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double*
 }
 
 // ---- kernel: PHASE_LINESEARCH -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, int B, double uprev_dt)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
-    const double* Kb = kkt_tiles + (size_t)(warp >> 5) * N * KW * TILE + (warp & 31);
+    const int slot = slot_of[warp];
+    const double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
     LsAcc a;
     lsacc_init(a);
     for (int k = lane; k < N; k += 32) ls_stage_steps(c, L, W, Kb, uprev_dt, k, a);
@@ -361,7 +437,7 @@ struct mpcb200_handle
     int *d_obst_count, *d_obst_type, *d_vp_count;
     unsigned char* d_reinit;
     double *d_useq, *d_xseq, *d_dt, *d_kkt, *d_upacked;
-    int *d_status, *d_iters, *d_nactive;
+    int *d_status, *d_iters, *d_nactive, *d_slot_of, *d_inst_of_slot;
     unsigned long long* d_counters;
     int* h_nactive;  // pinned
     double* d_flush; size_t flush_n;
@@ -469,6 +545,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
     CKC(cudaMalloc(&h->d_kkt, B * 8)); CKC(cudaMalloc(&h->d_upacked, B * (N - 1) * 2 * 8));
     CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 4));
+    CKC(cudaMalloc(&h->d_slot_of, B * 4)); CKC(cudaMalloc(&h->d_inst_of_slot, ((B + TILE - 1) / TILE) * TILE * 4));
     CKC(cudaMalloc(&h->d_counters, 16)); CKC(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
     CKC(cudaMallocHost(&h->h_nactive, 4));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
@@ -490,7 +567,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->ws, h->kkt_tiles, h->ric_tiles, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
-                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush, h->d_counters};
+                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush, h->d_counters, h->d_slot_of, h->d_inst_of_slot};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
@@ -541,19 +618,28 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
     {
         case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold); break;
         case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer); break;
-        case MPCB200_PHASE_EVAL: eval_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, B, h->uprev_dt, h->d_nactive); break;
+        case MPCB200_PHASE_EVAL: eval_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
         case MPCB200_PHASE_KKT:
         {
             const bool ext = h->cfg.variable_dt || h->cfg.xf_fixed[0] || h->cfg.xf_fixed[1] || h->cfg.xf_fixed[2];
             const int ntiles = (B + TILE - 1) / TILE;
-            if (ext) kkt_lane_kernel<true><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, B, h->d_counters);
-            else kkt_lane_kernel<false><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, B, h->d_counters);
+            if (ext) kkt_lane_kernel<true><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
+            else kkt_lane_kernel<false><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
             break;
         }
-        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, B, h->uprev_dt); break;
+        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt); break;
         default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
     }
     if (timed) ev_end(h);
+    h->stats.launches_total += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_regroup(mpcb200_handle* h, int B)
+{
+    const int nslots = ((B + TILE - 1) / TILE) * TILE;
+    regroup_kernel<<<1, 1024, 0, h->stream>>>(h->L, h->ws, B, h->d_slot_of, h->d_inst_of_slot, nslots);
     h->stats.launches_total += 1;
     CK(cudaGetLastError());
     return 0;
@@ -634,6 +720,7 @@ static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_
         {
             const bool poll = (it % 4 == 3) || it == h->cfg.max_iter;
             if (poll) CK(cudaMemsetAsync(h->d_nactive, 0, 4, h->stream));
+            if ((rc = launch_regroup(h, B))) return rc;
             if ((rc = launch_phase(h, MPCB200_PHASE_EVAL, B, 0, 0, true))) return rc;
             if (poll)
             {
@@ -767,12 +854,17 @@ extern "C" int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst)
     {   // device layout: 32-instance interleaved tiles [tile][k][42][32]; the API presents [B][42][N]
         const size_t ntiles = ((size_t)B + TILE - 1) / TILE, tw = (size_t)N * KW * TILE;
         std::vector<double> tmp(ntiles * tw);
+        std::vector<int> slot(B);
         CK(cudaMemcpyAsync(tmp.data(), h->kkt_tiles, tmp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(slot.data(), h->d_slot_of, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         for (int b = 0; b < B; ++b)
+        {
+            const int sl = slot[b];
             for (int k = 0; k < N; ++k)
                 for (int f = 0; f < KW; ++f)
-                    dst[((size_t)b * KW + f) * N + k] = tmp[(size_t)(b / TILE) * tw + ((size_t)k * KW + f) * TILE + (b % TILE)];
+                    dst[((size_t)b * KW + f) * N + k] = tmp[(size_t)(sl / TILE) * tw + ((size_t)k * KW + f) * TILE + (sl % TILE)];
+        }
         return 0;
     }
     const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * N;
@@ -792,10 +884,12 @@ extern "C" int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const doubl
     {
         const size_t ntiles = ((size_t)B + TILE - 1) / TILE, tw = (size_t)N * KW * TILE;
         std::vector<double> tmp(ntiles * tw, 0.0);
+        std::vector<int> slot(B);
+        CK(cudaMemcpy(slot.data(), h->d_slot_of, (size_t)B * 4, cudaMemcpyDeviceToHost));
         for (int b = 0; b < B; ++b)
             for (int k = 0; k < N; ++k)
                 for (int f = 0; f < KW; ++f)
-                    tmp[(size_t)(b / TILE) * tw + ((size_t)k * KW + f) * TILE + (b % TILE)] = src[((size_t)b * KW + f) * N + k];
+                    tmp[(size_t)(slot[b] / TILE) * tw + ((size_t)k * KW + f) * TILE + (slot[b] % TILE)] = src[((size_t)b * KW + f) * N + k];
         CK(cudaMemcpyAsync(h->kkt_tiles, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
@@ -811,6 +905,7 @@ extern "C" int mpcb200_run_phase(mpcb200_handle* h, int phase, int B)
     int rc = check_batch(h, B);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
+    if (phase == MPCB200_PHASE_EVAL && (rc = launch_regroup(h, B))) return rc;
     if ((rc = launch_phase(h, phase, B, phase == MPCB200_PHASE_INIT ? 0 : 0, 1, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     ev_collect(h);

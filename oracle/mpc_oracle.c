@@ -800,7 +800,7 @@ void orc_init_controls(const orc_problem* p, orc_ws* ws)
 #define ORC_SLACK_PUSH 1e-2
 #define ORC_ARMIJO 1e-4
 #define ORC_MAX_BACKTRACK 8
-#define ORC_MAX_INERTIA_TRIES 12
+#define ORC_MAX_INERTIA_TRIES 5
 #define ORC_MAX_DELTA 1e8
 #define ORC_TINY_STEP 1e-8
 #define ORC_TINY_STEP_COUNT 2
@@ -1154,6 +1154,7 @@ int orc_kkt_solve(const orc_problem* p, orc_ws* ws, double delta)
 #define KK(f, k) KKT[((f)) * N + (k)]
     double P[25], PI[25], TH[25];
     mat_zero(P, 25); mat_zero(PI, 25); mat_zero(TH, 25);
+    ws->SCAL[MPCB200_SC_LMIN] = 0.0;
     const int dt_free = c->variable_dt;
     /* terminal stage k = N-1: y = (dx_{N-1}, du_{N-2}) */
     {
@@ -1230,7 +1231,13 @@ int orc_kkt_solve(const orc_problem* p, orc_ws* ws, double delta)
         /* eliminate v = z[5..6] */
         double a = MM[5][5], b = 0.5 * (MM[5][6] + MM[6][5]), d = MM[6][6];
         double det = a * d - b * b;
-        if (!(a > 0.0) || !(det > 1e-14 * a * (d > 0 ? d : 1.0)) || !(d > 0.0)) return 1;
+        if (!(a > 0.0) || !(det > 1e-14 * a * (d > 0 ? d : 1.0)) || !(d > 0.0))
+        {
+            /* smallest eigenvalue of the failing 2x2 block: lets the caller jump straight to a sufficient delta */
+            double hm = 0.5 * (a + d), hd = 0.5 * (a - d);
+            ws->SCAL[MPCB200_SC_LMIN] = hm - sqrt(hd * hd + b * b);
+            return 1;
+        }
         double i00 = d / det, i01 = -b / det, i11 = a / det;
         double KGm[2][5], KTm[2][5]; /* Mvv^-1 Mvy, Mvv^-1 Nv */
         for (int j = 0; j < 5; ++j)
