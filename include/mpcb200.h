@@ -237,7 +237,7 @@ int mpcb200_flush_l2(mpcb200_handle* h);
 #define MPCB200_SC_GLDT 17   /* dL/d(dt) */
 #define MPCB200_SC_NBT 18    /* line-search backtracks so far */
 #define MPCB200_SC_COLD 19   /* 1 until the instance has been solved once (cold start pending) */
-#define MPCB200_SC_LMIN 21   /* smallest eigenvalue of the pivot block that failed the inertia test (0 if none) */
+#define MPCB200_SC_DEFER 21  /* 1 = the KKT phase spent its factorisation budget: null step, regularisation resumes next iteration */
 #define MPCB200_SC_TINY 20   /* consecutive iterations with a step length below 1e-8 (2 => the instance is given up) */
 
 int mpcb200_ws_count(const mpcb200_handle* h, int field);  /* number of components of a field (e.g. RS) */

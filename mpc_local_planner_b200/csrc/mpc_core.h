@@ -51,9 +51,10 @@ struct WsLayout
 #define TAU_MIN 0.99
 #define SLACK_PUSH 1e-2
 #define ARMIJO 1e-4
-#define MAX_BACKTRACK 8
-#define MAX_INERTIA_TRIES 5
+#define MAX_BACKTRACK 3
+#define MAX_INERTIA_TRIES 2      // factorisations per IPM iteration (escalation resumes in the next iteration: a retry of one lane stalls its whole launch)
 #define MAX_DELTA 1e8
+#define DELTA_FLOOR 1e-5
 #define TINY_STEP 1e-8
 #define TINY_STEP_COUNT 2
 #define KAPPA_SIGMA 1e10

@@ -336,7 +336,8 @@ HD inline int riccati_solve_lane(const Cfg& c, int N, const Rec& rec, const Ric&
     const int dt_free = c.variable_dt;
     RicState<EXT> s;
     double th[5] = {1.0, 0, 0, 0, 0};
-    double delta = 0.0;
+    // after a regularised iteration the first attempt is delta_last/3 (decays back to 0): a failed attempt costs a full sweep
+    double delta = (dlast > 0.0 && dlast / 3.0 >= DELTA_FLOOR) ? dlast / 3.0 : 0.0;
     int ok = 0, nreg = 0;
     for (int tries = 0; tries < MAX_INERTIA_TRIES; ++tries)
     {

@@ -172,7 +172,7 @@ __global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double up
     {
         ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
         ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
-        ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0;
+        ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0; ASC(MPCB200_SC_DEFER) = 0.0;
         if (repair) ASC(MPCB200_SC_COLD) = 0.0;
     }
 }
@@ -308,10 +308,18 @@ __global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double*
                                            &ddt, &delta, &nreg);
     if (counters) { atomicAdd(counters, 1ull); atomicAdd(counters + 1, (unsigned long long)(nreg + 1)); }
     ASC(MPCB200_SC_NREG) += (double)nreg;
+    if (!ok && delta <= MAX_DELTA)
+    {
+        // factorisation budget of this iteration spent: null step, the next iteration resumes at this delta (DELTA_LAST / 3)
+        ASC(MPCB200_SC_DELTA_LAST) = 3.0 * delta;
+        ASC(MPCB200_SC_DEFER) = 1.0;
+        return;
+    }
     if (!ok) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; return; }
+    ASC(MPCB200_SC_DEFER) = 0.0;
     ASC(MPCB200_SC_DDT) = ddt;
     ASC(MPCB200_SC_DELTA) = delta;
-    if (delta > 0.0) ASC(MPCB200_SC_DELTA_LAST) = delta;
+    ASC(MPCB200_SC_DELTA_LAST) = delta;
 }
 
 // ---- kernel: PHASE_LINESEARCH -------------------------------------------------------------------------------
@@ -322,6 +330,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, W
     double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    if (ASC(MPCB200_SC_DEFER) != 0.0)
+    {
+        __syncwarp();
+        if (lane == 0) { ASC(MPCB200_SC_DEFER) = 0.0; ASC(MPCB200_SC_ITER) += 1.0; ASC(MPCB200_SC_ALPHA) = 0.0; }
+        return;
+    }
     const int slot = slot_of[warp];
     const double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
     LsAcc a;

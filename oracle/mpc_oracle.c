@@ -799,9 +799,10 @@ void orc_init_controls(const orc_problem* p, orc_ws* ws)
 #define ORC_TAU_MIN 0.99
 #define ORC_SLACK_PUSH 1e-2
 #define ORC_ARMIJO 1e-4
-#define ORC_MAX_BACKTRACK 8
-#define ORC_MAX_INERTIA_TRIES 5
+#define ORC_MAX_BACKTRACK 3
+#define ORC_MAX_INERTIA_TRIES 2 /* factorisations per IPM iteration; escalation continues in the next iteration */
 #define ORC_MAX_DELTA 1e8
+#define ORC_DELTA_FLOOR 1e-5
 #define ORC_TINY_STEP 1e-8
 #define ORC_TINY_STEP_COUNT 2
 #define ORC_KAPPA_SIGMA 1e10
@@ -925,7 +926,6 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
         GL[IX(4, k)] += dt * fu_nu[1];
         for (int i = 0; i < 3; ++i) GL[IX(i, k + 1)] -= nu[i];
         gl_dt += nu[0] * f[0] + nu[1] * f[1] + nu[2] * f[2];
-        if (getenv("ORC_GNDYN")) { for (int i = 0; i < 6; ++i) Hc[i] = 0.0; }
         hadd(KKT, N, k, 2, 2, dt * Hc[0]);
         hadd(KKT, N, k, 2, 3, dt * Hc[1]);
         hadd(KKT, N, k, 2, 4, dt * Hc[2]);
@@ -1006,7 +1006,7 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
                 }
                 int q = 0;
                 for (int i = 0; i < 3; ++i)
-                    for (int j = i; j < 3; ++j, ++q) hadd(KKT, N, k, i, j, (getenv("ORC_GNOBS") ? 0.0 : lam * h6[q]) + sig * grad[i] * grad[j]);
+                    for (int j = i; j < 3; ++j, ++q) hadd(KKT, N, k, i, j, lam * h6[q] + sig * grad[i] * grad[j]);
                 continue;
             }
             /* u_k part */
@@ -1154,7 +1154,6 @@ int orc_kkt_solve(const orc_problem* p, orc_ws* ws, double delta)
 #define KK(f, k) KKT[((f)) * N + (k)]
     double P[25], PI[25], TH[25];
     mat_zero(P, 25); mat_zero(PI, 25); mat_zero(TH, 25);
-    ws->SCAL[MPCB200_SC_LMIN] = 0.0;
     const int dt_free = c->variable_dt;
     /* terminal stage k = N-1: y = (dx_{N-1}, du_{N-2}) */
     {
@@ -1232,12 +1231,7 @@ int orc_kkt_solve(const orc_problem* p, orc_ws* ws, double delta)
         double a = MM[5][5], b = 0.5 * (MM[5][6] + MM[6][5]), d = MM[6][6];
         double det = a * d - b * b;
         if (!(a > 0.0) || !(det > 1e-14 * a * (d > 0 ? d : 1.0)) || !(d > 0.0))
-        {
-            /* smallest eigenvalue of the failing 2x2 block: lets the caller jump straight to a sufficient delta */
-            double hm = 0.5 * (a + d), hd = 0.5 * (a - d);
-            ws->SCAL[MPCB200_SC_LMIN] = hm - sqrt(hd * hd + b * b);
             return 1;
-        }
         double i00 = d / det, i01 = -b / det, i11 = a / det;
         double KGm[2][5], KTm[2][5]; /* Mvv^-1 Mvy, Mvv^-1 Nv */
         for (int j = 0; j < 5; ++j)
@@ -1370,194 +1364,9 @@ static void trial_eval(const orc_problem* p, orc_ws* ws, const double* Xt, const
 }
 
 
-/* add sum_i grad g_i * (cvec_i / s_i) to the condensed gradient (rows' complementarity targets), returns nothing */
-static void rows_add_gradient(const orc_problem* p, orc_ws* ws, const double* cvec)
-{
-    const int N = ws->N, RS = ws->RS;
-    const double dt = ws->SCAL[MPCB200_SC_DT];
-    for (int k = 0; k < N; ++k)
-        for (int sl = 0; sl < RS; ++sl)
-        {
-            if (!row_active(p, ws, k, sl)) continue;
-            double grad[8];
-            row_value(p, ws, k, sl, ws->X, ws->U, dt, grad, NULL);
-            const double w = cvec[IX(sl, k)] / ws->S[IX(sl, k)];
-            for (int i = 0; i < 3; ++i) ws->KKT[(MPCB200_K_G + i) * N + k] += w * grad[i];
-            if (k <= N - 2) for (int i = 0; i < 2; ++i) ws->KKT[(MPCB200_K_G + 3 + i) * N + k] += w * grad[3 + i];
-            if (k >= 1) for (int i = 0; i < 2; ++i) ws->KKT[(MPCB200_K_G + 3 + i) * N + k - 1] += w * grad[5 + i];
-            ws->SCAL[MPCB200_SC_GT] += w * grad[7];
-        }
-}
-
-/* slack / multiplier steps for complementarity targets cvec; returns max step fractions (tau) */
-static void rows_steps(const orc_problem* p, orc_ws* ws, const double* cvec, double tau, double* a_p, double* a_d)
-{
-    const int N = ws->N, RS = ws->RS;
-    const double dt = ws->SCAL[MPCB200_SC_DT], ddt = ws->SCAL[MPCB200_SC_DDT];
-    double ap = 1.0, ad = 1.0;
-    for (int k = 0; k < N; ++k)
-        for (int sl = 0; sl < RS; ++sl)
-        {
-            if (!row_active(p, ws, k, sl)) { ws->DS[IX(sl, k)] = 0; ws->DLAM[IX(sl, k)] = 0; continue; }
-            double grad[8];
-            double g = row_value(p, ws, k, sl, ws->X, ws->U, dt, grad, NULL);
-            double gdz = 0.0;
-            for (int i = 0; i < 3; ++i) gdz += grad[i] * ws->STEP[IX(i, k)];
-            if (k <= N - 2) for (int i = 0; i < 2; ++i) gdz += grad[3 + i] * ws->STEP[IX(3 + i, k)];
-            if (k >= 1) for (int i = 0; i < 2; ++i) gdz += grad[5 + i] * ws->STEP[IX(3 + i, k - 1)];
-            gdz += grad[7] * ddt;
-            double s = ws->S[IX(sl, k)], lam = ws->LAM[IX(sl, k)];
-            double ds = -(g + s) - gdz;
-            double dl = cvec[IX(sl, k)] / s - lam - (lam / s) * ds;
-            ws->DS[IX(sl, k)] = ds; ws->DLAM[IX(sl, k)] = dl;
-            if (ds < 0 && -tau * s / ds < ap) ap = -tau * s / ds;
-            if (dl < 0 && -tau * lam / dl < ad) ad = -tau * lam / dl;
-        }
-    *a_p = ap; *a_d = ad;
-}
-
-/* EXPERIMENT: Mehrotra predictor-corrector with adaptive barrier parameter */
-static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res, int iter0);
-static int orc_solve_mehrotra(const orc_problem* p, orc_ws* ws, orc_result* res)
-{
-    double hist[4] = {1e300, 1e300, 1e300, 1e300};
-    const double hkappa = getenv("ORC_HKAPPA") ? atof(getenv("ORC_HKAPPA")) : 0.9999;
-    const int nhist = getenv("ORC_NHIST") ? atoi(getenv("ORC_NHIST")) : 4;
-    const mpcb200_config* c = p->cfg;
-    const int N = ws->N, RS = ws->RS;
-    int status = MPCB200_STATUS_MAX_ITER, iter = 0, nreg = 0, nbt = 0;
-    eval_info info;
-    double* G1 = (double*)malloc(sizeof(double) * (5 * N + 1));
-    double* cvec = (double*)calloc((size_t)RS * N, sizeof(double));
-    double* g0save = (double*)malloc(sizeof(double) * (5 * N + 1));
-    const int use_ls = getenv("ORC_MLS") != NULL;
-    for (;;)
-    {
-        eval_impl(p, ws, &info, G1);
-        ws->SCAL[MPCB200_SC_ITER] = (double)iter;
-        double e0 = scaled_error(&info, 0.0);
-        ws->SCAL[MPCB200_SC_ERR0] = e0;
-        if (e0 <= c->tol) { status = MPCB200_STATUS_CONVERGED; break; }
-        if (iter >= c->max_iter) break;
-        if (getenv("ORC_HYBRID"))
-        {
-            /* progress measure: sum of the three KKT error components */
-            double phi = info.dual_inf + info.prim_inf + (info.sl_max > 0 ? info.sl_max : 0);
-            double hmax = 0.0;
-            for (int i = 0; i < nhist; ++i) if (hist[i] < 1e299 && hist[i] > hmax) hmax = hist[i];
-            int filled = 0; for (int i = 0; i < nhist; ++i) filled += hist[i] < 1e299;
-            if (filled == nhist && phi > hkappa * hmax)
-            {
-                /* free mode stalled: continue in monotone mode from here */
-                double mu_cur = 0.0; int m = 0;
-                for (int k = 0; k < N; ++k) for (int sl = 0; sl < RS; ++sl) if (row_active(p, ws, k, sl)) { mu_cur += ws->S[IX(sl, k)] * ws->LAM[IX(sl, k)]; ++m; }
-                mu_cur /= (m > 0 ? m : 1);
-                if (mu_cur < c->tol / 10.0) mu_cur = c->tol / 10.0;
-                ws->SCAL[MPCB200_SC_MU] = mu_cur;
-                free(G1); free(cvec); free(g0save);
-                return orc_solve_monotone(p, ws, res, iter);
-            }
-            hist[iter % nhist] = phi;
-        }
-        const double dt = ws->SCAL[MPCB200_SC_DT];
-        /* current complementarity */
-        double mu_cur = 0.0; int m = 0;
-        for (int k = 0; k < N; ++k) for (int sl = 0; sl < RS; ++sl) if (row_active(p, ws, k, sl)) { mu_cur += ws->S[IX(sl, k)] * ws->LAM[IX(sl, k)]; ++m; }
-        mu_cur /= (m > 0 ? m : 1);
-        for (int k = 0; k < N; ++k) for (int i = 0; i < 5; ++i) g0save[IX(i, k)] = ws->KKT[(MPCB200_K_G + i) * N + k];
-        g0save[5 * N] = ws->SCAL[MPCB200_SC_GT];
-        /* predictor (affine scaling): targets 0 */
-        double delta = 0.0, dlast = ws->SCAL[MPCB200_SC_DELTA_LAST];
-        int ok = 0;
-        for (int tries = 0; tries < 40; ++tries)
-        {
-            if (orc_kkt_solve(p, ws, delta) == 0) { ok = 1; break; }
-            ++nreg;
-            if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : (dlast / 3.0 > 1e-20 ? dlast / 3.0 : 1e-20);
-            else delta *= (dlast == 0.0 ? 100.0 : 8.0);
-            if (delta > 1e20) break;
-        }
-        if (!ok) { status = MPCB200_STATUS_NUMERICAL_ERROR; break; }
-        if (delta > 0.0) ws->SCAL[MPCB200_SC_DELTA_LAST] = delta;
-        memset(cvec, 0, sizeof(double) * RS * N);
-        double aap, aad;
-        rows_steps(p, ws, cvec, 1.0, &aap, &aad);
-        double mu_aff = 0.0;
-        for (int k = 0; k < N; ++k) for (int sl = 0; sl < RS; ++sl) if (row_active(p, ws, k, sl))
-            mu_aff += (ws->S[IX(sl, k)] + aap * ws->DS[IX(sl, k)]) * (ws->LAM[IX(sl, k)] + aad * ws->DLAM[IX(sl, k)]);
-        mu_aff /= (m > 0 ? m : 1);
-        double sig = mu_aff / mu_cur; sig = sig * sig * sig;
-        if (sig > 1.0) sig = 1.0;
-        double mu_t = sig * mu_cur;
-        if (mu_t < c->tol / 10.0) mu_t = c->tol / 10.0;
-        /* corrector: targets mu_t - ds_a dl_a */
-        for (int k = 0; k < N; ++k) for (int sl = 0; sl < RS; ++sl)
-            cvec[IX(sl, k)] = row_active(p, ws, k, sl) ? mu_t - (getenv("ORC_NOCORR") ? 0.0 : ws->DS[IX(sl, k)] * ws->DLAM[IX(sl, k)]) : 0.0;
-        for (int k = 0; k < N; ++k) for (int i = 0; i < 5; ++i) ws->KKT[(MPCB200_K_G + i) * N + k] = g0save[IX(i, k)];
-        ws->SCAL[MPCB200_SC_GT] = g0save[5 * N];
-        rows_add_gradient(p, ws, cvec);
-        if (orc_kkt_solve(p, ws, delta) != 0) { status = MPCB200_STATUS_NUMERICAL_ERROR; break; }
-        const double tau = (1.0 - mu_t > ORC_TAU_MIN) ? 1.0 - mu_t : ORC_TAU_MIN;
-        double a_p, a_d;
-        rows_steps(p, ws, cvec, tau, &a_p, &a_d);
-        const double ddt = ws->SCAL[MPCB200_SC_DDT];
-        double alpha = a_p;
-        if (use_ls)
-        {
-            /* safeguard: l1 merit with barrier mu_t, memoryless rho */
-            double dJ = 0.0, dbar = 0.0;
-            /* objective directional derivative through the objective itself (finite difference free): use gradient g0 minus row terms is
-               messy; approximate by sampling: J(z + 1e-7 d) */
-            for (int k = 0; k < N; ++k) { for (int i = 0; i < 3; ++i) ws->XT[IX(i, k)] = ws->X[IX(i, k)] + 1e-7 * ws->STEP[IX(i, k)]; for (int i = 0; i < 2; ++i) ws->UT[IX(i, k)] = ws->U[IX(i, k)] + (k <= N - 2 ? 1e-7 * ws->STEP[IX(3 + i, k)] : 0.0); }
-            dJ = (orc_objective(p, ws, ws->XT, ws->UT, dt + 1e-7 * ddt) - info.obj) / 1e-7;
-            for (int k = 0; k < N; ++k) for (int sl = 0; sl < RS; ++sl) if (row_active(p, ws, k, sl)) dbar += -mu_t * ws->DS[IX(sl, k)] / ws->S[IX(sl, k)];
-            double rho = 1.0;
-            if (info.inf1 > 1e-14) { double rt = (dJ + dbar) / (0.9 * info.inf1); if (rho < rt) rho = rt + 1.0; }
-            const double phi0 = info.obj - mu_t * info.barrier_log + rho * info.inf1;
-            const double dphi = dJ + dbar - rho * info.inf1;
-            for (int bt = 0; bt < ORC_MAX_BACKTRACK; ++bt)
-            {
-                for (int k = 0; k < N; ++k) { for (int i = 0; i < 3; ++i) ws->XT[IX(i, k)] = ws->X[IX(i, k)] + alpha * ws->STEP[IX(i, k)]; for (int i = 0; i < 2; ++i) ws->UT[IX(i, k)] = ws->U[IX(i, k)] + (k <= N - 2 ? alpha * ws->STEP[IX(3 + i, k)] : 0.0); }
-                double obj, inft, blog;
-                trial_eval(p, ws, ws->XT, ws->UT, dt + alpha * ddt, alpha, &obj, &inft, &blog);
-                double phi = obj - mu_t * blog + rho * inft;
-                if (phi <= phi0 + ORC_ARMIJO * alpha * (dphi < 0 ? dphi : 0.0) + 1e-10 * fabs(phi0) ) break;
-                alpha *= 0.5; ++nbt;
-            }
-        }
-        double a_dual = a_d;
-        if (getenv("ORC_MSAME")) { if (a_dual > alpha) a_dual = alpha; }
-        for (int k = 0; k < N; ++k)
-        {
-            for (int i = 0; i < 3; ++i) ws->X[IX(i, k)] += alpha * ws->STEP[IX(i, k)];
-            if (k <= N - 2)
-            {
-                for (int i = 0; i < 2; ++i) ws->U[IX(i, k)] += alpha * ws->STEP[IX(3 + i, k)];
-                for (int i = 0; i < 3; ++i) ws->NU[IX(i, k)] += alpha * (ws->STEP[IX(5 + i, k)] - ws->NU[IX(i, k)]);
-            }
-            for (int sl = 0; sl < RS; ++sl)
-            {
-                if (!row_active(p, ws, k, sl)) continue;
-                ws->S[IX(sl, k)] += alpha * ws->DS[IX(sl, k)];
-                ws->LAM[IX(sl, k)] += a_dual * ws->DLAM[IX(sl, k)];
-            }
-        }
-        if (c->variable_dt) ws->SCAL[MPCB200_SC_DT] = dt + alpha * ddt;
-        if (getenv("ORC_DEBUG"))
-            fprintf(stderr, "it %3d mucur %.2e muaff %.2e sig %.2e E0 %.2e obj %.5f inf1 %.2e dinf %.2e delta %.1e aaff %.3f/%.3f a_p %.3f a_d %.3f alpha %.4f dt %.4f\n",
-                    iter, mu_cur, mu_aff, sig, e0, info.obj, info.inf1, info.dual_inf, delta, aap, aad, a_p, a_d, alpha, dt);
-        ++iter;
-    }
-    free(G1); free(cvec); free(g0save);
-    ws->SCAL[MPCB200_SC_STATUS] = (double)status;
-    if (res) { res->status = status; res->iters = iter; res->kkt_err = ws->SCAL[MPCB200_SC_ERR0]; res->objective = info.obj; res->dt = ws->SCAL[MPCB200_SC_DT]; res->n_regularised = nreg; res->n_backtracks = nbt; }
-    return status;
-}
-
 static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res, int iter0);
 int orc_solve(const orc_problem* p, orc_ws* ws, orc_result* res)
 {
-    if (getenv("ORC_MEHROTRA")) return orc_solve_mehrotra(p, ws, res);
     return orc_solve_monotone(p, ws, res, 0);
 }
 static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res, int iter0)
@@ -1578,6 +1387,13 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
         const double dt = ws->SCAL[MPCB200_SC_DT];
         /* ---- Newton step with inertia correction (Ipopt Algorithm IC) ---- */
         double delta = 0.0, dlast = ws->SCAL[MPCB200_SC_DELTA_LAST];
+        /* after a regularised iteration the first attempt is delta_last/3 (not 0): such instances need regularisation
+           again ~70% of the time and every failed attempt costs a full sweep; the value decays back to 0 */
+        if (dlast > 0.0)
+        {
+            delta = dlast / 3.0;
+            if (delta < ORC_DELTA_FLOOR) delta = 0.0;
+        }
         int ok = 0;
         for (int tries = 0; tries < ORC_MAX_INERTIA_TRIES; ++tries)
         {
@@ -1587,8 +1403,21 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
             else delta *= (dlast == 0.0 ? 100.0 : 8.0);
             if (delta > ORC_MAX_DELTA) break;
         }
+        if (!ok && delta <= ORC_MAX_DELTA)
+        {
+            /* deferred escalation: the factorisation budget of this iteration is spent (on the GPU every extra sweep of
+               one instance stalls the whole launch).  Null step; the next iteration resumes at this delta
+               (DELTA_LAST / 3 is its first attempt). */
+            ws->SCAL[MPCB200_SC_DELTA_LAST] = 3.0 * delta;
+            ws->SCAL[MPCB200_SC_DEFER] = 0.0; /* (the GPU path raises it in the KKT phase and clears it in the line-search phase) */
+            ws->SCAL[MPCB200_SC_ALPHA] = 0.0;
+            ++iter;
+            continue;
+        }
+        ws->SCAL[MPCB200_SC_DEFER] = 0.0;
         if (!ok) { status = MPCB200_STATUS_NUMERICAL_ERROR; break; }
         if (delta > 0.0) ws->SCAL[MPCB200_SC_DELTA_LAST] = delta;
+        else ws->SCAL[MPCB200_SC_DELTA_LAST] = 0.0;
         const double ddt = ws->SCAL[MPCB200_SC_DDT];
         /* ---- slack / multiplier steps and fraction to the boundary ---- */
         const double tau = (1.0 - mu > ORC_TAU_MIN) ? 1.0 - mu : ORC_TAU_MIN;
@@ -1739,9 +1568,10 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
             ws->SCAL[MPCB200_SC_TINY] = tiny;
             if (tiny >= (double)ORC_TINY_STEP_COUNT) { status = MPCB200_STATUS_NUMERICAL_ERROR; ++iter; break; }
         }
-        if (getenv("ORC_DEBUG"))
+#ifdef ORC_TRACE
             fprintf(stderr, "it %3d mu %.1e E0 %.2e Emu %.2e obj %.5f inf1 %.2e dinf %.2e delta %.1e a_p %.3f a_d %.3f alpha %.4f rho %.2e dphi %.2e acc %d dt %.4f\n",
                     iter, mu, ws->SCAL[MPCB200_SC_ERR0], ws->SCAL[MPCB200_SC_ERRMU], info.obj, inf1, info.dual_inf, delta, a_p, a_d, alpha, rho, dphi, accepted, dt);
+#endif
         ++iter;
     }
     ws->SCAL[MPCB200_SC_STATUS] = (double)status;

@@ -142,7 +142,7 @@ void emu_associate(const Cfg* cp, double* W, double uprev_dt, int first_outer)
     for (int k = 0; k < N; ++k) init_duals_stage(c, L, W, uprev_dt, k, mu);
     ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
     ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
-    ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0;
+    ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0; ASC(MPCB200_SC_DEFER) = 0.0;
     if (repair) ASC(MPCB200_SC_COLD) = 0.0;
 }
 
@@ -197,10 +197,17 @@ int emu_kkt(const Cfg* cp, double* W)
     if (ext) ok = riccati_solve_lane<true>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
     else ok = riccati_solve_lane<false>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
     ASC(MPCB200_SC_NREG) += (double)nreg;
+    if (!ok && delta <= MAX_DELTA)
+    {
+        ASC(MPCB200_SC_DELTA_LAST) = 3.0 * delta;
+        ASC(MPCB200_SC_DEFER) = 1.0;
+        return 0;
+    }
     if (!ok) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; return 1; }
+    ASC(MPCB200_SC_DEFER) = 0.0;
     ASC(MPCB200_SC_DDT) = ddt;
     ASC(MPCB200_SC_DELTA) = delta;
-    if (delta > 0.0) ASC(MPCB200_SC_DELTA_LAST) = delta;
+    ASC(MPCB200_SC_DELTA_LAST) = delta;
     return 0;
 }
 
@@ -211,6 +218,7 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
     make_layout(cp, MAX_OBST, MAX_VP, L);
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    if (ASC(MPCB200_SC_DEFER) != 0.0) { ASC(MPCB200_SC_DEFER) = 0.0; ASC(MPCB200_SC_ITER) += 1.0; ASC(MPCB200_SC_ALPHA) = 0.0; return; }
     LsAcc a;
     lsacc_init(a);
     for (int l = 0; l < 32; ++l)

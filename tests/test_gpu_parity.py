@@ -55,7 +55,9 @@ def test_phase_parity(cuda_lib, orc, cid, B):
         np.testing.assert_allclose(KKT[b], o.arr("KKT"), rtol=0, atol=1e-11 * scale)
         idx = [capi.SC_MU, capi.SC_HTT, capi.SC_GT, capi.SC_ERR0, capi.SC_ERRMU, capi.SC_OBJ, capi.SC_INF, capi.SC_BLOG]
         np.testing.assert_allclose(SC[b][idx], o.arr("SCAL")[idx], rtol=1e-10, atol=1e-12)
-        if SC2[b][capi.SC_DELTA] == 0.0:
+        if SC2[b][capi.SC_DEFER] != 0.0:
+            assert o.kkt_solve(0.0) == 1  # factorisation budget spent at this iterate: wrong inertia at delta = 0 for both
+        elif SC2[b][capi.SC_DELTA] == 0.0:
             assert o.kkt_solve(0.0) == 0
             sscale = np.abs(o.arr("STEP")).max()
             np.testing.assert_allclose(STEP[b], o.arr("STEP"), rtol=0, atol=1e-9 * sscale)
