@@ -24,6 +24,7 @@
 
 #define FULLMASK 0xffffffffu
 #define WARPS_PER_CTA 4
+#define MAX_GROUP_WARPS 4   // warps of the CTA that owns one instance in the eval / line-search kernels (lane per stage)
 
 // ---- warp reductions (fp64 via two 32-bit shuffles each) ------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)
@@ -252,31 +253,48 @@ __global__ void __launch_bounds__(1024) regroup_kernel(WsLayout L, const double*
 }
 
 // ---- kernel: PHASE_EVAL -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, const int* slot_of, int B, double uprev_dt, int* n_active)
+// ONE CTA PER INSTANCE, one lane per horizon stage: ceil(N/32) warps (at most MAX_GROUP_WARPS, then the stage loop
+// wraps).  Splitting an instance over several warps halves the dependent instruction stream each warp walks through --
+// at BASELINE batch sizes every kernel of the IPM iteration is latency- not throughput-bound.
+__device__ __forceinline__ void evalacc_warp_reduce(EvalAcc& a)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    double* W = ws + (int64_t)warp * L.stride;
-    const int N = L.N;
-    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;  // finished instance: exact no-op
-    const int slot = slot_of[warp];
-    double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
-    EvalAcc a;
-    evalacc_init(a);
-    for (int k = lane; k < N; k += 32) eval_stage(c, L, W, Kb, uprev_dt, k, a);
     a.dual_inf = warp_max(a.dual_inf); a.prim_inf = warp_max(a.prim_inf);
     a.sl_max = warp_max(a.sl_max); a.sl_min = warp_min(a.sl_min);
     a.sum_nu = warp_sum(a.sum_nu); a.sum_lam = warp_sum(a.sum_lam); a.inf1 = warp_sum(a.inf1); a.blog = warp_sum(a.blog);
     a.gt0 = warp_sum(a.gt0); a.gt1 = warp_sum(a.gt1); a.gldt = warp_sum(a.gldt); a.htt = warp_sum(a.htt);
     a.obj = warp_sum(a.obj); a.m_ineq = warp_sum(a.m_ineq); a.m_eq = warp_sum(a.m_eq);
-    double mu = 0.0;
-    int fin = 0;
-    if (lane == 0) mu = eval_finish(c, L, W, a, true, &fin);
-    mu = __shfl_sync(FULLMASK, mu, 0);
-    fin = __shfl_sync(FULLMASK, fin, 0);
-    if (fin) return;
-    if (lane == 0 && n_active) atomicAdd(n_active, 1);
-    for (int k = lane; k < N; k += 32) eval_finalize_stage(L, W, Kb, k, mu);
+}
+
+template <int G>
+__global__ void __maxnreg__(G <= 2 ? 144 : 168) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, const int* slot_of, int B, double uprev_dt, int* n_active)
+{
+    __shared__ EvalAcc s_acc[MAX_GROUP_WARPS];
+    __shared__ double s_mu;
+    __shared__ int s_fin;
+    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    double* W = ws + (int64_t)inst * L.stride;
+    const int N = L.N;
+    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;  // finished instance: exact no-op (uniform over the CTA)
+    const int slot = slot_of[inst];
+    double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
+    EvalAcc a;
+    evalacc_init(a);
+    for (int k = tid; k < N; k += blockDim.x) eval_stage(c, L, W, Kb, uprev_dt, k, a);
+    evalacc_warp_reduce(a);
+    if (lane == 0) s_acc[wid] = a;
+    __syncthreads();
+    if (tid == 0)
+    {
+        for (int w = 1; w < nw; ++w) evalacc_merge(a, s_acc[w]);
+        int fin = 0;
+        s_mu = eval_finish(c, L, W, a, true, &fin);
+        s_fin = fin;
+        if (!fin && n_active) atomicAdd(n_active, 1);
+    }
+    __syncthreads();
+    if (s_fin) return;
+    const double mu = s_mu;
+    for (int k = tid; k < N; k += blockDim.x) eval_finalize_stage(L, W, Kb, k, mu);
 }
 
 // ---- kernel: PHASE_KKT -- Riccati factorisation + solve, ONE LANE PER INSTANCE ------------------------------------
@@ -323,60 +341,93 @@ __global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double*
 }
 
 // ---- kernel: PHASE_LINESEARCH -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt)
+// one CTA per instance (lane per stage, see eval_kernel); thread 0 owns the scalar decisions of the line search.
+struct LsShared
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    double* W = ws + (int64_t)warp * L.stride;
+    LsAcc acc[MAX_GROUP_WARPS];
+    TrialAcc tr[MAX_GROUP_WARPS];
+    double alpha, a_dual;
+    int accept;
+};
+
+__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt)
+{
+    __shared__ LsShared sh;
+    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    double* W = ws + (int64_t)inst * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
     if (ASC(MPCB200_SC_DEFER) != 0.0)
     {
-        __syncwarp();
-        if (lane == 0) { ASC(MPCB200_SC_DEFER) = 0.0; ASC(MPCB200_SC_ITER) += 1.0; ASC(MPCB200_SC_ALPHA) = 0.0; }
+        // the KKT phase spent its factorisation budget: null step
+        __syncthreads();
+        if (tid == 0) { ASC(MPCB200_SC_DEFER) = 0.0; ASC(MPCB200_SC_ITER) += 1.0; ASC(MPCB200_SC_ALPHA) = 0.0; }
         return;
     }
-    const int slot = slot_of[warp];
+    const int slot = slot_of[inst];
     const double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
     LsAcc a;
     lsacc_init(a);
-    for (int k = lane; k < N; k += 32) ls_stage_steps(c, L, W, Kb, uprev_dt, k, a);
+    for (int k = tid; k < N; k += blockDim.x) ls_stage_steps(c, L, W, Kb, uprev_dt, k, a);
     a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
     a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
-    const double mu = ASC(MPCB200_SC_MU), inf1 = ASC(MPCB200_SC_INF), obj = ASC(MPCB200_SC_OBJ), blog = ASC(MPCB200_SC_BLOG);
-    const double ddt = ASC(MPCB200_SC_DDT), dt = ASC(MPCB200_SC_DT);
-    double rho = 1.0;
+    if (lane == 0) sh.acc[wid] = a;
+    __syncthreads();
+    // scalars of the merit function (thread 0 only)
+    double mu = 0.0, rho = 1.0, phi0 = 0.0, dphi = 0.0, a_d = 1.0;
+    if (tid == 0)
     {
+        for (int w = 1; w < nw; ++w)
+        {
+            const LsAcc& o = sh.acc[w];
+            a.a_p = fmin(a.a_p, o.a_p); a.a_d = fmin(a.a_d, o.a_d);
+            a.dphi_bar += o.dphi_bar; a.curv += o.curv; a.dJ += o.dJ;
+        }
+        mu = ASC(MPCB200_SC_MU);
+        const double inf1 = ASC(MPCB200_SC_INF), obj = ASC(MPCB200_SC_OBJ), blog = ASC(MPCB200_SC_BLOG);
         const double num = a.dJ + a.dphi_bar + 0.5 * (a.curv > 0 ? a.curv : 0.0);
         if (inf1 > 1e-14)
         {
             const double rho_trial = num / ((1.0 - 0.1) * inf1);
             if (rho < rho_trial) rho = rho_trial + 1.0;
         }
+        phi0 = obj - mu * blog + rho * inf1;
+        dphi = a.dJ + a.dphi_bar - rho * inf1;
+        a_d = a.a_d;
+        sh.alpha = a.a_p;
     }
-    const double phi0 = obj - mu * blog + rho * inf1;
-    const double dphi = a.dJ + a.dphi_bar - rho * inf1;
-    double alpha = a.a_p;
+    __syncthreads();
+    double alpha = sh.alpha;
     int nbt = 0;
-    __syncwarp();
     for (int bt = 0; bt < MAX_BACKTRACK; ++bt)
     {
         TrialAcc t;
         t.obj = t.inf1 = t.blog = 0.0;
-        for (int k = lane; k < N; k += 32) ls_stage_trial(c, L, W, uprev_dt, k, alpha, t);
+        for (int k = tid; k < N; k += blockDim.x) ls_stage_trial(c, L, W, uprev_dt, k, alpha, t);
         t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
-        const double phi = t.obj - mu * t.blog + rho * t.inf1;
-        if (phi <= phi0 + ARMIJO * alpha * dphi || (bt > 0 && fabs(phi - phi0) <= 1e-13 * (1.0 + fabs(phi0)))) break;
+        if (lane == 0) sh.tr[wid] = t;
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int w = 1; w < nw; ++w) { t.obj += sh.tr[w].obj; t.inf1 += sh.tr[w].inf1; t.blog += sh.tr[w].blog; }
+            const double phi = t.obj - mu * t.blog + rho * t.inf1;
+            sh.accept = (phi <= phi0 + ARMIJO * alpha * dphi || (bt > 0 && fabs(phi - phi0) <= 1e-13 * (1.0 + fabs(phi0)))) ? 1 : 0;
+        }
+        __syncthreads();
+        const int accept = sh.accept;
+        __syncthreads();  // sh.accept / sh.tr are rewritten by the next trial
+        if (accept) break;
         alpha *= 0.5;
         ++nbt;
     }
-    const double a_dual = a.a_d > alpha ? alpha : a.a_d;
-    __syncwarp();
-    for (int k = lane; k < N; k += 32) ls_stage_update(c, L, W, uprev_dt, k, alpha, a_dual);
-    __syncwarp();
-    if (lane == 0)
+    if (tid == 0) sh.a_dual = a_d > alpha ? alpha : a_d;
+    __syncthreads();
+    const double a_dual = sh.a_dual;
+    for (int k = tid; k < N; k += blockDim.x) ls_stage_update(c, L, W, uprev_dt, k, alpha, a_dual);
+    __syncthreads();
+    if (tid == 0)
     {
-        if (c.variable_dt) ASC(MPCB200_SC_DT) = dt + alpha * ddt;
+        if (c.variable_dt) ASC(MPCB200_SC_DT) = ASC(MPCB200_SC_DT) + alpha * ASC(MPCB200_SC_DDT);
         ASC(MPCB200_SC_ALPHA) = alpha;
         ASC(MPCB200_SC_RHO) = rho;
         ASC(MPCB200_SC_ITER) += 1.0;
@@ -627,12 +678,22 @@ static void ev_collect(mpcb200_handle* h)
 static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int first_outer, bool timed)
 {
     const int grid4 = grid_for(B, WARPS_PER_CTA);
+    const int gw = (h->cfg.n + 31) / 32;
+    const int group_threads = 32 * (gw < MAX_GROUP_WARPS ? gw : MAX_GROUP_WARPS);
     if (timed && ev_begin(h, phase)) return set_err(h, MPCB200_E_CUDA, "cudaEventCreate failed");
     switch (phase)
     {
         case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold); break;
         case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer); break;
-        case MPCB200_PHASE_EVAL: eval_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
+        case MPCB200_PHASE_EVAL:
+            switch (group_threads >> 5)
+            {
+                case 1: eval_kernel<1><<<B, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
+                case 2: eval_kernel<2><<<B, 64, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
+                case 3: eval_kernel<3><<<B, 96, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
+                default: eval_kernel<4><<<B, 128, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
+            }
+            break;
         case MPCB200_PHASE_KKT:
         {
             const bool ext = h->cfg.variable_dt || h->cfg.xf_fixed[0] || h->cfg.xf_fixed[1] || h->cfg.xf_fixed[2];
@@ -641,7 +702,7 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
             else kkt_lane_kernel<false><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
             break;
         }
-        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt); break;
+        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<B, group_threads, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt); break;
         default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
     }
     if (timed) ev_end(h);

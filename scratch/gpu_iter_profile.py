@@ -14,9 +14,9 @@ for it in range(100):
     st=s.stats(); sc=s.ws_read(capi.F_SCAL)
     act=prev[:,capi.SC_STATUS]<0
     dn=(sc[:,capi.SC_NREG]-prev[:,capi.SC_NREG])[act]; db=(sc[:,capi.SC_NBT]-prev[:,capi.SC_NBT])[act]
-    rows.append((it,int(act.sum()),st['ms'][2]*1e3,st['ms'][3]*1e3,st['ms'][4]*1e3, dn.max() if act.any() else 0, dn.mean() if act.any() else 0, db.max() if act.any() else 0))
+    rows.append((it,int(act.sum()),st['ms'][2]*1e3,st['ms'][3]*1e3,st['ms'][4]*1e3, dn.max() if act.any() else 0, dn.mean() if act.any() else 0, db.max() if act.any() else 0, db.mean() if act.any() else 0, (db>=1).mean() if act.any() else 0))
     prev=sc
     if not (sc[:,capi.SC_STATUS]<0).any(): break
-print("it active eval_us kkt_us ls_us max_extra_sweeps mean_extra max_bt")
-for r in rows[::3]: print("%3d %4d %6.1f %6.1f %6.1f %d %.3f %d"%r)
+print("it active eval_us kkt_us ls_us max_extra_sweeps mean_extra max_bt mean_bt frac_bt")
+for r in rows[::3]: print("%3d %4d %6.1f %6.1f %6.1f %d %.3f %d %.3f %.3f"%r)
 print("totals ms: eval %.2f kkt %.2f ls %.2f"%(sum(r[2] for r in rows)/1e3,sum(r[3] for r in rows)/1e3,sum(r[4] for r in rows)/1e3))
