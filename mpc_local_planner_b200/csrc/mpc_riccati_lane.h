@@ -75,40 +75,21 @@ HD inline void riccati_terminal(const Cfg& c, const Rec& rec, int N, double delt
     }
 }
 
-// one backward stage; returns 0 if M_vv is not positive definite.  Writes the gains of stage k.
-// load the 42-word record of stage k into registers (one coalesced 256-byte access per word across the warp)
-template <class Rec>
-HD inline void riccati_load(const Rec& rec, int k, double* r)
+// Record views: r(f) = word f of the stage record of this lane's instance.  PlainFeed reads the interleaved tile in
+// global memory directly (host emulator); the CUDA kernel reads the copy a bulk-async (TMA) transfer staged in shared memory.
+struct StridedView
 {
-#pragma unroll
-    for (int f = 0; f < MPCB200_KKT_WORDS; ++f) r[f] = rec(k, f);
-}
+    const double* p;  // word 0 of this lane's record, words TILE apart
+    HD double operator()(int f) const { return p[(size_t)f * TILE]; }
+};
 
-template <bool EXT, class Ric>
-HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta, int dt_free, RicState<EXT>& s)
+// one backward stage; returns 0 if M_vv is not positive definite.  Writes the gains of stage k.
+// Structure exploited: A = I + a e_theta', the p (= previous control) rows of M_yv are diag(C), M_pp = 0.
+template <bool EXT, class RV, class Ric>
+HD inline int riccati_stage(const RV& r, const Ric& ric, int k, double delta, int dt_free, RicState<EXT>& s)
 {
     constexpr int NC = RicState<EXT>::NC;
-    // ---- stage record (already in registers) ----
-    double H[5][5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = i; j < 5; ++j)
-        {
-            const double v = r[MPCB200_K_H + hidx(i, j)] + (i == j ? delta : 0.0);
-            H[i][j] = v; H[j][i] = v;
-        }
-    double g[5], a[3], Bm[3][2], e[3], Cc[2], hb[5], dv[3];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) { g[i] = r[MPCB200_K_G + i]; hb[i] = (EXT && dt_free) ? r[MPCB200_K_HB + i] : 0.0; }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-    {
-        a[i] = r[MPCB200_K_A + i]; e[i] = r[MPCB200_K_E + i];
-        dv[i] = (EXT && dt_free) ? r[MPCB200_K_D + i] : 0.0;
-        Bm[i][0] = r[MPCB200_K_B + 2 * i]; Bm[i][1] = r[MPCB200_K_B + 2 * i + 1];
-    }
-    Cc[0] = r[MPCB200_K_C]; Cc[1] = r[MPCB200_K_C + 1];
+    const bool dtf = EXT && dt_free;
     // ---- gains needed later: rows x of P_{k+1} and PI_{k+1} (for nu+) ----
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -118,6 +99,15 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc) ric(k, 15 + i * NC + cc) = s.PI[i][cc];
     }
+    double a[3], Bm[3][2], e[3], dv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        a[i] = r(MPCB200_K_A + i); e[i] = r(MPCB200_K_E + i);
+        dv[i] = dtf ? r(MPCB200_K_D + i) : 0.0;
+        Bm[i][0] = r(MPCB200_K_B + 2 * i); Bm[i][1] = r(MPCB200_K_B + 2 * i + 1);
+    }
+    const double Cc0 = r(MPCB200_K_C), Cc1 = r(MPCB200_K_C + 1);
     // ---- T1 = P Bbar (5x2), PA = Pxx a (3), W = P chat + PI (5 x NC) ----
     double T1[5][2], PA[3], Wm[5][NC];
 #pragma unroll
@@ -128,7 +118,7 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
         Wm[i][0] = s.P[i][0] * e[0] + s.P[i][1] * e[1] + s.P[i][2] * e[2] + s.PI[i][0];
         if (EXT)
         {
-            Wm[i][EXT ? 1 : 0] = s.P[i][0] * dv[0] + s.P[i][1] * dv[1] + s.P[i][2] * dv[2] + s.PI[i][EXT ? 1 : 0];
+            Wm[i][EXT ? 1 : 0] = dtf ? s.P[i][0] * dv[0] + s.P[i][1] * dv[1] + s.P[i][2] * dv[2] + s.PI[i][EXT ? 1 : 0] : s.PI[i][EXT ? 1 : 0];
 #pragma unroll
             for (int cc = 2; cc < NC; ++cc) Wm[i][cc] = s.PI[i][cc];
         }
@@ -136,27 +126,31 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
 #pragma unroll
     for (int i = 0; i < 3; ++i) PA[i] = s.P[i][0] * a[0] + s.P[i][1] * a[1] + s.P[i][2] * a[2];
     // ---- MM = M + F'PF ----
-    double Mvv[2][2], Mxv[3][2], Mxx[3][3];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-            Mvv[i][j] = H[3 + i][3 + j] + Bm[0][i] * T1[0][j] + Bm[1][i] * T1[1][j] + Bm[2][i] * T1[2][j] + T1[3 + i][j];
+    double Mvv[3], Mxv[3][2], Mxx[3][3];  // Mvv packed (00, 01, 11)
+    {
+        const double h33 = r(MPCB200_K_H + hidx(3, 3)) + delta, h34 = r(MPCB200_K_H + hidx(3, 4)), h44 = r(MPCB200_K_H + hidx(4, 4)) + delta;
+        Mvv[0] = h33 + Bm[0][0] * T1[0][0] + Bm[1][0] * T1[1][0] + Bm[2][0] * T1[2][0] + T1[3][0];
+        Mvv[2] = h44 + Bm[0][1] * T1[0][1] + Bm[1][1] * T1[1][1] + Bm[2][1] * T1[2][1] + T1[4][1];
+        const double m01 = h34 + Bm[0][0] * T1[0][1] + Bm[1][0] * T1[1][1] + Bm[2][0] * T1[2][1] + T1[3][1];
+        const double m10 = h34 + Bm[0][1] * T1[0][0] + Bm[1][1] * T1[1][0] + Bm[2][1] * T1[2][0] + T1[4][0];
+        Mvv[1] = 0.5 * (m01 + m10);
+    }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
     {
         const double at = a[0] * T1[0][j] + a[1] * T1[1][j] + a[2] * T1[2][j];
-        Mxv[0][j] = H[0][3 + j] + T1[0][j];
-        Mxv[1][j] = H[1][3 + j] + T1[1][j];
-        Mxv[2][j] = H[2][3 + j] + T1[2][j] + at;
+        Mxv[0][j] = r(MPCB200_K_H + hidx(0, 3 + j)) + T1[0][j];
+        Mxv[1][j] = r(MPCB200_K_H + hidx(1, 3 + j)) + T1[1][j];
+        Mxv[2][j] = r(MPCB200_K_H + hidx(2, 3 + j)) + T1[2][j] + at;
     }
     {
         const double apa = a[0] * PA[0] + a[1] * PA[1] + a[2] * PA[2];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                Mxx[i][j] = H[i][j] + s.P[i][j] + (i == 2 ? PA[j] : 0.0) + (j == 2 ? PA[i] : 0.0) + ((i == 2 && j == 2) ? apa : 0.0);
+        Mxx[0][0] = r(MPCB200_K_H + hidx(0, 0)) + delta + s.P[0][0];
+        Mxx[0][1] = r(MPCB200_K_H + hidx(0, 1)) + s.P[0][1];
+        Mxx[1][1] = r(MPCB200_K_H + hidx(1, 1)) + delta + s.P[1][1];
+        Mxx[0][2] = r(MPCB200_K_H + hidx(0, 2)) + s.P[0][2] + PA[0];
+        Mxx[1][2] = r(MPCB200_K_H + hidx(1, 2)) + s.P[1][2] + PA[1];
+        Mxx[2][2] = r(MPCB200_K_H + hidx(2, 2)) + delta + s.P[2][2] + (PA[2] + PA[2]) + apa;
     }
     // ---- NN = Mhat + F'W ----
     double Nx[3][NC], Nv[2][NC];
@@ -164,14 +158,23 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
     for (int cc = 0; cc < NC; ++cc)
     {
         const double aw = a[0] * Wm[0][cc] + a[1] * Wm[1][cc] + a[2] * Wm[2][cc];
-        const double mx0 = cc == 0 ? g[0] : (cc == 1 ? hb[0] : 0.0), mx1 = cc == 0 ? g[1] : (cc == 1 ? hb[1] : 0.0);
-        const double mx2 = cc == 0 ? g[2] : (cc == 1 ? hb[2] : 0.0);
-        const double mv0 = cc == 0 ? g[3] : (cc == 1 ? hb[3] : 0.0), mv1 = cc == 0 ? g[4] : (cc == 1 ? hb[4] : 0.0);
-        Nx[0][cc] = mx0 + Wm[0][cc];
-        Nx[1][cc] = mx1 + Wm[1][cc];
-        Nx[2][cc] = mx2 + Wm[2][cc] + aw;
-        Nv[0][cc] = mv0 + Bm[0][0] * Wm[0][cc] + Bm[1][0] * Wm[1][cc] + Bm[2][0] * Wm[2][cc] + Wm[3][cc];
-        Nv[1][cc] = mv1 + Bm[0][1] * Wm[0][cc] + Bm[1][1] * Wm[1][cc] + Bm[2][1] * Wm[2][cc] + Wm[4][cc];
+        const double bw0 = Bm[0][0] * Wm[0][cc] + Bm[1][0] * Wm[1][cc] + Bm[2][0] * Wm[2][cc] + Wm[3][cc];
+        const double bw1 = Bm[0][1] * Wm[0][cc] + Bm[1][1] * Wm[1][cc] + Bm[2][1] * Wm[2][cc] + Wm[4][cc];
+        if (cc == 0)
+        {
+            Nx[0][cc] = r(MPCB200_K_G + 0) + Wm[0][cc]; Nx[1][cc] = r(MPCB200_K_G + 1) + Wm[1][cc]; Nx[2][cc] = r(MPCB200_K_G + 2) + Wm[2][cc] + aw;
+            Nv[0][cc] = r(MPCB200_K_G + 3) + bw0; Nv[1][cc] = r(MPCB200_K_G + 4) + bw1;
+        }
+        else if (cc == 1 && dtf)
+        {
+            Nx[0][cc] = r(MPCB200_K_HB + 0) + Wm[0][cc]; Nx[1][cc] = r(MPCB200_K_HB + 1) + Wm[1][cc]; Nx[2][cc] = r(MPCB200_K_HB + 2) + Wm[2][cc] + aw;
+            Nv[0][cc] = r(MPCB200_K_HB + 3) + bw0; Nv[1][cc] = r(MPCB200_K_HB + 4) + bw1;
+        }
+        else
+        {
+            Nx[0][cc] = Wm[0][cc]; Nx[1][cc] = Wm[1][cc]; Nx[2][cc] = Wm[2][cc] + aw;
+            Nv[0][cc] = bw0; Nv[1][cc] = bw1;
+        }
     }
     // ---- TT = TH + Chat'W + PI'Chat (rows/cols 0,1 only carry chat) ----
     double TT[NC][NC];
@@ -183,21 +186,15 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
             for (int j = 0; j < NC; ++j)
             {
                 double v = s.TH[i][j];
-                if (i < 2)
-                {
-                    const double c0 = i == 0 ? e[0] : dv[0], c1 = i == 0 ? e[1] : dv[1], c2 = i == 0 ? e[2] : dv[2];
-                    v += c0 * Wm[0][j] + c1 * Wm[1][j] + c2 * Wm[2][j];
-                }
-                if (j < 2)
-                {
-                    const double c0 = j == 0 ? e[0] : dv[0], c1 = j == 0 ? e[1] : dv[1], c2 = j == 0 ? e[2] : dv[2];
-                    v += s.PI[0][i] * c0 + s.PI[1][i] * c1 + s.PI[2][i] * c2;
-                }
+                if (i == 0) v += e[0] * Wm[0][j] + e[1] * Wm[1][j] + e[2] * Wm[2][j];
+                if (i == 1) v += dv[0] * Wm[0][j] + dv[1] * Wm[1][j] + dv[2] * Wm[2][j];
+                if (j == 0) v += s.PI[0][i] * e[0] + s.PI[1][i] * e[1] + s.PI[2][i] * e[2];
+                if (j == 1) v += s.PI[0][i] * dv[0] + s.PI[1][i] * dv[1] + s.PI[2][i] * dv[2];
                 TT[i][j] = v;
             }
     }
     // ---- Lambda = Mvv^-1 with the inertia test ----
-    const double la = Mvv[0][0], lb = 0.5 * (Mvv[0][1] + Mvv[1][0]), ld = Mvv[1][1];
+    const double la = Mvv[0], lb = Mvv[1], ld = Mvv[2];
     const double det = la * ld - lb * lb;
     if (!(la > 0.0) || !(ld > 0.0) || !(det > 1e-14 * la * ld)) return 0;
     const double idet = 1.0 / det;
@@ -210,8 +207,8 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
         KG[0][j] = L00 * Mxv[j][0] + L01 * Mxv[j][1];
         KG[1][j] = L01 * Mxv[j][0] + L11 * Mxv[j][1];
     }
-    KG[0][3] = L00 * Cc[0]; KG[1][3] = L01 * Cc[0];
-    KG[0][4] = L01 * Cc[1]; KG[1][4] = L11 * Cc[1];
+    KG[0][3] = L00 * Cc0; KG[1][3] = L01 * Cc0;
+    KG[0][4] = L01 * Cc1; KG[1][4] = L11 * Cc1;
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
     {
@@ -222,44 +219,26 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
     for (int j = 0; j < 5; ++j) { ric(k, 15 + 3 * NC + j) = KG[0][j]; ric(k, 15 + 3 * NC + 5 + j) = KG[1][j]; }
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc) { ric(k, 25 + 3 * NC + cc) = KT[0][cc]; ric(k, 25 + 4 * NC + cc) = KT[1][cc]; }
-    // ---- Schur complements: P, PI, TH of stage k ----
-    // Myv rows: x rows = Mxv, p rows = diag(C)
-    double Pn[5][5];
+    // ---- Schur complements (upper triangle, mirrored): P = Myy - Myv KG, PI = Ny - Myv KT, TH = TT - Nv' KT ----
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 3; ++i)
+    {
 #pragma unroll
-        for (int j = i; j < 5; ++j)
+        for (int j = i; j < 3; ++j)
         {
-            const double m0 = i < 3 ? Mxv[i < 3 ? i : 0][0] : (i == 3 ? Cc[0] : 0.0);
-            const double m1 = i < 3 ? Mxv[i < 3 ? i : 0][1] : (i == 4 ? Cc[1] : 0.0);
-            const double z = (i < 3 && j < 3) ? Mxx[i < 3 ? i : 0][j < 3 ? j : 0] : 0.0;
-            const double v = z - (m0 * KG[0][j] + m1 * KG[1][j]);
-            Pn[i][j] = v; Pn[j][i] = v;
+            const double v = Mxx[i][j] - (Mxv[i][0] * KG[0][j] + Mxv[i][1] * KG[1][j]);
+            s.P[i][j] = v; s.P[j][i] = v;
         }
-    // symmetrise like the oracle: P_ij <- (P_ij + P_ji)/2 with P_ji computed from the transposed formula
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = i + 1; j < 5; ++j)
+        for (int j = 3; j < 5; ++j)
         {
-            const double m0 = j < 3 ? Mxv[j < 3 ? j : 0][0] : (j == 3 ? Cc[0] : 0.0);
-            const double m1 = j < 3 ? Mxv[j < 3 ? j : 0][1] : (j == 4 ? Cc[1] : 0.0);
-            const double z = (i < 3 && j < 3) ? Mxx[j < 3 ? j : 0][i < 3 ? i : 0] : 0.0;
-            const double vt = z - (m0 * KG[0][i] + m1 * KG[1][i]);
-            const double v = 0.5 * (Pn[i][j] + vt);
-            Pn[i][j] = v; Pn[j][i] = v;
+            const double v = -(Mxv[i][0] * KG[0][j] + Mxv[i][1] * KG[1][j]);
+            s.P[i][j] = v; s.P[j][i] = v;
         }
-    double PIn[5][NC];
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc)
-        {
-            const double m0 = i < 3 ? Mxv[i < 3 ? i : 0][0] : (i == 3 ? Cc[0] : 0.0);
-            const double m1 = i < 3 ? Mxv[i < 3 ? i : 0][1] : (i == 4 ? Cc[1] : 0.0);
-            const double z = i < 3 ? Nx[i < 3 ? i : 0][cc] : 0.0;
-            PIn[i][cc] = z - (m0 * KT[0][cc] + m1 * KT[1][cc]);
-        }
+    }
+    s.P[3][3] = -(Cc0 * KG[0][3]);
+    s.P[3][4] = -(Cc0 * KG[0][4]); s.P[4][3] = s.P[3][4];
+    s.P[4][4] = -(Cc1 * KG[1][4]);
     if (EXT)
     {
 #pragma unroll
@@ -268,12 +247,12 @@ HD inline int riccati_stage(const double* r, const Ric& ric, int k, double delta
             for (int j = 0; j < NC; ++j) s.TH[i][j] = TT[i][j] - (Nv[0][i] * KT[0][j] + Nv[1][i] * KT[1][j]);
     }
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
+    for (int cc = 0; cc < NC; ++cc)
     {
 #pragma unroll
-        for (int j = 0; j < 5; ++j) s.P[i][j] = Pn[i][j];
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc) s.PI[i][cc] = PIn[i][cc];
+        for (int i = 0; i < 3; ++i) s.PI[i][cc] = Nx[i][cc] - (Mxv[i][0] * KT[0][cc] + Mxv[i][1] * KT[1][cc]);
+        s.PI[3][cc] = -(Cc0 * KT[0][cc]);
+        s.PI[4][cc] = -(Cc1 * KT[1][cc]);
     }
     return 1;
 }
@@ -326,11 +305,39 @@ HD inline int riccati_root(const Cfg& c, const double TH[5][5], double* th)
     return 1;
 }
 
-// Full factorisation + solve of one instance with inertia-correcting regularisation (Ipopt's algorithm IC).
-// Step: callable step(k, c, value) receiving dw (c = 0..4) and nu+ (c = 5..7) of stage k.
-template <bool EXT, class Rec, class Ric, class Step>
-HD inline int riccati_solve_lane(const Cfg& c, int N, const Rec& rec, const Ric& ric, const Step& step, double htt, double gt,
-                                 double dlast, double* ddt_out, double* delta_out, int* nreg_out)
+// ---- feeds: how the stage records / gains reach the lane ---------------------------------------------------------
+// A feed hands out the record of backward stage k (all 42 words) and the data of forward stage k (the NG gain words the
+// backward sweep wrote + record words A,B,E (20..31) and D (39..41)).  PlainFeed indexes the tiles in place (host
+// emulator, tests).  The CUDA kernel's TmaFeed (mpcb200.cu) streams them through a shared-memory ring with bulk-async
+// copies so that no lane ever waits on a global load.  All feed calls are warp-uniform.
+struct FwdViewPlain
+{
+    const double* g;  // gains of stage k (word 0, this lane)
+    const double* r;  // record of stage k (word 0, this lane)
+    HD double gain(int w) const { return g[(size_t)w * TILE]; }
+    HD double rec(int f) const { return r[(size_t)f * TILE]; }
+};
+struct PlainFeed
+{
+    TileRec rec;
+    TileRic ric;
+    HD bool any(bool p) const { return p; }
+    HD void bwd_start(int) {}
+    HD StridedView bwd_acquire(int k) const { return StridedView{rec.base + (size_t)k * MPCB200_KKT_WORDS * TILE}; }
+    HD void bwd_release(int) {}
+    HD void bwd_abort() {}
+    HD void fwd_start(int) {}
+    HD FwdViewPlain fwd_acquire(int k) const { return FwdViewPlain{ric.base + (size_t)k * RICW_MAX * TILE, rec.base + (size_t)k * MPCB200_KKT_WORDS * TILE}; }
+    HD void fwd_release(int) {}
+};
+
+// Full factorisation + solve of the instances of one tile, one lane each, with inertia-correcting regularisation
+// (Ipopt's algorithm IC) limited to MAX_INERTIA_TRIES sweeps.  Control flow is warp-uniform: a lane that does not
+// need (another) sweep idles through it.  Step: callable step(k, c, value) receiving dw (c = 0..4) and nu+ (c = 5..7).
+// Returns 1 if this lane's system was solved; *delta_out is the last regularisation tried.
+template <bool EXT, class Feed, class Step>
+HD inline int riccati_solve_lane(const Cfg& c, int N, Feed& feed, const Step& step, bool active, double htt, double gt, double dlast,
+                                 double* ddt_out, double* delta_out, int* nreg_out)
 {
     constexpr int NC = RicState<EXT>::NC;
     const int dt_free = c.variable_dt;
@@ -339,91 +346,93 @@ HD inline int riccati_solve_lane(const Cfg& c, int N, const Rec& rec, const Ric&
     // after a regularised iteration the first attempt is delta_last/3 (decays back to 0): a failed attempt costs a full sweep
     double delta = (dlast > 0.0 && dlast / 3.0 >= DELTA_FLOOR) ? dlast / 3.0 : 0.0;
     int ok = 0, nreg = 0;
+    bool need = active;
     for (int tries = 0; tries < MAX_INERTIA_TRIES; ++tries)
     {
-        riccati_terminal<EXT>(c, rec, N, delta, htt, gt, s);
-        int good = 1;
-        double cur[MPCB200_KKT_WORDS], nxt[MPCB200_KKT_WORDS];
-        riccati_load(rec, N - 2, nxt);
+        if (!feed.any(need)) break;
+        bool alive = need;
+        if (alive) riccati_terminal<EXT>(c, feed.rec, N, delta, htt, gt, s);
+        feed.bwd_start(N - 2);
         for (int k = N - 2; k >= 0; --k)
         {
-#pragma unroll
-            for (int f = 0; f < MPCB200_KKT_WORDS; ++f) cur[f] = nxt[f];
-            if (k > 0) riccati_load(rec, k - 1, nxt);  // prefetch the next record while this stage is processed
-            if (!riccati_stage<EXT>(cur, ric, k, delta, dt_free, s)) { good = 0; break; }
+            const auto r = feed.bwd_acquire(k);
+            if (alive) alive = riccati_stage<EXT>(r, feed.ric, k, delta, dt_free, s) != 0;
+            feed.bwd_release(k);
+            if (!feed.any(alive)) { feed.bwd_abort(); break; }
         }
-        if (good && EXT)
+        if (alive && EXT)
         {
             double THf[5][5];
             for (int i = 0; i < 5; ++i)
                 for (int j = 0; j < 5; ++j) THf[i][j] = s.TH[i < NC ? i : 0][j < NC ? j : 0];
-            good = riccati_root(c, THf, th);
+            alive = riccati_root(c, THf, th) != 0;
         }
-        if (good) { ok = 1; break; }
-        ++nreg;
-        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
-        else delta *= (dlast == 0.0 ? 100.0 : 8.0);
-        if (delta > MAX_DELTA) break;
+        if (need)
+        {
+            if (alive) { ok = 1; need = false; }
+            else
+            {
+                ++nreg;
+                if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
+                else delta *= (dlast == 0.0 ? 100.0 : 8.0);
+                if (delta > MAX_DELTA) need = false;
+            }
+        }
     }
     *nreg_out = nreg;
     *delta_out = delta;
-    if (!ok) return 0;
-    // ---- forward substitution (gains + dynamics of stage k+1 are prefetched while stage k is processed) ----
-    constexpr int NG = 25 + 5 * NC;  // Px rows 15, PIx rows 3*NC, KG 10, KT 2*NC
+    *ddt_out = th[1];
+    // ---- forward substitution ----
+    if (!feed.any(ok != 0)) return 0;
     double y[5] = {0, 0, 0, 0, 0};
-    double gc[NG], gn[NG], dc[15], dn[15];
-    auto load_fwd = [&](int k, double* gg, double* dd) {
-#pragma unroll
-        for (int w = 0; w < NG; ++w) gg[w] = ric(k, w);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-        {
-            dd[i] = rec(k, MPCB200_K_A + i); dd[3 + 2 * i] = rec(k, MPCB200_K_B + 2 * i); dd[4 + 2 * i] = rec(k, MPCB200_K_B + 2 * i + 1);
-            dd[9 + i] = rec(k, MPCB200_K_E + i); dd[12 + i] = (EXT && dt_free) ? rec(k, MPCB200_K_D + i) : 0.0;
-        }
-    };
-    load_fwd(0, gn, dn);
+    feed.fwd_start(N);
     for (int k = 0; k <= N - 2; ++k)
     {
-#pragma unroll
-        for (int w = 0; w < NG; ++w) gc[w] = gn[w];
-#pragma unroll
-        for (int w = 0; w < 15; ++w) dc[w] = dn[w];
-        if (k < N - 2) load_fwd(k + 1, gn, dn);
-        double v0 = 0.0, v1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 5; ++j)
+        const auto f = feed.fwd_acquire(k);
+        if (ok)
         {
-            v0 -= gc[15 + 3 * NC + j] * y[j];
-            v1 -= gc[15 + 3 * NC + 5 + j] * y[j];
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+            {
+                v0 -= f.gain(15 + 3 * NC + j) * y[j];
+                v1 -= f.gain(15 + 3 * NC + 5 + j) * y[j];
+            }
+#pragma unroll
+            for (int cc = 0; cc < NC; ++cc)
+            {
+                v0 -= f.gain(25 + 3 * NC + cc) * th[cc];
+                v1 -= f.gain(25 + 4 * NC + cc) * th[cc];
+            }
+            step(k, 0, y[0]); step(k, 1, y[1]); step(k, 2, y[2]); step(k, 3, v0); step(k, 4, v1);
+            double yn[5];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+                double t = y[i] + f.rec(MPCB200_K_A + i) * y[2] + f.rec(MPCB200_K_B + 2 * i) * v0 + f.rec(MPCB200_K_B + 2 * i + 1) * v1 + f.rec(MPCB200_K_E + i);
+                if (EXT && dt_free) t += f.rec(MPCB200_K_D + i) * th[1];
+                yn[i] = t;
+            }
+            yn[3] = v0; yn[4] = v1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+                double sacc = 0.0;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) sacc += f.gain(i * 5 + j) * yn[j];
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) sacc += f.gain(15 + i * NC + cc) * th[cc];
+                step(k, 5 + i, sacc);
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) y[i] = yn[i];
         }
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc)
-        {
-            v0 -= gc[25 + 3 * NC + cc] * th[cc];
-            v1 -= gc[25 + 4 * NC + cc] * th[cc];
-        }
-        step(k, 0, y[0]); step(k, 1, y[1]); step(k, 2, y[2]); step(k, 3, v0); step(k, 4, v1);
-        double yn[5];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-            yn[i] = y[i] + dc[i] * y[2] + dc[3 + 2 * i] * v0 + dc[4 + 2 * i] * v1 + dc[9 + i] + ((EXT && dt_free) ? dc[12 + i] * th[1] : 0.0);
-        yn[3] = v0; yn[4] = v1;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-        {
-            double sacc = 0.0;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) sacc += gc[i * 5 + j] * yn[j];
-#pragma unroll
-            for (int cc = 0; cc < NC; ++cc) sacc += gc[15 + i * NC + cc] * th[cc];
-            step(k, 5 + i, sacc);
-        }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) y[i] = yn[i];
+        feed.fwd_release(k);
     }
-    step(N - 1, 0, y[0]); step(N - 1, 1, y[1]); step(N - 1, 2, y[2]);
-    for (int cc = 3; cc < 8; ++cc) step(N - 1, cc, 0.0);
-    *ddt_out = th[1];
-    return 1;
+    if (ok)
+    {
+        step(N - 1, 0, y[0]); step(N - 1, 1, y[1]); step(N - 1, 2, y[2]);
+        for (int cc = 3; cc < 8; ++cc) step(N - 1, cc, 0.0);
+    }
+    return ok;
 }

@@ -298,33 +298,171 @@ __global__ void __maxnreg__(G <= 2 ? 144 : 168) eval_kernel(Cfg c, WsLayout L, d
 }
 
 // ---- kernel: PHASE_KKT -- Riccati factorisation + solve, ONE LANE PER INSTANCE ------------------------------------
-// warp w handles the instances of tile w (32 consecutive instances); every record / gain access is one coalesced
-// 256-byte transaction across the warp.  Lanes whose instance is finished (or beyond B) idle.
+// One warp per 32-instance tile.  The stage records (backward sweep) and the gains + dynamics (forward sweep) of a tile
+// are contiguous 10.5 KB / 10.5-16 KB blocks, so they are streamed through a KKT_RING-deep shared-memory ring with
+// 1-D bulk-async copies (cp.async.bulk, the TMA engine) completing on mbarriers: the lanes read their words from
+// shared memory (conflict-free, 8 B per lane) and never stall on a global load.  Lanes whose instance is finished (or
+// beyond B) idle through the sweeps.
+#define KKT_RING 4
 struct StepOut
 {
     double* W; int oSTEP; int N;
     __device__ void operator()(int k, int c, double v) const { W[oSTEP + c * N + k] = v; }
 };
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct SmemView
+{
+    const double* p;  // word 0 of this lane in the staged block, words TILE apart
+    __device__ double operator()(int f) const { return p[f * TILE]; }
+};
+template <int NG>
+struct FwdViewSmem
+{
+    const double* p;  // staged block: NG gain words, then record words 20..31, then 39..41
+    __device__ double gain(int w) const { return p[w * TILE]; }
+    __device__ double rec(int f) const { return p[(f < MPCB200_K_D ? NG + (f - MPCB200_K_A) : NG + 12 + (f - MPCB200_K_D)) * TILE]; }
+};
+
+template <bool EXT>
+struct TmaFeed
+{
+    static constexpr int NC = EXT ? 5 : 1;
+    static constexpr int NG = 25 + 5 * NC;                                             // gain words read by the forward sweep
+    static constexpr int FWD_WORDS = NG + 12 + (EXT ? 3 : 0);
+    static constexpr int BUF_WORDS = FWD_WORDS > MPCB200_KKT_WORDS ? FWD_WORDS : MPCB200_KKT_WORDS;  // per ring slot, x TILE doubles
+    TileRec rec;              // this lane's words in the tile (direct global access: terminal record)
+    TileRic ric;              // this lane's gain words (written by the backward sweep)
+    const double* rec_tile;   // tile bases for the bulk copies
+    const double* ric_tile;
+    double* ring;             // shared-memory ring (generic address)
+    uint32_t ring_s, bar_s;   // ... and its shared-space address, the mbarriers
+    int lane, dt_free;
+    uint32_t issued, consumed;
+
+    __device__ bool any(bool p) const { return __any_sync(FULLMASK, p) != 0; }
+    __device__ void issue_bwd(int k)
+    {
+        if (lane == 0)
+        {
+            const uint32_t slot = issued % KKT_RING, bar = bar_s + 8 * slot;
+            mbar_expect_tx(bar, MPCB200_KKT_WORDS * TILE * 8);
+            bulk_g2s(ring_s + slot * (BUF_WORDS * TILE * 8), rec_tile + (size_t)k * MPCB200_KKT_WORDS * TILE, MPCB200_KKT_WORDS * TILE * 8, bar);
+        }
+        ++issued;
+    }
+    __device__ void issue_fwd(int k)
+    {
+        if (lane == 0)
+        {
+            const uint32_t slot = issued % KKT_RING, bar = bar_s + 8 * slot, dst = ring_s + slot * (BUF_WORDS * TILE * 8);
+            const bool with_d = EXT && dt_free;
+            mbar_expect_tx(bar, (NG + 12 + (with_d ? 3 : 0)) * TILE * 8);
+            bulk_g2s(dst, ric_tile + (size_t)k * RICW_MAX * TILE, NG * TILE * 8, bar);
+            bulk_g2s(dst + NG * TILE * 8, rec_tile + ((size_t)k * MPCB200_KKT_WORDS + MPCB200_K_A) * TILE, 12 * TILE * 8, bar);
+            if (with_d) bulk_g2s(dst + (NG + 12) * TILE * 8, rec_tile + ((size_t)k * MPCB200_KKT_WORDS + MPCB200_K_D) * TILE, 3 * TILE * 8, bar);
+        }
+        ++issued;
+    }
+    __device__ const double* acquire()
+    {
+        const uint32_t slot = consumed % KKT_RING;
+        mbar_wait(bar_s + 8 * slot, (consumed / KKT_RING) & 1u);
+        return ring + (size_t)slot * BUF_WORDS * TILE + lane;
+    }
+    __device__ void bwd_start(int kfirst)
+    {
+        for (int j = 0; j < KKT_RING && kfirst - j >= 0; ++j) issue_bwd(kfirst - j);
+    }
+    __device__ SmemView bwd_acquire(int) { return SmemView{acquire()}; }
+    __device__ void bwd_release(int k)
+    {
+        __syncwarp();  // every lane is done with the slot before the next copy lands in it
+        ++consumed;
+        if (k - KKT_RING >= 0) issue_bwd(k - KKT_RING);
+    }
+    __device__ void bwd_abort()
+    {
+        while (consumed != issued) { acquire(); ++consumed; }  // drain the copies in flight
+    }
+    __device__ void fwd_start(int N)
+    {
+        // the gains were written with ordinary stores by the lanes of this warp: order them before the async-proxy reads
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        for (int j = 0; j < KKT_RING && j <= N - 2; ++j) issue_fwd(j);
+        n_stages = N - 1;
+    }
+    int n_stages;
+    __device__ FwdViewSmem<NG> fwd_acquire(int) { return FwdViewSmem<NG>{acquire()}; }
+    __device__ void fwd_release(int k)
+    {
+        __syncwarp();
+        ++consumed;
+        if (k + KKT_RING < n_stages) issue_fwd(k + KKT_RING);
+    }
+};
+
 template <bool EXT>
 __global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, double* ric_tiles, const int* inst_of_slot, int B,
                                                        unsigned long long* counters)
 {
+    extern __shared__ __align__(128) unsigned char kkt_smem[];
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
-    const int b = inst_of_slot[tile * TILE + lane];
-    if (b < 0) return;
-    double* W = ws + (int64_t)b * L.stride;
     const int N = L.N;
-    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
-    TileRec rec{kkt_tiles + (size_t)tile * N * KW * TILE + lane};
-    TileRic ric{ric_tiles + (size_t)tile * N * RICW_MAX * TILE + lane};
+    const int b = inst_of_slot[tile * TILE + lane];
+    double* W = b >= 0 ? ws + (int64_t)b * L.stride : ws;
+    const bool active = b >= 0 && !(ASC(MPCB200_SC_STATUS) >= 0.0);
+    if (!__any_sync(FULLMASK, active)) return;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(kkt_smem);
+    TmaFeed<EXT> feed;
+    feed.rec_tile = kkt_tiles + (size_t)tile * N * KW * TILE;
+    feed.ric_tile = ric_tiles + (size_t)tile * N * RICW_MAX * TILE;
+    feed.rec = TileRec{feed.rec_tile + lane};
+    feed.ric = TileRic{ric_tiles + (size_t)tile * N * RICW_MAX * TILE + lane};
+    feed.ring = reinterpret_cast<double*>(kkt_smem + 128);
+    feed.ring_s = smem_addr(feed.ring);
+    feed.bar_s = smem_addr(bars);
+    feed.lane = lane; feed.dt_free = c.variable_dt;
+    feed.issued = feed.consumed = 0; feed.n_stages = N - 1;
+    if (lane == 0)
+    {
+        for (int i = 0; i < KKT_RING; ++i) mbar_init(feed.bar_s + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     StepOut step{W, L.oSTEP, N};
     double ddt = 0.0, delta = 0.0;
     int nreg = 0;
-    const int ok = riccati_solve_lane<EXT>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST),
-                                           &ddt, &delta, &nreg);
-    if (counters) { atomicAdd(counters, 1ull); atomicAdd(counters + 1, (unsigned long long)(nreg + 1)); }
+    const double htt = active ? ASC(MPCB200_SC_HTT) : 0.0, gt = active ? ASC(MPCB200_SC_GT) : 0.0, dlast = active ? ASC(MPCB200_SC_DELTA_LAST) : 0.0;
+    const int ok = riccati_solve_lane<EXT>(c, N, feed, step, active, htt, gt, dlast, &ddt, &delta, &nreg);
+    if (!active) return;
+    if (counters) { atomicAdd(counters, 1ull); atomicAdd(counters + 1, (unsigned long long)(nreg + (ok ? 1 : 0))); }
     ASC(MPCB200_SC_NREG) += (double)nreg;
     if (!ok && delta <= MAX_DELTA)
     {
@@ -339,6 +477,9 @@ __global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double*
     ASC(MPCB200_SC_DELTA) = delta;
     ASC(MPCB200_SC_DELTA_LAST) = delta;
 }
+
+template <bool EXT>
+static size_t kkt_smem_bytes() { return 128 + (size_t)KKT_RING * TmaFeed<EXT>::BUF_WORDS * TILE * 8; }
 
 // ---- kernel: PHASE_LINESEARCH -------------------------------------------------------------------------------
 // one CTA per instance (lane per stage, see eval_kernel); thread 0 owns the scalar decisions of the line search.
@@ -612,6 +753,8 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 4));
     CKC(cudaMalloc(&h->d_slot_of, B * 4)); CKC(cudaMalloc(&h->d_inst_of_slot, ((B + TILE - 1) / TILE) * TILE * 4));
     CKC(cudaMalloc(&h->d_counters, 16)); CKC(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
+    CKC(cudaFuncSetAttribute(kkt_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<true>()));
+    CKC(cudaFuncSetAttribute(kkt_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<false>()));
     CKC(cudaMallocHost(&h->h_nactive, 4));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
     CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
@@ -698,8 +841,8 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
         {
             const bool ext = h->cfg.variable_dt || h->cfg.xf_fixed[0] || h->cfg.xf_fixed[1] || h->cfg.xf_fixed[2];
             const int ntiles = (B + TILE - 1) / TILE;
-            if (ext) kkt_lane_kernel<true><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
-            else kkt_lane_kernel<false><<<ntiles, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
+            if (ext) kkt_lane_kernel<true><<<ntiles, 32, kkt_smem_bytes<true>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
+            else kkt_lane_kernel<false><<<ntiles, 32, kkt_smem_bytes<false>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
             break;
         }
         case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<B, group_threads, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt); break;

@@ -188,14 +188,13 @@ int emu_kkt(const Cfg* cp, double* W)
     make_layout(cp, MAX_OBST, MAX_VP, L);
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return 1;
-    TileRec rec{emu_kb(L, W)};
-    TileRic ric{emu_rb(L, W)};
+    PlainFeed feed{TileRec{emu_kb(L, W)}, TileRic{emu_rb(L, W)}};
     EmuStep step{W, L.oSTEP, N};
     const bool ext = c.variable_dt || c.xf_fixed[0] || c.xf_fixed[1] || c.xf_fixed[2];
     double ddt = 0.0, delta = 0.0;
     int nreg = 0, ok;
-    if (ext) ok = riccati_solve_lane<true>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
-    else ok = riccati_solve_lane<false>(c, N, rec, ric, step, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
+    if (ext) ok = riccati_solve_lane<true>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
+    else ok = riccati_solve_lane<false>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
     ASC(MPCB200_SC_NREG) += (double)nreg;
     if (!ok && delta <= MAX_DELTA)
     {
