@@ -215,7 +215,7 @@ int mpcb200_flush_l2(mpcb200_handle* h);
 #define MPCB200_K_HB 34  /* 5 : border column d2L/dw_k d(dt) */
 #define MPCB200_K_D 39   /* 3 : de_k/d(dt) = f(x_k,u_k) */
 #define MPCB200_STEP_WORDS 8
-#define MPCB200_SCAL_WORDS 24
+#define MPCB200_SCAL_WORDS 32
 /* indices into the SCAL field */
 #define MPCB200_SC_DT 0
 #define MPCB200_SC_MU 1
@@ -237,11 +237,15 @@ int mpcb200_flush_l2(mpcb200_handle* h);
 #define MPCB200_SC_GLDT 17   /* dL/d(dt) */
 #define MPCB200_SC_NBT 18    /* line-search backtracks so far */
 #define MPCB200_SC_COLD 19   /* 1 until the instance has been solved once (cold start pending) */
+#define MPCB200_SC_KKT_OK0 22 /* speculative KKT (small batches): attempt 0 / 1 of the iteration solved in parallel ... */
+#define MPCB200_SC_KKT_OK1 23
+#define MPCB200_SC_DELTA1 24  /* ... regularisation and d(dt) of attempt 1 (attempt 0 uses SC_DELTA / SC_DDT) */
+#define MPCB200_SC_DDT1 25
 #define MPCB200_SC_DEFER 21  /* 1 = the KKT phase spent its factorisation budget: null step, regularisation resumes next iteration */
 #define MPCB200_SC_TINY 20   /* consecutive iterations with a step length below 1e-8 (2 => the instance is given up) */
 
 int mpcb200_ws_count(const mpcb200_handle* h, int field);  /* number of components of a field (e.g. RS) */
-int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst);        /* dst: [B][count][N] (SCAL: [B][24]) */
+int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst);        /* dst: [B][count][N] (SCAL: [B][MPCB200_SCAL_WORDS]) */
 int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const double* src);
 
 /* phases of one solve, launchable one by one */
@@ -254,6 +258,9 @@ int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const double* src);
 int mpcb200_run_phase(mpcb200_handle* h, int phase, int B);
 /* Launch `phase` reps times back to back and report the mean device time per launch (CUDA events on the solver stream). */
 int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps, int flush_l2, double* ms_per_launch);
+/* Which phases a solve brackets with CUDA events for mpcb200_stats.ms (bit p = phase p).  Default: the KKT phase only
+   (1 << MPCB200_PHASE_KKT) -- every bracket costs a few microseconds of stream time; 0x1f times all of them. */
+int mpcb200_set_timing(mpcb200_handle* h, unsigned phase_mask);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */
 typedef struct mpcb200_stats {

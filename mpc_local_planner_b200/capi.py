@@ -16,7 +16,7 @@ OBST_STRIDE = 5
 INF = 1e30
 KKT_WORDS = 42
 STEP_WORDS = 8
-SCAL_WORDS = 24
+SCAL_WORDS = 32
 
 # enums (mirror include/mpcb200.h)
 ROBOT_UNICYCLE, ROBOT_SIMPLE_CAR, ROBOT_SIMPLE_CAR_FRONT, ROBOT_KIN_BICYCLE = 0, 1, 2, 3
@@ -160,7 +160,7 @@ EXPORTS = [
     "mpcb200_default_config", "mpcb200_create", "mpcb200_step_batch", "mpcb200_reset", "mpcb200_destroy",
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
-    "mpcb200_time_phase", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
+    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
 ]
 
 
@@ -199,6 +199,7 @@ def load_library(path=None):
     lib.mpcb200_ws_write.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.mpcb200_run_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.mpcb200_time_phase.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
+    lib.mpcb200_set_timing.argtypes = [vp, C.c_uint]
     lib.mpcb200_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.mpcb200_stats_reset.argtypes = [vp]
     if path == LIB_PATH:
@@ -328,6 +329,10 @@ class BatchSolver:
 
     def run_phase(self, phase, B=None):
         self._check(self.lib.mpcb200_run_phase(self.h, phase, B or self.B), "mpcb200_run_phase")
+
+    def set_timing(self, phase_mask):
+        """Phases bracketed by CUDA events inside a solve (bit p = phase p); default KKT only, 0x1f = all."""
+        self._check(self.lib.mpcb200_set_timing(self.h, phase_mask), "mpcb200_set_timing")
 
     def time_phase(self, phase, reps=10, flush_l2=True, B=None):
         ms = C.c_double(0.0)

@@ -29,7 +29,7 @@ struct WsLayout
 {
     int N, K, RS, M, V;      // grid points, obstacle rows per stage, row slots, max obstacles, max via-points
     int64_t stride;          // doubles per instance (multiple of 16 -> 128-byte aligned blocks)
-    int oX, oU, oNU, oS, oLAM, oKKT, oSTEP, oOBS, oSCAL, oDS, oDLAM, oRIC, oVPST;
+    int oX, oU, oNU, oS, oLAM, oKKT, oSTEP, oSTEP2, oOBS, oSCAL, oDS, oDLAM, oRIC, oVPST;
     int oR0, oOG;            // row residuals at the current point (RS x N), obstacle row value + gradient (4K x N)
     int oIN;                 // x0(3) xf(3) u_prev(2) n_obst n_vp has_xinit reinit
     int oOBST, oOTYPE, oVP, oXINIT;

@@ -16,7 +16,8 @@ static inline void make_layout(const mpcb200_config* c, int M, int V, WsLayout& 
     L.oIN = take(IN_WORDS);
     L.oX = take(3 * N); L.oU = take(2 * N); L.oNU = take(3 * N);
     L.oS = take(L.RS * N); L.oLAM = take(L.RS * N);
-    L.oKKT = -1; L.oSTEP = take(8 * N);  /* KKT records and Riccati gains live in 32-instance interleaved tiles */
+    L.oKKT = -1; L.oSTEP = take(8 * N); L.oSTEP2 = take(8 * N);  /* oSTEP2: step of the speculative second KKT attempt */
+     /* KKT records and Riccati gains live in 32-instance interleaved tiles */
     L.oOBS = take((L.K > 0 ? L.K : 1) * N);
     L.oDS = take(L.RS * N); L.oDLAM = take(L.RS * N);
     L.oR0 = take(L.RS * N); L.oOG = take(4 * (L.K > 0 ? L.K : 1) * N);

@@ -331,23 +331,52 @@ struct PlainFeed
     HD void fwd_release(int) {}
 };
 
+// Regularisation schedule of one IPM iteration (Ipopt's algorithm IC, at most MAX_INERTIA_TRIES attempts per iteration):
+// attempt 0 uses kkt_first_delta(), attempt t+1 uses kkt_escalate(delta_t).
+HD inline double kkt_first_delta(double dlast) { return (dlast > 0.0 && dlast / 3.0 >= DELTA_FLOOR) ? dlast / 3.0 : 0.0; }
+HD inline double kkt_escalate(double delta, double dlast)
+{
+    if (delta == 0.0) return (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
+    return delta * (dlast == 0.0 ? 100.0 : 8.0);
+}
+// Outcome of the two attempts of an iteration when they were run speculatively side by side (ok_t, delta_t of attempt
+// t): identical to running them one after the other.  Returns the winning attempt (0/1), -1 = null step (escalation
+// resumes next iteration at *delta_next), -2 = give up.  *nreg = failed attempts.
+HD inline int kkt_resolve(int ok0, int ok1, double d0, double d1, double dlast, int* nreg, double* delta_next)
+{
+    *delta_next = 0.0;
+    if (ok0) { *nreg = 0; return 0; }
+    *nreg = 1;
+    if (d1 > MAX_DELTA) return -2;
+    if (ok1) return 1;
+    *nreg = 2;
+    const double d2 = kkt_escalate(d1, dlast);
+    if (d2 > MAX_DELTA) return -2;
+    *delta_next = d2;
+    return -1;
+}
+
 // Full factorisation + solve of the instances of one tile, one lane each, with inertia-correcting regularisation
 // (Ipopt's algorithm IC) limited to MAX_INERTIA_TRIES sweeps.  Control flow is warp-uniform: a lane that does not
 // need (another) sweep idles through it.  Step: callable step(k, c, value) receiving dw (c = 0..4) and nu+ (c = 5..7).
-// Returns 1 if this lane's system was solved; *delta_out is the last regularisation tried.
+// Attempts try_first .. try_first + try_count - 1 of the iteration's schedule are run: (0, MAX_INERTIA_TRIES) is the
+// plain serial scheme; (t, 1) is attempt t alone (run side by side with the others on small batches, kkt_resolve()).
+// Returns 1 if this lane's system was solved; *delta_out is the regularisation used (serial: the next one after a failure).
 template <bool EXT, class Feed, class Step>
 HD inline int riccati_solve_lane(const Cfg& c, int N, Feed& feed, const Step& step, bool active, double htt, double gt, double dlast,
-                                 double* ddt_out, double* delta_out, int* nreg_out)
+                                 int try_first, int try_count, double* ddt_out, double* delta_out, int* nreg_out)
 {
     constexpr int NC = RicState<EXT>::NC;
     const int dt_free = c.variable_dt;
     RicState<EXT> s;
     double th[5] = {1.0, 0, 0, 0, 0};
     // after a regularised iteration the first attempt is delta_last/3 (decays back to 0): a failed attempt costs a full sweep
-    double delta = (dlast > 0.0 && dlast / 3.0 >= DELTA_FLOOR) ? dlast / 3.0 : 0.0;
+    double delta = kkt_first_delta(dlast);
     int ok = 0, nreg = 0;
     bool need = active;
-    for (int tries = 0; tries < MAX_INERTIA_TRIES; ++tries)
+    for (int t = 0; t < try_first; ++t) delta = kkt_escalate(delta, dlast);  // speculative later attempt: its delta is known up front
+    if (delta > MAX_DELTA) need = false;
+    for (int tries = 0; tries < try_count; ++tries)
     {
         if (!feed.any(need)) break;
         bool alive = need;
@@ -373,9 +402,11 @@ HD inline int riccati_solve_lane(const Cfg& c, int N, Feed& feed, const Step& st
             else
             {
                 ++nreg;
-                if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(dlast / 3.0, 1e-20);
-                else delta *= (dlast == 0.0 ? 100.0 : 8.0);
-                if (delta > MAX_DELTA) need = false;
+                if (try_count > 1)  // serial attempts: escalate for the next one (a lone speculative attempt reports the delta it used)
+                {
+                    delta = kkt_escalate(delta, dlast);
+                    if (delta > MAX_DELTA) need = false;
+                }
             }
         }
     }

@@ -428,12 +428,13 @@ struct TmaFeed
 };
 
 template <bool EXT>
-__global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, double* ric_tiles, const int* inst_of_slot, int B,
-                                                       unsigned long long* counters)
+__global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, double* ric_tiles, size_t ric_attempt_stride,
+                                                       const int* inst_of_slot, int B, int spec, unsigned long long* counters)
 {
     extern __shared__ __align__(128) unsigned char kkt_smem[];
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
+    const int attempt = blockIdx.y;  // speculative mode: attempt 0 and 1 of the regularisation schedule run side by side
     const int N = L.N;
     const int b = inst_of_slot[tile * TILE + lane];
     double* W = b >= 0 ? ws + (int64_t)b * L.stride : ws;
@@ -442,9 +443,9 @@ __global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double*
     uint64_t* bars = reinterpret_cast<uint64_t*>(kkt_smem);
     TmaFeed<EXT> feed;
     feed.rec_tile = kkt_tiles + (size_t)tile * N * KW * TILE;
-    feed.ric_tile = ric_tiles + (size_t)tile * N * RICW_MAX * TILE;
+    feed.ric_tile = ric_tiles + (size_t)attempt * ric_attempt_stride + (size_t)tile * N * RICW_MAX * TILE;
     feed.rec = TileRec{feed.rec_tile + lane};
-    feed.ric = TileRic{ric_tiles + (size_t)tile * N * RICW_MAX * TILE + lane};
+    feed.ric = TileRic{const_cast<double*>(feed.ric_tile) + lane};
     feed.ring = reinterpret_cast<double*>(kkt_smem + 128);
     feed.ring_s = smem_addr(feed.ring);
     feed.bar_s = smem_addr(bars);
@@ -456,13 +457,24 @@ __global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double*
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    StepOut step{W, L.oSTEP, N};
+    StepOut step{W, attempt ? L.oSTEP2 : L.oSTEP, N};
     double ddt = 0.0, delta = 0.0;
     int nreg = 0;
     const double htt = active ? ASC(MPCB200_SC_HTT) : 0.0, gt = active ? ASC(MPCB200_SC_GT) : 0.0, dlast = active ? ASC(MPCB200_SC_DELTA_LAST) : 0.0;
-    const int ok = riccati_solve_lane<EXT>(c, N, feed, step, active, htt, gt, dlast, &ddt, &delta, &nreg);
+    const int ok = riccati_solve_lane<EXT>(c, N, feed, step, active, htt, gt, dlast, spec ? attempt : 0, spec ? 1 : MAX_INERTIA_TRIES, &ddt, &delta, &nreg);
     if (!active) return;
-    if (counters) { atomicAdd(counters, 1ull); atomicAdd(counters + 1, (unsigned long long)(nreg + (ok ? 1 : 0))); }
+    if (counters)
+    {
+        if (attempt == 0) atomicAdd(counters, 1ull);
+        atomicAdd(counters + 1, spec ? 1ull : (unsigned long long)(nreg + (ok ? 1 : 0)));
+    }
+    if (spec)
+    {
+        // the line-search kernel picks the winner (kkt_resolve)
+        if (attempt == 0) { ASC(MPCB200_SC_KKT_OK0) = (double)ok; ASC(MPCB200_SC_DELTA) = delta; ASC(MPCB200_SC_DDT) = ddt; }
+        else { ASC(MPCB200_SC_KKT_OK1) = (double)ok; ASC(MPCB200_SC_DELTA1) = delta; ASC(MPCB200_SC_DDT1) = ddt; }
+        return;
+    }
     ASC(MPCB200_SC_NREG) += (double)nreg;
     if (!ok && delta <= MAX_DELTA)
     {
@@ -491,13 +503,42 @@ struct LsShared
     int accept;
 };
 
-__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt)
+__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt,
+                                                                             int spec)
 {
     __shared__ LsShared sh;
+    __shared__ int s_win;
     const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     double* W = ws + (int64_t)inst * L.stride;
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    if (spec)
+    {
+        // the KKT phase ran attempts 0 and 1 of the regularisation schedule side by side: pick the winner
+        __syncthreads();
+        if (tid == 0)
+        {
+            int nreg = 0;
+            double dnext = 0.0;
+            const double d0 = ASC(MPCB200_SC_DELTA), d1 = ASC(MPCB200_SC_DELTA1);
+            const int win = kkt_resolve(ASC(MPCB200_SC_KKT_OK0) != 0.0, ASC(MPCB200_SC_KKT_OK1) != 0.0, d0, d1, ASC(MPCB200_SC_DELTA_LAST), &nreg, &dnext);
+            ASC(MPCB200_SC_NREG) += (double)nreg;
+            if (win == -2) ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;
+            else if (win == -1) { ASC(MPCB200_SC_DELTA_LAST) = 3.0 * dnext; ASC(MPCB200_SC_DEFER) = 1.0; }
+            else
+            {
+                const double dw = win ? d1 : d0;
+                ASC(MPCB200_SC_DEFER) = 0.0;
+                if (win) ASC(MPCB200_SC_DDT) = ASC(MPCB200_SC_DDT1);
+                ASC(MPCB200_SC_DELTA) = dw;
+                ASC(MPCB200_SC_DELTA_LAST) = dw;
+            }
+            s_win = win;
+        }
+        __syncthreads();
+        if (s_win == -2) return;
+        if (s_win == 1) L.oSTEP = L.oSTEP2;
+    }
     if (ASC(MPCB200_SC_DEFER) != 0.0)
     {
         // the KKT phase spent its factorisation budget: null step
@@ -637,6 +678,10 @@ struct mpcb200_handle
     int max_batch, device, B;
     double* ws;
     double *kkt_tiles, *ric_tiles;
+    size_t ric_attempt_stride;  // doubles between the gain tiles of KKT attempt 0 and 1 (speculative mode)
+    int num_sms;
+    int spec;                   // this solve runs the two KKT attempts of an iteration side by side (small batches)
+    unsigned timing_mask;       // phases bracketed by CUDA events inside solve (bit = phase id); default: KKT only
     cudaStream_t stream;
     // compact device input / output staging
     double *d_x0, *d_xf, *d_uprev, *d_obst, *d_vp, *d_xinit;
@@ -645,7 +690,9 @@ struct mpcb200_handle
     double *d_useq, *d_xseq, *d_dt, *d_kkt, *d_upacked;
     int *d_status, *d_iters, *d_nactive, *d_slot_of, *d_inst_of_slot;
     unsigned long long* d_counters;
-    int* h_nactive;  // pinned
+    int* h_nactive;  // pinned, two poll slots
+    int* nactive_ptr;            // where the next eval launch counts unfinished instances (or null)
+    cudaEvent_t poll_ev[2];
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
     double uprev_dt;
@@ -739,9 +786,12 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     {
         const size_t ntiles = (B + TILE - 1) / TILE;
         CKC(cudaMalloc(&h->kkt_tiles, ntiles * N * KW * TILE * sizeof(double)));
-        CKC(cudaMalloc(&h->ric_tiles, ntiles * N * RICW_MAX * TILE * sizeof(double)));
+        h->ric_attempt_stride = ntiles * N * RICW_MAX * TILE;
+        CKC(cudaMalloc(&h->ric_tiles, 2 * h->ric_attempt_stride * sizeof(double)));
         CKC(cudaMemsetAsync(h->kkt_tiles, 0, ntiles * N * KW * TILE * sizeof(double), h->stream));
-        CKC(cudaMemsetAsync(h->ric_tiles, 0, ntiles * N * RICW_MAX * TILE * sizeof(double), h->stream));
+        CKC(cudaMemsetAsync(h->ric_tiles, 0, 2 * h->ric_attempt_stride * sizeof(double), h->stream));
+        h->spec = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT;
+        CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     }
     CKC(cudaMalloc(&h->d_x0, B * 3 * 8)); CKC(cudaMalloc(&h->d_xf, B * 3 * 8)); CKC(cudaMalloc(&h->d_uprev, B * 2 * 8));
     CKC(cudaMalloc(&h->d_obst, B * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CKC(cudaMalloc(&h->d_obst_count, B * 4));
@@ -750,12 +800,14 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_xinit, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_reinit, B));
     CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
     CKC(cudaMalloc(&h->d_kkt, B * 8)); CKC(cudaMalloc(&h->d_upacked, B * (N - 1) * 2 * 8));
-    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 4));
+    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8));
     CKC(cudaMalloc(&h->d_slot_of, B * 4)); CKC(cudaMalloc(&h->d_inst_of_slot, ((B + TILE - 1) / TILE) * TILE * 4));
     CKC(cudaMalloc(&h->d_counters, 16)); CKC(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
     CKC(cudaFuncSetAttribute(kkt_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<true>()));
     CKC(cudaFuncSetAttribute(kkt_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<false>()));
-    CKC(cudaMallocHost(&h->h_nactive, 4));
+    CKC(cudaMallocHost(&h->h_nactive, 8));
+    h->nactive_ptr = nullptr;
+    CKC(cudaEventCreateWithFlags(&h->poll_ev[0], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
     CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
     CKC(cudaMemsetAsync(h->d_flush, 0, h->flush_n * 8, h->stream));
@@ -823,6 +875,7 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
     const int grid4 = grid_for(B, WARPS_PER_CTA);
     const int gw = (h->cfg.n + 31) / 32;
     const int group_threads = 32 * (gw < MAX_GROUP_WARPS ? gw : MAX_GROUP_WARPS);
+    const int spec = h->spec;
     if (timed && ev_begin(h, phase)) return set_err(h, MPCB200_E_CUDA, "cudaEventCreate failed");
     switch (phase)
     {
@@ -831,27 +884,36 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
         case MPCB200_PHASE_EVAL:
             switch (group_threads >> 5)
             {
-                case 1: eval_kernel<1><<<B, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
-                case 2: eval_kernel<2><<<B, 64, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
-                case 3: eval_kernel<3><<<B, 96, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
-                default: eval_kernel<4><<<B, 128, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->d_nactive); break;
+                case 1: eval_kernel<1><<<B, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
+                case 2: eval_kernel<2><<<B, 64, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
+                case 3: eval_kernel<3><<<B, 96, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
+                default: eval_kernel<4><<<B, 128, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
             }
             break;
         case MPCB200_PHASE_KKT:
         {
             const bool ext = h->cfg.variable_dt || h->cfg.xf_fixed[0] || h->cfg.xf_fixed[1] || h->cfg.xf_fixed[2];
             const int ntiles = (B + TILE - 1) / TILE;
-            if (ext) kkt_lane_kernel<true><<<ntiles, 32, kkt_smem_bytes<true>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
-            else kkt_lane_kernel<false><<<ntiles, 32, kkt_smem_bytes<false>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->d_inst_of_slot, B, h->d_counters);
+            const dim3 kgrid(ntiles, spec ? 2 : 1);
+            if (ext) kkt_lane_kernel<true><<<kgrid, 32, kkt_smem_bytes<true>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->ric_attempt_stride, h->d_inst_of_slot, B, spec, h->d_counters);
+            else kkt_lane_kernel<false><<<kgrid, 32, kkt_smem_bytes<false>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->ric_attempt_stride, h->d_inst_of_slot, B, spec, h->d_counters);
             break;
         }
-        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<B, group_threads, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt); break;
+        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<B, group_threads, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec); break;
         default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
     }
     if (timed) ev_end(h);
     h->stats.launches_total += 1;
     CK(cudaGetLastError());
     return 0;
+}
+
+static int launch_phase_eval(mpcb200_handle* h, int B, int* nactive, bool timed)
+{
+    h->nactive_ptr = nactive;
+    const int rc = launch_phase(h, MPCB200_PHASE_EVAL, B, 0, 0, timed);
+    h->nactive_ptr = nullptr;
+    return rc;
 }
 
 static int launch_regroup(mpcb200_handle* h, int B)
@@ -928,27 +990,43 @@ static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_
     cudaEvent_t t0, t1;
     CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, h->stream));
-    int rc = launch_phase(h, MPCB200_PHASE_INIT, B, force_cold, 0, true);
+    const unsigned tm = h->timing_mask;
+    auto timed = [&](int phase) { return ((tm >> phase) & 1u) != 0; };
+    // small batches leave most SMs idle in the KKT phase: run both regularisation attempts of an iteration side by side
+    h->spec = (2 * ((B + TILE - 1) / TILE) <= h->num_sms) ? 1 : 0;
+    int rc = launch_phase(h, MPCB200_PHASE_INIT, B, force_cold, 0, timed(MPCB200_PHASE_INIT));
     if (rc) return rc;
     const int outer = h->cfg.outer_iterations > 0 ? h->cfg.outer_iterations : 1;
     for (int oi = 0; oi < outer; ++oi)
     {
-        if ((rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, oi == 0, true))) return rc;
-        for (int it = 0; it <= h->cfg.max_iter; ++it)
+        if ((rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, oi == 0, timed(MPCB200_PHASE_ASSOCIATE)))) return rc;
+        // The number of unfinished instances is polled every POLL iterations, one poll behind: the host keeps queueing
+        // iterations while the count of the previous poll travels back, so the stream never drains (a finished
+        // instance makes every kernel an immediate no-op, so the few surplus iterations are free).
+        const int POLL = 4;
+        int pending = -1;  // slot of the poll in flight
+        bool done = false;
+        for (int it = 0; it <= h->cfg.max_iter && !done; ++it)
         {
-            const bool poll = (it % 4 == 3) || it == h->cfg.max_iter;
-            if (poll) CK(cudaMemsetAsync(h->d_nactive, 0, 4, h->stream));
+            const bool poll = (it % POLL == POLL - 1) || it == h->cfg.max_iter;
+            const int slot = (it / POLL) & 1;
+            if (poll) CK(cudaMemsetAsync(h->d_nactive + slot, 0, 4, h->stream));
             if ((rc = launch_regroup(h, B))) return rc;
-            if ((rc = launch_phase(h, MPCB200_PHASE_EVAL, B, 0, 0, true))) return rc;
+            if ((rc = launch_phase_eval(h, B, poll ? h->d_nactive + slot : nullptr, timed(MPCB200_PHASE_EVAL)))) return rc;
             if (poll)
             {
-                CK(cudaMemcpyAsync(h->h_nactive, h->d_nactive, 4, cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaStreamSynchronize(h->stream));
-                if (*h->h_nactive == 0) break;
+                CK(cudaMemcpyAsync(h->h_nactive + slot, h->d_nactive + slot, 4, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaEventRecord(h->poll_ev[slot], h->stream));
+                if (pending >= 0)
+                {
+                    CK(cudaEventSynchronize(h->poll_ev[pending]));
+                    if (h->h_nactive[pending] == 0) done = true;
+                }
+                pending = slot;
             }
-            if (it == h->cfg.max_iter) break;
-            if ((rc = launch_phase(h, MPCB200_PHASE_KKT, B, 0, 0, true))) return rc;
-            if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, true))) return rc;
+            if (it == h->cfg.max_iter || done) break;
+            if ((rc = launch_phase(h, MPCB200_PHASE_KKT, B, 0, 0, timed(MPCB200_PHASE_KKT)))) return rc;
+            if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, timed(MPCB200_PHASE_LINESEARCH)))) return rc;
         }
     }
     OutputPtrs o{h->d_useq, h->d_xseq, h->d_dt, h->d_status, h->d_kkt, h->d_iters, h->d_upacked};
@@ -1123,10 +1201,18 @@ extern "C" int mpcb200_run_phase(mpcb200_handle* h, int phase, int B)
     int rc = check_batch(h, B);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
+    h->spec = 0;  // single phases run the plain serial KKT attempts
     if (phase == MPCB200_PHASE_EVAL && (rc = launch_regroup(h, B))) return rc;
-    if ((rc = launch_phase(h, phase, B, phase == MPCB200_PHASE_INIT ? 0 : 0, 1, true))) return rc;
+    if ((rc = launch_phase(h, phase, B, 0, 1, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     ev_collect(h);
+    return 0;
+}
+
+extern "C" int mpcb200_set_timing(mpcb200_handle* h, unsigned phase_mask)
+{
+    if (!h) return MPCB200_E_INVALID;
+    h->timing_mask = phase_mask;
     return 0;
 }
 
@@ -1134,6 +1220,7 @@ extern "C" int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps,
 {
     int rc = check_batch(h, B);
     if (rc) return rc;
+    h->spec = 0;
     if (reps < 1) reps = 1;
     CK(cudaSetDevice(h->device));
     cudaEvent_t a, b;

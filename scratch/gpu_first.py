@@ -8,7 +8,11 @@ for cid,B,tol in ((2,1024,1e-6),(2,4096,1e-6),(3,1024,1e-6),(4,2048,1e-6)):
     for rep in range(3):
         s.reset(); s.stats_reset()
         t=time.time(); out=s.step(data["x0"],data["xf"],data["u_prev"],data["u_prev_dt"],data["obstacles"],data["viapoints"]); el=time.time()-t
-    st=s.stats(); conv=(out['status']==0).sum()
+    conv=(out['status']==0).sum()
+    s.set_timing(0x1f); s.reset(); s.stats_reset()
+    out2=s.step(data["x0"],data["xf"],data["u_prev"],data["u_prev_dt"],data["obstacles"],data["viapoints"])
+    st=s.stats(); s.set_timing(1<<3)
+    assert (out2['status']==out['status']).all()
     print(json.dumps(dict(cfg=cid,B=B,conv=int(conv),wall_ms=el*1e3,dev_ms=out['solve_time_s']*1e3,solves_per_s=conv/el,stats=st,iters_mean=float(out['iters'].mean()))))
     # kernel timing
     s.reset(); s.upload(data["x0"],data["xf"],data["u_prev"],data["u_prev_dt"],data["obstacles"],data["viapoints"])

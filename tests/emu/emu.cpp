@@ -193,8 +193,8 @@ int emu_kkt(const Cfg* cp, double* W)
     const bool ext = c.variable_dt || c.xf_fixed[0] || c.xf_fixed[1] || c.xf_fixed[2];
     double ddt = 0.0, delta = 0.0;
     int nreg = 0, ok;
-    if (ext) ok = riccati_solve_lane<true>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
-    else ok = riccati_solve_lane<false>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
+    if (ext) ok = riccati_solve_lane<true>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), 0, MAX_INERTIA_TRIES, &ddt, &delta, &nreg);
+    else ok = riccati_solve_lane<false>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), 0, MAX_INERTIA_TRIES, &ddt, &delta, &nreg);
     ASC(MPCB200_SC_NREG) += (double)nreg;
     if (!ok && delta <= MAX_DELTA)
     {
