@@ -61,6 +61,31 @@ class ClockSampler(threading.Thread):
         self.rows = []
 
     def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        while not self.stop_flag:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            self.rows.append([str(sm), str(mx), str(pw)] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+            time.sleep(0.01)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -71,7 +96,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.03)
 
     def summary(self):
         if not self.rows:
@@ -95,7 +120,7 @@ def cpu_arm(cfg, data_fn, seconds_target, threads):
     el = time.time() - t
     # grow the sample towards the time target (bounded)
     if el < seconds_target / 4:
-        n2 = int(min(n * (seconds_target / 2) / max(el, 1e-3), 4096))
+        n2 = int(min(n * (seconds_target / 2) / max(el, 1e-3), 32768))
         data = data_fn(n2)
         t = time.time()
         out = orc.step_batch(cfg, data, n_threads=threads)
@@ -108,7 +133,7 @@ def cpu_arm(cfg, data_fn, seconds_target, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
@@ -176,6 +201,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one CUDA stream carries the solver kernels, the L2 flush, the export of u* and the NCCL all-gather, so that
+    # CUDA events recorded on it bracket the timed region on the device
+    stream = torch.cuda.Stream(device=dev)
+    solver.set_stream(stream.cuda_stream)
+
     # all-gather buffers for u* (SURVEY 8e): every rank ends up with all optimal controls
     send = torch.empty(B * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}")
     recv = torch.empty(world * B * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}") if world > 1 else None
@@ -186,25 +216,42 @@ def main():
         if world > 1:
             solver.export_controls(send.data_ptr())
             dist.all_gather_into_tensor(recv, send)
-        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; returns the device time between CUDA events on the work stream."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                last = fn()
+            e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) * 1e-3, last
 
     solver.upload(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
-    for _ in range(args.warmup):
-        resident_step()
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            resident_step()
+    torch.cuda.synchronize()
     solver.stats_reset()
     sampler = ClockSampler(dev)
     sampler.start()
-    barrier()
-    t0 = time.time()
-    for _ in range(args.steps):
-        resident_step()
-    barrier()
-    el = time.time() - t0
+    el, _ = timed(resident_step, args.steps)
     sampler.stop_flag = True
     st = solver.stats()
     res = solver.fetch()
     conv_local = int((res["status"] == 0).sum())
     iters_mean = float(res["iters"].mean())
+    # per-phase device times: one extra, untimed step with every phase bracketed by events (the brackets cost stream time,
+    # so the timed region above only brackets the KKT phase)
+    solver.set_timing(0x1f)
+    solver.stats_reset()
+    with torch.cuda.stream(stream):
+        resident_step()
+    torch.cuda.synchronize()
+    st_all = solver.stats()
+    solver.set_timing(1 << capi.PHASE_KKT)
 
     # ---- end-to-end through the C ABI with pinned host buffers ----
     def pinned(a):
@@ -221,22 +268,18 @@ def main():
     def e2e_step():
         solver.reset()
         solver.flush_l2()
-        out = solver.step(hx0, hxf, hup, data["u_prev_dt"], (oc, ot, op), None)
+        out = solver.step(hx0, hxf, hup, data["u_prev_dt"], (oc, ot, op), None)  # H2D inputs, solve, D2H results
         if world > 1:
             solver.export_controls(send.data_ptr())
             dist.all_gather_into_tensor(recv, send)
-            torch.cuda.synchronize()
         return out
-    for _ in range(2):
-        e2e_step()
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            e2e_step()
+    torch.cuda.synchronize()
     st0 = solver.stats()
-    barrier()
-    t1 = time.time()
     e2e_steps = max(3, args.steps // 2)
-    for _ in range(e2e_steps):
-        out = e2e_step()
-    barrier()
-    el_e2e = time.time() - t1
+    el_e2e, out = timed(e2e_step, e2e_steps)
     st1 = solver.stats()
     conv_e2e = int((out["status"] == 0).sum())
 
@@ -271,7 +314,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    total_ms = sum(st["ms"])
+    total_ms = el / args.steps * 1e3 * args.steps
     roofline = {"bound": "hbm", "kernel": "kkt_kernel (Riccati factorisation + solve)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_instance": bpi, "instances_per_launch_avg": units / kkt_launches,
@@ -290,7 +333,8 @@ def main():
                 "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps,
                 "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps},
         "gpu_launches": int(st["launches_total"]),
-        "kernel_ms": dict(zip(["init", "associate", "eval", "kkt", "linesearch"], [m / args.steps for m in st["ms"]])),
+        "kernel_ms": dict(zip(["init", "associate", "eval", "kkt", "linesearch"], st_all["ms"])),
+        "timing": "CUDA events on the work stream around the K steps (max over ranks); kernel_ms from one extra step with all phases bracketed",
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline and world == 1:

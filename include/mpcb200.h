@@ -261,6 +261,9 @@ int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps, int flush_
 /* Which phases a solve brackets with CUDA events for mpcb200_stats.ms (bit p = phase p).  Default: the KKT phase only
    (1 << MPCB200_PHASE_KKT) -- every bracket costs a few microseconds of stream time; 0x1f times all of them. */
 int mpcb200_set_timing(mpcb200_handle* h, unsigned phase_mask);
+/* Run all work of this handle on the caller's CUDA stream (a cudaStream_t; NULL restores the handle's own stream), e.g. the
+   stream the NCCL all-gather of the optimal controls is enqueued on.  The previous stream is drained first. */
+int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */
 typedef struct mpcb200_stats {

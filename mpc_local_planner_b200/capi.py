@@ -160,7 +160,7 @@ EXPORTS = [
     "mpcb200_default_config", "mpcb200_create", "mpcb200_step_batch", "mpcb200_reset", "mpcb200_destroy",
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
-    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
+    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
 ]
 
 
@@ -200,6 +200,7 @@ def load_library(path=None):
     lib.mpcb200_run_phase.argtypes = [vp, C.c_int, C.c_int]
     lib.mpcb200_time_phase.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     lib.mpcb200_set_timing.argtypes = [vp, C.c_uint]
+    lib.mpcb200_set_stream.argtypes = [vp, vp]
     lib.mpcb200_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.mpcb200_stats_reset.argtypes = [vp]
     if path == LIB_PATH:
@@ -329,6 +330,10 @@ class BatchSolver:
 
     def run_phase(self, phase, B=None):
         self._check(self.lib.mpcb200_run_phase(self.h, phase, B or self.B), "mpcb200_run_phase")
+
+    def set_stream(self, cuda_stream):
+        """Run on the caller's CUDA stream (an integer cudaStream_t, e.g. torch.cuda.Stream().cuda_stream); 0 restores."""
+        self._check(self.lib.mpcb200_set_stream(self.h, C.c_void_p(int(cuda_stream) if cuda_stream else None)), "mpcb200_set_stream")
 
     def set_timing(self, phase_mask):
         """Phases bracketed by CUDA events inside a solve (bit p = phase p); default KKT only, 0x1f = all."""

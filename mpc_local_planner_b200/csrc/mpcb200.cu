@@ -682,7 +682,7 @@ struct mpcb200_handle
     int num_sms;
     int spec;                   // this solve runs the two KKT attempts of an iteration side by side (small batches)
     unsigned timing_mask;       // phases bracketed by CUDA events inside solve (bit = phase id); default: KKT only
-    cudaStream_t stream;
+    cudaStream_t stream, own_stream;  // stream in use / the stream the handle created
     // compact device input / output staging
     double *d_x0, *d_xf, *d_uprev, *d_obst, *d_vp, *d_xinit;
     int *d_obst_count, *d_obst_type, *d_vp_count;
@@ -779,7 +779,8 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
         if (e_ != cudaSuccess) { std::string m = std::string(#call) + ": " + cudaGetErrorString(e_); delete h; return set_err(nullptr, MPCB200_E_CUDA, m); } \
     } while (0)
     CKC(cudaSetDevice(device));
-    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
     const size_t B = (size_t)max_batch, N = (size_t)cfg->n;
     CKC(cudaMalloc(&h->ws, B * h->L.stride * sizeof(double)));
     CKC(cudaMemsetAsync(h->ws, 0, B * h->L.stride * sizeof(double), h->stream));
@@ -831,7 +832,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
-    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
@@ -1206,6 +1207,15 @@ extern "C" int mpcb200_run_phase(mpcb200_handle* h, int phase, int B)
     if ((rc = launch_phase(h, phase, B, 0, 1, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     ev_collect(h);
+    return 0;
+}
+
+extern "C" int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream)
+{
+    if (!h) return MPCB200_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     return 0;
 }
 
