@@ -23,8 +23,16 @@
 #define AOBS(c_, k_) W[L.oOBS + (c_) * N + (k_)]
 #define ADS(c_, k_) W[L.oDS + (c_) * N + (k_)]
 #define ADLAM(c_, k_) W[L.oDLAM + (c_) * N + (k_)]
-#define AR0(c_, k_) W[L.oR0 + (c_) * N + (k_)]
-#define AOG(c_, k_) W[L.oOG + (c_) * N + (k_)]
+// W addresses the instance image: the leading part of the workspace (scalars, inputs, iterate, steps, obstacles), which the
+// eval / line-search kernels stage in shared memory; G always addresses the instance's workspace in global memory (fields
+// outside the image, and every result that must outlive the kernel).  Host emulator and the init kernels pass W == G.
+#define GR0(c_, k_) G[L.oR0 + (c_) * N + (k_)]
+#define GOG(c_, k_) G[L.oOG + (c_) * N + (k_)]
+#define GX(c_, k_) G[L.oX + (c_) * N + (k_)]
+#define GU(c_, k_) G[L.oU + (c_) * N + (k_)]
+#define GNU(c_, k_) G[L.oNU + (c_) * N + (k_)]
+#define GS(c_, k_) G[L.oS + (c_) * N + (k_)]
+#define GLAM(c_, k_) G[L.oLAM + (c_) * N + (k_)]
 #define ASC(i_) W[L.oSCAL + (i_)]
 #define AIN(i_) W[L.oIN + (i_)]
 
@@ -130,7 +138,7 @@ HD inline void lin_rows_component(const Cfg& c, const WsLayout& L, const double*
 
 // Stage functions + derivatives of stage k -> condensed KKT record (G holds the mu-independent part g0, the
 // coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
-HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb, double uprev_dt, int k, EvalAcc& acc)
+HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G, double* Kb, double uprev_dt, int k, EvalAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT);
@@ -292,7 +300,7 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* Kb
             const double rs = 1.0 / s, r = g + s, sig = lam * rs, c0 = sig * r;
             row_stats(acc, rp, r, s, lam);
             const double gr[3] = {-gd[0], -gd[1], -gd[2]};
-            AOG(4 * j + 0, k) = g; AOG(4 * j + 1, k) = gr[0]; AOG(4 * j + 2, k) = gr[1]; AOG(4 * j + 3, k) = gr[2];
+            GOG(4 * j + 0, k) = g; GOG(4 * j + 1, k) = gr[0]; GOG(4 * j + 2, k) = gr[1]; GOG(4 * j + 3, k) = gr[2];
             int q = 0;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -386,7 +394,7 @@ struct LsAcc
 HD inline void lsacc_init(LsAcc& a) { a.a_p = 1.0; a.a_d = 1.0; a.dphi_bar = a.curv = a.dJ = 0.0; }
 
 // slack / multiplier steps of the rows owned by stage k, fraction to the boundary, directional derivatives
-HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const double* Kb, double uprev_dt, int k, LsAcc& acc)
+HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double* G, const double* Kb, double uprev_dt, int k, LsAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT), mu = ASC(MPCB200_SC_MU), ddt = ASC(MPCB200_SC_DDT);
@@ -404,7 +412,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const 
         double g, gdz;
         if (sl < 8)
         {
-            if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; AR0(sl, k) = 0.0; continue; }
+            if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
             const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
             const double uk = (k <= N - 2) ? AU(i, k) : 0.0;
             const double um = (sl >= 4) ? ((k >= 1) ? AU(i, k - 1) : AIN(IN_UPREV + i)) : 0.0;
@@ -417,9 +425,9 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const 
         {
             const int j = sl - 8;
             const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(j, k) : -1;
-            if (oi < 0) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; AR0(sl, k) = 0.0; continue; }
-            g = AOG(4 * j + 0, k);
-            gdz = AOG(4 * j + 1, k) * dx[0] + AOG(4 * j + 2, k) * dx[1] + AOG(4 * j + 3, k) * dx[2];
+            if (oi < 0) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
+            g = GOG(4 * j + 0, k);
+            gdz = GOG(4 * j + 1, k) * dx[0] + GOG(4 * j + 2, k) * dx[1] + GOG(4 * j + 3, k) * dx[2];
         }
         const double s = AS(sl, k), lam = ALAM(sl, k);
         const double rs = 1.0 / s;
@@ -428,7 +436,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const 
         const double dl = mu * rs - lam - (lam * rs) * ds;
         ADS(sl, k) = ds;
         ADLAM(sl, k) = dl;
-        AR0(sl, k) = r0;
+        GR0(sl, k) = r0;
         if (ds < 0) acc.a_p = fmin(acc.a_p, -tau * s / ds);
         if (dl < 0) acc.a_d = fmin(acc.a_d, -tau * lam / dl);
         acc.dphi_bar += -mu * ds * rs;
@@ -494,7 +502,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, const 
 struct TrialAcc { double obj, inf1, blog; };
 // merit pieces of stage k at the trial point z + alpha dz, s + alpha ds.  Linear rows are exact in alpha:
 // g(alpha) + s(alpha) = (1 - alpha) r0, so only the dynamics defect, the objective and the obstacle rows are re-evaluated.
-HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, double uprev_dt, int k, double alpha, TrialAcc& acc)
+HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, const double* G, double uprev_dt, int k, double alpha, TrialAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dtt = ASC(MPCB200_SC_DT) + (c.variable_dt ? alpha * ASC(MPCB200_SC_DDT) : 0.0);
@@ -563,7 +571,7 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
     for (int sl = 0; sl < 8; ++sl)
     {
         if (!lin_row_active(c, N, k, sl, uprev_dt)) continue;
-        acc.inf1 += fabs(oma * AR0(sl, k));
+        acc.inf1 += fabs(oma * GR0(sl, k));
         rowprod_add(rp, AS(sl, k) + alpha * ADS(sl, k), acc.blog);
     }
     if (k >= 1 && k <= N - 2)
@@ -581,18 +589,18 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
 }
 
 // accept the step: z, s, lambda, nu of stage k
-HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int k, double alpha, double a_dual)
+HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W, double* G, double uprev_dt, int k, double alpha, double a_dual)
 {
     const int N = L.N, K = L.K;
     const double mu = ASC(MPCB200_SC_MU);
     // NOTE: reads STEP of stage k only -> safe to run lane-parallel after all trial evaluations are done
     const double d0 = ASTEP(0, k), d1 = ASTEP(1, k), d2 = ASTEP(2, k);
-    AX(0, k) += alpha * d0; AX(1, k) += alpha * d1; AX(2, k) += alpha * d2;
+    GX(0, k) = AX(0, k) + alpha * d0; GX(1, k) = AX(1, k) + alpha * d1; GX(2, k) = AX(2, k) + alpha * d2;
     if (k <= N - 2)
     {
-        AU(0, k) += alpha * ASTEP(3, k);
-        AU(1, k) += alpha * ASTEP(4, k);
-        for (int i = 0; i < 3; ++i) ANU(i, k) += alpha * (ASTEP(5 + i, k) - ANU(i, k));
+        GU(0, k) = AU(0, k) + alpha * ASTEP(3, k);
+        GU(1, k) = AU(1, k) + alpha * ASTEP(4, k);
+        for (int i = 0; i < 3; ++i) GNU(i, k) = ANU(i, k) + alpha * (ASTEP(5 + i, k) - ANU(i, k));
     }
     for (int sl = 0; sl < 8 + K; ++sl)
     {
@@ -605,8 +613,8 @@ HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, double* W, doubl
         const double lo = mu / (KAPPA_SIGMA * s), hi = KAPPA_SIGMA * mu / s;
         if (lam < lo) lam = lo;
         if (lam > hi) lam = hi;
-        AS(sl, k) = s;
-        ALAM(sl, k) = lam;
+        GS(sl, k) = s;
+        GLAM(sl, k) = lam;
     }
 }
 

@@ -24,6 +24,7 @@
 
 #define FULLMASK 0xffffffffu
 #define WARPS_PER_CTA 4
+#define MAX_IMG_SMEM (227 * 1024 - 2048)  // dynamic shared memory the eval / line-search kernels may request
 #define MAX_GROUP_WARPS 4   // warps of the CTA that owns one instance in the eval / line-search kernels (lane per stage)
 
 // ---- warp reductions (fp64 via two 32-bit shuffles each) ------------------------------------------------
@@ -252,64 +253,6 @@ __global__ void __launch_bounds__(1024) regroup_kernel(WsLayout L, const double*
     for (int sidx = B + tid; sidx < nslots; sidx += 1024) inst_of_slot[sidx] = -1;
 }
 
-// ---- kernel: PHASE_EVAL -----------------------------------------------------------------------------------
-// ONE CTA PER INSTANCE, one lane per horizon stage: ceil(N/32) warps (at most MAX_GROUP_WARPS, then the stage loop
-// wraps).  Splitting an instance over several warps halves the dependent instruction stream each warp walks through --
-// at BASELINE batch sizes every kernel of the IPM iteration is latency- not throughput-bound.
-__device__ __forceinline__ void evalacc_warp_reduce(EvalAcc& a)
-{
-    a.dual_inf = warp_max(a.dual_inf); a.prim_inf = warp_max(a.prim_inf);
-    a.sl_max = warp_max(a.sl_max); a.sl_min = warp_min(a.sl_min);
-    a.sum_nu = warp_sum(a.sum_nu); a.sum_lam = warp_sum(a.sum_lam); a.inf1 = warp_sum(a.inf1); a.blog = warp_sum(a.blog);
-    a.gt0 = warp_sum(a.gt0); a.gt1 = warp_sum(a.gt1); a.gldt = warp_sum(a.gldt); a.htt = warp_sum(a.htt);
-    a.obj = warp_sum(a.obj); a.m_ineq = warp_sum(a.m_ineq); a.m_eq = warp_sum(a.m_eq);
-}
-
-template <int G>
-__global__ void __maxnreg__(G <= 2 ? 144 : 168) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, const int* slot_of, int B, double uprev_dt, int* n_active)
-{
-    __shared__ EvalAcc s_acc[MAX_GROUP_WARPS];
-    __shared__ double s_mu;
-    __shared__ int s_fin;
-    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    double* W = ws + (int64_t)inst * L.stride;
-    const int N = L.N;
-    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;  // finished instance: exact no-op (uniform over the CTA)
-    const int slot = slot_of[inst];
-    double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
-    EvalAcc a;
-    evalacc_init(a);
-    for (int k = tid; k < N; k += blockDim.x) eval_stage(c, L, W, Kb, uprev_dt, k, a);
-    evalacc_warp_reduce(a);
-    if (lane == 0) s_acc[wid] = a;
-    __syncthreads();
-    if (tid == 0)
-    {
-        for (int w = 1; w < nw; ++w) evalacc_merge(a, s_acc[w]);
-        int fin = 0;
-        s_mu = eval_finish(c, L, W, a, true, &fin);
-        s_fin = fin;
-        if (!fin && n_active) atomicAdd(n_active, 1);
-    }
-    __syncthreads();
-    if (s_fin) return;
-    const double mu = s_mu;
-    for (int k = tid; k < N; k += blockDim.x) eval_finalize_stage(L, W, Kb, k, mu);
-}
-
-// ---- kernel: PHASE_KKT -- Riccati factorisation + solve, ONE LANE PER INSTANCE ------------------------------------
-// One warp per 32-instance tile.  The stage records (backward sweep) and the gains + dynamics (forward sweep) of a tile
-// are contiguous 10.5 KB / 10.5-16 KB blocks, so they are streamed through a KKT_RING-deep shared-memory ring with
-// 1-D bulk-async copies (cp.async.bulk, the TMA engine) completing on mbarriers: the lanes read their words from
-// shared memory (conflict-free, 8 B per lane) and never stall on a global load.  Lanes whose instance is finished (or
-// beyond B) idle through the sweeps.
-#define KKT_RING 4
-struct StepOut
-{
-    double* W; int oSTEP; int N;
-    __device__ void operator()(int k, int c, double v) const { W[oSTEP + c * N + k] = v; }
-};
-
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
@@ -333,6 +276,101 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+
+
+// ---- instance image: the leading part of an instance's workspace staged in shared memory ---------------------------
+// The eval / line-search kernels walk long chains of dependent loads (row slots -> obstacle indices -> obstacle
+// parameters ...); out of L2 every link costs ~600 cycles.  One elected thread therefore pulls the image -- scalars,
+// inputs, iterate, (step,) obstacles: 20-30 KB, contiguous by construction of the layout (mpc_layout.h) -- into
+// shared memory with two or three bulk-async (TMA) copies, and the stage functions read it from there.
+// Layout of the dynamic shared memory: [0,8) mbarrier, [16, 16 + 8*img_words) image.
+struct ImageCopy { int step_src; };  // -1: no step (eval); else offset of the step to place at L.oSTEP (line search)
+__device__ __forceinline__ double* load_image(unsigned char* smem, const WsLayout& L, const double* Gp, int img_words, int step_src, int tid)
+{
+    double* img = reinterpret_cast<double*>(smem + 16);
+    const uint32_t bar = smem_addr(smem), dst = smem_addr(img);
+    if (tid == 0)
+    {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        // scalars of this instance may have been written by this thread a moment ago (generic proxy): order them first
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const uint32_t bytes_a = (uint32_t)L.oSTEP * 8u, bytes_c = (uint32_t)(img_words - L.oOTYPE) * 8u;
+        const uint32_t bytes_b = step_src >= 0 ? (uint32_t)(8 * L.N) * 8u : 0u;
+        mbar_expect_tx(bar, bytes_a + bytes_b + bytes_c);
+        bulk_g2s(dst, Gp, bytes_a, bar);
+        if (step_src >= 0) bulk_g2s(dst + (uint32_t)L.oSTEP * 8u, Gp + step_src, bytes_b, bar);
+        bulk_g2s(dst + (uint32_t)L.oOTYPE * 8u, Gp + L.oOTYPE, bytes_c, bar);
+    }
+    mbar_wait(bar, 0);
+    return img;
+}
+
+// ---- kernel: PHASE_EVAL -----------------------------------------------------------------------------------
+// ONE CTA PER INSTANCE, one lane per horizon stage: ceil(N/32) warps (at most MAX_GROUP_WARPS, then the stage loop
+// wraps).  Splitting an instance over several warps halves the dependent instruction stream each warp walks through --
+// at BASELINE batch sizes every kernel of the IPM iteration is latency- not throughput-bound.
+__device__ __forceinline__ void evalacc_warp_reduce(EvalAcc& a)
+{
+    a.dual_inf = warp_max(a.dual_inf); a.prim_inf = warp_max(a.prim_inf);
+    a.sl_max = warp_max(a.sl_max); a.sl_min = warp_min(a.sl_min);
+    a.sum_nu = warp_sum(a.sum_nu); a.sum_lam = warp_sum(a.sum_lam); a.inf1 = warp_sum(a.inf1); a.blog = warp_sum(a.blog);
+    a.gt0 = warp_sum(a.gt0); a.gt1 = warp_sum(a.gt1); a.gldt = warp_sum(a.gldt); a.htt = warp_sum(a.htt);
+    a.obj = warp_sum(a.obj); a.m_ineq = warp_sum(a.m_ineq); a.m_eq = warp_sum(a.m_eq);
+}
+
+template <int NW>
+__global__ void __maxnreg__(NW <= 2 ? 144 : 168) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, const int* slot_of, int B, double uprev_dt, int* n_active,
+                                                             int img_words)
+{
+    extern __shared__ __align__(128) unsigned char img_smem[];
+    __shared__ EvalAcc s_acc[MAX_GROUP_WARPS];
+    __shared__ double s_mu;
+    __shared__ int s_fin;
+    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    double* Gp = ws + (int64_t)inst * L.stride;
+    const int N = L.N;
+    if (Gp[L.oSCAL + MPCB200_SC_STATUS] >= 0.0) return;  // finished instance: exact no-op (uniform over the CTA)
+    double* W = load_image(img_smem, L, Gp, img_words, -1, tid);
+    const int slot = slot_of[inst];
+    double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
+    EvalAcc a;
+    evalacc_init(a);
+    for (int k = tid; k < N; k += blockDim.x) eval_stage(c, L, W, Gp, Kb, uprev_dt, k, a);
+    evalacc_warp_reduce(a);
+    if (lane == 0) s_acc[wid] = a;
+    __syncthreads();
+    if (tid == 0)
+    {
+        for (int w = 1; w < nw; ++w) evalacc_merge(a, s_acc[w]);
+        int fin = 0;
+        s_mu = eval_finish(c, L, Gp, a, true, &fin);
+        s_fin = fin;
+        if (!fin && n_active) atomicAdd(n_active, 1);
+    }
+    __syncthreads();
+    if (s_fin) return;
+    const double mu = s_mu;
+    for (int k = tid; k < N; k += blockDim.x) eval_finalize_stage(L, W, Kb, k, mu);
+}
+
+// ---- kernel: PHASE_KKT -- Riccati factorisation + solve, ONE LANE PER INSTANCE ------------------------------------
+// One warp per 32-instance tile.  The stage records (backward sweep) and the gains + dynamics (forward sweep) of a tile
+// are contiguous 10.5 KB / 10.5-16 KB blocks, so they are streamed through a KKT_RING-deep shared-memory ring with
+// 1-D bulk-async copies (cp.async.bulk, the TMA engine) completing on mbarriers: the lanes read their words from
+// shared memory (conflict-free, 8 B per lane) and never stall on a global load.  Lanes whose instance is finished (or
+// beyond B) idle through the sweeps.
+#define KKT_RING 4
+struct StepOut
+{
+    double* W; int oSTEP; int N;
+    __device__ void operator()(int k, int c, double v) const { W[oSTEP + c * N + k] = v; }
+};
 
 struct SmemView
 {
@@ -503,15 +541,18 @@ struct LsShared
     int accept;
 };
 
+#define GSC(i_) Gp[L.oSCAL + (i_)]
 __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt,
-                                                                             int spec)
+                                                                             int spec, int img_words)
 {
+    extern __shared__ __align__(128) unsigned char img_smem[];
     __shared__ LsShared sh;
     __shared__ int s_win;
     const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    double* W = ws + (int64_t)inst * L.stride;
+    double* Gp = ws + (int64_t)inst * L.stride;
     const int N = L.N;
-    if (ASC(MPCB200_SC_STATUS) >= 0.0) return;
+    if (GSC(MPCB200_SC_STATUS) >= 0.0) return;
+    int step_src = L.oSTEP;
     if (spec)
     {
         // the KKT phase ran attempts 0 and 1 of the regularisation schedule side by side: pick the winner
@@ -520,37 +561,38 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg
         {
             int nreg = 0;
             double dnext = 0.0;
-            const double d0 = ASC(MPCB200_SC_DELTA), d1 = ASC(MPCB200_SC_DELTA1);
-            const int win = kkt_resolve(ASC(MPCB200_SC_KKT_OK0) != 0.0, ASC(MPCB200_SC_KKT_OK1) != 0.0, d0, d1, ASC(MPCB200_SC_DELTA_LAST), &nreg, &dnext);
-            ASC(MPCB200_SC_NREG) += (double)nreg;
-            if (win == -2) ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;
-            else if (win == -1) { ASC(MPCB200_SC_DELTA_LAST) = 3.0 * dnext; ASC(MPCB200_SC_DEFER) = 1.0; }
+            const double d0 = GSC(MPCB200_SC_DELTA), d1 = GSC(MPCB200_SC_DELTA1);
+            const int win = kkt_resolve(GSC(MPCB200_SC_KKT_OK0) != 0.0, GSC(MPCB200_SC_KKT_OK1) != 0.0, d0, d1, GSC(MPCB200_SC_DELTA_LAST), &nreg, &dnext);
+            GSC(MPCB200_SC_NREG) += (double)nreg;
+            if (win == -2) GSC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;
+            else if (win == -1) { GSC(MPCB200_SC_DELTA_LAST) = 3.0 * dnext; GSC(MPCB200_SC_DEFER) = 1.0; }
             else
             {
                 const double dw = win ? d1 : d0;
-                ASC(MPCB200_SC_DEFER) = 0.0;
-                if (win) ASC(MPCB200_SC_DDT) = ASC(MPCB200_SC_DDT1);
-                ASC(MPCB200_SC_DELTA) = dw;
-                ASC(MPCB200_SC_DELTA_LAST) = dw;
+                GSC(MPCB200_SC_DEFER) = 0.0;
+                if (win) GSC(MPCB200_SC_DDT) = GSC(MPCB200_SC_DDT1);
+                GSC(MPCB200_SC_DELTA) = dw;
+                GSC(MPCB200_SC_DELTA_LAST) = dw;
             }
             s_win = win;
         }
         __syncthreads();
         if (s_win == -2) return;
-        if (s_win == 1) L.oSTEP = L.oSTEP2;
+        if (s_win == 1) step_src = L.oSTEP2;
     }
-    if (ASC(MPCB200_SC_DEFER) != 0.0)
+    if (GSC(MPCB200_SC_DEFER) != 0.0)
     {
         // the KKT phase spent its factorisation budget: null step
         __syncthreads();
-        if (tid == 0) { ASC(MPCB200_SC_DEFER) = 0.0; ASC(MPCB200_SC_ITER) += 1.0; ASC(MPCB200_SC_ALPHA) = 0.0; }
+        if (tid == 0) { GSC(MPCB200_SC_DEFER) = 0.0; GSC(MPCB200_SC_ITER) += 1.0; GSC(MPCB200_SC_ALPHA) = 0.0; }
         return;
     }
+    double* W = load_image(img_smem, L, Gp, img_words, step_src, tid);  // image incl. the winning step at L.oSTEP
     const int slot = slot_of[inst];
     const double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
     LsAcc a;
     lsacc_init(a);
-    for (int k = tid; k < N; k += blockDim.x) ls_stage_steps(c, L, W, Kb, uprev_dt, k, a);
+    for (int k = tid; k < N; k += blockDim.x) ls_stage_steps(c, L, W, Gp, Kb, uprev_dt, k, a);
     a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
     a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
     if (lane == 0) sh.acc[wid] = a;
@@ -585,7 +627,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg
     {
         TrialAcc t;
         t.obj = t.inf1 = t.blog = 0.0;
-        for (int k = tid; k < N; k += blockDim.x) ls_stage_trial(c, L, W, uprev_dt, k, alpha, t);
+        for (int k = tid; k < N; k += blockDim.x) ls_stage_trial(c, L, W, Gp, uprev_dt, k, alpha, t);
         t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
         if (lane == 0) sh.tr[wid] = t;
         __syncthreads();
@@ -605,18 +647,17 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg
     if (tid == 0) sh.a_dual = a_d > alpha ? alpha : a_d;
     __syncthreads();
     const double a_dual = sh.a_dual;
-    for (int k = tid; k < N; k += blockDim.x) ls_stage_update(c, L, W, uprev_dt, k, alpha, a_dual);
-    __syncthreads();
+    for (int k = tid; k < N; k += blockDim.x) ls_stage_update(c, L, W, Gp, uprev_dt, k, alpha, a_dual);
     if (tid == 0)
     {
-        if (c.variable_dt) ASC(MPCB200_SC_DT) = ASC(MPCB200_SC_DT) + alpha * ASC(MPCB200_SC_DDT);
-        ASC(MPCB200_SC_ALPHA) = alpha;
-        ASC(MPCB200_SC_RHO) = rho;
-        ASC(MPCB200_SC_ITER) += 1.0;
-        ASC(MPCB200_SC_NBT) += (double)nbt;
+        if (c.variable_dt) GSC(MPCB200_SC_DT) = ASC(MPCB200_SC_DT) + alpha * ASC(MPCB200_SC_DDT);
+        GSC(MPCB200_SC_ALPHA) = alpha;
+        GSC(MPCB200_SC_RHO) = rho;
+        GSC(MPCB200_SC_ITER) = ASC(MPCB200_SC_ITER) + 1.0;
+        GSC(MPCB200_SC_NBT) = ASC(MPCB200_SC_NBT) + (double)nbt;
         const double tiny = alpha < TINY_STEP ? ASC(MPCB200_SC_TINY) + 1.0 : 0.0;
-        ASC(MPCB200_SC_TINY) = tiny;
-        if (tiny >= (double)TINY_STEP_COUNT) ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;  /* jammed: give up */
+        GSC(MPCB200_SC_TINY) = tiny;
+        if (tiny >= (double)TINY_STEP_COUNT) GSC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;  /* jammed: give up */
     }
 }
 
@@ -804,6 +845,11 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8));
     CKC(cudaMalloc(&h->d_slot_of, B * 4)); CKC(cudaMalloc(&h->d_inst_of_slot, ((B + TILE - 1) / TILE) * TILE * 4));
     CKC(cudaMalloc(&h->d_counters, 16)); CKC(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
+    CKC(cudaFuncSetAttribute(eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
     CKC(cudaFuncSetAttribute(kkt_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<true>()));
     CKC(cudaFuncSetAttribute(kkt_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<false>()));
     CKC(cudaMallocHost(&h->h_nactive, 8));
@@ -877,6 +923,11 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
     const int gw = (h->cfg.n + 31) / 32;
     const int group_threads = 32 * (gw < MAX_GROUP_WARPS ? gw : MAX_GROUP_WARPS);
     const int spec = h->spec;
+    // instance image staged in shared memory by the eval / line-search kernels: everything up to the obstacles in use
+    const int m_used = h->has_obst ? ((h->obst_max + 1) & ~1) : 0;
+    const int img_words = h->L.oOBST + MPCB200_OBST_STRIDE * m_used;
+    const size_t img_smem = 16 + (size_t)img_words * 8;
+    if (img_smem > MAX_IMG_SMEM) return set_err(h, MPCB200_E_UNSUPPORTED, "horizon too long: the instance image does not fit in shared memory");
     if (timed && ev_begin(h, phase)) return set_err(h, MPCB200_E_CUDA, "cudaEventCreate failed");
     switch (phase)
     {
@@ -885,10 +936,10 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
         case MPCB200_PHASE_EVAL:
             switch (group_threads >> 5)
             {
-                case 1: eval_kernel<1><<<B, 32, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
-                case 2: eval_kernel<2><<<B, 64, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
-                case 3: eval_kernel<3><<<B, 96, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
-                default: eval_kernel<4><<<B, 128, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr); break;
+                case 1: eval_kernel<1><<<B, 32, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
+                case 2: eval_kernel<2><<<B, 64, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
+                case 3: eval_kernel<3><<<B, 96, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
+                default: eval_kernel<4><<<B, 128, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
             }
             break;
         case MPCB200_PHASE_KKT:
@@ -900,7 +951,7 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
             else kkt_lane_kernel<false><<<kgrid, 32, kkt_smem_bytes<false>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->ric_attempt_stride, h->d_inst_of_slot, B, spec, h->d_counters);
             break;
         }
-        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<B, group_threads, 0, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec); break;
+        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<B, group_threads, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec, img_words); break;
         default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
     }
     if (timed) ev_end(h);

@@ -165,7 +165,7 @@ int emu_eval(const Cfg* cp, double* W, double uprev_dt)
     for (int l = 0; l < 32; ++l)
     {
         evalacc_init(a[l]);
-        for (int k = l; k < N; k += 32) eval_stage(c, L, W, emu_kb(L, W), uprev_dt, k, a[l]);
+        for (int k = l; k < N; k += 32) eval_stage(c, L, W, W, emu_kb(L, W), uprev_dt, k, a[l]);
     }
     reduce_eval(a);
     int fin = 0;
@@ -224,7 +224,7 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
     {
         LsAcc t;
         lsacc_init(t);
-        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, emu_kb(L, W), uprev_dt, k, t);
+        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, W, emu_kb(L, W), uprev_dt, k, t);
         a.a_p = fmin(a.a_p, t.a_p); a.a_d = fmin(a.a_d, t.a_d);
         a.dphi_bar += t.dphi_bar; a.curv += t.curv; a.dJ += t.dJ;
     }
@@ -247,14 +247,14 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
     {
         TrialAcc t;
         t.obj = t.inf1 = t.blog = 0.0;
-        for (int k = 0; k < N; ++k) ls_stage_trial(c, L, W, uprev_dt, k, alpha, t);
+        for (int k = 0; k < N; ++k) ls_stage_trial(c, L, W, W, uprev_dt, k, alpha, t);
         const double phi = t.obj - mu * t.blog + rho * t.inf1;
         if (phi <= phi0 + ARMIJO * alpha * dphi || (bt > 0 && fabs(phi - phi0) <= 1e-13 * (1.0 + fabs(phi0)))) break;
         alpha *= 0.5;
         ++nbt;
     }
     const double a_dual = a.a_d > alpha ? alpha : a.a_d;
-    for (int k = 0; k < N; ++k) ls_stage_update(c, L, W, uprev_dt, k, alpha, a_dual);
+    for (int k = 0; k < N; ++k) ls_stage_update(c, L, W, W, uprev_dt, k, alpha, a_dual);
     if (c.variable_dt) ASC(MPCB200_SC_DT) = dt + alpha * ddt;
     ASC(MPCB200_SC_ALPHA) = alpha;
     ASC(MPCB200_SC_RHO) = rho;
