@@ -264,6 +264,11 @@ int mpcb200_set_timing(mpcb200_handle* h, unsigned phase_mask);
 /* Run all work of this handle on the caller's CUDA stream (a cudaStream_t; NULL restores the handle's own stream), e.g. the
    stream the NCCL all-gather of the optimal controls is enqueued on.  The previous stream is drained first. */
 int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
+/* Execution options (never change results).  MPCB200_OPT_KKT_ATTEMPTS: how the (at most two) regularisation attempts of
+   an IPM iteration are run -- 0 = automatic (side by side when the batch leaves SMs idle, i.e. 2*ceil(B/32) <= #SMs),
+   1 = one after the other inside the KKT kernel, 2 = always side by side. */
+#define MPCB200_OPT_KKT_ATTEMPTS 1
+int mpcb200_set_option(mpcb200_handle* h, int option, int value);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */
 typedef struct mpcb200_stats {

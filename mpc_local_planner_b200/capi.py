@@ -28,6 +28,7 @@ STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NUMERICAL_ERROR, STATUS_INVALID_INPUT 
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5
 F_X, F_U, F_NU, F_S, F_LAM, F_KKT, F_STEP, F_SCAL, F_OBSIDX = range(9)
 PHASE_INIT, PHASE_ASSOCIATE, PHASE_EVAL, PHASE_KKT, PHASE_LINESEARCH = range(5)
+OPT_KKT_ATTEMPTS = 1
 NUM_PHASES = 5
 K_H, K_G, K_A, K_B, K_E, K_C, K_HB, K_D = 0, 15, 20, 23, 29, 32, 34, 39
 (SC_DT, SC_MU, SC_RHO, SC_DELTA, SC_HTT, SC_GT, SC_DDT, SC_ERR0, SC_ERRMU, SC_ITER, SC_STATUS, SC_ALPHA, SC_OBJ,
@@ -160,7 +161,7 @@ EXPORTS = [
     "mpcb200_default_config", "mpcb200_create", "mpcb200_step_batch", "mpcb200_reset", "mpcb200_destroy",
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
-    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
+    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
 ]
 
 
@@ -201,6 +202,7 @@ def load_library(path=None):
     lib.mpcb200_time_phase.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     lib.mpcb200_set_timing.argtypes = [vp, C.c_uint]
     lib.mpcb200_set_stream.argtypes = [vp, vp]
+    lib.mpcb200_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.mpcb200_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.mpcb200_stats_reset.argtypes = [vp]
     if path == LIB_PATH:
@@ -334,6 +336,9 @@ class BatchSolver:
     def set_stream(self, cuda_stream):
         """Run on the caller's CUDA stream (an integer cudaStream_t, e.g. torch.cuda.Stream().cuda_stream); 0 restores."""
         self._check(self.lib.mpcb200_set_stream(self.h, C.c_void_p(int(cuda_stream) if cuda_stream else None)), "mpcb200_set_stream")
+
+    def set_option(self, option, value):
+        self._check(self.lib.mpcb200_set_option(self.h, option, value), "mpcb200_set_option")
 
     def set_timing(self, phase_mask):
         """Phases bracketed by CUDA events inside a solve (bit p = phase p); default KKT only, 0x1f = all."""

@@ -325,7 +325,8 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
 #pragma unroll
     for (int i = 0; i < 15; ++i) AKKT(MPCB200_K_H + i, k) = H[i];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { AKKT(MPCB200_K_G + i, k) = g0[i]; ASTEP(i, k) = g1[i]; AKKT(MPCB200_K_HB + i, k) = hb[i]; }
+    for (int i = 0; i < 5; ++i) { ADS(i, k) = g0[i]; ASTEP(i, k) = g1[i]; AKKT(MPCB200_K_HB + i, k) = hb[i]; }  // g = g0 + mu g1 is stored by eval_finalize_stage
+    // (g0, g1 wait in the image -- DS / STEP are free during the evaluation -- so that the record is written exactly once)
 #pragma unroll
     for (int i = 0; i < 3; ++i) { AKKT(MPCB200_K_A + i, k) = a3[i]; AKKT(MPCB200_K_E + i, k) = e[i]; AKKT(MPCB200_K_D + i, k) = dvec[i]; }
 #pragma unroll
@@ -380,7 +381,7 @@ HD inline void eval_finalize_stage(const WsLayout& L, double* W, double* Kb, int
 {
     const int N = L.N;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) AKKT(MPCB200_K_G + i, k) += mu * ASTEP(i, k);
+    for (int i = 0; i < 5; ++i) AKKT(MPCB200_K_G + i, k) = ADS(i, k) + mu * ASTEP(i, k);
 }
 
 // ------------------------------------------------------------------------------------------------------

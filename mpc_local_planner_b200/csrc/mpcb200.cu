@@ -24,6 +24,7 @@
 
 #define FULLMASK 0xffffffffu
 #define WARPS_PER_CTA 4
+#define REGROUP_EVERY 4    // IPM iterations between two re-assignments of instances to KKT tile slots
 #define MAX_IMG_SMEM (227 * 1024 - 2048)  // dynamic shared memory the eval / line-search kernels may request
 #define MAX_GROUP_WARPS 4   // warps of the CTA that owns one instance in the eval / line-search kernels (lane per stage)
 
@@ -721,6 +722,7 @@ struct mpcb200_handle
     double *kkt_tiles, *ric_tiles;
     size_t ric_attempt_stride;  // doubles between the gain tiles of KKT attempt 0 and 1 (speculative mode)
     int num_sms;
+    int spec_mode;              // MPCB200_OPT_KKT_ATTEMPTS: 0 auto, 1 serial, 2 side by side
     int spec;                   // this solve runs the two KKT attempts of an iteration side by side (small batches)
     unsigned timing_mask;       // phases bracketed by CUDA events inside solve (bit = phase id); default: KKT only
     cudaStream_t stream, own_stream;  // stream in use / the stream the handle created
@@ -832,7 +834,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
         CKC(cudaMalloc(&h->ric_tiles, 2 * h->ric_attempt_stride * sizeof(double)));
         CKC(cudaMemsetAsync(h->kkt_tiles, 0, ntiles * N * KW * TILE * sizeof(double), h->stream));
         CKC(cudaMemsetAsync(h->ric_tiles, 0, 2 * h->ric_attempt_stride * sizeof(double), h->stream));
-        h->spec = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT;
+        h->spec = 0; h->spec_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT;
         CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     }
     CKC(cudaMalloc(&h->d_x0, B * 3 * 8)); CKC(cudaMalloc(&h->d_xf, B * 3 * 8)); CKC(cudaMalloc(&h->d_uprev, B * 2 * 8));
@@ -1045,7 +1047,7 @@ static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_
     const unsigned tm = h->timing_mask;
     auto timed = [&](int phase) { return ((tm >> phase) & 1u) != 0; };
     // small batches leave most SMs idle in the KKT phase: run both regularisation attempts of an iteration side by side
-    h->spec = (2 * ((B + TILE - 1) / TILE) <= h->num_sms) ? 1 : 0;
+    h->spec = h->spec_mode == 0 ? ((2 * ((B + TILE - 1) / TILE) <= h->num_sms) ? 1 : 0) : (h->spec_mode == 2 ? 1 : 0);
     int rc = launch_phase(h, MPCB200_PHASE_INIT, B, force_cold, 0, timed(MPCB200_PHASE_INIT));
     if (rc) return rc;
     const int outer = h->cfg.outer_iterations > 0 ? h->cfg.outer_iterations : 1;
@@ -1063,7 +1065,7 @@ static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_
             const bool poll = (it % POLL == POLL - 1) || it == h->cfg.max_iter;
             const int slot = (it / POLL) & 1;
             if (poll) CK(cudaMemsetAsync(h->d_nactive + slot, 0, 4, h->stream));
-            if ((rc = launch_regroup(h, B))) return rc;
+            if (it % REGROUP_EVERY == 0 && (rc = launch_regroup(h, B))) return rc;  // slots stay valid in between (finished lanes idle)
             if ((rc = launch_phase_eval(h, B, poll ? h->d_nactive + slot : nullptr, timed(MPCB200_PHASE_EVAL)))) return rc;
             if (poll)
             {
@@ -1268,6 +1270,13 @@ extern "C" int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream)
     CK(cudaStreamSynchronize(h->stream));
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     return 0;
+}
+
+extern "C" int mpcb200_set_option(mpcb200_handle* h, int option, int value)
+{
+    if (!h) return MPCB200_E_INVALID;
+    if (option == MPCB200_OPT_KKT_ATTEMPTS && value >= 0 && value <= 2) { h->spec_mode = value; return 0; }
+    return set_err(h, MPCB200_E_INVALID, "unknown option or value");
 }
 
 extern "C" int mpcb200_set_timing(mpcb200_handle* h, unsigned phase_mask)

@@ -229,3 +229,23 @@ def test_golden_g1_and_cfg2(cuda_lib):
         assert out["status"][b] == 0
         assert np.abs(out["u_seq"][b][:-1] - np.array(r["U"])).max() < 2e-4
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cid,B", [(2, 96), (3, 40)])
+def test_kkt_attempt_scheduling_does_not_change_results(cuda_lib, cid, B):
+    """Running the two regularisation attempts of an iteration side by side (small batches) or one after the other is
+    an execution choice only: statuses, iteration counts and controls are identical."""
+    cfg = configs.config_for(cid, tol=1e-8)
+    data = _data(cid, B)
+    outs = []
+    for mode in (1, 2):
+        s = _solver(cfg, B)
+        s.set_option(capi.OPT_KKT_ATTEMPTS, mode)
+        outs.append(s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"]))
+        s.close()
+    a, b = outs
+    np.testing.assert_array_equal(a["status"], b["status"])
+    np.testing.assert_array_equal(a["iters"], b["iters"])
+    np.testing.assert_array_equal(a["u_seq"], b["u_seq"])
+    np.testing.assert_array_equal(a["dt"], b["dt"])
