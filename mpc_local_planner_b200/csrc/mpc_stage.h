@@ -737,10 +737,27 @@ HD inline void associate_stage(const Cfg& c, const WsLayout& L, double* W, int k
     }
 }
 
-// initial-guess repair of stage k: push the pose out of violated obstacle rows
+// initial-guess repair, step 1, stage k: push the pose out of violated obstacle rows, one row after the other.
+// Leaves the pose before the repair in STEP(0..1,k) and the largest remaining row value in STEP(2,k) for step 2.
+HD inline double stage_max_obstacle_row(const Cfg& c, const WsLayout& L, const double* W, int k, double px, double py)
+{
+    const int N = L.N, K = L.K;
+    double m = -1e300;
+    for (int j = 0; j < K; ++j)
+    {
+        const int oi = (int)AOBS(j, k);
+        if (oi < 0) continue;
+        const double dist = footprint_distance<false, false>(c, px, py, AX(2, k), (int)W[L.oOTYPE + oi], W + L.oOBST + oi * MPCB200_OBST_STRIDE,
+                                                             nullptr, nullptr);
+        const double g = c.min_obstacle_dist - dist;
+        if (g > m) m = g;
+    }
+    return m;
+}
 HD inline void project_stage(const Cfg& c, const WsLayout& L, double* W, int k)
 {
     const int N = L.N, K = L.K;
+    ASTEP(0, k) = AX(0, k); ASTEP(1, k) = AX(1, k); ASTEP(2, k) = -1e300;
     if (k < 1 || k > N - 2) return;
     for (int sweep = 0; sweep < PROJ_SWEEPS; ++sweep)
     {
@@ -763,6 +780,61 @@ HD inline void project_stage(const Cfg& c, const WsLayout& L, double* W, int k)
             moved = 1;
         }
         if (!moved) break;
+    }
+    ASTEP(2, k) = stage_max_obstacle_row(c, L, W, k, AX(0, k), AX(1, k));
+}
+// Step 2 (stages in order): a pose that is still pinched between obstacles after step 1 is moved sideways -- along the
+// normal (nx, ny) of the start -> goal line, in LAT_STEP increments up to +-LAT_MAX_STEPS -- to the clear position whose
+// lateral offset is closest to the one of the previous stage (keeps the guess on one side of an obstacle).
+// lateral_candidate: cost of candidate m for stage k (1e300 = not clear).
+#define LAT_STEP 0.1
+#define LAT_MAX_STEPS 25
+HD inline void lateral_normal(const WsLayout& L, const double* W, double* nx, double* ny)
+{
+    const int N = L.N;
+    double ax = -(ASTEP(1, N - 1) - ASTEP(1, 0)), ay = ASTEP(0, N - 1) - ASTEP(0, 0);
+    const double nn = sqrt(ax * ax + ay * ay);
+    if (nn < 1e-12) { ax = 0.0; ay = 1.0; } else { ax /= nn; ay /= nn; }
+    *nx = ax; *ny = ay;
+}
+HD inline bool lateral_needed(const WsLayout& L, const double* W, int k) { const int N = L.N; return ASTEP(2, k) > -0.5 * PROJ_MARGIN; }
+HD inline double lateral_offset(const WsLayout& L, const double* W, int k, double nx, double ny)
+{
+    const int N = L.N;
+    return (AX(0, k) - ASTEP(0, k)) * nx + (AX(1, k) - ASTEP(1, k)) * ny;
+}
+HD inline double lateral_candidate(const Cfg& c, const WsLayout& L, const double* W, int k, int m, double o_prev, double nx, double ny)
+{
+    const int N = L.N;
+    const double o = LAT_STEP * (double)m;
+    if (stage_max_obstacle_row(c, L, W, k, ASTEP(0, k) + o * nx, ASTEP(1, k) + o * ny) > -PROJ_MARGIN) return 1e300;
+    return fabs(o - o_prev) + 1e-3 * fabs(o);
+}
+HD inline void lateral_apply(const WsLayout& L, double* W, int k, int m, bool found, double nx, double ny)
+{
+    const int N = L.N;
+    const double o = found ? LAT_STEP * (double)m : 0.0;
+    AX(0, k) = ASTEP(0, k) + o * nx;
+    AX(1, k) = ASTEP(1, k) + o * ny;
+}
+// serial form (host emulator; the CUDA kernel spreads the candidates of a stage over the lanes of the warp)
+HD inline void repair_lateral_serial(const Cfg& c, const WsLayout& L, double* W)
+{
+    const int N = L.N;
+    double nx, ny;
+    lateral_normal(L, W, &nx, &ny);
+    for (int k = 1; k <= N - 2; ++k)
+    {
+        if (!lateral_needed(L, W, k)) continue;
+        const double o_prev = lateral_offset(L, W, k - 1, nx, ny);
+        double best = 1e300;
+        int best_m = 0;
+        for (int m = -LAT_MAX_STEPS; m <= LAT_MAX_STEPS; ++m)
+        {
+            const double cost = lateral_candidate(c, L, W, k, m, o_prev, nx, ny);
+            if (cost < best) { best = cost; best_m = m; }
+        }
+        lateral_apply(L, W, k, best_m, best < 1e299, nx, ny);
     }
 }
 

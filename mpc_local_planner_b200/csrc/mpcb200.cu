@@ -163,6 +163,31 @@ __global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double up
     {
         for (int k = lane; k < N; k += 32) project_stage(c, L, W, k);
         __syncwarp();
+        {
+            // step 2 of the repair: stages in order, the lateral candidates of a pinched stage spread over the lanes
+            double nx, ny;
+            lateral_normal(L, W, &nx, &ny);
+            for (int k = 1; k <= N - 2; ++k)
+            {
+                if (!lateral_needed(L, W, k)) continue;  // warp-uniform
+                const double o_prev = lateral_offset(L, W, k - 1, nx, ny);
+                double best = 1e300;
+                int best_m = 0;
+                for (int m = -LAT_MAX_STEPS + lane; m <= LAT_MAX_STEPS; m += 32)
+                {
+                    const double cost = lateral_candidate(c, L, W, k, m, o_prev, nx, ny);
+                    if (cost < best) { best = cost; best_m = m; }
+                }
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    const double oc = __shfl_xor_sync(FULLMASK, best, o);
+                    const int om = __shfl_xor_sync(FULLMASK, best_m, o);
+                    if (oc < best || (oc == best && om < best_m)) { best = oc; best_m = om; }
+                }
+                if (lane == 0) lateral_apply(L, W, k, best_m, best < 1e299, nx, ny);
+                __syncwarp();
+            }
+        }
         for (int k = lane; k < N; k += 32) init_controls_stage(c, L, W, k);
         __syncwarp();
         if (lane == 0) clip_rates_serial(c, L, W, uprev_dt);

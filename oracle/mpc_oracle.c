@@ -684,16 +684,39 @@ void orc_associate(const orc_problem* p, orc_ws* ws)
  * obstacle row (the straight-line guess usually cuts through obstacles) are pushed out along the row's position
  * gradient until the row holds with margin.  Interior-point iterations started from violated nonconvex rows jam
  * (Waechter & Biegler 2000); Ipopt escapes through its restoration phase, we avoid the situation up front.
+ * A pose that stays pinched between obstacles after these sweeps is moved sideways instead: along the normal of the
+ * start -> goal line, in 0.1 m increments up to +-2.5 m, to the clear position whose lateral offset is closest to the one
+ * of the previous stage (so that consecutive poses pass an obstacle on the same side).
  */
 #define ORC_PROJ_MARGIN 0.05
 #define ORC_PROJ_SWEEPS 6
+#define ORC_LAT_STEP 0.1
+#define ORC_LAT_MAX_STEPS 25
 static double row_value(const orc_problem* p, const orc_ws* ws, int k, int slot, const double* X, const double* U,
                         double dt, double* grad8, double* hess6);
+static double stage_max_row(const orc_problem* p, orc_ws* ws, int k)
+{
+    const int N = ws->N;
+    double m = -1e300;
+    for (int sl = 8; sl < 8 + ws->K; ++sl)
+    {
+        if (ws->OBSIDX[IX(sl - 8, k)] < 0.0) continue;
+        double g = row_value(p, ws, k, sl, ws->X, ws->U, 0.0, NULL, NULL);
+        if (g > m) m = g;
+    }
+    return m;
+}
 void orc_project_init(const orc_problem* p, orc_ws* ws)
 {
     const int N = ws->N, K = ws->K;
     const double margin = ORC_PROJ_MARGIN;
+    /* unit normal of the start -> goal line */
+    double nx = -(ws->X[IX(1, N - 1)] - ws->X[IX(1, 0)]), ny = ws->X[IX(0, N - 1)] - ws->X[IX(0, 0)];
+    { double nn = sqrt(nx * nx + ny * ny); if (nn < 1e-12) { nx = 0; ny = 1; } else { nx /= nn; ny /= nn; } }
+    double o_prev = 0.0;
     for (int k = 1; k <= N - 2; ++k)
+    {
+        const double bx = ws->X[IX(0, k)], by = ws->X[IX(1, k)];
         for (int sweep = 0; sweep < ORC_PROJ_SWEEPS; ++sweep)
         {
             int moved = 0;
@@ -712,6 +735,23 @@ void orc_project_init(const orc_problem* p, orc_ws* ws)
             }
             if (!moved) break;
         }
+        if (stage_max_row(p, ws, k) > -0.5 * margin)
+        {
+            /* the sweeps are pinched between obstacles: look sideways for the clear lateral offset closest to the previous stage's */
+            double best = 1e300, best_o = 0.0; int found = 0;
+            for (int m = -ORC_LAT_MAX_STEPS; m <= ORC_LAT_MAX_STEPS; ++m)
+            {
+                const double o = ORC_LAT_STEP * (double)m;
+                ws->X[IX(0, k)] = bx + o * nx; ws->X[IX(1, k)] = by + o * ny;
+                if (stage_max_row(p, ws, k) > -margin) continue;
+                const double cost = fabs(o - o_prev) + 1e-3 * fabs(o);
+                if (cost < best) { best = cost; best_o = o; found = 1; }
+            }
+            if (found) { ws->X[IX(0, k)] = bx + best_o * nx; ws->X[IX(1, k)] = by + best_o * ny; }
+            else { ws->X[IX(0, k)] = bx; ws->X[IX(1, k)] = by; }
+        }
+        o_prev = (ws->X[IX(0, k)] - bx) * nx + (ws->X[IX(1, k)] - by) * ny;
+    }
 }
 
 /*

@@ -135,6 +135,7 @@ void emu_associate(const Cfg* cp, double* W, double uprev_dt, int first_outer)
     if (repair)
     {
         for (int k = 0; k < N; ++k) project_stage(c, L, W, k);
+        repair_lateral_serial(c, L, W);
         for (int k = 0; k < N; ++k) init_controls_stage(c, L, W, k);
         clip_rates_serial(c, L, W, uprev_dt);
     }
