@@ -102,3 +102,25 @@ def test_full_size_batches(cuda_lib, orc, cid, B, n):
         # tol 1e-6 here (BASELINE), so allow the distance two tol-1e-6 solutions of the same problem can have
         assert (du < 1e-3).all() and (du < U_TOL).mean() >= 0.8
     s.close()
+
+
+def test_machine_filling_batch_matches_small_batch(cuda_lib):
+    """A batch large enough to fill the SMs runs the regularisation attempts one after the other inside the KKT kernel
+    (small batches run them side by side): an execution choice only, the first 96 instances come out bit-identical to
+    a 96-instance batch."""
+    cfg = configs.config_for(2, tol=1e-6)
+    base = configs.generate(2, 2048)
+    B = 32768
+    rep = B // 2048
+    tile = lambda a: np.concatenate([a] * rep)
+    big = capi.BatchSolver(cfg, B, device=0)
+    out = big.step(tile(base["x0"]), tile(base["xf"]), tile(base["u_prev"]), base["u_prev_dt"], tuple(tile(a) for a in base["obstacles"]), None)
+    big.close()
+    small = capi.BatchSolver(cfg, 96, device=0)
+    ref = small.step(base["x0"][:96], base["xf"][:96], base["u_prev"][:96], base["u_prev_dt"], tuple(a[:96] for a in base["obstacles"]), None)
+    small.close()
+    np.testing.assert_array_equal(out["status"][:96], ref["status"])
+    np.testing.assert_array_equal(out["iters"][:96], ref["iters"])
+    np.testing.assert_array_equal(out["u_seq"][:96], ref["u_seq"])
+    # and the copies of the 2048 base instances inside the big batch agree with each other
+    np.testing.assert_array_equal(out["u_seq"][:2048], out["u_seq"][2048 * (rep - 1):])
