@@ -1,3 +1,5 @@
+"""Per-iteration profile of a cfg-2 solve driven phase by phase through the C ABI (serial KKT attempts): unfinished instances,
+device time of eval / KKT / line search, regularisation retries and backtracks.  Usage: python tools/iteration_profile.py"""
 import sys; sys.path.insert(0,'.')
 import numpy as np
 from mpc_local_planner_b200 import capi, configs

@@ -1,3 +1,4 @@
+"""Text summary (launch configuration, instruction counts, DRAM bytes, stall reasons) of .ncu-rep files: python tools/ncu_summary.py a.ncu-rep ..."""
 import csv, subprocess, sys, io
 def summary(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

@@ -1,3 +1,4 @@
+"""Two cold solves of cfg 2 (B from argv, default 1024) -- the target of the ncu captures under profiles/."""
 import sys; sys.path.insert(0,'.')
 from mpc_local_planner_b200 import capi, configs
 B=int(sys.argv[1]) if len(sys.argv)>1 else 1024

@@ -1,3 +1,4 @@
+"""Convergence statistics of the CPU oracle on a BASELINE configuration: python tools/oracle_convergence.py <cfg id> <instances>"""
 import sys; sys.path.insert(0,'.')
 import numpy as np, time
 from mpc_local_planner_b200 import configs, capi

@@ -1,3 +1,5 @@
+"""Whole-solve timings of the BASELINE configurations on one GPU: wall / device ms, converged solves/s, per-phase device
+times (one extra solve with every phase bracketed) and the eval / KKT kernels timed alone.  Usage: python tools/solve_timings.py"""
 import sys, time, json; sys.path.insert(0,'.')
 import numpy as np
 from mpc_local_planner_b200 import capi, configs
