@@ -111,5 +111,29 @@ def main():
     json.dump(dict(config_id=2, instances=rows), open(os.path.join(HERE, "slsqp_cfg2.json"), "w"), indent=1)
 
 
+def extra():
+    """python tests/golden/make_golden.py extra -- fixtures for the via-point objective (cfg 4) and the car-like minimum-time
+    problem with the polygon footprint (cfg 3 at N=30, so that SLSQP with numeric Jacobians finishes in minutes)."""
+    for cid, n, fname, want in ((4, None, "slsqp_cfg4.json", 6), (3, 30, "slsqp_cfg3_n30.json", 5)):
+        cfg = configs.config_for(cid, n=n, tol=1e-8)
+        data = configs.generate(cid, 48, n=n)
+        ref = orc.step_batch(cfg, data, n_threads=4)
+        sel = [b for b in range(48) if ref["status"][b] == 0][:want + 3]
+        rows = []
+        for b in sel:
+            t = time.time()
+            r = scipy_solve(cfg, data, b)
+            r["instance"] = b
+            print("cfg%d inst %d f %.6f ceq %.1e cin %.1e nit %d dt %.6f (%.0fs)" % (cid, b, r["f"], r["ceq"], r["cin"], r["nit"], r["dt"], time.time() - t), flush=True)
+            if r["ceq"] < 1e-8 and r["cin"] > -1e-8:
+                rows.append(r)
+            if len(rows) >= want:
+                break
+        json.dump(dict(config_id=cid, n=n, instances=rows), open(os.path.join(HERE, fname), "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        extra()
+    else:
+        main()

@@ -231,6 +231,18 @@ def test_golden_g1_and_cfg2(cuda_lib):
     s.close()
 
 
+def test_golden_cfg4_and_cfg3(cuda_lib):
+    """CUDA path against the scipy fixtures of the via-point objective (cfg 4) and the car-like minimum-time problem (cfg 3, N=30)."""
+    import golden_checks as gc
+    for cid, n, name, check in ((4, None, "slsqp_cfg4.json", gc.check_cfg4), (3, 30, "slsqp_cfg3_n30.json", gc.check_cfg3_n30)):
+        cfg = configs.config_for(cid, n=n, tol=1e-9)
+        data = configs.generate(cid, 48, n=n)
+        s = _solver(cfg, 48)
+        out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
+        check(out, gc.load(name)["instances"])
+        s.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cid,B", [(2, 96), (3, 40)])
 def test_kkt_attempt_scheduling_does_not_change_results(cuda_lib, cid, B):

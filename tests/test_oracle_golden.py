@@ -51,6 +51,18 @@ def test_cfg2_instances_match_scipy(orc):
         assert np.abs(u[:-1] - np.array(r["U"])).max() < U_TOL_SCIPY
 
 
+def test_cfg4_and_cfg3_fixtures(orc):
+    import golden_checks as gc
+    g = gc.load("slsqp_cfg4.json")
+    cfg = configs.config_for(4, tol=1e-9)
+    out = orc.step_batch(cfg, configs.generate(4, 48), n_threads=2)
+    gc.check_cfg4(out, g["instances"])
+    g = gc.load("slsqp_cfg3_n30.json")
+    cfg = configs.config_for(3, n=30, tol=1e-9)
+    out = orc.step_batch(cfg, configs.generate(3, 48, n=30), n_threads=2)
+    gc.check_cfg3_n30(out, g["instances"])
+
+
 def test_converged_solutions_are_feasible_kkt_points(orc):
     """Independent of any solver: at the returned point the reference-form defects vanish, all rows hold, the bounds hold."""
     import ctypes as C
