@@ -1,7 +1,8 @@
-// mpc_stage.h -- per-stage (= per-lane) bodies of the solver phases.  One warp owns one OCP instance; lane l handles
-// the stages k = l, l+32, ...  Each function below is the work of ONE stage; the kernels in mpcb200.cu (and the CPU
-// warp emulator in tests/emu, test infrastructure) loop over a lane's stages and combine the accumulators with warp
-// reductions.  All functions are host/device.
+// mpc_stage.h -- per-stage (= per-lane) bodies of the solver phases.  A group of lanes (a CTA of ceil(N/32) warps in the
+// eval / line-search kernels, one warp in the init kernels) owns one OCP instance and each lane handles the stages
+// k = t, t + group size, ...  Each function below is the work of ONE stage; the kernels in mpcb200.cu (and the CPU
+// warp emulator in tests/emu, test infrastructure) loop over a lane's stages and combine the accumulators with
+// shuffle / shared-memory reductions.  All functions are host/device.
 //
 // Reference structure restated here:
 //   which term attaches to which stage      R/src/optimal_control/finite_differences_grid_se2.cpp:36-152

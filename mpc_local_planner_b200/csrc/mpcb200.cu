@@ -1,11 +1,12 @@
 // mpcb200.cu -- sm_100a kernels + C-ABI host side of the batched receding-horizon OCP solver (include/mpcb200.h).
 //
-// One warp owns one OCP instance.  The instance's working set is one contiguous, 128-byte aligned block in HBM in
-// which every array is laid out [component][stage] (stage fastest): in the stage-parallel phases (EVAL, LINESEARCH,
-// INIT, ASSOCIATE) lane l handles stages l, l+32, ... so that the 32 lanes touch consecutive addresses; in the
-// sequential KKT phase ONE LANE owns one instance (mpc_riccati_lane.h): the condensed KKT stage records and the
-// Riccati gains live in 32-instance interleaved tiles so that the 32 lanes of a warp, sweeping 32 instances in
-// lock-step, touch 256 consecutive bytes per access.
+// Thread mapping.  The stage-parallel phases put one lane on one horizon stage: EVAL and LINESEARCH run one CTA of
+// ceil(N/32) warps per instance and read the instance image (the leading, contiguous part of the instance's
+// workspace block, mpc_layout.h) from shared memory, where a bulk-async copy staged it; INIT and ASSOCIATE (once per
+// solve) run one warp per instance straight on global memory.  Arrays are [component][stage] (stage fastest).
+// In the sequential KKT phase ONE LANE owns one instance (mpc_riccati_lane.h): the condensed KKT stage records and
+// the Riccati gains live in 32-instance interleaved tiles, a warp sweeps 32 instances in lock-step, and each stage of
+// a tile is one contiguous block that a bulk-async copy streams through a shared-memory ring.
 //
 // This file is the ONLY implementation of the hot path: there is no CPU fallback.  Every entry point fails with
 // MPCB200_E_NODEVICE / MPCB200_E_CUDA when no CUDA device is usable.
