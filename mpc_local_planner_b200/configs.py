@@ -173,6 +173,27 @@ def generate(config_id, B, first=0, n=None):
     return dict(x0=x0, xf=xf, u_prev=np.zeros((B, 2)), u_prev_dt=0.2, obstacles=(count, types, params), viapoints=vps)
 
 
+def with_line_obstacles(data, seed=0, every=2):
+    """Variant of a generated batch in which every `every`-th obstacle is a LINE obstacle (a wall segment through the
+    original centre, random direction, half-length radius + 0.25 m) -- exercises the LineObstacle distance of SURVEY App. B.3."""
+    count, types, params = (a.copy() for a in data["obstacles"])
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(SEED_BASE + 77 + seed)))
+    B, M = types.shape
+    for b in range(B):
+        for j in range(0, M, every):
+            c = params[b, j, 0:2].copy()
+            half = params[b, j, 4] + 0.25
+            ang = rng.uniform(0.0, math.pi)
+            d = half * np.array([math.cos(ang), math.sin(ang)])
+            params[b, j, 0:2] = c - d
+            params[b, j, 2:4] = c + d
+            params[b, j, 4] = 0.0
+            types[b, j] = capi.OBST_LINE
+    out = dict(data)
+    out["obstacles"] = (count, types, params)
+    return out
+
+
 def config_for(config_id, n=None, tol=1e-6):
     if config_id == 1:
         return cfg1(tol)

@@ -206,12 +206,13 @@ HD inline double footprint_distance(const Cfg& c, double px, double py, double p
     return footprint_distance_sc<WITH_GRAD, WITH_HESS>(c, px, py, s, co, obst_type, op, grad3, hess6);
 }
 
-// same with the sine / cosine of the heading supplied by the caller (one sincos per stage, shared by all rows)
+// footprint <-> obstacle POINT (wx, wy) (+ obstacle radius r_obst): the point is taken to the robot frame and the closest
+// footprint feature is differentiated through q = R(theta)'(w - p)
 template <bool WITH_GRAD, bool WITH_HESS>
-HD inline double footprint_distance_sc(const Cfg& c, double px, double py, double s, double co, int obst_type, const double* op,
-                                       double* grad3, double* hess6)
+HD inline double footprint_distance_point(const Cfg& c, double px, double py, double s, double co, double wx, double wy, double r_obst,
+                                          double* grad3, double* hess6)
 {
-    const double ox = op[0] - px, oy = op[1] - py;
+    const double ox = wx - px, oy = wy - py;
     const double qx = co * ox + s * oy, qy = -s * ox + co * oy;
     double best = 1e300, bcx = 0, bcy = 0, brho = 0;
     int bvert = 1;
@@ -259,7 +260,6 @@ HD inline double footprint_distance_sc(const Cfg& c, double px, double py, doubl
         double d = rho - rad;
         if (d < best) { best = d; bcx = cx; bcy = cy; brho = rho; bvert = isv; }
     }
-    double r_obst = (obst_type == MPCB200_OBST_CIRCLE) ? op[4] : 0.0;
     double dist = best - r_obst;
     if (WITH_GRAD)
     {
@@ -288,6 +288,135 @@ HD inline double footprint_distance_sc(const Cfg& c, double px, double py, doubl
         }
     }
     return dist;
+}
+
+
+// number of footprint vertices / circle centres and the i-th one in the robot frame (with its radius)
+HD inline int footprint_num_vertices(const Cfg& c)
+{
+    switch (c.footprint_type)
+    {
+        case MPCB200_FOOTPRINT_POINT:
+        case MPCB200_FOOTPRINT_CIRCULAR: return 1;
+        case MPCB200_FOOTPRINT_TWO_CIRCLES:
+        case MPCB200_FOOTPRINT_LINE: return 2;
+        default: return c.n_poly;
+    }
+}
+HD inline void footprint_vertex(const Cfg& c, int i, double* vx, double* vy, double* rad)
+{
+    *rad = 0.0;
+    switch (c.footprint_type)
+    {
+        case MPCB200_FOOTPRINT_POINT: *vx = 0.0; *vy = 0.0; break;
+        case MPCB200_FOOTPRINT_CIRCULAR: *vx = 0.0; *vy = 0.0; *rad = c.footprint_params[0]; break;
+        case MPCB200_FOOTPRINT_TWO_CIRCLES:
+            if (i == 0) { *vx = c.footprint_params[0]; *vy = 0.0; *rad = c.footprint_params[1]; }
+            else { *vx = -c.footprint_params[2]; *vy = 0.0; *rad = c.footprint_params[3]; }
+            break;
+        case MPCB200_FOOTPRINT_LINE: *vx = c.footprint_params[2 * i]; *vy = c.footprint_params[2 * i + 1]; break;
+        default: *vx = c.poly_xy[2 * i]; *vy = c.poly_xy[2 * i + 1];
+    }
+}
+// proper crossing of segments (p1,p2) and (p3,p4) (teb's check_line_segments_intersection_2d: touching counts)
+HD inline bool segments_intersect(double p1x, double p1y, double p2x, double p2y, double p3x, double p3y, double p4x, double p4y)
+{
+    const double d1x = p2x - p1x, d1y = p2y - p1y, d2x = p4x - p3x, d2y = p4y - p3y;
+    const double den = d1x * d2y - d1y * d2x;
+    if (fabs(den) < 1e-14) return false;  // parallel (collinear overlap is left to the endpoint distances: they are 0 then)
+    const double rx = p3x - p1x, ry = p3y - p1y;
+    const double t = (rx * d2y - ry * d2x) / den, u = (rx * d1y - ry * d1x) / den;
+    return t >= 0.0 && t <= 1.0 && u >= 0.0 && u <= 1.0;
+}
+// footprint <-> LINE obstacle (a, b): 0 if an edge of a line / polygon footprint crosses the segment, else the
+// smaller of (i) the footprint's distance to the two end points and (ii) the distance of the footprint's vertices /
+// circle centres to the interior of the segment.
+template <bool WITH_GRAD, bool WITH_HESS>
+HD inline double footprint_distance_line(const Cfg& c, double px, double py, double s, double co, const double* op, double* grad3, double* hess6)
+{
+    const double ax = op[0], ay = op[1], bx = op[2], by = op[3];
+    double ux = bx - ax, uy = by - ay;
+    const double len = sqrt(ux * ux + uy * uy);
+    if (!(len > 1e-12)) return footprint_distance_point<WITH_GRAD, WITH_HESS>(c, px, py, s, co, ax, ay, 0.0, grad3, hess6);
+    ux /= len; uy /= len;
+    const double nx = -uy, ny = ux;
+    const int nv = footprint_num_vertices(c);
+    if (c.footprint_type == MPCB200_FOOTPRINT_LINE || (c.footprint_type == MPCB200_FOOTPRINT_POLYGON && c.n_poly >= 2))
+    {
+        const int ne = (c.footprint_type == MPCB200_FOOTPRINT_LINE || c.n_poly == 2) ? 1 : nv;
+        for (int i = 0; i < ne; ++i)
+        {
+            double v0x, v0y, v1x, v1y, r0;
+            footprint_vertex(c, i, &v0x, &v0y, &r0);
+            footprint_vertex(c, (i + 1) % nv, &v1x, &v1y, &r0);
+            const double w0x = px + co * v0x - s * v0y, w0y = py + s * v0x + co * v0y;
+            const double w1x = px + co * v1x - s * v1y, w1y = py + s * v1x + co * v1y;
+            if (segments_intersect(w0x, w0y, w1x, w1y, ax, ay, bx, by))
+            {
+                if (WITH_GRAD) { grad3[0] = grad3[1] = grad3[2] = 0.0; }
+                if (WITH_HESS) { for (int j = 0; j < 6; ++j) hess6[j] = 0.0; }
+                return 0.0;
+            }
+        }
+    }
+    // (ii) vertices against the interior of the obstacle segment
+    double best = 1e300, bsig = 1.0, bvx = 0.0, bvy = 0.0;
+    for (int i = 0; i < nv; ++i)
+    {
+        double vx, vy, rad;
+        footprint_vertex(c, i, &vx, &vy, &rad);
+        const double wx = px + co * vx - s * vy, wy = py + s * vx + co * vy;
+        const double t = ((wx - ax) * ux + (wy - ay) * uy) / len;
+        if (!(t > 0.0 && t < 1.0)) continue;
+        const double sd = (wx - ax) * nx + (wy - ay) * ny;
+        const double d = fabs(sd) - rad;
+        if (d < best) { best = d; bsig = sd >= 0.0 ? 1.0 : -1.0; bvx = vx; bvy = vy; }
+    }
+    // (i) the two end points as point obstacles
+    double ga[3], ha[6], gb[3], hb[6];
+    const double da = footprint_distance_point<WITH_GRAD, WITH_HESS>(c, px, py, s, co, ax, ay, 0.0, ga, ha);
+    const double db = footprint_distance_point<WITH_GRAD, WITH_HESS>(c, px, py, s, co, bx, by, 0.0, gb, hb);
+    if (da <= best && da <= db)
+    {
+        if (WITH_GRAD) { grad3[0] = ga[0]; grad3[1] = ga[1]; grad3[2] = ga[2]; }
+        if (WITH_HESS) { for (int j = 0; j < 6; ++j) hess6[j] = ha[j]; }
+        return da;
+    }
+    if (db <= best)
+    {
+        if (WITH_GRAD) { grad3[0] = gb[0]; grad3[1] = gb[1]; grad3[2] = gb[2]; }
+        if (WITH_HESS) { for (int j = 0; j < 6; ++j) hess6[j] = hb[j]; }
+        return db;
+    }
+    if (WITH_GRAD)
+    {
+        // d = sigma n.(p + R v - a) - rad:  dR/dtheta v = (-s vx - co vy, co vx - s vy),  d2R/dtheta2 v = -(R v)
+        const double rx = co * bvx - s * bvy, ry = s * bvx + co * bvy;
+        grad3[0] = bsig * nx; grad3[1] = bsig * ny; grad3[2] = bsig * (nx * (-ry) + ny * rx);
+        if (WITH_HESS)
+        {
+            hess6[0] = hess6[1] = hess6[2] = hess6[3] = hess6[4] = 0.0;
+            hess6[5] = -bsig * (nx * rx + ny * ry);
+        }
+    }
+    return best;
+}
+
+// distance footprint(pose) <-> obstacle (point, circle: params x, y, -, -, radius; line: x0, y0, x1, y1) with the sine / cosine of
+// the heading supplied by the caller (one sincos per stage, shared by all rows)
+template <bool WITH_GRAD, bool WITH_HESS>
+HD inline double footprint_distance_sc(const Cfg& c, double px, double py, double s, double co, int obst_type, const double* op,
+                                       double* grad3, double* hess6)
+{
+    if (obst_type == MPCB200_OBST_LINE) return footprint_distance_line<WITH_GRAD, WITH_HESS>(c, px, py, s, co, op, grad3, hess6);
+    return footprint_distance_point<WITH_GRAD, WITH_HESS>(c, px, py, s, co, op[0], op[1], obst_type == MPCB200_OBST_CIRCLE ? op[4] : 0.0, grad3, hess6);
+}
+
+// centroid of an obstacle (teb getCentroid(): point / circle centre, segment midpoint) -- the side test of the association
+HD inline void obstacle_centroid(int obst_type, const double* op, double* cx, double* cy)
+{
+    if (obst_type == MPCB200_OBST_LINE) { *cx = 0.5 * (op[0] + op[2]); *cy = 0.5 * (op[1] + op[3]); }
+    else { *cx = op[0]; *cy = op[1]; }
 }
 
 // ---- config predicates ----

@@ -719,7 +719,9 @@ HD inline void associate_stage(const Cfg& c, const WsLayout& L, double* W, int k
                 if (!(dist < c.force_inclusion_dist))
                 {
                     if (dist > c.cutoff_dist) continue;
-                    if (ox * op[1] - op[0] * oy > 0) { if (dist < left_min) { left_min = dist; left = j; } }
+                    double ccx, ccy;
+                    obstacle_centroid((int)W[L.oOTYPE + j], op, &ccx, &ccy);
+                    if (ox * ccy - ccx * oy > 0) { if (dist < left_min) { left_min = dist; left = j; } }
                     else { if (dist < right_min) { right_min = dist; right = j; } }
                     continue;
                 }

@@ -1030,7 +1030,7 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
         if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
         const size_t M = (size_t)obst->max_per_instance;
         for (size_t i = 0; i < (size_t)B * M; ++i)
-            if (obst->type[i] == MPCB200_OBST_LINE) return set_err(h, MPCB200_E_UNSUPPORTED, "line obstacles are not implemented in this round");
+            if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
         CK(cudaMemcpyAsync(h->d_obst_count, obst->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst_type, obst->type, (size_t)B * M * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst, obst->params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));

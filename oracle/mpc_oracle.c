@@ -249,9 +249,11 @@ static double point_segment(double qx, double qy, const fp_seg* sg, double* cx, 
  * frame, q = R(theta)^T (o - p); dist = min_i (dist(q, seg_i) - rad_i) - r_obst.  Derivatives are those of the
  * active (arg-min) feature; hess6 = (xx, xy, xt, yy, yt, tt).
  */
+static double footprint_distance_line(const mpcb200_config* cfg, const double* pose, const double* op, double* grad3, double* hess6);
 double orc_footprint_distance(const mpcb200_config* cfg, const double* pose, int obst_type, const double* op,
                               double* grad3, double* hess6)
 {
+    if (obst_type == MPCB200_OBST_LINE) return footprint_distance_line(cfg, pose, op, grad3, hess6);
     fp_seg seg[MPCB200_MAX_POLY + 2];
     int ns = footprint_segments(cfg, seg);
     const double c = cos(pose[2]), s = sin(pose[2]);
@@ -298,6 +300,89 @@ double orc_footprint_distance(const mpcb200_config* cfg, const double* pose, int
         }
     }
     return dist;
+}
+
+/* teb check_line_segments_intersection_2d: do (p1,p2) and (p3,p4) cross (touching counts)? */
+static int seg_intersect(const double* p1, const double* p2, const double* p3, const double* p4)
+{
+    const double d1x = p2[0] - p1[0], d1y = p2[1] - p1[1], d2x = p4[0] - p3[0], d2y = p4[1] - p3[1];
+    const double den = d1x * d2y - d1y * d2x;
+    if (fabs(den) < 1e-14) return 0;
+    const double rx = p3[0] - p1[0], ry = p3[1] - p1[1];
+    const double t = (rx * d2y - ry * d2x) / den, u = (rx * d1y - ry * d1x) / den;
+    return t >= 0.0 && t <= 1.0 && u >= 0.0 && u <= 1.0;
+}
+
+/*
+ * calculateDistance(pose, LineObstacle(a,b)), evaluated in the WORLD frame: every footprint feature
+ * (segment or circle centre) is moved to the world, its distance to the obstacle segment follows teb's
+ * distance_segment_to_segment_2d (0 if the segments cross, else the minimum of the four end-point/segment distances),
+ * circles subtract their radius.  Derivatives are those of the active pair: an obstacle end point against the footprint
+ * (then exactly the point-obstacle case) or a footprint vertex against the interior of the obstacle segment
+ * (d = |n.(p + R v - a)| - r, n = unit normal of the segment).
+ */
+static double footprint_distance_line(const mpcb200_config* cfg, const double* pose, const double* op, double* grad3, double* hess6)
+{
+    const double a[2] = {op[0], op[1]}, b[2] = {op[2], op[3]};
+    double ux = b[0] - a[0], uy = b[1] - a[1];
+    const double len = sqrt(ux * ux + uy * uy);
+    if (!(len > 1e-12)) return orc_footprint_distance(cfg, pose, MPCB200_OBST_POINT, op, grad3, hess6);
+    ux /= len; uy /= len;
+    fp_seg seg[MPCB200_MAX_POLY + 2];
+    const int ns = footprint_segments(cfg, seg);
+    const double c = cos(pose[2]), s = sin(pose[2]);
+    double best = 1e300;
+    int kind = 0;               /* 1: obstacle end point a, 2: end point b, 3: footprint vertex vs segment interior */
+    double bv[2] = {0, 0}, bsig = 1.0;
+    for (int i = 0; i < ns; ++i)
+    {
+        /* footprint feature in the world */
+        const double fr[2][2] = {{seg[i].ax, seg[i].ay}, {seg[i].bx, seg[i].by}};
+        double fw[2][2];
+        for (int e = 0; e < 2; ++e)
+        {
+            fw[e][0] = pose[0] + c * fr[e][0] - s * fr[e][1];
+            fw[e][1] = pose[1] + s * fr[e][0] + c * fr[e][1];
+        }
+        const int degenerate = fr[0][0] == fr[1][0] && fr[0][1] == fr[1][1];
+        if (!degenerate && seg_intersect(fw[0], fw[1], a, b))
+        {
+            if (grad3) grad3[0] = grad3[1] = grad3[2] = 0.0;
+            if (hess6) for (int j = 0; j < 6; ++j) hess6[j] = 0.0;
+            return 0.0;
+        }
+        /* obstacle end points against this footprint feature (world-frame point/segment distance) */
+        const fp_seg wseg = {fw[0][0], fw[0][1], fw[1][0], fw[1][1], 0.0};
+        for (int e = 0; e < 2; ++e)
+        {
+            double cx, cy; int isv;
+            const double* q = e ? b : a;
+            const double d = point_segment(q[0], q[1], &wseg, &cx, &cy, &isv) - seg[i].rad;
+            if (d < best) { best = d; kind = 1 + e; }
+        }
+        /* footprint end points against the obstacle segment */
+        for (int e = 0; e < (degenerate ? 1 : 2); ++e)
+        {
+            const double t = ((fw[e][0] - a[0]) * ux + (fw[e][1] - a[1]) * uy) / len;
+            if (!(t > 0.0 && t < 1.0)) continue; /* clamped: that is an obstacle end point against this vertex, covered above */
+            const double sd = -(fw[e][0] - a[0]) * uy + (fw[e][1] - a[1]) * ux;
+            const double d = fabs(sd) - seg[i].rad;
+            if (d < best) { best = d; kind = 3; bv[0] = fr[e][0]; bv[1] = fr[e][1]; bsig = sd >= 0.0 ? 1.0 : -1.0; }
+        }
+    }
+    if (kind == 1 || kind == 2)
+    {
+        const double pt[5] = {kind == 1 ? a[0] : b[0], kind == 1 ? a[1] : b[1], 0, 0, 0};
+        return orc_footprint_distance(cfg, pose, MPCB200_OBST_POINT, pt, grad3, hess6);
+    }
+    if (grad3 || hess6)
+    {
+        const double nx = -uy, ny = ux;
+        const double rx = c * bv[0] - s * bv[1], ry = s * bv[0] + c * bv[1]; /* R v */
+        if (grad3) { grad3[0] = bsig * nx; grad3[1] = bsig * ny; grad3[2] = bsig * (-nx * ry + ny * rx); }
+        if (hess6) { hess6[0] = hess6[1] = hess6[2] = hess6[3] = hess6[4] = 0.0; hess6[5] = -bsig * (nx * rx + ny * ry); }
+    }
+    return best;
 }
 
 /* ---- config helpers ------------------------------------------------------------------------------------ */
@@ -634,8 +719,10 @@ void orc_associate(const orc_problem* p, orc_ws* ws)
             double dist = orc_footprint_distance(c, pose, p->obst_type[j], op, NULL, NULL);
             if (dist < c->force_inclusion_dist) { assoc_insert(ws, k, &cnt, dists, j, dist); continue; }
             if (dist > c->cutoff_dist) continue;
-            /* centroid of point / circle = centre */
-            if (ox * op[1] - op[0] * oy > 0)
+            /* teb getCentroid(): point / circle centre, segment midpoint; quirk 5: world coordinates, not relative to the pose */
+            const int is_line = p->obst_type[j] == MPCB200_OBST_LINE;
+            const double ccx = is_line ? 0.5 * (op[0] + op[2]) : op[0], ccy = is_line ? 0.5 * (op[1] + op[3]) : op[1];
+            if (ox * ccy - ccx * oy > 0)
             {
                 if (dist < left_min) { left_min = dist; left = j; }
             }

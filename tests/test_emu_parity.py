@@ -102,3 +102,30 @@ def test_warm_start_shift_matches_oracle(orc, emu):
         if st2 == 0:
             u2e, _ = e.outputs()
             assert np.abs(u2e - u2).max() < 1e-6
+
+
+@pytest.mark.parametrize("cid,B", [(2, 10), (3, 6)])
+def test_line_obstacles_match_oracle(orc, emu, cid, B):
+    """LineObstacle rows (every second obstacle of the batch turned into a wall segment): association, condensed records
+    and whole solves of the device code against the oracle."""
+    cfg = configs.config_for(cid, tol=1e-8)
+    data = configs.with_line_obstacles(configs.generate(cid, B))
+    ref = orc.step_batch(cfg, data, n_threads=2)
+    agree = 0
+    for b in range(B):
+        o = _oracle_init(orc, cfg, data, b)
+        e = emu.instance_from_batch(cfg, data, b)
+        e.init(); e.associate()
+        np.testing.assert_allclose(e.field(capi.F_X), o.arr("X"), atol=1e-12)
+        np.testing.assert_array_equal(e.field(capi.F_OBSIDX), o.arr("OBSIDX"))
+        o.eval(); e.eval()
+        scale = np.abs(o.arr("KKT")).max()
+        np.testing.assert_allclose(e.field(capi.F_KKT), o.arr("KKT"), atol=1e-9 * scale)
+        st = e.solve()
+        u, x = e.outputs()
+        agree += st == ref["status"][b]
+        if st == 0 and ref["status"][b] == 0:
+            assert abs(e.field(capi.F_SCAL)[capi.SC_DT] - ref["dt"][b]) < 1e-7
+            if not cfg.variable_dt:
+                assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
+    assert agree >= B - 1

@@ -231,6 +231,36 @@ def test_golden_g1_and_cfg2(cuda_lib):
     s.close()
 
 
+@pytest.mark.parametrize("cid,B", [(2, 48), (3, 24)])
+def test_line_obstacles(cuda_lib, orc, cid, B):
+    """LineObstacle rows through the C ABI: records of the first evaluation and whole solves against the oracle."""
+    cfg = configs.config_for(cid, tol=1e-8)
+    data = configs.with_line_obstacles(configs.generate(cid, B))
+    s = _solver(cfg, B)
+    _load_inputs(s, data)
+    s.run_phase(capi.PHASE_INIT); s.run_phase(capi.PHASE_ASSOCIATE)
+    X, OBS = s.ws_read(capi.F_X), s.ws_read(capi.F_OBSIDX)
+    s.run_phase(capi.PHASE_EVAL)
+    KKT = s.ws_read(capi.F_KKT)
+    for b in range(0, B, 4):
+        o = _oracle_state(orc, cfg, data, b, 0)
+        np.testing.assert_allclose(X[b], o.arr("X"), rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(OBS[b], o.arr("OBSIDX"))
+        o.eval()
+        np.testing.assert_allclose(KKT[b], o.arr("KKT"), rtol=0, atol=1e-10 * np.abs(o.arr("KKT")).max())
+    s.close()
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
+    ref = orc.step_batch(cfg, data, n_threads=4)
+    assert (out["status"] == ref["status"]).mean() >= 0.85
+    both = (out["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= 4
+    assert np.abs(out["dt"][both] - ref["dt"][both]).max() < 1e-6
+    if not cfg.variable_dt:
+        assert np.abs(out["u_seq"][both] - ref["u_seq"][both]).max() < U_TOL
+    s.close()
+
+
 def test_golden_cfg4_and_cfg3(cuda_lib):
     """CUDA path against the scipy fixtures of the via-point objective (cfg 4) and the car-like minimum-time problem (cfg 3, N=30)."""
     import golden_checks as gc

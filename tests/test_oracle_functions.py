@@ -160,6 +160,82 @@ def test_footprint_distance(orc, kind):
         np.testing.assert_allclose(Hm, Hfd, atol=1e-4)
 
 
+@pytest.mark.parametrize("kind", [capi.FOOTPRINT_POINT, capi.FOOTPRINT_CIRCULAR, capi.FOOTPRINT_TWO_CIRCLES, capi.FOOTPRINT_LINE,
+                                  capi.FOOTPRINT_POLYGON])
+def test_footprint_distance_to_line_obstacle(orc, kind):
+    """LineObstacle: value by brute force (teb's segment / segment rule written independently with
+    numpy), gradient / Hessian by finite differences."""
+    L = orc.lib()
+    cfg = _fp_cfg(kind)
+    rng = np.random.default_rng(100 + kind)
+
+    def dist(pose, op):
+        return L.orc_footprint_distance(C.byref(cfg), _dp(np.ascontiguousarray(pose)), capi.OBST_LINE, _dp(op), None, None)
+
+    def pt_seg(q, a, b):
+        ab = b - a; sq = ab @ ab
+        t = 0.0 if sq == 0 else min(1.0, max(0.0, ((q - a) @ ab) / sq))
+        return np.linalg.norm(q - (a + t * ab))
+
+    def cross(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    def seg_seg(a, b, c_, d):
+        if (a == b).all():
+            return pt_seg(a, c_, d)
+        # proper crossing via orientation tests
+        if cross(a, b, c_) * cross(a, b, d) <= 0 and cross(c_, d, a) * cross(c_, d, b) <= 0 and abs(cross(a, b, c_)) + abs(cross(a, b, d)) > 0:
+            return 0.0
+        return min(pt_seg(a, c_, d), pt_seg(b, c_, d), pt_seg(c_, a, b), pt_seg(d, a, b))
+
+    def features():
+        if kind == capi.FOOTPRINT_POINT:
+            return [(np.zeros(2), np.zeros(2), 0.0)]
+        if kind == capi.FOOTPRINT_CIRCULAR:
+            return [(np.zeros(2), np.zeros(2), 0.25)]
+        if kind == capi.FOOTPRINT_TWO_CIRCLES:
+            return [(np.array([0.2, 0.0]),) * 2 + (0.15,), (np.array([-0.25, 0.0]),) * 2 + (0.2,)]
+        if kind == capi.FOOTPRINT_LINE:
+            return [(np.array([-0.1, 0.05]), np.array([0.4, -0.02]), 0.0)]
+        P = np.array(configs.CARLIKE_POLYGON)
+        return [(P[i], P[(i + 1) % len(P)], 0.0) for i in range(len(P))]
+
+    def brute(pose, op):
+        c, s = math.cos(pose[2]), math.sin(pose[2])
+        R = np.array([[c, -s], [s, c]])
+        a, b = op[0:2], op[2:4]
+        return min(seg_seg(pose[:2] + R @ f0, pose[:2] + R @ f1, a, b) - r for f0, f1, r in features())
+
+    checked = 0
+    for _ in range(60):
+        pose = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-3, 3)])
+        a = rng.uniform(-2, 2, 2)
+        ang = rng.uniform(0, 2 * math.pi)
+        b = a + rng.uniform(0.2, 2.0) * np.array([math.cos(ang), math.sin(ang)])
+        op = np.array([a[0], a[1], b[0], b[1], 0.0])
+        d = dist(pose, op)
+        assert d == pytest.approx(brute(pose, op), abs=1e-12)
+        if d < 1e-3:
+            continue  # crossing / touching: the distance is clamped at 0 there
+        g = np.zeros(3); H = np.zeros(6)
+        L.orc_footprint_distance(C.byref(cfg), _dp(pose), capi.OBST_LINE, _dp(op), _dp(g), _dp(H))
+        h = 1e-6
+        gfd = np.array([(dist(pose + h * e, op) - dist(pose - h * e, op)) / (2 * h) for e in np.eye(3)])
+        np.testing.assert_allclose(g, gfd, atol=1e-7)
+        hh = 1e-4
+        Hfd = np.zeros((3, 3))
+        for i in range(3):
+            for j in range(3):
+                ei, ej = np.eye(3)[i] * hh, np.eye(3)[j] * hh
+                Hfd[i, j] = (dist(pose + ei + ej, op) - dist(pose + ei - ej, op) - dist(pose - ei + ej, op) + dist(pose - ei - ej, op)) / (4 * hh * hh)
+        Hm = np.array([[H[0], H[1], H[2]], [H[1], H[3], H[4]], [H[2], H[4], H[5]]])
+        if np.abs(Hfd - Hm).max() > 1e-4:  # feature switch inside the FD stencil (piecewise smooth distance)
+            continue
+        np.testing.assert_allclose(Hm, Hfd, atol=1e-4)
+        checked += 1
+    assert checked >= 30
+
+
 def _random_iterate(orc, cid, b, seed):
     cfg = configs.config_for(cid, tol=1e-8)
     data = configs.g1_instance() if cid == 1 else configs.generate(cid, b + 1)
