@@ -193,7 +193,9 @@ HD inline int footprint_segments(const Cfg& c, FpSeg* seg)
 }
 
 // distance footprint(pose) <-> point/circle obstacle; optional gradient (x,y,theta) and Hessian (xx,xy,xt,yy,yt,tt)
-template <bool WITH_GRAD, bool WITH_HESS>
+// LINES = false compiles the line-obstacle path out (the host knows whether a batch contains line obstacles; the hot
+// kernels are instantiated both ways so that point / circle batches do not pay its registers)
+template <bool WITH_GRAD, bool WITH_HESS, bool LINES = true>
 HD inline double footprint_distance_sc(const Cfg& c, double px, double py, double s, double co, int obst_type, const double* op,
                                        double* grad3, double* hess6);
 
@@ -203,7 +205,7 @@ HD inline double footprint_distance(const Cfg& c, double px, double py, double p
 {
     double s, co;
     sincos(pth, &s, &co);
-    return footprint_distance_sc<WITH_GRAD, WITH_HESS>(c, px, py, s, co, obst_type, op, grad3, hess6);
+    return footprint_distance_sc<WITH_GRAD, WITH_HESS, true>(c, px, py, s, co, obst_type, op, grad3, hess6);
 }
 
 // footprint <-> obstacle POINT (wx, wy) (+ obstacle radius r_obst): the point is taken to the robot frame and the closest
@@ -404,11 +406,11 @@ HD inline double footprint_distance_line(const Cfg& c, double px, double py, dou
 
 // distance footprint(pose) <-> obstacle (point, circle: params x, y, -, -, radius; line: x0, y0, x1, y1) with the sine / cosine of
 // the heading supplied by the caller (one sincos per stage, shared by all rows)
-template <bool WITH_GRAD, bool WITH_HESS>
+template <bool WITH_GRAD, bool WITH_HESS, bool LINES>
 HD inline double footprint_distance_sc(const Cfg& c, double px, double py, double s, double co, int obst_type, const double* op,
                                        double* grad3, double* hess6)
 {
-    if (obst_type == MPCB200_OBST_LINE) return footprint_distance_line<WITH_GRAD, WITH_HESS>(c, px, py, s, co, op, grad3, hess6);
+    if (LINES && obst_type == MPCB200_OBST_LINE) return footprint_distance_line<WITH_GRAD, WITH_HESS>(c, px, py, s, co, op, grad3, hess6);
     return footprint_distance_point<WITH_GRAD, WITH_HESS>(c, px, py, s, co, op[0], op[1], obst_type == MPCB200_OBST_CIRCLE ? op[4] : 0.0, grad3, hess6);
 }
 

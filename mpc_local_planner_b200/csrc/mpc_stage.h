@@ -139,6 +139,7 @@ HD inline void lin_rows_component(const Cfg& c, const WsLayout& L, const double*
 
 // Stage functions + derivatives of stage k -> condensed KKT record (G holds the mu-independent part g0, the
 // coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
+template <bool LINES = true>
 HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G, double* Kb, double uprev_dt, int k, EvalAcc& acc)
 {
     const int N = L.N, K = L.K;
@@ -294,7 +295,7 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
             const int oi = (int)AOBS(j, k);
             if (oi < 0) continue;
             double gd[3], hd[6];
-            const double dist = footprint_distance_sc<true, true>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
+            const double dist = footprint_distance_sc<true, true, LINES>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
                                                                   W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, hd);
             const double g = c.min_obstacle_dist - dist;
             const double s = AS(8 + j, k), lam = ALAM(8 + j, k);
@@ -504,6 +505,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
 struct TrialAcc { double obj, inf1, blog; };
 // merit pieces of stage k at the trial point z + alpha dz, s + alpha ds.  Linear rows are exact in alpha:
 // g(alpha) + s(alpha) = (1 - alpha) r0, so only the dynamics defect, the objective and the obstacle rows are re-evaluated.
+template <bool LINES = true>
 HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, const double* G, double uprev_dt, int k, double alpha, TrialAcc& acc)
 {
     const int N = L.N, K = L.K;
@@ -581,7 +583,7 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
         {
             const int oi = (int)AOBS(j, k);
             if (oi < 0) continue;
-            const double dist = footprint_distance_sc<false, false>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
+            const double dist = footprint_distance_sc<false, false, LINES>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
                                                                     W + L.oOBST + oi * MPCB200_OBST_STRIDE, nullptr, nullptr);
             const double sn = AS(8 + j, k) + alpha * ADS(8 + j, k);
             acc.inf1 += fabs(c.min_obstacle_dist - dist + sn);

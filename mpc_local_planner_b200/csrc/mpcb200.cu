@@ -351,7 +351,7 @@ __device__ __forceinline__ void evalacc_warp_reduce(EvalAcc& a)
     a.obj = warp_sum(a.obj); a.m_ineq = warp_sum(a.m_ineq); a.m_eq = warp_sum(a.m_eq);
 }
 
-template <int NW>
+template <int NW, bool LINES>
 __global__ void __maxnreg__(NW <= 2 ? 144 : 168) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, const int* slot_of, int B, double uprev_dt, int* n_active,
                                                              int img_words)
 {
@@ -368,7 +368,7 @@ __global__ void __maxnreg__(NW <= 2 ? 144 : 168) eval_kernel(Cfg c, WsLayout L, 
     double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
     EvalAcc a;
     evalacc_init(a);
-    for (int k = tid; k < N; k += blockDim.x) eval_stage(c, L, W, Gp, Kb, uprev_dt, k, a);
+    for (int k = tid; k < N; k += blockDim.x) eval_stage<LINES>(c, L, W, Gp, Kb, uprev_dt, k, a);
     evalacc_warp_reduce(a);
     if (lane == 0) s_acc[wid] = a;
     __syncthreads();
@@ -569,6 +569,7 @@ struct LsShared
 };
 
 #define GSC(i_) Gp[L.oSCAL + (i_)]
+template <bool LINES>
 __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt,
                                                                              int spec, int img_words)
 {
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg
     {
         TrialAcc t;
         t.obj = t.inf1 = t.blog = 0.0;
-        for (int k = tid; k < N; k += blockDim.x) ls_stage_trial(c, L, W, Gp, uprev_dt, k, alpha, t);
+        for (int k = tid; k < N; k += blockDim.x) ls_stage_trial<LINES>(c, L, W, Gp, uprev_dt, k, alpha, t);
         t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
         if (lane == 0) sh.tr[wid] = t;
         __syncthreads();
@@ -764,6 +765,7 @@ struct mpcb200_handle
     cudaEvent_t poll_ev[2];
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
+    int has_lines;  // the uploaded batch contains line obstacles: the eval / line-search kernels are launched with that path compiled in
     double uprev_dt;
     mpcb200_stats stats;
     std::vector<cudaEvent_t> ev;  // pool of event pairs
@@ -873,11 +875,16 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8));
     CKC(cudaMalloc(&h->d_slot_of, B * 4)); CKC(cudaMalloc(&h->d_inst_of_slot, ((B + TILE - 1) / TILE) * TILE * 4));
     CKC(cudaMalloc(&h->d_counters, 16)); CKC(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
-    CKC(cudaFuncSetAttribute(eval_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(eval_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(linesearch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
+    CKC(cudaFuncSetAttribute(linesearch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
     CKC(cudaFuncSetAttribute(kkt_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<true>()));
     CKC(cudaFuncSetAttribute(kkt_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<false>()));
     CKC(cudaMallocHost(&h->h_nactive, 8));
@@ -962,13 +969,15 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
         case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold); break;
         case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer); break;
         case MPCB200_PHASE_EVAL:
+#define EVAL_LAUNCH(NW, LN) eval_kernel<NW, LN><<<B, NW * 32, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words)
             switch (group_threads >> 5)
             {
-                case 1: eval_kernel<1><<<B, 32, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
-                case 2: eval_kernel<2><<<B, 64, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
-                case 3: eval_kernel<3><<<B, 96, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
-                default: eval_kernel<4><<<B, 128, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words); break;
+                case 1: if (h->has_lines) EVAL_LAUNCH(1, true); else EVAL_LAUNCH(1, false); break;
+                case 2: if (h->has_lines) EVAL_LAUNCH(2, true); else EVAL_LAUNCH(2, false); break;
+                case 3: if (h->has_lines) EVAL_LAUNCH(3, true); else EVAL_LAUNCH(3, false); break;
+                default: if (h->has_lines) EVAL_LAUNCH(4, true); else EVAL_LAUNCH(4, false); break;
             }
+#undef EVAL_LAUNCH
             break;
         case MPCB200_PHASE_KKT:
         {
@@ -979,7 +988,10 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
             else kkt_lane_kernel<false><<<kgrid, 32, kkt_smem_bytes<false>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->ric_attempt_stride, h->d_inst_of_slot, B, spec, h->d_counters);
             break;
         }
-        case MPCB200_PHASE_LINESEARCH: linesearch_kernel<<<B, group_threads, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec, img_words); break;
+        case MPCB200_PHASE_LINESEARCH:
+            if (h->has_lines) linesearch_kernel<true><<<B, group_threads, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec, img_words);
+            else linesearch_kernel<false><<<B, group_threads, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec, img_words);
+            break;
         default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
     }
     if (timed) ev_end(h);
@@ -1024,13 +1036,18 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
     if (u_prev) { CK(cudaMemcpyAsync(h->d_uprev, u_prev, (size_t)B * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)B * 16; }
     else CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
     h->uprev_dt = u_prev_dt;
-    h->has_obst = 0; h->obst_max = 0;
+    h->has_obst = 0; h->obst_max = 0; h->has_lines = 0;
     if (obst && obst->count && obst->max_per_instance > 0)
     {
         if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
         const size_t M = (size_t)obst->max_per_instance;
+        int lines = 0;
         for (size_t i = 0; i < (size_t)B * M; ++i)
+        {
             if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
+            lines |= obst->type[i] == MPCB200_OBST_LINE;
+        }
+        h->has_lines = lines;
         CK(cudaMemcpyAsync(h->d_obst_count, obst->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst_type, obst->type, (size_t)B * M * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst, obst->params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
