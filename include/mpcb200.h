@@ -116,6 +116,10 @@ typedef struct mpcb200_config {
     double tol;            /* scaled KKT error tolerance; "converged" <=> error <= tol */
     double mu_init;        /* initial barrier parameter (Ipopt default 0.1) */
     int outer_iterations;  /* controller/outer_ocp_iterations */
+    /* planning/objective/quadratic_form/integral_form (src/controller.cpp:593-594): the running cost enters as
+       sum_k dt * l(x_k, u_k) (grid/cost_integration_method left_sum, finite_differences_grid_se2.cpp:66-70; the
+       trapezoidal rule is not implemented).  Default 0 = every shipped configuration. */
+    int quadratic_integral_form;
 } mpcb200_config;
 
 /* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]). */

@@ -75,6 +75,7 @@ class Config(C.Structure):
         ("tol", C.c_double),
         ("mu_init", C.c_double),
         ("outer_iterations", C.c_int),
+        ("quadratic_integral_form", C.c_int),
     ]
 
     def copy(self):
@@ -126,6 +127,7 @@ def default_config():
     c.k_max_obstacles_per_stage = 5
     c.max_iter, c.tol, c.mu_init = 100, 1e-6, 0.1
     c.outer_iterations = 1
+    c.quadratic_integral_form = 0
     return c
 
 

@@ -173,6 +173,15 @@ def generate(config_id, B, first=0, n=None):
     return dict(x0=x0, xf=xf, u_prev=np.zeros((B, 2)), u_prev_dt=0.2, obstacles=(count, types, params), viapoints=vps)
 
 
+def cfg2_integral_form(n=50, tol=1e-6):
+    """cfg 2 with `planning/objective/quadratic_form/integral_form: true` (left sum) and a free dt in [0.05, 1.0] s --
+    not a BASELINE configuration; exercises the dt-dependence of the integrated running cost."""
+    c = cfg2(n, tol)
+    c.quadratic_integral_form = 1
+    c.variable_dt, c.dt_lb, c.dt_ub = 1, 0.05, 1.0
+    return c
+
+
 def with_line_obstacles(data, seed=0, every=2):
     """Variant of a generated batch in which every `every`-th obstacle is a LINE obstacle (a wall segment through the
     original centre, random direction, half-length radius + 0.25 m) -- exercises the LineObstacle distance of SURVEY App. B.3."""

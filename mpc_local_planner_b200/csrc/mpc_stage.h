@@ -184,6 +184,9 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
         // quadratic running cost (k = 0 state term is a constant: its gradient is never used since x_0 is fixed)
         if (has_quadratic(c))
         {
+            // integral form (left sum): dt * l(x_k, u_k); then l itself is the dt-gradient and grad l the w-dt cross Hessian
+            const bool integ = c.quadratic_integral_form != 0;
+            const double wq = integ ? dt : 1.0;
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             double o = 0.0;
 #pragma unroll
@@ -195,9 +198,10 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
                 {
                     gi += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j];
                     o += d[i] * c.Q[i * 3 + j] * d[j];
-                    if (j >= i) H[hidx(i, j)] += c.Q[i * 3 + j] + c.Q[j * 3 + i];
+                    if (j >= i) H[hidx(i, j)] += wq * (c.Q[i * 3 + j] + c.Q[j * 3 + i]);
                 }
-                g0[i] += gi; GL[i] += gi;
+                g0[i] += wq * gi; GL[i] += wq * gi;
+                if (integ && c.variable_dt) hb[i] += gi;
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -208,11 +212,13 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
                 {
                     gi += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j];
                     o += u[i] * c.R[i * 2 + j] * u[j];
-                    if (j >= i) H[hidx(3 + i, 3 + j)] += c.R[i * 2 + j] + c.R[j * 2 + i];
+                    if (j >= i) H[hidx(3 + i, 3 + j)] += wq * (c.R[i * 2 + j] + c.R[j * 2 + i]);
                 }
-                g0[3 + i] += gi; GL[3 + i] += gi;
+                g0[3 + i] += wq * gi; GL[3 + i] += wq * gi;
+                if (integ && c.variable_dt) hb[3 + i] += gi;
             }
-            acc.obj += o;
+            acc.obj += wq * o;
+            if (integ && c.variable_dt) { acc.gt0 += o; acc.gldt += o; }
         }
         // Lagrangian terms of nu_k^T e_k
         const double fx_nu = nu[0] * J[0] + nu[1] * J[3] + nu[2] * J[6];
@@ -453,10 +459,14 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         {
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             const double u[2] = {AU(0, k), AU(1, k)};
+            const bool integ = c.quadratic_integral_form != 0;
+            const double wq = integ ? ASC(MPCB200_SC_DT) : 1.0;
+            double dl = 0.0, l = 0.0;
             for (int i = 0; i < 3; ++i)
-                for (int j = 0; j < 3; ++j) dJ += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j] * dx[i];
+                for (int j = 0; j < 3; ++j) { dl += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j] * dx[i]; l += d[i] * c.Q[i * 3 + j] * d[j]; }
             for (int i = 0; i < 2; ++i)
-                for (int j = 0; j < 2; ++j) dJ += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j] * du[i];
+                for (int j = 0; j < 2; ++j) { dl += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j] * du[i]; l += u[i] * c.R[i * 2 + j] * u[j]; }
+            dJ += wq * dl + ((integ && c.variable_dt) ? l * ddt : 0.0);
         }
     }
     else
@@ -541,7 +551,7 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
             for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) o += u[i] * c.R[i * 2 + j] * u[j];
-            acc.obj += o;
+            acc.obj += (c.quadratic_integral_form ? dtt : 1.0) * o;
         }
     }
     else

@@ -803,7 +803,7 @@ extern "C" void mpcb200_default_config(mpcb200_config* c)
     c->min_obstacle_dist = 0.5; c->force_inclusion_dist = 0.5; c->cutoff_dist = 2.0;
     c->footprint_type = MPCB200_FOOTPRINT_POINT;
     c->k_max_obstacles_per_stage = 5;
-    c->max_iter = 100; c->tol = 1e-6; c->mu_init = 0.1; c->outer_iterations = 1;
+    c->max_iter = 100; c->tol = 1e-6; c->mu_init = 0.1; c->outer_iterations = 1; c->quadratic_integral_form = 0;
 }
 
 static int validate_config(const mpcb200_config* c, std::string& why)

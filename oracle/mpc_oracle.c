@@ -523,7 +523,8 @@ double orc_objective(const orc_problem* p, const orc_ws* ws, const double* X, co
         {
             double d[3] = {X[IX(0, k)] - p->xf[0], X[IX(1, k)] - p->xf[1], orc_normalize_theta(X[IX(2, k)] - p->xf[2])};
             double u[2] = {U[IX(0, k)], U[IX(1, k)]};
-            J += quad3(c->Q, d) + quad2(c->R, u);
+            /* integral form (quadratic_cost_se2.cpp:54-84 through corbo's LeftSumCostEdge, finite_differences_grid_se2.cpp:66-70): dt * l */
+            J += (c->quadratic_integral_form ? dt : 1.0) * (quad3(c->Q, d) + quad2(c->R, u));
         }
     }
     if (has_terminal_cost(c))
@@ -1030,15 +1031,28 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
         if (has_quadratic(c))
         {
             double d[3] = {x[0] - p->xf[0], x[1] - p->xf[1], orc_normalize_theta(x[2] - p->xf[2])};
+            const int integ = c->quadratic_integral_form != 0;
+            const double wq = integ ? dt : 1.0;
+            double gxl[3] = {0, 0, 0}, gul[2] = {0, 0};
             for (int i = 0; i < 3; ++i)
             {
-                for (int j = 0; j < 3; ++j) gx[i] += (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j];
-                for (int j = i; j < 3; ++j) hadd(KKT, N, k, i, j, c->Q[i * 3 + j] + c->Q[j * 3 + i]);
+                for (int j = 0; j < 3; ++j) gxl[i] += (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j];
+                for (int j = i; j < 3; ++j) hadd(KKT, N, k, i, j, wq * (c->Q[i * 3 + j] + c->Q[j * 3 + i]));
+                gx[i] = wq * gxl[i];
             }
             for (int i = 0; i < 2; ++i)
             {
-                for (int j = 0; j < 2; ++j) gu[i] += (c->R[i * 2 + j] + c->R[j * 2 + i]) * u[j];
-                for (int j = i; j < 2; ++j) hadd(KKT, N, k, 3 + i, 3 + j, c->R[i * 2 + j] + c->R[j * 2 + i]);
+                for (int j = 0; j < 2; ++j) gul[i] += (c->R[i * 2 + j] + c->R[j * 2 + i]) * u[j];
+                for (int j = i; j < 2; ++j) hadd(KKT, N, k, 3 + i, 3 + j, wq * (c->R[i * 2 + j] + c->R[j * 2 + i]));
+                gu[i] = wq * gul[i];
+            }
+            if (integ && c->variable_dt)
+            {
+                /* d/ddt of dt * l is l; the w-dt cross Hessian is grad l */
+                const double l = quad3(c->Q, d) + quad2(c->R, u);
+                gt0 += l; gl_dt += l;
+                for (int i = 0; i < 3; ++i) KK(MPCB200_K_HB + i, k) += gxl[i];
+                for (int i = 0; i < 2; ++i) KK(MPCB200_K_HB + 3 + i, k) += gul[i];
             }
         }
         for (int i = 0; i < 3; ++i) { KK(MPCB200_K_G + i, k) += gx[i]; GL[IX(i, k)] += gx[i]; }
@@ -1584,10 +1598,12 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
                 {
                     double d[3] = {ws->X[IX(0, k)] - p->xf[0], ws->X[IX(1, k)] - p->xf[1], orc_normalize_theta(ws->X[IX(2, k)] - p->xf[2])};
                     double u[2] = {ws->U[IX(0, k)], ws->U[IX(1, k)]};
+                    const double wq = c->quadratic_integral_form ? dt : 1.0;
                     for (int i = 0; i < 3; ++i)
-                        for (int j = 0; j < 3; ++j) dJ += (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j] * ws->STEP[IX(i, k)];
+                        for (int j = 0; j < 3; ++j) dJ += wq * (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j] * ws->STEP[IX(i, k)];
                     for (int i = 0; i < 2; ++i)
-                        for (int j = 0; j < 2; ++j) dJ += (c->R[i * 2 + j] + c->R[j * 2 + i]) * u[j] * ws->STEP[IX(3 + i, k)];
+                        for (int j = 0; j < 2; ++j) dJ += wq * (c->R[i * 2 + j] + c->R[j * 2 + i]) * u[j] * ws->STEP[IX(3 + i, k)];
+                    if (c->quadratic_integral_form && c->variable_dt) dJ += (quad3(c->Q, d) + quad2(c->R, u)) * ddt;
                 }
             if (has_terminal_cost(c))
             {

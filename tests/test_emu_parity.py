@@ -129,3 +129,28 @@ def test_line_obstacles_match_oracle(orc, emu, cid, B):
             if not cfg.variable_dt:
                 assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
     assert agree >= B - 1
+
+
+def test_integral_form_cost_matches_oracle(orc, emu):
+    """quadratic_form/integral_form (left sum) with a free dt: records of the first evaluation and whole solves."""
+    cfg = configs.cfg2_integral_form(tol=1e-8)
+    B = 8
+    data = configs.generate(2, B)
+    ref = orc.step_batch(cfg, data, n_threads=2)
+    n_both = 0
+    for b in range(B):
+        o = _oracle_init(orc, cfg, data, b)
+        e = emu.instance_from_batch(cfg, data, b)
+        e.init(); e.associate()
+        o.eval(); e.eval()
+        scale = np.abs(o.arr("KKT")).max()
+        np.testing.assert_allclose(e.field(capi.F_KKT), o.arr("KKT"), atol=1e-9 * scale)
+        idx = [capi.SC_HTT, capi.SC_GT, capi.SC_OBJ, capi.SC_ERR0]
+        np.testing.assert_allclose(e.field(capi.F_SCAL)[idx], o.arr("SCAL")[idx], rtol=1e-8, atol=1e-10)
+        st = e.solve()
+        u, x = e.outputs()
+        if st == 0 and ref["status"][b] == 0:
+            n_both += 1
+            assert abs(e.field(capi.F_SCAL)[capi.SC_DT] - ref["dt"][b]) < 1e-7
+            assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
+    assert n_both >= 2

@@ -261,6 +261,22 @@ def test_line_obstacles(cuda_lib, orc, cid, B):
     s.close()
 
 
+def test_integral_form_cost(cuda_lib, orc):
+    """quadratic_form/integral_form (left sum) with a free dt through the C ABI against the oracle."""
+    cfg = configs.cfg2_integral_form(tol=1e-8)
+    B = 32
+    data = configs.generate(2, B)
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    ref = orc.step_batch(cfg, data, n_threads=4)
+    assert (out["status"] == ref["status"]).mean() >= 0.85
+    both = (out["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= 6
+    assert np.abs(out["dt"][both] - ref["dt"][both]).max() < 1e-6
+    assert np.abs(out["u_seq"][both] - ref["u_seq"][both]).max() < U_TOL
+    s.close()
+
+
 def test_golden_cfg4_and_cfg3(cuda_lib):
     """CUDA path against the scipy fixtures of the via-point objective (cfg 4) and the car-like minimum-time problem (cfg 3, N=30)."""
     import golden_checks as gc
