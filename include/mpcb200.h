@@ -120,6 +120,12 @@ typedef struct mpcb200_config {
        sum_k dt * l(x_k, u_k) (grid/cost_integration_method left_sum, finite_differences_grid_se2.cpp:66-70; the
        trapezoidal rule is not implemented).  Default 0 = every shipped configuration. */
     int quadratic_integral_form;
+    /* planning/terminal_constraint (src/controller.cpp:676-709): type "l2_ball" = TerminalBallSE2, one inequality row on the
+       final state, d' S d - gamma <= 0 with d = x_{N-1} - x_f (theta wrapped), final_state_conditions_se2.cpp:54-64;
+       gamma is the configured `radius` passed through unchanged (controller.cpp:702-703).  Ignored when x_f is fully fixed. */
+    int terminal_ball;
+    double terminal_ball_S[9];
+    double terminal_ball_gamma;
 } mpcb200_config;
 
 /* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]). */

@@ -76,6 +76,9 @@ class Config(C.Structure):
         ("mu_init", C.c_double),
         ("outer_iterations", C.c_int),
         ("quadratic_integral_form", C.c_int),
+        ("terminal_ball", C.c_int),
+        ("terminal_ball_S", C.c_double * 9),
+        ("terminal_ball_gamma", C.c_double),
     ]
 
     def copy(self):
@@ -128,6 +131,10 @@ def default_config():
     c.max_iter, c.tol, c.mu_init = 100, 1e-6, 0.1
     c.outer_iterations = 1
     c.quadratic_integral_form = 0
+    c.terminal_ball = 0
+    for i in range(9):
+        c.terminal_ball_S[i] = 1.0 if i % 4 == 0 else 0.0
+    c.terminal_ball_gamma = 5.0
     return c
 
 

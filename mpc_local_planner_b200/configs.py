@@ -182,6 +182,16 @@ def cfg2_integral_form(n=50, tol=1e-6):
     return c
 
 
+def cfg2_terminal_ball(n=50, tol=1e-6, gamma=0.05):
+    """cfg 2 with `planning/terminal_constraint/type: l2_ball` (TerminalBallSE2: d' S d - gamma <= 0 on the final state),
+    S = diag(1, 1, 0.5) -- not a BASELINE configuration."""
+    c = cfg2(n, tol)
+    c.terminal_ball = 1
+    _diag(c.terminal_ball_S, [1.0, 1.0, 0.5])
+    c.terminal_ball_gamma = gamma
+    return c
+
+
 def with_line_obstacles(data, seed=0, every=2):
     """Variant of a generated batch in which every `every`-th obstacle is a LINE obstacle (a wall segment through the
     original centre, random direction, half-length radius + 0.25 m) -- exercises the LineObstacle distance of SURVEY App. B.3."""

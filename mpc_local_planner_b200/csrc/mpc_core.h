@@ -435,6 +435,37 @@ HD inline bool has_viapoints(const Cfg& c)
 }
 HD inline bool has_terminal_cost(const Cfg& c) { return c.terminal_cost && !xf_all_fixed(c); }
 
+// ---- terminal ball (TerminalBallSE2, R/src/optimal_control/final_state_conditions_se2.cpp:54-64): row slot 2 of stage N-1 ----
+#define BALL_SLOT 2
+HD inline bool ball_active(const Cfg& c) { return c.terminal_ball != 0 && !xf_all_fixed(c); }
+// g = d'Sd - gamma, d = x - x_f (theta wrapped); optional gradient (S + S')d and Hessian S + S' (packed xx,xy,xt,yy,yt,tt)
+HD inline double ball_row(const Cfg& c, const double* x, const double* xf, double* grad3, double* hess6)
+{
+    const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+    double g = -c.terminal_ball_gamma;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        double gi = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+        {
+            g += d[i] * c.terminal_ball_S[i * 3 + j] * d[j];
+            gi += (c.terminal_ball_S[i * 3 + j] + c.terminal_ball_S[j * 3 + i]) * d[j];
+        }
+        if (grad3) grad3[i] = gi;
+    }
+    if (hess6)
+    {
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i; j < 3; ++j, ++q) hess6[q] = c.terminal_ball_S[i * 3 + j] + c.terminal_ball_S[j * 3 + i];
+    }
+    return g;
+}
+
 // ---- linear inequality rows (slots 0..7; see DESIGN.md "row slots") ----
 // slot < 4, k <= N-2: control bounds; k == N-1: dt bounds.  slot 4..7: control-rate rows of stage k.
 HD inline bool lin_row_active(const Cfg& c, int N, int k, int slot, double uprev_dt)

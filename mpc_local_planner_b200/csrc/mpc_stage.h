@@ -270,6 +270,23 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
             row_stats(acc, rp, r, s, lam);
             acc.gt0 += c0 * gdt; acc.gt1 += rs * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt;
         }
+        if (ball_active(c))
+        {
+            // terminal ball on x_{N-1} (slot BALL_SLOT): a nonlinear state row, handled like an obstacle row
+            double gr[3], hd[6];
+            const double g = ball_row(c, x, xf, gr, hd);
+            const double s = AS(BALL_SLOT, k), lam = ALAM(BALL_SLOT, k);
+            const double rs = 1.0 / s, r = g + s, sig = lam * rs, c0 = sig * r;
+            row_stats(acc, rp, r, s, lam);
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+                g0[i] += c0 * gr[i]; g1[i] += rs * gr[i]; GL[i] += lam * gr[i];
+#pragma unroll
+                for (int jj = i; jj < 3; ++jj, ++q) H[hidx(i, jj)] += lam * hd[q] + sig * gr[i] * gr[jj];
+            }
+        }
     }
     // multiplier of the previous defect: d/dx_k ( nu_{k-1}^T e_{k-1} ) = -nu_{k-1}
     if (k >= 1) { GL[0] -= ANU(0, k - 1); GL[1] -= ANU(1, k - 1); GL[2] -= ANU(2, k - 1); }
@@ -419,7 +436,13 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
     for (int sl = 0; sl < 8 + K; ++sl)
     {
         double g, gdz;
-        if (sl < 8)
+        if (sl == BALL_SLOT && k == N - 1 && ball_active(c))
+        {
+            double gr[3];
+            g = ball_row(c, x, xf, gr, nullptr);
+            gdz = gr[0] * dx[0] + gr[1] * dx[1] + gr[2] * dx[2];
+        }
+        else if (sl < 8)
         {
             if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
             const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
@@ -599,6 +622,12 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
             acc.inf1 += fabs(c.min_obstacle_dist - dist + sn);
             rowprod_add(rp, sn, acc.blog);
         }
+    if (k == N - 1 && ball_active(c))
+    {
+        const double sn = AS(BALL_SLOT, k) + alpha * ADS(BALL_SLOT, k);
+        acc.inf1 += fabs(ball_row(c, x, xf, nullptr, nullptr) + sn);
+        rowprod_add(rp, sn, acc.blog);
+    }
     rowprod_flush(rp, acc.blog);
 }
 
@@ -619,7 +648,7 @@ HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W,
     for (int sl = 0; sl < 8 + K; ++sl)
     {
         bool act;
-        if (sl < 8) act = lin_row_active(c, N, k, sl, uprev_dt);
+        if (sl < 8) act = lin_row_active(c, N, k, sl, uprev_dt) || (sl == BALL_SLOT && k == N - 1 && ball_active(c));
         else act = (k >= 1 && k <= N - 2) && AOBS(sl - 8, k) >= 0.0;
         if (!act) continue;
         double s = AS(sl, k) + alpha * ADS(sl, k);
@@ -929,7 +958,13 @@ HD inline void init_duals_stage(const Cfg& c, const WsLayout& L, double* W, doub
     {
         double s = 1.0, lam = 0.0, g = 0.0;
         bool act;
-        if (sl < 8)
+        if (sl == BALL_SLOT && k == N - 1 && ball_active(c))
+        {
+            const double xk[3] = {AX(0, k), AX(1, k), AX(2, k)}, xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
+            act = true;
+            g = ball_row(c, xk, xf, nullptr, nullptr);
+        }
+        else if (sl < 8)
         {
             act = lin_row_active(c, N, k, sl, uprev_dt);
             if (act)

@@ -405,6 +405,7 @@ static int has_terminal_cost(const mpcb200_config* c) { return c->terminal_cost 
  * Row slots per stage (RS = 8 + K):
  *   0..3  k <= N-2: control bounds (u0 lb, u0 ub, u1 lb, u1 ub)       [R/src/controller.cpp:511,527,543]
  *         k == N-1: dt bounds (slot 0 lb, slot 1 ub) when dt is free   [R/src/controller.cpp:242-246]
+ *                   slot 2: terminal ball on x_{N-1}                    [R/src/optimal_control/final_state_conditions_se2.cpp:54-64]
  *   4..7  control-rate rows of stage k (comp0 lb, comp0 ub, comp1 lb, comp1 ub), k = 0..N-1
  *         [R/src/optimal_control/stage_inequality_se2.cpp:191-222; wiring finite_differences_grid_se2.cpp:47-50,146-151]
  *   8..   obstacle rows, k = 1..N-2                                    [stage_inequality_se2.cpp:164-175]
@@ -420,6 +421,7 @@ static int row_active(const orc_problem* p, const orc_ws* ws, int k, int slot)
             int i = slot >> 1;
             return (slot & 1) ? (c->u_ub[i] < MPCB200_INF) : (c->u_lb[i] > -MPCB200_INF);
         }
+        if (slot == 2) return c->terminal_ball && !xf_all_fixed(c); /* TerminalBallSE2 on x_{N-1} */
         if (!c->variable_dt) return 0;
         if (slot == 0) return c->dt_lb > -MPCB200_INF;
         if (slot == 1) return c->dt_ub < MPCB200_INF;
@@ -455,6 +457,25 @@ static double row_value(const orc_problem* p, const orc_ws* ws, int k, int slot,
             if (slot & 1) { if (grad8) grad8[3 + i] = 1.0;  return U[IX(i, k)] - c->u_ub[i]; }
             if (grad8) grad8[3 + i] = -1.0;
             return c->u_lb[i] - U[IX(i, k)];
+        }
+        if (slot == 2)
+        {
+            /* terminal ball d' S d - gamma (final_state_conditions_se2.cpp:54-64) */
+            const double d[3] = {X[IX(0, k)] - p->xf[0], X[IX(1, k)] - p->xf[1], orc_normalize_theta(X[IX(2, k)] - p->xf[2])};
+            const double* S = c->terminal_ball_S;
+            double g = -c->terminal_ball_gamma;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) g += d[i] * S[i * 3 + j] * d[j];
+            if (grad8)
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) grad8[i] += (S[i * 3 + j] + S[j * 3 + i]) * d[j];
+            if (hess6)
+            {
+                int q = 0;
+                for (int i = 0; i < 3; ++i)
+                    for (int j = i; j < 3; ++j, ++q) hess6[q] = S[i * 3 + j] + S[j * 3 + i];
+            }
+            return g;
         }
         if (slot == 0) { if (grad8) grad8[7] = -1.0; return c->dt_lb - dt; }
         if (grad8) grad8[7] = 1.0;
@@ -1123,7 +1144,8 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
         {
             if (!row_active(p, ws, k, sl)) { ws->G[IX(sl, k)] = 0.0; continue; }
             double grad[8], h6[6];
-            double g = row_value(p, ws, k, sl, ws->X, ws->U, dt, grad, sl >= 8 ? h6 : NULL);
+            const int state_row = sl >= 8 || (k == N - 1 && sl == 2); /* rows on x_k: obstacles, terminal ball */
+            double g = row_value(p, ws, k, sl, ws->X, ws->U, dt, grad, state_row ? h6 : NULL);
             ws->G[IX(sl, k)] = g;
             double s = ws->S[IX(sl, k)], lam = ws->LAM[IX(sl, k)];
             double r = g + s, sig = lam / s;
@@ -1136,8 +1158,8 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
             ++m_ineq;
             double c0 = sig * r; /* mu-independent part of gamma = mu/s + sig r */
             double c1 = 1.0 / s; /* coefficient of mu */
-            /* x_k part (obstacle rows) */
-            if (sl >= 8)
+            /* x_k part (obstacle rows, terminal ball) */
+            if (state_row)
             {
                 for (int i = 0; i < 3; ++i)
                 {

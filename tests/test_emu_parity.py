@@ -154,3 +154,32 @@ def test_integral_form_cost_matches_oracle(orc, emu):
             assert abs(e.field(capi.F_SCAL)[capi.SC_DT] - ref["dt"][b]) < 1e-7
             assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
     assert n_both >= 2
+
+
+def test_terminal_ball_matches_oracle(orc, emu):
+    """terminal_constraint l2_ball (TerminalBallSE2): records of the first evaluation and whole solves; the ball is
+    active on some instances (final state on its boundary) and inactive on others."""
+    cfg = configs.cfg2_terminal_ball(tol=1e-8)
+    B = 14
+    data = configs.generate(2, B)
+    ref = orc.step_batch(cfg, data, n_threads=2)
+    n_both = n_active = 0
+    for b in range(B):
+        o = _oracle_init(orc, cfg, data, b)
+        e = emu.instance_from_batch(cfg, data, b)
+        e.init(); e.associate()
+        np.testing.assert_allclose(e.field(capi.F_S), o.arr("S"), rtol=1e-9)
+        o.eval(); e.eval()
+        scale = np.abs(o.arr("KKT")).max()
+        np.testing.assert_allclose(e.field(capi.F_KKT), o.arr("KKT"), atol=1e-9 * scale)
+        st = e.solve()
+        u, x = e.outputs()
+        if st == 0 and ref["status"][b] == 0:
+            n_both += 1
+            assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
+            d = x[-1] - data["xf"][b]
+            d[2] = (d[2] + np.pi) % (2 * np.pi) - np.pi
+            val = d[0] ** 2 + d[1] ** 2 + 0.5 * d[2] ** 2
+            assert val <= cfg.terminal_ball_gamma + 1e-7
+            n_active += abs(val - cfg.terminal_ball_gamma) < 1e-6
+    assert n_both >= 3 and n_active >= 1

@@ -277,6 +277,25 @@ def test_integral_form_cost(cuda_lib, orc):
     s.close()
 
 
+def test_terminal_ball(cuda_lib, orc):
+    """terminal_constraint l2_ball (TerminalBallSE2) through the C ABI against the oracle."""
+    cfg = configs.cfg2_terminal_ball(tol=1e-8)
+    B = 48
+    data = configs.generate(2, B)
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    ref = orc.step_batch(cfg, data, n_threads=4)
+    assert (out["status"] == ref["status"]).mean() >= 0.85
+    both = (out["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= 8
+    assert np.abs(out["u_seq"][both] - ref["u_seq"][both]).max() < U_TOL
+    d = out["x_seq"][both][:, -1] - data["xf"][both]
+    d[:, 2] = (d[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    val = d[:, 0] ** 2 + d[:, 1] ** 2 + 0.5 * d[:, 2] ** 2
+    assert (val <= cfg.terminal_ball_gamma + 1e-6).all() and (np.abs(val - cfg.terminal_ball_gamma) < 1e-5).any()
+    s.close()
+
+
 def test_golden_cfg4_and_cfg3(cuda_lib):
     """CUDA path against the scipy fixtures of the via-point objective (cfg 4) and the car-like minimum-time problem (cfg 3, N=30)."""
     import golden_checks as gc

@@ -237,8 +237,8 @@ def test_footprint_distance_to_line_obstacle(orc, kind):
 
 
 def _random_iterate(orc, cid, b, seed):
-    cfg = configs.cfg2_integral_form(tol=1e-8) if cid == 21 else configs.config_for(cid, tol=1e-8)
-    cid = 2 if cid == 21 else cid
+    cfg = configs.cfg2_integral_form(tol=1e-8) if cid == 21 else (configs.cfg2_terminal_ball(tol=1e-8) if cid == 22 else configs.config_for(cid, tol=1e-8))
+    cid = 2 if cid in (21, 22) else cid
     data = configs.g1_instance() if cid == 1 else configs.generate(cid, b + 1)
     inst = orc.instance_from_batch(cfg, data, 0 if cid == 1 else b)
     N = inst.N
@@ -270,7 +270,7 @@ def _lagrangian(inst):
     return S[capi.SC_OBJ] + (inst.arr("NU")[:, :N - 1] * e).sum() + (inst.arr("LAM") * (inst.arr("G") + inst.arr("S")) * (inst.arr("LAM") > 0)).sum()
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22])
 def test_lagrangian_gradient_and_newton_step(orc, cid):
     """Analytic Lagrangian gradient vs finite differences; the Riccati Newton step (incl. the dt border and the fixed
     terminal state) vs a dense numpy solve of the full KKT system assembled by finite differences."""
