@@ -68,7 +68,7 @@ extern "C" {
 #define MPCB200_E_NODEVICE -5    /* no CUDA device: there is NO CPU fallback */
 
 #define MPCB200_MAX_POLY 16
-#define MPCB200_OBST_STRIDE 5    /* doubles per obstacle in mpcb200_obstacles.params */
+#define MPCB200_OBST_STRIDE 7    /* doubles per obstacle in mpcb200_obstacles.params */
 #define MPCB200_INF 1e30         /* |bound| >= this means "no bound" (corbo CORBO_INF_DBL sentinel) */
 
 /*
@@ -123,6 +123,10 @@ typedef struct mpcb200_config {
     /* planning/terminal_constraint (src/controller.cpp:676-709): type "l2_ball" = TerminalBallSE2, one inequality row on the
        final state, d' S d - gamma <= 0 with d = x_{N-1} - x_f (theta wrapped), final_state_conditions_se2.cpp:54-64;
        gamma is the configured `radius` passed through unchanged (controller.cpp:702-703).  Ignored when x_f is fully fixed. */
+    /* collision_avoidance/enable_dynamic_obstacles (src/controller.cpp:721-723): obstacles with a non-zero velocity are kept
+       at every stage (stage_inequality_se2.cpp:99-106) and their rows use the position predicted at t = k dt with constant
+       velocity (teb estimateSpatioTemporalDistance, stage_inequality_se2.cpp:177-189).  Default 0 (the reference's). */
+    int enable_dynamic_obstacles;
     int terminal_ball;
     double terminal_ball_S[9];
     double terminal_ball_gamma;
@@ -133,7 +137,7 @@ typedef struct mpcb200_obstacles {
     int max_per_instance;
     const int* count;      /* [B] */
     const int* type;       /* [B*max_per_instance] MPCB200_OBST_* */
-    const double* params;  /* [B*max_per_instance*MPCB200_OBST_STRIDE]: x0, y0, x1, y1, radius */
+    const double* params;  /* [B*max_per_instance*MPCB200_OBST_STRIDE]: x0, y0, x1, y1, radius, vx, vy (velocity: dynamic obstacles) */
 } mpcb200_obstacles;
 
 /* Per-instance via-points (teb PoseSE2 list handed to Controller::configure, inc/controller.h:61-63). */

@@ -27,7 +27,7 @@ namespace mpcb200 {
 
 struct PoseSE2 { double x = 0, y = 0, theta = 0; };
 struct Twist { double linear_x = 0, linear_y = 0, angular_z = 0; };
-struct Obstacle { int type = MPCB200_OBST_POINT; double x0 = 0, y0 = 0, x1 = 0, y1 = 0, radius = 0; };
+struct Obstacle { int type = MPCB200_OBST_POINT; double x0 = 0, y0 = 0, x1 = 0, y1 = 0, radius = 0, vx = 0, vy = 0; };  // (vx, vy): centroid velocity of a dynamic obstacle
 
 struct TimeSeries
 {
@@ -187,7 +187,7 @@ class Controller
                 const Obstacle& o = (*_obstacles)[i];
                 otype[i] = o.type;
                 double* p = &oparams[(size_t)i * MPCB200_OBST_STRIDE];
-                p[0] = o.x0; p[1] = o.y0; p[2] = o.x1; p[3] = o.y1; p[4] = o.radius;
+                p[0] = o.x0; p[1] = o.y0; p[2] = o.x1; p[3] = o.y1; p[4] = o.radius; p[5] = o.vx; p[6] = o.vy;
             }
             ob.max_per_instance = ocount; ob.count = &ocount; ob.type = otype.data(); ob.params = oparams.data();
         }

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 MAX_POLY = 16
-OBST_STRIDE = 5
+OBST_STRIDE = 7
 INF = 1e30
 KKT_WORDS = 42
 STEP_WORDS = 8
@@ -76,6 +76,7 @@ class Config(C.Structure):
         ("mu_init", C.c_double),
         ("outer_iterations", C.c_int),
         ("quadratic_integral_form", C.c_int),
+        ("enable_dynamic_obstacles", C.c_int),
         ("terminal_ball", C.c_int),
         ("terminal_ball_S", C.c_double * 9),
         ("terminal_ball_gamma", C.c_double),
@@ -131,6 +132,7 @@ def default_config():
     c.max_iter, c.tol, c.mu_init = 100, 1e-6, 0.1
     c.outer_iterations = 1
     c.quadratic_integral_form = 0
+    c.enable_dynamic_obstacles = 0
     c.terminal_ball = 0
     for i in range(9):
         c.terminal_ball_S[i] = 1.0 if i % 4 == 0 else 0.0

@@ -192,6 +192,17 @@ def cfg2_terminal_ball(n=50, tol=1e-6, gamma=0.05):
     return c
 
 
+def with_moving_obstacles(data, seed=0, vmax=0.15):
+    """Variant of a batch in which every obstacle moves with a constant velocity ~U(-vmax, vmax)^2 (dynamic obstacles: set
+    `enable_dynamic_obstacles` in the config to make the solver use the predicted positions)."""
+    count, types, params = (a.copy() for a in data["obstacles"])
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(SEED_BASE + 99 + seed)))
+    params[:, :, 5:7] = rng.uniform(-vmax, vmax, size=params[:, :, 5:7].shape)
+    out = dict(data)
+    out["obstacles"] = (count, types, params)
+    return out
+
+
 def with_line_obstacles(data, seed=0, every=2):
     """Variant of a generated batch in which every `every`-th obstacle is a LINE obstacle (a wall segment through the
     original centre, random direction, half-length radius + 0.25 m) -- exercises the LineObstacle distance of SURVEY App. B.3."""

@@ -414,6 +414,19 @@ HD inline double footprint_distance_sc(const Cfg& c, double px, double py, doubl
     return footprint_distance_point<WITH_GRAD, WITH_HESS>(c, px, py, s, co, op[0], op[1], obst_type == MPCB200_OBST_CIRCLE ? op[4] : 0.0, grad3, hess6);
 }
 
+// A dynamic obstacle (collision_avoidance/enable_dynamic_obstacles, velocity op[5..6] != 0) enters stage k at the position
+// predicted for t = k dt with constant velocity (teb estimateSpatioTemporalDistance, R/src/optimal_control/stage_inequality_se2.cpp:177-189)
+HD inline bool obstacle_is_dynamic(const Cfg& c, const double* op) { return c.enable_dynamic_obstacles != 0 && (op[5] != 0.0 || op[6] != 0.0); }
+HD inline const double* obstacle_at(const Cfg& c, const double* op, int k, double dt, double* buf)
+{
+    if (!obstacle_is_dynamic(c, op)) return op;
+    const double t = (double)k * dt;
+    buf[0] = op[0] + t * op[5]; buf[1] = op[1] + t * op[6];
+    buf[2] = op[2] + t * op[5]; buf[3] = op[3] + t * op[6];
+    buf[4] = op[4];
+    return buf;
+}
+
 // centroid of an obstacle (teb getCentroid(): point / circle centre, segment midpoint) -- the side test of the association
 HD inline void obstacle_centroid(int obst_type, const double* op, double* cx, double* cy)
 {

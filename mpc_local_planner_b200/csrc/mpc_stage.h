@@ -317,14 +317,27 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
         {
             const int oi = (int)AOBS(j, k);
             if (oi < 0) continue;
-            double gd[3], hd[6];
+            double gd[3], hd[6], ob[5];
+            const double* op = W + L.oOBST + oi * MPCB200_OBST_STRIDE;
             const double dist = footprint_distance_sc<true, true, LINES>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
-                                                                  W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, hd);
+                                                                  obstacle_at(c, op, k, dt, ob), gd, hd);
             const double g = c.min_obstacle_dist - dist;
             const double s = AS(8 + j, k), lam = ALAM(8 + j, k);
             const double rs = 1.0 / s, r = g + s, sig = lam * rs, c0 = sig * r;
             row_stats(acc, rp, r, s, lam);
             const double gr[3] = {-gd[0], -gd[1], -gd[2]};
+            if (c.variable_dt && obstacle_is_dynamic(c, op))
+            {
+                // g = G(p - o - k dt v, theta): dg/ddt = -k grad_p g . v, d2g/dpose ddt = -k H_g v, d2g/ddt2 = k^2 v'H_g v  (H_g = -hd)
+                const double kk = (double)k, vx = op[5], vy = op[6];
+                const double gdt = -kk * (gr[0] * vx + gr[1] * vy);
+                const double hx = -(hd[0] * vx + hd[1] * vy), hy = -(hd[1] * vx + hd[3] * vy), ht = -(hd[2] * vx + hd[4] * vy);
+                hb[0] += lam * (-kk * hx) + sig * gr[0] * gdt;
+                hb[1] += lam * (-kk * hy) + sig * gr[1] * gdt;
+                hb[2] += lam * (-kk * ht) + sig * gr[2] * gdt;
+                acc.htt += lam * (kk * kk * (vx * hx + vy * hy)) + sig * gdt * gdt;
+                acc.gt0 += c0 * gdt; acc.gt1 += rs * gdt; acc.gldt += lam * gdt;
+            }
             GOG(4 * j + 0, k) = g; GOG(4 * j + 1, k) = gr[0]; GOG(4 * j + 2, k) = gr[1]; GOG(4 * j + 3, k) = gr[2];
             int q = 0;
 #pragma unroll
@@ -460,6 +473,8 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
             if (oi < 0) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
             g = GOG(4 * j + 0, k);
             gdz = GOG(4 * j + 1, k) * dx[0] + GOG(4 * j + 2, k) * dx[1] + GOG(4 * j + 3, k) * dx[2];
+            const double* op = W + L.oOBST + oi * MPCB200_OBST_STRIDE;
+            if (c.variable_dt && obstacle_is_dynamic(c, op)) gdz += -(double)k * (GOG(4 * j + 1, k) * op[5] + GOG(4 * j + 2, k) * op[6]) * ddt;
         }
         const double s = AS(sl, k), lam = ALAM(sl, k);
         const double rs = 1.0 / s;
@@ -616,8 +631,9 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
         {
             const int oi = (int)AOBS(j, k);
             if (oi < 0) continue;
+            double ob[5];
             const double dist = footprint_distance_sc<false, false, LINES>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
-                                                                    W + L.oOBST + oi * MPCB200_OBST_STRIDE, nullptr, nullptr);
+                                                                    obstacle_at(c, W + L.oOBST + oi * MPCB200_OBST_STRIDE, k, dtt, ob), nullptr, nullptr);
             const double sn = AS(8 + j, k) + alpha * ADS(8 + j, k);
             acc.inf1 += fabs(c.min_obstacle_dist - dist + sn);
             rowprod_add(rp, sn, acc.blog);
@@ -752,12 +768,15 @@ HD inline void associate_stage(const Cfg& c, const WsLayout& L, double* W, int k
         if (pass > 0 && jb < 0) continue;
         for (int j = jb; j < je; ++j)
         {
-            const double* op = W + L.oOBST + j * MPCB200_OBST_STRIDE;
+            double ob[5];
+            const double* op0 = W + L.oOBST + j * MPCB200_OBST_STRIDE;
+            const double* op = obstacle_at(c, op0, k, ASC(MPCB200_SC_DT), ob);
             double dist;
             if (pass == 0)
             {
                 dist = footprint_distance<false, false>(c, px, py, pth, (int)W[L.oOTYPE + j], op, nullptr, nullptr);
-                if (!(dist < c.force_inclusion_dist))
+                // dynamic obstacles are kept at every stage (stage_inequality_se2.cpp:99-106)
+                if (!(dist < c.force_inclusion_dist) && !obstacle_is_dynamic(c, op0))
                 {
                     if (dist > c.cutoff_dist) continue;
                     double ccx, ccy;
@@ -791,8 +810,9 @@ HD inline double stage_max_obstacle_row(const Cfg& c, const WsLayout& L, const d
     {
         const int oi = (int)AOBS(j, k);
         if (oi < 0) continue;
-        const double dist = footprint_distance<false, false>(c, px, py, AX(2, k), (int)W[L.oOTYPE + oi], W + L.oOBST + oi * MPCB200_OBST_STRIDE,
-                                                             nullptr, nullptr);
+        double ob[5];
+        const double dist = footprint_distance<false, false>(c, px, py, AX(2, k), (int)W[L.oOTYPE + oi],
+                                                             obstacle_at(c, W + L.oOBST + oi * MPCB200_OBST_STRIDE, k, ASC(MPCB200_SC_DT), ob), nullptr, nullptr);
         const double g = c.min_obstacle_dist - dist;
         if (g > m) m = g;
     }
@@ -811,8 +831,9 @@ HD inline void project_stage(const Cfg& c, const WsLayout& L, double* W, int k)
             const int oi = (int)AOBS(j, k);
             if (oi < 0) continue;
             double gd[3];
+            double ob[5];
             const double dist = footprint_distance<true, false>(c, AX(0, k), AX(1, k), AX(2, k), (int)W[L.oOTYPE + oi],
-                                                                W + L.oOBST + oi * MPCB200_OBST_STRIDE, gd, nullptr);
+                                                                obstacle_at(c, W + L.oOBST + oi * MPCB200_OBST_STRIDE, k, ASC(MPCB200_SC_DT), ob), gd, nullptr);
             const double g = c.min_obstacle_dist - dist;
             if (g <= -PROJ_MARGIN) continue;
             double gx = -gd[0], gy = -gd[1];
@@ -980,9 +1001,10 @@ HD inline void init_duals_stage(const Cfg& c, const WsLayout& L, double* W, doub
         {
             const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(sl - 8, k) : -1;
             act = oi >= 0;
+            double ob[5];
             if (act)
                 g = c.min_obstacle_dist - footprint_distance<false, false>(c, AX(0, k), AX(1, k), AX(2, k), (int)W[L.oOTYPE + oi],
-                                                                           W + L.oOBST + oi * MPCB200_OBST_STRIDE, nullptr, nullptr);
+                                                                           obstacle_at(c, W + L.oOBST + oi * MPCB200_OBST_STRIDE, k, dt, ob), nullptr, nullptr);
         }
         if (act) { s = -g > SLACK_PUSH ? -g : SLACK_PUSH; lam = mu / s; }
         AS(sl, k) = s;

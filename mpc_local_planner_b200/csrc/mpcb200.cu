@@ -804,6 +804,7 @@ extern "C" void mpcb200_default_config(mpcb200_config* c)
     c->footprint_type = MPCB200_FOOTPRINT_POINT;
     c->k_max_obstacles_per_stage = 5;
     c->max_iter = 100; c->tol = 1e-6; c->mu_init = 0.1; c->outer_iterations = 1; c->quadratic_integral_form = 0;
+    c->enable_dynamic_obstacles = 0;
     c->terminal_ball = 0; c->terminal_ball_gamma = 5.0;
     for (int i = 0; i < 9; ++i) c->terminal_ball_S[i] = (i % 4 == 0) ? 1.0 : 0.0;
 }

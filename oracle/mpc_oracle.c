@@ -438,6 +438,19 @@ static int row_active(const orc_problem* p, const orc_ws* ws, int k, int slot)
     return ws->OBSIDX[IX(slot - 8, k)] >= 0.0;
 }
 
+/* dynamic obstacle (enable_dynamic_obstacles, velocity != 0) at its predicted position of stage k */
+static int obstacle_is_dynamic(const mpcb200_config* c, const double* op) { return c->enable_dynamic_obstacles && (op[5] != 0.0 || op[6] != 0.0); }
+static const double* obstacle_at(const mpcb200_config* c, const double* op, int k, double dt, double* buf)
+{
+    if (!obstacle_is_dynamic(c, op)) return op;
+    const double t = (double)k * dt;
+    buf[0] = op[0] + t * op[5]; buf[1] = op[1] + t * op[6]; buf[2] = op[2] + t * op[5]; buf[3] = op[3] + t * op[6];
+    buf[4] = op[4]; buf[5] = op[5]; buf[6] = op[6];
+    return buf;
+}
+/* optional extra output of row_value for rows that depend on the pose AND dt (dynamic obstacles): d2g/dx ddt (3), d2g/ddt2 */
+static __thread double* g_row_hdt = NULL;
+
 /*
  * Value of inequality row (k, slot) at (X,U,dt) and, optionally, its gradient wrt the local variables
  * loc = [x_k (0..2), u_k (3..4), u_{k-1} (5..6), dt (7)] and the Hessian wrt x_k (obstacle rows only).
@@ -500,14 +513,28 @@ static double row_value(const orc_problem* p, const orc_ws* ws, int k, int slot,
         }
         return sgn * (delta - bnd * T);
     }
-    /* obstacle row: min_obstacle_dist - dist(footprint(x_k), obstacle) <= 0 */
+    /* obstacle row: min_obstacle_dist - dist(footprint(x_k), obstacle) <= 0; a dynamic obstacle is taken at its predicted
+       position at t = k dt (estimateSpatioTemporalDistance, stage_inequality_se2.cpp:177-189), which makes the row depend on dt */
     int j = (int)ws->OBSIDX[IX(slot - 8, k)];
     double pose[3] = {X[IX(0, k)], X[IX(1, k)], X[IX(2, k)]};
-    double g3[3], h6[6];
-    double d = orc_footprint_distance(c, pose, p->obst_type[j], p->obst_params + j * MPCB200_OBST_STRIDE,
-                                      grad8 ? g3 : NULL, hess6 ? h6 : NULL);
+    double g3[3], h6[6], ob[MPCB200_OBST_STRIDE];
+    const double* op = obstacle_at(c, p->obst_params + j * MPCB200_OBST_STRIDE, k, dt, ob);
+    const int dyn = op == ob;
+    double d = orc_footprint_distance(c, pose, p->obst_type[j], op, (grad8 || g_row_hdt) ? g3 : NULL, (hess6 || g_row_hdt) ? h6 : NULL);
     if (grad8) for (int i = 0; i < 3; ++i) grad8[i] = -g3[i];
     if (hess6) for (int i = 0; i < 6; ++i) hess6[i] = -h6[i];
+    if (dyn && c->variable_dt)
+    {
+        /* the distance depends on p - (o + k dt v): d/ddt = -k v . d/dp */
+        const double kk = (double)k, vx = op[5], vy = op[6];
+        if (grad8) grad8[7] = -kk * (-g3[0] * vx - g3[1] * vy);
+        if (g_row_hdt)
+        {
+            const double hx = -(h6[0] * vx + h6[1] * vy), hy = -(h6[1] * vx + h6[3] * vy), ht = -(h6[2] * vx + h6[4] * vy);
+            g_row_hdt[0] = -kk * hx; g_row_hdt[1] = -kk * hy; g_row_hdt[2] = -kk * ht; g_row_hdt[3] = kk * kk * (vx * hx + vy * hy);
+        }
+    }
+    else if (g_row_hdt) g_row_hdt[0] = g_row_hdt[1] = g_row_hdt[2] = g_row_hdt[3] = 0.0;
     return c->min_obstacle_dist - d;
 }
 
@@ -737,9 +764,12 @@ void orc_associate(const orc_problem* p, orc_ws* ws)
         double dists[64];
         for (int j = 0; j < p->n_obst; ++j)
         {
-            const double* op = p->obst_params + j * MPCB200_OBST_STRIDE;
+            double ob[MPCB200_OBST_STRIDE];
+            const double* op0 = p->obst_params + j * MPCB200_OBST_STRIDE;
+            const double* op = obstacle_at(c, op0, k, ws->SCAL[MPCB200_SC_DT], ob);
             double dist = orc_footprint_distance(c, pose, p->obst_type[j], op, NULL, NULL);
-            if (dist < c->force_inclusion_dist) { assoc_insert(ws, k, &cnt, dists, j, dist); continue; }
+            /* dynamic obstacles are kept at every stage (stage_inequality_se2.cpp:99-106) */
+            if (dist < c->force_inclusion_dist || obstacle_is_dynamic(c, op0)) { assoc_insert(ws, k, &cnt, dists, j, dist); continue; }
             if (dist > c->cutoff_dist) continue;
             /* teb getCentroid(): point / circle centre, segment midpoint; quirk 5: world coordinates, not relative to the pose */
             const int is_line = p->obst_type[j] == MPCB200_OBST_LINE;
@@ -810,7 +840,7 @@ static double stage_max_row(const orc_problem* p, orc_ws* ws, int k)
     for (int sl = 8; sl < 8 + ws->K; ++sl)
     {
         if (ws->OBSIDX[IX(sl - 8, k)] < 0.0) continue;
-        double g = row_value(p, ws, k, sl, ws->X, ws->U, 0.0, NULL, NULL);
+        double g = row_value(p, ws, k, sl, ws->X, ws->U, ws->SCAL[MPCB200_SC_DT], NULL, NULL);
         if (g > m) m = g;
     }
     return m;
@@ -833,7 +863,7 @@ void orc_project_init(const orc_problem* p, orc_ws* ws)
             {
                 if (ws->OBSIDX[IX(sl - 8, k)] < 0.0) continue;
                 double grad[8];
-                double g = row_value(p, ws, k, sl, ws->X, ws->U, 0.0, grad, NULL);
+                double g = row_value(p, ws, k, sl, ws->X, ws->U, ws->SCAL[MPCB200_SC_DT], grad, NULL);
                 if (g <= -margin) continue;
                 double n2 = grad[0] * grad[0] + grad[1] * grad[1];
                 if (n2 < 1e-16) { grad[0] = 1.0; grad[1] = 0.0; n2 = 1.0; }
@@ -1145,7 +1175,10 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
             if (!row_active(p, ws, k, sl)) { ws->G[IX(sl, k)] = 0.0; continue; }
             double grad[8], h6[6];
             const int state_row = sl >= 8 || (k == N - 1 && sl == 2); /* rows on x_k: obstacles, terminal ball */
+            double hdt[4] = {0, 0, 0, 0};
+            g_row_hdt = sl >= 8 ? hdt : NULL;
             double g = row_value(p, ws, k, sl, ws->X, ws->U, dt, grad, state_row ? h6 : NULL);
+            g_row_hdt = NULL;
             ws->G[IX(sl, k)] = g;
             double s = ws->S[IX(sl, k)], lam = ws->LAM[IX(sl, k)];
             double r = g + s, sig = lam / s;
@@ -1170,6 +1203,15 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
                 int q = 0;
                 for (int i = 0; i < 3; ++i)
                     for (int j = i; j < 3; ++j, ++q) hadd(KKT, N, k, i, j, lam * h6[q] + sig * grad[i] * grad[j]);
+                if (grad[7] != 0.0)
+                {
+                    /* dynamic obstacle with a free dt: the row also depends on dt */
+                    for (int i = 0; i < 3; ++i) KK(MPCB200_K_HB + i, k) += lam * hdt[i] + sig * grad[i] * grad[7];
+                    gt0 += c0 * grad[7];
+                    gt1 += c1 * grad[7];
+                    gl_dt += lam * grad[7];
+                    htt += lam * hdt[3] + sig * grad[7] * grad[7];
+                }
                 continue;
             }
             /* u_k part */

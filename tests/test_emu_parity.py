@@ -183,3 +183,34 @@ def test_terminal_ball_matches_oracle(orc, emu):
             assert val <= cfg.terminal_ball_gamma + 1e-7
             n_active += abs(val - cfg.terminal_ball_gamma) < 1e-6
     assert n_both >= 3 and n_active >= 1
+
+
+@pytest.mark.parametrize("free_dt", [False, True])
+def test_dynamic_obstacles_match_oracle(orc, emu, free_dt):
+    """enable_dynamic_obstacles: every obstacle moves with a constant velocity; rows use the predicted positions at t = k dt
+    (with a free dt they depend on dt as well)."""
+    cfg = configs.cfg2_integral_form(tol=1e-8) if free_dt else configs.cfg2(tol=1e-8)
+    cfg.enable_dynamic_obstacles = 1
+    B = 8
+    data = configs.with_moving_obstacles(configs.generate(2, B))
+    ref = orc.step_batch(cfg, data, n_threads=2)
+    n_both = 0
+    for b in range(B):
+        o = _oracle_init(orc, cfg, data, b)
+        e = emu.instance_from_batch(cfg, data, b)
+        e.init(); e.associate()
+        np.testing.assert_array_equal(e.field(capi.F_OBSIDX), o.arr("OBSIDX"))
+        assert (o.arr("OBSIDX")[:, 1:-1] >= 0).all()  # all (moving) obstacles are kept at every stage
+        np.testing.assert_allclose(e.field(capi.F_X), o.arr("X"), atol=1e-12)
+        o.eval(); e.eval()
+        scale = np.abs(o.arr("KKT")).max()
+        np.testing.assert_allclose(e.field(capi.F_KKT), o.arr("KKT"), atol=1e-9 * scale)
+        idx = [capi.SC_HTT, capi.SC_GT, capi.SC_ERR0]
+        np.testing.assert_allclose(e.field(capi.F_SCAL)[idx], o.arr("SCAL")[idx], rtol=1e-8, atol=1e-10)
+        st = e.solve()
+        u, x = e.outputs()
+        if st == 0 and ref["status"][b] == 0:
+            n_both += 1
+            assert abs(e.field(capi.F_SCAL)[capi.SC_DT] - ref["dt"][b]) < 1e-7
+            assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
+    assert n_both >= 2

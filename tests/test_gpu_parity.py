@@ -296,6 +296,31 @@ def test_terminal_ball(cuda_lib, orc):
     s.close()
 
 
+@pytest.mark.parametrize("free_dt", [False, True])
+def test_dynamic_obstacles(cuda_lib, orc, free_dt):
+    """enable_dynamic_obstacles through the C ABI against the oracle; with the flag off the velocities are ignored."""
+    cfg = configs.cfg2_integral_form(tol=1e-8) if free_dt else configs.cfg2(tol=1e-8)
+    cfg.enable_dynamic_obstacles = 1
+    B = 32
+    static = configs.generate(2, B)
+    data = configs.with_moving_obstacles(static)
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    s.close()
+    ref = orc.step_batch(cfg, data, n_threads=4)
+    assert (out["status"] == ref["status"]).mean() >= 0.85
+    both = (out["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= 5
+    assert np.abs(out["dt"][both] - ref["dt"][both]).max() < 1e-6
+    assert np.abs(out["u_seq"][both] - ref["u_seq"][both]).max() < U_TOL
+    cfg.enable_dynamic_obstacles = 0
+    s = _solver(cfg, B)
+    a = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    b = s.step(static["x0"], static["xf"], static["u_prev"], static["u_prev_dt"], static["obstacles"], None, reinit=np.ones(B, dtype=np.uint8))
+    s.close()
+    np.testing.assert_array_equal(a["u_seq"], b["u_seq"])
+
+
 def test_golden_cfg4_and_cfg3(cuda_lib):
     """CUDA path against the scipy fixtures of the via-point objective (cfg 4) and the car-like minimum-time problem (cfg 3, N=30)."""
     import golden_checks as gc

@@ -237,9 +237,15 @@ def test_footprint_distance_to_line_obstacle(orc, kind):
 
 
 def _random_iterate(orc, cid, b, seed):
-    cfg = configs.cfg2_integral_form(tol=1e-8) if cid == 21 else (configs.cfg2_terminal_ball(tol=1e-8) if cid == 22 else configs.config_for(cid, tol=1e-8))
-    cid = 2 if cid in (21, 22) else cid
+    """cid 21 / 22 / 23: cfg 2 with the integral-form cost + free dt / the terminal ball / moving obstacles + free dt;
+    cid 31: cfg 3 (car-like minimum time, polygon footprint) with moving obstacles"""
+    moving = cid in (23, 31)
+    cfg = configs.cfg2_integral_form(tol=1e-8) if cid in (21, 23) else (configs.cfg2_terminal_ball(tol=1e-8) if cid == 22 else configs.config_for(3 if cid == 31 else cid, tol=1e-8))
+    cid = 2 if cid in (21, 22, 23) else (3 if cid == 31 else cid)
     data = configs.g1_instance() if cid == 1 else configs.generate(cid, b + 1)
+    if moving:
+        cfg.enable_dynamic_obstacles = 1
+        data = configs.with_moving_obstacles(data)
     inst = orc.instance_from_batch(cfg, data, 0 if cid == 1 else b)
     N = inst.N
     inst.init_cold()
@@ -270,7 +276,7 @@ def _lagrangian(inst):
     return S[capi.SC_OBJ] + (inst.arr("NU")[:, :N - 1] * e).sum() + (inst.arr("LAM") * (inst.arr("G") + inst.arr("S")) * (inst.arr("LAM") > 0)).sum()
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22, 23, 31])
 def test_lagrangian_gradient_and_newton_step(orc, cid):
     """Analytic Lagrangian gradient vs finite differences; the Riccati Newton step (incl. the dt border and the fixed
     terminal state) vs a dense numpy solve of the full KKT system assembled by finite differences."""
