@@ -139,6 +139,7 @@ HD inline void lin_rows_component(const Cfg& c, const WsLayout& L, const double*
 
 // Stage functions + derivatives of stage k -> condensed KKT record (G holds the mu-independent part g0, the
 // coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
+// LINES = false compiles the rarely used obstacle kinds out (line obstacles, moving obstacles): see footprint_distance_sc
 template <bool LINES = true>
 HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G, double* Kb, double uprev_dt, int k, EvalAcc& acc)
 {
@@ -320,13 +321,13 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
             double gd[3], hd[6], ob[5];
             const double* op = W + L.oOBST + oi * MPCB200_OBST_STRIDE;
             const double dist = footprint_distance_sc<true, true, LINES>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
-                                                                  obstacle_at(c, op, k, dt, ob), gd, hd);
+                                                                  LINES ? obstacle_at(c, op, k, dt, ob) : op, gd, hd);
             const double g = c.min_obstacle_dist - dist;
             const double s = AS(8 + j, k), lam = ALAM(8 + j, k);
             const double rs = 1.0 / s, r = g + s, sig = lam * rs, c0 = sig * r;
             row_stats(acc, rp, r, s, lam);
             const double gr[3] = {-gd[0], -gd[1], -gd[2]};
-            if (c.variable_dt && obstacle_is_dynamic(c, op))
+            if (LINES && c.variable_dt && obstacle_is_dynamic(c, op))
             {
                 // g = G(p - o - k dt v, theta): dg/ddt = -k grad_p g . v, d2g/dpose ddt = -k H_g v, d2g/ddt2 = k^2 v'H_g v  (H_g = -hd)
                 const double kk = (double)k, vx = op[5], vy = op[6];
@@ -633,7 +634,8 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
             if (oi < 0) continue;
             double ob[5];
             const double dist = footprint_distance_sc<false, false, LINES>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
-                                                                    obstacle_at(c, W + L.oOBST + oi * MPCB200_OBST_STRIDE, k, dtt, ob), nullptr, nullptr);
+                                                                    LINES ? obstacle_at(c, W + L.oOBST + oi * MPCB200_OBST_STRIDE, k, dtt, ob) : W + L.oOBST + oi * MPCB200_OBST_STRIDE,
+                                                                    nullptr, nullptr);
             const double sn = AS(8 + j, k) + alpha * ADS(8 + j, k);
             acc.inf1 += fabs(c.min_obstacle_dist - dist + sn);
             rowprod_add(rp, sn, acc.blog);

@@ -765,7 +765,7 @@ struct mpcb200_handle
     cudaEvent_t poll_ev[2];
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
-    int has_lines;  // the uploaded batch contains line obstacles: the eval / line-search kernels are launched with that path compiled in
+    int has_lines;  // the uploaded batch contains line obstacles or obstacles may move: the eval / line-search kernels are launched with those paths compiled in
     double uprev_dt;
     mpcb200_stats stats;
     std::vector<cudaEvent_t> ev;  // pool of event pairs
@@ -1050,7 +1050,7 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
             if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
             lines |= obst->type[i] == MPCB200_OBST_LINE;
         }
-        h->has_lines = lines;
+        h->has_lines = lines || h->cfg.enable_dynamic_obstacles;  // the kernel variants with the rarely used obstacle kinds compiled in
         CK(cudaMemcpyAsync(h->d_obst_count, obst->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst_type, obst->type, (size_t)B * M * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst, obst->params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
