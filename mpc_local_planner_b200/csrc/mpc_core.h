@@ -29,11 +29,10 @@ struct WsLayout
 {
     int N, K, RS, M, V;      // grid points, obstacle rows per stage, row slots, max obstacles, max via-points
     int64_t stride;          // doubles per instance (multiple of 16 -> 128-byte aligned blocks)
-    int oX, oU, oNU, oS, oLAM, oKKT, oSTEP, oSTEP2, oOBS, oSCAL, oDS, oDLAM, oRIC, oVPST;
+    int oX, oU, oNU, oS, oLAM, oSTEP, oSTEP2, oOBS, oSCAL, oDS, oDLAM, oVPST;
     int oR0, oOG;            // row residuals at the current point (RS x N), obstacle row value + gradient (4K x N)
     int oIN;                 // x0(3) xf(3) u_prev(2) n_obst n_vp has_xinit reinit
     int oOBST, oOTYPE, oVP, oXINIT;
-    int ricw;                // Riccati scratch words per stage
 };
 #define IN_X0 0
 #define IN_XF 3
@@ -162,36 +161,6 @@ HD inline void dynamics_value(const Cfg& c, double th, double v, double w, doubl
 }
 
 // ---- footprint geometry ----
-struct FpSeg { double ax, ay, bx, by, rad; };
-
-HD inline int footprint_segments(const Cfg& c, FpSeg* seg)
-{
-    switch (c.footprint_type)
-    {
-        case MPCB200_FOOTPRINT_POINT: seg[0] = FpSeg{0, 0, 0, 0, 0}; return 1;
-        case MPCB200_FOOTPRINT_CIRCULAR: seg[0] = FpSeg{0, 0, 0, 0, c.footprint_params[0]}; return 1;
-        case MPCB200_FOOTPRINT_TWO_CIRCLES:
-            seg[0] = FpSeg{c.footprint_params[0], 0, c.footprint_params[0], 0, c.footprint_params[1]};
-            seg[1] = FpSeg{-c.footprint_params[2], 0, -c.footprint_params[2], 0, c.footprint_params[3]};
-            return 2;
-        case MPCB200_FOOTPRINT_LINE:
-            seg[0] = FpSeg{c.footprint_params[0], c.footprint_params[1], c.footprint_params[2], c.footprint_params[3], 0};
-            return 1;
-        default:
-        {
-            int n = c.n_poly;
-            if (n == 1) { seg[0] = FpSeg{c.poly_xy[0], c.poly_xy[1], c.poly_xy[0], c.poly_xy[1], 0}; return 1; }
-            if (n == 2) { seg[0] = FpSeg{c.poly_xy[0], c.poly_xy[1], c.poly_xy[2], c.poly_xy[3], 0}; return 1; }
-            for (int i = 0; i < n; ++i)
-            {
-                int j = (i + 1) % n;
-                seg[i] = FpSeg{c.poly_xy[2 * i], c.poly_xy[2 * i + 1], c.poly_xy[2 * j], c.poly_xy[2 * j + 1], 0};
-            }
-            return n;
-        }
-    }
-}
-
 // distance footprint(pose) <-> point/circle obstacle; optional gradient (x,y,theta) and Hessian (xx,xy,xt,yy,yt,tt)
 // LINES = false compiles the line-obstacle path out (the host knows whether a batch contains line obstacles; the hot
 // kernels are instantiated both ways so that point / circle batches do not pay its registers)

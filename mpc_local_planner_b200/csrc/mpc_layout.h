@@ -20,15 +20,13 @@ static inline void make_layout(const mpcb200_config* c, int M, int V, WsLayout& 
     L.oOBS = take((L.K > 0 ? L.K : 1) * N);
     L.oVPST = take(V > 0 ? V : 1);
     L.oVP = take((V > 0 ? V : 1) * 3);
-    L.oKKT = -1; L.oSTEP = take(8 * N);  /* KKT records and Riccati gains live in 32-instance interleaved tiles */
+    L.oSTEP = take(8 * N);  /* (KKT records and Riccati gains live in 32-instance interleaved tiles, not here) */
     L.oDS = take(L.RS * N); L.oDLAM = take(L.RS * N);
     L.oOTYPE = take(M > 0 ? M : 1);
     L.oOBST = take((M > 0 ? M : 1) * MPCB200_OBST_STRIDE);  // image ends after the obstacles in use (<= M)
     // ---- global memory only ----
     L.oSTEP2 = take(8 * N);  /* step of the speculative second KKT attempt */
     L.oR0 = take(L.RS * N); L.oOG = take(4 * (L.K > 0 ? L.K : 1) * N);
-    L.ricw = RICW_MAX;
-    L.oRIC = -1;
     L.oXINIT = take(3 * N);
     L.stride = ((int64_t)o + 15) / 16 * 16;
 }
