@@ -129,6 +129,63 @@ def test_masked_obstacle_noop(cuda_lib):
     s.close()
 
 
+def test_ragged_obstacle_counts_and_odd_batch(cuda_lib, orc):
+    """A batch that is not a multiple of the tile size, every instance with its own number of obstacles (0..5); the unused
+    slots of the fixed-stride obstacle arrays hold NaN and must never be read."""
+    cfg = configs.cfg2(tol=1e-8)
+    B = 37
+    data = configs.generate(2, B)
+    rng = np.random.default_rng(3)
+    count, types, params = (a.copy() for a in data["obstacles"])
+    count[:] = rng.integers(0, 6, size=B)
+    count[0] = 0
+    for b in range(B):
+        params[b, count[b]:] = np.nan
+    data = dict(data, obstacles=(count, types, params))
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"])
+    s.close()
+    assert np.isfinite(out["u_seq"]).all() and np.isfinite(out["kkt_err"]).all()
+    ref = orc.step_batch(cfg, data, n_threads=4)
+    assert (out["status"] == ref["status"]).mean() >= 0.9
+    both = (out["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= 15 and both[0]
+    assert np.abs(out["u_seq"][both] - ref["u_seq"][both]).max() < U_TOL
+
+
+def test_maximum_obstacle_count(cuda_lib, orc):
+    """64 obstacles per instance (the capacity of the obstacle table) with K = 5 row slots per stage."""
+    cfg = configs.cfg2(tol=1e-8)
+    B, M = 6, 64
+    base = configs.generate(2, B)
+    rng = np.random.default_rng(5)
+    count = np.full(B, M, dtype=np.int32)
+    types = np.zeros((B, M), dtype=np.int32)
+    params = np.zeros((B, M, capi.OBST_STRIDE))
+    for b in range(B):
+        goal = base["xf"][b, :2]
+        n = np.array([-goal[1], goal[0]]) / np.linalg.norm(goal)
+        for j in range(M):
+            # two rows of posts along the corridor start -> goal, 0.9 .. 1.6 m to either side
+            side = 1.0 if j % 2 == 0 else -1.0
+            params[b, j, 0:2] = goal * rng.uniform(0.05, 0.95) + side * n * rng.uniform(0.9, 1.6)
+            params[b, j, 4] = rng.uniform(0.05, 0.15)
+            types[b, j] = capi.OBST_CIRCLE
+    data = dict(base, obstacles=(count, types, params))
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"])
+    s.close()
+    ref = orc.step_batch(cfg, data, n_threads=4)
+    np.testing.assert_array_equal(out["status"], ref["status"])
+    both = out["status"] == 0
+    assert both.sum() >= 3
+    assert np.abs(out["u_seq"][both] - ref["u_seq"][both]).max() < U_TOL
+    with pytest.raises(capi.SolverError):  # 65 obstacles: over the capacity
+        s2 = _solver(cfg, B)
+        s2.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"],
+                (np.full(B, 65, dtype=np.int32), np.zeros((B, 65), dtype=np.int32), np.zeros((B, 65, capi.OBST_STRIDE))))
+
+
 def test_rigid_motion_equivariance(cuda_lib):
     """Rotating + translating the whole scene rotates the optimal path and leaves the optimal controls unchanged."""
     cfg = configs.cfg2(tol=1e-9)
