@@ -123,6 +123,12 @@ typedef struct mpcb200_config {
     /* planning/terminal_constraint (src/controller.cpp:676-709): type "l2_ball" = TerminalBallSE2, one inequality row on the
        final state, d' S d - gamma <= 0 with d = x_{N-1} - x_f (theta wrapped), final_state_conditions_se2.cpp:54-64;
        gamma is the configured `radius` passed through unchanged (controller.cpp:702-703).  Ignored when x_f is fully fixed. */
+    /* Solver-side choice of the cold initial guess (not in the reference, which starts from the straight line start -> goal,
+       full_discretization_grid_base_se2.cpp:192-239): among the 2n+1 laterally bumped lines
+       p_k + 0.4 m * sin(pi k/(N-1)) n_perp, m = -n..n, the one that violates the obstacle clearances least is taken (the
+       straight line itself whenever it is clear).  Only when no initial plan is supplied.  0 = always the straight line.
+       Default 4 ("cold initial guess"). */
+    int initial_guess_bumps;
     /* collision_avoidance/enable_dynamic_obstacles (src/controller.cpp:721-723): obstacles with a non-zero velocity are kept
        at every stage (stage_inequality_se2.cpp:99-106) and their rows use the position predicted at t = k dt with constant
        velocity (teb estimateSpatioTemporalDistance, stage_inequality_se2.cpp:177-189).  Default 0 (the reference's). */

@@ -76,6 +76,7 @@ class Config(C.Structure):
         ("mu_init", C.c_double),
         ("outer_iterations", C.c_int),
         ("quadratic_integral_form", C.c_int),
+        ("initial_guess_bumps", C.c_int),
         ("enable_dynamic_obstacles", C.c_int),
         ("terminal_ball", C.c_int),
         ("terminal_ball_S", C.c_double * 9),
@@ -132,6 +133,7 @@ def default_config():
     c.max_iter, c.tol, c.mu_init = 100, 1e-6, 0.1
     c.outer_iterations = 1
     c.quadratic_integral_form = 0
+    c.initial_guess_bumps = 4
     c.enable_dynamic_obstacles = 0
     c.terminal_ball = 0
     for i in range(9):

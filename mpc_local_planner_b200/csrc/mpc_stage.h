@@ -702,6 +702,63 @@ HD inline void init_cold_stage(const Cfg& c, const WsLayout& L, double* W, int k
     AU(1, k) = 0.0;
 }
 
+// Choice of the cold initial guess (solver-side, DESIGN.md "cold initial guess"): among the laterally bumped straight lines
+// p_k + A sin(pi k/(N-1)) n_perp, A = BUMP_STEP * m, |m| <= initial_guess_bumps, the one that violates the obstacle clearances
+// least is taken; 1e-3 |A| breaks ties.  bump_stage_violation: contribution of stage k for one candidate.
+#define BUMP_STEP 0.4
+#define BUMP_MARGIN 0.05
+HD inline bool bump_enabled(const Cfg& c, const WsLayout& L, const double* W)
+{
+    return c.initial_guess_bumps > 0 && AIN(IN_HASXINIT) == 0.0 && (int)AIN(IN_NOBST) > 0;
+}
+HD inline bool bump_normal(const WsLayout& L, const double* W, double* nx, double* ny)
+{
+    double ax = -(AIN(IN_XF + 1) - AIN(IN_X0 + 1)), ay = AIN(IN_XF) - AIN(IN_X0);
+    const double nn = sqrt(ax * ax + ay * ay);
+    if (!(nn > 1e-9)) return false;
+    *nx = ax / nn; *ny = ay / nn;
+    return true;
+}
+HD inline double bump_offset(int N, int k, double A) { return A * sin(M_PI * (double)k / (double)(N - 1)); }
+HD inline double bump_stage_violation(const Cfg& c, const WsLayout& L, const double* W, int k, double A, double nx, double ny)
+{
+    const int N = L.N;
+    if (k < 1 || k > N - 2) return 0.0;
+    const double o = bump_offset(N, k, A);
+    const double px = AX(0, k) + o * nx, py = AX(1, k) + o * ny;
+    double sn, cs;
+    sincos(AX(2, k), &sn, &cs);
+    const int nobst = (int)AIN(IN_NOBST);
+    double v = 0.0;
+    for (int j = 0; j < nobst; ++j)
+    {
+        double ob[5];
+        const double* op = obstacle_at(c, W + L.oOBST + j * MPCB200_OBST_STRIDE, k, c.dt_ref, ob);
+        const double d = footprint_distance_sc<false, false, true>(c, px, py, sn, cs, (int)W[L.oOTYPE + j], op, nullptr, nullptr);
+        const double viol = c.min_obstacle_dist + BUMP_MARGIN - d;
+        if (viol > 0.0) v += viol;
+    }
+    return v;
+}
+// candidate m is better than the best so far only beyond rounding noise: the order of the candidates decides exact ties
+HD inline bool bump_better(double score, double best) { return score < best - 1e-9 * (1.0 + best); }
+// serial form (host emulator; the CUDA kernel spreads the stages of a candidate over the lanes of the warp)
+HD inline void bump_select_serial(const Cfg& c, const WsLayout& L, double* W)
+{
+    const int N = L.N;
+    double nx, ny;
+    if (!bump_enabled(c, L, W) || !bump_normal(L, W, &nx, &ny)) return;
+    double best = 1e300, best_a = 0.0;
+    for (int m = -c.initial_guess_bumps; m <= c.initial_guess_bumps; ++m)
+    {
+        const double A = BUMP_STEP * (double)m;
+        double score = 1e-3 * fabs(A);
+        for (int k = 1; k <= N - 2; ++k) score += bump_stage_violation(c, L, W, k, A, nx, ny);
+        if (bump_better(score, best)) { best = score; best_a = A; }
+    }
+    for (int k = 1; k <= N - 2; ++k) { const double o = bump_offset(N, k, best_a); AX(0, k) += o * nx; AX(1, k) += o * ny; }
+}
+
 // warm start shift (serial; run by one lane): FullDiscretizationGridBaseSE2::warmStartShifting + findNearestState
 HD inline void warm_shift_serial(const Cfg& c, const WsLayout& L, double* W)
 {

@@ -96,6 +96,23 @@ __global__ void init_kernel(Cfg c, WsLayout L, double* ws, int B, int force_cold
     if (cold)
     {
         for (int k = lane; k < N; k += 32) init_cold_stage(c, L, W, k);
+        __syncwarp();
+        double nx, ny;
+        if (bump_enabled(c, L, W) && bump_normal(L, W, &nx, &ny))
+        {
+            // choice of the cold initial guess: candidates one after the other, their stages spread over the lanes
+            double best = 1e300, best_a = 0.0;
+            for (int m = -c.initial_guess_bumps; m <= c.initial_guess_bumps; ++m)
+            {
+                const double A = BUMP_STEP * (double)m;
+                double v = 0.0;
+                for (int k = lane; k < N; k += 32) v += bump_stage_violation(c, L, W, k, A, nx, ny);
+                const double score = 1e-3 * fabs(A) + warp_sum(v);
+                if (bump_better(score, best)) { best = score; best_a = A; }
+            }
+            for (int k = lane; k < N; k += 32)
+                if (k >= 1 && k <= N - 2) { const double o = bump_offset(N, k, best_a); AX(0, k) += o * nx; AX(1, k) += o * ny; }
+        }
         if (lane == 0) { ASC(MPCB200_SC_DT) = c.dt_ref; ASC(MPCB200_SC_COLD) = 2.0; /* 2: cold init done, repair pending */ }
     }
     else
@@ -804,6 +821,7 @@ extern "C" void mpcb200_default_config(mpcb200_config* c)
     c->footprint_type = MPCB200_FOOTPRINT_POINT;
     c->k_max_obstacles_per_stage = 5;
     c->max_iter = 100; c->tol = 1e-6; c->mu_init = 0.1; c->outer_iterations = 1; c->quadratic_integral_form = 0;
+    c->initial_guess_bumps = 4;
     c->enable_dynamic_obstacles = 0;
     c->terminal_ball = 0; c->terminal_ball_gamma = 5.0;
     for (int i = 0; i < 9; ++i) c->terminal_ball_S[i] = (i % 4 == 0) ? 1.0 : 0.0;

@@ -638,6 +638,36 @@ void orc_ws_free(orc_ws* ws)
  * Controller::step(start, goal, ...) [R/src/controller.cpp:102-109,807-857] is sampled: linear in time with
  * TimeSeriesSE2's angle-aware interpolation [R/src/utils/time_series_se2.cpp:86-102].
  */
+/*
+ * Cold initial guess: linear interpolation start -> goal (FullDiscretizationGridBaseSE2::initializeSequences,
+ * full_discretization_grid_base_se2.cpp:192-239) or the supplied initial plan.  Solver-side addition (not in the
+ * reference): without an initial plan, the straight line is replaced by the laterally bumped line
+ *     p_k + A sin(pi k/(N-1)) n_perp,  A = ORC_BUMP_STEP * m,  m = -initial_guess_bumps .. initial_guess_bumps,
+ * that violates the obstacle clearances (d_min + margin, all obstacles, all interior stages) least; |A| breaks ties, so a
+ * clear straight line stays.  A locally convergent method inherits the homotopy class of its starting point: with the
+ * straight line 40 % of the SURVEY-8d instances end in an infeasible stationary point squeezed between obstacles.
+ */
+#define ORC_BUMP_STEP 0.4
+#define ORC_BUMP_MARGIN 0.05
+static double bump_score(const orc_problem* p, const orc_ws* ws, double A, double nx, double ny)
+{
+    const mpcb200_config* c = p->cfg;
+    const int N = ws->N;
+    double score = 1e-3 * fabs(A);
+    for (int k = 1; k <= N - 2; ++k)
+    {
+        const double o = A * sin(M_PI * (double)k / (double)(N - 1));
+        const double pose[3] = {ws->X[IX(0, k)] + o * nx, ws->X[IX(1, k)] + o * ny, ws->X[IX(2, k)]};
+        for (int j = 0; j < p->n_obst; ++j)
+        {
+            double ob[MPCB200_OBST_STRIDE];
+            const double* op = obstacle_at(c, p->obst_params + j * MPCB200_OBST_STRIDE, k, c->dt_ref, ob);
+            const double v = c->min_obstacle_dist + ORC_BUMP_MARGIN - orc_footprint_distance(c, pose, p->obst_type[j], op, NULL, NULL);
+            if (v > 0.0) score += v;
+        }
+    }
+    return score;
+}
 void orc_init_cold(const orc_problem* p, const double* x_init, orc_ws* ws)
 {
     const int N = ws->N;
@@ -666,6 +696,30 @@ void orc_init_cold(const orc_problem* p, const double* x_init, orc_ws* ws)
         ws->U[IX(1, k)] = 0.0;
     }
     ws->SCAL[MPCB200_SC_DT] = p->cfg->dt_ref;
+    const int nb = p->cfg->initial_guess_bumps;
+    if (!x_init && nb > 0 && p->n_obst > 0)
+    {
+        double nx = -(p->xf[1] - p->x0[1]), ny = p->xf[0] - p->x0[0];
+        const double nn = sqrt(nx * nx + ny * ny);
+        if (nn > 1e-9)
+        {
+            nx /= nn; ny /= nn;
+            double best = 1e300, best_a = 0.0;
+            for (int m = -nb; m <= nb; ++m)
+            {
+                const double A = ORC_BUMP_STEP * (double)m;
+                const double score = bump_score(p, ws, A, nx, ny);
+                /* strictly better beyond rounding noise: the order of the candidates decides exact ties (symmetric scenes) */
+                if (score < best - 1e-9 * (1.0 + best)) { best = score; best_a = A; }
+            }
+            for (int k = 1; k <= N - 2; ++k)
+            {
+                const double o = best_a * sin(M_PI * (double)k / (double)(N - 1));
+                ws->X[IX(0, k)] += o * nx;
+                ws->X[IX(1, k)] += o * ny;
+            }
+        }
+    }
 }
 
 /*

@@ -82,6 +82,7 @@ void emu_init(const Cfg* cp, double* W, int force_cold)
     if (cold)
     {
         for (int k = 0; k < N; ++k) init_cold_stage(c, L, W, k);
+        bump_select_serial(c, L, W);
         ASC(MPCB200_SC_DT) = c.dt_ref;
         ASC(MPCB200_SC_COLD) = 2.0;
     }
