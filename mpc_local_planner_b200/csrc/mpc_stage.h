@@ -740,6 +740,13 @@ HD inline double bump_stage_violation(const Cfg& c, const WsLayout& L, const dou
     }
     return v;
 }
+// car-like models cannot turn on the spot: on a bumped line their headings follow the path (central differences of the positions)
+HD inline bool bump_align_headings(const Cfg& c, double A) { return A != 0.0 && c.robot_type != MPCB200_ROBOT_UNICYCLE; }
+HD inline double bump_heading(const WsLayout& L, const double* W, int k)
+{
+    const int N = L.N;
+    return atan2(AX(1, k + 1) - AX(1, k - 1), AX(0, k + 1) - AX(0, k - 1));
+}
 // candidate m is better than the best so far only beyond rounding noise: the order of the candidates decides exact ties
 HD inline bool bump_better(double score, double best) { return score < best - 1e-9 * (1.0 + best); }
 // serial form (host emulator; the CUDA kernel spreads the stages of a candidate over the lanes of the warp)
@@ -757,6 +764,8 @@ HD inline void bump_select_serial(const Cfg& c, const WsLayout& L, double* W)
         if (bump_better(score, best)) { best = score; best_a = A; }
     }
     for (int k = 1; k <= N - 2; ++k) { const double o = bump_offset(N, k, best_a); AX(0, k) += o * nx; AX(1, k) += o * ny; }
+    if (bump_align_headings(c, best_a))
+        for (int k = 1; k <= N - 2; ++k) AX(2, k) = bump_heading(L, W, k);
 }
 
 // warm start shift (serial; run by one lane): FullDiscretizationGridBaseSE2::warmStartShifting + findNearestState

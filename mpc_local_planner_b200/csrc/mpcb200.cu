@@ -112,6 +112,10 @@ __global__ void init_kernel(Cfg c, WsLayout L, double* ws, int B, int force_cold
             }
             for (int k = lane; k < N; k += 32)
                 if (k >= 1 && k <= N - 2) { const double o = bump_offset(N, k, best_a); AX(0, k) += o * nx; AX(1, k) += o * ny; }
+            __syncwarp();
+            if (bump_align_headings(c, best_a))
+                for (int k = lane; k < N; k += 32)
+                    if (k >= 1 && k <= N - 2) AX(2, k) = bump_heading(L, W, k);
         }
         if (lane == 0) { ASC(MPCB200_SC_DT) = c.dt_ref; ASC(MPCB200_SC_COLD) = 2.0; /* 2: cold init done, repair pending */ }
     }

@@ -718,6 +718,10 @@ void orc_init_cold(const orc_problem* p, const double* x_init, orc_ws* ws)
                 ws->X[IX(0, k)] += o * nx;
                 ws->X[IX(1, k)] += o * ny;
             }
+            /* car-like models cannot turn on the spot: on a bumped line their headings follow the path (central differences) */
+            if (best_a != 0.0 && p->cfg->robot_type != MPCB200_ROBOT_UNICYCLE)
+                for (int k = 1; k <= N - 2; ++k)
+                    ws->X[IX(2, k)] = atan2(ws->X[IX(1, k + 1)] - ws->X[IX(1, k - 1)], ws->X[IX(0, k + 1)] - ws->X[IX(0, k - 1)]);
         }
     }
 }
