@@ -344,6 +344,11 @@ def test_lagrangian_gradient_and_newton_step(orc, cid):
         if (ev > 0).sum() != nf or (ev < 0).sum() != m:
             assert rc == 1  # wrong inertia must be detected
             continue
+        if rc == 1 and any(cfg.xf_fixed[i] for i in range(3)):
+            # the Riccati pivot test is sufficient, not necessary, when terminal components are fixed: it asks for positive
+            # curvature before the terminal constraint is imposed (the constraint enters through the multiplier block at the
+            # root); a conservative "wrong inertia" only costs a regularised step
+            continue
         assert rc == 0
         sol = np.linalg.solve(Kmat, np.concatenate([-gt[free], -e]))
         STEP = inst.arr("STEP"); ddt = inst.arr("SCAL")[capi.SC_DDT]
