@@ -114,7 +114,8 @@ typedef struct mpcb200_config {
     /* solver (src/controller.cpp:380-421): the interior-point method replaces Ipopt */
     int max_iter;          /* solver/ipopt/iterations (100) */
     double tol;            /* scaled KKT error tolerance; "converged" <=> error <= tol */
-    double mu_init;        /* initial barrier parameter (Ipopt default 0.1) */
+    double mu_init;        /* initial barrier parameter; > 0: as given (Ipopt's mu_init, default there 0.1); 0 (default): chosen per
+                              instance, |f(x_0)| / #rows clamped to [0.1, 1] ("initial barrier parameter") */
     int outer_iterations;  /* controller/outer_ocp_iterations */
     /* planning/objective/quadratic_form/integral_form (src/controller.cpp:593-594): the running cost enters as
        sum_k dt * l(x_k, u_k) (grid/cost_integration_method left_sum, finite_differences_grid_se2.cpp:66-70; the

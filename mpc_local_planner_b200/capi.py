@@ -130,7 +130,7 @@ def default_config():
     c.footprint_type = FOOTPRINT_POINT
     c.n_poly = 0
     c.k_max_obstacles_per_stage = 5
-    c.max_iter, c.tol, c.mu_init = 100, 1e-6, 0.1
+    c.max_iter, c.tol, c.mu_init = 100, 1e-6, 0.0
     c.outer_iterations = 1
     c.quadratic_integral_form = 0
     c.initial_guess_bumps = 4

@@ -551,6 +551,59 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
     }
 }
 
+// objective contribution of stage k at (x, u, dt): quadratic running cost (k <= N-2; dt-weighted in integral form), terminal
+// cost and minimum-time term (k = N-1), via-points attached to the stage.  u is read for k <= N-2 only.
+HD inline double stage_objective(const Cfg& c, const WsLayout& L, const double* W, int k, const double* x, const double* u, double dtt)
+{
+    const int N = L.N;
+    const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
+    double obj = 0.0;
+    if (k <= N - 2)
+    {
+        if (has_quadratic(c))
+        {
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double o = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) o += d[i] * c.Q[i * 3 + j] * d[j];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) o += u[i] * c.R[i * 2 + j] * u[j];
+            obj += (c.quadratic_integral_form ? dtt : 1.0) * o;
+        }
+    }
+    else
+    {
+        if (has_mintime(c)) obj += (double)(N - 1) * dtt;
+        if (has_terminal_cost(c))
+        {
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double o = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) o += d[i] * c.Qf[i * 3 + j] * d[j];
+            obj += o;
+        }
+    }
+    if (has_viapoints(c) && k >= 1 && k <= N - 2)
+    {
+        const int nvp = (int)AIN(IN_NVP);
+        for (int j = 0; j < nvp && j < L.V; ++j)
+        {
+            if ((int)W[L.oVPST + j] != k) continue;
+            const double ex = W[L.oVP + 3 * j] - x[0], ey = W[L.oVP + 3 * j + 1] - x[1];
+            obj += c.vp_position_weight * (ex * ex + ey * ey);
+            if (c.vp_orientation_weight > 0)
+                obj += c.vp_orientation_weight * normalize_theta(W[L.oVP + 3 * j + 2] - x[2]);
+        }
+    }
+    return obj;
+}
+
 struct TrialAcc { double obj, inf1, blog; };
 // merit pieces of stage k at the trial point z + alpha dz, s + alpha ds.  Linear rows are exact in alpha:
 // g(alpha) + s(alpha) = (1 - alpha) r0, so only the dynamics defect, the objective and the obstacle rows are re-evaluated.
@@ -578,47 +631,9 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
                               AX(2, k + 1) + alpha * ASTEP(2, k + 1)};
         acc.inf1 += fabs(x[0] + dtt * f[0] - xn[0]) + fabs(x[1] + dtt * f[1] - xn[1]) +
                     fabs(dtt * f[2] - normalize_theta(xn[2] - x[2]));
-        if (has_quadratic(c))
-        {
-            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
-            double o = 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) o += d[i] * c.Q[i * 3 + j] * d[j];
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) o += u[i] * c.R[i * 2 + j] * u[j];
-            acc.obj += (c.quadratic_integral_form ? dtt : 1.0) * o;
-        }
+        acc.obj += stage_objective(c, L, W, k, x, u, dtt);
     }
-    else
-    {
-        if (has_mintime(c)) acc.obj += (double)(N - 1) * dtt;
-        if (has_terminal_cost(c))
-        {
-            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
-            double o = 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) o += d[i] * c.Qf[i * 3 + j] * d[j];
-            acc.obj += o;
-        }
-    }
-    if (has_viapoints(c) && k >= 1 && k <= N - 2)
-    {
-        const int nvp = (int)AIN(IN_NVP);
-        for (int j = 0; j < nvp && j < L.V; ++j)
-        {
-            if ((int)W[L.oVPST + j] != k) continue;
-            const double ex = W[L.oVP + 3 * j] - x[0], ey = W[L.oVP + 3 * j + 1] - x[1];
-            acc.obj += c.vp_position_weight * (ex * ex + ey * ey);
-            if (c.vp_orientation_weight > 0)
-                acc.obj += c.vp_orientation_weight * normalize_theta(W[L.oVP + 3 * j + 2] - x[2]);
-        }
-    }
+    else acc.obj += stage_objective(c, L, W, k, x, nullptr, dtt);
     RowProd rp; rp.p = 1.0; rp.n = 0;
     const double oma = 1.0 - alpha;
     for (int sl = 0; sl < 8; ++sl)
@@ -1036,6 +1051,31 @@ HD inline void clip_rates_serial(const Cfg& c, const WsLayout& L, double* W, dou
             next = AU(i, k);
         }
     }
+}
+
+// Automatic initial barrier parameter (mu_init <= 0): the barrier has one term per inequality row; it is balanced against the
+// objective at the initial guess, mu_0 = |f(x_0)| / m clamped to [MU_AUTO_MIN, MU_AUTO_MAX] (0.1 = Ipopt's mu_init).
+// auto_mu_stage: objective value and number of active rows of stage k.
+#define MU_AUTO_MIN 0.1
+#define MU_AUTO_MAX 1.0
+HD inline void auto_mu_stage(const Cfg& c, const WsLayout& L, const double* W, double uprev_dt, int k, double* obj, double* rows)
+{
+    const int N = L.N, K = L.K;
+    const double x[3] = {AX(0, k), AX(1, k), AX(2, k)};
+    const double u[2] = {k <= N - 2 ? AU(0, k) : 0.0, k <= N - 2 ? AU(1, k) : 0.0};
+    *obj += stage_objective(c, L, W, k, x, u, ASC(MPCB200_SC_DT));
+    int m = 0;
+    for (int sl = 0; sl < 8; ++sl) m += lin_row_active(c, N, k, sl, uprev_dt) || (sl == BALL_SLOT && k == N - 1 && ball_active(c));
+    if (k >= 1 && k <= N - 2)
+        for (int j = 0; j < K; ++j) m += AOBS(j, k) >= 0.0;
+    *rows += (double)m;
+}
+HD inline double auto_mu(double obj, double rows)
+{
+    double mu = rows > 0.0 ? fabs(obj) / rows : MU_AUTO_MIN;
+    if (mu < MU_AUTO_MIN) mu = MU_AUTO_MIN;
+    if (mu > MU_AUTO_MAX) mu = MU_AUTO_MAX;
+    return mu;
 }
 
 // slack / multiplier initialisation of stage k

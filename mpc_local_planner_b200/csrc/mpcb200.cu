@@ -215,7 +215,13 @@ __global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double up
         if (lane == 0) clip_rates_serial(c, L, W, uprev_dt);
         __syncwarp();
     }
-    const double mu = c.mu_init > 0 ? c.mu_init : 0.1;
+    double mu = c.mu_init;
+    if (!(mu > 0.0))
+    {
+        double obj = 0.0, rows = 0.0;
+        for (int k = lane; k < N; k += 32) auto_mu_stage(c, L, W, uprev_dt, k, &obj, &rows);
+        mu = auto_mu(warp_sum(obj), warp_sum(rows));
+    }
     for (int k = lane; k < N; k += 32) init_duals_stage(c, L, W, uprev_dt, k, mu);
     __syncwarp();
     if (lane == 0)
@@ -824,7 +830,7 @@ extern "C" void mpcb200_default_config(mpcb200_config* c)
     c->min_obstacle_dist = 0.5; c->force_inclusion_dist = 0.5; c->cutoff_dist = 2.0;
     c->footprint_type = MPCB200_FOOTPRINT_POINT;
     c->k_max_obstacles_per_stage = 5;
-    c->max_iter = 100; c->tol = 1e-6; c->mu_init = 0.1; c->outer_iterations = 1; c->quadratic_integral_form = 0;
+    c->max_iter = 100; c->tol = 1e-6; c->mu_init = 0.0; c->outer_iterations = 1; c->quadratic_integral_form = 0;
     c->initial_guess_bumps = 4;
     c->enable_dynamic_obstacles = 0;
     c->terminal_ball = 0; c->terminal_ball_gamma = 5.0;

@@ -1030,6 +1030,8 @@ void orc_init_controls(const orc_problem* p, orc_ws* ws)
 /* Part 2: interior-point method                                                                            */
 /* ======================================================================================================= */
 
+#define ORC_MU_AUTO_MIN 0.1
+#define ORC_MU_AUTO_MAX 1.0
 #define ORC_KAPPA_EPS 10.0
 #define ORC_KAPPA_MU 0.2
 #define ORC_THETA_MU 1.5
@@ -1050,7 +1052,20 @@ void orc_init_duals(const orc_problem* p, orc_ws* ws)
 {
     const int N = ws->N, RS = ws->RS;
     double dt = ws->SCAL[MPCB200_SC_DT];
-    double mu = p->cfg->mu_init > 0 ? p->cfg->mu_init : 0.1;
+    double mu = p->cfg->mu_init;
+    if (!(mu > 0.0))
+    {
+        /* automatic initial barrier parameter: the barrier mu * sum(ln s) has one term per inequality row; it is balanced
+           against the objective at the initial guess, mu_0 = |f(x_0)| / m clamped to [0.1, 1] (0.1 = Ipopt's mu_init).
+           Quadratic-form problems (f ~ 10^3) start at 1, minimum-time problems (f ~ 10^1) at 0.1. */
+        int m = 0;
+        for (int k = 0; k < N; ++k)
+            for (int sl = 0; sl < RS; ++sl) m += row_active(p, ws, k, sl);
+        const double f0 = fabs(orc_objective(p, ws, ws->X, ws->U, dt));
+        mu = m > 0 ? f0 / (double)m : ORC_MU_AUTO_MIN;
+        if (mu < ORC_MU_AUTO_MIN) mu = ORC_MU_AUTO_MIN;
+        if (mu > ORC_MU_AUTO_MAX) mu = ORC_MU_AUTO_MAX;
+    }
     for (int k = 0; k < N; ++k)
     {
         for (int sl = 0; sl < RS; ++sl)

@@ -140,7 +140,13 @@ void emu_associate(const Cfg* cp, double* W, double uprev_dt, int first_outer)
         for (int k = 0; k < N; ++k) init_controls_stage(c, L, W, k);
         clip_rates_serial(c, L, W, uprev_dt);
     }
-    const double mu = c.mu_init > 0 ? c.mu_init : 0.1;
+    double mu = c.mu_init;
+    if (!(mu > 0.0))
+    {
+        double obj = 0.0, rows = 0.0;
+        for (int k = 0; k < N; ++k) auto_mu_stage(c, L, W, uprev_dt, k, &obj, &rows);
+        mu = auto_mu(obj, rows);
+    }
     for (int k = 0; k < N; ++k) init_duals_stage(c, L, W, uprev_dt, k, mu);
     ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
     ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
