@@ -311,7 +311,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "kkt_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            ratio = json.load(open(tp)).get("traffic_over_algorithmic")
+            traffic = int(ratio * units * bpi / kkt_launches) if ratio else None  # DRAM bytes of the average launch (ncu ratio x algorithmic)
         except Exception:
             traffic = None
     total_ms = el / args.steps * 1e3 * args.steps
