@@ -283,14 +283,27 @@ def main():
     st1 = solver.stats()
     conv_e2e = int((out["status"] == 0).sum())
 
+    # ---- continuous batching: the K steps' instances as ONE queue through the same 1024-slot pool (mpcb200_solve_stream),
+    #      host buffers in, host buffers out.  Reported next to the per-batch numbers, not instead of them. ----
+    reps = args.steps
+    tile = lambda a: np.ascontiguousarray(np.concatenate([a] * reps))
+    q = dict(x0=tile(data["x0"]), xf=tile(data["xf"]), u_prev=tile(data["u_prev"]), obstacles=tuple(tile(a) for a in data["obstacles"]))
+    def stream_job():
+        return solver.solve_stream(q["x0"], q["xf"], q["u_prev"], data["u_prev_dt"], q["obstacles"], None)
+    with torch.cuda.stream(stream):
+        solver.solve_stream(q["x0"][: 2 * B], q["xf"][: 2 * B], q["u_prev"][: 2 * B], data["u_prev_dt"], tuple(a[: 2 * B] for a in q["obstacles"]), None)
+    torch.cuda.synchronize()
+    el_stream, sout = timed(stream_job, 1)
+    conv_stream = int((sout["status"] == 0).sum())
+
     # ---- max over ranks / totals ----
     if dist is not None:
-        t = torch.tensor([el, el_e2e], dtype=torch.float64, device=f"cuda:{dev}")
+        t = torch.tensor([el, el_e2e, el_stream], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        el, el_e2e = float(t[0]), float(t[1])
-        c = torch.tensor([conv_local, conv_e2e], dtype=torch.float64, device=f"cuda:{dev}")
+        el, el_e2e, el_stream = float(t[0]), float(t[1]), float(t[2])
+        c = torch.tensor([conv_local, conv_e2e, conv_stream], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        conv_total, conv_e2e_total = int(c[0]), int(c[1])
+        conv_total, conv_e2e_total, conv_stream = int(c[0]), int(c[1]), int(c[2])
     else:
         conv_total, conv_e2e_total = conv_local, conv_e2e
     if rank != 0:
@@ -333,6 +346,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps,
                 "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps},
+        "streaming": {"value": conv_stream / el_stream, "unit": UNIT, "queue_per_gpu": reps * B, "pool_slots_per_gpu": B,
+                      "ms_per_1024": el_stream / reps * 1e3,
+                      "what": "the same K x 1024 instances per GPU as ONE queue through the 1024-slot pool (mpcb200_solve_stream, "
+                              "continuous batching: a finished slot takes the next instance), host buffers in and out; per-instance "
+                              "results are bit-identical to the batch solves"},
         "gpu_launches": int(st["launches_total"]),
         "kernel_ms": dict(zip(["init", "associate", "eval", "kkt", "linesearch"], st_all["ms"])),
         "timing": "CUDA events on the work stream around the K steps (max over ranks); kernel_ms from one extra step with all phases bracketed",

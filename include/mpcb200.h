@@ -184,6 +184,19 @@ int mpcb200_step_batch(mpcb200_handle* h, int B, const double* x0, const double*
                        const double* x_init, const unsigned char* reinit, double* u_seq, double* x_seq,
                        double* dt_out, int* status, double* kkt_err, int* iters, double* solve_time_s);
 
+/*
+ * The same solves for a QUEUE of `total` instances (total may exceed max_batch by any factor): the handle's max_batch
+ * workspaces form a pool of slots, and a slot whose instance has finished hands its result over and takes the next
+ * instance of the queue while the other slots keep iterating (continuous batching).  The interior-point iterations of
+ * different instances are independent, so every instance gets exactly the result mpcb200_step_batch would give it from a
+ * cold start; what changes is the cost: a batch pays max-over-instances iterations, the pool pays the mean.
+ * Arrays as in mpcb200_step_batch with B = total; always a cold start, no x_init / reinit; outer_iterations must be 1.
+ * Afterwards the handle is in the state after mpcb200_reset.
+ */
+int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                         const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, double* u_seq, double* x_seq, double* dt_out,
+                         int* status, double* kkt_err, int* iters, double* solve_time_s);
+
 /* Replaces Controller::reset (inc/controller.h:104): which == NULL resets every instance, else those with which[b] != 0. */
 int mpcb200_reset(mpcb200_handle* h, const unsigned char* which, int B);
 
@@ -262,6 +275,7 @@ int mpcb200_flush_l2(mpcb200_handle* h);
 #define MPCB200_SC_KKT_OK1 23
 #define MPCB200_SC_DELTA1 24  /* ... regularisation and d(dt) of attempt 1 (attempt 0 uses SC_DELTA / SC_DDT) */
 #define MPCB200_SC_DDT1 25
+#define MPCB200_SC_NEW 26     /* streaming: the slot was just refilled, init / associate pending */
 #define MPCB200_SC_DEFER 21  /* 1 = the KKT phase spent its factorisation budget: null step, regularisation resumes next iteration */
 #define MPCB200_SC_TINY 20   /* consecutive iterations with a step length below 1e-8 (2 => the instance is given up) */
 

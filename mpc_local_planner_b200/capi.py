@@ -174,7 +174,7 @@ EXPORTS = [
     "mpcb200_default_config", "mpcb200_create", "mpcb200_step_batch", "mpcb200_reset", "mpcb200_destroy",
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
-    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
+    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
 ]
 
 
@@ -196,6 +196,8 @@ def load_library(path=None):
     lib.mpcb200_create.argtypes = [C.POINTER(Config), C.c_int, C.c_int, C.POINTER(vp)]
     lib.mpcb200_step_batch.argtypes = [vp, C.c_int, dp, dp, dp, C.c_double, C.POINTER(Obstacles), C.POINTER(ViaPoints),
                                        dp, ucp, dp, dp, dp, ip, dp, ip, dp]
+    lib.mpcb200_solve_stream.argtypes = [vp, C.c_int, dp, dp, dp, C.c_double, C.POINTER(Obstacles), C.POINTER(ViaPoints),
+                                         dp, dp, dp, ip, dp, ip, dp]
     lib.mpcb200_reset.argtypes = [vp, ucp, C.c_int]
     lib.mpcb200_destroy.argtypes = [vp]
     lib.mpcb200_destroy.restype = None
@@ -278,6 +280,20 @@ class BatchSolver:
             xi = np.ascontiguousarray(x_init, dtype=np.float64)
             keep.append(xi)
         return B, x0, xf, u_prev, o, v, xi, keep
+
+    def solve_stream(self, x0, xf, u_prev=None, u_prev_dt=0.0, obstacles=None, viapoints=None):
+        """A queue of len(x0) instances (any number) through the pool of max_batch slots: continuous batching, cold starts."""
+        T, x0, xf, u_prev, o, v, xi, keep = self._prep_inputs(x0, xf, u_prev, obstacles, viapoints, None)
+        N = self.N
+        out = dict(u_seq=np.empty((T, N, 2)), x_seq=np.empty((T, N, 3)), dt=np.empty(T),
+                   status=np.empty(T, dtype=np.int32), kkt_err=np.empty(T), iters=np.empty(T, dtype=np.int32))
+        t = C.c_double(0.0)
+        rc = self.lib.mpcb200_solve_stream(
+            self.h, T, _dp(x0), _dp(xf), _dp(u_prev), float(u_prev_dt), C.byref(o) if o else None, C.byref(v) if v else None,
+            _dp(out["u_seq"]), _dp(out["x_seq"]), _dp(out["dt"]), _ip(out["status"]), _dp(out["kkt_err"]), _ip(out["iters"]), C.byref(t))
+        self._check(rc, "mpcb200_solve_stream")
+        out["solve_time_s"] = t.value
+        return out
 
     def step(self, x0, xf, u_prev=None, u_prev_dt=0.0, obstacles=None, viapoints=None, x_init=None, reinit=None):
         """Controller::step for a batch (host arrays in, host arrays out; copies inside the call)."""

@@ -58,39 +58,44 @@ struct InputPtrs
     const unsigned char* reinit;                                   // [B] or null
 };
 
-// ---- kernel: scatter the compact input arrays into the instance blocks -------------------------------------
-__global__ void scatter_inputs_kernel(WsLayout L, double* ws, int B, InputPtrs in)
+// ---- scatter the compact input arrays into an instance block (inputs of instance `src` into the block W) -------
+__device__ __forceinline__ void scatter_one(const WsLayout& L, double* W, const InputPtrs& in, int64_t src, int lane)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
-    if (lane < 3) { AIN(IN_X0 + lane) = in.x0[warp * 3 + lane]; AIN(IN_XF + lane) = in.xf[warp * 3 + lane]; }
-    if (lane < 2) AIN(IN_UPREV + lane) = in.u_prev ? in.u_prev[warp * 2 + lane] : 0.0;
+    if (lane < 3) { AIN(IN_X0 + lane) = in.x0[src * 3 + lane]; AIN(IN_XF + lane) = in.xf[src * 3 + lane]; }
+    if (lane < 2) AIN(IN_UPREV + lane) = in.u_prev ? in.u_prev[src * 2 + lane] : 0.0;
     int nob = 0, nvp = 0;
-    if (in.obst_count) nob = min(in.obst_count[warp], min(in.obst_max, L.M));
-    if (in.vp_count) nvp = min(in.vp_count[warp], min(in.vp_max, L.V));
+    if (in.obst_count) nob = min(in.obst_count[src], min(in.obst_max, L.M));
+    if (in.vp_count) nvp = min(in.vp_count[src], min(in.vp_max, L.V));
     if (lane == 0)
     {
         AIN(IN_NOBST) = (double)nob; AIN(IN_NVP) = (double)nvp;
         AIN(IN_HASXINIT) = in.x_init ? 1.0 : 0.0;
-        AIN(IN_REINIT) = (in.reinit && in.reinit[warp]) ? 1.0 : 0.0;
+        AIN(IN_REINIT) = (in.reinit && in.reinit[src]) ? 1.0 : 0.0;
     }
     for (int i = lane; i < nob * MPCB200_OBST_STRIDE; i += 32)
-        W[L.oOBST + i] = in.obst_params[(int64_t)warp * in.obst_max * MPCB200_OBST_STRIDE + i];
-    for (int i = lane; i < nob; i += 32) W[L.oOTYPE + i] = (double)in.obst_type[(int64_t)warp * in.obst_max + i];
-    for (int i = lane; i < nvp * 3; i += 32) W[L.oVP + i] = in.vp_poses[(int64_t)warp * in.vp_max * 3 + i];
+        W[L.oOBST + i] = in.obst_params[src * in.obst_max * MPCB200_OBST_STRIDE + i];
+    for (int i = lane; i < nob; i += 32) W[L.oOTYPE + i] = (double)in.obst_type[src * in.obst_max + i];
+    for (int i = lane; i < nvp * 3; i += 32) W[L.oVP + i] = in.vp_poses[src * in.vp_max * 3 + i];
     if (in.x_init)
-        for (int i = lane; i < 3 * N; i += 32) W[L.oXINIT + i] = in.x_init[(int64_t)warp * 3 * N + i];
+        for (int i = lane; i < 3 * N; i += 32) W[L.oXINIT + i] = in.x_init[src * 3 * N + i];
+}
+
+__global__ void scatter_inputs_kernel(WsLayout L, double* ws, int B, InputPtrs in)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    scatter_one(L, ws + (int64_t)warp * L.stride, in, warp, lane);
 }
 
 // ---- kernel: PHASE_INIT -- cold initial guess or warm-start shift ------------------------------------------
-__global__ void init_kernel(Cfg c, WsLayout L, double* ws, int B, int force_cold)
+__global__ void init_kernel(Cfg c, WsLayout L, double* ws, int B, int force_cold, int only_new)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
+    if (only_new && ASC(MPCB200_SC_NEW) == 0.0) return;  // streaming: only the slots that were just refilled
     const bool cold = force_cold || ASC(MPCB200_SC_COLD) != 0.0 || AIN(IN_REINIT) != 0.0;
     __syncwarp();
     if (cold)
@@ -136,12 +141,13 @@ __global__ void init_kernel(Cfg c, WsLayout L, double* ws, int B, int force_cold
 }
 
 // ---- kernel: PHASE_ASSOCIATE -- obstacle / via-point association, initial-guess repair, dual initialisation ----
-__global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt, int first_outer)
+__global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt, int first_outer, int only_new)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
+    if (only_new && ASC(MPCB200_SC_NEW) == 0.0) return;  // streaming: only the slots that were just refilled
     const bool repair = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
     __syncwarp();
     for (int k = lane; k < N; k += 32) associate_stage(c, L, W, k);
@@ -230,6 +236,7 @@ __global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double up
         ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
         ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0; ASC(MPCB200_SC_DEFER) = 0.0;
         if (repair) ASC(MPCB200_SC_COLD) = 0.0;
+        ASC(MPCB200_SC_NEW) = 0.0;
     }
 }
 
@@ -718,33 +725,82 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg
 
 // ---- kernel: gather results into compact arrays ----------------------------------------------------------------
 struct OutputPtrs { double* u_seq; double* x_seq; double* dt; int* status; double* kkt; int* iters; double* u_packed; };
-__global__ void gather_outputs_kernel(WsLayout L, const double* ws, int B, OutputPtrs o)
+__device__ __forceinline__ void gather_one(const WsLayout& L, const double* W, const OutputPtrs& o, int64_t dst, int lane)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    const double* W = ws + (int64_t)warp * L.stride;
     const int N = L.N;
     for (int k = lane; k < N; k += 32)
     {
         const int kk = k <= N - 2 ? k : N - 2;
-        o.u_seq[((int64_t)warp * N + k) * 2 + 0] = AU(0, kk);
-        o.u_seq[((int64_t)warp * N + k) * 2 + 1] = AU(1, kk);
-        o.x_seq[((int64_t)warp * N + k) * 3 + 0] = AX(0, k);
-        o.x_seq[((int64_t)warp * N + k) * 3 + 1] = AX(1, k);
-        o.x_seq[((int64_t)warp * N + k) * 3 + 2] = normalize_theta(AX(2, k));
+        o.u_seq[(dst * N + k) * 2 + 0] = AU(0, kk);
+        o.u_seq[(dst * N + k) * 2 + 1] = AU(1, kk);
+        o.x_seq[(dst * N + k) * 3 + 0] = AX(0, k);
+        o.x_seq[(dst * N + k) * 3 + 1] = AX(1, k);
+        o.x_seq[(dst * N + k) * 3 + 2] = normalize_theta(AX(2, k));
         if (k <= N - 2)
         {
-            o.u_packed[((int64_t)warp * (N - 1) + k) * 2 + 0] = AU(0, k);
-            o.u_packed[((int64_t)warp * (N - 1) + k) * 2 + 1] = AU(1, k);
+            o.u_packed[(dst * (N - 1) + k) * 2 + 0] = AU(0, k);
+            o.u_packed[(dst * (N - 1) + k) * 2 + 1] = AU(1, k);
         }
     }
     if (lane == 0)
     {
-        o.dt[warp] = ASC(MPCB200_SC_DT);
+        o.dt[dst] = ASC(MPCB200_SC_DT);
         const double st = ASC(MPCB200_SC_STATUS);
-        o.status[warp] = st < 0 ? MPCB200_STATUS_MAX_ITER : (int)st;
-        o.kkt[warp] = ASC(MPCB200_SC_ERR0);
-        o.iters[warp] = (int)ASC(MPCB200_SC_ITER);
+        o.status[dst] = st < 0 ? MPCB200_STATUS_MAX_ITER : (int)st;
+        o.kkt[dst] = ASC(MPCB200_SC_ERR0);
+        o.iters[dst] = (int)ASC(MPCB200_SC_ITER);
+    }
+}
+
+__global__ void gather_outputs_kernel(WsLayout L, const double* ws, int B, OutputPtrs o)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    gather_one(L, ws + (int64_t)warp * L.stride, o, warp, lane);
+}
+
+// ---- streaming: a pool of B slots works through a queue of instances (continuous batching) ---------------------------
+// A slot whose instance has finished hands its result over (gather into the arrays of the whole job at the instance's
+// index) and takes the next instance of the queue; the IPM iteration kernels neither know nor care which slot holds
+// which instance.  Run every STREAM_REFILL_EVERY iterations, followed by the init / associate kernels restricted to the
+// slots marked SC_NEW.  counters[0] = next instance of the queue, counters[1] = results handed over.
+#define STREAM_REFILL_EVERY 2
+struct StreamState { int* slot_inst; int* counters; int total; };
+__global__ void stream_begin_kernel(WsLayout L, double* ws, int B, StreamState st)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) { st.counters[0] = 0; st.counters[1] = 0; }
+    if (b >= B) return;
+    double* W = ws + (int64_t)b * L.stride;
+    ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_INVALID_INPUT;  // any value >= 0: the slot is free
+    ASC(MPCB200_SC_NEW) = 0.0;
+    st.slot_inst[b] = -1;
+}
+__global__ void stream_refill_kernel(WsLayout L, double* ws, int B, InputPtrs in, OutputPtrs o, StreamState st)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    double* W = ws + (int64_t)warp * L.stride;
+    if (!(ASC(MPCB200_SC_STATUS) >= 0.0)) return;  // still iterating
+    const int id = st.slot_inst[warp];
+    __syncwarp();
+    if (id >= 0)
+    {
+        gather_one(L, W, o, id, lane);
+        if (lane == 0) atomicAdd(&st.counters[1], 1);
+    }
+    int nid = 0;
+    if (lane == 0) nid = atomicAdd(&st.counters[0], 1);
+    nid = __shfl_sync(FULLMASK, nid, 0);
+    if (nid < st.total)
+    {
+        scatter_one(L, W, in, nid, lane);
+        if (lane == 0) { st.slot_inst[warp] = nid; ASC(MPCB200_SC_COLD) = 1.0; ASC(MPCB200_SC_NEW) = 1.0; }
+    }
+    else if (lane == 0)
+    {
+        st.slot_inst[warp] = -1;
+        if (nid > (1 << 30)) st.counters[0] = st.total;  // idle slots keep asking: never let the counter wrap
     }
 }
 
@@ -792,6 +848,12 @@ struct mpcb200_handle
     cudaEvent_t poll_ev[2];
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
+    int only_new;   // streaming: init / associate touch only the slots marked SC_NEW
+    // streaming job: inputs / outputs of the whole queue on the device (grown on demand), slot -> instance map, counters
+    size_t stream_cap;
+    double *s_x0, *s_xf, *s_uprev, *s_obst, *s_vp, *s_useq, *s_xseq, *s_dt, *s_kkt, *s_upacked;
+    int *s_obst_count, *s_obst_type, *s_vp_count, *s_status, *s_iters, *d_slot_inst, *d_stream_counters;
+    int* h_stream_counters;  // pinned, two poll slots
     int has_lines;  // the uploaded batch contains line obstacles or obstacles may move: the eval / line-search kernels are launched with those paths compiled in
     double uprev_dt;
     mpcb200_stats stats;
@@ -920,6 +982,11 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaFuncSetAttribute(kkt_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<false>()));
     CKC(cudaMallocHost(&h->h_nactive, 8));
     h->nactive_ptr = nullptr;
+    h->only_new = 0; h->stream_cap = 0;
+    h->s_x0 = h->s_xf = h->s_uprev = h->s_obst = h->s_vp = h->s_useq = h->s_xseq = h->s_dt = h->s_kkt = h->s_upacked = nullptr;
+    h->s_obst_count = h->s_obst_type = h->s_vp_count = h->s_status = h->s_iters = nullptr;
+    CKC(cudaMalloc(&h->d_slot_inst, B * 4)); CKC(cudaMalloc(&h->d_stream_counters, 8));
+    CKC(cudaMallocHost(&h->h_stream_counters, 16));
     CKC(cudaEventCreateWithFlags(&h->poll_ev[0], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
     CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
@@ -942,6 +1009,10 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     void* ptrs[] = {h->ws, h->kkt_tiles, h->ric_tiles, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
                     h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush, h->d_counters, h->d_slot_of, h->d_inst_of_slot};
     for (void* p : ptrs) if (p) cudaFree(p);
+    void* sptrs[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
+                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_slot_inst, h->d_stream_counters};
+    for (void* p : sptrs) if (p) cudaFree(p);
+    if (h->h_stream_counters) cudaFreeHost(h->h_stream_counters);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
@@ -997,8 +1068,8 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
     if (timed && ev_begin(h, phase)) return set_err(h, MPCB200_E_CUDA, "cudaEventCreate failed");
     switch (phase)
     {
-        case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold); break;
-        case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer); break;
+        case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold, h->only_new); break;
+        case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer, h->only_new); break;
         case MPCB200_PHASE_EVAL:
 #define EVAL_LAUNCH(NW, LN) eval_kernel<NW, LN><<<B, NW * 32, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words)
             switch (group_threads >> 5)
@@ -1180,6 +1251,145 @@ static int fetch_results(mpcb200_handle* h, int B, double* u_seq, double* x_seq,
     if (status) { CK(cudaMemcpyAsync(status, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += B * 4; }
     if (kkt_err) { CK(cudaMemcpyAsync(kkt_err, h->d_kkt, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += B * 8; }
     if (iters) { CK(cudaMemcpyAsync(iters, h->d_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += B * 4; }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- streaming solve: `total` instances through the pool of max_batch slots (continuous batching) ----------------------
+static int stream_reserve(mpcb200_handle* h, size_t total)
+{
+    if (total <= h->stream_cap) return 0;
+    void* old[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
+                   h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters};
+    for (void* p : old) if (p) cudaFree(p);
+    const size_t N = (size_t)h->cfg.n, T = total;
+    CK(cudaMalloc(&h->s_x0, T * 3 * 8)); CK(cudaMalloc(&h->s_xf, T * 3 * 8)); CK(cudaMalloc(&h->s_uprev, T * 2 * 8));
+    CK(cudaMalloc(&h->s_obst, T * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CK(cudaMalloc(&h->s_obst_count, T * 4)); CK(cudaMalloc(&h->s_obst_type, T * MAX_OBST * 4));
+    CK(cudaMalloc(&h->s_vp, T * MAX_VP * 3 * 8)); CK(cudaMalloc(&h->s_vp_count, T * 4));
+    CK(cudaMalloc(&h->s_useq, T * N * 2 * 8)); CK(cudaMalloc(&h->s_xseq, T * N * 3 * 8)); CK(cudaMalloc(&h->s_dt, T * 8)); CK(cudaMalloc(&h->s_kkt, T * 8));
+    CK(cudaMalloc(&h->s_upacked, T * (N - 1) * 2 * 8)); CK(cudaMalloc(&h->s_status, T * 4)); CK(cudaMalloc(&h->s_iters, T * 4));
+    h->stream_cap = total;
+    return 0;
+}
+
+extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                                    const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, double* u_seq, double* x_seq, double* dt_out,
+                                    int* status, double* kkt_err, int* iters, double* solve_time_s)
+{
+    if (!h) return MPCB200_E_INVALID;
+    if (total < 1 || !x0 || !xf) return set_err(h, MPCB200_E_INVALID, "total >= 1, x0 and xf are required");
+    if (h->cfg.outer_iterations > 1) return set_err(h, MPCB200_E_UNSUPPORTED, "streaming runs one outer iteration per instance");
+    CK(cudaSetDevice(h->device));
+    int rc = stream_reserve(h, (size_t)total);
+    if (rc) return rc;
+    const size_t T = (size_t)total, N = (size_t)h->cfg.n;
+    const int B = total < h->max_batch ? total : h->max_batch;  // slots in use
+    // ---- inputs of the whole job ----
+    CK(cudaMemcpyAsync(h->s_x0, x0, T * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->s_xf, xf, T * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (long long)(T * 6 * 8);
+    if (u_prev) { CK(cudaMemcpyAsync(h->s_uprev, u_prev, T * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)(T * 16); }
+    h->uprev_dt = u_prev_dt;
+    h->has_obst = 0; h->obst_max = 0; h->has_lines = 0; h->has_vp = 0; h->vp_max = 0; h->has_xinit = 0; h->has_reinit = 0;
+    if (obst && obst->count && obst->max_per_instance > 0)
+    {
+        if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
+        const size_t M = (size_t)obst->max_per_instance;
+        int lines = 0;
+        for (size_t i = 0; i < T * M; ++i)
+        {
+            if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
+            lines |= obst->type[i] == MPCB200_OBST_LINE;
+        }
+        h->has_lines = lines || h->cfg.enable_dynamic_obstacles;
+        CK(cudaMemcpyAsync(h->s_obst_count, obst->count, T * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->s_obst_type, obst->type, T * M * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->s_obst, obst->params, T * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (long long)(T * 4 + T * M * 4 + T * M * MPCB200_OBST_STRIDE * 8);
+        h->has_obst = 1; h->obst_max = (int)M;
+    }
+    if (vp && vp->count && vp->max_per_instance > 0)
+    {
+        if (vp->max_per_instance > MAX_VP) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 8 via-points per instance");
+        const size_t V = (size_t)vp->max_per_instance;
+        CK(cudaMemcpyAsync(h->s_vp_count, vp->count, T * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->s_vp, vp->poses, T * V * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += (long long)(T * 4 + T * V * 24);
+        h->has_vp = 1; h->vp_max = (int)V;
+    }
+    InputPtrs in;
+    in.x0 = h->s_x0; in.xf = h->s_xf; in.u_prev = u_prev ? h->s_uprev : nullptr;
+    in.obst_count = h->has_obst ? h->s_obst_count : nullptr; in.obst_type = h->s_obst_type; in.obst_params = h->s_obst; in.obst_max = h->obst_max;
+    in.vp_count = h->has_vp ? h->s_vp_count : nullptr; in.vp_poses = h->s_vp; in.vp_max = h->vp_max;
+    in.x_init = nullptr; in.reinit = nullptr;
+    OutputPtrs o{h->s_useq, h->s_xseq, h->s_dt, h->s_status, h->s_kkt, h->s_iters, h->s_upacked};
+    StreamState st{h->d_slot_inst, h->d_stream_counters, total};
+    // ---- the pool ----
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, h->stream));
+    const unsigned tm = h->timing_mask;
+    auto timed = [&](int phase) { return ((tm >> phase) & 1u) != 0; };
+    h->spec = h->spec_mode == 0 ? ((2 * ((B + TILE - 1) / TILE) <= h->num_sms) ? 1 : 0) : (h->spec_mode == 2 ? 1 : 0);
+    h->B = B;
+    stream_begin_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, B, st);
+    h->stats.launches_total += 1;
+    const int grid4 = grid_for(B, WARPS_PER_CTA);
+    const long long max_rounds = ((long long)(total + B - 1) / B + 2) * (h->cfg.max_iter + 2 + STREAM_REFILL_EVERY);
+    const int POLL = 4;
+    int pending = -1;
+    bool done = false;
+    h->only_new = 1;
+    for (long long it = 0; it < max_rounds && !done; ++it)
+    {
+        if (it % STREAM_REFILL_EVERY == 0)
+        {
+            stream_refill_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->L, h->ws, B, in, o, st);
+            h->stats.launches_total += 1;
+            if ((rc = launch_phase(h, MPCB200_PHASE_INIT, B, 0, 0, timed(MPCB200_PHASE_INIT)))) break;
+            if ((rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, 1, timed(MPCB200_PHASE_ASSOCIATE)))) break;
+            if ((it / STREAM_REFILL_EVERY) % POLL == POLL - 1)
+            {
+                // results handed over so far, polled one poll behind (see solve_device)
+                const int slot = (int)((it / STREAM_REFILL_EVERY / POLL) & 1);
+                CK(cudaMemcpyAsync(h->h_stream_counters + 2 * slot, h->d_stream_counters, 8, cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaEventRecord(h->poll_ev[slot], h->stream));
+                if (pending >= 0)
+                {
+                    CK(cudaEventSynchronize(h->poll_ev[pending]));
+                    if (h->h_stream_counters[2 * pending + 1] >= total) done = true;
+                }
+                pending = slot;
+            }
+        }
+        if (done) break;
+        if (it % REGROUP_EVERY == 0 && (rc = launch_regroup(h, B))) break;
+        if ((rc = launch_phase_eval(h, B, nullptr, timed(MPCB200_PHASE_EVAL)))) break;
+        if ((rc = launch_phase(h, MPCB200_PHASE_KKT, B, 0, 0, timed(MPCB200_PHASE_KKT)))) break;
+        if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, timed(MPCB200_PHASE_LINESEARCH)))) break;
+    }
+    h->only_new = 0;
+    if (rc) return rc;
+    CK(cudaEventRecord(t1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int cnt[2];
+    CK(cudaMemcpy(cnt, h->d_stream_counters, 8, cudaMemcpyDeviceToHost));
+    if (cnt[1] < total) return set_err(h, MPCB200_E_CUDA, "streaming solve ended before every instance was handed over");
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    if (solve_time_s) *solve_time_s = ms * 1e-3;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    ev_collect(h);
+    // ---- results of the whole job ----
+    if (u_seq) { CK(cudaMemcpyAsync(u_seq, h->s_useq, T * N * 16, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * N * 16); }
+    if (x_seq) { CK(cudaMemcpyAsync(x_seq, h->s_xseq, T * N * 24, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * N * 24); }
+    if (dt_out) { CK(cudaMemcpyAsync(dt_out, h->s_dt, T * 8, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * 8); }
+    if (status) { CK(cudaMemcpyAsync(status, h->s_status, T * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * 4); }
+    if (kkt_err) { CK(cudaMemcpyAsync(kkt_err, h->s_kkt, T * 8, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * 8); }
+    if (iters) { CK(cudaMemcpyAsync(iters, h->s_iters, T * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * 4); }
+    CK(cudaStreamSynchronize(h->stream));
+    // the pool's workspaces now hold arbitrary instances of the job: the next step_batch must start cold
+    reset_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, B, nullptr);
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }

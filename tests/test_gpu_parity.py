@@ -186,6 +186,27 @@ def test_maximum_obstacle_count(cuda_lib, orc):
                 (np.full(B, 65, dtype=np.int32), np.zeros((B, 65), dtype=np.int32), np.zeros((B, 65, capi.OBST_STRIDE))))
 
 
+@pytest.mark.parametrize("cid,pool,total", [(2, 64, 300), (3, 32, 100), (4, 96, 96)])
+def test_streaming_pool_gives_batch_results(cuda_lib, cid, pool, total):
+    """mpcb200_solve_stream: a queue of instances through a small pool of slots (continuous batching) returns, instance by
+    instance, bit-identical results to cold batch solves -- only the order of execution differs."""
+    cfg = configs.config_for(cid, tol=1e-6)
+    data = configs.generate(cid, total)
+    s = _solver(cfg, pool)
+    out = s.solve_stream(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
+    # the same handle is usable for ordinary batches afterwards
+    first = {k: (v[:pool] if isinstance(v, np.ndarray) else v) for k, v in data.items() if k not in ("obstacles", "viapoints")}
+    b0 = s.step(first["x0"], first["xf"], first["u_prev"], data["u_prev_dt"], tuple(a[:pool] for a in data["obstacles"]),
+                tuple(a[:pool] for a in data["viapoints"]) if data["viapoints"] is not None else None)
+    s.close()
+    big = _solver(cfg, total)
+    ref = big.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
+    big.close()
+    for key in ("status", "iters", "u_seq", "x_seq", "dt", "kkt_err"):
+        np.testing.assert_array_equal(out[key], ref[key], err_msg=key)
+        np.testing.assert_array_equal(b0[key], ref[key][:pool], err_msg=key)
+
+
 def test_rigid_motion_equivariance(cuda_lib):
     """Rotating + translating the whole scene rotates the optimal path and leaves the optimal controls unchanged."""
     cfg = configs.cfg2(tol=1e-9)
