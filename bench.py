@@ -283,34 +283,38 @@ def main():
     st1 = solver.stats()
     conv_e2e = int((out["status"] == 0).sum())
 
+    # ---- max over ranks / totals ----
+    if dist is not None:
+        t = torch.tensor([el, el_e2e], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el, el_e2e = float(t[0]), float(t[1])
+        c = torch.tensor([conv_local, conv_e2e], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        conv_total, conv_e2e_total = int(c[0]), int(c[1])
+    else:
+        conv_total, conv_e2e_total = conv_local, conv_e2e
     # ---- continuous batching: the K steps' instances as ONE queue through the same 1024-slot pool (mpcb200_solve_stream),
-    #      host buffers in, host buffers out.  Reported next to the per-batch numbers, not instead of them. ----
+    #      host buffers in, host buffers out.  Reported next to the per-batch numbers, not instead of them; a failure here
+    #      must never take the contract line down. ----
     reps = args.steps
-    tile = lambda a: np.ascontiguousarray(np.concatenate([a] * reps))
-    q = dict(x0=tile(data["x0"]), xf=tile(data["xf"]), u_prev=tile(data["u_prev"]), obstacles=tuple(tile(a) for a in data["obstacles"]))
-    def stream_job():
-        return solver.solve_stream(q["x0"], q["xf"], q["u_prev"], data["u_prev_dt"], q["obstacles"], None)
-    stream_err = None
+    stream_err, el_stream, conv_stream = None, 1.0, 0
     try:
+        tile = lambda a: np.ascontiguousarray(np.concatenate([a] * reps))
+        q = dict(x0=tile(data["x0"]), xf=tile(data["xf"]), u_prev=tile(data["u_prev"]), obstacles=tuple(tile(a) for a in data["obstacles"]))
         with torch.cuda.stream(stream):
             solver.solve_stream(q["x0"][: 2 * B], q["xf"][: 2 * B], q["u_prev"][: 2 * B], data["u_prev_dt"], tuple(a[: 2 * B] for a in q["obstacles"]), None)
         torch.cuda.synchronize()
-        el_stream, sout = timed(stream_job, 1)
+        el_stream, sout = timed(lambda: solver.solve_stream(q["x0"], q["xf"], q["u_prev"], data["u_prev_dt"], q["obstacles"], None), 1)
         conv_stream = int((sout["status"] == 0).sum())
-    except Exception as e:  # the secondary measurement must never take the contract line down
-        stream_err, el_stream, conv_stream = repr(e), 1.0, 0
-        barrier()
+        if dist is not None:
+            t = torch.tensor([el_stream], dtype=torch.float64, device=f"cuda:{dev}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c = torch.tensor([conv_stream], dtype=torch.float64, device=f"cuda:{dev}")
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            el_stream, conv_stream = float(t[0]), int(c[0])
+    except Exception as e:
+        stream_err = repr(e)
 
-    # ---- max over ranks / totals ----
-    if dist is not None:
-        t = torch.tensor([el, el_e2e, el_stream], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        el, el_e2e, el_stream = float(t[0]), float(t[1]), float(t[2])
-        c = torch.tensor([conv_local, conv_e2e, conv_stream], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        conv_total, conv_e2e_total, conv_stream = int(c[0]), int(c[1]), int(c[2])
-    else:
-        conv_total, conv_e2e_total = conv_local, conv_e2e
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
