@@ -233,10 +233,17 @@ __global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double up
     if (lane == 0)
     {
         ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
-        ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
+        ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
         ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0; ASC(MPCB200_SC_DEFER) = 0.0;
         if (repair) ASC(MPCB200_SC_COLD) = 0.0;
-        ASC(MPCB200_SC_NEW) = 0.0;
+        if (only_new)
+        {
+            // streaming: this kernel runs beside the iteration kernels of the other slots; the slot stays parked (status >= 0,
+            // never -1 in between) until the next refill kernel, which runs after this one on the main stream, activates it
+            ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_INVALID_INPUT;
+            ASC(MPCB200_SC_NEW) = 2.0;
+        }
+        else { ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NEW) = 0.0; }
     }
 }
 
@@ -782,6 +789,14 @@ __global__ void stream_refill_kernel(WsLayout L, double* ws, int B, InputPtrs in
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
     if (!(ASC(MPCB200_SC_STATUS) >= 0.0)) return;  // still iterating
+    const double nw = ASC(MPCB200_SC_NEW);
+    __syncwarp();
+    if (nw != 0.0)
+    {
+        // refilled in the previous round, initialised on the side stream since then: starts iterating now
+        if (lane == 0 && nw == 2.0) { ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NEW) = 0.0; }
+        return;
+    }
     const int id = st.slot_inst[warp];
     __syncwarp();
     if (id >= 0)
@@ -854,6 +869,8 @@ struct mpcb200_handle
     double *s_x0, *s_xf, *s_uprev, *s_obst, *s_vp, *s_useq, *s_xseq, *s_dt, *s_kkt, *s_upacked;
     int *s_obst_count, *s_obst_type, *s_vp_count, *s_status, *s_iters, *d_slot_inst, *d_stream_counters;
     int* h_stream_counters;  // pinned, two poll slots
+    cudaStream_t side_stream;            // streaming: init / associate of refilled slots run beside the iterations of the others
+    cudaEvent_t ev_refill, ev_ready;
     int has_lines;  // the uploaded batch contains line obstacles or obstacles may move: the eval / line-search kernels are launched with those paths compiled in
     double uprev_dt;
     mpcb200_stats stats;
@@ -987,6 +1004,8 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     h->s_obst_count = h->s_obst_type = h->s_vp_count = h->s_status = h->s_iters = nullptr;
     CKC(cudaMalloc(&h->d_slot_inst, B * 4)); CKC(cudaMalloc(&h->d_stream_counters, 8));
     CKC(cudaMallocHost(&h->h_stream_counters, 16));
+    CKC(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->ev_refill, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->poll_ev[0], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
     CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
@@ -1015,6 +1034,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     if (h->h_stream_counters) cudaFreeHost(h->h_stream_counters);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(h->side_stream); cudaEventDestroy(h->ev_refill); cudaEventDestroy(h->ev_ready);
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -1335,19 +1355,29 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
     stream_begin_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, B, st);
     h->stats.launches_total += 1;
     const int grid4 = grid_for(B, WARPS_PER_CTA);
-    const long long max_rounds = ((long long)(total + B - 1) / B + 2) * (h->cfg.max_iter + 2 + STREAM_REFILL_EVERY);
+    const long long max_rounds = ((long long)(total + B - 1) / B + 2) * (h->cfg.max_iter + 2 + 3 * STREAM_REFILL_EVERY);
     const int POLL = 4;
     int pending = -1;
     bool done = false;
     h->only_new = 1;
+    const cudaStream_t main_stream = h->stream;
     for (long long it = 0; it < max_rounds && !done; ++it)
     {
         if (it % STREAM_REFILL_EVERY == 0)
         {
-            stream_refill_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->L, h->ws, B, in, o, st);
+            // refill on the main stream (after the side work of the previous round); the cold initialisation and the
+            // association of the refilled slots then run on the side stream, beside the next iterations of the other slots
+            if (it > 0) CK(cudaStreamWaitEvent(main_stream, h->ev_ready, 0));
+            stream_refill_kernel<<<grid4, WARPS_PER_CTA * 32, 0, main_stream>>>(h->L, h->ws, B, in, o, st);
             h->stats.launches_total += 1;
-            if ((rc = launch_phase(h, MPCB200_PHASE_INIT, B, 0, 0, timed(MPCB200_PHASE_INIT)))) break;
-            if ((rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, 1, timed(MPCB200_PHASE_ASSOCIATE)))) break;
+            CK(cudaEventRecord(h->ev_refill, main_stream));
+            CK(cudaStreamWaitEvent(h->side_stream, h->ev_refill, 0));
+            h->stream = h->side_stream;
+            rc = launch_phase(h, MPCB200_PHASE_INIT, B, 0, 0, timed(MPCB200_PHASE_INIT));
+            if (!rc) rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, 1, timed(MPCB200_PHASE_ASSOCIATE));
+            h->stream = main_stream;
+            if (rc) break;
+            CK(cudaEventRecord(h->ev_ready, h->side_stream));
             if ((it / STREAM_REFILL_EVERY) % POLL == POLL - 1)
             {
                 // results handed over so far, polled one poll behind (see solve_device)
@@ -1369,6 +1399,8 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
         if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, timed(MPCB200_PHASE_LINESEARCH)))) break;
     }
     h->only_new = 0;
+    h->stream = main_stream;
+    CK(cudaStreamWaitEvent(main_stream, h->ev_ready, 0));
     if (rc) return rc;
     CK(cudaEventRecord(t1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
