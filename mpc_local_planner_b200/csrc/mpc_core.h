@@ -54,6 +54,11 @@ struct WsLayout
 #define MAX_INERTIA_TRIES 2      // factorisations per IPM iteration (escalation resumes in the next iteration: a retry of one lane stalls its whole launch)
 #define MAX_DELTA 1e8
 #define DELTA_FLOOR 1e-5
+// Clipped slack steps (see the oracle, ORC_CLIP_*): the rows that block the step most -- at most 1/CLIP_DIV of the rows, in
+// whole sqrt(2)-wide bins of their step ratio -- are excluded from the fraction-to-the-boundary rule; their slacks are clipped.
+#define CLIP_DIV 8
+#define CLIP_FLOOR 0.01
+#define CLIP_BINS 40
 #define TINY_STEP 1e-8
 #define TINY_STEP_COUNT 2
 #define KAPPA_SIGMA 1e10
@@ -401,6 +406,23 @@ HD inline void obstacle_centroid(int obst_type, const double* op, double* cx, do
 {
     if (obst_type == MPCB200_OBST_LINE) { *cx = 0.5 * (op[0] + op[2]); *cy = 0.5 * (op[1] + op[3]); }
     else { *cx = op[0]; *cy = op[1]; }
+}
+
+HD inline int clip_bin(double ratio)  // bin j holds the ratios in (2^(-(j+1)/2), 2^(-j/2)]
+{
+    const int j = (int)floor(-2.0 * log2(ratio));
+    return j < 0 ? 0 : (j >= CLIP_BINS ? CLIP_BINS - 1 : j);
+}
+// threshold bin from the histogram of blocking ratios: the bins jt.. hold at most rows / CLIP_DIV rows
+HD inline int clip_threshold_bin(const int* hist, int rows)
+{
+    int jt = CLIP_BINS, cum = 0;
+    for (int j = CLIP_BINS - 1; j >= 0; --j)
+    {
+        if (cum + hist[j] > rows / CLIP_DIV) break;
+        cum += hist[j]; jt = j;
+    }
+    return jt;
 }
 
 // ---- config predicates ----

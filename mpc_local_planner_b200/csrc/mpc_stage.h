@@ -434,7 +434,13 @@ struct LsAcc
 HD inline void lsacc_init(LsAcc& a) { a.a_p = 1.0; a.a_d = 1.0; a.dphi_bar = a.curv = a.dJ = 0.0; }
 
 // slack / multiplier steps of the rows owned by stage k, fraction to the boundary, directional derivatives
-HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double* G, const double* Kb, double uprev_dt, int k, LsAcc& acc)
+// hist: CLIP_BINS counters of the blocking step ratios + one counter of the active rows (shared memory in the kernel)
+#ifdef __CUDA_ARCH__
+#define HIST_ADD(p_) atomicAdd((p_), 1)
+#else
+#define HIST_ADD(p_) (++*(p_))
+#endif
+HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double* G, const double* Kb, double uprev_dt, int k, LsAcc& acc, int* hist)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT), mu = ASC(MPCB200_SC_MU), ddt = ASC(MPCB200_SC_DDT);
@@ -485,7 +491,8 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         ADS(sl, k) = ds;
         ADLAM(sl, k) = dl;
         GR0(sl, k) = r0;
-        if (ds < 0) acc.a_p = fmin(acc.a_p, -tau * s / ds);
+        HIST_ADD(hist + CLIP_BINS);
+        if (ds < 0 && -tau * s / ds < 1.0) HIST_ADD(hist + clip_bin(-tau * s / ds));
         if (dl < 0) acc.a_d = fmin(acc.a_d, -tau * lam / dl);
         acc.dphi_bar += -mu * ds * rs;
         acc.curv += (lam * rs) * ds * ds;
@@ -549,6 +556,23 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         if (c.variable_dt && k == N - 1) cv += ddt * ddt * (ASC(MPCB200_SC_HTT) + delta);
         acc.curv += cv;
     }
+}
+
+// primal step length: smallest step ratio over the rows of stage k that are not clipped (bins below jt)
+HD inline double ls_stage_ap(const WsLayout& L, const double* W, int k, int jt)
+{
+    const int N = L.N, RS = L.RS;
+    const double mu = ASC(MPCB200_SC_MU);
+    const double tau = (1.0 - mu > TAU_MIN) ? 1.0 - mu : TAU_MIN;
+    double a_p = 1.0;
+    for (int sl = 0; sl < RS; ++sl)
+    {
+        const double ds = ADS(sl, k);  // 0 for inactive rows
+        if (!(ds < 0)) continue;
+        const double r = -tau * AS(sl, k) / ds;
+        if (r < a_p && clip_bin(r) < jt) a_p = r;
+    }
+    return a_p;
 }
 
 // objective contribution of stage k at (x, u, dt): quadratic running cost (k <= N-2; dt-weighted in integral form), terminal
@@ -639,8 +663,12 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
     for (int sl = 0; sl < 8; ++sl)
     {
         if (!lin_row_active(c, N, k, sl, uprev_dt)) continue;
-        acc.inf1 += fabs(oma * GR0(sl, k));
-        rowprod_add(rp, AS(sl, k) + alpha * ADS(sl, k), acc.blog);
+        const double s0 = AS(sl, k), ds = ADS(sl, k);
+        double sn = s0 + alpha * ds;
+        double res = oma * GR0(sl, k);           // g(alpha) + s + alpha ds, exact for linear rows
+        if (sn < CLIP_FLOOR * s0) { res += CLIP_FLOOR * s0 - sn; sn = CLIP_FLOOR * s0; }  // clipped slack: the residual keeps the difference
+        acc.inf1 += fabs(res);
+        rowprod_add(rp, sn, acc.blog);
     }
     if (k >= 1 && k <= N - 2)
         for (int j = 0; j < K; ++j)
@@ -651,13 +679,15 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
             const double dist = footprint_distance_sc<false, false, LINES>(c, x[0], x[1], sc[0], sc[1], (int)W[L.oOTYPE + oi],
                                                                     LINES ? obstacle_at(c, W + L.oOBST + oi * MPCB200_OBST_STRIDE, k, dtt, ob) : W + L.oOBST + oi * MPCB200_OBST_STRIDE,
                                                                     nullptr, nullptr);
-            const double sn = AS(8 + j, k) + alpha * ADS(8 + j, k);
+            double sn = AS(8 + j, k) + alpha * ADS(8 + j, k);
+            if (sn < CLIP_FLOOR * AS(8 + j, k)) sn = CLIP_FLOOR * AS(8 + j, k);
             acc.inf1 += fabs(c.min_obstacle_dist - dist + sn);
             rowprod_add(rp, sn, acc.blog);
         }
     if (k == N - 1 && ball_active(c))
     {
-        const double sn = AS(BALL_SLOT, k) + alpha * ADS(BALL_SLOT, k);
+        double sn = AS(BALL_SLOT, k) + alpha * ADS(BALL_SLOT, k);
+        if (sn < CLIP_FLOOR * AS(BALL_SLOT, k)) sn = CLIP_FLOOR * AS(BALL_SLOT, k);
         acc.inf1 += fabs(ball_row(c, x, xf, nullptr, nullptr) + sn);
         rowprod_add(rp, sn, acc.blog);
     }
@@ -685,6 +715,7 @@ HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W,
         else act = (k >= 1 && k <= N - 2) && AOBS(sl - 8, k) >= 0.0;
         if (!act) continue;
         double s = AS(sl, k) + alpha * ADS(sl, k);
+        if (s < CLIP_FLOOR * AS(sl, k)) s = CLIP_FLOOR * AS(sl, k);
         double lam = ALAM(sl, k) + a_dual * ADLAM(sl, k);
         const double lo = mu / (KAPPA_SIGMA * s), hi = KAPPA_SIGMA * mu / s;
         if (lam < lo) lam = lo;

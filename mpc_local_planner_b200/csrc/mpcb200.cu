@@ -605,6 +605,7 @@ struct LsShared
 {
     LsAcc acc[MAX_GROUP_WARPS];
     TrialAcc tr[MAX_GROUP_WARPS];
+    int hist[CLIP_BINS + 1];
     double alpha, a_dual;
     int accept;
 };
@@ -661,7 +662,13 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg
     const double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
     LsAcc a;
     lsacc_init(a);
-    for (int k = tid; k < N; k += blockDim.x) ls_stage_steps(c, L, W, Gp, Kb, uprev_dt, k, a);
+    // histogram of the blocking step ratios (+ row count) -> threshold bin of the clipped rows -> primal step length
+    for (int j = tid; j <= CLIP_BINS; j += blockDim.x) sh.hist[j] = 0;
+    __syncthreads();
+    for (int k = tid; k < N; k += blockDim.x) ls_stage_steps(c, L, W, Gp, Kb, uprev_dt, k, a, sh.hist);
+    __syncthreads();
+    const int jt = clip_threshold_bin(sh.hist, sh.hist[CLIP_BINS]);  // same value in every thread
+    for (int k = tid; k < N; k += blockDim.x) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt));
     a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
     a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
     if (lane == 0) sh.acc[wid] = a;

@@ -1030,6 +1030,18 @@ void orc_init_controls(const orc_problem* p, orc_ws* ws)
 /* Part 2: interior-point method                                                                            */
 /* ======================================================================================================= */
 
+/* Clipped slack steps: the fraction-to-the-boundary rule lets ONE nearly active row cut the step of all variables.  The rows
+   that block most -- at most 1/ORC_CLIP_DIV of the rows, taken in whole sqrt(2)-wide bins of their step ratio -- are
+   excluded from the rule; their slacks are clipped at ORC_CLIP_FLOOR times their value instead (their rows then lose less
+   infeasibility than the Newton step promised, which the merit line search sees). */
+#define ORC_CLIP_DIV 8
+#define ORC_CLIP_FLOOR 0.01
+#define ORC_CLIP_BINS 40
+static int clip_bin(double ratio) /* bin j holds the ratios in (2^(-(j+1)/2), 2^(-j/2)] */
+{
+    int j = (int)floor(-2.0 * log2(ratio));
+    return j < 0 ? 0 : (j >= ORC_CLIP_BINS ? ORC_CLIP_BINS - 1 : j);
+}
 #define ORC_MU_AUTO_MIN 0.1
 #define ORC_MU_AUTO_MAX 1.0
 #define ORC_KAPPA_EPS 10.0
@@ -1633,6 +1645,7 @@ static void trial_eval(const orc_problem* p, orc_ws* ws, const double* Xt, const
             if (!row_active(p, ws, k, sl)) continue;
             double g = row_value(p, ws, k, sl, Xt, Ut, dtt, NULL, NULL);
             double s = ws->S[IX(sl, k)] + alpha * ws->DS[IX(sl, k)];
+            if (s < ORC_CLIP_FLOOR * ws->S[IX(sl, k)]) s = ORC_CLIP_FLOOR * ws->S[IX(sl, k)];
             inf += fabs(g + s);
             bl += log(s);
         }
@@ -1702,10 +1715,13 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
         double a_p = 1.0, a_d = 1.0;
         double dphi_bar = 0.0; /* -mu sum ds/s */
         double curv = 0.0;     /* sum sigma ds^2 */
+        int hist[ORC_CLIP_BINS], m_rows = 0;
+        for (int j = 0; j < ORC_CLIP_BINS; ++j) hist[j] = 0;
         for (int k = 0; k < N; ++k)
             for (int sl = 0; sl < RS; ++sl)
             {
                 if (!row_active(p, ws, k, sl)) { ws->DS[IX(sl, k)] = 0; ws->DLAM[IX(sl, k)] = 0; continue; }
+                ++m_rows;
                 double grad[8];
                 double g = row_value(p, ws, k, sl, ws->X, ws->U, dt, grad, NULL);
                 double gdz = 0.0;
@@ -1718,11 +1734,29 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
                 double dl = mu / s - lam - (lam / s) * ds;
                 ws->DS[IX(sl, k)] = ds;
                 ws->DLAM[IX(sl, k)] = dl;
-                if (ds < 0 && -tau * s / ds < a_p) a_p = -tau * s / ds;
+                if (ds < 0 && -tau * s / ds < 1.0) hist[clip_bin(-tau * s / ds)]++;
                 if (dl < 0 && -tau * lam / dl < a_d) a_d = -tau * lam / dl;
                 dphi_bar += -mu * ds / s;
                 curv += (lam / s) * ds * ds;
             }
+        {
+            /* threshold bin: the bins jt.. (smallest ratios) hold at most m_rows / ORC_CLIP_DIV rows: those are clipped; the
+               primal step length is the smallest ratio of the other rows */
+            int jt = ORC_CLIP_BINS, cum = 0;
+            for (int j = ORC_CLIP_BINS - 1; j >= 0; --j)
+            {
+                if (cum + hist[j] > m_rows / ORC_CLIP_DIV) break;
+                cum += hist[j]; jt = j;
+            }
+            for (int k = 0; k < N; ++k)
+                for (int sl = 0; sl < RS; ++sl)
+                {
+                    const double ds = ws->DS[IX(sl, k)];
+                    if (!(ds < 0)) continue;
+                    const double r = -tau * ws->S[IX(sl, k)] / ds;
+                    if (r < a_p && clip_bin(r) < jt) a_p = r;
+                }
+        }
         /* ---- l1 merit function and its directional derivative ---- */
         /* grad J . dz : cost gradient = condensed gradient minus the row terms; recompute from the objective pieces:
            use GL - (dynamics + row multiplier terms) is messy, so accumulate directly: dJ = sum (g_k - rowpart).  Simpler and
@@ -1832,6 +1866,7 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
             {
                 if (!row_active(p, ws, k, sl)) continue;
                 double s = ws->S[IX(sl, k)] + alpha * ws->DS[IX(sl, k)];
+                if (s < ORC_CLIP_FLOOR * ws->S[IX(sl, k)]) s = ORC_CLIP_FLOOR * ws->S[IX(sl, k)];
                 double lam = ws->LAM[IX(sl, k)] + a_dual * ws->DLAM[IX(sl, k)];
                 double lo = mu / (ORC_KAPPA_SIGMA * s), hi = ORC_KAPPA_SIGMA * mu / s;
                 if (lam < lo) lam = lo;

@@ -228,14 +228,18 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
     if (ASC(MPCB200_SC_DEFER) != 0.0) { ASC(MPCB200_SC_DEFER) = 0.0; ASC(MPCB200_SC_ITER) += 1.0; ASC(MPCB200_SC_ALPHA) = 0.0; return; }
     LsAcc a;
     lsacc_init(a);
+    int hist[CLIP_BINS + 1];
+    for (int j = 0; j <= CLIP_BINS; ++j) hist[j] = 0;
     for (int l = 0; l < 32; ++l)
     {
         LsAcc t;
         lsacc_init(t);
-        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, W, emu_kb(L, W), uprev_dt, k, t);
-        a.a_p = fmin(a.a_p, t.a_p); a.a_d = fmin(a.a_d, t.a_d);
+        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, W, emu_kb(L, W), uprev_dt, k, t, hist);
+        a.a_d = fmin(a.a_d, t.a_d);
         a.dphi_bar += t.dphi_bar; a.curv += t.curv; a.dJ += t.dJ;
     }
+    const int jt = clip_threshold_bin(hist, hist[CLIP_BINS]);
+    for (int k = 0; k < N; ++k) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt));
     const double mu = ASC(MPCB200_SC_MU), inf1 = ASC(MPCB200_SC_INF), obj = ASC(MPCB200_SC_OBJ), blog = ASC(MPCB200_SC_BLOG);
     const double ddt = ASC(MPCB200_SC_DDT), dt = ASC(MPCB200_SC_DT);
     double rho = 1.0;
