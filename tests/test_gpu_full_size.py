@@ -36,7 +36,8 @@ def _check_feasible(cfg, data, out, sel, point_footprint, obsidx):
     assert (np.abs(defect) * dt).max() < 20 * cfg.tol
     assert np.abs(x[:, 0] - data["x0"][sel]).max() < 1e-12
     lb = np.array(cfg.u_lb[:]); ub = np.array(cfg.u_ub[:])
-    assert (u >= lb - 1e-8).all() and (u <= ub + 1e-8).all()
+    # rows hold up to the solver tolerance (the scaled KKT error bounds every row residual g + s with s > 0)
+    assert (u >= lb - 20 * cfg.tol).all() and (u <= ub + 20 * cfg.tol).all()
     dlb = np.array(cfg.du_lb[:]); dub = np.array(cfg.du_ub[:])
     if np.isfinite(dub).all() and (dub < 1e29).all():
         du = np.diff(u, axis=1) / dt
@@ -44,7 +45,7 @@ def _check_feasible(cfg, data, out, sel, point_footprint, obsidx):
         first = (u[:, 0] - data["u_prev"][sel]) / data["u_prev_dt"]
         assert (first >= dlb - 1e-5).all() and (first <= dub + 1e-5).all()
     if cfg.variable_dt:
-        assert (out["dt"][sel] >= cfg.dt_lb - 1e-9).all() and (out["dt"][sel] <= cfg.dt_ub + 1e-9).all()
+        assert (out["dt"][sel] >= cfg.dt_lb - 20 * cfg.tol).all() and (out["dt"][sel] <= cfg.dt_ub + 20 * cfg.tol).all()
     if point_footprint:
         # obstacle rows exist for the obstacles associated with a stage at the initial guess (stage_inequality_se2.cpp:50-162;
         # like the reference, the association is not redone during the solve): read the association back and check those
