@@ -31,6 +31,9 @@ extern "C" {
 #define MPCB200_ROBOT_SIMPLE_CAR_FRONT 2  /* inc/systems/simple_car.h:131-141 */
 #define MPCB200_ROBOT_KIN_BICYCLE 3       /* inc/systems/kinematic_bicycle_model.h:65-77 */
 
+/* grid/cost_integration_method (src/controller.cpp:318-333) */
+#define MPCB200_COST_LEFT_SUM 0
+#define MPCB200_COST_TRAPEZOIDAL 1
 /* grid/collocation_method (src/controller.cpp:298-316) */
 #define MPCB200_COLLOC_FORWARD 0   /* inc/optimal_control/fd_collocation_se2.h:54-69 (default, every shipped config) */
 #define MPCB200_COLLOC_MIDPOINT 1  /* :91-108  -- not implemented in this round: create() returns E_UNSUPPORTED */
@@ -118,8 +121,8 @@ typedef struct mpcb200_config {
                               instance, |f(x_0)| / #rows clamped to [0.1, 1] ("initial barrier parameter") */
     int outer_iterations;  /* controller/outer_ocp_iterations */
     /* planning/objective/quadratic_form/integral_form (src/controller.cpp:593-594): the running cost enters as
-       sum_k dt * l(x_k, u_k) (grid/cost_integration_method left_sum, finite_differences_grid_se2.cpp:66-70; the
-       trapezoidal rule is not implemented).  Default 0 = every shipped configuration. */
+       sum_k dt * l(x_k, u_k) (grid/cost_integration_method left_sum, finite_differences_grid_se2.cpp:66-70) or by the
+       trapezoidal rule (`cost_integration` below).  Default 0 = every shipped configuration. */
     int quadratic_integral_form;
     /* planning/terminal_constraint (src/controller.cpp:676-709): type "l2_ball" = TerminalBallSE2, one inequality row on the
        final state, d' S d - gamma <= 0 with d = x_{N-1} - x_f (theta wrapped), final_state_conditions_se2.cpp:54-64;
@@ -137,6 +140,11 @@ typedef struct mpcb200_config {
     int terminal_ball;
     double terminal_ball_S[9];
     double terminal_ball_gamma;
+    /* grid/cost_integration_method (src/controller.cpp:318-333), used by the integral form only:
+       MPCB200_COST_LEFT_SUM (default)  sum_{k<=N-2} dt l(x_k, u_k)                        (finite_differences_grid_se2.cpp:66-70)
+       MPCB200_COST_TRAPEZOIDAL         sum_{k<=N-2} dt/2 ( l(x_k, u_k) + l(x_{k+1}, u_k) ) (finite_differences_grid_se2.cpp:59-65;
+       corbo's TrapezoidalIntegralCostEdge evaluates both ends with the control of the interval). */
+    int cost_integration;
 } mpcb200_config;
 
 /* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]). */

@@ -21,6 +21,7 @@ SCAL_WORDS = 32
 # enums (mirror include/mpcb200.h)
 ROBOT_UNICYCLE, ROBOT_SIMPLE_CAR, ROBOT_SIMPLE_CAR_FRONT, ROBOT_KIN_BICYCLE = 0, 1, 2, 3
 COLLOC_FORWARD, COLLOC_MIDPOINT, COLLOC_CRANK_NICOLSON = 0, 1, 2
+COST_LEFT_SUM, COST_TRAPEZOIDAL = 0, 1
 OBJ_MINIMUM_TIME, OBJ_QUADRATIC_FORM, OBJ_MINIMUM_TIME_VIA_POINTS = 0, 1, 2
 FOOTPRINT_POINT, FOOTPRINT_CIRCULAR, FOOTPRINT_TWO_CIRCLES, FOOTPRINT_LINE, FOOTPRINT_POLYGON = 0, 1, 2, 3, 4
 OBST_POINT, OBST_CIRCLE, OBST_LINE = 0, 1, 2
@@ -81,6 +82,7 @@ class Config(C.Structure):
         ("terminal_ball", C.c_int),
         ("terminal_ball_S", C.c_double * 9),
         ("terminal_ball_gamma", C.c_double),
+        ("cost_integration", C.c_int),
     ]
 
     def copy(self):
@@ -139,6 +141,7 @@ def default_config():
     for i in range(9):
         c.terminal_ball_S[i] = 1.0 if i % 4 == 0 else 0.0
     c.terminal_ball_gamma = 5.0
+    c.cost_integration = COST_LEFT_SUM
     return c
 
 

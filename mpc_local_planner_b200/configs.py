@@ -182,6 +182,16 @@ def cfg2_integral_form(n=50, tol=1e-6):
     return c
 
 
+def cfg2_trapezoidal(n=50, tol=1e-6, variable_dt=True):
+    """cfg 2 in integral form integrated by the trapezoidal rule (`grid/cost_integration_method: trapezoidal_rule`), with a
+    free dt in [0.05, 1.0] s (the end term dt/2 l(x_{N-1}) then couples the free final state and dt) or the fixed dt of
+    cfg 2 -- not a BASELINE configuration."""
+    c = cfg2_integral_form(n, tol) if variable_dt else cfg2(n, tol)
+    c.quadratic_integral_form = 1
+    c.cost_integration = capi.COST_TRAPEZOIDAL
+    return c
+
+
 def cfg2_terminal_ball(n=50, tol=1e-6, gamma=0.05):
     """cfg 2 with `planning/terminal_constraint/type: l2_ball` (TerminalBallSE2: d' S d - gamma <= 0 on the final state),
     S = diag(1, 1, 0.5) -- not a BASELINE configuration."""

@@ -438,6 +438,17 @@ HD inline bool has_viapoints(const Cfg& c)
            (c.objective == MPCB200_OBJ_QUADRATIC_FORM && c.vp_attraction_with_quadratic);
 }
 HD inline bool has_terminal_cost(const Cfg& c) { return c.terminal_cost && !xf_all_fixed(c); }
+// Integral form of the quadratic running cost (quadratic_cost_se2.cpp:54-84 through corbo's LeftSumCostEdge /
+// TrapezoidalIntegralCostEdge, finite_differences_grid_se2.cpp:57-72): the state term of stage k enters with weight
+// dt * integral_state_weight -- left sum 1 for k <= N-2 and 0 at k = N-1; trapezoidal rule 1/2 at both ends, 1 between --
+// the control term of interval k with weight dt in both rules (both ends of the trapezoid use u_k).
+HD inline bool has_trapezoid(const Cfg& c)
+{ return has_quadratic(c) && c.quadratic_integral_form != 0 && c.cost_integration == MPCB200_COST_TRAPEZOIDAL; }
+HD inline double integral_state_weight(const Cfg& c, int N, int k)
+{
+    if (c.cost_integration == MPCB200_COST_TRAPEZOIDAL) return (k == 0 || k == N - 1) ? 0.5 : 1.0;
+    return k <= N - 2 ? 1.0 : 0.0;
+}
 
 // ---- terminal ball (TerminalBallSE2, R/src/optimal_control/final_state_conditions_se2.cpp:54-64): row slot 2 of stage N-1 ----
 #define BALL_SLOT 2

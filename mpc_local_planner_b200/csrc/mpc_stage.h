@@ -185,11 +185,13 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
         // quadratic running cost (k = 0 state term is a constant: its gradient is never used since x_0 is fixed)
         if (has_quadratic(c))
         {
-            // integral form (left sum): dt * l(x_k, u_k); then l itself is the dt-gradient and grad l the w-dt cross Hessian
+            // integral form: dt * (w_k l_x(x_k) + l_u(u_k)), w_k the state weight of the integration rule (left sum or
+            // trapezoid, integral_state_weight); then the dt-gradient is w_k l_x + l_u and the w-dt cross Hessian its gradient
             const bool integ = c.quadratic_integral_form != 0;
-            const double wq = integ ? dt : 1.0;
+            const double fx = integ ? integral_state_weight(c, N, k) : 1.0;
+            const double wx = integ ? dt * fx : 1.0, wu = integ ? dt : 1.0;
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
-            double o = 0.0;
+            double ox = 0.0, ou = 0.0;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
             {
@@ -198,11 +200,11 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
                 for (int j = 0; j < 3; ++j)
                 {
                     gi += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j];
-                    o += d[i] * c.Q[i * 3 + j] * d[j];
-                    if (j >= i) H[hidx(i, j)] += wq * (c.Q[i * 3 + j] + c.Q[j * 3 + i]);
+                    ox += d[i] * c.Q[i * 3 + j] * d[j];
+                    if (j >= i) H[hidx(i, j)] += wx * (c.Q[i * 3 + j] + c.Q[j * 3 + i]);
                 }
-                g0[i] += wq * gi; GL[i] += wq * gi;
-                if (integ && c.variable_dt) hb[i] += gi;
+                g0[i] += wx * gi; GL[i] += wx * gi;
+                if (integ && c.variable_dt) hb[i] += fx * gi;
             }
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -212,14 +214,14 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
                 for (int j = 0; j < 2; ++j)
                 {
                     gi += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j];
-                    o += u[i] * c.R[i * 2 + j] * u[j];
-                    if (j >= i) H[hidx(3 + i, 3 + j)] += wq * (c.R[i * 2 + j] + c.R[j * 2 + i]);
+                    ou += u[i] * c.R[i * 2 + j] * u[j];
+                    if (j >= i) H[hidx(3 + i, 3 + j)] += wu * (c.R[i * 2 + j] + c.R[j * 2 + i]);
                 }
-                g0[3 + i] += wq * gi; GL[3 + i] += wq * gi;
+                g0[3 + i] += wu * gi; GL[3 + i] += wu * gi;
                 if (integ && c.variable_dt) hb[3 + i] += gi;
             }
-            acc.obj += wq * o;
-            if (integ && c.variable_dt) { acc.gt0 += o; acc.gldt += o; }
+            acc.obj += wx * ox + wu * ou;
+            if (integ && c.variable_dt) { acc.gt0 += fx * ox + ou; acc.gldt += fx * ox + ou; }
         }
         // Lagrangian terms of nu_k^T e_k
         const double fx_nu = nu[0] * J[0] + nu[1] * J[3] + nu[2] * J[6];
@@ -257,6 +259,29 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
                 g0[i] += gi; GL[i] += gi;
             }
             acc.obj += o;
+        }
+        if (has_trapezoid(c))
+        {
+            // end term of the trapezoidal rule: dt/2 * l_x(x_{N-1})
+            const double fx = integral_state_weight(c, N, k);
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double ox = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+                double gi = 0.0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                {
+                    gi += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j];
+                    ox += d[i] * c.Q[i * 3 + j] * d[j];
+                    if (j >= i) H[hidx(i, j)] += dt * fx * (c.Q[i * 3 + j] + c.Q[j * 3 + i]);
+                }
+                g0[i] += dt * fx * gi; GL[i] += dt * fx * gi;
+                if (c.variable_dt) hb[i] += fx * gi;
+            }
+            acc.obj += dt * fx * ox;
+            if (c.variable_dt) { acc.gt0 += fx * ox; acc.gldt += fx * ox; }
         }
         if (has_mintime(c)) { acc.gt0 += (double)(N - 1); acc.gldt += (double)(N - 1); acc.obj += (double)(N - 1) * dt; }
         for (int sl = 0; sl < 8; ++sl)
@@ -506,13 +531,14 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             const double u[2] = {AU(0, k), AU(1, k)};
             const bool integ = c.quadratic_integral_form != 0;
-            const double wq = integ ? ASC(MPCB200_SC_DT) : 1.0;
-            double dl = 0.0, l = 0.0;
+            const double fx = integ ? integral_state_weight(c, N, k) : 1.0;
+            const double wx = integ ? ASC(MPCB200_SC_DT) * fx : 1.0, wu = integ ? ASC(MPCB200_SC_DT) : 1.0;
+            double dlx = 0.0, dlu = 0.0, lx = 0.0, lu = 0.0;
             for (int i = 0; i < 3; ++i)
-                for (int j = 0; j < 3; ++j) { dl += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j] * dx[i]; l += d[i] * c.Q[i * 3 + j] * d[j]; }
+                for (int j = 0; j < 3; ++j) { dlx += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j] * dx[i]; lx += d[i] * c.Q[i * 3 + j] * d[j]; }
             for (int i = 0; i < 2; ++i)
-                for (int j = 0; j < 2; ++j) { dl += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j] * du[i]; l += u[i] * c.R[i * 2 + j] * u[j]; }
-            dJ += wq * dl + ((integ && c.variable_dt) ? l * ddt : 0.0);
+                for (int j = 0; j < 2; ++j) { dlu += (c.R[i * 2 + j] + c.R[j * 2 + i]) * u[j] * du[i]; lu += u[i] * c.R[i * 2 + j] * u[j]; }
+            dJ += wx * dlx + wu * dlu + ((integ && c.variable_dt) ? (fx * lx + lu) * ddt : 0.0);
         }
     }
     else
@@ -523,6 +549,15 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
             for (int i = 0; i < 3; ++i)
                 for (int j = 0; j < 3; ++j) dJ += (c.Qf[i * 3 + j] + c.Qf[j * 3 + i]) * d[j] * dx[i];
+        }
+        if (has_trapezoid(c))
+        {
+            const double fx = integral_state_weight(c, N, k);
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double dlx = 0.0, lx = 0.0;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) { dlx += (c.Q[i * 3 + j] + c.Q[j * 3 + i]) * d[j] * dx[i]; lx += d[i] * c.Q[i * 3 + j] * d[j]; }
+            dJ += ASC(MPCB200_SC_DT) * fx * dlx + (c.variable_dt ? fx * lx * ddt : 0.0);
         }
     }
     if (has_viapoints(c) && k >= 1 && k <= N - 2)
@@ -551,8 +586,8 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
             }
         if (k >= 1 && k <= N - 2)
             for (int i = 0; i < 2; ++i) cv += 2.0 * ASTEP(3 + i, k - 1) * AKKT(MPCB200_K_C + i, k) * du[i];
-        if (c.variable_dt && k <= N - 2)
-            for (int i = 0; i < 5; ++i) cv += 2.0 * ddt * AKKT(MPCB200_K_HB + i, k) * st[i];
+        if (c.variable_dt)  // border (the terminal record carries one only with the trapezoidal rule)
+            for (int i = 0; i < nv; ++i) cv += 2.0 * ddt * AKKT(MPCB200_K_HB + i, k) * st[i];
         if (c.variable_dt && k == N - 1) cv += ddt * ddt * (ASC(MPCB200_SC_HTT) + delta);
         acc.curv += cv;
     }
@@ -587,20 +622,31 @@ HD inline double stage_objective(const Cfg& c, const WsLayout& L, const double* 
         if (has_quadratic(c))
         {
             const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
-            double o = 0.0;
+            double ox = 0.0, ou = 0.0;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) o += d[i] * c.Q[i * 3 + j] * d[j];
+                for (int j = 0; j < 3; ++j) ox += d[i] * c.Q[i * 3 + j] * d[j];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) o += u[i] * c.R[i * 2 + j] * u[j];
-            obj += (c.quadratic_integral_form ? dtt : 1.0) * o;
+                for (int j = 0; j < 2; ++j) ou += u[i] * c.R[i * 2 + j] * u[j];
+            const bool integ = c.quadratic_integral_form != 0;
+            obj += (integ ? dtt * integral_state_weight(c, N, k) : 1.0) * ox + (integ ? dtt : 1.0) * ou;
         }
     }
     else
     {
+        if (has_trapezoid(c))
+        {
+            const double d[3] = {x[0] - xf[0], x[1] - xf[1], normalize_theta(x[2] - xf[2])};
+            double ox = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ox += d[i] * c.Q[i * 3 + j] * d[j];
+            obj += dtt * integral_state_weight(c, N, k) * ox;
+        }
         if (has_mintime(c)) obj += (double)(N - 1) * dtt;
         if (has_terminal_cost(c))
         {

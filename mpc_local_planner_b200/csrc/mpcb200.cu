@@ -921,6 +921,7 @@ extern "C" void mpcb200_default_config(mpcb200_config* c)
     c->enable_dynamic_obstacles = 0;
     c->terminal_ball = 0; c->terminal_ball_gamma = 5.0;
     for (int i = 0; i < 9; ++i) c->terminal_ball_S[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    c->cost_integration = MPCB200_COST_LEFT_SUM;
 }
 
 static int validate_config(const mpcb200_config* c, std::string& why)
@@ -930,6 +931,8 @@ static int validate_config(const mpcb200_config* c, std::string& why)
     if (c->collocation != MPCB200_COLLOC_FORWARD)
     { why = "only forward_differences collocation is implemented (midpoint / crank_nicolson: next round)"; return MPCB200_E_UNSUPPORTED; }
     if (c->objective < 0 || c->objective > 2) { why = "unknown objective"; return MPCB200_E_INVALID; }
+    if (c->cost_integration != MPCB200_COST_LEFT_SUM && c->cost_integration != MPCB200_COST_TRAPEZOIDAL)
+    { why = "unknown cost_integration"; return MPCB200_E_INVALID; }
     if (c->footprint_type < 0 || c->footprint_type > 4) { why = "unknown footprint_type"; return MPCB200_E_INVALID; }
     if (c->footprint_type == MPCB200_FOOTPRINT_POLYGON && (c->n_poly < 1 || c->n_poly > MPCB200_MAX_POLY))
     { why = "polygon footprint needs 1..16 vertices"; return MPCB200_E_INVALID; }

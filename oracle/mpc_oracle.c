@@ -400,6 +400,17 @@ static int has_viapoints(const mpcb200_config* c)
 }
 /* terminal cost edge exists only if x_f is not fully fixed (R/src/optimal_control/finite_differences_grid_se2.cpp:126-131) */
 static int has_terminal_cost(const mpcb200_config* c) { return c->terminal_cost && !xf_all_fixed(c); }
+/* Integral form of the quadratic running cost (R/src/optimal_control/quadratic_cost_se2.cpp:54-84), integrated by the edge
+ * R/src/optimal_control/finite_differences_grid_se2.cpp:57-72 selects: corbo's LeftSumCostEdge, dt l(x_k, u_k), or its
+ * TrapezoidalIntegralCostEdge, dt/2 ( l(x_k, u_k) + l(x_{k+1}, u_k) ) [EXT: both ends use the control of the interval].
+ * Summed over the horizon the state term of stage k carries dt * integral_state_weight, the control term of interval k dt. */
+static int has_trapezoid(const mpcb200_config* c)
+{ return has_quadratic(c) && c->quadratic_integral_form && c->cost_integration == MPCB200_COST_TRAPEZOIDAL; }
+static double integral_state_weight(const mpcb200_config* c, int N, int k)
+{
+    if (c->cost_integration == MPCB200_COST_TRAPEZOIDAL) return (k == 0 || k == N - 1) ? 0.5 : 1.0;
+    return k <= N - 2 ? 1.0 : 0.0;
+}
 
 /*
  * Row slots per stage (RS = 8 + K):
@@ -571,8 +582,15 @@ double orc_objective(const orc_problem* p, const orc_ws* ws, const double* X, co
         {
             double d[3] = {X[IX(0, k)] - p->xf[0], X[IX(1, k)] - p->xf[1], orc_normalize_theta(X[IX(2, k)] - p->xf[2])};
             double u[2] = {U[IX(0, k)], U[IX(1, k)]};
-            /* integral form (quadratic_cost_se2.cpp:54-84 through corbo's LeftSumCostEdge, finite_differences_grid_se2.cpp:66-70): dt * l */
-            J += (c->quadratic_integral_form ? dt : 1.0) * (quad3(c->Q, d) + quad2(c->R, u));
+            /* integral form: dt * (w_k l_x + l_u), w_k by the integration rule (integral_state_weight) */
+            const int integ = c->quadratic_integral_form != 0;
+            J += (integ ? dt * integral_state_weight(c, N, k) : 1.0) * quad3(c->Q, d) + (integ ? dt : 1.0) * quad2(c->R, u);
+        }
+        if (has_trapezoid(c))
+        {
+            int k = N - 1;
+            double d[3] = {X[IX(0, k)] - p->xf[0], X[IX(1, k)] - p->xf[1], orc_normalize_theta(X[IX(2, k)] - p->xf[2])};
+            J += dt * integral_state_weight(c, N, k) * quad3(c->Q, d);
         }
     }
     if (has_terminal_cost(c))
@@ -1168,26 +1186,27 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
         {
             double d[3] = {x[0] - p->xf[0], x[1] - p->xf[1], orc_normalize_theta(x[2] - p->xf[2])};
             const int integ = c->quadratic_integral_form != 0;
-            const double wq = integ ? dt : 1.0;
+            const double fx = integ ? integral_state_weight(c, N, k) : 1.0;
+            const double wx = integ ? dt * fx : 1.0, wu = integ ? dt : 1.0;
             double gxl[3] = {0, 0, 0}, gul[2] = {0, 0};
             for (int i = 0; i < 3; ++i)
             {
                 for (int j = 0; j < 3; ++j) gxl[i] += (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j];
-                for (int j = i; j < 3; ++j) hadd(KKT, N, k, i, j, wq * (c->Q[i * 3 + j] + c->Q[j * 3 + i]));
-                gx[i] = wq * gxl[i];
+                for (int j = i; j < 3; ++j) hadd(KKT, N, k, i, j, wx * (c->Q[i * 3 + j] + c->Q[j * 3 + i]));
+                gx[i] = wx * gxl[i];
             }
             for (int i = 0; i < 2; ++i)
             {
                 for (int j = 0; j < 2; ++j) gul[i] += (c->R[i * 2 + j] + c->R[j * 2 + i]) * u[j];
-                for (int j = i; j < 2; ++j) hadd(KKT, N, k, 3 + i, 3 + j, wq * (c->R[i * 2 + j] + c->R[j * 2 + i]));
-                gu[i] = wq * gul[i];
+                for (int j = i; j < 2; ++j) hadd(KKT, N, k, 3 + i, 3 + j, wu * (c->R[i * 2 + j] + c->R[j * 2 + i]));
+                gu[i] = wu * gul[i];
             }
             if (integ && c->variable_dt)
             {
-                /* d/ddt of dt * l is l; the w-dt cross Hessian is grad l */
-                const double l = quad3(c->Q, d) + quad2(c->R, u);
+                /* d/ddt of dt * (w l_x + l_u) is w l_x + l_u; the w-dt cross Hessian is its gradient */
+                const double l = fx * quad3(c->Q, d) + quad2(c->R, u);
                 gt0 += l; gl_dt += l;
-                for (int i = 0; i < 3; ++i) KK(MPCB200_K_HB + i, k) += gxl[i];
+                for (int i = 0; i < 3; ++i) KK(MPCB200_K_HB + i, k) += fx * gxl[i];
                 for (int i = 0; i < 2; ++i) KK(MPCB200_K_HB + 3 + i, k) += gul[i];
             }
         }
@@ -1229,6 +1248,23 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
             GL[IX(i, k)] += g;
             for (int j = i; j < 3; ++j) hadd(KKT, N, k, i, j, c->Qf[i * 3 + j] + c->Qf[j * 3 + i]);
         }
+    }
+    /* end term of the trapezoidal rule: dt/2 l_x(x_{N-1}) */
+    if (has_trapezoid(c))
+    {
+        int k = N - 1;
+        const double fx = integral_state_weight(c, N, k);
+        double d[3] = {ws->X[IX(0, k)] - p->xf[0], ws->X[IX(1, k)] - p->xf[1], orc_normalize_theta(ws->X[IX(2, k)] - p->xf[2])};
+        for (int i = 0; i < 3; ++i)
+        {
+            double g = 0;
+            for (int j = 0; j < 3; ++j) g += (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j];
+            KK(MPCB200_K_G + i, k) += dt * fx * g;
+            GL[IX(i, k)] += dt * fx * g;
+            for (int j = i; j < 3; ++j) hadd(KKT, N, k, i, j, dt * fx * (c->Q[i * 3 + j] + c->Q[j * 3 + i]));
+            if (c->variable_dt) KK(MPCB200_K_HB + i, k) += fx * g;
+        }
+        if (c->variable_dt) { gt0 += fx * quad3(c->Q, d); gl_dt += fx * quad3(c->Q, d); }
     }
     /* via-points */
     if (has_viapoints(c))
@@ -1459,6 +1495,8 @@ int orc_kkt_solve(const orc_problem* p, orc_ws* ws, double delta)
         {
             PI[i * 5 + 0] = c->xf_fixed[i] ? 0.0 : KK(MPCB200_K_G + i, k);
             if (c->xf_fixed[i]) PI[i * 5 + 2 + i] = 1.0;
+            /* x_{N-1} - dt cross term: end term of the trapezoidal cost rule */
+            if (dt_free && has_trapezoid(c) && !c->xf_fixed[i]) PI[i * 5 + 1] = KK(MPCB200_K_HB + i, k);
         }
         TH[0 * 5 + 1] = TH[1 * 5 + 0] = ws->SCAL[MPCB200_SC_GT];
         TH[1 * 5 + 1] = ws->SCAL[MPCB200_SC_HTT] + delta;
@@ -1769,13 +1807,24 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
                 {
                     double d[3] = {ws->X[IX(0, k)] - p->xf[0], ws->X[IX(1, k)] - p->xf[1], orc_normalize_theta(ws->X[IX(2, k)] - p->xf[2])};
                     double u[2] = {ws->U[IX(0, k)], ws->U[IX(1, k)]};
-                    const double wq = c->quadratic_integral_form ? dt : 1.0;
+                    const int integ = c->quadratic_integral_form != 0;
+                    const double fx = integ ? integral_state_weight(c, N, k) : 1.0;
+                    const double wx = integ ? dt * fx : 1.0, wu = integ ? dt : 1.0;
                     for (int i = 0; i < 3; ++i)
-                        for (int j = 0; j < 3; ++j) dJ += wq * (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j] * ws->STEP[IX(i, k)];
+                        for (int j = 0; j < 3; ++j) dJ += wx * (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j] * ws->STEP[IX(i, k)];
                     for (int i = 0; i < 2; ++i)
-                        for (int j = 0; j < 2; ++j) dJ += wq * (c->R[i * 2 + j] + c->R[j * 2 + i]) * u[j] * ws->STEP[IX(3 + i, k)];
-                    if (c->quadratic_integral_form && c->variable_dt) dJ += (quad3(c->Q, d) + quad2(c->R, u)) * ddt;
+                        for (int j = 0; j < 2; ++j) dJ += wu * (c->R[i * 2 + j] + c->R[j * 2 + i]) * u[j] * ws->STEP[IX(3 + i, k)];
+                    if (integ && c->variable_dt) dJ += (fx * quad3(c->Q, d) + quad2(c->R, u)) * ddt;
                 }
+            if (has_trapezoid(c))
+            {
+                int k = N - 1;
+                const double fx = integral_state_weight(c, N, k);
+                double d[3] = {ws->X[IX(0, k)] - p->xf[0], ws->X[IX(1, k)] - p->xf[1], orc_normalize_theta(ws->X[IX(2, k)] - p->xf[2])};
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) dJ += dt * fx * (c->Q[i * 3 + j] + c->Q[j * 3 + i]) * d[j] * ws->STEP[IX(i, k)];
+                if (c->variable_dt) dJ += fx * quad3(c->Q, d) * ddt;
+            }
             if (has_terminal_cost(c))
             {
                 int k = N - 1;
@@ -1808,8 +1857,8 @@ static int orc_solve_monotone(const orc_problem* p, orc_ws* ws, orc_result* res,
                     }
                 if (k >= 1 && k <= N - 2)
                     for (int i = 0; i < 2; ++i) curv += 2.0 * ws->STEP[IX(3 + i, k - 1)] * KKT[(MPCB200_K_C + i) * N + k] * ws->STEP[IX(3 + i, k)];
-                if (c->variable_dt && k <= N - 2)
-                    for (int i = 0; i < 5; ++i) curv += 2.0 * ddt * KKT[(MPCB200_K_HB + i) * N + k] * ws->STEP[IX(i, k)];
+                if (c->variable_dt) /* border; the terminal record carries one only with the trapezoidal rule */
+                    for (int i = 0; i < nv; ++i) curv += 2.0 * ddt * KKT[(MPCB200_K_HB + i) * N + k] * ws->STEP[IX(i, k)];
             }
             if (c->variable_dt) curv += ddt * ddt * (ws->SCAL[MPCB200_SC_HTT] + ws->SCAL[MPCB200_SC_DELTA]);
         }

@@ -238,10 +238,14 @@ def test_footprint_distance_to_line_obstacle(orc, kind):
 
 def _random_iterate(orc, cid, b, seed):
     """cid 21 / 22 / 23: cfg 2 with the integral-form cost + free dt / the terminal ball / moving obstacles + free dt;
+    cid 24 / 25: integral form integrated by the trapezoidal rule, free / fixed dt;
     cid 31: cfg 3 (car-like minimum time, polygon footprint) with moving obstacles"""
     moving = cid in (23, 31)
-    cfg = configs.cfg2_integral_form(tol=1e-8) if cid in (21, 23) else (configs.cfg2_terminal_ball(tol=1e-8) if cid == 22 else configs.config_for(3 if cid == 31 else cid, tol=1e-8))
-    cid = 2 if cid in (21, 22, 23) else (3 if cid == 31 else cid)
+    if cid in (24, 25):
+        cfg = configs.cfg2_trapezoidal(tol=1e-8, variable_dt=cid == 24)
+    else:
+        cfg = configs.cfg2_integral_form(tol=1e-8) if cid in (21, 23) else (configs.cfg2_terminal_ball(tol=1e-8) if cid == 22 else configs.config_for(3 if cid == 31 else cid, tol=1e-8))
+    cid = 2 if cid in (21, 22, 23, 24, 25) else (3 if cid == 31 else cid)
     data = configs.g1_instance() if cid == 1 else configs.generate(cid, b + 1)
     if moving:
         cfg.enable_dynamic_obstacles = 1
@@ -276,7 +280,30 @@ def _lagrangian(inst):
     return S[capi.SC_OBJ] + (inst.arr("NU")[:, :N - 1] * e).sum() + (inst.arr("LAM") * (inst.arr("G") + inst.arr("S")) * (inst.arr("LAM") > 0)).sum()
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22, 23, 31])
+@pytest.mark.parametrize("rule", ["left_sum", "trapezoidal"])
+def test_integral_form_objective_is_the_edge_sum(orc, rule):
+    """The objective of the integral form against the sum of the reference's per-interval cost edges written out in numpy
+    (finite_differences_grid_se2.cpp:57-72): left sum dt l(x_k, u_k); trapezoid dt/2 (l(x_k, u_k) + l(x_{k+1}, u_k))."""
+    inst, cfg = _random_iterate(orc, 24 if rule == "trapezoidal" else 21, 1, 3)
+    inst.eval()
+    N = inst.N
+    X = inst.arr("X"); U = inst.arr("U"); dt = inst.arr("SCAL")[capi.SC_DT]
+    xf = configs.generate(2, 2)["xf"][1]
+    Q = np.array(cfg.Q[:]).reshape(3, 3); R = np.array(cfg.R[:]).reshape(2, 2); Qf = np.array(cfg.Qf[:]).reshape(3, 3)
+
+    def d(k):
+        v = X[:, k] - xf
+        v[2] = (v[2] + np.pi) % (2 * np.pi) - np.pi
+        return v
+    l = lambda k, j: d(k) @ Q @ d(k) + U[:, j] @ R @ U[:, j]
+    J = 0.0
+    for k in range(N - 1):
+        J += dt * l(k, k) if rule == "left_sum" else 0.5 * dt * (l(k, k) + l(k + 1, k))
+    J += d(N - 1) @ Qf @ d(N - 1)
+    assert abs(inst.arr("SCAL")[capi.SC_OBJ] - J) < 1e-10 * max(1.0, abs(J))
+
+
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22, 23, 24, 25, 31])
 def test_lagrangian_gradient_and_newton_step(orc, cid):
     """Analytic Lagrangian gradient vs finite differences; the Riccati Newton step (incl. the dt border and the fixed
     terminal state) vs a dense numpy solve of the full KKT system assembled by finite differences."""
