@@ -145,6 +145,10 @@ typedef struct mpcb200_config {
        MPCB200_COST_TRAPEZOIDAL         sum_{k<=N-2} dt/2 ( l(x_k, u_k) + l(x_{k+1}, u_k) ) (finite_differences_grid_se2.cpp:59-65;
        corbo's TrapezoidalIntegralCostEdge evaluates both ends with the control of the interval). */
     int cost_integration;
+    /* planning/objective/quadratic_form/hybrid_cost_minimum_time (src/controller.cpp:595-620): adds the minimum-time term
+       (N-1) dt to the quadratic control cost.  As in the reference it takes effect only with zero state weights Q and
+       non-zero control weights R (and needs variable_dt); with any other weights the plain quadratic form is used. */
+    int hybrid_cost_minimum_time;
 } mpcb200_config;
 
 /* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]). */

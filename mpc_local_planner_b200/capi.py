@@ -83,6 +83,7 @@ class Config(C.Structure):
         ("terminal_ball_S", C.c_double * 9),
         ("terminal_ball_gamma", C.c_double),
         ("cost_integration", C.c_int),
+        ("hybrid_cost_minimum_time", C.c_int),
     ]
 
     def copy(self):
@@ -142,6 +143,7 @@ def default_config():
         c.terminal_ball_S[i] = 1.0 if i % 4 == 0 else 0.0
     c.terminal_ball_gamma = 5.0
     c.cost_integration = COST_LEFT_SUM
+    c.hybrid_cost_minimum_time = 0
     return c
 
 

@@ -192,6 +192,20 @@ def cfg2_trapezoidal(n=50, tol=1e-6, variable_dt=True):
     return c
 
 
+def cfg2_hybrid_min_time(n=50, tol=1e-6, integral_form=False):
+    """cfg 2 as `quadratic_form/hybrid_cost_minimum_time: true` allows it (src/controller.cpp:595-620): zero state weights,
+    control weights R, the minimum-time term, a free dt in [0.05, 1.0] s and a fixed final state (without state weights nothing
+    else pulls the robot to the goal; the terminal cost edge disappears with it) -- not a BASELINE configuration."""
+    c = cfg2(n, tol)
+    for i in range(9):
+        c.Q[i] = 0.0
+    c.hybrid_cost_minimum_time = 1
+    c.quadratic_integral_form = int(integral_form)
+    c.variable_dt, c.dt_lb, c.dt_ub = 1, 0.05, 1.0
+    c.xf_fixed[0] = c.xf_fixed[1] = c.xf_fixed[2] = 1
+    return c
+
+
 def cfg2_terminal_ball(n=50, tol=1e-6, gamma=0.05):
     """cfg 2 with `planning/terminal_constraint/type: l2_ball` (TerminalBallSE2: d' S d - gamma <= 0 on the final state),
     S = diag(1, 1, 0.5) -- not a BASELINE configuration."""

@@ -428,9 +428,20 @@ HD inline int clip_threshold_bin(const int* hist, int rows)
 // ---- config predicates ----
 HD inline bool xf_all_fixed(const Cfg& c) { return c.xf_fixed[0] && c.xf_fixed[1] && c.xf_fixed[2]; }
 HD inline bool has_quadratic(const Cfg& c) { return c.objective == MPCB200_OBJ_QUADRATIC_FORM; }
+// quadratic_form/hybrid_cost_minimum_time (src/controller.cpp:595-620): honoured only for zero state weights and non-zero
+// control weights (corbo::MinTimeQuadraticControls: dt per interval + the quadratic control term); otherwise the reference
+// logs an error and falls back to the plain quadratic form
+HD inline bool has_hybrid_mintime(const Cfg& c)
+{
+    if (!c.hybrid_cost_minimum_time || c.objective != MPCB200_OBJ_QUADRATIC_FORM) return false;
+    bool qz = true, rz = true;
+    for (int i = 0; i < 9; ++i) qz = qz && c.Q[i] == 0.0;
+    for (int i = 0; i < 4; ++i) rz = rz && c.R[i] == 0.0;
+    return qz && !rz;
+}
 HD inline bool has_mintime(const Cfg& c)
 {
-    return c.objective == MPCB200_OBJ_MINIMUM_TIME || c.objective == MPCB200_OBJ_MINIMUM_TIME_VIA_POINTS;
+    return c.objective == MPCB200_OBJ_MINIMUM_TIME || c.objective == MPCB200_OBJ_MINIMUM_TIME_VIA_POINTS || has_hybrid_mintime(c);
 }
 HD inline bool has_viapoints(const Cfg& c)
 {

@@ -922,6 +922,7 @@ extern "C" void mpcb200_default_config(mpcb200_config* c)
     c->terminal_ball = 0; c->terminal_ball_gamma = 5.0;
     for (int i = 0; i < 9; ++i) c->terminal_ball_S[i] = (i % 4 == 0) ? 1.0 : 0.0;
     c->cost_integration = MPCB200_COST_LEFT_SUM;
+    c->hybrid_cost_minimum_time = 0;
 }
 
 static int validate_config(const mpcb200_config* c, std::string& why)

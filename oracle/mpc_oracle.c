@@ -389,9 +389,20 @@ static double footprint_distance_line(const mpcb200_config* cfg, const double* p
 
 static int xf_all_fixed(const mpcb200_config* c) { return c->xf_fixed[0] && c->xf_fixed[1] && c->xf_fixed[2]; }
 static int has_quadratic(const mpcb200_config* c) { return c->objective == MPCB200_OBJ_QUADRATIC_FORM; }
+/* planning/objective/quadratic_form/hybrid_cost_minimum_time: R/src/controller.cpp:595-620 installs corbo's
+ * MinTimeQuadraticControls [EXT: dt per interval + the quadratic control term] only when Q is zero and R is not; in every
+ * other case it logs an error and keeps the plain quadratic form. */
+static int has_hybrid_mintime(const mpcb200_config* c)
+{
+    if (!c->hybrid_cost_minimum_time || c->objective != MPCB200_OBJ_QUADRATIC_FORM) return 0;
+    int qz = 1, rz = 1;
+    for (int i = 0; i < 9; ++i) qz = qz && c->Q[i] == 0.0;
+    for (int i = 0; i < 4; ++i) rz = rz && c->R[i] == 0.0;
+    return qz && !rz;
+}
 static int has_mintime(const mpcb200_config* c)
 {
-    return c->objective == MPCB200_OBJ_MINIMUM_TIME || c->objective == MPCB200_OBJ_MINIMUM_TIME_VIA_POINTS;
+    return c->objective == MPCB200_OBJ_MINIMUM_TIME || c->objective == MPCB200_OBJ_MINIMUM_TIME_VIA_POINTS || has_hybrid_mintime(c);
 }
 static int has_viapoints(const mpcb200_config* c)
 {

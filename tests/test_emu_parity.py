@@ -131,11 +131,11 @@ def test_line_obstacles_match_oracle(orc, emu, cid, B):
     assert agree >= B - 1
 
 
-@pytest.mark.parametrize("rule", ["left_sum", "trapezoidal"])
+@pytest.mark.parametrize("rule", ["left_sum", "trapezoidal", "hybrid_min_time"])
 def test_integral_form_cost_matches_oracle(orc, emu, rule):
-    """quadratic_form/integral_form (left sum or trapezoidal rule) with a free dt: records of the first evaluation and
-    whole solves."""
-    cfg = configs.cfg2_integral_form(tol=1e-8) if rule == "left_sum" else configs.cfg2_trapezoidal(tol=1e-8)
+    """quadratic_form/integral_form (left sum or trapezoidal rule) with a free dt, and the hybrid minimum-time + quadratic
+    control cost: records of the first evaluation and whole solves."""
+    cfg = {"left_sum": configs.cfg2_integral_form, "trapezoidal": configs.cfg2_trapezoidal, "hybrid_min_time": configs.cfg2_hybrid_min_time}[rule](tol=1e-8)
     B = 8
     data = configs.generate(2, B)
     ref = orc.step_batch(cfg, data, n_threads=2)

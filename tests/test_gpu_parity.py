@@ -335,11 +335,14 @@ def test_line_obstacles(cuda_lib, orc, cid, B):
     s.close()
 
 
-@pytest.mark.parametrize("rule", ["left_sum", "trapezoidal", "trapezoidal_fixed_dt"])
+@pytest.mark.parametrize("rule", ["left_sum", "trapezoidal", "trapezoidal_fixed_dt", "hybrid_min_time"])
 def test_integral_form_cost(cuda_lib, orc, rule):
-    """quadratic_form/integral_form (left sum / trapezoidal rule) with a free dt, and the trapezoidal rule at the fixed dt of
-    cfg 2, through the C ABI against the oracle."""
-    cfg = configs.cfg2_integral_form(tol=1e-8) if rule == "left_sum" else configs.cfg2_trapezoidal(tol=1e-8, variable_dt=rule == "trapezoidal")
+    """quadratic_form/integral_form (left sum / trapezoidal rule) with a free dt, the trapezoidal rule at the fixed dt of
+    cfg 2, and the hybrid minimum-time + quadratic control cost, through the C ABI against the oracle."""
+    if rule == "hybrid_min_time":
+        cfg = configs.cfg2_hybrid_min_time(tol=1e-8)
+    else:
+        cfg = configs.cfg2_integral_form(tol=1e-8) if rule == "left_sum" else configs.cfg2_trapezoidal(tol=1e-8, variable_dt=rule == "trapezoidal")
     B = 32
     data = configs.generate(2, B)
     s = _solver(cfg, B)

@@ -239,13 +239,16 @@ def test_footprint_distance_to_line_obstacle(orc, kind):
 def _random_iterate(orc, cid, b, seed):
     """cid 21 / 22 / 23: cfg 2 with the integral-form cost + free dt / the terminal ball / moving obstacles + free dt;
     cid 24 / 25: integral form integrated by the trapezoidal rule, free / fixed dt;
+    cid 26 / 27: hybrid minimum-time + quadratic control cost (Q = 0, fixed final state), point / integral form;
     cid 31: cfg 3 (car-like minimum time, polygon footprint) with moving obstacles"""
     moving = cid in (23, 31)
     if cid in (24, 25):
         cfg = configs.cfg2_trapezoidal(tol=1e-8, variable_dt=cid == 24)
+    elif cid in (26, 27):
+        cfg = configs.cfg2_hybrid_min_time(tol=1e-8, integral_form=cid == 27)
     else:
         cfg = configs.cfg2_integral_form(tol=1e-8) if cid in (21, 23) else (configs.cfg2_terminal_ball(tol=1e-8) if cid == 22 else configs.config_for(3 if cid == 31 else cid, tol=1e-8))
-    cid = 2 if cid in (21, 22, 23, 24, 25) else (3 if cid == 31 else cid)
+    cid = 2 if cid in (21, 22, 23, 24, 25, 26, 27) else (3 if cid == 31 else cid)
     data = configs.g1_instance() if cid == 1 else configs.generate(cid, b + 1)
     if moving:
         cfg.enable_dynamic_obstacles = 1
@@ -303,7 +306,7 @@ def test_integral_form_objective_is_the_edge_sum(orc, rule):
     assert abs(inst.arr("SCAL")[capi.SC_OBJ] - J) < 1e-10 * max(1.0, abs(J))
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22, 23, 24, 25, 31])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22, 23, 24, 25, 26, 27, 31])
 def test_lagrangian_gradient_and_newton_step(orc, cid):
     """Analytic Lagrangian gradient vs finite differences; the Riccati Newton step (incl. the dt border and the fixed
     terminal state) vs a dense numpy solve of the full KKT system assembled by finite differences."""
