@@ -212,6 +212,23 @@ int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* x0, const d
 /* Replaces Controller::reset (inc/controller.h:104): which == NULL resets every instance, else those with which[b] != 0. */
 int mpcb200_reset(mpcb200_handle* h, const unsigned char* which, int B);
 
+/*
+ * Horizon change of the whole batch: replaces FullDiscretizationGridBaseSE2::resampleTrajectory(n_new)
+ * (src/optimal_control/full_discretization_grid_base_se2.cpp:440-524), the operation behind the grid adaptation of the
+ * variable grid (FiniteDifferencesVariableGridSE2::adaptGridTimeBasedSingleStep,
+ * src/optimal_control/finite_differences_variable_grid_se2.cpp:99-121: n + 1 when the optimised dt exceeds
+ * dt_ref (1 + dt_hyst_ratio), n - 1 when it falls below dt_ref (1 - dt_hyst_ratio); the policy itself lives with the caller,
+ * include/mpcb200_controller.hpp).  Every warm trajectory of the handle is resampled on the device to n_new grid points
+ * over the same horizon time (dt becomes dt (n-1)/(n_new-1)); empty (reset / never solved) instances just take the new
+ * horizon.  From the next mpcb200_step_batch on every per-instance array has n_new samples.  All instances of a handle
+ * share the horizon: robots that adapt independently are grouped by n (one handle per group).
+ * n_new must lie in [3, n the handle was created with] -- create the handle with config.n = grid/variable_grid/
+ * grid_adaptation/max_grid_size and call mpcb200_resample(h, grid_size_ref) once before the first step.
+ */
+int mpcb200_resample(mpcb200_handle* h, int n_new);
+/* current horizon and the capacity (config.n at create) */
+int mpcb200_get_horizon(const mpcb200_handle* h, int* n, int* n_capacity);
+
 void mpcb200_destroy(mpcb200_handle* h);
 
 /* Last error message of this handle (or of create() when h == NULL). Never NULL. */

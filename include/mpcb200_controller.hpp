@@ -59,6 +59,14 @@ struct ControllerParams
     bool allow_init_with_backward_motion = true;
     bool global_plan_overwrite_orientation = true;  // _initial_plan_estimate_orientation
     bool print_cpu_time = false;
+    // grid/variable_grid/grid_adaptation/* (src/controller.cpp:247-262; used only with a variable grid, config.variable_dt):
+    // TimeBasedSingleStep with adapt_first_iter = true -- before every step but the first after a (re-)initialisation the
+    // horizon grows by one grid point when the last optimal dt exceeds dt_ref (1 + dt_hyst_ratio) and shrinks by one when
+    // it is below dt_ref (1 - dt_hyst_ratio) (finite_differences_variable_grid_se2.cpp:99-121).  The reference's defaults.
+    bool grid_adaptation = true;
+    int max_grid_size = 50;
+    int min_grid_size = 2;   // the solver needs 3 grid points: values below 3 act as 3
+    double dt_hyst_ratio = 0.1;
 };
 
 // initial state trajectory from an initial plan (Controller::generateInitialStateTrajectory, src/controller.cpp:807-857,
@@ -115,13 +123,19 @@ class Controller
     {
         if (_h) { mpcb200_destroy(_h); _h = nullptr; }
         _cfg = cfg; _params = params; _obstacles = obstacles; _via_points = via_points;
-        const int rc = mpcb200_create(&_cfg, 1, device, &_h);
+        _n_ref = cfg.n;
+        _adapt = params.grid_adaptation && cfg.variable_dt;
+        // with grid adaptation the handle is sized for the largest horizon and starts at grid_size_ref
+        mpcb200_config cap = cfg;
+        if (_adapt && params.max_grid_size > cap.n) cap.n = params.max_grid_size;
+        int rc = mpcb200_create(&cap, 1, device, &_h);
         if (rc != MPCB200_OK)
         {
             std::fprintf(stderr, "Controller::configure(): %s\n", mpcb200_last_error(nullptr));
             _h = nullptr;
             return false;
         }
+        if (!setHorizon(_n_ref)) return false;
         _ocp_seq = 0; _grid_empty = true; _ocp_successful = false;
         return true;
     }
@@ -163,6 +177,23 @@ class Controller
         }
         unsigned char reinit = 0;
         const double* x_init_ptr = nullptr;
+        if (_grid_empty)
+        {
+            // FullDiscretizationGridBaseSE2::clear() forgets the adapted grid size: initialisation uses grid_size_ref again
+            // (full_discretization_grid_base_se2.cpp:153,526-536)
+            if (!setHorizon(_n_ref)) return false;
+        }
+        else if (_adapt)
+        {
+            // FiniteDifferencesVariableGridSE2::adaptGridTimeBasedSingleStep (finite_differences_variable_grid_se2.cpp:99-121),
+            // called at the start of the grid update of a non-empty grid (full_discretization_grid_base_se2.cpp:52-56)
+            const int n = _cfg.n, n_min = _params.min_grid_size < 3 ? 3 : _params.min_grid_size;
+            int n_max = 0;
+            mpcb200_get_horizon(_h, nullptr, &n_max);
+            if (_params.max_grid_size < n_max) n_max = _params.max_grid_size;
+            if (_last_dt > _cfg.dt_ref * (1.0 + _params.dt_hyst_ratio) && n < n_max) { if (!setHorizon(n + 1)) return false; }
+            else if (_last_dt < _cfg.dt_ref * (1.0 - _params.dt_hyst_ratio) && n > n_min) { if (!setHorizon(n - 1)) return false; }
+        }
         if (_grid_empty)
         {
             const bool backward = _params.allow_init_with_backward_motion &&
@@ -233,6 +264,7 @@ class Controller
     }
 
     bool isOptimizationSuccessful() const { return _ocp_successful; }
+    int gridSize() const { return _cfg.n; }  // current number of grid points (getN())
     double lastDt() const { return _last_dt; }
     int lastStatus() const { return _last_status; }
     int lastIterations() const { return _last_iters; }
@@ -240,6 +272,19 @@ class Controller
     double lastSolveTime() const { return _last_solve_time; }
 
  private:
+    // resampleTrajectory(n) on the device (or just the new horizon for an empty grid); _cfg.n follows
+    bool setHorizon(int n)
+    {
+        if (n == _cfg.n) { int cur = 0; mpcb200_get_horizon(_h, &cur, nullptr); if (cur == n) return true; }
+        const int rc = mpcb200_resample(_h, n);
+        if (rc != MPCB200_OK)
+        {
+            std::fprintf(stderr, "Controller: horizon change to %d grid points failed: %s\n", n, mpcb200_last_error(_h));
+            return false;
+        }
+        _cfg.n = n;
+        return true;
+    }
     static void fill(TimeSeries& ts, const std::vector<double>& v, int dim, int N, double dt)
     {
         ts.clear(); ts.dim = dim;
@@ -256,6 +301,8 @@ class Controller
     std::vector<double> _x_init, _u, _x;
     PoseSE2 _last_goal;
     int _ocp_seq = 0;
+    int _n_ref = 0;       // grid/grid_size_ref
+    bool _adapt = false;  // grid adaptation active (variable grid + grid_adaptation/enable)
     bool _grid_empty = true, _ocp_successful = false;
     double _last_dt = 0, _last_kkt = 0, _last_solve_time = 0;
     int _last_status = -1, _last_iters = 0;

@@ -180,6 +180,7 @@ EXPORTS = [
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
     "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
+    "mpcb200_resample", "mpcb200_get_horizon",
 ]
 
 
@@ -204,6 +205,8 @@ def load_library(path=None):
     lib.mpcb200_solve_stream.argtypes = [vp, C.c_int, dp, dp, dp, C.c_double, C.POINTER(Obstacles), C.POINTER(ViaPoints),
                                          dp, dp, dp, ip, dp, ip, dp]
     lib.mpcb200_reset.argtypes = [vp, ucp, C.c_int]
+    lib.mpcb200_resample.argtypes = [vp, C.c_int]
+    lib.mpcb200_get_horizon.argtypes = [vp, ip, ip]
     lib.mpcb200_destroy.argtypes = [vp]
     lib.mpcb200_destroy.restype = None
     lib.mpcb200_last_error.argtypes = [vp]
@@ -347,6 +350,16 @@ class BatchSolver:
             w = np.ascontiguousarray(which, dtype=np.uint8)
         self._check(self.lib.mpcb200_reset(self.h, w.ctypes.data_as(C.POINTER(C.c_ubyte)) if w is not None else None,
                                            self.B), "mpcb200_reset")
+
+    def resample(self, n_new):
+        """resampleTrajectory(n_new) for every instance: the horizon of the batch becomes n_new (<= cfg.n at create)."""
+        self._check(self.lib.mpcb200_resample(self.h, int(n_new)), "mpcb200_resample")
+        self.N = self.horizon()[0]
+
+    def horizon(self):
+        n, cap = C.c_int(0), C.c_int(0)
+        self._check(self.lib.mpcb200_get_horizon(self.h, C.byref(n), C.byref(cap)), "mpcb200_get_horizon")
+        return n.value, cap.value
 
     # kernel-level access ------------------------------------------------------------------------------------
     def ws_count(self, field):

@@ -907,6 +907,35 @@ HD inline void warm_shift_serial(const Cfg& c, const WsLayout& L, double* W)
         if (c.xf_fixed[i]) AX(i, N - 1) = xf[i];
 }
 
+// Horizon change of a warm trajectory (FullDiscretizationGridBaseSE2::resampleTrajectory,
+// full_discretization_grid_base_se2.cpp:440-524; the grid adaptation of the variable grid calls it with n +- 1,
+// finite_differences_variable_grid_se2.cpp:99-121).  The horizon time is kept, dt_new = dt (n-1)/(n_new-1); sample
+// idx_new sits at t = idx_new dt_new on the old polyline (positions linear, heading by interpolate_angle), its control is
+// the one of the old interval it falls into; the first sample and the final state are carried over.
+// Xo/Uo: old trajectory, component-major with n columns (column n-1 of Xo = the final-state vertex); Xn/Un: n_new columns.
+// A non-positive old dt (never produced by a solve with dt_lb > 0) would divide by zero in the reference; here the new
+// samples then collapse onto the old sample 0.  Returns dt_new.
+HD inline double resample_serial(int n, const double* Xo, const double* Uo, double dt_old, int n_new, double* Xn, double* Un)
+{
+    const double dt_new = dt_old * (double)(n - 1) / (double)(n_new - 1);
+    for (int i = 0; i < 3; ++i) { Xn[i * n_new] = Xo[i * n]; Xn[i * n_new + n_new - 1] = Xo[i * n + n - 1]; }
+    for (int j = 0; j < 2; ++j) { Un[j * n_new] = Uo[j * n]; Un[j * n_new + n_new - 1] = 0.0; }
+    int idx_old = 1;
+    for (int idx_new = 1; idx_new < n_new - 1; ++idx_new)
+    {
+        const double t_new = dt_new * (double)idx_new;
+        while (t_new > (double)idx_old * dt_old && idx_old < n) ++idx_old;  // old sample that follows t_new
+        const double t_old_p1 = (double)idx_old * dt_old;
+        const double f = dt_old > 0.0 ? (t_new - (t_old_p1 - dt_old)) / dt_old : 0.0;
+        const int p = idx_old - 1 < n - 1 ? idx_old - 1 : n - 1, q = idx_old < n - 1 ? idx_old : n - 1;
+        for (int i = 0; i < 2; ++i) Xn[i * n_new + idx_new] = Xo[i * n + p] + f * (Xo[i * n + q] - Xo[i * n + p]);
+        Xn[2 * n_new + idx_new] = interpolate_angle(Xo[2 * n + p], Xo[2 * n + q], f);
+        const int pu = idx_old - 1 < n - 2 ? idx_old - 1 : n - 2;  // the time series repeats the last control at sample n-1
+        for (int j = 0; j < 2; ++j) Un[j * n_new + idx_new] = Uo[j * n + pu];
+    }
+    return dt_new;
+}
+
 // obstacle association of stage k
 HD inline void associate_stage(const Cfg& c, const WsLayout& L, double* W, int k)
 {

@@ -836,6 +836,30 @@ __global__ void reset_kernel(WsLayout L, double* ws, int B, const unsigned char*
     ASC(MPCB200_SC_STATUS) = -1.0;
 }
 
+// ---- horizon change (grid adaptation): pack the warm trajectories, switch the layout, resample into the new one ----
+// record per instance: SCAL words, X (3 x n_old), U (2 x n_old)
+__global__ void resample_pack_kernel(WsLayout L, const double* ws, double* rec, int rec_words, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* W = ws + (int64_t)b * L.stride;
+    double* r = rec + (size_t)b * rec_words;
+    const int N = L.N;
+    for (int i = 0; i < MPCB200_SCAL_WORDS; ++i) r[i] = W[L.oSCAL + i];
+    for (int i = 0; i < 3 * N; ++i) r[MPCB200_SCAL_WORDS + i] = W[L.oX + i];
+    for (int i = 0; i < 2 * N; ++i) r[MPCB200_SCAL_WORDS + 3 * N + i] = W[L.oU + i];
+}
+__global__ void resample_unpack_kernel(WsLayout L, double* ws, const double* rec, int rec_words, int n_old, int B)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* W = ws + (int64_t)b * L.stride;
+    const double* r = rec + (size_t)b * rec_words;
+    for (int i = 0; i < MPCB200_SCAL_WORDS; ++i) W[L.oSCAL + i] = r[i];
+    if (ASC(MPCB200_SC_COLD) != 0.0) return;  // empty grid: the next step initialises it at the new horizon
+    ASC(MPCB200_SC_DT) = resample_serial(n_old, r + MPCB200_SCAL_WORDS, r + MPCB200_SCAL_WORDS + 3 * n_old, r[MPCB200_SC_DT], L.N, W + L.oX, W + L.oU);
+}
+
 __global__ void flush_kernel(double* buf, size_t n)
 {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -850,6 +874,8 @@ struct mpcb200_handle
     Cfg cfg;
     WsLayout L;
     int max_batch, device, B;
+    int n_cap;                  // horizon the buffers were sized for at create (mpcb200_resample moves cfg.n within [3, n_cap])
+    double* d_resample;         // scratch of mpcb200_resample, allocated on first use
     double* ws;
     double *kkt_tiles, *ric_tiles;
     size_t ric_attempt_stride;  // doubles between the gain tiles of KKT attempt 0 and 1 (speculative mode)
@@ -964,6 +990,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->kkt_tiles = nullptr; h->ric_tiles = nullptr; h->ev_used = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
+    h->n_cap = cfg->n; h->d_resample = nullptr;
     h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
@@ -1040,7 +1067,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
                     h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush, h->d_counters, h->d_slot_of, h->d_inst_of_slot};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* sptrs[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
-                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_slot_inst, h->d_stream_counters};
+                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_slot_inst, h->d_stream_counters, h->d_resample};
     for (void* p : sptrs) if (p) cudaFree(p);
     if (h->h_stream_counters) cudaFreeHost(h->h_stream_counters);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
@@ -1293,7 +1320,7 @@ static int stream_reserve(mpcb200_handle* h, size_t total)
     void* old[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
                    h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters};
     for (void* p : old) if (p) cudaFree(p);
-    const size_t N = (size_t)h->cfg.n, T = total;
+    const size_t N = (size_t)h->n_cap, T = total;  // sized for the largest horizon the handle can be resampled to
     CK(cudaMalloc(&h->s_x0, T * 3 * 8)); CK(cudaMalloc(&h->s_xf, T * 3 * 8)); CK(cudaMalloc(&h->s_uprev, T * 2 * 8));
     CK(cudaMalloc(&h->s_obst, T * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CK(cudaMalloc(&h->s_obst_count, T * 4)); CK(cudaMalloc(&h->s_obst_type, T * MAX_OBST * 4));
     CK(cudaMalloc(&h->s_vp, T * MAX_VP * 3 * 8)); CK(cudaMalloc(&h->s_vp_count, T * 4));
@@ -1492,6 +1519,33 @@ extern "C" int mpcb200_reset(mpcb200_handle* h, const unsigned char* which, int 
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+extern "C" int mpcb200_resample(mpcb200_handle* h, int n_new)
+{
+    if (!h) return MPCB200_E_INVALID;
+    if (n_new < 3 || n_new > h->n_cap) return set_err(h, MPCB200_E_INVALID, "resample: horizon must be in [3, n the handle was created with]");
+    if (n_new == h->cfg.n) return MPCB200_OK;
+    CK(cudaSetDevice(h->device));
+    const int B = h->max_batch, n_old = h->cfg.n;
+    const int rec_words = MPCB200_SCAL_WORDS + 5 * h->n_cap;
+    if (!h->d_resample) CK(cudaMalloc(&h->d_resample, (size_t)B * rec_words * sizeof(double)));
+    resample_pack_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, h->d_resample, rec_words, B);
+    CK(cudaGetLastError());
+    h->cfg.n = n_new;
+    make_layout(&h->cfg, h->L.M, h->L.V, h->L);
+    resample_unpack_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, h->d_resample, rec_words, n_old, B);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return MPCB200_OK;
+}
+
+extern "C" int mpcb200_get_horizon(const mpcb200_handle* h, int* n, int* n_capacity)
+{
+    if (!h) return MPCB200_E_INVALID;
+    if (n) *n = h->cfg.n;
+    if (n_capacity) *n_capacity = h->n_cap;
+    return MPCB200_OK;
 }
 
 // ---- kernel-level access ------------------------------------------------------------------------------------

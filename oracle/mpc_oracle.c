@@ -756,6 +756,44 @@ void orc_init_cold(const orc_problem* p, const double* x_init, orc_ws* ws)
 }
 
 /*
+ * FullDiscretizationGridBaseSE2::resampleTrajectory(n_new)
+ * [R/src/optimal_control/full_discretization_grid_base_se2.cpp:440-524], the operation the grid adaptation applies with
+ * n_new = n +- 1 [R/src/optimal_control/finite_differences_variable_grid_se2.cpp:99-121].
+ *   dt_new = dt (n-1)/(n_new-1)                                                              (:467)
+ *   for idx_new = 1 .. n_new-2: t = idx_new dt_new; idx_old = first old sample with idx_old dt >= t (search resumes where
+ *   the previous sample stopped, :478-481); x = x_prev + f (x_cur - x_prev), f = (t - (idx_old-1) dt)/dt, with
+ *   x_prev = old sample idx_old-1, x_cur = old sample idx_old or the final-state vertex (:484-485); heading by
+ *   interpolate_angle (:493); control = old control of interval idx_old-1 (:497, :507)
+ *   sample 0 and the final state are not touched (:472-474).
+ * X / U: component-major, n columns (column n-1 of X = final state); Xn / Un: n_new columns.  Returns dt_new.
+ */
+double orc_resample_trajectory(int n, const double* X, const double* U, double dt, int n_new, double* Xn, double* Un)
+{
+    const double dt_new = dt * (double)(n - 1) / (double)(n_new - 1);
+    int idx_old = 1;
+    for (int c = 0; c < 3; ++c) Xn[c * n_new + 0] = X[c * n + 0];
+    for (int c = 0; c < 2; ++c) Un[c * n_new + 0] = U[c * n + 0];
+    for (int idx_new = 1; idx_new < n_new - 1; ++idx_new)
+    {
+        const double t_new = dt_new * (double)idx_new;
+        while (t_new > (double)idx_old * dt && idx_old < n) ++idx_old;
+        const double t_old_p1 = (double)idx_old * dt;
+        int prev = idx_old - 1, cur = idx_old;
+        if (cur > n - 1) cur = n - 1;   /* beyond the last interval: the final-state vertex */
+        if (prev > n - 1) prev = n - 1;
+        const double frac = dt > 0.0 ? (t_new - (t_old_p1 - dt)) / dt : 0.0;
+        for (int c = 0; c < 2; ++c) Xn[c * n_new + idx_new] = X[c * n + prev] + frac * (X[c * n + cur] - X[c * n + prev]);
+        Xn[2 * n_new + idx_new] = orc_interpolate_angle(X[2 * n + prev], X[2 * n + cur], frac);
+        int iu = idx_old - 1;
+        if (iu > n - 2) iu = n - 2;     /* the control time series repeats its last sample */
+        for (int c = 0; c < 2; ++c) Un[c * n_new + idx_new] = U[c * n + iu];
+    }
+    for (int c = 0; c < 3; ++c) Xn[c * n_new + n_new - 1] = X[c * n + n - 1];
+    for (int c = 0; c < 2; ++c) Un[c * n_new + n_new - 1] = 0.0;
+    return dt_new;
+}
+
+/*
  * Warm start: FullDiscretizationGridBaseSE2::warmStartShifting + findNearestState
  * [R/src/optimal_control/full_discretization_grid_base_se2.cpp:241-339], then x_0 <- measured state and the fixed
  * components of x_f <- goal [:104-109].

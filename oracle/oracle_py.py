@@ -59,6 +59,8 @@ def lib():
         L.orc_objective.restype = C.c_double
         L.orc_objective.argtypes = [C.POINTER(Problem), C.POINTER(Ws), dp, dp, C.c_double]
         L.orc_ws_alloc.restype = C.POINTER(Ws)
+        L.orc_resample_trajectory.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, dp, dp]
+        L.orc_resample_trajectory.restype = C.c_double
         L.orc_ws_alloc.argtypes = [C.c_int, C.c_int]
         L.orc_ws_free.argtypes = [C.POINTER(Ws)]
         for f in ("orc_warm_shift", "orc_associate", "orc_init_duals", "orc_eval"):
@@ -168,6 +170,15 @@ class Instance:
         X = np.ascontiguousarray(X)
         U = np.ascontiguousarray(U)
         return self.L.orc_objective(C.byref(self.p), self.ws, _dp(X), _dp(U), float(dt))
+
+
+def resample_trajectory(X, U, dt, n_new):
+    """resampleTrajectory(n_new) of one trajectory: X [3, n], U [2, n] (component-major) -> (Xn [3, n_new], Un [2, n_new], dt_new)"""
+    X = np.ascontiguousarray(X, dtype=np.float64); U = np.ascontiguousarray(U, dtype=np.float64)
+    n = X.shape[1]
+    Xn = np.zeros((3, n_new)); Un = np.zeros((2, n_new))
+    dt_new = lib().orc_resample_trajectory(n, _dp(X), _dp(U), float(dt), int(n_new), _dp(Xn), _dp(Un))
+    return Xn, Un, dt_new
 
 
 def instance_from_batch(cfg, data, b):

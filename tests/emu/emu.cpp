@@ -313,4 +313,10 @@ void emu_outputs(const Cfg* cp, const double* W, double* u_seq, double* x_seq)
     }
 }
 
+// the device's horizon change (mpcb200_resample) on one trajectory
+double emu_resample(int n, const double* X, const double* U, double dt, int n_new, double* Xn, double* Un)
+{
+    return resample_serial(n, X, U, dt, n_new, Xn, Un);
+}
+
 }  // extern "C"

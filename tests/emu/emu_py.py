@@ -41,12 +41,21 @@ def lib():
         L.emu_linesearch.argtypes = [cp, dp, C.c_double]
         L.emu_solve.argtypes = [cp, dp, C.c_double, C.c_int]
         L.emu_outputs.argtypes = [cp, dp, dp, dp]
+        L.emu_resample.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, dp, dp]
+        L.emu_resample.restype = C.c_double
         _LIB = L
     return _LIB
 
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def resample(X, U, dt, n_new):
+    X = np.ascontiguousarray(X, dtype=np.float64); U = np.ascontiguousarray(U, dtype=np.float64)
+    Xn = np.zeros((3, n_new)); Un = np.zeros((2, n_new))
+    dt_new = lib().emu_resample(X.shape[1], _dp(X), _dp(U), float(dt), int(n_new), _dp(Xn), _dp(Un))
+    return Xn, Un, dt_new
 
 
 class EmuInstance:

@@ -216,3 +216,15 @@ def test_dynamic_obstacles_match_oracle(orc, emu, free_dt):
             assert abs(e.field(capi.F_SCAL)[capi.SC_DT] - ref["dt"][b]) < 1e-7
             assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
     assert n_both >= 2
+
+
+@pytest.mark.parametrize("n,n_new", [(20, 21), (20, 19), (50, 43), (7, 30), (4, 3)])
+def test_resample_matches_oracle(orc, emu, n, n_new):
+    """the device's horizon change (resample_serial, behind mpcb200_resample) against the oracle's resampleTrajectory"""
+    rng = np.random.default_rng(n + 1000 * n_new)
+    X = np.cumsum(rng.normal(0, 0.3, (3, n)), axis=1)
+    U = rng.normal(0, 0.3, (2, n)); U[:, n - 1] = 0
+    for dt in (0.3, 0.71287734, 1e-3):
+        a = emu.resample(X, U, dt, n_new); b = orc.resample_trajectory(X, U, dt, n_new)
+        np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
+        assert a[2] == b[2]

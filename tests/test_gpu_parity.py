@@ -430,3 +430,51 @@ def test_kkt_attempt_scheduling_does_not_change_results(cuda_lib, cid, B):
     np.testing.assert_array_equal(a["iters"], b["iters"])
     np.testing.assert_array_equal(a["u_seq"], b["u_seq"])
     np.testing.assert_array_equal(a["dt"], b["dt"])
+
+
+def test_resample_changes_the_horizon_of_warm_trajectories(cuda_lib, orc):
+    """mpcb200_resample (resampleTrajectory, the operation behind grid adaptation): the warm trajectories of the batch after a
+    horizon change against the oracle's restatement, and the warm solve at the new horizon."""
+    cfg = configs.config_for(1, tol=1e-8)
+    cfg.n = 26   # capacity of the handle
+    B = 12
+    data = configs.generate(2, B)
+    s = _solver(cfg, B)
+    assert s.horizon() == (26, 26)
+    s.resample(20)
+    assert s.horizon() == (20, 26) and s.N == 20
+    out = s.step(data["x0"], data["xf"], None, 0.0, None, None)
+    assert out["u_seq"].shape == (B, 20, 2) and (out["status"] == 0).all()
+    T0 = 19 * out["dt"]
+    for n_new in (21, 26, 19):
+        n_old = s.N
+        X = s.ws_read(capi.F_X); U = s.ws_read(capi.F_U); dt = s.ws_read(capi.F_SCAL)[:, capi.SC_DT]
+        s.resample(n_new)
+        Xn = s.ws_read(capi.F_X); Un = s.ws_read(capi.F_U); dtn = s.ws_read(capi.F_SCAL)[:, capi.SC_DT]
+        assert Xn.shape == (B, 3, n_new)
+        for b in range(B):
+            rx, ru, rdt = orc.resample_trajectory(X[b], U[b], dt[b], n_new)
+            np.testing.assert_allclose(Xn[b], rx, atol=1e-13); np.testing.assert_allclose(Un[b][:, :n_new - 1], ru[:, :n_new - 1], atol=1e-13)
+            assert abs(dtn[b] - rdt) < 1e-15 and abs(rdt * (n_new - 1) - dt[b] * (n_old - 1)) < 1e-12
+        out = s.step(data["x0"], data["xf"], None, 0.0, None, None)   # warm start from the resampled trajectories
+        assert out["x_seq"].shape == (B, n_new, 3) and (out["status"] == 0).all()
+        # the minimum time of the finer / coarser grid stays close to the one of the first solve
+        assert np.abs((n_new - 1) * out["dt"] - T0).max() < 0.05 * T0.max()
+        ref = orc.step_batch(cfg_with_n(cfg, n_new), data_no_obstacles(data), n_threads=4)
+        both = ref["status"] == 0
+        assert both.sum() >= B - 2 and (np.abs(out["dt"][both] - ref["dt"][both]) < 1e-6).mean() >= 0.8
+    with pytest.raises(capi.SolverError):
+        s.resample(27)
+    with pytest.raises(capi.SolverError):
+        s.resample(2)
+    s.close()
+
+
+def cfg_with_n(cfg, n):
+    c = cfg.copy(); c.n = n
+    return c
+
+
+def data_no_obstacles(data):
+    d = dict(data); d["obstacles"] = None; d["viapoints"] = None
+    return d

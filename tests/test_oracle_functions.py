@@ -386,3 +386,29 @@ def test_lagrangian_gradient_and_newton_step(orc, cid):
         nup = STEP[5:8, :N - 1].T.ravel()
         assert np.abs(dz[free] - sol[:nf]).max() < 1e-5 * max(1.0, np.abs(sol[:nf]).max())
         assert np.abs(nup - sol[nf:]).max() < 1e-5 * max(1.0, np.abs(sol[nf:]).max())
+
+
+@pytest.mark.parametrize("n,n_new", [(20, 21), (20, 19), (50, 57), (33, 12), (5, 3), (3, 8)])
+def test_resample_trajectory_properties(orc, n, n_new):
+    """resampleTrajectory (full_discretization_grid_base_se2.cpp:440-524) against numpy's piecewise-linear interpolation of
+    the old polyline at the new sample times: horizon time kept, first sample and final state carried over, headings
+    interpolated on the short way round, controls taken from the old interval a new sample falls into."""
+    rng = np.random.default_rng(n * 100 + n_new)
+    dt = 0.37
+    X = np.cumsum(rng.normal(0, 0.2, (3, n)), axis=1)
+    X[2] = (X[2] + np.pi) % (2 * np.pi) - np.pi
+    U = rng.normal(0, 0.3, (2, n)); U[:, n - 1] = 0
+    Xn, Un, dt_new = orc.resample_trajectory(X, U, dt, n_new)
+    assert abs(dt_new * (n_new - 1) - dt * (n - 1)) < 1e-12
+    np.testing.assert_array_equal(Xn[:, 0], X[:, 0]); np.testing.assert_array_equal(Xn[:, -1], X[:, -1])
+    np.testing.assert_array_equal(Un[:, 0], U[:, 0])
+    t_old = dt * np.arange(n); t_new = dt_new * np.arange(n_new)
+    for c in range(2):
+        np.testing.assert_allclose(Xn[c, 1:-1], np.interp(t_new[1:-1], t_old, X[c]), atol=1e-12)
+    th = np.unwrap(X[2])
+    d = Xn[2, 1:-1] - np.interp(t_new[1:-1], t_old, th)
+    assert np.abs((d + np.pi) % (2 * np.pi) - np.pi).max() < 1e-12
+    assert (Xn[2] >= -np.pi).all() and (Xn[2] < np.pi).all()
+    # controls: the old interval that ends at or after t_new (a sample exactly on an old grid point takes the interval before it)
+    idx = np.minimum(np.ceil(t_new[1:-1] / dt - 1e-12).astype(int), n - 1)
+    np.testing.assert_array_equal(Un[:, 1:-1], U[:, np.minimum(idx - 1, n - 2)])
