@@ -36,8 +36,8 @@ extern "C" {
 #define MPCB200_COST_TRAPEZOIDAL 1
 /* grid/collocation_method (src/controller.cpp:298-316) */
 #define MPCB200_COLLOC_FORWARD 0   /* inc/optimal_control/fd_collocation_se2.h:54-69 (default, every shipped config) */
-#define MPCB200_COLLOC_MIDPOINT 1  /* :91-108  -- not implemented in this round: create() returns E_UNSUPPORTED */
-#define MPCB200_COLLOC_CRANK_NICOLSON 2 /* :130-147 -- idem (see SURVEY App. C.1 for the reference quirk) */
+#define MPCB200_COLLOC_MIDPOINT 1  /* :91-108  f at the mean pose of the interval (heading by interpolate_angle) */
+#define MPCB200_COLLOC_CRANK_NICOLSON 2 /* :130-147 -- not implemented: create() returns E_UNSUPPORTED (the reference's code and its documentation disagree) */
 
 /* planning/objective/type (src/controller.cpp:551-641) */
 #define MPCB200_OBJ_MINIMUM_TIME 0            /* corbo::MinimumTime: J = (N-1)*dt */

@@ -428,6 +428,7 @@ HD inline int clip_threshold_bin(const int* hist, int rows)
 // ---- config predicates ----
 HD inline bool xf_all_fixed(const Cfg& c) { return c.xf_fixed[0] && c.xf_fixed[1] && c.xf_fixed[2]; }
 HD inline bool has_quadratic(const Cfg& c) { return c.objective == MPCB200_OBJ_QUADRATIC_FORM; }
+HD inline bool is_midpoint(const Cfg& c) { return c.collocation == MPCB200_COLLOC_MIDPOINT; }
 // quadratic_form/hybrid_cost_minimum_time (src/controller.cpp:595-620): honoured only for zero state weights and non-zero
 // control weights (corbo::MinTimeQuadraticControls: dt per interval + the quadratic control term); otherwise the reference
 // logs an error and falls back to the plain quadratic form

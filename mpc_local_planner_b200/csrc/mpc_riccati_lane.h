@@ -67,8 +67,8 @@ HD inline void riccati_terminal(const Cfg& c, const Rec& rec, int N, double delt
         }
         s.PI[i][0] = c.xf_fixed[i] ? 0.0 : rec(k, MPCB200_K_G + i);
         if (EXT && c.xf_fixed[i]) s.PI[i][(EXT ? 2 + i : 0)] = 1.0;
-        // x_{N-1} - dt cross term (end term of the trapezoidal cost rule, the only one the terminal stage can have)
-        if (EXT && c.variable_dt && has_trapezoid(c) && !c.xf_fixed[i]) s.PI[i][EXT ? 1 : 0] = rec(k, MPCB200_K_HB + i);
+        // x_{N-1} - dt cross term: end term of the trapezoidal cost rule, or the heading of the last midpoint defect
+        if (EXT && c.variable_dt && (has_trapezoid(c) || is_midpoint(c)) && !c.xf_fixed[i]) s.PI[i][EXT ? 1 : 0] = rec(k, MPCB200_K_HB + i);
     }
     if (EXT)
     {

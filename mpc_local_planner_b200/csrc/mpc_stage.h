@@ -166,10 +166,14 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
         const double u[2] = {AU(0, k), AU(1, k)};
         const double nu[3] = {ANU(0, k), ANU(1, k), ANU(2, k)};
         double f[3], J[9], Hc[6];
-        dynamics_derivs(c, x[2], u[0], u[1], nu, f, J, Hc, sc);
+        // midpoint differences (fd_collocation_se2.h:91-108) evaluate f at the mean heading of the interval; see midpoint_* below
+        const bool mid = LINES && is_midpoint(c);
+        const double dth = normalize_theta(AX(2, k + 1) - x[2]);
+        if (mid) dynamics_derivs(c, x[2] + 0.5 * dth, u[0], u[1], nu, f, J, Hc, nullptr);
+        else dynamics_derivs(c, x[2], u[0], u[1], nu, f, J, Hc, sc);
         e[0] = x[0] + dt * f[0] - AX(0, k + 1);
         e[1] = x[1] + dt * f[1] - AX(1, k + 1);
-        e[2] = dt * f[2] - normalize_theta(AX(2, k + 1) - x[2]);
+        e[2] = dt * f[2] - dth;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
         {
@@ -182,6 +186,21 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
             acc.sum_nu += fabs(nu[i]);
         }
         acc.m_eq += 3.0;
+        if (mid)
+        {
+            // the defect depends on x_{k+1} through the mean heading: de/dx_k = I + a e_th', de/dx_{k+1} = -(I - a e_th'),
+            // a = dt/2 f_theta (a_theta = 0 for every model).  Multiplying the linearised row by (I - a e_th')^{-1} = I + a e_th'
+            // restores the explicit form dx_{k+1} = (I + 2a e_th') dx_k + B~ du + d~ d(dt) + e~ the Riccati sweep expects
+            // (a3 above is already 2a); the multiplier it returns belongs to the transformed row (ls_stage_update undoes this).
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+            {
+                const double ai = 0.5 * a3[i];
+                Bm[2 * i] += ai * Bm[4]; Bm[2 * i + 1] += ai * Bm[5];
+                dvec[i] += ai * dvec[2];
+                e[i] += ai * e[2];
+            }
+        }
         // quadratic running cost (k = 0 state term is a constant: its gradient is never used since x_0 is fixed)
         if (has_quadratic(c))
         {
@@ -227,12 +246,37 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
         const double fx_nu = nu[0] * J[0] + nu[1] * J[3] + nu[2] * J[6];
         const double fu_nu0 = nu[0] * J[1] + nu[1] * J[4] + nu[2] * J[7];
         const double fu_nu1 = nu[0] * J[2] + nu[1] * J[5] + nu[2] * J[8];
-        GL[0] += nu[0]; GL[1] += nu[1]; GL[2] += nu[2] + dt * fx_nu;
-        GL[3] += dt * fu_nu0; GL[4] += dt * fu_nu1;
         acc.gldt += nu[0] * f[0] + nu[1] * f[1] + nu[2] * f[2];
-        H[hidx(2, 2)] += dt * Hc[0]; H[hidx(2, 3)] += dt * Hc[1]; H[hidx(2, 4)] += dt * Hc[2];
+        GL[0] += nu[0]; GL[1] += nu[1];
+        GL[3] += dt * fu_nu0; GL[4] += dt * fu_nu1;
         H[hidx(3, 3)] += dt * Hc[3]; H[hidx(3, 4)] += dt * Hc[4]; H[hidx(4, 4)] += dt * Hc[5];
-        if (c.variable_dt) { hb[2] += fx_nu; hb[3] += fu_nu0; hb[4] += fu_nu1; }
+        if (c.variable_dt) { hb[3] += fu_nu0; hb[4] += fu_nu1; }
+        if (!mid)
+        {
+            GL[2] += nu[2] + dt * fx_nu;
+            H[hidx(2, 2)] += dt * Hc[0]; H[hidx(2, 3)] += dt * Hc[1]; H[hidx(2, 4)] += dt * Hc[2];
+            if (c.variable_dt) hb[2] += fx_nu;
+        }
+        else
+        {
+            // theta_k enters through the mean heading with weight 1/2
+            GL[2] += nu[2] + 0.5 * dt * fx_nu;
+            H[hidx(2, 2)] += 0.25 * dt * Hc[0]; H[hidx(2, 3)] += 0.5 * dt * Hc[1]; H[hidx(2, 4)] += 0.5 * dt * Hc[2];
+            if (c.variable_dt) hb[2] += 0.5 * fx_nu;
+            // Hessian block between theta_{k+1} and (theta_k, u_k): q = (dt/4 Hc_tt, dt/2 Hc_t0, dt/2 Hc_t1).  It is condensed
+            // into this stage with the linearised heading row d(theta_{k+1}) = r' dw_k + e~_2 + d~_2 d(dt), r = (1, B~_20, B~_21):
+            // H += q r' + r q', Newton gradient += q e~_2, dt border += q d~_2 (exact; DESIGN.md "midpoint differences")
+            const double q[3] = {0.25 * dt * Hc[0], 0.5 * dt * Hc[1], 0.5 * dt * Hc[2]};
+            const double r[3] = {1.0, Bm[4], Bm[5]};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+            {
+#pragma unroll
+                for (int j = i; j < 3; ++j) H[hidx(2 + i, 2 + j)] += q[i] * r[j] + r[i] * q[j];
+                g0[2 + i] += q[i] * e[2];
+                if (c.variable_dt) hb[2 + i] += q[i] * dvec[2];
+            }
+        }
         // linear rows touching u_k (own bounds, own rate rows, rate rows of stage k+1)
         lin_rows_component<0>(c, L, W, uprev_dt, k, dt, u[0], H, g0, g1, GL, hb, Cc, acc, rp);
         lin_rows_component<1>(c, L, W, uprev_dt, k, dt, u[1], H, g0, g1, GL, hb, Cc, acc, rp);
@@ -316,6 +360,17 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
     }
     // multiplier of the previous defect: d/dx_k ( nu_{k-1}^T e_{k-1} ) = -nu_{k-1}
     if (k >= 1) { GL[0] -= ANU(0, k - 1); GL[1] -= ANU(1, k - 1); GL[2] -= ANU(2, k - 1); }
+    if (LINES && is_midpoint(c) && k >= 1)
+    {
+        // midpoint differences: theta_k is also the far end of interval k-1 (weight 1/2 in its mean heading)
+        const double nup[3] = {ANU(0, k - 1), ANU(1, k - 1), ANU(2, k - 1)};
+        double fp[3], Jp[9], Hp[6];
+        dynamics_derivs(c, AX(2, k - 1) + 0.5 * normalize_theta(x[2] - AX(2, k - 1)), AU(0, k - 1), AU(1, k - 1), nup, fp, Jp, Hp, nullptr);
+        const double fx_nu_p = nup[0] * Jp[0] + nup[1] * Jp[3] + nup[2] * Jp[6];
+        GL[2] += 0.5 * dt * fx_nu_p;
+        H[hidx(2, 2)] += 0.25 * dt * Hp[0];
+        if (c.variable_dt) hb[2] += 0.5 * fx_nu_p;
+    }
     // via-points attached to this stage
     if (has_viapoints(c) && k >= 1 && k <= N - 2)
     {
@@ -690,7 +745,9 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
     {
         const double u[2] = {AU(0, k) + alpha * ASTEP(3, k), AU(1, k) + alpha * ASTEP(4, k)};
         double f[3];
-        if (c.robot_type == MPCB200_ROBOT_KIN_BICYCLE) dynamics_value(c, x[2], u[0], u[1], f);
+        const double xn2 = AX(2, k + 1) + alpha * ASTEP(2, k + 1);
+        if (LINES && is_midpoint(c)) dynamics_value(c, x[2] + 0.5 * normalize_theta(xn2 - x[2]), u[0], u[1], f);
+        else if (c.robot_type == MPCB200_ROBOT_KIN_BICYCLE) dynamics_value(c, x[2], u[0], u[1], f);
         else
         {
             f[0] = u[0] * sc[1]; f[1] = u[0] * sc[0];
@@ -741,18 +798,36 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
 }
 
 // accept the step: z, s, lambda, nu of stage k
+template <bool LINES = true>
 HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W, double* G, double uprev_dt, int k, double alpha, double a_dual)
 {
     const int N = L.N, K = L.K;
     const double mu = ASC(MPCB200_SC_MU);
-    // NOTE: reads STEP of stage k only -> safe to run lane-parallel after all trial evaluations are done
+    // NOTE: reads STEP of stage k only (midpoint differences: also the heading of stage k+1, before anything of stage k is
+    // written, so that the in-place serial emulation sees the old iterate) -> safe to run lane-parallel after all trial
+    // evaluations are done
     const double d0 = ASTEP(0, k), d1 = ASTEP(1, k), d2 = ASTEP(2, k);
+    double nup[3] = {0.0, 0.0, 0.0};
+    if (k <= N - 2)
+    {
+        nup[0] = ASTEP(5, k); nup[1] = ASTEP(6, k); nup[2] = ASTEP(7, k);
+        if (LINES && is_midpoint(c))
+        {
+            // the sweep solved the transformed, condensed system (eval_stage): nu+ = (I + e_th a') nu~ + e_th (q' dw_k)
+            const double nu[3] = {ANU(0, k), ANU(1, k), ANU(2, k)};
+            const double dt = ASC(MPCB200_SC_DT);
+            double f[3], J[9], Hc[6];
+            dynamics_derivs(c, AX(2, k) + 0.5 * normalize_theta(AX(2, k + 1) - AX(2, k)), AU(0, k), AU(1, k), nu, f, J, Hc, nullptr);
+            nup[2] += 0.5 * dt * (J[0] * nup[0] + J[3] * nup[1]);
+            nup[2] += 0.25 * dt * Hc[0] * d2 + 0.5 * dt * (Hc[1] * ASTEP(3, k) + Hc[2] * ASTEP(4, k));
+        }
+    }
     GX(0, k) = AX(0, k) + alpha * d0; GX(1, k) = AX(1, k) + alpha * d1; GX(2, k) = AX(2, k) + alpha * d2;
     if (k <= N - 2)
     {
         GU(0, k) = AU(0, k) + alpha * ASTEP(3, k);
         GU(1, k) = AU(1, k) + alpha * ASTEP(4, k);
-        for (int i = 0; i < 3; ++i) GNU(i, k) = ANU(i, k) + alpha * (ASTEP(5 + i, k) - ANU(i, k));
+        for (int i = 0; i < 3; ++i) GNU(i, k) = ANU(i, k) + alpha * (nup[i] - ANU(i, k));
     }
     for (int sl = 0; sl < 8 + K; ++sl)
     {

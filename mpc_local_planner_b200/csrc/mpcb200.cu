@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg
     if (tid == 0) sh.a_dual = a_d > alpha ? alpha : a_d;
     __syncthreads();
     const double a_dual = sh.a_dual;
-    for (int k = tid; k < N; k += blockDim.x) ls_stage_update(c, L, W, Gp, uprev_dt, k, alpha, a_dual);
+    for (int k = tid; k < N; k += blockDim.x) ls_stage_update<LINES>(c, L, W, Gp, uprev_dt, k, alpha, a_dual);
     if (tid == 0)
     {
         if (c.variable_dt) GSC(MPCB200_SC_DT) = ASC(MPCB200_SC_DT) + alpha * ASC(MPCB200_SC_DDT);
@@ -904,7 +904,7 @@ struct mpcb200_handle
     int* h_stream_counters;  // pinned, two poll slots
     cudaStream_t side_stream;            // streaming: init / associate of refilled slots run beside the iterations of the others
     cudaEvent_t ev_refill, ev_ready;
-    int has_lines;  // the uploaded batch contains line obstacles or obstacles may move: the eval / line-search kernels are launched with those paths compiled in
+    int has_lines;  // line obstacles in the batch, moving obstacles or midpoint differences: the eval / line-search kernels are launched with those (rarely used) paths compiled in
     double uprev_dt;
     mpcb200_stats stats;
     std::vector<cudaEvent_t> ev;  // pool of event pairs
@@ -955,8 +955,8 @@ static int validate_config(const mpcb200_config* c, std::string& why)
 {
     if (c->n < 3 || c->n > 512) { why = "n must be in [3, 512]"; return MPCB200_E_INVALID; }
     if (c->robot_type < 0 || c->robot_type > 3) { why = "unknown robot_type"; return MPCB200_E_INVALID; }
-    if (c->collocation != MPCB200_COLLOC_FORWARD)
-    { why = "only forward_differences collocation is implemented (midpoint / crank_nicolson: next round)"; return MPCB200_E_UNSUPPORTED; }
+    if (c->collocation != MPCB200_COLLOC_FORWARD && c->collocation != MPCB200_COLLOC_MIDPOINT)
+    { why = "collocation: forward_differences and midpoint_differences are implemented, crank_nicolson is not"; return MPCB200_E_UNSUPPORTED; }
     if (c->objective < 0 || c->objective > 2) { why = "unknown objective"; return MPCB200_E_INVALID; }
     if (c->cost_integration != MPCB200_COST_LEFT_SUM && c->cost_integration != MPCB200_COST_TRAPEZOIDAL)
     { why = "unknown cost_integration"; return MPCB200_E_INVALID; }
@@ -1196,7 +1196,7 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
     if (u_prev) { CK(cudaMemcpyAsync(h->d_uprev, u_prev, (size_t)B * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)B * 16; }
     else CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
     h->uprev_dt = u_prev_dt;
-    h->has_obst = 0; h->obst_max = 0; h->has_lines = 0;
+    h->has_obst = 0; h->obst_max = 0; h->has_lines = is_midpoint(h->cfg);  // the kernel variants with the rarely used paths compiled in
     if (obst && obst->count && obst->max_per_instance > 0)
     {
         if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
@@ -1207,7 +1207,7 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
             if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
             lines |= obst->type[i] == MPCB200_OBST_LINE;
         }
-        h->has_lines = lines || h->cfg.enable_dynamic_obstacles;  // the kernel variants with the rarely used obstacle kinds compiled in
+        h->has_lines = lines || h->cfg.enable_dynamic_obstacles || is_midpoint(h->cfg);
         CK(cudaMemcpyAsync(h->d_obst_count, obst->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst_type, obst->type, (size_t)B * M * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_obst, obst->params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1348,7 +1348,7 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
     h->stats.h2d_bytes += (long long)(T * 6 * 8);
     if (u_prev) { CK(cudaMemcpyAsync(h->s_uprev, u_prev, T * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)(T * 16); }
     h->uprev_dt = u_prev_dt;
-    h->has_obst = 0; h->obst_max = 0; h->has_lines = 0; h->has_vp = 0; h->vp_max = 0; h->has_xinit = 0; h->has_reinit = 0;
+    h->has_obst = 0; h->obst_max = 0; h->has_lines = is_midpoint(h->cfg); h->has_vp = 0; h->vp_max = 0; h->has_xinit = 0; h->has_reinit = 0;
     if (obst && obst->count && obst->max_per_instance > 0)
     {
         if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
@@ -1359,7 +1359,7 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
             if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
             lines |= obst->type[i] == MPCB200_OBST_LINE;
         }
-        h->has_lines = lines || h->cfg.enable_dynamic_obstacles;
+        h->has_lines = lines || h->cfg.enable_dynamic_obstacles || is_midpoint(h->cfg);
         CK(cudaMemcpyAsync(h->s_obst_count, obst->count, T * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->s_obst_type, obst->type, T * M * 4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->s_obst, obst->params, T * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));

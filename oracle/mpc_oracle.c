@@ -161,11 +161,28 @@ void orc_dynamics_derivs(const mpcb200_config* cfg, const double* x, const doubl
     }
 }
 
-/* ForwardDiffCollocationSE2::computeEqualityConstraint as coded: R/include/mpc_local_planner/optimal_control/fd_collocation_se2.h:54-69 */
+/* pose at which the collocation scheme evaluates the dynamics:
+ *   forward differences   x_k                                   [R/include/mpc_local_planner/optimal_control/fd_collocation_se2.h:54-69]
+ *   midpoint differences  (x_k + x_{k+1})/2 with the heading interpolate_angle(theta_k, theta_{k+1}, 0.5)      [:91-108]
+ * (only the heading matters: none of the models' dynamics depend on the position) */
+static int is_midpoint(const mpcb200_config* c) { return c->collocation == MPCB200_COLLOC_MIDPOINT; }
+static void collocation_pose(const mpcb200_config* cfg, const double* x1, const double* x2, double* xe)
+{
+    xe[0] = x1[0]; xe[1] = x1[1]; xe[2] = x1[2];
+    if (is_midpoint(cfg))
+    {
+        xe[0] = 0.5 * (x1[0] + x2[0]); xe[1] = 0.5 * (x1[1] + x2[1]);
+        xe[2] = x1[2] + 0.5 * orc_normalize_theta(x2[2] - x1[2]); /* = interpolate_angle up to a multiple of 2 pi */
+    }
+}
+
+/* {Forward,Midpoint}DiffCollocationSE2::computeEqualityConstraint as coded: fd_collocation_se2.h:54-69, 91-108 */
 void orc_defect_reference(const mpcb200_config* cfg, const double* x1, const double* u1, const double* x2, double dt,
                           double* e)
 {
-    orc_dynamics(cfg, x1, u1, e);
+    double xe[3];
+    collocation_pose(cfg, x1, x2, xe);
+    orc_dynamics(cfg, xe, u1, e);
     e[0] -= (x2[0] - x1[0]) / dt;
     e[1] -= (x2[1] - x1[1]) / dt;
     e[2] -= orc_normalize_theta(x2[2] - x1[2]) / dt;
@@ -174,8 +191,9 @@ void orc_defect_reference(const mpcb200_config* cfg, const double* x1, const dou
 /* dt-multiplied form used by the solvers: e = dt * (reference defect) */
 void orc_defect(const mpcb200_config* cfg, const double* x1, const double* u1, const double* x2, double dt, double* e)
 {
-    double f[3];
-    orc_dynamics(cfg, x1, u1, f);
+    double f[3], xe[3];
+    collocation_pose(cfg, x1, x2, xe);
+    orc_dynamics(cfg, xe, u1, f);
     e[0] = dt * f[0] - (x2[0] - x1[0]);
     e[1] = dt * f[1] - (x2[1] - x1[1]);
     e[2] = dt * f[2] - orc_normalize_theta(x2[2] - x1[2]);
@@ -1212,7 +1230,12 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
         double u[2] = {ws->U[IX(0, k)], ws->U[IX(1, k)]};
         double nu[3] = {ws->NU[IX(0, k)], ws->NU[IX(1, k)], ws->NU[IX(2, k)]};
         double f[3], Jf[9], Hc[6];
-        orc_dynamics_derivs(c, x, u, nu, f, Jf, Hc);
+        const int mid = is_midpoint(c);
+        {
+            double xn[3] = {ws->X[IX(0, k + 1)], ws->X[IX(1, k + 1)], ws->X[IX(2, k + 1)]}, xe[3];
+            collocation_pose(c, x, xn, xe);
+            orc_dynamics_derivs(c, xe, u, nu, f, Jf, Hc);
+        }
         double e[3];
         e[0] = x[0] + dt * f[0] - ws->X[IX(0, k + 1)];
         e[1] = x[1] + dt * f[1] - ws->X[IX(1, k + 1)];
@@ -1229,6 +1252,22 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
             sum_nu += fabs(nu[i]);
         }
         m_eq += 3;
+        if (mid)
+        {
+            /* Midpoint differences: the mean heading makes the defect depend on x_{k+1} too,
+             *   de/dx_k = I + a e_th',  de/dx_{k+1} = -(I - a e_th'),  a = dt/2 df/dtheta  (a_theta = 0 for all models).
+             * The linearised row is multiplied by (I - a e_th')^{-1} = I + a e_th' so that the record keeps the explicit form
+             *   dx_{k+1} = (I + 2a e_th') dx_k + B~ du_k + d~ d(dt) + e~      (K_A = 2a is what the loop above stored)
+             * the Riccati sweep works on; the multiplier of the transformed row is nu~ = (I - a e_th')' nu. */
+            for (int i = 0; i < 2; ++i)
+            {
+                const double ai = 0.5 * KK(MPCB200_K_A + i, k);
+                KK(MPCB200_K_B + 2 * i, k) += ai * KK(MPCB200_K_B + 4, k);
+                KK(MPCB200_K_B + 2 * i + 1, k) += ai * KK(MPCB200_K_B + 5, k);
+                KK(MPCB200_K_D + i, k) += ai * KK(MPCB200_K_D + 2, k);
+                KK(MPCB200_K_E + i, k) += ai * KK(MPCB200_K_E + 2, k);
+            }
+        }
         /* quadratic cost */
         double gx[3] = {0, 0, 0}, gu[2] = {0, 0};
         if (has_quadratic(c))
@@ -1264,24 +1303,47 @@ static void eval_impl(const orc_problem* p, orc_ws* ws, eval_info* info, double*
         /* Lagrangian terms of the dynamics: nu_k^T e_k */
         double fx_nu = nu[0] * Jf[0] + nu[1] * Jf[3] + nu[2] * Jf[6];
         double fu_nu[2] = {nu[0] * Jf[1] + nu[1] * Jf[4] + nu[2] * Jf[7], nu[0] * Jf[2] + nu[1] * Jf[5] + nu[2] * Jf[8]};
+        /* the heading of x_k enters the dynamics with weight wth (1, or 1/2 through the mean heading) */
+        const double wth = mid ? 0.5 : 1.0;
         GL[IX(0, k)] += nu[0];
         GL[IX(1, k)] += nu[1];
-        GL[IX(2, k)] += nu[2] + dt * fx_nu;
+        GL[IX(2, k)] += nu[2] + wth * dt * fx_nu;
         GL[IX(3, k)] += dt * fu_nu[0];
         GL[IX(4, k)] += dt * fu_nu[1];
         for (int i = 0; i < 3; ++i) GL[IX(i, k + 1)] -= nu[i];
         gl_dt += nu[0] * f[0] + nu[1] * f[1] + nu[2] * f[2];
-        hadd(KKT, N, k, 2, 2, dt * Hc[0]);
-        hadd(KKT, N, k, 2, 3, dt * Hc[1]);
-        hadd(KKT, N, k, 2, 4, dt * Hc[2]);
+        hadd(KKT, N, k, 2, 2, wth * wth * dt * Hc[0]);
+        hadd(KKT, N, k, 2, 3, wth * dt * Hc[1]);
+        hadd(KKT, N, k, 2, 4, wth * dt * Hc[2]);
         hadd(KKT, N, k, 3, 3, dt * Hc[3]);
         hadd(KKT, N, k, 3, 4, dt * Hc[4]);
         hadd(KKT, N, k, 4, 4, dt * Hc[5]);
         if (c->variable_dt)
         {
-            KK(MPCB200_K_HB + 2, k) += fx_nu;
+            KK(MPCB200_K_HB + 2, k) += wth * fx_nu;
             KK(MPCB200_K_HB + 3, k) += fu_nu[0];
             KK(MPCB200_K_HB + 4, k) += fu_nu[1];
+        }
+        if (mid)
+        {
+            /* the other half of the mean heading belongs to theta_{k+1} */
+            GL[IX(2, k + 1)] += 0.5 * dt * fx_nu;
+            hadd(KKT, N, k + 1, 2, 2, 0.25 * dt * Hc[0]);
+            if (c->variable_dt) KK(MPCB200_K_HB + 2, k + 1) += 0.5 * fx_nu;
+            /* ... and the Lagrangian has a Hessian block between theta_{k+1} and w_k = (theta_k, u_k),
+             *   q = (dt/4 Hc_tt, dt/2 Hc_t0, dt/2 Hc_t1),
+             * which the stage-wise record cannot hold.  It is condensed into stage k with the linearised heading row
+             *   d(theta_{k+1}) = r' dw_k + e~_2 + d~_2 d(dt),  r = (1, B~_20, B~_21):
+             * H_k += q r' + r q', Newton gradient += q e~_2, dt border += q d~_2 -- the same Newton step; the multiplier the
+             * sweep returns is nu+ - e_th (q' dw_k) (undone in orc_kkt_solve). */
+            const double q[3] = {0.25 * dt * Hc[0], 0.5 * dt * Hc[1], 0.5 * dt * Hc[2]};
+            const double r[3] = {1.0, KK(MPCB200_K_B + 4, k), KK(MPCB200_K_B + 5, k)};
+            for (int i = 0; i < 3; ++i)
+            {
+                for (int j = i; j < 3; ++j) hadd(KKT, N, k, 2 + i, 2 + j, q[i] * r[j] + r[i] * q[j]);
+                KK(MPCB200_K_G + 2 + i, k) += q[i] * KK(MPCB200_K_E + 2, k);
+                if (c->variable_dt) KK(MPCB200_K_HB + 2 + i, k) += q[i] * KK(MPCB200_K_D + 2, k);
+            }
         }
     }
     /* terminal cost */
@@ -1544,8 +1606,8 @@ int orc_kkt_solve(const orc_problem* p, orc_ws* ws, double delta)
         {
             PI[i * 5 + 0] = c->xf_fixed[i] ? 0.0 : KK(MPCB200_K_G + i, k);
             if (c->xf_fixed[i]) PI[i * 5 + 2 + i] = 1.0;
-            /* x_{N-1} - dt cross term: end term of the trapezoidal cost rule */
-            if (dt_free && has_trapezoid(c) && !c->xf_fixed[i]) PI[i * 5 + 1] = KK(MPCB200_K_HB + i, k);
+            /* x_{N-1} - dt cross term: end term of the trapezoidal cost rule, heading of the last midpoint defect */
+            if (dt_free && (has_trapezoid(c) || is_midpoint(c)) && !c->xf_fixed[i]) PI[i * 5 + 1] = KK(MPCB200_K_HB + i, k);
         }
         TH[0 * 5 + 1] = TH[1 * 5 + 0] = ws->SCAL[MPCB200_SC_GT];
         TH[1 * 5 + 1] = ws->SCAL[MPCB200_SC_HTT] + delta;
@@ -1706,6 +1768,25 @@ int orc_kkt_solve(const orc_problem* p, orc_ws* ws, double delta)
     }
     for (int i = 0; i < 3; ++i) STEP[IX(i, N - 1)] = y[i];
     for (int i = 3; i < 8; ++i) STEP[IX(i, N - 1)] = 0.0;
+    if (is_midpoint(c))
+    {
+        /* midpoint differences (orc_eval): the sweep worked on the transformed, condensed system,
+         *   nu+ = (I + e_th a') nu~ + e_th (q' dw_k),  a = K_A / 2,  q from the Hessian of nu' f at the current iterate */
+        const double dtc = ws->SCAL[MPCB200_SC_DT];
+        for (int k = 0; k <= N - 2; ++k)
+        {
+            double x[3] = {ws->X[IX(0, k)], ws->X[IX(1, k)], ws->X[IX(2, k)]};
+            double xn[3] = {ws->X[IX(0, k + 1)], ws->X[IX(1, k + 1)], ws->X[IX(2, k + 1)]}, xe[3];
+            double u[2] = {ws->U[IX(0, k)], ws->U[IX(1, k)]};
+            double nu[3] = {ws->NU[IX(0, k)], ws->NU[IX(1, k)], ws->NU[IX(2, k)]};
+            double f[3], Jf[9], Hc[6];
+            collocation_pose(c, x, xn, xe);
+            orc_dynamics_derivs(c, xe, u, nu, f, Jf, Hc);
+            double corr = 0.5 * KK(MPCB200_K_A + 0, k) * STEP[IX(5, k)] + 0.5 * KK(MPCB200_K_A + 1, k) * STEP[IX(6, k)];
+            corr += 0.25 * dtc * Hc[0] * STEP[IX(2, k)] + 0.5 * dtc * (Hc[1] * STEP[IX(3, k)] + Hc[2] * STEP[IX(4, k)]);
+            STEP[IX(7, k)] += corr;
+        }
+    }
     ws->SCAL[MPCB200_SC_DDT] = th[1];
     ws->SCAL[MPCB200_SC_DELTA] = delta;
 #undef KK

@@ -121,6 +121,15 @@ class Instance:
         shp = shapes[name]
         return np.ctypeslib.as_array(getattr(self.ws.contents, name), shape=shp)
 
+    def defects(self):
+        """dt-multiplied collocation defects e_k of the current iterate, [3, N-1] (orc_defect per interval)"""
+        X = self.arr("X"); U = self.arr("U"); dt = float(self.arr("SCAL")[capi.SC_DT])
+        e = np.zeros((self.N - 1, 3))
+        for k in range(self.N - 1):
+            x1 = np.ascontiguousarray(X[:, k]); x2 = np.ascontiguousarray(X[:, k + 1]); u1 = np.ascontiguousarray(U[:, k])
+            self.L.orc_defect(C.byref(self.cfg), _dp(x1), _dp(u1), _dp(x2), dt, _dp(e[k]))
+        return e.T.copy()
+
     def vp_stage(self):
         return np.ctypeslib.as_array(self.ws.contents.vp_stage)[: self.p.n_vp].copy()
 

@@ -35,7 +35,7 @@ def test_invalid_configs_rejected(cuda_lib):
     h = C.c_void_p()
     c = capi.default_config(); c.n = 2
     assert cuda_lib.mpcb200_create(C.byref(c), 4, 0, C.byref(h)) == capi.E_INVALID
-    c = capi.default_config(); c.collocation = capi.COLLOC_MIDPOINT
+    c = capi.default_config(); c.collocation = capi.COLLOC_CRANK_NICOLSON
     assert cuda_lib.mpcb200_create(C.byref(c), 4, 0, C.byref(h)) == capi.E_UNSUPPORTED
     assert b"forward_differences" in cuda_lib.mpcb200_last_error(None)
     c = capi.default_config(); c.objective = capi.OBJ_MINIMUM_TIME; c.variable_dt = 0

@@ -228,3 +228,41 @@ def test_resample_matches_oracle(orc, emu, n, n_new):
         a = emu.resample(X, U, dt, n_new); b = orc.resample_trajectory(X, U, dt, n_new)
         np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
         assert a[2] == b[2]
+
+
+@pytest.mark.parametrize("base", ["cfg2", "cfg2_integral_free_dt", "cfg3"])
+def test_midpoint_differences_match_oracle(orc, emu, base):
+    """grid/collocation_method midpoint_differences (fd_collocation_se2.h:91-108): records of the first evaluation
+    (transformed to the explicit form, cross Hessian block condensed) and whole solves, device code against the oracle."""
+    cid = 3 if base == "cfg3" else 2
+    n = 30 if base == "cfg3" else 50
+    cfg = {"cfg2": configs.cfg2, "cfg2_integral_free_dt": configs.cfg2_integral_form, "cfg3": configs.cfg3}[base](n=n, tol=1e-8)
+    cfg.collocation = capi.COLLOC_MIDPOINT
+    B = 6
+    data = configs.generate(cid, B, n=n)
+    ref = orc.step_batch(cfg, data, n_threads=2)
+    n_both = 0
+    for b in range(B):
+        o = _oracle_init(orc, cfg, data, b)
+        e = emu.instance_from_batch(cfg, data, b)
+        e.init(); e.associate()
+        o.eval(); e.eval()
+        scale = np.abs(o.arr("KKT")).max()
+        np.testing.assert_allclose(e.field(capi.F_KKT), o.arr("KKT"), atol=1e-9 * scale)
+        idx = [capi.SC_HTT, capi.SC_GT, capi.SC_OBJ, capi.SC_ERR0]
+        np.testing.assert_allclose(e.field(capi.F_SCAL)[idx], o.arr("SCAL")[idx], rtol=1e-8, atol=1e-10)
+        st = e.solve()
+        u, x = e.outputs()
+        if st == 0 and ref["status"][b] == 0:
+            n_both += 1
+            assert abs(e.field(capi.F_SCAL)[capi.SC_DT] - ref["dt"][b]) < 1e-7
+            if base != "cfg3":   # minimum-time optima need not be strict in the controls
+                assert np.abs(u - ref["u_seq"][b]).max() < 1e-5
+            # the converged trajectory satisfies the reference's midpoint defect
+            dt = e.field(capi.F_SCAL)[capi.SC_DT]
+            for k in range(n - 1):
+                d = np.zeros(3)
+                orc.lib().orc_defect_reference(cfg, x[k].copy().ctypes.data_as(orc.C.POINTER(orc.C.c_double)), u[k].copy().ctypes.data_as(orc.C.POINTER(orc.C.c_double)),
+                                               x[k + 1].copy().ctypes.data_as(orc.C.POINTER(orc.C.c_double)), float(dt), d.ctypes.data_as(orc.C.POINTER(orc.C.c_double)))
+                assert np.abs(d).max() * dt < 1e-6
+    assert n_both >= 2

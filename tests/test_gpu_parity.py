@@ -274,7 +274,7 @@ def test_error_paths(cuda_lib):
     data = configs.generate(2, 8)
     with pytest.raises(capi.SolverError):
         s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"])  # B > max_batch
-    bad = configs.cfg2(); bad.collocation = capi.COLLOC_MIDPOINT
+    bad = configs.cfg2(); bad.collocation = capi.COLLOC_CRANK_NICOLSON
     with pytest.raises(capi.SolverError):
         capi.BatchSolver(bad, 4)
     s.close()
@@ -482,3 +482,39 @@ def cfg_with_n(cfg, n):
 def data_no_obstacles(data):
     d = dict(data); d["obstacles"] = None; d["viapoints"] = None
     return d
+
+
+@pytest.mark.parametrize("base", ["cfg2", "cfg2_integral_free_dt", "cfg3", "cfg1"])
+def test_midpoint_differences(cuda_lib, orc, base):
+    """grid/collocation_method midpoint_differences (MidpointDiffCollocationSE2, fd_collocation_se2.h:91-108) through the
+    C ABI against the oracle; the converged trajectories satisfy the reference's own midpoint defect."""
+    cid = {"cfg2": 2, "cfg2_integral_free_dt": 2, "cfg3": 3, "cfg1": 2}[base]
+    n = {"cfg2": 50, "cfg2_integral_free_dt": 50, "cfg3": 40, "cfg1": 20}[base]
+    make = {"cfg2": configs.cfg2, "cfg2_integral_free_dt": configs.cfg2_integral_form, "cfg3": configs.cfg3, "cfg1": configs.cfg1}[base]
+    cfg = make(tol=1e-8) if base == "cfg1" else make(n=n, tol=1e-8)
+    cfg.collocation = capi.COLLOC_MIDPOINT
+    B = 32
+    data = configs.generate(cid, B, n=n)
+    if base == "cfg1":
+        data = data_no_obstacles(data)
+    s = _solver(cfg, B)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    ref = orc.step_batch(cfg, data, n_threads=8)
+    assert (out["status"] == ref["status"]).mean() >= 0.8
+    both = (out["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= 8
+    assert np.abs(out["dt"][both] - ref["dt"][both]).max() < 1e-6
+    du = np.abs(out["u_seq"][both] - ref["u_seq"][both]).reshape(both.sum(), -1).max(axis=1)
+    if cfg.objective == capi.OBJ_QUADRATIC_FORM:
+        assert (du < U_TOL).mean() >= 0.9
+    # midpoint defect in the reference's form: f((x_k + x_{k+1})/2, u_k) - (x_{k+1} - x_k)/dt
+    x = out["x_seq"][both]; u = out["u_seq"][both][:, : n - 1]; dt = out["dt"][both][:, None]
+    dth = (x[:, 1:, 2] - x[:, :-1, 2] + np.pi) % (2 * np.pi) - np.pi
+    thm = x[:, :-1, 2] + 0.5 * dth
+    if cfg.robot_type == capi.ROBOT_UNICYCLE:
+        f = np.stack([u[..., 0] * np.cos(thm), u[..., 0] * np.sin(thm), u[..., 1]], -1)
+    else:
+        f = np.stack([u[..., 0] * np.cos(thm), u[..., 0] * np.sin(thm), u[..., 0] * np.tan(u[..., 1]) / cfg.wheelbase], -1)
+    d = x[:, 1:] - x[:, :-1]; d[..., 2] = dth
+    assert np.abs(f * dt[..., None] - d).max() < 1e-6
+    s.close()

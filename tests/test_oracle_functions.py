@@ -236,19 +236,24 @@ def test_footprint_distance_to_line_obstacle(orc, kind):
     assert checked >= 30
 
 
-def _random_iterate(orc, cid, b, seed):
+def _random_iterate(orc, cid, b, seed, nu_scale=1.0):
     """cid 21 / 22 / 23: cfg 2 with the integral-form cost + free dt / the terminal ball / moving obstacles + free dt;
     cid 24 / 25: integral form integrated by the trapezoidal rule, free / fixed dt;
     cid 26 / 27: hybrid minimum-time + quadratic control cost (Q = 0, fixed final state), point / integral form;
+    cid 41 / 42 / 43: midpoint differences on cfg 2 (fixed dt), cfg 2 in integral form (free dt, free final state) and
+    cfg 3 (car-like minimum time, fixed final state);
     cid 31: cfg 3 (car-like minimum time, polygon footprint) with moving obstacles"""
     moving = cid in (23, 31)
     if cid in (24, 25):
         cfg = configs.cfg2_trapezoidal(tol=1e-8, variable_dt=cid == 24)
     elif cid in (26, 27):
         cfg = configs.cfg2_hybrid_min_time(tol=1e-8, integral_form=cid == 27)
+    elif cid in (41, 42, 43):
+        cfg = {41: configs.cfg2, 42: configs.cfg2_integral_form, 43: configs.cfg3}[cid](tol=1e-8)
+        cfg.collocation = capi.COLLOC_MIDPOINT
     else:
         cfg = configs.cfg2_integral_form(tol=1e-8) if cid in (21, 23) else (configs.cfg2_terminal_ball(tol=1e-8) if cid == 22 else configs.config_for(3 if cid == 31 else cid, tol=1e-8))
-    cid = 2 if cid in (21, 22, 23, 24, 25, 26, 27) else (3 if cid == 31 else cid)
+    cid = 2 if cid in (21, 22, 23, 24, 25, 26, 27, 41, 42) else (3 if cid in (31, 43) else cid)
     data = configs.g1_instance() if cid == 1 else configs.generate(cid, b + 1)
     if moving:
         cfg.enable_dynamic_obstacles = 1
@@ -260,7 +265,7 @@ def _random_iterate(orc, cid, b, seed):
     inst.arr("X")[:, 1:] += 0.05 * rng.standard_normal((3, N - 1))
     inst.arr("U")[:] = 0.1 * rng.standard_normal((2, N)); inst.arr("U")[:, N - 1] = 0
     inst.associate(); inst.init_duals()
-    inst.arr("NU")[:] = rng.standard_normal((3, N)); inst.arr("NU")[:, N - 1] = 0
+    inst.arr("NU")[:] = nu_scale * rng.standard_normal((3, N)); inst.arr("NU")[:, N - 1] = 0
     act = inst.arr("LAM") > 0
     inst.arr("LAM")[:] = np.where(act, rng.uniform(0.5, 2, act.shape), 0)
     inst.arr("SCAL")[capi.SC_MU] = 0.1
@@ -279,7 +284,7 @@ def _unpack(inst, z):
 def _lagrangian(inst):
     inst.eval()
     S = inst.arr("SCAL"); K = inst.arr("KKT"); N = inst.N
-    e = K[capi.K_E:capi.K_E + 3, :N - 1]
+    e = inst.defects()   # (the record holds them too, transformed to the explicit form for midpoint differences)
     return S[capi.SC_OBJ] + (inst.arr("NU")[:, :N - 1] * e).sum() + (inst.arr("LAM") * (inst.arr("G") + inst.arr("S")) * (inst.arr("LAM") > 0)).sum()
 
 
@@ -306,11 +311,18 @@ def test_integral_form_objective_is_the_edge_sum(orc, rule):
     assert abs(inst.arr("SCAL")[capi.SC_OBJ] - J) < 1e-10 * max(1.0, abs(J))
 
 
-@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22, 23, 24, 25, 26, 27, 31])
+@pytest.mark.parametrize("cid", [1, 2, 3, 4, 21, 22, 23, 24, 25, 26, 27, 31, 41, 42, 43])
 def test_lagrangian_gradient_and_newton_step(orc, cid):
     """Analytic Lagrangian gradient vs finite differences; the Riccati Newton step (incl. the dt border and the fixed
-    terminal state) vs a dense numpy solve of the full KKT system assembled by finite differences."""
-    inst, cfg = _random_iterate(orc, cid, 0, 0)
+    terminal state) vs a dense numpy solve of the full KKT system assembled by finite differences.  Two random iterates:
+    multipliers of size 1 (indefinite Hessians: the inertia test must fire) and of size 0.05 (the step is compared)."""
+    compared = _check_gradient_and_newton_step(orc, cid, 1.0) + _check_gradient_and_newton_step(orc, cid, 0.05)
+    assert compared >= 1
+
+
+def _check_gradient_and_newton_step(orc, cid, nu_scale):
+    inst, cfg = _random_iterate(orc, cid, 0, 0, nu_scale)
+    compared = 0
     N = inst.N
     z0 = _pack(inst)
     n = len(z0)
@@ -346,7 +358,7 @@ def test_lagrangian_gradient_and_newton_step(orc, cid):
         _unpack(inst, z); inst.eval()
         G_ = inst.arr("GL")
         g = np.concatenate([G_[:3].ravel(), G_[3:5].ravel(), [inst.ws.contents.gl_dt]])
-        return g, inst.arr("KKT")[capi.K_E:capi.K_E + 3, :N - 1].T.ravel().copy(), inst.arr("G").copy()
+        return g, inst.defects().T.ravel().copy(), inst.arr("G").copy()
     m = 3 * (N - 1); RS = inst.RS
     W = np.zeros((n, n)); Jc = np.zeros((m, n)); Jg = np.zeros((RS * N, n))
     for i in range(n):
@@ -364,9 +376,9 @@ def test_lagrangian_gradient_and_newton_step(orc, cid):
     gJ = gl - Jc.T @ nu - Jg.T @ np.where(act, LAM, 0)
     r = np.where(act, G + S, 0)
     gt = gJ + Jg.T @ (np.where(act, mu / S, 0) + sig * r)
-    e = inst.arr("KKT")[capi.K_E:capi.K_E + 3, :N - 1].T.ravel()
+    e = inst.defects().T.ravel()
     nf = len(free)
-    for delta in (0.0, 1e-2):
+    for delta in (0.0, 1e-2, 1.0, 100.0):   # (free-dt problems are indefinite away from the solution: large shifts get compared)
         Kmat = np.zeros((nf + m, nf + m))
         Kmat[:nf, :nf] = Hc[np.ix_(free, free)] + delta * np.eye(nf); Kmat[:nf, nf:] = Jc[:, free].T; Kmat[nf:, :nf] = Jc[:, free]
         ev = np.linalg.eigvalsh(Kmat)
@@ -386,6 +398,8 @@ def test_lagrangian_gradient_and_newton_step(orc, cid):
         nup = STEP[5:8, :N - 1].T.ravel()
         assert np.abs(dz[free] - sol[:nf]).max() < 1e-5 * max(1.0, np.abs(sol[:nf]).max())
         assert np.abs(nup - sol[nf:]).max() < 1e-5 * max(1.0, np.abs(sol[nf:]).max())
+        compared += 1
+    return compared
 
 
 @pytest.mark.parametrize("n,n_new", [(20, 21), (20, 19), (50, 57), (33, 12), (5, 3), (3, 8)])
