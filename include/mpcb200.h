@@ -330,8 +330,10 @@ int mpcb200_set_timing(mpcb200_handle* h, unsigned phase_mask);
 int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
 /* Execution options (never change results).  MPCB200_OPT_KKT_ATTEMPTS: how the (at most two) regularisation attempts of
    an IPM iteration are run -- 0 = automatic (side by side when the batch leaves SMs idle, i.e. 2*ceil(B/32) <= #SMs),
-   1 = one after the other inside the KKT kernel, 2 = always side by side. */
+   1 = one after the other inside the KKT kernel, 2 = always side by side.
+   MPCB200_OPT_STREAM_REFILL_EVERY: IPM iterations between two refills of the pool of mpcb200_solve_stream (1..16). */
 #define MPCB200_OPT_KKT_ATTEMPTS 1
+#define MPCB200_OPT_STREAM_REFILL_EVERY 2
 int mpcb200_set_option(mpcb200_handle* h, int option, int value);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */

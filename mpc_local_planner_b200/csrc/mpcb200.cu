@@ -881,6 +881,7 @@ struct mpcb200_handle
     size_t ric_attempt_stride;  // doubles between the gain tiles of KKT attempt 0 and 1 (speculative mode)
     int num_sms;
     int spec_mode;              // MPCB200_OPT_KKT_ATTEMPTS: 0 auto, 1 serial, 2 side by side
+    int refill_every;           // MPCB200_OPT_STREAM_REFILL_EVERY: IPM iterations between two refills of the streaming pool
     int spec;                   // this solve runs the two KKT attempts of an iteration side by side (small batches)
     unsigned timing_mask;       // phases bracketed by CUDA events inside solve (bit = phase id); default: KKT only
     cudaStream_t stream, own_stream;  // stream in use / the stream the handle created
@@ -1010,7 +1011,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
         CKC(cudaMalloc(&h->ric_tiles, 2 * h->ric_attempt_stride * sizeof(double)));
         CKC(cudaMemsetAsync(h->kkt_tiles, 0, ntiles * N * KW * TILE * sizeof(double), h->stream));
         CKC(cudaMemsetAsync(h->ric_tiles, 0, 2 * h->ric_attempt_stride * sizeof(double), h->stream));
-        h->spec = 0; h->spec_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT;
+        h->spec = 0; h->spec_mode = 0; h->refill_every = STREAM_REFILL_EVERY; h->timing_mask = 1u << MPCB200_PHASE_KKT;
         CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     }
     CKC(cudaMalloc(&h->d_x0, B * 3 * 8)); CKC(cudaMalloc(&h->d_xf, B * 3 * 8)); CKC(cudaMalloc(&h->d_uprev, B * 2 * 8));
@@ -1393,7 +1394,8 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
     stream_begin_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, B, st);
     h->stats.launches_total += 1;
     const int grid4 = grid_for(B, WARPS_PER_CTA);
-    const long long max_rounds = ((long long)(total + B - 1) / B + 2) * (h->cfg.max_iter + 2 + 3 * STREAM_REFILL_EVERY);
+    const int refill_every = h->refill_every;
+    const long long max_rounds = ((long long)(total + B - 1) / B + 2) * (h->cfg.max_iter + 2 + 3 * refill_every);
     const int POLL = 4;
     int pending = -1;
     bool done = false;
@@ -1401,7 +1403,7 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
     const cudaStream_t main_stream = h->stream;
     for (long long it = 0; it < max_rounds && !done; ++it)
     {
-        if (it % STREAM_REFILL_EVERY == 0)
+        if (it % refill_every == 0)
         {
             // refill on the main stream (after the side work of the previous round); the cold initialisation and the
             // association of the refilled slots then run on the side stream, beside the next iterations of the other slots
@@ -1416,10 +1418,10 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
             h->stream = main_stream;
             if (rc) break;
             CK(cudaEventRecord(h->ev_ready, h->side_stream));
-            if ((it / STREAM_REFILL_EVERY) % POLL == POLL - 1)
+            if ((it / refill_every) % POLL == POLL - 1)
             {
                 // results handed over so far, polled one poll behind (see solve_device)
-                const int slot = (int)((it / STREAM_REFILL_EVERY / POLL) & 1);
+                const int slot = (int)((it / refill_every / POLL) & 1);
                 CK(cudaMemcpyAsync(h->h_stream_counters + 2 * slot, h->d_stream_counters, 8, cudaMemcpyDeviceToHost, h->stream));
                 CK(cudaEventRecord(h->poll_ev[slot], h->stream));
                 if (pending >= 0)
@@ -1657,6 +1659,7 @@ extern "C" int mpcb200_set_option(mpcb200_handle* h, int option, int value)
 {
     if (!h) return MPCB200_E_INVALID;
     if (option == MPCB200_OPT_KKT_ATTEMPTS && value >= 0 && value <= 2) { h->spec_mode = value; return 0; }
+    if (option == MPCB200_OPT_STREAM_REFILL_EVERY && value >= 1 && value <= 16) { h->refill_every = value; return 0; }
     return set_err(h, MPCB200_E_INVALID, "unknown option or value");
 }
 
