@@ -64,7 +64,7 @@ def scipy_solve(cfg, data, b, method="SLSQP"):
         setz(z); inst.eval(); return SC[capi.SC_OBJ]
 
     def ceq(z):
-        setz(z); inst.eval(); return inst.arr("KKT")[capi.K_E:capi.K_E + 3, :N - 1].ravel().copy()
+        setz(z); return inst.defects().ravel().copy()   # raw collocation defects (orc_defect per interval)
 
     def cin(z):
         setz(z); inst.eval(); return -(inst.arr("G")[act]).copy()
@@ -149,8 +149,42 @@ def extra():
         json.dump(dict(config_id=cid, n=n, instances=rows), open(os.path.join(HERE, fname), "w"), indent=1)
 
 
+def options():
+    """python tests/golden/make_golden.py options -- fixtures for non-default options on cfg 2 (fixed dt): midpoint differences,
+    and the integral-form cost integrated by the trapezoidal rule.  (With a free dt the integral-form problems have many
+    local optima -- dt l(x, u) is indefinite in (x, u, dt) -- and two local methods rarely meet: no fixture.)"""
+    only = sys.argv[2] if len(sys.argv) > 2 else None
+    for name, make, fname, want in (("midpoint", lambda: _with(configs.cfg2(tol=1e-8), collocation=capi.COLLOC_MIDPOINT), "slsqp_cfg2_midpoint.json", 5),
+                                    ("trapezoidal", lambda: configs.cfg2_trapezoidal(tol=1e-8, variable_dt=False), "slsqp_cfg2_trapezoidal.json", 4)):
+        if only and name != only:
+            continue
+        cfg = make()
+        data = configs.generate(2, 32)
+        ref = orc.step_batch(cfg, data, n_threads=4)
+        sel = [b for b in range(32) if ref["status"][b] == 0][:want + 4]
+        rows = []
+        for b in sel:
+            t = time.time()
+            r = scipy_solve(cfg, data, b)
+            r["instance"] = b
+            print("%s inst %d f %.6f ceq %.1e cin %.1e nit %d dt %.6f (%.0fs)" % (name, b, r["f"], r["ceq"], r["cin"], r["nit"], r["dt"], time.time() - t), flush=True)
+            if r["ceq"] < 1e-8 and r["cin"] > -1e-8 and r["nit"] < 500:
+                rows.append(annotate(cfg, data, b, r))
+            if len(rows) >= want:
+                break
+        json.dump(dict(config_id=2, option=name, instances=rows), open(os.path.join(HERE, fname), "w"), indent=1)
+
+
+def _with(cfg, **kw):
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+    if len(sys.argv) > 1 and sys.argv[1] == "options":
+        options()
+    elif len(sys.argv) > 1 and sys.argv[1] == "extra":
         extra()
     else:
         main()

@@ -41,3 +41,14 @@ def check_cfg3_n30(out, rows):
         assert abs(out["dt"][b] - r["dt_oracle"]) < 1e-6
         same += abs(r["dt_oracle"] - r["dt"]) < 1e-5
     assert same >= (len(rows) + 1) // 2
+
+
+def option_config(name, tol=1e-9):
+    """the configurations of the option fixtures (tests/golden/make_golden.py options)"""
+    from mpc_local_planner_b200 import capi, configs
+    if name == "midpoint":
+        cfg = configs.cfg2(tol=tol)
+        cfg.collocation = capi.COLLOC_MIDPOINT
+        return cfg
+    assert name == "trapezoidal"
+    return configs.cfg2_trapezoidal(tol=tol, variable_dt=False)

@@ -412,6 +412,17 @@ def test_golden_cfg4_and_cfg3(cuda_lib):
         s.close()
 
 
+@pytest.mark.parametrize("option", ["midpoint", "trapezoidal"])
+def test_golden_option_fixtures(cuda_lib, option):
+    """CUDA path against the scipy fixtures of midpoint differences and of the trapezoidal cost rule (cfg 2, fixed dt)."""
+    import golden_checks as gc
+    data = configs.generate(2, 32)
+    s = _solver(gc.option_config(option), 32)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    gc.check_fixed_dt(out, gc.load(f"slsqp_cfg2_{option}.json")["instances"], min_rows=4)
+    s.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cid,B", [(2, 96), (3, 40)])
 def test_kkt_attempt_scheduling_does_not_change_results(cuda_lib, cid, B):

@@ -63,6 +63,15 @@ def test_cfg4_and_cfg3_fixtures(orc):
     gc.check_cfg3_n30(out, g["instances"])
 
 
+@pytest.mark.parametrize("option", ["midpoint", "trapezoidal"])
+def test_option_fixtures(orc, option):
+    """Midpoint differences and the trapezoidal cost rule on cfg 2 against SLSQP on the same restated functions."""
+    import golden_checks as gc
+    g = gc.load(f"slsqp_cfg2_{option}.json")
+    out = orc.step_batch(gc.option_config(option), configs.generate(2, 32), n_threads=2)
+    gc.check_fixed_dt(out, g["instances"], min_rows=4)
+
+
 def test_converged_solutions_are_feasible_kkt_points(orc):
     """Independent of any solver: at the returned point the reference-form defects vanish, all rows hold, the bounds hold."""
     import ctypes as C
