@@ -229,6 +229,28 @@ int mpcb200_resample(mpcb200_handle* h, int n_new);
 /* current horizon and the capacity (config.n at create) */
 int mpcb200_get_horizon(const mpcb200_handle* h, int* n, int* n_capacity);
 
+/*
+ * Costmap -> point obstacles for B robots: replaces MpcLocalPlannerROS::updateObstacleContainerWithCostmap
+ * (src/mpc_local_planner_ros.cpp:474-499).  Every LETHAL cell (costmap_2d::LETHAL_OBSTACLE = 254) of the cells
+ * mx = 0..size_x-2, my = 0..size_y-2 (the reference's loop bounds) becomes a point obstacle at the cell centre
+ * (Costmap2D::mapToWorld: origin + (m + 0.5) resolution) unless it lies behind the robot (negative projection on the heading)
+ * AND farther than behind_robot_dist (costmap_obstacles_behind_robot_dist).  Order = the reference's push_back order
+ * (mx outer, my inner).  Outputs in the layout of mpcb200_obstacles with max_per_instance slots per robot:
+ * count[b] = obstacles written = min(found[b], max_per_instance); found[b] = cells that qualified (found > count: the list was
+ * cut -- the solver takes at most 64 obstacles per instance in this round); velocities 0.
+ */
+typedef struct mpcb200_costmaps {
+    int size_x, size_y;          /* cells: Costmap2D::getSizeInCellsX / Y */
+    double resolution;           /* metres per cell */
+    const double* origin;        /* [B*2] world coordinates of the lower-left corner of cell (0,0): getOriginX / Y */
+    const unsigned char* cost;   /* [B*size_y*size_x], cell (mx, my) at my*size_x + mx (Costmap2D::getIndex) */
+} mpcb200_costmaps;
+int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* robot_pose /*[B*3]*/,
+                              double behind_robot_dist, int max_per_instance, int* count /*[B]*/, int* found /*[B] or NULL*/,
+                              int* type /*[B*max]*/, double* params /*[B*max*MPCB200_OBST_STRIDE]*/);
+/* device time (ms, CUDA events around the three kernels) of the last mpcb200_costmap_obstacles call */
+double mpcb200_costmap_last_ms(const mpcb200_handle* h);
+
 void mpcb200_destroy(mpcb200_handle* h);
 
 /* Last error message of this handle (or of create() when h == NULL). Never NULL. */

@@ -93,6 +93,11 @@ class Config(C.Structure):
         return c
 
 
+class Costmaps(C.Structure):
+    _fields_ = [("size_x", C.c_int), ("size_y", C.c_int), ("resolution", C.c_double), ("origin", C.POINTER(C.c_double)),
+                ("cost", C.POINTER(C.c_ubyte))]
+
+
 class Obstacles(C.Structure):
     _fields_ = [("max_per_instance", C.c_int), ("count", C.POINTER(C.c_int)), ("type", C.POINTER(C.c_int)),
                 ("params", C.POINTER(C.c_double))]
@@ -181,7 +186,7 @@ EXPORTS = [
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
     "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
-    "mpcb200_resample", "mpcb200_get_horizon",
+    "mpcb200_resample", "mpcb200_get_horizon", "mpcb200_costmap_obstacles", "mpcb200_costmap_last_ms",
 ]
 
 
@@ -207,6 +212,9 @@ def load_library(path=None):
                                          dp, dp, dp, ip, dp, ip, dp]
     lib.mpcb200_reset.argtypes = [vp, ucp, C.c_int]
     lib.mpcb200_resample.argtypes = [vp, C.c_int]
+    lib.mpcb200_costmap_obstacles.argtypes = [vp, C.c_int, C.POINTER(Costmaps), dp, C.c_double, C.c_int, ip, ip, ip, dp]
+    lib.mpcb200_costmap_last_ms.argtypes = [vp]
+    lib.mpcb200_costmap_last_ms.restype = C.c_double
     lib.mpcb200_get_horizon.argtypes = [vp, ip, ip]
     lib.mpcb200_destroy.argtypes = [vp]
     lib.mpcb200_destroy.restype = None
@@ -351,6 +359,22 @@ class BatchSolver:
             w = np.ascontiguousarray(which, dtype=np.uint8)
         self._check(self.lib.mpcb200_reset(self.h, w.ctypes.data_as(C.POINTER(C.c_ubyte)) if w is not None else None,
                                            self.B), "mpcb200_reset")
+
+    def costmap_obstacles(self, cost, origin, resolution, robot_pose, behind_robot_dist, max_per_instance):
+        """updateObstacleContainerWithCostmap for B robots: cost [B, size_y, size_x] uint8, origin [B, 2], robot_pose [B, 3]
+        -> (count [B], type [B, M], params [B, M, OBST_STRIDE]) in the layout step() takes as `obstacles`, and found [B]."""
+        cost = np.ascontiguousarray(cost, dtype=np.uint8)
+        origin = np.ascontiguousarray(origin, dtype=np.float64); pose = np.ascontiguousarray(robot_pose, dtype=np.float64)
+        B, M = cost.shape[0], int(max_per_instance)
+        m = Costmaps(cost.shape[2], cost.shape[1], float(resolution), _dp(origin), cost.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        count = np.zeros(B, dtype=np.int32); found = np.zeros(B, dtype=np.int32)
+        typ = np.zeros((B, M), dtype=np.int32); par = np.zeros((B, M, OBST_STRIDE))
+        self._check(self.lib.mpcb200_costmap_obstacles(self.h, B, C.byref(m), _dp(pose), float(behind_robot_dist), M, _ip(count), _ip(found),
+                                                       _ip(typ), _dp(par)), "mpcb200_costmap_obstacles")
+        return (count, typ, par), found
+
+    def costmap_last_ms(self):
+        return float(self.lib.mpcb200_costmap_last_ms(self.h))
 
     def resample(self, n_new):
         """resampleTrajectory(n_new) for every instance: the horizon of the batch becomes n_new (<= cfg.n at create)."""

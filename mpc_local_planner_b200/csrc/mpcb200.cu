@@ -860,6 +860,95 @@ __global__ void resample_unpack_kernel(WsLayout L, double* ws, const double* rec
     ASC(MPCB200_SC_DT) = resample_serial(n_old, r + MPCB200_SCAL_WORDS, r + MPCB200_SCAL_WORDS + 3 * n_old, r[MPCB200_SC_DT], L.N, W + L.oX, W + L.oU);
 }
 
+// ---- costmap -> point obstacles (MpcLocalPlannerROS::updateObstacleContainerWithCostmap, mpc_local_planner_ros.cpp:474-499) ----
+// The reference walks the cells mx = 0..size_x-2 (outer), my = 0..size_y-2 (inner), keeps the LETHAL ones that are not farther
+// than behind_dist behind the robot and appends them as point obstacles at the cell centres.  Here a thread owns one column mx
+// (consecutive threads read consecutive bytes of a row) and walks it in my order, so that column counts + an exclusive scan
+// over the columns reproduce the reference's order exactly: pass 1 counts, pass 2 scans, pass 3 writes.  HBM-bound byte work:
+// the map is read twice (the second time mostly from L2), 1 byte per cell.
+#define COSTMAP_LETHAL 254   // costmap_2d::LETHAL_OBSTACLE
+struct CostmapArgs
+{
+    int size_x, size_y;
+    double resolution, behind_dist;
+    const unsigned char* cost;   // [B][size_y][size_x]
+    const double* origin;        // [B][2]
+    const double* pose;          // [B][3]
+};
+__device__ __forceinline__ bool costmap_keep(const CostmapArgs& a, int mx, int my, double ox, double oy, double px, double py, double dirx, double diry,
+                                             double* wx, double* wy)
+{
+    // Costmap2D::mapToWorld: cell centre
+    *wx = ox + ((double)mx + 0.5) * a.resolution;
+    *wy = oy + ((double)my + 0.5) * a.resolution;
+    const double dx = *wx - px, dy = *wy - py;
+    // "not far behind the robot" (mpc_local_planner_ros.cpp:492-493)
+    return !(dx * dirx + dy * diry < 0.0 && sqrt(dx * dx + dy * dy) > a.behind_dist);
+}
+template <bool WRITE>
+__global__ void costmap_scan_kernel(CostmapArgs a, int B, int* colcount /*[B][size_x]*/, const int* colstart /*[B][size_x]*/, int max_out,
+                                    double* params /*[B][max_out][MPCB200_OBST_STRIDE]*/, int* type /*[B][max_out]*/)
+{
+    const int b = blockIdx.y;
+    const int mx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || mx >= a.size_x) return;
+    int n = 0;
+    if (mx < a.size_x - 1)
+    {
+        const unsigned char* map = a.cost + (size_t)b * a.size_x * a.size_y;
+        const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
+        const double px = a.pose[3 * b], py = a.pose[3 * b + 1];
+        double diry, dirx;
+        sincos(a.pose[3 * b + 2], &diry, &dirx);   // PoseSE2::orientationUnitVec
+        const int base = WRITE ? colstart[(size_t)b * a.size_x + mx] : 0;
+        for (int my = 0; my < a.size_y - 1; ++my)
+        {
+            if (map[(size_t)my * a.size_x + mx] != COSTMAP_LETHAL) continue;
+            double wx, wy;
+            if (!costmap_keep(a, mx, my, ox, oy, px, py, dirx, diry, &wx, &wy)) continue;
+            if (WRITE)
+            {
+                const int o = base + n;
+                if (o < max_out)
+                {
+                    double* q = params + ((size_t)b * max_out + o) * MPCB200_OBST_STRIDE;
+                    q[0] = wx; q[1] = wy;
+                    for (int i = 2; i < MPCB200_OBST_STRIDE; ++i) q[i] = 0.0;
+                    type[(size_t)b * max_out + o] = MPCB200_OBST_POINT;
+                }
+            }
+            ++n;
+        }
+    }
+    if (!WRITE) colcount[(size_t)b * a.size_x + mx] = n;
+}
+// exclusive scan of the column counts of one robot (one CTA per robot); found = total, count = min(total, max_out)
+__global__ void costmap_offsets_kernel(int size_x, int B, const int* colcount, int* colstart, int max_out, int* count, int* found)
+{
+    const int b = blockIdx.x;
+    __shared__ int carry;
+    __shared__ int warp_tot[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < size_x; base += blockDim.x)
+    {
+        const int i = base + threadIdx.x;
+        const int v = i < size_x ? colcount[(size_t)b * size_x + i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) { if (w < wid) woff += warp_tot[w]; tot += warp_tot[w]; }
+        if (i < size_x) colstart[(size_t)b * size_x + i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { found[b] = carry; count[b] = carry < max_out ? carry : max_out; }
+}
+
 __global__ void flush_kernel(double* buf, size_t n)
 {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -876,6 +965,7 @@ struct mpcb200_handle
     int max_batch, device, B;
     int n_cap;                  // horizon the buffers were sized for at create (mpcb200_resample moves cfg.n within [3, n_cap])
     double* d_resample;         // scratch of mpcb200_resample, allocated on first use
+    void* d_cm; size_t cm_cap; double costmap_ms;  // scratch of mpcb200_costmap_obstacles (grown on demand), device ms of its last call
     double* ws;
     double *kkt_tiles, *ric_tiles;
     size_t ric_attempt_stride;  // doubles between the gain tiles of KKT attempt 0 and 1 (speculative mode)
@@ -991,7 +1081,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->kkt_tiles = nullptr; h->ric_tiles = nullptr; h->ev_used = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
-    h->n_cap = cfg->n; h->d_resample = nullptr;
+    h->n_cap = cfg->n; h->d_resample = nullptr; h->d_cm = nullptr; h->cm_cap = 0; h->costmap_ms = 0.0;
     h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
@@ -1068,7 +1158,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
                     h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush, h->d_counters, h->d_slot_of, h->d_inst_of_slot};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* sptrs[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
-                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_slot_inst, h->d_stream_counters, h->d_resample};
+                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_slot_inst, h->d_stream_counters, h->d_resample, h->d_cm};
     for (void* p : sptrs) if (p) cudaFree(p);
     if (h->h_stream_counters) cudaFreeHost(h->h_stream_counters);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
@@ -1726,6 +1816,64 @@ extern "C" int mpcb200_export_controls(mpcb200_handle* h, void* dst_dev)
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
+extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* robot_pose, double behind_robot_dist,
+                                         int max_per_instance, int* count, int* found, int* type, double* params)
+{
+    if (!h) return MPCB200_E_INVALID;
+    if (B < 1 || !maps || !maps->cost || !maps->origin || !robot_pose || !count || !type || !params || max_per_instance < 1)
+        return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: B >= 1, maps, poses and output arrays are required");
+    if (maps->size_x < 2 || maps->size_y < 2 || !(maps->resolution > 0)) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: maps of at least 2 x 2 cells with a positive resolution");
+    CK(cudaSetDevice(h->device));
+    const size_t W = (size_t)maps->size_x, H = (size_t)maps->size_y, M = (size_t)max_per_instance;
+    const size_t need = (size_t)B * W * H + (size_t)B * 5 * 8 + 2 * (size_t)B * W * 4 + 2 * (size_t)B * 4 + (size_t)B * M * (MPCB200_OBST_STRIDE * 8 + 4) + 256;
+    if (need > h->cm_cap)
+    {
+        if (h->d_cm) cudaFree(h->d_cm);
+        h->d_cm = nullptr; h->cm_cap = 0;
+        CK(cudaMalloc(&h->d_cm, need));
+        h->cm_cap = need;
+    }
+    // carve the scratch: doubles first (alignment), then ints, then the maps
+    char* p = (char*)h->d_cm;
+    double* d_origin = (double*)p; p += (size_t)B * 2 * 8;
+    double* d_pose = (double*)p; p += (size_t)B * 3 * 8;
+    double* d_params = (double*)p; p += (size_t)B * M * MPCB200_OBST_STRIDE * 8;
+    int* d_colcount = (int*)p; p += (size_t)B * W * 4;
+    int* d_colstart = (int*)p; p += (size_t)B * W * 4;
+    int* d_count = (int*)p; p += (size_t)B * 4;
+    int* d_found = (int*)p; p += (size_t)B * 4;
+    int* d_type = (int*)p; p += (size_t)B * M * 4;
+    unsigned char* d_cost = (unsigned char*)p;
+    CK(cudaMemcpyAsync(d_cost, maps->cost, (size_t)B * W * H, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_origin, maps->origin, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_pose, robot_pose, (size_t)B * 24, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * 40);
+    CostmapArgs a{maps->size_x, maps->size_y, maps->resolution, behind_robot_dist, d_cost, d_origin, d_pose};
+    const dim3 grid((unsigned)((W + 127) / 128), (unsigned)B);
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    CK(cudaEventRecord(t0, h->stream));
+    costmap_scan_kernel<false><<<grid, 128, 0, h->stream>>>(a, B, d_colcount, nullptr, max_per_instance, nullptr, nullptr);
+    costmap_offsets_kernel<<<B, 256, 0, h->stream>>>(maps->size_x, B, d_colcount, d_colstart, max_per_instance, d_count, d_found);
+    costmap_scan_kernel<true><<<grid, 128, 0, h->stream>>>(a, B, nullptr, d_colstart, max_per_instance, d_params, d_type);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(t1, h->stream));
+    h->stats.launches_total += 3;
+    CK(cudaMemcpyAsync(count, d_count, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (found) CK(cudaMemcpyAsync(found, d_found, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(type, d_type, (size_t)B * M * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(params, d_params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (long long)((size_t)B * 8 + (size_t)B * M * (4 + MPCB200_OBST_STRIDE * 8));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    h->costmap_ms = ms;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    return MPCB200_OK;
+}
+
+extern "C" double mpcb200_costmap_last_ms(const mpcb200_handle* h) { return h ? h->costmap_ms : 0.0; }
+
 extern "C" int mpcb200_flush_l2(mpcb200_handle* h)
 {
     if (!h) return MPCB200_E_INVALID;

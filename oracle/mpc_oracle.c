@@ -774,6 +774,31 @@ void orc_init_cold(const orc_problem* p, const double* x_init, orc_ws* ws)
 }
 
 /*
+ * MpcLocalPlannerROS::updateObstacleContainerWithCostmap [R/src/mpc_local_planner_ros.cpp:474-499] for one robot:
+ * cells mx = 0..size_x-2 (outer loop), my = 0..size_y-2 (inner loop) whose cost is costmap_2d::LETHAL_OBSTACLE (254) become
+ * point obstacles at Costmap2D::mapToWorld(mx, my) = origin + (m + 0.5) resolution [EXT: costmap_2d], unless
+ * obs_dir . robot_orient < 0 and |obs_dir| > behind_dist (:492-493).  cost: cell (mx, my) at my*size_x + mx (Costmap2D::getIndex).
+ * Writes at most max_out points (x, y pairs) in the reference's push_back order; returns how many cells qualified.
+ */
+int orc_costmap_obstacles(int size_x, int size_y, double resolution, const double* origin, const unsigned char* cost,
+                          const double* robot_pose, double behind_dist, int max_out, double* xy)
+{
+    const double ox = cos(robot_pose[2]), oy = sin(robot_pose[2]); /* PoseSE2::orientationUnitVec */
+    int found = 0;
+    for (int i = 0; i < size_x - 1; ++i)
+        for (int j = 0; j < size_y - 1; ++j)
+        {
+            if (cost[(size_t)j * size_x + i] != 254) continue;
+            const double wx = origin[0] + (i + 0.5) * resolution, wy = origin[1] + (j + 0.5) * resolution;
+            const double dx = wx - robot_pose[0], dy = wy - robot_pose[1];
+            if (dx * ox + dy * oy < 0 && sqrt(dx * dx + dy * dy) > behind_dist) continue;
+            if (found < max_out) { xy[2 * found] = wx; xy[2 * found + 1] = wy; }
+            ++found;
+        }
+    return found;
+}
+
+/*
  * FullDiscretizationGridBaseSE2::resampleTrajectory(n_new)
  * [R/src/optimal_control/full_discretization_grid_base_se2.cpp:440-524], the operation the grid adaptation applies with
  * n_new = n +- 1 [R/src/optimal_control/finite_differences_variable_grid_se2.cpp:99-121].

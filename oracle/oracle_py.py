@@ -59,6 +59,7 @@ def lib():
         L.orc_objective.restype = C.c_double
         L.orc_objective.argtypes = [C.POINTER(Problem), C.POINTER(Ws), dp, dp, C.c_double]
         L.orc_ws_alloc.restype = C.POINTER(Ws)
+        L.orc_costmap_obstacles.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_ubyte), dp, C.c_double, C.c_int, dp]
         L.orc_resample_trajectory.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, dp, dp]
         L.orc_resample_trajectory.restype = C.c_double
         L.orc_ws_alloc.argtypes = [C.c_int, C.c_int]
@@ -179,6 +180,16 @@ class Instance:
         X = np.ascontiguousarray(X)
         U = np.ascontiguousarray(U)
         return self.L.orc_objective(C.byref(self.p), self.ws, _dp(X), _dp(U), float(dt))
+
+
+def costmap_obstacles(cost, origin, resolution, robot_pose, behind_dist, max_out):
+    """updateObstacleContainerWithCostmap for one robot: cost [size_y, size_x] uint8 -> (xy [min(found, max_out), 2], found)"""
+    cost = np.ascontiguousarray(cost, dtype=np.uint8)
+    origin = np.ascontiguousarray(origin, dtype=np.float64); pose = np.ascontiguousarray(robot_pose, dtype=np.float64)
+    xy = np.zeros((max_out, 2))
+    found = lib().orc_costmap_obstacles(cost.shape[1], cost.shape[0], float(resolution), _dp(origin),
+                                        cost.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(pose), float(behind_dist), int(max_out), _dp(xy))
+    return xy[: min(found, max_out)].copy(), found
 
 
 def resample_trajectory(X, U, dt, n_new):

@@ -529,3 +529,41 @@ def test_midpoint_differences(cuda_lib, orc, base):
     d = x[:, 1:] - x[:, :-1]; d[..., 2] = dth
     assert np.abs(f * dt[..., None] - d).max() < 1e-6
     s.close()
+
+
+def test_costmap_obstacles_match_oracle_and_feed_the_solver(cuda_lib, orc):
+    """mpcb200_costmap_obstacles (updateObstacleContainerWithCostmap for a batch of robots) against the oracle's loops: same
+    cells, same order, same cut; the lists then go straight into step() as its obstacles."""
+    from test_oracle_functions import _random_costmap
+    rng = np.random.default_rng(5)
+    B, W, H, res = 24, 200, 160, 0.05
+    cost = np.stack([_random_costmap(rng, W, H, 0.002) for _ in range(B)])
+    for b in range(B):
+        cost[b, :, W - 1] = 0; cost[b, H - 1, :] = 0
+    cost[0] = 0                      # an empty map
+    cost[1, 10:40, 20:60] = 254      # a dense block: more cells than slots
+    origin = rng.uniform(-3, 3, (B, 2))
+    pose = np.concatenate([origin + rng.uniform(2.0, 6.0, (B, 2)), rng.uniform(-np.pi, np.pi, (B, 1))], axis=1)
+    cfg = configs.cfg2(tol=1e-6)
+    s = _solver(cfg, B)
+    M = 64
+    (count, typ, par), found = s.costmap_obstacles(cost, origin, res, pose, 0.3, M)
+    assert s.costmap_last_ms() > 0
+    for b in range(B):
+        xy, f = orc.costmap_obstacles(cost[b], origin[b], res, pose[b], 0.3, M)
+        assert found[b] == f and count[b] == min(f, M)
+        np.testing.assert_allclose(par[b, :count[b], :2], xy, atol=1e-12)
+        assert (par[b, :count[b], 2:] == 0).all() and (typ[b, :count[b]] == capi.OBST_POINT).all()
+    assert count[0] == 0 and found[1] > M and count[1] == M
+    # chain: robots at their poses, goals 3 m ahead, the extracted lists as obstacles (rows where the goal or start is not
+    # inside an obstacle's clearance converge like any cfg-2 instance)
+    x0 = pose.copy()
+    xf = pose.copy(); xf[:, 0] += 3.0 * np.cos(pose[:, 2]); xf[:, 1] += 3.0 * np.sin(pose[:, 2])
+    out = s.step(x0, xf, None, 0.2, (count, typ, par), None)
+    ref = orc.step_batch(cfg, dict(x0=x0, xf=xf, u_prev=np.zeros((B, 2)), u_prev_dt=0.2, obstacles=(count, typ, par), viapoints=None), n_threads=8)
+    assert (out["status"] == ref["status"]).mean() >= 0.8
+    both = (out["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= B // 3
+    du = np.abs(out["u_seq"][both] - ref["u_seq"][both]).reshape(both.sum(), -1).max(axis=1)
+    assert (du < U_TOL).mean() >= 0.8
+    s.close()

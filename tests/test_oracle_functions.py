@@ -426,3 +426,33 @@ def test_resample_trajectory_properties(orc, n, n_new):
     # controls: the old interval that ends at or after t_new (a sample exactly on an old grid point takes the interval before it)
     idx = np.minimum(np.ceil(t_new[1:-1] / dt - 1e-12).astype(int), n - 1)
     np.testing.assert_array_equal(Un[:, 1:-1], U[:, np.minimum(idx - 1, n - 2)])
+
+
+def _random_costmap(rng, W, H, density=0.01):
+    cost = rng.choice(np.array([0, 1, 100, 253, 255], dtype=np.uint8), size=(H, W))   # free, inflated, inscribed, unknown
+    cost[rng.random((H, W)) < density] = 254                                          # costmap_2d::LETHAL_OBSTACLE
+    cost[:, W - 1] = 254; cost[H - 1, :] = 254   # the reference's loops stop one cell short of both upper edges
+    return cost
+
+
+@pytest.mark.parametrize("W,H", [(60, 40), (33, 77), (2, 2), (128, 3)])
+def test_costmap_obstacles_against_numpy(orc, W, H):
+    """updateObstacleContainerWithCostmap (mpc_local_planner_ros.cpp:474-499): the oracle's loops against a vectorised numpy
+    restatement -- which cells qualify, their world coordinates, the reference's push_back order, the cut at max_out."""
+    rng = np.random.default_rng(W * 1000 + H)
+    cost = _random_costmap(rng, W, H, 0.05)
+    origin = rng.uniform(-5, 5, 2); res = 0.05
+    pose = np.array([origin[0] + 0.5 * W * res, origin[1] + 0.5 * H * res, rng.uniform(-np.pi, np.pi)])
+    behind = 0.4
+    mx, my = np.meshgrid(np.arange(W - 1), np.arange(H - 1), indexing="ij")          # [mx, my]: mx outer, my inner
+    wx = origin[0] + (mx + 0.5) * res; wy = origin[1] + (my + 0.5) * res
+    dx, dy = wx - pose[0], wy - pose[1]
+    keep = (cost[:H - 1, :W - 1].T == 254) & ~((dx * np.cos(pose[2]) + dy * np.sin(pose[2]) < 0) & (np.hypot(dx, dy) > behind))
+    want = np.stack([wx[keep], wy[keep]], -1)                                         # boolean indexing walks mx-major
+    xy, found = orc.costmap_obstacles(cost, origin, res, pose, behind, max_out=10000)
+    assert found == len(want)
+    np.testing.assert_allclose(xy, want, atol=1e-12)
+    if found > 3:
+        xy3, found3 = orc.costmap_obstacles(cost, origin, res, pose, behind, max_out=3)
+        assert found3 == found and len(xy3) == 3
+        np.testing.assert_array_equal(xy3, xy[:3])
