@@ -862,11 +862,15 @@ __global__ void resample_unpack_kernel(WsLayout L, double* ws, const double* rec
 
 // ---- costmap -> point obstacles (MpcLocalPlannerROS::updateObstacleContainerWithCostmap, mpc_local_planner_ros.cpp:474-499) ----
 // The reference walks the cells mx = 0..size_x-2 (outer), my = 0..size_y-2 (inner), keeps the LETHAL ones that are not farther
-// than behind_dist behind the robot and appends them as point obstacles at the cell centres.  Here a thread owns one column mx
-// (consecutive threads read consecutive bytes of a row) and walks it in my order, so that column counts + an exclusive scan
-// over the columns reproduce the reference's order exactly: pass 1 counts, pass 2 scans, pass 3 writes.  HBM-bound byte work:
-// the map is read twice (the second time mostly from L2), 1 byte per cell.
-#define COSTMAP_LETHAL 254   // costmap_2d::LETHAL_OBSTACLE
+// than behind_dist behind the robot and appends them as point obstacles at the cell centres.  HBM-bound byte work, one byte per
+// cell, read ONCE:
+//   mark    a thread owns four adjacent columns (one 32-bit load per row, a warp reads 128 contiguous bytes), tests the word
+//           for a LETHAL byte with one bit trick, applies the filter to the few hits and records them as one bit per cell in
+//           per-column masks (32 rows per word, 1/8 byte per cell) next to the per-column counts;
+//   offsets exclusive scan of the column counts of each robot;
+//   emit    a thread owns one column and walks its mask words in row order: column offsets + bit order reproduce the
+//           reference's push_back order (mx outer, my inner) exactly.
+#define COSTMAP_LETHAL 254u   // costmap_2d::LETHAL_OBSTACLE
 struct CostmapArgs
 {
     int size_x, size_y;
@@ -875,52 +879,95 @@ struct CostmapArgs
     const double* origin;        // [B][2]
     const double* pose;          // [B][3]
 };
-__device__ __forceinline__ bool costmap_keep(const CostmapArgs& a, int mx, int my, double ox, double oy, double px, double py, double dirx, double diry,
-                                             double* wx, double* wy)
+// Costmap2D::mapToWorld: cell centre
+__device__ __forceinline__ double costmap_world(double o, int m, double res) { return o + ((double)m + 0.5) * res; }
+__device__ __forceinline__ bool costmap_keep(const CostmapArgs& a, int mx, int my, double ox, double oy, double px, double py, double dirx, double diry)
 {
-    // Costmap2D::mapToWorld: cell centre
-    *wx = ox + ((double)mx + 0.5) * a.resolution;
-    *wy = oy + ((double)my + 0.5) * a.resolution;
-    const double dx = *wx - px, dy = *wy - py;
+    const double dx = costmap_world(ox, mx, a.resolution) - px, dy = costmap_world(oy, my, a.resolution) - py;
     // "not far behind the robot" (mpc_local_planner_ros.cpp:492-493)
     return !(dx * dirx + dy * diry < 0.0 && sqrt(dx * dx + dy * dy) > a.behind_dist);
 }
-template <bool WRITE>
-__global__ void costmap_scan_kernel(CostmapArgs a, int B, int* colcount /*[B][size_x]*/, const int* colstart /*[B][size_x]*/, int max_out,
+__device__ __forceinline__ bool word_has_lethal(unsigned w)
+{
+    const unsigned x = w ^ 0xFEFEFEFEu;                       // LETHAL bytes become zero bytes
+    return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u;
+}
+template <bool VEC>   // VEC: size_x % 4 == 0, every row of every map starts 4-byte aligned
+__global__ void costmap_mark_kernel(CostmapArgs a, int B, int nrb, int Wp, unsigned* mask /*[B][nrb][Wp]*/, int* colcount /*[B][size_x]*/)
+{
+    const int b = blockIdx.y;
+    const int c0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (b >= B || c0 >= a.size_x) return;
+    const unsigned char* map = a.cost + (size_t)b * a.size_x * a.size_y;
+    const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
+    const double px = a.pose[3 * b], py = a.pose[3 * b + 1];
+    double diry, dirx;
+    sincos(a.pose[3 * b + 2], &diry, &dirx);   // PoseSE2::orientationUnitVec
+    int cnt[4] = {0, 0, 0, 0};
+    const int rows = a.size_y - 1;
+    for (int rb = 0; rb < nrb; ++rb)
+    {
+        unsigned m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 8)
+        {
+            unsigned w[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+            {
+                const int my = rb * 32 + r0 + r;
+                w[r] = 0u;
+                if (my < rows)
+                {
+                    const unsigned char* q = map + (size_t)my * a.size_x + c0;
+                    if (VEC) w[r] = *reinterpret_cast<const unsigned*>(q);
+                    else
+                        for (int i = 0; i < 4; ++i)
+                            if (c0 + i < a.size_x) w[r] |= (unsigned)q[i] << (8 * i);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+            {
+                if (!word_has_lethal(w[r])) continue;
+                const int my = rb * 32 + r0 + r;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (((w[r] >> (8 * i)) & 0xFFu) == COSTMAP_LETHAL && c0 + i < a.size_x - 1 &&
+                        costmap_keep(a, c0 + i, my, ox, oy, px, py, dirx, diry))
+                        m[i] |= 1u << (r0 + r);
+            }
+        }
+        *reinterpret_cast<uint4*>(mask + ((size_t)b * nrb + rb) * Wp + c0) = make_uint4(m[0], m[1], m[2], m[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cnt[i] += __popc(m[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (c0 + i < a.size_x) colcount[(size_t)b * a.size_x + c0 + i] = cnt[i];
+}
+__global__ void costmap_emit_kernel(CostmapArgs a, int B, int nrb, int Wp, const unsigned* mask, const int* colstart, int max_out,
                                     double* params /*[B][max_out][MPCB200_OBST_STRIDE]*/, int* type /*[B][max_out]*/)
 {
     const int b = blockIdx.y;
     const int mx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B || mx >= a.size_x) return;
-    int n = 0;
-    if (mx < a.size_x - 1)
+    if (b >= B || mx >= a.size_x - 1) return;
+    const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
+    int o = colstart[(size_t)b * a.size_x + mx];
+    for (int rb = 0; rb < nrb && o < max_out; ++rb)
     {
-        const unsigned char* map = a.cost + (size_t)b * a.size_x * a.size_y;
-        const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
-        const double px = a.pose[3 * b], py = a.pose[3 * b + 1];
-        double diry, dirx;
-        sincos(a.pose[3 * b + 2], &diry, &dirx);   // PoseSE2::orientationUnitVec
-        const int base = WRITE ? colstart[(size_t)b * a.size_x + mx] : 0;
-        for (int my = 0; my < a.size_y - 1; ++my)
+        unsigned m = mask[((size_t)b * nrb + rb) * Wp + mx];
+        while (m && o < max_out)
         {
-            if (map[(size_t)my * a.size_x + mx] != COSTMAP_LETHAL) continue;
-            double wx, wy;
-            if (!costmap_keep(a, mx, my, ox, oy, px, py, dirx, diry, &wx, &wy)) continue;
-            if (WRITE)
-            {
-                const int o = base + n;
-                if (o < max_out)
-                {
-                    double* q = params + ((size_t)b * max_out + o) * MPCB200_OBST_STRIDE;
-                    q[0] = wx; q[1] = wy;
-                    for (int i = 2; i < MPCB200_OBST_STRIDE; ++i) q[i] = 0.0;
-                    type[(size_t)b * max_out + o] = MPCB200_OBST_POINT;
-                }
-            }
-            ++n;
+            const int my = rb * 32 + __ffs(m) - 1;
+            m &= m - 1u;
+            double* q = params + ((size_t)b * max_out + o) * MPCB200_OBST_STRIDE;
+            q[0] = costmap_world(ox, mx, a.resolution); q[1] = costmap_world(oy, my, a.resolution);
+            for (int i = 2; i < MPCB200_OBST_STRIDE; ++i) q[i] = 0.0;
+            type[(size_t)b * max_out + o] = MPCB200_OBST_POINT;
+            ++o;
         }
     }
-    if (!WRITE) colcount[(size_t)b * a.size_x + mx] = n;
 }
 // exclusive scan of the column counts of one robot (one CTA per robot); found = total, count = min(total, max_out)
 __global__ void costmap_offsets_kernel(int size_x, int B, const int* colcount, int* colstart, int max_out, int* count, int* found)
@@ -1825,7 +1872,11 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     if (maps->size_x < 2 || maps->size_y < 2 || !(maps->resolution > 0)) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: maps of at least 2 x 2 cells with a positive resolution");
     CK(cudaSetDevice(h->device));
     const size_t W = (size_t)maps->size_x, H = (size_t)maps->size_y, M = (size_t)max_per_instance;
-    const size_t need = (size_t)B * W * H + (size_t)B * 5 * 8 + 2 * (size_t)B * W * 4 + 2 * (size_t)B * 4 + (size_t)B * M * (MPCB200_OBST_STRIDE * 8 + 4) + 256;
+    const int nrb = (int)((H - 1 + 31) / 32);            // 32-row blocks of the rows the reference visits
+    const int Wp = (int)((W + 3) / 4 * 4);               // mask row pitch: four columns per marking thread
+    const size_t mask_words = (size_t)B * nrb * Wp;
+    const size_t need = (size_t)B * W * H + (size_t)B * 5 * 8 + 2 * (size_t)B * W * 4 + 2 * (size_t)B * 4 + (size_t)B * M * (MPCB200_OBST_STRIDE * 8 + 4) +
+                        mask_words * 4 + 512;
     if (need > h->cm_cap)
     {
         if (h->d_cm) cudaFree(h->d_cm);
@@ -1833,29 +1884,31 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
         CK(cudaMalloc(&h->d_cm, need));
         h->cm_cap = need;
     }
-    // carve the scratch: doubles first (alignment), then ints, then the maps
+    // carve the scratch: 16-byte aligned pieces first (mask rows are stored as uint4), then ints, then the maps
     char* p = (char*)h->d_cm;
+    unsigned* d_mask = (unsigned*)p; p += mask_words * 4;
+    double* d_params = (double*)p; p += (size_t)B * M * MPCB200_OBST_STRIDE * 8;
     double* d_origin = (double*)p; p += (size_t)B * 2 * 8;
     double* d_pose = (double*)p; p += (size_t)B * 3 * 8;
-    double* d_params = (double*)p; p += (size_t)B * M * MPCB200_OBST_STRIDE * 8;
     int* d_colcount = (int*)p; p += (size_t)B * W * 4;
     int* d_colstart = (int*)p; p += (size_t)B * W * 4;
     int* d_count = (int*)p; p += (size_t)B * 4;
     int* d_found = (int*)p; p += (size_t)B * 4;
     int* d_type = (int*)p; p += (size_t)B * M * 4;
-    unsigned char* d_cost = (unsigned char*)p;
+    unsigned char* d_cost = (unsigned char*)p;            // 4-byte aligned: everything before it is a multiple of 4 bytes
     CK(cudaMemcpyAsync(d_cost, maps->cost, (size_t)B * W * H, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_origin, maps->origin, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_pose, robot_pose, (size_t)B * 24, cudaMemcpyHostToDevice, h->stream));
     h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * 40);
     CostmapArgs a{maps->size_x, maps->size_y, maps->resolution, behind_robot_dist, d_cost, d_origin, d_pose};
-    const dim3 grid((unsigned)((W + 127) / 128), (unsigned)B);
+    const dim3 grid_mark((unsigned)((W / 4 + 1 + 63) / 64), (unsigned)B), grid_emit((unsigned)((W + 127) / 128), (unsigned)B);
     cudaEvent_t t0, t1;
     CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, h->stream));
-    costmap_scan_kernel<false><<<grid, 128, 0, h->stream>>>(a, B, d_colcount, nullptr, max_per_instance, nullptr, nullptr);
+    if (W % 4 == 0) costmap_mark_kernel<true><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
+    else costmap_mark_kernel<false><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
     costmap_offsets_kernel<<<B, 256, 0, h->stream>>>(maps->size_x, B, d_colcount, d_colstart, max_per_instance, d_count, d_found);
-    costmap_scan_kernel<true><<<grid, 128, 0, h->stream>>>(a, B, nullptr, d_colstart, max_per_instance, d_params, d_type);
+    costmap_emit_kernel<<<grid_emit, 128, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colstart, max_per_instance, d_params, d_type);
     CK(cudaGetLastError());
     CK(cudaEventRecord(t1, h->stream));
     h->stats.launches_total += 3;

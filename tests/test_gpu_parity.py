@@ -531,6 +531,25 @@ def test_midpoint_differences(cuda_lib, orc, base):
     s.close()
 
 
+@pytest.mark.parametrize("W,H", [(203, 97), (64, 33), (5, 2), (130, 300)])
+def test_costmap_obstacles_odd_sizes(cuda_lib, orc, W, H):
+    """map widths that are not a multiple of four (byte path of the marking kernel), heights around the 32-row mask words"""
+    from test_oracle_functions import _random_costmap
+    rng = np.random.default_rng(W + 7 * H)
+    B, res = 6, 0.1
+    cost = np.stack([_random_costmap(rng, W, H, 0.03) for _ in range(B)])
+    origin = rng.uniform(-3, 3, (B, 2))
+    pose = np.concatenate([origin + 0.5 * res * np.array([W, H]) + rng.uniform(-1, 1, (B, 2)), rng.uniform(-np.pi, np.pi, (B, 1))], axis=1)
+    s = _solver(configs.cfg2(), 1)
+    for M in (16, 4096):
+        (count, typ, par), found = s.costmap_obstacles(cost, origin, res, pose, 0.5, M)
+        for b in range(B):
+            xy, f = orc.costmap_obstacles(cost[b], origin[b], res, pose[b], 0.5, M)
+            assert found[b] == f and count[b] == min(f, M)
+            np.testing.assert_allclose(par[b, :count[b], :2], xy, atol=1e-12)
+    s.close()
+
+
 def test_costmap_obstacles_match_oracle_and_feed_the_solver(cuda_lib, orc):
     """mpcb200_costmap_obstacles (updateObstacleContainerWithCostmap for a batch of robots) against the oracle's loops: same
     cells, same order, same cut; the lists then go straight into step() as its obstacles."""
