@@ -893,56 +893,58 @@ __device__ __forceinline__ bool word_has_lethal(unsigned w)
     return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u;
 }
 template <bool VEC>   // VEC: size_x % 4 == 0, every row of every map starts 4-byte aligned
-__global__ void costmap_mark_kernel(CostmapArgs a, int B, int nrb, int Wp, unsigned* mask /*[B][nrb][Wp]*/)
+__global__ void costmap_mark_kernel(CostmapArgs a, int B, int nrb, int Wp, unsigned* mask /*[B][nrb][Wp]*/, int* colcount /*[B][size_x]*/)
 {
-    // thread = four adjacent columns x one block of 32 rows (eight loads in flight per thread, B * nrb * size_x/4 threads)
-    const int b = blockIdx.z, rb = blockIdx.y;
+    const int b = blockIdx.y;
     const int c0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (b >= B || c0 >= a.size_x) return;
     const unsigned char* map = a.cost + (size_t)b * a.size_x * a.size_y;
+    const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
+    const double px = a.pose[3 * b], py = a.pose[3 * b + 1];
+    double diry, dirx;
+    sincos(a.pose[3 * b + 2], &diry, &dirx);   // PoseSE2::orientationUnitVec
+    int cnt[4] = {0, 0, 0, 0};
     const int rows = a.size_y - 1;
-    unsigned m[4] = {0u, 0u, 0u, 0u};
-    bool have_pose = false;
-    double ox = 0, oy = 0, px = 0, py = 0, dirx = 0, diry = 0;
-#pragma unroll
-    for (int r0 = 0; r0 < 32; r0 += 8)
+    for (int rb = 0; rb < nrb; ++rb)
     {
-        unsigned w[8];
+        unsigned m[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r0 = 0; r0 < 32; r0 += 8)
         {
-            const int my = rb * 32 + r0 + r;
-            w[r] = 0u;
-            if (my < rows)
+            unsigned w[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
             {
-                const unsigned char* q = map + (size_t)my * a.size_x + c0;
-                if (VEC) w[r] = *reinterpret_cast<const unsigned*>(q);
-                else
-                    for (int i = 0; i < 4; ++i)
-                        if (c0 + i < a.size_x) w[r] |= (unsigned)q[i] << (8 * i);
+                const int my = rb * 32 + r0 + r;
+                w[r] = 0u;
+                if (my < rows)
+                {
+                    const unsigned char* q = map + (size_t)my * a.size_x + c0;
+                    if (VEC) w[r] = *reinterpret_cast<const unsigned*>(q);
+                    else
+                        for (int i = 0; i < 4; ++i)
+                            if (c0 + i < a.size_x) w[r] |= (unsigned)q[i] << (8 * i);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+            {
+                if (!word_has_lethal(w[r])) continue;
+                const int my = rb * 32 + r0 + r;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (((w[r] >> (8 * i)) & 0xFFu) == COSTMAP_LETHAL && c0 + i < a.size_x - 1 &&
+                        costmap_keep(a, c0 + i, my, ox, oy, px, py, dirx, diry))
+                        m[i] |= 1u << (r0 + r);
             }
         }
+        *reinterpret_cast<uint4*>(mask + ((size_t)b * nrb + rb) * Wp + c0) = make_uint4(m[0], m[1], m[2], m[3]);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-        {
-            if (!word_has_lethal(w[r])) continue;
-            if (!have_pose)
-            {
-                // robot data only when a LETHAL cell shows up (most threads never need it)
-                ox = a.origin[2 * b]; oy = a.origin[2 * b + 1];
-                px = a.pose[3 * b]; py = a.pose[3 * b + 1];
-                sincos(a.pose[3 * b + 2], &diry, &dirx);   // PoseSE2::orientationUnitVec
-                have_pose = true;
-            }
-            const int my = rb * 32 + r0 + r;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (((w[r] >> (8 * i)) & 0xFFu) == COSTMAP_LETHAL && c0 + i < a.size_x - 1 &&
-                    costmap_keep(a, c0 + i, my, ox, oy, px, py, dirx, diry))
-                    m[i] |= 1u << (r0 + r);
-        }
+        for (int i = 0; i < 4; ++i) cnt[i] += __popc(m[i]);
     }
-    *reinterpret_cast<uint4*>(mask + ((size_t)b * nrb + rb) * Wp + c0) = make_uint4(m[0], m[1], m[2], m[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (c0 + i < a.size_x) colcount[(size_t)b * a.size_x + c0 + i] = cnt[i];
 }
 __global__ void costmap_emit_kernel(CostmapArgs a, int B, int nrb, int Wp, const unsigned* mask, const int* colstart, int max_out,
                                     double* params /*[B][max_out][MPCB200_OBST_STRIDE]*/, int* type /*[B][max_out]*/)
@@ -967,9 +969,8 @@ __global__ void costmap_emit_kernel(CostmapArgs a, int B, int nrb, int Wp, const
         }
     }
 }
-// column counts from the masks + exclusive scan over the columns of one robot (one CTA per robot);
-// found = total, count = min(total, max_out)
-__global__ void costmap_offsets_kernel(int size_x, int B, int nrb, int Wp, const unsigned* mask, int* colstart, int max_out, int* count, int* found)
+// exclusive scan of the column counts of one robot (one CTA per robot); found = total, count = min(total, max_out)
+__global__ void costmap_offsets_kernel(int size_x, int B, const int* colcount, int* colstart, int max_out, int* count, int* found)
 {
     const int b = blockIdx.x;
     __shared__ int carry;
@@ -980,9 +981,7 @@ __global__ void costmap_offsets_kernel(int size_x, int B, int nrb, int Wp, const
     for (int base = 0; base < size_x; base += blockDim.x)
     {
         const int i = base + threadIdx.x;
-        int v = 0;
-        if (i < size_x)
-            for (int rb = 0; rb < nrb; ++rb) v += __popc(mask[((size_t)b * nrb + rb) * Wp + i]);
+        const int v = i < size_x ? colcount[(size_t)b * size_x + i] : 0;
         int incl = v;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
         if (lane == 31) warp_tot[wid] = incl;
@@ -1868,7 +1867,6 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
                                          int max_per_instance, int* count, int* found, int* type, double* params)
 {
     if (!h) return MPCB200_E_INVALID;
-    if (B > 65535) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: at most 65535 robots per call");
     if (B < 1 || !maps || !maps->cost || !maps->origin || !robot_pose || !count || !type || !params || max_per_instance < 1)
         return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: B >= 1, maps, poses and output arrays are required");
     if (maps->size_x < 2 || maps->size_y < 2 || !(maps->resolution > 0)) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: maps of at least 2 x 2 cells with a positive resolution");
@@ -1892,7 +1890,7 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     double* d_params = (double*)p; p += (size_t)B * M * MPCB200_OBST_STRIDE * 8;
     double* d_origin = (double*)p; p += (size_t)B * 2 * 8;
     double* d_pose = (double*)p; p += (size_t)B * 3 * 8;
-    p += (size_t)B * W * 4;   // (spare)
+    int* d_colcount = (int*)p; p += (size_t)B * W * 4;
     int* d_colstart = (int*)p; p += (size_t)B * W * 4;
     int* d_count = (int*)p; p += (size_t)B * 4;
     int* d_found = (int*)p; p += (size_t)B * 4;
@@ -1903,13 +1901,13 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     CK(cudaMemcpyAsync(d_pose, robot_pose, (size_t)B * 24, cudaMemcpyHostToDevice, h->stream));
     h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * 40);
     CostmapArgs a{maps->size_x, maps->size_y, maps->resolution, behind_robot_dist, d_cost, d_origin, d_pose};
-    const dim3 grid_mark((unsigned)((W / 4 + 1 + 63) / 64), (unsigned)nrb, (unsigned)B), grid_emit((unsigned)((W + 127) / 128), (unsigned)B);
+    const dim3 grid_mark((unsigned)((W / 4 + 1 + 63) / 64), (unsigned)B), grid_emit((unsigned)((W + 127) / 128), (unsigned)B);
     cudaEvent_t t0, t1;
     CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
     CK(cudaEventRecord(t0, h->stream));
-    if (W % 4 == 0) costmap_mark_kernel<true><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask);
-    else costmap_mark_kernel<false><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask);
-    costmap_offsets_kernel<<<B, 256, 0, h->stream>>>(maps->size_x, B, nrb, Wp, d_mask, d_colstart, max_per_instance, d_count, d_found);
+    if (W % 4 == 0) costmap_mark_kernel<true><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
+    else costmap_mark_kernel<false><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
+    costmap_offsets_kernel<<<B, 256, 0, h->stream>>>(maps->size_x, B, d_colcount, d_colstart, max_per_instance, d_count, d_found);
     costmap_emit_kernel<<<grid_emit, 128, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colstart, max_per_instance, d_params, d_type);
     CK(cudaGetLastError());
     CK(cudaEventRecord(t1, h->stream));
