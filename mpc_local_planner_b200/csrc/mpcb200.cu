@@ -1867,6 +1867,7 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
                                          int max_per_instance, int* count, int* found, int* type, double* params)
 {
     if (!h) return MPCB200_E_INVALID;
+    if (B > 65535) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: at most 65535 robots per call");
     if (B < 1 || !maps || !maps->cost || !maps->origin || !robot_pose || !count || !type || !params || max_per_instance < 1)
         return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: B >= 1, maps, poses and output arrays are required");
     if (maps->size_x < 2 || maps->size_y < 2 || !(maps->resolution > 0)) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: maps of at least 2 x 2 cells with a positive resolution");
