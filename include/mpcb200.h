@@ -322,11 +322,7 @@ int mpcb200_flush_l2(mpcb200_handle* h);
 #define MPCB200_SC_GLDT 17   /* dL/d(dt) */
 #define MPCB200_SC_NBT 18    /* line-search backtracks so far */
 #define MPCB200_SC_COLD 19   /* 1 until the instance has been solved once (cold start pending) */
-#define MPCB200_SC_KKT_OK0 22 /* speculative KKT (small batches): attempt 0 / 1 of the iteration solved in parallel ... */
-#define MPCB200_SC_KKT_OK1 23
-#define MPCB200_SC_DELTA1 24  /* ... regularisation and d(dt) of attempt 1 (attempt 0 uses SC_DELTA / SC_DDT) */
-#define MPCB200_SC_DDT1 25
-#define MPCB200_SC_NEW 26     /* streaming: the slot was just refilled, init / associate pending */
+#define MPCB200_SC_VALID 22   /* 1 = the inputs of the instance are finite (else status INVALID_INPUT, never iterated) */
 #define MPCB200_SC_DEFER 21  /* 1 = the KKT phase spent its factorisation budget: null step, regularisation resumes next iteration */
 #define MPCB200_SC_TINY 20   /* consecutive iterations with a step length below 1e-8 (2 => the instance is given up) */
 
@@ -344,18 +340,17 @@ int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const double* src);
 int mpcb200_run_phase(mpcb200_handle* h, int phase, int B);
 /* Launch `phase` reps times back to back and report the mean device time per launch (CUDA events on the solver stream). */
 int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps, int flush_l2, double* ms_per_launch);
-/* Which phases a solve brackets with CUDA events for mpcb200_stats.ms (bit p = phase p).  Default: the KKT phase only
-   (1 << MPCB200_PHASE_KKT) -- every bracket costs a few microseconds of stream time; 0x1f times all of them. */
+/* Phased solve mode only: which phases a solve brackets with CUDA events for mpcb200_stats.ms (bit p = phase p).  Default: the
+   KKT phase only (1 << MPCB200_PHASE_KKT) -- every bracket costs a few microseconds of stream time; 0x1f times all of them.
+   (The fused solve kernel counts SM cycles per phase itself: mpcb200_stats.ms is then the mean time a CTA spent in the phase.) */
 int mpcb200_set_timing(mpcb200_handle* h, unsigned phase_mask);
 /* Run all work of this handle on the caller's CUDA stream (a cudaStream_t; NULL restores the handle's own stream), e.g. the
    stream the NCCL all-gather of the optimal controls is enqueued on.  The previous stream is drained first. */
 int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
-/* Execution options (never change results).  MPCB200_OPT_KKT_ATTEMPTS: how the (at most two) regularisation attempts of
-   an IPM iteration are run -- 0 = automatic (side by side when the batch leaves SMs idle, i.e. 2*ceil(B/32) <= #SMs),
-   1 = one after the other inside the KKT kernel, 2 = always side by side.
-   MPCB200_OPT_STREAM_REFILL_EVERY: IPM iterations between two refills of the pool of mpcb200_solve_stream (1..16). */
-#define MPCB200_OPT_KKT_ATTEMPTS 1
-#define MPCB200_OPT_STREAM_REFILL_EVERY 2
+/* Execution options (never change results).  MPCB200_OPT_SOLVE_MODE: 0 (default) = one persistent kernel per solve -- a CTA owns
+   an instance from the initial guess to convergence, all phases in shared memory; 1 = one kernel launch per phase, the host
+   queues the iterations (the same device functions; per-phase CUDA-event timing, the KKT kernel measurable on its own). */
+#define MPCB200_OPT_SOLVE_MODE 3
 int mpcb200_set_option(mpcb200_handle* h, int option, int value);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */
@@ -364,7 +359,7 @@ typedef struct mpcb200_stats {
     double ms[MPCB200_NUM_PHASES];
     long long launches_total;
     long long h2d_bytes, d2h_bytes;
-    long long kkt_instances; /* number of (instance, launch) pairs the KKT kernel actually factorised */
+    long long kkt_instances; /* number of (instance, iteration) pairs the KKT phase actually factorised */
     long long kkt_sweeps;    /* backward sweeps incl. inertia-correction refactorisations */
 } mpcb200_stats;
 int mpcb200_stats_get(const mpcb200_handle* h, mpcb200_stats* out);

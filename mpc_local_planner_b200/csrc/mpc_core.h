@@ -29,8 +29,9 @@ struct WsLayout
 {
     int N, K, RS, M, V;      // grid points, obstacle rows per stage, row slots, max obstacles, max via-points
     int64_t stride;          // doubles per instance (multiple of 16 -> 128-byte aligned blocks)
-    int oX, oU, oNU, oS, oLAM, oSTEP, oSTEP2, oOBS, oSCAL, oDS, oDLAM, oVPST;
+    int oX, oU, oNU, oS, oLAM, oSTEP, oOBS, oSCAL, oDS, oVPST, oSTATE_END;
     int oR0, oOG;            // row residuals at the current point (RS x N), obstacle row value + gradient (4K x N)
+    int oKKT, oMM;           // condensed KKT stage records [k][RSTR]; stage matrices + gains of the KKT sweep [k][MSTR]
     int oIN;                 // x0(3) xf(3) u_prev(2) n_obst n_vp has_xinit reinit
     int oOBST, oOTYPE, oVP, oXINIT;
 };

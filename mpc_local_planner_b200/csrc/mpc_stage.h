@@ -19,11 +19,10 @@
 #define ANU(c_, k_) W[L.oNU + (c_) * N + (k_)]
 #define AS(c_, k_) W[L.oS + (c_) * N + (k_)]
 #define ALAM(c_, k_) W[L.oLAM + (c_) * N + (k_)]
-#define AKKT(c_, k_) Kb[((size_t)(k_) * KW + (c_)) * 32]  /* 32-instance interleaved tile; Kb = tile base + slot of this instance */
+#define AKKT(c_, k_) W[L.oKKT + (k_) * RSTR + (c_)]  /* stage records [k][RSTR] (odd stride: lane-per-stage accesses without bank conflicts) */
 #define ASTEP(c_, k_) W[L.oSTEP + (c_) * N + (k_)]
 #define AOBS(c_, k_) W[L.oOBS + (c_) * N + (k_)]
 #define ADS(c_, k_) W[L.oDS + (c_) * N + (k_)]
-#define ADLAM(c_, k_) W[L.oDLAM + (c_) * N + (k_)]
 // W addresses the instance image: the leading part of the workspace (scalars, inputs, iterate, steps, obstacles), which the
 // eval / line-search kernels stage in shared memory; G always addresses the instance's workspace in global memory (fields
 // outside the image, and every result that must outlive the kernel).  Host emulator and the init kernels pass W == G.
@@ -141,7 +140,7 @@ HD inline void lin_rows_component(const Cfg& c, const WsLayout& L, const double*
 // coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
 // LINES = false compiles the rarely used obstacle kinds out (line obstacles, moving obstacles): see footprint_distance_sc
 template <bool LINES = true>
-HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G, double* Kb, double uprev_dt, int k, EvalAcc& acc)
+HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, EvalAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT);
@@ -496,7 +495,7 @@ HD inline double eval_finish(const Cfg& c, const WsLayout& L, double* W, const E
     *finished = fin;
     return mu;
 }
-HD inline void eval_finalize_stage(const WsLayout& L, double* W, double* Kb, int k, double mu)
+HD inline void eval_finalize_stage(const WsLayout& L, double* W, int k, double mu)
 {
     const int N = L.N;
 #pragma unroll
@@ -520,7 +519,7 @@ HD inline void lsacc_init(LsAcc& a) { a.a_p = 1.0; a.a_d = 1.0; a.dphi_bar = a.c
 #else
 #define HIST_ADD(p_) (++*(p_))
 #endif
-HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double* G, const double* Kb, double uprev_dt, int k, LsAcc& acc, int* hist)
+HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, LsAcc& acc, int* hist)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT), mu = ASC(MPCB200_SC_MU), ddt = ASC(MPCB200_SC_DDT);
@@ -544,7 +543,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         }
         else if (sl < 8)
         {
-            if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
+            if (!lin_row_active(c, N, k, sl, uprev_dt)) { ADS(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
             const int i = (sl < 4) ? (sl >> 1) : ((sl - 4) >> 1);
             const double uk = (k <= N - 2) ? AU(i, k) : 0.0;
             const double um = (sl >= 4) ? ((k >= 1) ? AU(i, k - 1) : AIN(IN_UPREV + i)) : 0.0;
@@ -557,7 +556,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         {
             const int j = sl - 8;
             const int oi = (k >= 1 && k <= N - 2) ? (int)AOBS(j, k) : -1;
-            if (oi < 0) { ADS(sl, k) = 0.0; ADLAM(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
+            if (oi < 0) { ADS(sl, k) = 0.0; GR0(sl, k) = 0.0; continue; }
             g = GOG(4 * j + 0, k);
             gdz = GOG(4 * j + 1, k) * dx[0] + GOG(4 * j + 2, k) * dx[1] + GOG(4 * j + 3, k) * dx[2];
             const double* op = W + L.oOBST + oi * MPCB200_OBST_STRIDE;
@@ -569,7 +568,6 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         const double ds = -r0 - gdz;
         const double dl = mu * rs - lam - (lam * rs) * ds;
         ADS(sl, k) = ds;
-        ADLAM(sl, k) = dl;
         GR0(sl, k) = r0;
         HIST_ADD(hist + CLIP_BINS);
         if (ds < 0 && -tau * s / ds < 1.0) HIST_ADD(hist + clip_bin(-tau * s / ds));
@@ -797,31 +795,30 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
     rowprod_flush(rp, acc.blog);
 }
 
-// accept the step: z, s, lambda, nu of stage k
-template <bool LINES = true>
+// midpoint differences: the sweep solved the transformed, condensed system (eval_stage): nu+ = (I + e_th a') nu~ + e_th (q' dw_k).
+// Rewrites STEP(7, k) in place; reads the heading of stage k+1, so it runs for all stages BEFORE any stage is updated.
+HD inline void ls_stage_midpoint_fix(const Cfg& c, const WsLayout& L, double* W, int k)
+{
+    const int N = L.N;
+    if (k > N - 2) return;
+    const double nu[3] = {ANU(0, k), ANU(1, k), ANU(2, k)};
+    const double dt = ASC(MPCB200_SC_DT);
+    double f[3], J[9], Hc[6];
+    dynamics_derivs(c, AX(2, k) + 0.5 * normalize_theta(AX(2, k + 1) - AX(2, k)), AU(0, k), AU(1, k), nu, f, J, Hc, nullptr);
+    double n2 = ASTEP(7, k);
+    n2 += 0.5 * dt * (J[0] * ASTEP(5, k) + J[3] * ASTEP(6, k));
+    n2 += 0.25 * dt * Hc[0] * ASTEP(2, k) + 0.5 * dt * (Hc[1] * ASTEP(3, k) + Hc[2] * ASTEP(4, k));
+    ASTEP(7, k) = n2;
+}
+
+// accept the step: z, s, lambda, nu of stage k (reads and writes stage k only: safe to run lane-parallel in place)
 HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W, double* G, double uprev_dt, int k, double alpha, double a_dual)
 {
     const int N = L.N, K = L.K;
     const double mu = ASC(MPCB200_SC_MU);
-    // NOTE: reads STEP of stage k only (midpoint differences: also the heading of stage k+1, before anything of stage k is
-    // written, so that the in-place serial emulation sees the old iterate) -> safe to run lane-parallel after all trial
-    // evaluations are done
     const double d0 = ASTEP(0, k), d1 = ASTEP(1, k), d2 = ASTEP(2, k);
     double nup[3] = {0.0, 0.0, 0.0};
-    if (k <= N - 2)
-    {
-        nup[0] = ASTEP(5, k); nup[1] = ASTEP(6, k); nup[2] = ASTEP(7, k);
-        if (LINES && is_midpoint(c))
-        {
-            // the sweep solved the transformed, condensed system (eval_stage): nu+ = (I + e_th a') nu~ + e_th (q' dw_k)
-            const double nu[3] = {ANU(0, k), ANU(1, k), ANU(2, k)};
-            const double dt = ASC(MPCB200_SC_DT);
-            double f[3], J[9], Hc[6];
-            dynamics_derivs(c, AX(2, k) + 0.5 * normalize_theta(AX(2, k + 1) - AX(2, k)), AU(0, k), AU(1, k), nu, f, J, Hc, nullptr);
-            nup[2] += 0.5 * dt * (J[0] * nup[0] + J[3] * nup[1]);
-            nup[2] += 0.25 * dt * Hc[0] * d2 + 0.5 * dt * (Hc[1] * ASTEP(3, k) + Hc[2] * ASTEP(4, k));
-        }
-    }
+    if (k <= N - 2) { nup[0] = ASTEP(5, k); nup[1] = ASTEP(6, k); nup[2] = ASTEP(7, k); }
     GX(0, k) = AX(0, k) + alpha * d0; GX(1, k) = AX(1, k) + alpha * d1; GX(2, k) = AX(2, k) + alpha * d2;
     if (k <= N - 2)
     {
@@ -835,9 +832,12 @@ HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W,
         if (sl < 8) act = lin_row_active(c, N, k, sl, uprev_dt) || (sl == BALL_SLOT && k == N - 1 && ball_active(c));
         else act = (k >= 1 && k <= N - 2) && AOBS(sl - 8, k) >= 0.0;
         if (!act) continue;
-        double s = AS(sl, k) + alpha * ADS(sl, k);
-        if (s < CLIP_FLOOR * AS(sl, k)) s = CLIP_FLOOR * AS(sl, k);
-        double lam = ALAM(sl, k) + a_dual * ADLAM(sl, k);
+        const double s0 = AS(sl, k), ds = ADS(sl, k), lam0 = ALAM(sl, k);
+        const double rs = 1.0 / s0;
+        const double dl = mu * rs - lam0 - (lam0 * rs) * ds;   // multiplier step of the row (as in ls_stage_steps)
+        double s = s0 + alpha * ds;
+        if (s < CLIP_FLOOR * s0) s = CLIP_FLOOR * s0;
+        double lam = lam0 + a_dual * dl;
         const double lo = mu / (KAPPA_SIGMA * s), hi = KAPPA_SIGMA * mu / s;
         if (lam < lo) lam = lo;
         if (lam > hi) lam = hi;
@@ -850,14 +850,14 @@ HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W,
 // INITIALISATION / ASSOCIATION
 // ------------------------------------------------------------------------------------------------------
 // cold initial guess of stage k
-HD inline void init_cold_stage(const Cfg& c, const WsLayout& L, double* W, int k)
+HD inline void init_cold_stage(const Cfg& c, const WsLayout& L, double* W, int k, const double* xinit /* [N][3] initial plan samples of this instance, read when IN_HASXINIT */)
 {
     const int N = L.N;
     const double* x0 = &AIN(IN_X0);
     const double* xf = &AIN(IN_XF);
     if (k == 0) { for (int i = 0; i < 3; ++i) AX(i, k) = x0[i]; }
     else if (k == N - 1) { for (int i = 0; i < 3; ++i) AX(i, k) = xf[i]; }
-    else if (AIN(IN_HASXINIT) != 0.0) { for (int i = 0; i < 3; ++i) AX(i, k) = W[L.oXINIT + 3 * k + i]; }
+    else if (AIN(IN_HASXINIT) != 0.0) { for (int i = 0; i < 3; ++i) AX(i, k) = xinit[3 * k + i]; }
     else
     {
         const double frac = (double)k / (double)(N - 1);

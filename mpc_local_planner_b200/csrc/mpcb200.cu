@@ -1,12 +1,18 @@
 // mpcb200.cu -- sm_100a kernels + C-ABI host side of the batched receding-horizon OCP solver (include/mpcb200.h).
 //
-// Thread mapping.  The stage-parallel phases put one lane on one horizon stage: EVAL and LINESEARCH run one CTA of
-// ceil(N/32) warps per instance and read the instance image (the leading, contiguous part of the instance's
-// workspace block, mpc_layout.h) from shared memory, where a bulk-async copy staged it; INIT and ASSOCIATE (once per
-// solve) run one warp per instance straight on global memory.  Arrays are [component][stage] (stage fastest).
-// In the sequential KKT phase ONE LANE owns one instance (mpc_riccati_lane.h): the condensed KKT stage records and
-// the Riccati gains live in 32-instance interleaved tiles, a warp sweeps 32 instances in lock-step, and each stage of
-// a tile is one contiguous block that a bulk-async copy streams through a shared-memory ring.
+// Execution model.  ONE CTA OWNS ONE INSTANCE FOR ITS WHOLE SOLVE: solve_fused_kernel is a persistent kernel whose CTAs take
+// instances from a queue (atomic counter), keep the instance's resident prefix (mpc_layout.h: iterate, slacks, multipliers,
+// KKT stage records, KKT stage matrices, obstacles -- 50-70 KB) in shared memory, and run initial guess, association and the
+// interior-point iterations (eval -> KKT -> line search, mpc_device.cuh) back to back until the instance converges or gives
+// up; then the results are written and the CTA takes the next instance.  No launch chain, no HBM round trip of records or
+// gains between the phases, and no instance waits for the slowest one of its batch.  Thread mapping inside the CTA: the
+// stage-parallel phases (eval, line search) put one lane on one horizon stage (ceil(N/32) warps); the KKT phase is the
+// warp-cooperative Riccati sweep of mpc_riccati_warp.h on warp 0 (lanes = entries of the stage matrix, one barrier per stage).
+//
+// The same device functions are exposed phase by phase (mpcb200_run_phase / mpcb200_time_phase, and the "phased" solve mode)
+// through phase_kernel (stages the prefix, runs one phase, writes it back) and kkt_warp_kernel (one warp per instance:
+// bulk-async copy of the stage records into shared memory, sweep, Newton step back to HBM) -- the kernel the HBM roofline of
+// the KKT factorisation is measured on.
 //
 // This file is the ONLY implementation of the hot path: there is no CPU fallback.  Every entry point fails with
 // MPCB200_E_NODEVICE / MPCB200_E_CUDA when no CUDA device is usable.
@@ -18,812 +24,247 @@
 #include <string>
 #include <vector>
 
-#include "mpc_core.h"
-#include "mpc_riccati_lane.h"
-#include "mpc_stage.h"
-#include "mpc_layout.h"
+#include "mpc_device.cuh"
+#include "mpc_costmap.cuh"
 
-#define FULLMASK 0xffffffffu
 #define WARPS_PER_CTA 4
-#define REGROUP_EVERY 4    // IPM iterations between two re-assignments of instances to KKT tile slots
-#define MAX_IMG_SMEM (227 * 1024 - 2048)  // dynamic shared memory the eval / line-search kernels may request
-#define MAX_GROUP_WARPS 4   // warps of the CTA that owns one instance in the eval / line-search kernels (lane per stage)
+#define MAX_IMG_SMEM (227 * 1024 - 2048)  // dynamic shared memory a CTA may request
+#define IMG_HEAD 16                        // bytes in front of the resident prefix in dynamic shared memory (mbarrier)
 
-// ---- warp reductions (fp64 via two 32-bit shuffles each) ------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULLMASK, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_min(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULLMASK, v, o));
-    return v;
-}
+// device-side counters of a handle (unsigned long long each)
+#define CNT_KKT_INST 0     // (instance, iteration) pairs the KKT phase factorised
+#define CNT_KKT_SWEEPS 1   // backward sweeps incl. inertia-correction refactorisations
+#define CNT_CYC 2          // +phase: SM cycles CTAs spent in each phase of the fused kernel (thread 0's clock64)
+#define CNT_CYC_TOTAL 7    // SM cycles CTAs spent on instances in the fused kernel
+#define CNT_INST 8         // instances solved by the fused kernel
+#define CNT_WORDS 16
 
-struct InputPtrs
-{
-    const double* x0; const double* xf; const double* u_prev;      // [B][3],[B][3],[B][2]
-    const int* obst_count; const int* obst_type; const double* obst_params; int obst_max;
-    const int* vp_count; const double* vp_poses; int vp_max;
-    const double* x_init;                                          // [B][N][3] or null
-    const unsigned char* reinit;                                   // [B] or null
-};
-
-// ---- scatter the compact input arrays into an instance block (inputs of instance `src` into the block W) -------
-__device__ __forceinline__ void scatter_one(const WsLayout& L, double* W, const InputPtrs& in, int64_t src, int lane)
-{
-    const int N = L.N;
-    if (lane < 3) { AIN(IN_X0 + lane) = in.x0[src * 3 + lane]; AIN(IN_XF + lane) = in.xf[src * 3 + lane]; }
-    if (lane < 2) AIN(IN_UPREV + lane) = in.u_prev ? in.u_prev[src * 2 + lane] : 0.0;
-    int nob = 0, nvp = 0;
-    if (in.obst_count) nob = min(in.obst_count[src], min(in.obst_max, L.M));
-    if (in.vp_count) nvp = min(in.vp_count[src], min(in.vp_max, L.V));
-    if (lane == 0)
-    {
-        AIN(IN_NOBST) = (double)nob; AIN(IN_NVP) = (double)nvp;
-        AIN(IN_HASXINIT) = in.x_init ? 1.0 : 0.0;
-        AIN(IN_REINIT) = (in.reinit && in.reinit[src]) ? 1.0 : 0.0;
-    }
-    for (int i = lane; i < nob * MPCB200_OBST_STRIDE; i += 32)
-        W[L.oOBST + i] = in.obst_params[src * in.obst_max * MPCB200_OBST_STRIDE + i];
-    for (int i = lane; i < nob; i += 32) W[L.oOTYPE + i] = (double)in.obst_type[src * in.obst_max + i];
-    for (int i = lane; i < nvp * 3; i += 32) W[L.oVP + i] = in.vp_poses[src * in.vp_max * 3 + i];
-    if (in.x_init)
-        for (int i = lane; i < 3 * N; i += 32) W[L.oXINIT + i] = in.x_init[src * 3 * N + i];
-}
-
+// ---- kernel: inputs of a batch into the instance blocks (phased path; the fused kernel scatters into shared memory itself) ----
 __global__ void scatter_inputs_kernel(WsLayout L, double* ws, int B, InputPtrs in)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
-    scatter_one(L, ws + (int64_t)warp * L.stride, in, warp, lane);
-}
-
-// ---- kernel: PHASE_INIT -- cold initial guess or warm-start shift ------------------------------------------
-__global__ void init_kernel(Cfg c, WsLayout L, double* ws, int B, int force_cold, int only_new)
-{
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
-    const int N = L.N;
-    if (only_new && ASC(MPCB200_SC_NEW) == 0.0) return;  // streaming: only the slots that were just refilled
-    const bool cold = force_cold || ASC(MPCB200_SC_COLD) != 0.0 || AIN(IN_REINIT) != 0.0;
-    __syncwarp();
-    if (cold)
-    {
-        for (int k = lane; k < N; k += 32) init_cold_stage(c, L, W, k);
-        __syncwarp();
-        double nx, ny;
-        if (bump_enabled(c, L, W) && bump_normal(L, W, &nx, &ny))
-        {
-            // choice of the cold initial guess: candidates one after the other, their stages spread over the lanes
-            double best = 1e300, best_a = 0.0;
-            for (int m = -c.initial_guess_bumps; m <= c.initial_guess_bumps; ++m)
-            {
-                const double A = BUMP_STEP * (double)m;
-                double v = 0.0;
-                for (int k = lane; k < N; k += 32) v += bump_stage_violation(c, L, W, k, A, nx, ny);
-                const double score = 1e-3 * fabs(A) + warp_sum(v);
-                if (bump_better(score, best)) { best = score; best_a = A; }
-            }
-            for (int k = lane; k < N; k += 32)
-                if (k >= 1 && k <= N - 2) { const double o = bump_offset(N, k, best_a); AX(0, k) += o * nx; AX(1, k) += o * ny; }
-            __syncwarp();
-            if (bump_align_headings(c, best_a))
-                for (int k = lane; k < N; k += 32)
-                    if (k >= 1 && k <= N - 2) AX(2, k) = bump_heading(L, W, k);
-        }
-        if (lane == 0) { ASC(MPCB200_SC_DT) = c.dt_ref; ASC(MPCB200_SC_COLD) = 2.0; /* 2: cold init done, repair pending */ }
-    }
-    else
-    {
-        if (lane == 0)
-        {
-            if (c.warm_start && !c.variable_dt) warm_shift_serial(c, L, W);
-            else
-            {
-                for (int i = 0; i < 3; ++i) AX(i, 0) = AIN(IN_X0 + i);
-                for (int i = 0; i < 3; ++i)
-                    if (c.xf_fixed[i]) AX(i, N - 1) = AIN(IN_XF + i);
-            }
-            ASC(MPCB200_SC_COLD) = 0.0;
-        }
-    }
+    const bool ok = scatter_one(L, W, in, warp, lane, W + L.oXINIT);
+    if (lane == 0) ASC(MPCB200_SC_VALID) = ok ? 1.0 : 0.0;
 }
 
-// ---- kernel: PHASE_ASSOCIATE -- obstacle / via-point association, initial-guess repair, dual initialisation ----
-__global__ void associate_kernel(Cfg c, WsLayout L, double* ws, int B, double uprev_dt, int first_outer, int only_new)
+// stage [0, words) of an instance block in shared memory (one bulk-async copy) / write [0, words) back
+__device__ __forceinline__ void stage_in(double* W, const double* Gp, int words, uint32_t bar, uint32_t parity, int tid)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    double* W = ws + (int64_t)warp * L.stride;
-    const int N = L.N;
-    if (only_new && ASC(MPCB200_SC_NEW) == 0.0) return;  // streaming: only the slots that were just refilled
-    const bool repair = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
-    __syncwarp();
-    for (int k = lane; k < N; k += 32) associate_stage(c, L, W, k);
-    // via-points: MinTimeViaPointsCost::update with findClosestPose (argmin over the grid, first minimum wins)
-    if (has_viapoints(c))
-    {
-        const int nvp = (int)AIN(IN_NVP);
-        int start_idx = 0;
-        for (int j = 0; j < nvp && j < L.V; ++j)
-        {
-            const double vx = W[L.oVP + 3 * j], vy = W[L.oVP + 3 * j + 1];
-            double best = 1e300; int bidx = -1;
-            for (int i = start_idx + lane; i < N - 1; i += 32)
-            {
-                const double dx = AX(0, i) - vx, dy = AX(1, i) - vy;
-                const double d = sqrt(dx * dx + dy * dy);
-                if (d < best) { best = d; bidx = i; }
-            }
-            // warp argmin with smallest index on ties
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                const double ob = __shfl_xor_sync(FULLMASK, best, o);
-                const int oi = __shfl_xor_sync(FULLMASK, bidx, o);
-                if (ob < best || (ob == best && oi >= 0 && (bidx < 0 || oi < bidx))) { best = ob; bidx = oi; }
-            }
-            {
-                const double dx = AX(0, N - 1) - vx, dy = AX(1, N - 1) - vy;
-                const double d = sqrt(dx * dx + dy * dy);
-                if (d < best) { best = d; bidx = N - 1; }
-            }
-            int idx = bidx;
-            if (c.vp_ordered) start_idx = idx + 2;
-            if (idx > N - 2) idx = N - 2;
-            if (idx < 1) idx = c.vp_ordered ? 1 : -1;
-            if (lane == 0) W[L.oVPST + j] = (double)idx;
-        }
-        for (int j = nvp + lane; j < L.V; j += 32) W[L.oVPST + j] = -1.0;
-    }
-    __syncwarp();
-    if (repair)
-    {
-        for (int k = lane; k < N; k += 32) project_stage(c, L, W, k);
-        __syncwarp();
-        {
-            // step 2 of the repair: stages in order, the lateral candidates of a pinched stage spread over the lanes
-            double nx, ny;
-            lateral_normal(L, W, &nx, &ny);
-            for (int k = 1; k <= N - 2; ++k)
-            {
-                if (!lateral_needed(L, W, k)) continue;  // warp-uniform
-                const double o_prev = lateral_offset(L, W, k - 1, nx, ny);
-                double best = 1e300;
-                int best_m = 0;
-                for (int m = -LAT_MAX_STEPS + lane; m <= LAT_MAX_STEPS; m += 32)
-                {
-                    const double cost = lateral_candidate(c, L, W, k, m, o_prev, nx, ny);
-                    if (cost < best) { best = cost; best_m = m; }
-                }
-                for (int o = 16; o > 0; o >>= 1)
-                {
-                    const double oc = __shfl_xor_sync(FULLMASK, best, o);
-                    const int om = __shfl_xor_sync(FULLMASK, best_m, o);
-                    if (oc < best || (oc == best && om < best_m)) { best = oc; best_m = om; }
-                }
-                if (lane == 0) lateral_apply(L, W, k, best_m, best < 1e299, nx, ny);
-                __syncwarp();
-            }
-        }
-        for (int k = lane; k < N; k += 32) init_controls_stage(c, L, W, k);
-        __syncwarp();
-        if (lane == 0) clip_rates_serial(c, L, W, uprev_dt);
-        __syncwarp();
-    }
-    double mu = c.mu_init;
-    if (!(mu > 0.0))
-    {
-        double obj = 0.0, rows = 0.0;
-        for (int k = lane; k < N; k += 32) auto_mu_stage(c, L, W, uprev_dt, k, &obj, &rows);
-        mu = auto_mu(warp_sum(obj), warp_sum(rows));
-    }
-    for (int k = lane; k < N; k += 32) init_duals_stage(c, L, W, uprev_dt, k, mu);
-    __syncwarp();
-    if (lane == 0)
-    {
-        ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
-        ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
-        ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0; ASC(MPCB200_SC_DEFER) = 0.0;
-        if (repair) ASC(MPCB200_SC_COLD) = 0.0;
-        if (only_new)
-        {
-            // streaming: this kernel runs beside the iteration kernels of the other slots; the slot stays parked (status >= 0,
-            // never -1 in between) until the next refill kernel, which runs after this one on the main stream, activates it
-            ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_INVALID_INPUT;
-            ASC(MPCB200_SC_NEW) = 2.0;
-        }
-        else { ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NEW) = 0.0; }
-    }
-}
-
-// ---- kernel: regroup -- assign tile slots so that instances in the same state share tiles ------------------------------
-// key 0: active, last factorisation needed no regularisation; key 1: active, regularised last time (will sweep more
-// than once); key 2: finished.  The lane-per-instance KKT kernel pays max-over-lanes per warp, so homogeneous tiles
-// remove most of the divergence (and tiles of finished instances exit immediately).  Results do not depend on the slot.
-__global__ void __launch_bounds__(1024) regroup_kernel(WsLayout L, const double* ws, int B, int* slot_of, int* inst_of_slot, int nslots)
-{
-    __shared__ int wcount[3][32];   // per-warp counts of the current chunk -> exclusive scan
-    __shared__ int chunk_total[3];
-    __shared__ int running[3];      // next free slot of each key class
-    __shared__ int total[3];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid < 3) total[tid] = 0;
-    __syncthreads();
-    // pass 0: class sizes
-    for (int c0 = 0; c0 < B; c0 += 1024)
-    {
-        const int b = c0 + tid;
-        int key = -1;
-        if (b < B)
-        {
-            const double* W = ws + (int64_t)b * L.stride;
-            key = ASC(MPCB200_SC_STATUS) >= 0.0 ? 2 : (ASC(MPCB200_SC_DELTA_LAST) > 0.0 ? 1 : 0);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-        {
-            const unsigned m = __ballot_sync(FULLMASK, key == k);
-            if (lane == 0 && m) atomicAdd(&total[k], __popc(m));
-        }
-    }
-    __syncthreads();
-    if (tid == 0) { running[0] = 0; running[1] = total[0]; running[2] = total[0] + total[1]; }
-    __syncthreads();
-    // pass 1: deterministic slot assignment (instance order preserved inside a class)
-    for (int c0 = 0; c0 < B; c0 += 1024)
-    {
-        const int b = c0 + tid;
-        int key = -1;
-        if (b < B)
-        {
-            const double* W = ws + (int64_t)b * L.stride;
-            key = ASC(MPCB200_SC_STATUS) >= 0.0 ? 2 : (ASC(MPCB200_SC_DELTA_LAST) > 0.0 ? 1 : 0);
-        }
-        int myoff = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-        {
-            const unsigned m = __ballot_sync(FULLMASK, key == k);
-            if (key == k) myoff = __popc(m & ((1u << lane) - 1u));
-            if (lane == 0) wcount[k][wid] = __popc(m);
-        }
-        __syncthreads();
-        if (wid < 3)
-        {
-            const int v = wcount[wid][lane];
-            int incl = v;
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
-            wcount[wid][lane] = incl - v;
-            if (lane == 31) chunk_total[wid] = incl;
-        }
-        __syncthreads();
-        if (key >= 0)
-        {
-            const int sidx = running[key] + wcount[key][wid] + myoff;
-            slot_of[b] = sidx;
-            inst_of_slot[sidx] = b;
-        }
-        __syncthreads();
-        if (tid < 3) running[tid] += chunk_total[tid];
-        __syncthreads();
-    }
-    for (int sidx = B + tid; sidx < nslots; sidx += 1024) inst_of_slot[sidx] = -1;
-}
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-
-// ---- instance image: the leading part of an instance's workspace staged in shared memory ---------------------------
-// The eval / line-search kernels walk long chains of dependent loads (row slots -> obstacle indices -> obstacle
-// parameters ...); out of L2 every link costs ~600 cycles.  One elected thread therefore pulls the image -- scalars,
-// inputs, iterate, (step,) obstacles: 20-30 KB, contiguous by construction of the layout (mpc_layout.h) -- into
-// shared memory with two or three bulk-async (TMA) copies, and the stage functions read it from there.
-// Layout of the dynamic shared memory: [0,8) mbarrier, [16, 16 + 8*img_words) image.
-struct ImageCopy { int step_src; };  // -1: no step (eval); else offset of the step to place at L.oSTEP (line search)
-__device__ __forceinline__ double* load_image(unsigned char* smem, const WsLayout& L, const double* Gp, int img_words, int step_src, int tid)
-{
-    double* img = reinterpret_cast<double*>(smem + 16);
-    const uint32_t bar = smem_addr(smem), dst = smem_addr(img);
     if (tid == 0)
+    {
+        fence_async();
+        mbar_expect_tx(bar, (uint32_t)words * 8u);
+        bulk_g2s(smem_addr(W), Gp, (uint32_t)words * 8u, bar);
+    }
+    mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void stage_out(double* Gp, const double* W, int words, int tid)
+{
+    __syncthreads();
+    if (tid == 0)
+    {
+        fence_async();   // the CTA's ordinary stores to shared memory before the async-proxy read
+        bulk_s2g(Gp, smem_addr(W), (uint32_t)words * 8u);
+        bulk_commit_wait();
+    }
+    __syncthreads();
+}
+
+// an instance whose inputs are not finite: reported, never iterated, starts cold next time
+__device__ __forceinline__ void mark_invalid(const WsLayout& L, double* W)
+{
+    ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_INVALID_INPUT;
+    ASC(MPCB200_SC_COLD) = 1.0; ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_ERR0) = 0.0; ASC(MPCB200_SC_DT) = 0.0;
+}
+
+// ---- kernel: ONE PHASE of the solve for every instance of a batch (kernel-level API and the phased solve mode) ----
+template <bool LINES>
+__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) phase_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, double* ws, int B, int phase,
+                                                                       double uprev_dt, int force_cold, int first_outer, int* n_active, int img_words)
+{
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ CtaShared sh;
+    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nt = blockDim.x;
+    double* Gp = ws + (int64_t)inst * L.stride;
+    if (Gp[L.oSCAL + MPCB200_SC_VALID] == 0.0)
+    {
+        if (tid == 0 && phase == MPCB200_PHASE_INIT) mark_invalid(L, Gp);
+        return;
+    }
+    if (phase >= MPCB200_PHASE_EVAL && Gp[L.oSCAL + MPCB200_SC_STATUS] >= 0.0) return;  // finished instance: exact no-op (uniform over the CTA)
+    double* W = reinterpret_cast<double*>(dyn_smem + IMG_HEAD);
+    const uint32_t bar = smem_addr(dyn_smem);
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    stage_in(W, Gp, img_words, bar, 0, tid);
+    switch (phase)
+    {
+        case MPCB200_PHASE_INIT: if (wid == 0) dev_init(c, L, W, Gp + L.oXINIT, force_cold, lane); break;
+        case MPCB200_PHASE_ASSOCIATE: if (wid == 0) dev_associate(c, L, W, uprev_dt, first_outer, lane); break;
+        case MPCB200_PHASE_EVAL:
+        {
+            const int fin = dev_eval<LINES>(c, L, W, uprev_dt, sh, tid, nt);
+            if (!fin && n_active && tid == 0) atomicAdd(n_active, 1);
+            break;
+        }
+        case MPCB200_PHASE_LINESEARCH: dev_linesearch<LINES>(c, L, W, uprev_dt, sh, tid, nt); break;
+        default: break;
+    }
+    stage_out(Gp, W, L.oOTYPE, tid);   // everything but the inputs
+}
+
+// ---- kernel: PHASE_KKT -- one warp per instance: records HBM -> shared memory (one bulk-async copy), warp-cooperative
+//      Riccati sweep (mpc_riccati_warp.h), Newton step -> HBM.  Algorithmic traffic: the records in, 8 words per stage out. ----
+template <bool EXT>
+__global__ void __launch_bounds__(32) kkt_warp_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, double* ws, int B, unsigned long long* counters)
+{
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    const int inst = blockIdx.x, lane = threadIdx.x;
+    const int N = L.N;
+    double* Gp = ws + (int64_t)inst * L.stride;
+    if (Gp[L.oSCAL + MPCB200_SC_VALID] == 0.0 || Gp[L.oSCAL + MPCB200_SC_STATUS] >= 0.0) return;
+    const int rec_words = (N * RSTR + 1) & ~1;
+    double* recs = reinterpret_cast<double*>(dyn_smem + IMG_HEAD);
+    double* mms = recs + rec_words;
+    double* stp = mms + rw_scratch_words<EXT>(N);
+    const uint32_t bar = smem_addr(dyn_smem);
+    if (lane == 0)
     {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)rec_words * 8u);
+        bulk_g2s(smem_addr(recs), Gp + L.oKKT, (uint32_t)rec_words * 8u, bar);
     }
-    __syncthreads();
-    if (tid == 0)
-    {
-        // scalars of this instance may have been written by this thread a moment ago (generic proxy): order them first
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        const uint32_t bytes_a = (uint32_t)L.oSTEP * 8u, bytes_c = (uint32_t)(img_words - L.oOTYPE) * 8u;
-        const uint32_t bytes_b = step_src >= 0 ? (uint32_t)(8 * L.N) * 8u : 0u;
-        mbar_expect_tx(bar, bytes_a + bytes_b + bytes_c);
-        bulk_g2s(dst, Gp, bytes_a, bar);
-        if (step_src >= 0) bulk_g2s(dst + (uint32_t)L.oSTEP * 8u, Gp + step_src, bytes_b, bar);
-        bulk_g2s(dst + (uint32_t)L.oOTYPE * 8u, Gp + L.oOTYPE, bytes_c, bar);
-    }
-    mbar_wait(bar, 0);
-    return img;
-}
-
-// ---- kernel: PHASE_EVAL -----------------------------------------------------------------------------------
-// ONE CTA PER INSTANCE, one lane per horizon stage: ceil(N/32) warps (at most MAX_GROUP_WARPS, then the stage loop
-// wraps).  Splitting an instance over several warps halves the dependent instruction stream each warp walks through --
-// at BASELINE batch sizes every kernel of the IPM iteration is latency- not throughput-bound.
-__device__ __forceinline__ void evalacc_warp_reduce(EvalAcc& a)
-{
-    a.dual_inf = warp_max(a.dual_inf); a.prim_inf = warp_max(a.prim_inf);
-    a.sl_max = warp_max(a.sl_max); a.sl_min = warp_min(a.sl_min);
-    a.sum_nu = warp_sum(a.sum_nu); a.sum_lam = warp_sum(a.sum_lam); a.inf1 = warp_sum(a.inf1); a.blog = warp_sum(a.blog);
-    a.gt0 = warp_sum(a.gt0); a.gt1 = warp_sum(a.gt1); a.gldt = warp_sum(a.gldt); a.htt = warp_sum(a.htt);
-    a.obj = warp_sum(a.obj); a.m_ineq = warp_sum(a.m_ineq); a.m_eq = warp_sum(a.m_eq);
-}
-
-template <int NW, bool LINES>
-__global__ void __maxnreg__(NW <= 2 ? 144 : 168) eval_kernel(Cfg c, WsLayout L, double* ws, double* kkt_tiles, const int* slot_of, int B, double uprev_dt, int* n_active,
-                                                             int img_words)
-{
-    extern __shared__ __align__(128) unsigned char img_smem[];
-    __shared__ EvalAcc s_acc[MAX_GROUP_WARPS];
-    __shared__ double s_mu;
-    __shared__ int s_fin;
-    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    double* Gp = ws + (int64_t)inst * L.stride;
-    const int N = L.N;
-    if (Gp[L.oSCAL + MPCB200_SC_STATUS] >= 0.0) return;  // finished instance: exact no-op (uniform over the CTA)
-    double* W = load_image(img_smem, L, Gp, img_words, -1, tid);
-    const int slot = slot_of[inst];
-    double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
-    EvalAcc a;
-    evalacc_init(a);
-    for (int k = tid; k < N; k += blockDim.x) eval_stage<LINES>(c, L, W, Gp, Kb, uprev_dt, k, a);
-    evalacc_warp_reduce(a);
-    if (lane == 0) s_acc[wid] = a;
-    __syncthreads();
-    if (tid == 0)
-    {
-        for (int w = 1; w < nw; ++w) evalacc_merge(a, s_acc[w]);
-        int fin = 0;
-        s_mu = eval_finish(c, L, Gp, a, true, &fin);
-        s_fin = fin;
-        if (!fin && n_active) atomicAdd(n_active, 1);
-    }
-    __syncthreads();
-    if (s_fin) return;
-    const double mu = s_mu;
-    for (int k = tid; k < N; k += blockDim.x) eval_finalize_stage(L, W, Kb, k, mu);
-}
-
-// ---- kernel: PHASE_KKT -- Riccati factorisation + solve, ONE LANE PER INSTANCE ------------------------------------
-// One warp per 32-instance tile.  The stage records (backward sweep) and the gains + dynamics (forward sweep) of a tile
-// are contiguous 10.5 KB / 10.5-16 KB blocks, so they are streamed through a KKT_RING-deep shared-memory ring with
-// 1-D bulk-async copies (cp.async.bulk, the TMA engine) completing on mbarriers: the lanes read their words from
-// shared memory (conflict-free, 8 B per lane) and never stall on a global load.  Lanes whose instance is finished (or
-// beyond B) idle through the sweeps.
-#define KKT_RING 4
-struct StepOut
-{
-    double* W; int oSTEP; int N;
-    __device__ void operator()(int k, int c, double v) const { W[oSTEP + c * N + k] = v; }
-};
-
-struct SmemView
-{
-    const double* p;  // word 0 of this lane in the staged block, words TILE apart
-    __device__ double operator()(int f) const { return p[f * TILE]; }
-};
-template <int NG>
-struct FwdViewSmem
-{
-    const double* p;  // staged block: NG gain words, then record words 20..31, then 39..41
-    __device__ double gain(int w) const { return p[w * TILE]; }
-    __device__ double rec(int f) const { return p[(f < MPCB200_K_D ? NG + (f - MPCB200_K_A) : NG + 12 + (f - MPCB200_K_D)) * TILE]; }
-};
-
-template <bool EXT>
-struct TmaFeed
-{
-    static constexpr int NC = EXT ? 5 : 1;
-    static constexpr int NG = 25 + 5 * NC;                                             // gain words read by the forward sweep
-    static constexpr int FWD_WORDS = NG + 12 + (EXT ? 3 : 0);
-    static constexpr int BUF_WORDS = FWD_WORDS > MPCB200_KKT_WORDS ? FWD_WORDS : MPCB200_KKT_WORDS;  // per ring slot, x TILE doubles
-    TileRec rec;              // this lane's words in the tile (direct global access: terminal record)
-    TileRic ric;              // this lane's gain words (written by the backward sweep)
-    const double* rec_tile;   // tile bases for the bulk copies
-    const double* ric_tile;
-    double* ring;             // shared-memory ring (generic address)
-    uint32_t ring_s, bar_s;   // ... and its shared-space address, the mbarriers
-    int lane, dt_free;
-    uint32_t issued, consumed;
-
-    __device__ bool any(bool p) const { return __any_sync(FULLMASK, p) != 0; }
-    __device__ void issue_bwd(int k)
-    {
-        if (lane == 0)
-        {
-            const uint32_t slot = issued % KKT_RING, bar = bar_s + 8 * slot;
-            mbar_expect_tx(bar, MPCB200_KKT_WORDS * TILE * 8);
-            bulk_g2s(ring_s + slot * (BUF_WORDS * TILE * 8), rec_tile + (size_t)k * MPCB200_KKT_WORDS * TILE, MPCB200_KKT_WORDS * TILE * 8, bar);
-        }
-        ++issued;
-    }
-    __device__ void issue_fwd(int k)
-    {
-        if (lane == 0)
-        {
-            const uint32_t slot = issued % KKT_RING, bar = bar_s + 8 * slot, dst = ring_s + slot * (BUF_WORDS * TILE * 8);
-            const bool with_d = EXT && dt_free;
-            mbar_expect_tx(bar, (NG + 12 + (with_d ? 3 : 0)) * TILE * 8);
-            bulk_g2s(dst, ric_tile + (size_t)k * RICW_MAX * TILE, NG * TILE * 8, bar);
-            bulk_g2s(dst + NG * TILE * 8, rec_tile + ((size_t)k * MPCB200_KKT_WORDS + MPCB200_K_A) * TILE, 12 * TILE * 8, bar);
-            if (with_d) bulk_g2s(dst + (NG + 12) * TILE * 8, rec_tile + ((size_t)k * MPCB200_KKT_WORDS + MPCB200_K_D) * TILE, 3 * TILE * 8, bar);
-        }
-        ++issued;
-    }
-    __device__ const double* acquire()
-    {
-        const uint32_t slot = consumed % KKT_RING;
-        mbar_wait(bar_s + 8 * slot, (consumed / KKT_RING) & 1u);
-        return ring + (size_t)slot * BUF_WORDS * TILE + lane;
-    }
-    __device__ void bwd_start(int kfirst)
-    {
-        for (int j = 0; j < KKT_RING && kfirst - j >= 0; ++j) issue_bwd(kfirst - j);
-    }
-    __device__ SmemView bwd_acquire(int) { return SmemView{acquire()}; }
-    __device__ void bwd_release(int k)
-    {
-        __syncwarp();  // every lane is done with the slot before the next copy lands in it
-        ++consumed;
-        if (k - KKT_RING >= 0) issue_bwd(k - KKT_RING);
-    }
-    __device__ void bwd_abort()
-    {
-        while (consumed != issued) { acquire(); ++consumed; }  // drain the copies in flight
-    }
-    __device__ void fwd_start(int N)
-    {
-        // the gains were written with ordinary stores by the lanes of this warp: order them before the async-proxy reads
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncwarp();
-        for (int j = 0; j < KKT_RING && j <= N - 2; ++j) issue_fwd(j);
-        n_stages = N - 1;
-    }
-    int n_stages;
-    __device__ FwdViewSmem<NG> fwd_acquire(int) { return FwdViewSmem<NG>{acquire()}; }
-    __device__ void fwd_release(int k)
-    {
-        __syncwarp();
-        ++consumed;
-        if (k + KKT_RING < n_stages) issue_fwd(k + KKT_RING);
-    }
-};
-
-template <bool EXT>
-__global__ void __launch_bounds__(32) kkt_lane_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, double* ric_tiles, size_t ric_attempt_stride,
-                                                       const int* inst_of_slot, int B, int spec, unsigned long long* counters)
-{
-    extern __shared__ __align__(128) unsigned char kkt_smem[];
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int attempt = blockIdx.y;  // speculative mode: attempt 0 and 1 of the regularisation schedule run side by side
-    const int N = L.N;
-    const int b = inst_of_slot[tile * TILE + lane];
-    double* W = b >= 0 ? ws + (int64_t)b * L.stride : ws;
-    const bool active = b >= 0 && !(ASC(MPCB200_SC_STATUS) >= 0.0);
-    if (!__any_sync(FULLMASK, active)) return;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(kkt_smem);
-    TmaFeed<EXT> feed;
-    feed.rec_tile = kkt_tiles + (size_t)tile * N * KW * TILE;
-    feed.ric_tile = ric_tiles + (size_t)attempt * ric_attempt_stride + (size_t)tile * N * RICW_MAX * TILE;
-    feed.rec = TileRec{feed.rec_tile + lane};
-    feed.ric = TileRic{const_cast<double*>(feed.ric_tile) + lane};
-    feed.ring = reinterpret_cast<double*>(kkt_smem + 128);
-    feed.ring_s = smem_addr(feed.ring);
-    feed.bar_s = smem_addr(bars);
-    feed.lane = lane; feed.dt_free = c.variable_dt;
-    feed.issued = feed.consumed = 0; feed.n_stages = N - 1;
-    if (lane == 0)
-    {
-        for (int i = 0; i < KKT_RING; ++i) mbar_init(feed.bar_s + 8 * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    CudaWarp<EXT> ex;
+    ex.lane = lane;
+    kkt_warp_setup<EXT>(ex, c.variable_dt);   // beside the copy
+    const double htt = Gp[L.oSCAL + MPCB200_SC_HTT], gt = Gp[L.oSCAL + MPCB200_SC_GT], dlast = Gp[L.oSCAL + MPCB200_SC_DELTA_LAST];
     __syncwarp();
-    StepOut step{W, attempt ? L.oSTEP2 : L.oSTEP, N};
+    mbar_wait(bar, 0);
     double ddt = 0.0, delta = 0.0;
     int nreg = 0;
-    const double htt = active ? ASC(MPCB200_SC_HTT) : 0.0, gt = active ? ASC(MPCB200_SC_GT) : 0.0, dlast = active ? ASC(MPCB200_SC_DELTA_LAST) : 0.0;
-    const int ok = riccati_solve_lane<EXT>(c, N, feed, step, active, htt, gt, dlast, spec ? attempt : 0, spec ? 1 : MAX_INERTIA_TRIES, &ddt, &delta, &nreg);
-    if (!active) return;
-    if (counters)
-    {
-        if (attempt == 0) atomicAdd(counters, 1ull);
-        atomicAdd(counters + 1, spec ? 1ull : (unsigned long long)(nreg + (ok ? 1 : 0)));
-    }
-    if (spec)
-    {
-        // the line-search kernel picks the winner (kkt_resolve)
-        if (attempt == 0) { ASC(MPCB200_SC_KKT_OK0) = (double)ok; ASC(MPCB200_SC_DELTA) = delta; ASC(MPCB200_SC_DDT) = ddt; }
-        else { ASC(MPCB200_SC_KKT_OK1) = (double)ok; ASC(MPCB200_SC_DELTA1) = delta; ASC(MPCB200_SC_DDT1) = ddt; }
-        return;
-    }
-    ASC(MPCB200_SC_NREG) += (double)nreg;
-    if (!ok && delta <= MAX_DELTA)
-    {
-        // factorisation budget of this iteration spent: null step, the next iteration resumes at this delta (DELTA_LAST / 3)
-        ASC(MPCB200_SC_DELTA_LAST) = 3.0 * delta;
-        ASC(MPCB200_SC_DEFER) = 1.0;
-        return;
-    }
-    if (!ok) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; return; }
-    ASC(MPCB200_SC_DEFER) = 0.0;
-    ASC(MPCB200_SC_DDT) = ddt;
-    ASC(MPCB200_SC_DELTA) = delta;
-    ASC(MPCB200_SC_DELTA_LAST) = delta;
-}
-
-template <bool EXT>
-static size_t kkt_smem_bytes() { return 128 + (size_t)KKT_RING * TmaFeed<EXT>::BUF_WORDS * TILE * 8; }
-
-// ---- kernel: PHASE_LINESEARCH -------------------------------------------------------------------------------
-// one CTA per instance (lane per stage, see eval_kernel); thread 0 owns the scalar decisions of the line search.
-struct LsShared
-{
-    LsAcc acc[MAX_GROUP_WARPS];
-    TrialAcc tr[MAX_GROUP_WARPS];
-    int hist[CLIP_BINS + 1];
-    double alpha, a_dual;
-    int accept;
-};
-
-#define GSC(i_) Gp[L.oSCAL + (i_)]
-template <bool LINES>
-__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 4) linesearch_kernel(Cfg c, WsLayout L, double* ws, const double* kkt_tiles, const int* slot_of, int B, double uprev_dt,
-                                                                             int spec, int img_words)
-{
-    extern __shared__ __align__(128) unsigned char img_smem[];
-    __shared__ LsShared sh;
-    __shared__ int s_win;
-    const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    double* Gp = ws + (int64_t)inst * L.stride;
-    const int N = L.N;
-    if (GSC(MPCB200_SC_STATUS) >= 0.0) return;
-    int step_src = L.oSTEP;
-    if (spec)
-    {
-        // the KKT phase ran attempts 0 and 1 of the regularisation schedule side by side: pick the winner
-        __syncthreads();
-        if (tid == 0)
-        {
-            int nreg = 0;
-            double dnext = 0.0;
-            const double d0 = GSC(MPCB200_SC_DELTA), d1 = GSC(MPCB200_SC_DELTA1);
-            const int win = kkt_resolve(GSC(MPCB200_SC_KKT_OK0) != 0.0, GSC(MPCB200_SC_KKT_OK1) != 0.0, d0, d1, GSC(MPCB200_SC_DELTA_LAST), &nreg, &dnext);
-            GSC(MPCB200_SC_NREG) += (double)nreg;
-            if (win == -2) GSC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;
-            else if (win == -1) { GSC(MPCB200_SC_DELTA_LAST) = 3.0 * dnext; GSC(MPCB200_SC_DEFER) = 1.0; }
-            else
-            {
-                const double dw = win ? d1 : d0;
-                GSC(MPCB200_SC_DEFER) = 0.0;
-                if (win) GSC(MPCB200_SC_DDT) = GSC(MPCB200_SC_DDT1);
-                GSC(MPCB200_SC_DELTA) = dw;
-                GSC(MPCB200_SC_DELTA_LAST) = dw;
-            }
-            s_win = win;
-        }
-        __syncthreads();
-        if (s_win == -2) return;
-        if (s_win == 1) step_src = L.oSTEP2;
-    }
-    if (GSC(MPCB200_SC_DEFER) != 0.0)
-    {
-        // the KKT phase spent its factorisation budget: null step
-        __syncthreads();
-        if (tid == 0) { GSC(MPCB200_SC_DEFER) = 0.0; GSC(MPCB200_SC_ITER) += 1.0; GSC(MPCB200_SC_ALPHA) = 0.0; }
-        return;
-    }
-    double* W = load_image(img_smem, L, Gp, img_words, step_src, tid);  // image incl. the winning step at L.oSTEP
-    const int slot = slot_of[inst];
-    const double* Kb = kkt_tiles + (size_t)(slot >> 5) * N * KW * TILE + (slot & 31);
-    LsAcc a;
-    lsacc_init(a);
-    // histogram of the blocking step ratios (+ row count) -> threshold bin of the clipped rows -> primal step length
-    for (int j = tid; j <= CLIP_BINS; j += blockDim.x) sh.hist[j] = 0;
-    __syncthreads();
-    for (int k = tid; k < N; k += blockDim.x) ls_stage_steps(c, L, W, Gp, Kb, uprev_dt, k, a, sh.hist);
-    __syncthreads();
-    const int jt = clip_threshold_bin(sh.hist, sh.hist[CLIP_BINS]);  // same value in every thread
-    for (int k = tid; k < N; k += blockDim.x) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt));
-    a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
-    a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
-    if (lane == 0) sh.acc[wid] = a;
-    __syncthreads();
-    // scalars of the merit function (thread 0 only)
-    double mu = 0.0, rho = 1.0, phi0 = 0.0, dphi = 0.0, a_d = 1.0;
-    if (tid == 0)
-    {
-        for (int w = 1; w < nw; ++w)
-        {
-            const LsAcc& o = sh.acc[w];
-            a.a_p = fmin(a.a_p, o.a_p); a.a_d = fmin(a.a_d, o.a_d);
-            a.dphi_bar += o.dphi_bar; a.curv += o.curv; a.dJ += o.dJ;
-        }
-        mu = ASC(MPCB200_SC_MU);
-        const double inf1 = ASC(MPCB200_SC_INF), obj = ASC(MPCB200_SC_OBJ), blog = ASC(MPCB200_SC_BLOG);
-        const double num = a.dJ + a.dphi_bar + 0.5 * (a.curv > 0 ? a.curv : 0.0);
-        if (inf1 > 1e-14)
-        {
-            const double rho_trial = num / ((1.0 - 0.1) * inf1);
-            if (rho < rho_trial) rho = rho_trial + 1.0;
-        }
-        phi0 = obj - mu * blog + rho * inf1;
-        dphi = a.dJ + a.dphi_bar - rho * inf1;
-        a_d = a.a_d;
-        sh.alpha = a.a_p;
-    }
-    __syncthreads();
-    double alpha = sh.alpha;
-    int nbt = 0;
-    for (int bt = 0; bt < MAX_BACKTRACK; ++bt)
-    {
-        TrialAcc t;
-        t.obj = t.inf1 = t.blog = 0.0;
-        for (int k = tid; k < N; k += blockDim.x) ls_stage_trial<LINES>(c, L, W, Gp, uprev_dt, k, alpha, t);
-        t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
-        if (lane == 0) sh.tr[wid] = t;
-        __syncthreads();
-        if (tid == 0)
-        {
-            for (int w = 1; w < nw; ++w) { t.obj += sh.tr[w].obj; t.inf1 += sh.tr[w].inf1; t.blog += sh.tr[w].blog; }
-            const double phi = t.obj - mu * t.blog + rho * t.inf1;
-            sh.accept = (phi <= phi0 + ARMIJO * alpha * dphi || (bt > 0 && fabs(phi - phi0) <= 1e-13 * (1.0 + fabs(phi0)))) ? 1 : 0;
-        }
-        __syncthreads();
-        const int accept = sh.accept;
-        __syncthreads();  // sh.accept / sh.tr are rewritten by the next trial
-        if (accept) break;
-        alpha *= 0.5;
-        ++nbt;
-    }
-    if (tid == 0) sh.a_dual = a_d > alpha ? alpha : a_d;
-    __syncthreads();
-    const double a_dual = sh.a_dual;
-    for (int k = tid; k < N; k += blockDim.x) ls_stage_update<LINES>(c, L, W, Gp, uprev_dt, k, alpha, a_dual);
-    if (tid == 0)
-    {
-        if (c.variable_dt) GSC(MPCB200_SC_DT) = ASC(MPCB200_SC_DT) + alpha * ASC(MPCB200_SC_DDT);
-        GSC(MPCB200_SC_ALPHA) = alpha;
-        GSC(MPCB200_SC_RHO) = rho;
-        GSC(MPCB200_SC_ITER) = ASC(MPCB200_SC_ITER) + 1.0;
-        GSC(MPCB200_SC_NBT) = ASC(MPCB200_SC_NBT) + (double)nbt;
-        const double tiny = alpha < TINY_STEP ? ASC(MPCB200_SC_TINY) + 1.0 : 0.0;
-        GSC(MPCB200_SC_TINY) = tiny;
-        if (tiny >= (double)TINY_STEP_COUNT) GSC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR;  /* jammed: give up */
-    }
-}
-
-// ---- kernel: gather results into compact arrays ----------------------------------------------------------------
-struct OutputPtrs { double* u_seq; double* x_seq; double* dt; int* status; double* kkt; int* iters; double* u_packed; };
-__device__ __forceinline__ void gather_one(const WsLayout& L, const double* W, const OutputPtrs& o, int64_t dst, int lane)
-{
-    const int N = L.N;
-    for (int k = lane; k < N; k += 32)
-    {
-        const int kk = k <= N - 2 ? k : N - 2;
-        o.u_seq[(dst * N + k) * 2 + 0] = AU(0, kk);
-        o.u_seq[(dst * N + k) * 2 + 1] = AU(1, kk);
-        o.x_seq[(dst * N + k) * 3 + 0] = AX(0, k);
-        o.x_seq[(dst * N + k) * 3 + 1] = AX(1, k);
-        o.x_seq[(dst * N + k) * 3 + 2] = normalize_theta(AX(2, k));
-        if (k <= N - 2)
-        {
-            o.u_packed[(dst * (N - 1) + k) * 2 + 0] = AU(0, k);
-            o.u_packed[(dst * (N - 1) + k) * 2 + 1] = AU(1, k);
-        }
-    }
+    const int ok = kkt_warp_solve<EXT>(ex, c, N, recs, mms, stp, htt, gt, dlast, &ddt, &delta, &nreg);
+    __syncwarp();
+    if (ok)
+        for (int i = lane; i < 8 * N; i += 32) Gp[L.oSTEP + i] = stp[i];
     if (lane == 0)
     {
-        o.dt[dst] = ASC(MPCB200_SC_DT);
-        const double st = ASC(MPCB200_SC_STATUS);
-        o.status[dst] = st < 0 ? MPCB200_STATUS_MAX_ITER : (int)st;
-        o.kkt[dst] = ASC(MPCB200_SC_ERR0);
-        o.iters[dst] = (int)ASC(MPCB200_SC_ITER);
+        kkt_store_outcome(Gp + L.oSCAL, ok, ddt, delta, nreg);
+        if (counters) { atomicAdd(counters + CNT_KKT_INST, 1ull); atomicAdd(counters + CNT_KKT_SWEEPS, (unsigned long long)(nreg + (ok ? 1 : 0))); }
+    }
+}
+template <bool EXT>
+static size_t kkt_smem_bytes(int N) { return IMG_HEAD + (size_t)(((N * RSTR + 1) & ~1) + rw_scratch_words<EXT>(N) + 8 * N) * 8; }
+
+// ---- kernel: THE SOLVE.  Persistent CTAs take instances from a queue and own them until they terminate. ----
+struct FusedArgs
+{
+    double* ws;              // instance blocks (batch mode: instance i <-> block i, warm state in / out); unused in queue mode
+    InputPtrs in;
+    OutputPtrs out;
+    int total;               // instances in the queue
+    int queue_mode;          // 1: a queue of cold instances without blocks (mpcb200_solve_stream)
+    int force_cold;
+    double uprev_dt;
+    int img_words;           // resident prefix
+    int* queue;              // next instance
+    unsigned long long* counters;
+};
+template <bool LINES, bool EXT>
+__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, const __grid_constant__ FusedArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ CtaShared sh;
+    __shared__ int s_inst, s_valid;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nt = blockDim.x;
+    const int N = L.N;
+    double* W = reinterpret_cast<double*>(dyn_smem + IMG_HEAD);
+    const uint32_t bar = smem_addr(dyn_smem);
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    CudaWarp<EXT> ex;
+    ex.lane = lane;
+    if (wid == 0) kkt_warp_setup<EXT>(ex, c.variable_dt);
+    __syncthreads();
+    uint32_t parity = 0;
+    unsigned long long cyc[MPCB200_NUM_PHASES] = {0, 0, 0, 0, 0}, cyc_total = 0, n_kkt = 0, n_sweeps = 0, n_inst = 0;
+    const int outer = c.outer_iterations > 0 ? c.outer_iterations : 1;
+#define TICK(p_) do { if (tid == 0) { const long long t_ = clock64(); cyc[p_] += (unsigned long long)(t_ - t_mark); t_mark = t_; } } while (0)
+    for (;;)
+    {
+        if (tid == 0) s_inst = atomicAdd(a.queue, 1);
+        __syncthreads();
+        const int inst = s_inst;
+        if (inst >= a.total) break;
+        long long t_mark = clock64();
+        const long long t_begin = t_mark;
+        double* Gp = a.queue_mode ? nullptr : a.ws + (int64_t)inst * L.stride;
+        // ---- state: warm trajectory and scalars of the block, or a fresh cold slot ----
+        if (!a.queue_mode) { stage_in(W, Gp, L.oNU, bar, parity, tid); parity ^= 1u; }
+        else if (tid < MPCB200_SCAL_WORDS) W[L.oSCAL + tid] = tid == MPCB200_SC_COLD ? 1.0 : (tid == MPCB200_SC_STATUS ? -1.0 : 0.0);
+        __syncthreads();
+        // ---- inputs ----
+        if (wid == 0)
+        {
+            const bool ok = scatter_one(L, W, a.in, inst, lane, nullptr);
+            if (lane == 0) { s_valid = ok; ASC(MPCB200_SC_VALID) = ok ? 1.0 : 0.0; if (!ok) mark_invalid(L, W); }
+        }
+        __syncthreads();
+        if (s_valid)
+        {
+            if (wid == 0) dev_init(c, L, W, a.in.x_init ? a.in.x_init + (int64_t)inst * 3 * N : nullptr, a.force_cold, lane);
+            __syncthreads();
+            TICK(MPCB200_PHASE_INIT);
+            for (int oi = 0; oi < outer; ++oi)
+            {
+                if (wid == 0) dev_associate(c, L, W, a.uprev_dt, oi == 0, lane);
+                __syncthreads();
+                TICK(MPCB200_PHASE_ASSOCIATE);
+                for (;;)
+                {
+                    const int fin = dev_eval<LINES>(c, L, W, a.uprev_dt, sh, tid, nt);
+                    TICK(MPCB200_PHASE_EVAL);
+                    if (fin) break;
+                    if (wid == 0) dev_kkt<EXT>(c, L, W, ex, &n_sweeps);
+                    __syncthreads();
+                    TICK(MPCB200_PHASE_KKT);
+                    if (tid == 0) ++n_kkt;
+                    if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // inertia correction failed: given up
+                    dev_linesearch<LINES>(c, L, W, a.uprev_dt, sh, tid, nt);
+                    TICK(MPCB200_PHASE_LINESEARCH);
+                    if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // jammed: given up
+                }
+            }
+            // a failed solve leaves nothing to warm-start from
+            if (tid == 0 && ASC(MPCB200_SC_STATUS) == (double)MPCB200_STATUS_NUMERICAL_ERROR) ASC(MPCB200_SC_COLD) = 1.0;
+        }
+        __syncthreads();
+        gather_one(L, W, a.out, inst, tid, nt);
+        if (!a.queue_mode) stage_out(Gp, W, L.oSTATE_END, tid);   // state (and what the kernel-level API reads back)
+        else __syncthreads();
+        if (tid == 0) { cyc_total += (unsigned long long)(clock64() - t_begin); ++n_inst; }
+    }
+#undef TICK
+    if (tid == 0 && a.counters)
+    {
+        for (int p = 0; p < MPCB200_NUM_PHASES; ++p) atomicAdd(a.counters + CNT_CYC + p, cyc[p]);
+        atomicAdd(a.counters + CNT_CYC_TOTAL, cyc_total);
+        atomicAdd(a.counters + CNT_KKT_INST, n_kkt);
+        atomicAdd(a.counters + CNT_KKT_SWEEPS, n_sweeps);
+        atomicAdd(a.counters + CNT_INST, n_inst);
     }
 }
 
-__global__ void gather_outputs_kernel(WsLayout L, const double* ws, int B, OutputPtrs o)
-{
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    gather_one(L, ws + (int64_t)warp * L.stride, o, warp, lane);
-}
-
-// ---- streaming: a pool of B slots works through a queue of instances (continuous batching) ---------------------------
-// A slot whose instance has finished hands its result over (gather into the arrays of the whole job at the instance's
-// index) and takes the next instance of the queue; the IPM iteration kernels neither know nor care which slot holds
-// which instance.  Run every STREAM_REFILL_EVERY iterations, followed by the init / associate kernels restricted to the
-// slots marked SC_NEW.  counters[0] = next instance of the queue, counters[1] = results handed over.
-#define STREAM_REFILL_EVERY 2
-struct StreamState { int* slot_inst; int* counters; int total; };
-__global__ void stream_begin_kernel(WsLayout L, double* ws, int B, StreamState st)
-{
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) { st.counters[0] = 0; st.counters[1] = 0; }
-    if (b >= B) return;
-    double* W = ws + (int64_t)b * L.stride;
-    ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_INVALID_INPUT;  // any value >= 0: the slot is free
-    ASC(MPCB200_SC_NEW) = 0.0;
-    st.slot_inst[b] = -1;
-}
-__global__ void stream_refill_kernel(WsLayout L, double* ws, int B, InputPtrs in, OutputPtrs o, StreamState st)
+// ---- kernel: gather results into compact arrays (phased path) ----------------------------------------------------------------
+__global__ void gather_outputs_kernel(WsLayout L, double* ws, int B, OutputPtrs o)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     double* W = ws + (int64_t)warp * L.stride;
-    if (!(ASC(MPCB200_SC_STATUS) >= 0.0)) return;  // still iterating
-    const double nw = ASC(MPCB200_SC_NEW);
+    if (lane == 0 && ASC(MPCB200_SC_STATUS) == (double)MPCB200_STATUS_NUMERICAL_ERROR) ASC(MPCB200_SC_COLD) = 1.0;
     __syncwarp();
-    if (nw != 0.0)
-    {
-        // refilled in the previous round, initialised on the side stream since then: starts iterating now
-        if (lane == 0 && nw == 2.0) { ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NEW) = 0.0; }
-        return;
-    }
-    const int id = st.slot_inst[warp];
-    __syncwarp();
-    if (id >= 0)
-    {
-        gather_one(L, W, o, id, lane);
-        if (lane == 0) atomicAdd(&st.counters[1], 1);
-    }
-    int nid = 0;
-    if (lane == 0) nid = atomicAdd(&st.counters[0], 1);
-    nid = __shfl_sync(FULLMASK, nid, 0);
-    if (nid < st.total)
-    {
-        scatter_one(L, W, in, nid, lane);
-        if (lane == 0) { st.slot_inst[warp] = nid; ASC(MPCB200_SC_COLD) = 1.0; ASC(MPCB200_SC_NEW) = 1.0; }
-    }
-    else if (lane == 0)
-    {
-        st.slot_inst[warp] = -1;
-        if (nid > (1 << 30)) st.counters[0] = st.total;  // idle slots keep asking: never let the counter wrap
-    }
+    gather_one(L, W, o, warp, lane, 32);
 }
 
 __global__ void reset_kernel(WsLayout L, double* ws, int B, const unsigned char* which)
@@ -860,141 +301,6 @@ __global__ void resample_unpack_kernel(WsLayout L, double* ws, const double* rec
     ASC(MPCB200_SC_DT) = resample_serial(n_old, r + MPCB200_SCAL_WORDS, r + MPCB200_SCAL_WORDS + 3 * n_old, r[MPCB200_SC_DT], L.N, W + L.oX, W + L.oU);
 }
 
-// ---- costmap -> point obstacles (MpcLocalPlannerROS::updateObstacleContainerWithCostmap, mpc_local_planner_ros.cpp:474-499) ----
-// The reference walks the cells mx = 0..size_x-2 (outer), my = 0..size_y-2 (inner), keeps the LETHAL ones that are not farther
-// than behind_dist behind the robot and appends them as point obstacles at the cell centres.  HBM-bound byte work, one byte per
-// cell, read ONCE:
-//   mark    a thread owns four adjacent columns (one 32-bit load per row, a warp reads 128 contiguous bytes), tests the word
-//           for a LETHAL byte with one bit trick, applies the filter to the few hits and records them as one bit per cell in
-//           per-column masks (32 rows per word, 1/8 byte per cell) next to the per-column counts;
-//   offsets exclusive scan of the column counts of each robot;
-//   emit    a thread owns one column and walks its mask words in row order: column offsets + bit order reproduce the
-//           reference's push_back order (mx outer, my inner) exactly.
-#define COSTMAP_LETHAL 254u   // costmap_2d::LETHAL_OBSTACLE
-struct CostmapArgs
-{
-    int size_x, size_y;
-    double resolution, behind_dist;
-    const unsigned char* cost;   // [B][size_y][size_x]
-    const double* origin;        // [B][2]
-    const double* pose;          // [B][3]
-};
-// Costmap2D::mapToWorld: cell centre
-__device__ __forceinline__ double costmap_world(double o, int m, double res) { return o + ((double)m + 0.5) * res; }
-__device__ __forceinline__ bool costmap_keep(const CostmapArgs& a, int mx, int my, double ox, double oy, double px, double py, double dirx, double diry)
-{
-    const double dx = costmap_world(ox, mx, a.resolution) - px, dy = costmap_world(oy, my, a.resolution) - py;
-    // "not far behind the robot" (mpc_local_planner_ros.cpp:492-493)
-    return !(dx * dirx + dy * diry < 0.0 && sqrt(dx * dx + dy * dy) > a.behind_dist);
-}
-__device__ __forceinline__ bool word_has_lethal(unsigned w)
-{
-    const unsigned x = w ^ 0xFEFEFEFEu;                       // LETHAL bytes become zero bytes
-    return ((x - 0x01010101u) & ~x & 0x80808080u) != 0u;
-}
-template <bool VEC>   // VEC: size_x % 4 == 0, every row of every map starts 4-byte aligned
-__global__ void costmap_mark_kernel(CostmapArgs a, int B, int nrb, int Wp, unsigned* mask /*[B][nrb][Wp]*/, int* colcount /*[B][size_x]*/)
-{
-    const int b = blockIdx.y;
-    const int c0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (b >= B || c0 >= a.size_x) return;
-    const unsigned char* map = a.cost + (size_t)b * a.size_x * a.size_y;
-    const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
-    const double px = a.pose[3 * b], py = a.pose[3 * b + 1];
-    double diry, dirx;
-    sincos(a.pose[3 * b + 2], &diry, &dirx);   // PoseSE2::orientationUnitVec
-    int cnt[4] = {0, 0, 0, 0};
-    const int rows = a.size_y - 1;
-    for (int rb = 0; rb < nrb; ++rb)
-    {
-        unsigned m[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int r0 = 0; r0 < 32; r0 += 8)
-        {
-            unsigned w[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-            {
-                const int my = rb * 32 + r0 + r;
-                w[r] = 0u;
-                if (my < rows)
-                {
-                    const unsigned char* q = map + (size_t)my * a.size_x + c0;
-                    if (VEC) w[r] = *reinterpret_cast<const unsigned*>(q);
-                    else
-                        for (int i = 0; i < 4; ++i)
-                            if (c0 + i < a.size_x) w[r] |= (unsigned)q[i] << (8 * i);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-            {
-                if (!word_has_lethal(w[r])) continue;
-                const int my = rb * 32 + r0 + r;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (((w[r] >> (8 * i)) & 0xFFu) == COSTMAP_LETHAL && c0 + i < a.size_x - 1 &&
-                        costmap_keep(a, c0 + i, my, ox, oy, px, py, dirx, diry))
-                        m[i] |= 1u << (r0 + r);
-            }
-        }
-        *reinterpret_cast<uint4*>(mask + ((size_t)b * nrb + rb) * Wp + c0) = make_uint4(m[0], m[1], m[2], m[3]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cnt[i] += __popc(m[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (c0 + i < a.size_x) colcount[(size_t)b * a.size_x + c0 + i] = cnt[i];
-}
-__global__ void costmap_emit_kernel(CostmapArgs a, int B, int nrb, int Wp, const unsigned* mask, const int* colstart, int max_out,
-                                    double* params /*[B][max_out][MPCB200_OBST_STRIDE]*/, int* type /*[B][max_out]*/)
-{
-    const int b = blockIdx.y;
-    const int mx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B || mx >= a.size_x - 1) return;
-    const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
-    int o = colstart[(size_t)b * a.size_x + mx];
-    for (int rb = 0; rb < nrb && o < max_out; ++rb)
-    {
-        unsigned m = mask[((size_t)b * nrb + rb) * Wp + mx];
-        while (m && o < max_out)
-        {
-            const int my = rb * 32 + __ffs(m) - 1;
-            m &= m - 1u;
-            double* q = params + ((size_t)b * max_out + o) * MPCB200_OBST_STRIDE;
-            q[0] = costmap_world(ox, mx, a.resolution); q[1] = costmap_world(oy, my, a.resolution);
-            for (int i = 2; i < MPCB200_OBST_STRIDE; ++i) q[i] = 0.0;
-            type[(size_t)b * max_out + o] = MPCB200_OBST_POINT;
-            ++o;
-        }
-    }
-}
-// exclusive scan of the column counts of one robot (one CTA per robot); found = total, count = min(total, max_out)
-__global__ void costmap_offsets_kernel(int size_x, int B, const int* colcount, int* colstart, int max_out, int* count, int* found)
-{
-    const int b = blockIdx.x;
-    __shared__ int carry;
-    __shared__ int warp_tot[32];
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int base = 0; base < size_x; base += blockDim.x)
-    {
-        const int i = base + threadIdx.x;
-        const int v = i < size_x ? colcount[(size_t)b * size_x + i] : 0;
-        int incl = v;
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) warp_tot[wid] = incl;
-        __syncthreads();
-        int woff = 0, tot = 0;
-        for (int w = 0; w < nw; ++w) { if (w < wid) woff += warp_tot[w]; tot += warp_tot[w]; }
-        if (i < size_x) colstart[(size_t)b * size_x + i] = carry + woff + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { found[b] = carry; count[b] = carry < max_out ? carry : max_out; }
-}
 
 __global__ void flush_kernel(double* buf, size_t n)
 {
@@ -1014,36 +320,28 @@ struct mpcb200_handle
     double* d_resample;         // scratch of mpcb200_resample, allocated on first use
     void* d_cm; size_t cm_cap; double costmap_ms;  // scratch of mpcb200_costmap_obstacles (grown on demand), device ms of its last call
     double* ws;
-    double *kkt_tiles, *ric_tiles;
-    size_t ric_attempt_stride;  // doubles between the gain tiles of KKT attempt 0 and 1 (speculative mode)
-    int num_sms;
-    int spec_mode;              // MPCB200_OPT_KKT_ATTEMPTS: 0 auto, 1 serial, 2 side by side
-    int refill_every;           // MPCB200_OPT_STREAM_REFILL_EVERY: IPM iterations between two refills of the streaming pool
-    int spec;                   // this solve runs the two KKT attempts of an iteration side by side (small batches)
-    unsigned timing_mask;       // phases bracketed by CUDA events inside solve (bit = phase id); default: KKT only
+    int num_sms, clock_khz;
+    int solve_mode;             // MPCB200_OPT_SOLVE_MODE: 0 fused persistent kernel (default), 1 one kernel per phase
+    unsigned timing_mask;       // phased mode: phases bracketed by CUDA events inside solve (bit = phase id)
     cudaStream_t stream, own_stream;  // stream in use / the stream the handle created
     // compact device input / output staging
     double *d_x0, *d_xf, *d_uprev, *d_obst, *d_vp, *d_xinit;
     int *d_obst_count, *d_obst_type, *d_vp_count;
     unsigned char* d_reinit;
     double *d_useq, *d_xseq, *d_dt, *d_kkt, *d_upacked;
-    int *d_status, *d_iters, *d_nactive, *d_slot_of, *d_inst_of_slot;
+    int *d_status, *d_iters, *d_nactive, *d_queue;
     unsigned long long* d_counters;
     int* h_nactive;  // pinned, two poll slots
-    int* nactive_ptr;            // where the next eval launch counts unfinished instances (or null)
-    cudaEvent_t poll_ev[2];
+    cudaEvent_t poll_ev[2], t0, t1;
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
-    int only_new;   // streaming: init / associate touch only the slots marked SC_NEW
-    // streaming job: inputs / outputs of the whole queue on the device (grown on demand), slot -> instance map, counters
+    // queue job (mpcb200_solve_stream): inputs / outputs of the whole queue on the device (grown on demand)
     size_t stream_cap;
     double *s_x0, *s_xf, *s_uprev, *s_obst, *s_vp, *s_useq, *s_xseq, *s_dt, *s_kkt, *s_upacked;
-    int *s_obst_count, *s_obst_type, *s_vp_count, *s_status, *s_iters, *d_slot_inst, *d_stream_counters;
-    int* h_stream_counters;  // pinned, two poll slots
-    cudaStream_t side_stream;            // streaming: init / associate of refilled slots run beside the iterations of the others
-    cudaEvent_t ev_refill, ev_ready;
-    int has_lines;  // line obstacles in the batch, moving obstacles or midpoint differences: the eval / line-search kernels are launched with those (rarely used) paths compiled in
+    int *s_obst_count, *s_obst_type, *s_vp_count, *s_status, *s_iters;
+    int has_lines;  // line obstacles in the batch, moving obstacles or midpoint differences: the kernels are launched with those (rarely used) paths compiled in
     double uprev_dt;
+    int fused_grid;  // CTAs of the last fused launch
     mpcb200_stats stats;
     std::vector<cudaEvent_t> ev;  // pool of event pairs
     std::vector<int> ev_phase;
@@ -1089,6 +387,10 @@ extern "C" void mpcb200_default_config(mpcb200_config* c)
     c->hybrid_cost_minimum_time = 0;
 }
 
+
+// doubles of the resident prefix with the largest obstacle list the handle accepts
+static size_t max_resident_bytes(const WsLayout& L) { return IMG_HEAD + (size_t)resident_words(L, L.M) * 8; }
+
 static int validate_config(const mpcb200_config* c, std::string& why)
 {
     if (c->n < 3 || c->n > 512) { why = "n must be in [3, 512]"; return MPCB200_E_INVALID; }
@@ -1108,9 +410,20 @@ static int validate_config(const mpcb200_config* c, std::string& why)
     if (!(c->tol > 0) || c->max_iter < 1) { why = "tol > 0 and max_iter >= 1 required"; return MPCB200_E_INVALID; }
     for (int i = 0; i < 2; ++i)
         if (!(c->u_ub[i] > c->u_lb[i])) { why = "u_ub must exceed u_lb"; return MPCB200_E_INVALID; }
+    // one CTA keeps the instance's resident prefix in shared memory: that bounds the horizon (about (56 + 6 RS + 4 K) N words)
+    WsLayout L;
+    make_layout(c, MAX_OBST, MAX_VP, L);
+    if (max_resident_bytes(L) > MAX_IMG_SMEM)
+    {
+        why = "horizon too long for this row budget: the instance does not fit in shared memory (n = " + std::to_string(c->n) + " needs " +
+              std::to_string(max_resident_bytes(L)) + " bytes of " + std::to_string((size_t)MAX_IMG_SMEM) + ")";
+        return MPCB200_E_UNSUPPORTED;
+    }
     return 0;
 }
 
+template <class K>
+static cudaError_t allow_smem(K kernel) { return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM); }
 
 extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int device, mpcb200_handle** out)
 {
@@ -1125,11 +438,12 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
         return set_err(nullptr, MPCB200_E_NODEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) + "): this solver has no CPU fallback");
     if (device < 0 || device >= ndev) return set_err(nullptr, MPCB200_E_INVALID, "device index out of range");
     h = new mpcb200_handle();
-    h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->kkt_tiles = nullptr; h->ric_tiles = nullptr; h->ev_used = 0;
+    h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->ev_used = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
     h->n_cap = cfg->n; h->d_resample = nullptr; h->d_cm = nullptr; h->cm_cap = 0; h->costmap_ms = 0.0;
-    h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0;
+    h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0; h->has_lines = 0;
+    h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
         cudaError_t e_ = (call);                                                                                   \
@@ -1141,16 +455,8 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     const size_t B = (size_t)max_batch, N = (size_t)cfg->n;
     CKC(cudaMalloc(&h->ws, B * h->L.stride * sizeof(double)));
     CKC(cudaMemsetAsync(h->ws, 0, B * h->L.stride * sizeof(double), h->stream));
-    {
-        const size_t ntiles = (B + TILE - 1) / TILE;
-        CKC(cudaMalloc(&h->kkt_tiles, ntiles * N * KW * TILE * sizeof(double)));
-        h->ric_attempt_stride = ntiles * N * RICW_MAX * TILE;
-        CKC(cudaMalloc(&h->ric_tiles, 2 * h->ric_attempt_stride * sizeof(double)));
-        CKC(cudaMemsetAsync(h->kkt_tiles, 0, ntiles * N * KW * TILE * sizeof(double), h->stream));
-        CKC(cudaMemsetAsync(h->ric_tiles, 0, 2 * h->ric_attempt_stride * sizeof(double), h->stream));
-        h->spec = 0; h->spec_mode = 0; h->refill_every = STREAM_REFILL_EVERY; h->timing_mask = 1u << MPCB200_PHASE_KKT;
-        CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
-    }
+    CKC(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    CKC(cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device));
     CKC(cudaMalloc(&h->d_x0, B * 3 * 8)); CKC(cudaMalloc(&h->d_xf, B * 3 * 8)); CKC(cudaMalloc(&h->d_uprev, B * 2 * 8));
     CKC(cudaMalloc(&h->d_obst, B * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CKC(cudaMalloc(&h->d_obst_count, B * 4));
     CKC(cudaMalloc(&h->d_obst_type, B * MAX_OBST * 4));
@@ -1158,31 +464,18 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_xinit, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_reinit, B));
     CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
     CKC(cudaMalloc(&h->d_kkt, B * 8)); CKC(cudaMalloc(&h->d_upacked, B * (N - 1) * 2 * 8));
-    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8));
-    CKC(cudaMalloc(&h->d_slot_of, B * 4)); CKC(cudaMalloc(&h->d_inst_of_slot, ((B + TILE - 1) / TILE) * TILE * 4));
-    CKC(cudaMalloc(&h->d_counters, 16)); CKC(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
-    CKC(cudaFuncSetAttribute(eval_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(eval_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(linesearch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(linesearch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_IMG_SMEM));
-    CKC(cudaFuncSetAttribute(kkt_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<true>()));
-    CKC(cudaFuncSetAttribute(kkt_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kkt_smem_bytes<false>()));
+    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8)); CKC(cudaMalloc(&h->d_queue, 4));
+    CKC(cudaMalloc(&h->d_counters, CNT_WORDS * 8)); CKC(cudaMemsetAsync(h->d_counters, 0, CNT_WORDS * 8, h->stream));
+    CKC(allow_smem(phase_kernel<false>)); CKC(allow_smem(phase_kernel<true>));
+    CKC(allow_smem(kkt_warp_kernel<false>)); CKC(allow_smem(kkt_warp_kernel<true>));
+    CKC(allow_smem(solve_fused_kernel<false, false>)); CKC(allow_smem(solve_fused_kernel<false, true>));
+    CKC(allow_smem(solve_fused_kernel<true, false>)); CKC(allow_smem(solve_fused_kernel<true, true>));
     CKC(cudaMallocHost(&h->h_nactive, 8));
-    h->nactive_ptr = nullptr;
-    h->only_new = 0; h->stream_cap = 0;
+    h->stream_cap = 0;
     h->s_x0 = h->s_xf = h->s_uprev = h->s_obst = h->s_vp = h->s_useq = h->s_xseq = h->s_dt = h->s_kkt = h->s_upacked = nullptr;
     h->s_obst_count = h->s_obst_type = h->s_vp_count = h->s_status = h->s_iters = nullptr;
-    CKC(cudaMalloc(&h->d_slot_inst, B * 4)); CKC(cudaMalloc(&h->d_stream_counters, 8));
-    CKC(cudaMallocHost(&h->h_stream_counters, 16));
-    CKC(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
-    CKC(cudaEventCreateWithFlags(&h->ev_refill, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->poll_ev[0], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
+    CKC(cudaEventCreate(&h->t0)); CKC(cudaEventCreate(&h->t1));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
     CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
     CKC(cudaMemsetAsync(h->d_flush, 0, h->flush_n * 8, h->stream));
@@ -1201,16 +494,15 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* ptrs[] = {h->ws, h->kkt_tiles, h->ric_tiles, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
-                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_flush, h->d_counters, h->d_slot_of, h->d_inst_of_slot};
+    void* ptrs[] = {h->ws, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
+                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_queue, h->d_flush, h->d_counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* sptrs[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
-                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_slot_inst, h->d_stream_counters, h->d_resample, h->d_cm};
+                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_resample, h->d_cm};
     for (void* p : sptrs) if (p) cudaFree(p);
-    if (h->h_stream_counters) cudaFreeHost(h->h_stream_counters);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
-    cudaStreamDestroy(h->side_stream); cudaEventDestroy(h->ev_refill); cudaEventDestroy(h->ev_ready);
+    cudaEventDestroy(h->poll_ev[0]); cudaEventDestroy(h->poll_ev[1]); cudaEventDestroy(h->t0); cudaEventDestroy(h->t1);
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -1250,66 +542,32 @@ static void ev_collect(mpcb200_handle* h)
     h->ev_used = 0;
 }
 
-static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int first_outer, bool timed)
+// threads of the CTA that owns an instance: one lane per stage up to MAX_GROUP_WARPS warps
+static int group_threads(const mpcb200_handle* h)
 {
-    const int grid4 = grid_for(B, WARPS_PER_CTA);
     const int gw = (h->cfg.n + 31) / 32;
-    const int group_threads = 32 * (gw < MAX_GROUP_WARPS ? gw : MAX_GROUP_WARPS);
-    const int spec = h->spec;
-    // instance image staged in shared memory by the eval / line-search kernels: everything up to the obstacles in use
-    const int m_used = h->has_obst ? ((h->obst_max + 1) & ~1) : 0;
-    const int img_words = h->L.oOBST + MPCB200_OBST_STRIDE * m_used;
-    const size_t img_smem = 16 + (size_t)img_words * 8;
-    if (img_smem > MAX_IMG_SMEM) return set_err(h, MPCB200_E_UNSUPPORTED, "horizon too long: the instance image does not fit in shared memory");
+    return 32 * (gw < MAX_GROUP_WARPS ? gw : MAX_GROUP_WARPS);
+}
+static int image_words(const mpcb200_handle* h) { return resident_words(h->L, h->has_obst ? h->obst_max : 0); }
+
+static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int first_outer, int* n_active, bool timed)
+{
+    const int img_words = image_words(h);
+    const size_t img_smem = IMG_HEAD + (size_t)img_words * 8;
+    if (img_smem > MAX_IMG_SMEM) return set_err(h, MPCB200_E_UNSUPPORTED, "the instance does not fit in shared memory");
     if (timed && ev_begin(h, phase)) return set_err(h, MPCB200_E_CUDA, "cudaEventCreate failed");
-    switch (phase)
+    if (phase == MPCB200_PHASE_KKT)
     {
-        case MPCB200_PHASE_INIT: init_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, force_cold, h->only_new); break;
-        case MPCB200_PHASE_ASSOCIATE: associate_kernel<<<grid4, WARPS_PER_CTA * 32, 0, h->stream>>>(h->cfg, h->L, h->ws, B, h->uprev_dt, first_outer, h->only_new); break;
-        case MPCB200_PHASE_EVAL:
-#define EVAL_LAUNCH(NW, LN) eval_kernel<NW, LN><<<B, NW * 32, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, h->nactive_ptr, img_words)
-            switch (group_threads >> 5)
-            {
-                case 1: if (h->has_lines) EVAL_LAUNCH(1, true); else EVAL_LAUNCH(1, false); break;
-                case 2: if (h->has_lines) EVAL_LAUNCH(2, true); else EVAL_LAUNCH(2, false); break;
-                case 3: if (h->has_lines) EVAL_LAUNCH(3, true); else EVAL_LAUNCH(3, false); break;
-                default: if (h->has_lines) EVAL_LAUNCH(4, true); else EVAL_LAUNCH(4, false); break;
-            }
-#undef EVAL_LAUNCH
-            break;
-        case MPCB200_PHASE_KKT:
-        {
-            const bool ext = h->cfg.variable_dt || h->cfg.xf_fixed[0] || h->cfg.xf_fixed[1] || h->cfg.xf_fixed[2];
-            const int ntiles = (B + TILE - 1) / TILE;
-            const dim3 kgrid(ntiles, spec ? 2 : 1);
-            if (ext) kkt_lane_kernel<true><<<kgrid, 32, kkt_smem_bytes<true>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->ric_attempt_stride, h->d_inst_of_slot, B, spec, h->d_counters);
-            else kkt_lane_kernel<false><<<kgrid, 32, kkt_smem_bytes<false>(), h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->ric_tiles, h->ric_attempt_stride, h->d_inst_of_slot, B, spec, h->d_counters);
-            break;
-        }
-        case MPCB200_PHASE_LINESEARCH:
-            if (h->has_lines) linesearch_kernel<true><<<B, group_threads, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec, img_words);
-            else linesearch_kernel<false><<<B, group_threads, img_smem, h->stream>>>(h->cfg, h->L, h->ws, h->kkt_tiles, h->d_slot_of, B, h->uprev_dt, spec, img_words);
-            break;
-        default: return set_err(h, MPCB200_E_INVALID, "unknown phase");
+        if (kkt_is_ext(h->cfg)) kkt_warp_kernel<true><<<B, 32, kkt_smem_bytes<true>(h->cfg.n), h->stream>>>(h->cfg, h->L, h->ws, B, h->d_counters);
+        else kkt_warp_kernel<false><<<B, 32, kkt_smem_bytes<false>(h->cfg.n), h->stream>>>(h->cfg, h->L, h->ws, B, h->d_counters);
     }
+    else if (phase >= 0 && phase < MPCB200_NUM_PHASES)
+    {
+        if (h->has_lines) phase_kernel<true><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words);
+        else phase_kernel<false><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words);
+    }
+    else return set_err(h, MPCB200_E_INVALID, "unknown phase");
     if (timed) ev_end(h);
-    h->stats.launches_total += 1;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-static int launch_phase_eval(mpcb200_handle* h, int B, int* nactive, bool timed)
-{
-    h->nactive_ptr = nactive;
-    const int rc = launch_phase(h, MPCB200_PHASE_EVAL, B, 0, 0, timed);
-    h->nactive_ptr = nullptr;
-    return rc;
-}
-
-static int launch_regroup(mpcb200_handle* h, int B)
-{
-    const int nslots = ((B + TILE - 1) / TILE) * TILE;
-    regroup_kernel<<<1, 1024, 0, h->stream>>>(h->L, h->ws, B, h->d_slot_of, h->d_inst_of_slot, nslots);
     h->stats.launches_total += 1;
     CK(cudaGetLastError());
     return 0;
@@ -1322,33 +580,42 @@ static int check_batch(mpcb200_handle* h, int B)
     return 0;
 }
 
-static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
-                         const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init, const unsigned char* reinit)
+// which kernel variants a batch needs: line obstacles among the obstacles in use (padding slots are never read)
+static int scan_obstacles(mpcb200_handle* h, size_t B, const mpcb200_obstacles* obst)
+{
+    const size_t M = (size_t)obst->max_per_instance;
+    int lines = 0;
+    for (size_t b = 0; b < B; ++b)
+    {
+        const int cnt = obst->count[b] < (int)M ? obst->count[b] : (int)M;
+        for (int i = 0; i < cnt; ++i) lines |= obst->type[b * M + i] == MPCB200_OBST_LINE;
+    }
+    h->has_lines = lines || h->cfg.enable_dynamic_obstacles || is_midpoint(h->cfg);
+    return 0;
+}
+
+// host -> device copies of the inputs of `B` instances into the compact staging arrays d (batch) or s (queue job)
+struct Staging { double *x0, *xf, *uprev, *obst, *vp, *xinit; int *obst_count, *obst_type, *vp_count; unsigned char* reinit; };
+static int copy_inputs(mpcb200_handle* h, const Staging& d, size_t B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                       const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init, const unsigned char* reinit, InputPtrs* in)
 {
     if (!x0 || !xf) return set_err(h, MPCB200_E_INVALID, "x0 and xf are required");
     const size_t N = (size_t)h->cfg.n;
-    CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(h->d_x0, x0, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_xf, xf, (size_t)B * 3 * 8, cudaMemcpyHostToDevice, h->stream));
-    h->stats.h2d_bytes += (long long)B * 6 * 8;
-    if (u_prev) { CK(cudaMemcpyAsync(h->d_uprev, u_prev, (size_t)B * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)B * 16; }
-    else CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
+    CK(cudaMemcpyAsync(d.x0, x0, B * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d.xf, xf, B * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (long long)(B * 6 * 8);
+    if (u_prev) { CK(cudaMemcpyAsync(d.uprev, u_prev, B * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)(B * 16); }
     h->uprev_dt = u_prev_dt;
     h->has_obst = 0; h->obst_max = 0; h->has_lines = is_midpoint(h->cfg);  // the kernel variants with the rarely used paths compiled in
     if (obst && obst->count && obst->max_per_instance > 0)
     {
         if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
+        if (!obst->type || !obst->params) return set_err(h, MPCB200_E_INVALID, "obstacle types and parameters are required");
         const size_t M = (size_t)obst->max_per_instance;
-        int lines = 0;
-        for (size_t i = 0; i < (size_t)B * M; ++i)
-        {
-            if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
-            lines |= obst->type[i] == MPCB200_OBST_LINE;
-        }
-        h->has_lines = lines || h->cfg.enable_dynamic_obstacles || is_midpoint(h->cfg);
-        CK(cudaMemcpyAsync(h->d_obst_count, obst->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_obst_type, obst->type, (size_t)B * M * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_obst, obst->params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
+        scan_obstacles(h, B, obst);
+        CK(cudaMemcpyAsync(d.obst_count, obst->count, B * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.obst_type, obst->type, B * M * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.obst, obst->params, B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
         h->stats.h2d_bytes += (long long)(B * 4 + B * M * 4 + B * M * MPCB200_OBST_STRIDE * 8);
         h->has_obst = 1; h->obst_max = (int)M;
     }
@@ -1357,21 +624,44 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
     {
         if (vp->max_per_instance > MAX_VP) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 8 via-points per instance");
         const size_t V = (size_t)vp->max_per_instance;
-        CK(cudaMemcpyAsync(h->d_vp_count, vp->count, (size_t)B * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_vp, vp->poses, (size_t)B * V * 3 * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.vp_count, vp->count, B * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(d.vp, vp->poses, B * V * 3 * 8, cudaMemcpyHostToDevice, h->stream));
         h->stats.h2d_bytes += (long long)(B * 4 + B * V * 24);
         h->has_vp = 1; h->vp_max = (int)V;
     }
     h->has_xinit = 0;
-    if (x_init) { CK(cudaMemcpyAsync(h->d_xinit, x_init, (size_t)B * N * 3 * 8, cudaMemcpyHostToDevice, h->stream)); h->has_xinit = 1; h->stats.h2d_bytes += (long long)(B * N * 24); }
+    if (x_init && d.xinit) { CK(cudaMemcpyAsync(d.xinit, x_init, B * N * 3 * 8, cudaMemcpyHostToDevice, h->stream)); h->has_xinit = 1; h->stats.h2d_bytes += (long long)(B * N * 24); }
     h->has_reinit = 0;
-    if (reinit) { CK(cudaMemcpyAsync(h->d_reinit, reinit, (size_t)B, cudaMemcpyHostToDevice, h->stream)); h->has_reinit = 1; h->stats.h2d_bytes += B; }
+    if (reinit && d.reinit) { CK(cudaMemcpyAsync(d.reinit, reinit, B, cudaMemcpyHostToDevice, h->stream)); h->has_reinit = 1; h->stats.h2d_bytes += (long long)B; }
+    in->x0 = d.x0; in->xf = d.xf; in->u_prev = u_prev ? d.uprev : nullptr;
+    in->obst_count = h->has_obst ? d.obst_count : nullptr; in->obst_type = d.obst_type; in->obst_params = d.obst; in->obst_max = h->obst_max;
+    in->vp_count = h->has_vp ? d.vp_count : nullptr; in->vp_poses = d.vp; in->vp_max = h->vp_max;
+    in->x_init = h->has_xinit ? d.xinit : nullptr;
+    in->reinit = h->has_reinit ? d.reinit : nullptr;
+    return 0;
+}
+static Staging batch_staging(mpcb200_handle* h) { return Staging{h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_vp, h->d_xinit, h->d_obst_count, h->d_obst_type, h->d_vp_count, h->d_reinit}; }
+static InputPtrs batch_inputs(mpcb200_handle* h, bool with_uprev)
+{
     InputPtrs in;
-    in.x0 = h->d_x0; in.xf = h->d_xf; in.u_prev = h->d_uprev;
+    in.x0 = h->d_x0; in.xf = h->d_xf; in.u_prev = with_uprev ? h->d_uprev : nullptr;
     in.obst_count = h->has_obst ? h->d_obst_count : nullptr; in.obst_type = h->d_obst_type; in.obst_params = h->d_obst; in.obst_max = h->obst_max;
     in.vp_count = h->has_vp ? h->d_vp_count : nullptr; in.vp_poses = h->d_vp; in.vp_max = h->vp_max;
     in.x_init = h->has_xinit ? h->d_xinit : nullptr;
     in.reinit = h->has_reinit ? h->d_reinit : nullptr;
+    return in;
+}
+
+static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                         const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init, const unsigned char* reinit)
+{
+    CK(cudaSetDevice(h->device));
+    InputPtrs in;
+    if (!u_prev) CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
+    int rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit, &in);
+    if (rc) return rc;
+    // the instance blocks get the inputs as well: the kernel-level API (phase kernels) works on the blocks
+    in.u_prev = h->d_uprev;
     scatter_inputs_kernel<<<grid_for(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, h->stream>>>(h->L, h->ws, B, in);
     h->stats.launches_total += 1;
     CK(cudaGetLastError());
@@ -1379,25 +669,47 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
     return 0;
 }
 
-// the solve proper: INIT, then outer_iterations x (ASSOCIATE, interior-point iterations)
-static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_time_s)
+// ---- the solve: one launch of the persistent kernel over a queue of `total` instances ----
+static int launch_fused(mpcb200_handle* h, int total, int queue_mode, int force_cold, const InputPtrs& in, const OutputPtrs& out)
 {
-    cudaEvent_t t0, t1;
-    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
-    CK(cudaEventRecord(t0, h->stream));
+    FusedArgs a;
+    a.ws = h->ws; a.in = in; a.out = out; a.total = total; a.queue_mode = queue_mode; a.force_cold = force_cold; a.uprev_dt = h->uprev_dt;
+    a.img_words = image_words(h); a.queue = h->d_queue; a.counters = h->d_counters;
+    const size_t smem = IMG_HEAD + (size_t)a.img_words * 8;
+    if (smem > MAX_IMG_SMEM) return set_err(h, MPCB200_E_UNSUPPORTED, "the instance does not fit in shared memory");
+    const int threads = group_threads(h);
+    const bool ext = kkt_is_ext(h->cfg);
+    int per_sm = 0;
+#define FUSED_DO(LN, EX)                                                                                                       \
+    do {                                                                                                                       \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_fused_kernel<LN, EX>, threads, smem));                 \
+        if (per_sm < 1) return set_err(h, MPCB200_E_UNSUPPORTED, "the solve kernel does not fit on an SM with this configuration"); \
+        const int grid = total < per_sm * h->num_sms ? total : per_sm * h->num_sms;                                            \
+        h->fused_grid = grid;                                                                                                  \
+        CK(cudaMemsetAsync(h->d_queue, 0, 4, h->stream));                                                                      \
+        solve_fused_kernel<LN, EX><<<grid, threads, smem, h->stream>>>(h->cfg, h->L, a);                                       \
+    } while (0)
+    if (h->has_lines) { if (ext) FUSED_DO(true, true); else FUSED_DO(true, false); }
+    else { if (ext) FUSED_DO(false, true); else FUSED_DO(false, false); }
+#undef FUSED_DO
+    h->stats.launches_total += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// the phased form of the same solve (MPCB200_OPT_SOLVE_MODE 1): one kernel per phase, the host queues the iterations
+static int solve_phased(mpcb200_handle* h, int B, int force_cold)
+{
     const unsigned tm = h->timing_mask;
     auto timed = [&](int phase) { return ((tm >> phase) & 1u) != 0; };
-    // small batches leave most SMs idle in the KKT phase: run both regularisation attempts of an iteration side by side
-    h->spec = h->spec_mode == 0 ? ((2 * ((B + TILE - 1) / TILE) <= h->num_sms) ? 1 : 0) : (h->spec_mode == 2 ? 1 : 0);
-    int rc = launch_phase(h, MPCB200_PHASE_INIT, B, force_cold, 0, timed(MPCB200_PHASE_INIT));
+    int rc = launch_phase(h, MPCB200_PHASE_INIT, B, force_cold, 0, nullptr, timed(MPCB200_PHASE_INIT));
     if (rc) return rc;
     const int outer = h->cfg.outer_iterations > 0 ? h->cfg.outer_iterations : 1;
     for (int oi = 0; oi < outer; ++oi)
     {
-        if ((rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, oi == 0, timed(MPCB200_PHASE_ASSOCIATE)))) return rc;
+        if ((rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, oi == 0, nullptr, timed(MPCB200_PHASE_ASSOCIATE)))) return rc;
         // The number of unfinished instances is polled every POLL iterations, one poll behind: the host keeps queueing
-        // iterations while the count of the previous poll travels back, so the stream never drains (a finished
-        // instance makes every kernel an immediate no-op, so the few surplus iterations are free).
+        // iterations while the count of the previous poll travels back (a finished instance makes every kernel a no-op).
         const int POLL = 4;
         int pending = -1;  // slot of the poll in flight
         bool done = false;
@@ -1406,8 +718,7 @@ static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_
             const bool poll = (it % POLL == POLL - 1) || it == h->cfg.max_iter;
             const int slot = (it / POLL) & 1;
             if (poll) CK(cudaMemsetAsync(h->d_nactive + slot, 0, 4, h->stream));
-            if (it % REGROUP_EVERY == 0 && (rc = launch_regroup(h, B))) return rc;  // slots stay valid in between (finished lanes idle)
-            if ((rc = launch_phase_eval(h, B, poll ? h->d_nactive + slot : nullptr, timed(MPCB200_PHASE_EVAL)))) return rc;
+            if ((rc = launch_phase(h, MPCB200_PHASE_EVAL, B, 0, 0, poll ? h->d_nactive + slot : nullptr, timed(MPCB200_PHASE_EVAL)))) return rc;
             if (poll)
             {
                 CK(cudaMemcpyAsync(h->h_nactive + slot, h->d_nactive + slot, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1420,22 +731,49 @@ static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_
                 pending = slot;
             }
             if (it == h->cfg.max_iter || done) break;
-            if ((rc = launch_phase(h, MPCB200_PHASE_KKT, B, 0, 0, timed(MPCB200_PHASE_KKT)))) return rc;
-            if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, timed(MPCB200_PHASE_LINESEARCH)))) return rc;
+            if ((rc = launch_phase(h, MPCB200_PHASE_KKT, B, 0, 0, nullptr, timed(MPCB200_PHASE_KKT)))) return rc;
+            if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, nullptr, timed(MPCB200_PHASE_LINESEARCH)))) return rc;
         }
     }
     OutputPtrs o{h->d_useq, h->d_xseq, h->d_dt, h->d_status, h->d_kkt, h->d_iters, h->d_upacked};
     gather_outputs_kernel<<<grid_for(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, h->stream>>>(h->L, h->ws, B, o);
     h->stats.launches_total += 1;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(t1, h->stream));
+    return 0;
+}
+
+// fold the cycle counters of the fused kernel into the per-phase statistics: average time a CTA spent in each phase
+static int collect_fused_counters(mpcb200_handle* h)
+{
+    unsigned long long cnt[CNT_WORDS];
+    CK(cudaMemcpy(cnt, h->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    const double per_cta = h->fused_grid > 0 ? 1.0 / ((double)h->fused_grid * (double)h->clock_khz) : 0.0;  // cycles -> ms per CTA
+    for (int p = 0; p < MPCB200_NUM_PHASES; ++p) h->stats.ms[p] += (double)cnt[CNT_CYC + p] * per_cta;
+    h->stats.kkt_instances += (long long)cnt[CNT_KKT_INST];
+    h->stats.kkt_sweeps += (long long)cnt[CNT_KKT_SWEEPS];
+    h->stats.launches[MPCB200_PHASE_KKT] += (long long)cnt[CNT_KKT_INST];
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(cnt), h->stream));
+    return 0;
+}
+
+static int solve_device(mpcb200_handle* h, int B, int force_cold, double* solve_time_s)
+{
+    CK(cudaEventRecord(h->t0, h->stream));
+    int rc;
+    if (h->solve_mode == 1) rc = solve_phased(h, B, force_cold);
+    else
+    {
+        OutputPtrs o{h->d_useq, h->d_xseq, h->d_dt, h->d_status, h->d_kkt, h->d_iters, h->d_upacked};
+        rc = launch_fused(h, B, 0, force_cold, batch_inputs(h, true), o);
+    }
+    if (rc) return rc;
+    CK(cudaEventRecord(h->t1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, t0, t1));
+    CK(cudaEventElapsedTime(&ms, h->t0, h->t1));
     if (solve_time_s) *solve_time_s = ms * 1e-3;
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
     ev_collect(h);
-    return 0;
+    return collect_fused_counters(h);
 }
 
 static int fetch_results(mpcb200_handle* h, int B, double* u_seq, double* x_seq, double* dt_out, int* status, double* kkt_err, int* iters)
@@ -1451,13 +789,14 @@ static int fetch_results(mpcb200_handle* h, int B, double* u_seq, double* x_seq,
     return 0;
 }
 
-// ---- streaming solve: `total` instances through the pool of max_batch slots (continuous batching) ----------------------
+// ---- queue solve: `total` cold instances through the persistent kernel (continuous batching) ----------------------
 static int stream_reserve(mpcb200_handle* h, size_t total)
 {
     if (total <= h->stream_cap) return 0;
     void* old[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
                    h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters};
     for (void* p : old) if (p) cudaFree(p);
+    h->stream_cap = 0;
     const size_t N = (size_t)h->n_cap, T = total;  // sized for the largest horizon the handle can be resampled to
     CK(cudaMalloc(&h->s_x0, T * 3 * 8)); CK(cudaMalloc(&h->s_xf, T * 3 * 8)); CK(cudaMalloc(&h->s_uprev, T * 2 * 8));
     CK(cudaMalloc(&h->s_obst, T * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CK(cudaMalloc(&h->s_obst_count, T * 4)); CK(cudaMalloc(&h->s_obst_type, T * MAX_OBST * 4));
@@ -1474,121 +813,22 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
 {
     if (!h) return MPCB200_E_INVALID;
     if (total < 1 || !x0 || !xf) return set_err(h, MPCB200_E_INVALID, "total >= 1, x0 and xf are required");
-    if (h->cfg.outer_iterations > 1) return set_err(h, MPCB200_E_UNSUPPORTED, "streaming runs one outer iteration per instance");
     CK(cudaSetDevice(h->device));
     int rc = stream_reserve(h, (size_t)total);
     if (rc) return rc;
     const size_t T = (size_t)total, N = (size_t)h->cfg.n;
-    const int B = total < h->max_batch ? total : h->max_batch;  // slots in use
-    // ---- inputs of the whole job ----
-    CK(cudaMemcpyAsync(h->s_x0, x0, T * 3 * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->s_xf, xf, T * 3 * 8, cudaMemcpyHostToDevice, h->stream));
-    h->stats.h2d_bytes += (long long)(T * 6 * 8);
-    if (u_prev) { CK(cudaMemcpyAsync(h->s_uprev, u_prev, T * 2 * 8, cudaMemcpyHostToDevice, h->stream)); h->stats.h2d_bytes += (long long)(T * 16); }
-    h->uprev_dt = u_prev_dt;
-    h->has_obst = 0; h->obst_max = 0; h->has_lines = is_midpoint(h->cfg); h->has_vp = 0; h->vp_max = 0; h->has_xinit = 0; h->has_reinit = 0;
-    if (obst && obst->count && obst->max_per_instance > 0)
-    {
-        if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
-        const size_t M = (size_t)obst->max_per_instance;
-        int lines = 0;
-        for (size_t i = 0; i < T * M; ++i)
-        {
-            if (obst->type[i] < MPCB200_OBST_POINT || obst->type[i] > MPCB200_OBST_LINE) return set_err(h, MPCB200_E_INVALID, "unknown obstacle type");
-            lines |= obst->type[i] == MPCB200_OBST_LINE;
-        }
-        h->has_lines = lines || h->cfg.enable_dynamic_obstacles || is_midpoint(h->cfg);
-        CK(cudaMemcpyAsync(h->s_obst_count, obst->count, T * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->s_obst_type, obst->type, T * M * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->s_obst, obst->params, T * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyHostToDevice, h->stream));
-        h->stats.h2d_bytes += (long long)(T * 4 + T * M * 4 + T * M * MPCB200_OBST_STRIDE * 8);
-        h->has_obst = 1; h->obst_max = (int)M;
-    }
-    if (vp && vp->count && vp->max_per_instance > 0)
-    {
-        if (vp->max_per_instance > MAX_VP) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 8 via-points per instance");
-        const size_t V = (size_t)vp->max_per_instance;
-        CK(cudaMemcpyAsync(h->s_vp_count, vp->count, T * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->s_vp, vp->poses, T * V * 3 * 8, cudaMemcpyHostToDevice, h->stream));
-        h->stats.h2d_bytes += (long long)(T * 4 + T * V * 24);
-        h->has_vp = 1; h->vp_max = (int)V;
-    }
     InputPtrs in;
-    in.x0 = h->s_x0; in.xf = h->s_xf; in.u_prev = u_prev ? h->s_uprev : nullptr;
-    in.obst_count = h->has_obst ? h->s_obst_count : nullptr; in.obst_type = h->s_obst_type; in.obst_params = h->s_obst; in.obst_max = h->obst_max;
-    in.vp_count = h->has_vp ? h->s_vp_count : nullptr; in.vp_poses = h->s_vp; in.vp_max = h->vp_max;
-    in.x_init = nullptr; in.reinit = nullptr;
+    Staging s{h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, nullptr, h->s_obst_count, h->s_obst_type, h->s_vp_count, nullptr};
+    if ((rc = copy_inputs(h, s, T, x0, xf, u_prev, u_prev_dt, obst, vp, nullptr, nullptr, &in))) return rc;
     OutputPtrs o{h->s_useq, h->s_xseq, h->s_dt, h->s_status, h->s_kkt, h->s_iters, h->s_upacked};
-    StreamState st{h->d_slot_inst, h->d_stream_counters, total};
-    // ---- the pool ----
-    cudaEvent_t t0, t1;
-    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
-    CK(cudaEventRecord(t0, h->stream));
-    const unsigned tm = h->timing_mask;
-    auto timed = [&](int phase) { return ((tm >> phase) & 1u) != 0; };
-    h->spec = h->spec_mode == 0 ? ((2 * ((B + TILE - 1) / TILE) <= h->num_sms) ? 1 : 0) : (h->spec_mode == 2 ? 1 : 0);
-    h->B = B;
-    stream_begin_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, B, st);
-    h->stats.launches_total += 1;
-    const int grid4 = grid_for(B, WARPS_PER_CTA);
-    const int refill_every = h->refill_every;
-    const long long max_rounds = ((long long)(total + B - 1) / B + 2) * (h->cfg.max_iter + 2 + 3 * refill_every);
-    const int POLL = 4;
-    int pending = -1;
-    bool done = false;
-    h->only_new = 1;
-    const cudaStream_t main_stream = h->stream;
-    for (long long it = 0; it < max_rounds && !done; ++it)
-    {
-        if (it % refill_every == 0)
-        {
-            // refill on the main stream (after the side work of the previous round); the cold initialisation and the
-            // association of the refilled slots then run on the side stream, beside the next iterations of the other slots
-            if (it > 0) CK(cudaStreamWaitEvent(main_stream, h->ev_ready, 0));
-            stream_refill_kernel<<<grid4, WARPS_PER_CTA * 32, 0, main_stream>>>(h->L, h->ws, B, in, o, st);
-            h->stats.launches_total += 1;
-            CK(cudaEventRecord(h->ev_refill, main_stream));
-            CK(cudaStreamWaitEvent(h->side_stream, h->ev_refill, 0));
-            h->stream = h->side_stream;
-            rc = launch_phase(h, MPCB200_PHASE_INIT, B, 0, 0, timed(MPCB200_PHASE_INIT));
-            if (!rc) rc = launch_phase(h, MPCB200_PHASE_ASSOCIATE, B, 0, 1, timed(MPCB200_PHASE_ASSOCIATE));
-            h->stream = main_stream;
-            if (rc) break;
-            CK(cudaEventRecord(h->ev_ready, h->side_stream));
-            if ((it / refill_every) % POLL == POLL - 1)
-            {
-                // results handed over so far, polled one poll behind (see solve_device)
-                const int slot = (int)((it / refill_every / POLL) & 1);
-                CK(cudaMemcpyAsync(h->h_stream_counters + 2 * slot, h->d_stream_counters, 8, cudaMemcpyDeviceToHost, h->stream));
-                CK(cudaEventRecord(h->poll_ev[slot], h->stream));
-                if (pending >= 0)
-                {
-                    CK(cudaEventSynchronize(h->poll_ev[pending]));
-                    if (h->h_stream_counters[2 * pending + 1] >= total) done = true;
-                }
-                pending = slot;
-            }
-        }
-        if (done) break;
-        if (it % REGROUP_EVERY == 0 && (rc = launch_regroup(h, B))) break;
-        if ((rc = launch_phase_eval(h, B, nullptr, timed(MPCB200_PHASE_EVAL)))) break;
-        if ((rc = launch_phase(h, MPCB200_PHASE_KKT, B, 0, 0, timed(MPCB200_PHASE_KKT)))) break;
-        if ((rc = launch_phase(h, MPCB200_PHASE_LINESEARCH, B, 0, 0, timed(MPCB200_PHASE_LINESEARCH)))) break;
-    }
-    h->only_new = 0;
-    h->stream = main_stream;
-    CK(cudaStreamWaitEvent(main_stream, h->ev_ready, 0));
-    if (rc) return rc;
-    CK(cudaEventRecord(t1, h->stream));
+    CK(cudaEventRecord(h->t0, h->stream));
+    if ((rc = launch_fused(h, total, 1, 1, in, o))) return rc;
+    CK(cudaEventRecord(h->t1, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    int cnt[2];
-    CK(cudaMemcpy(cnt, h->d_stream_counters, 8, cudaMemcpyDeviceToHost));
-    if (cnt[1] < total) return set_err(h, MPCB200_E_CUDA, "streaming solve ended before every instance was handed over");
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, t0, t1));
+    CK(cudaEventElapsedTime(&ms, h->t0, h->t1));
     if (solve_time_s) *solve_time_s = ms * 1e-3;
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
-    ev_collect(h);
+    if ((rc = collect_fused_counters(h))) return rc;
     // ---- results of the whole job ----
     if (u_seq) { CK(cudaMemcpyAsync(u_seq, h->s_useq, T * N * 16, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * N * 16); }
     if (x_seq) { CK(cudaMemcpyAsync(x_seq, h->s_xseq, T * N * 24, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * N * 24); }
@@ -1596,9 +836,6 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
     if (status) { CK(cudaMemcpyAsync(status, h->s_status, T * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * 4); }
     if (kkt_err) { CK(cudaMemcpyAsync(kkt_err, h->s_kkt, T * 8, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * 8); }
     if (iters) { CK(cudaMemcpyAsync(iters, h->s_iters, T * 4, cudaMemcpyDeviceToHost, h->stream)); h->stats.d2h_bytes += (long long)(T * 4); }
-    CK(cudaStreamSynchronize(h->stream));
-    // the pool's workspaces now hold arbitrary instances of the job: the next step_batch must start cold
-    reset_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->L, h->ws, B, nullptr);
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1610,7 +847,19 @@ extern "C" int mpcb200_step_batch(mpcb200_handle* h, int B, const double* x0, co
 {
     int rc = check_batch(h, B);
     if (rc) return rc;
-    if ((rc = upload_inputs(h, B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit))) return rc;
+    CK(cudaSetDevice(h->device));
+    if (h->solve_mode == 1)
+    {
+        if ((rc = upload_inputs(h, B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit))) return rc;
+    }
+    else
+    {
+        // fused mode: the solve kernel reads the compact arrays itself, the blocks only carry the warm state
+        InputPtrs in;
+        if (!u_prev) CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
+        if ((rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit, &in))) return rc;
+        h->B = B;
+    }
     if ((rc = solve_device(h, B, 0, solve_time_s))) return rc;
     return fetch_results(h, B, u_seq, x_seq, dt_out, status, kkt_err, iters);
 }
@@ -1698,7 +947,7 @@ static int field_info(const mpcb200_handle* h, int field, int* off, int* cnt)
         case MPCB200_F_NU: *off = L.oNU; *cnt = 3; return 0;
         case MPCB200_F_S: *off = L.oS; *cnt = L.RS; return 0;
         case MPCB200_F_LAM: *off = L.oLAM; *cnt = L.RS; return 0;
-        case MPCB200_F_KKT: *off = 0; *cnt = KW; return 0;
+        case MPCB200_F_KKT: *off = L.oKKT; *cnt = KW; return 0;
         case MPCB200_F_STEP: *off = L.oSTEP; *cnt = 8; return 0;
         case MPCB200_F_SCAL: *off = L.oSCAL; *cnt = MPCB200_SCAL_WORDS; return 0;
         case MPCB200_F_OBSIDX: *off = L.oOBS; *cnt = L.K > 0 ? L.K : 1; return 0;
@@ -1721,20 +970,13 @@ extern "C" int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst)
     CK(cudaSetDevice(h->device));
     const int N = h->L.N;
     if (field == MPCB200_F_KKT)
-    {   // device layout: 32-instance interleaved tiles [tile][k][42][32]; the API presents [B][42][N]
-        const size_t ntiles = ((size_t)B + TILE - 1) / TILE, tw = (size_t)N * KW * TILE;
-        std::vector<double> tmp(ntiles * tw);
-        std::vector<int> slot(B);
-        CK(cudaMemcpyAsync(tmp.data(), h->kkt_tiles, tmp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(slot.data(), h->d_slot_of, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    {   // device layout: stage records [k][RSTR] inside the instance block; the API presents [B][42][N]
+        std::vector<double> tmp((size_t)B * N * RSTR);
+        CK(cudaMemcpy2DAsync(tmp.data(), (size_t)N * RSTR * 8, h->ws + off, (size_t)h->L.stride * 8, (size_t)N * RSTR * 8, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         for (int b = 0; b < B; ++b)
-        {
-            const int sl = slot[b];
             for (int k = 0; k < N; ++k)
-                for (int f = 0; f < KW; ++f)
-                    dst[((size_t)b * KW + f) * N + k] = tmp[(size_t)(sl / TILE) * tw + ((size_t)k * KW + f) * TILE + (sl % TILE)];
-        }
+                for (int f = 0; f < KW; ++f) dst[((size_t)b * KW + f) * N + k] = tmp[((size_t)b * N + k) * RSTR + f];
         return 0;
     }
     const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * N;
@@ -1752,15 +994,11 @@ extern "C" int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const doubl
     const int N = h->L.N;
     if (field == MPCB200_F_KKT)
     {
-        const size_t ntiles = ((size_t)B + TILE - 1) / TILE, tw = (size_t)N * KW * TILE;
-        std::vector<double> tmp(ntiles * tw, 0.0);
-        std::vector<int> slot(B);
-        CK(cudaMemcpy(slot.data(), h->d_slot_of, (size_t)B * 4, cudaMemcpyDeviceToHost));
+        std::vector<double> tmp((size_t)B * N * RSTR, 0.0);
         for (int b = 0; b < B; ++b)
             for (int k = 0; k < N; ++k)
-                for (int f = 0; f < KW; ++f)
-                    tmp[(size_t)(slot[b] / TILE) * tw + ((size_t)k * KW + f) * TILE + (slot[b] % TILE)] = src[((size_t)b * KW + f) * N + k];
-        CK(cudaMemcpyAsync(h->kkt_tiles, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, h->stream));
+                for (int f = 0; f < KW; ++f) tmp[((size_t)b * N + k) * RSTR + f] = src[((size_t)b * KW + f) * N + k];
+        CK(cudaMemcpy2DAsync(h->ws + off, (size_t)h->L.stride * 8, tmp.data(), (size_t)N * RSTR * 8, (size_t)N * RSTR * 8, (size_t)B, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
@@ -1775,9 +1013,7 @@ extern "C" int mpcb200_run_phase(mpcb200_handle* h, int phase, int B)
     int rc = check_batch(h, B);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
-    h->spec = 0;  // single phases run the plain serial KKT attempts
-    if (phase == MPCB200_PHASE_EVAL && (rc = launch_regroup(h, B))) return rc;
-    if ((rc = launch_phase(h, phase, B, 0, 1, true))) return rc;
+    if ((rc = launch_phase(h, phase, B, 0, 1, nullptr, true))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     ev_collect(h);
     return 0;
@@ -1795,8 +1031,7 @@ extern "C" int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream)
 extern "C" int mpcb200_set_option(mpcb200_handle* h, int option, int value)
 {
     if (!h) return MPCB200_E_INVALID;
-    if (option == MPCB200_OPT_KKT_ATTEMPTS && value >= 0 && value <= 2) { h->spec_mode = value; return 0; }
-    if (option == MPCB200_OPT_STREAM_REFILL_EVERY && value >= 1 && value <= 16) { h->refill_every = value; return 0; }
+    if (option == MPCB200_OPT_SOLVE_MODE && value >= 0 && value <= 1) { h->solve_mode = value; return 0; }
     return set_err(h, MPCB200_E_INVALID, "unknown option or value");
 }
 
@@ -1811,24 +1046,20 @@ extern "C" int mpcb200_time_phase(mpcb200_handle* h, int phase, int B, int reps,
 {
     int rc = check_batch(h, B);
     if (rc) return rc;
-    h->spec = 0;
     if (reps < 1) reps = 1;
     CK(cudaSetDevice(h->device));
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     double total = 0.0;
     for (int r = 0; r < reps; ++r)
     {
         if (flush_l2) { flush_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_n); CK(cudaGetLastError()); }
-        CK(cudaEventRecord(a, h->stream));
-        if ((rc = launch_phase(h, phase, B, 0, 1, false))) return rc;
-        CK(cudaEventRecord(b, h->stream));
+        CK(cudaEventRecord(h->t0, h->stream));
+        if ((rc = launch_phase(h, phase, B, 0, 1, nullptr, false))) return rc;
+        CK(cudaEventRecord(h->t1, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, a, b));
+        CK(cudaEventElapsedTime(&ms, h->t0, h->t1));
         total += ms;
     }
-    cudaEventDestroy(a); cudaEventDestroy(b);
     if (ms_per_launch) *ms_per_launch = total / reps;
     return 0;
 }
@@ -1837,12 +1068,11 @@ extern "C" int mpcb200_stats_get(const mpcb200_handle* hc, mpcb200_stats* out)
 {
     mpcb200_handle* h = const_cast<mpcb200_handle*>(hc);
     if (!h || !out) return MPCB200_E_INVALID;
-    unsigned long long cnt[2] = {0, 0};
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(cnt, h->d_counters, 16, cudaMemcpyDeviceToHost));
-    h->stats.kkt_instances = (long long)cnt[0];
-    h->stats.kkt_sweeps = (long long)cnt[1];
+    int rc = collect_fused_counters(h);   // also picks up the counters of phase-wise KKT launches
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
     *out = h->stats;
     return 0;
 }
@@ -1851,7 +1081,7 @@ extern "C" int mpcb200_stats_reset(mpcb200_handle* h)
     if (!h) return MPCB200_E_INVALID;
     memset(&h->stats, 0, sizeof(h->stats));
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
+    CK(cudaMemsetAsync(h->d_counters, 0, CNT_WORDS * 8, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }

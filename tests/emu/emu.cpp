@@ -1,6 +1,6 @@
 // emu.cpp -- CPU WARP EMULATOR of the device code (TEST INFRASTRUCTURE, not product code).
 //
-// Compiles the SAME host/device headers that the CUDA kernels are made of (mpc_core.h, mpc_stage.h, mpc_riccati_lane.h,
+// Compiles the SAME host/device headers that the CUDA kernels are made of (mpc_core.h, mpc_stage.h, mpc_riccati_warp.h,
 // mpc_layout.h) with g++ and replays the kernels' warp-level orchestration (lane loops, reductions, passes) serially
 // for ONE instance.  Purpose: `-m "not gpu"` tests can check the device algorithm (stage bodies, Riccati task tables,
 // line search) against the oracle on a box without a GPU.  It is never loaded by the product package; the product
@@ -10,22 +10,29 @@
 #include <string.h>
 
 #include "../../mpc_local_planner_b200/csrc/mpc_core.h"
-#include "../../mpc_local_planner_b200/csrc/mpc_riccati_lane.h"
+#include "../../mpc_local_planner_b200/csrc/mpc_riccati_warp.h"
 #include "../../mpc_local_planner_b200/csrc/mpc_stage.h"
 #include "../../mpc_local_planner_b200/csrc/mpc_layout.h"
 
-#define EMU_SLOT 5  /* the emulated instance sits in lane slot 5 of its tile (catches tile-indexing bugs) */
-static inline double* emu_kb(const WsLayout& L, double* W) { return W + L.stride + EMU_SLOT; }
-static inline double* emu_rb(const WsLayout& L, double* W) { return W + L.stride + (size_t)L.N * KW * TILE + EMU_SLOT; }
+// serial replay of a warp: every "phase" between two warp barriers runs lane after lane on 32 lane states
+template <bool EXT>
+struct SerialWarp
+{
+    RwLane<EXT> ls[32];
+    template <class F> void each(const F& f) { for (int l = 0; l < 32; ++l) f(l, ls[l]); }
+    void sync() {}
+    bool all(bool p) const { return p; }   // the driver only votes on values that are the same in every lane
+    void shift_up(int d) { for (int l = 31; l >= d; --l) ls[l].in = ls[l - d].out; }
+};
 
 extern "C" {
 
-// words of the emulator buffer: instance block + one KKT tile + one gains tile
+// words of the emulator buffer: one instance block
 long long emu_stride(const Cfg* c)
 {
     WsLayout L;
     make_layout(c, MAX_OBST, MAX_VP, L);
-    return (long long)L.stride + (long long)L.N * KW * TILE + (long long)L.N * RICW_MAX * TILE;
+    return (long long)L.stride;
 }
 
 int emu_field_offset(const Cfg* c, int field, int* cnt)
@@ -39,7 +46,7 @@ int emu_field_offset(const Cfg* c, int field, int* cnt)
         case MPCB200_F_NU: *cnt = 3; return L.oNU;
         case MPCB200_F_S: *cnt = L.RS; return L.oS;
         case MPCB200_F_LAM: *cnt = L.RS; return L.oLAM;
-        case MPCB200_F_KKT: *cnt = KW; return (int)L.stride + EMU_SLOT;  /* tile: element (k,f) at ((k*42+f)*32) */
+        case MPCB200_F_KKT: *cnt = KW; return L.oKKT;  /* records [k][RSTR]: element (k, f) at k * RSTR + f */
         case MPCB200_F_STEP: *cnt = 8; return L.oSTEP;
         case MPCB200_F_SCAL: *cnt = MPCB200_SCAL_WORDS; return L.oSCAL;
         case MPCB200_F_OBSIDX: *cnt = L.K > 0 ? L.K : 1; return L.oOBS;
@@ -81,7 +88,7 @@ void emu_init(const Cfg* cp, double* W, int force_cold)
     const bool cold = force_cold || ASC(MPCB200_SC_COLD) != 0.0 || AIN(IN_REINIT) != 0.0;
     if (cold)
     {
-        for (int k = 0; k < N; ++k) init_cold_stage(c, L, W, k);
+        for (int k = 0; k < N; ++k) init_cold_stage(c, L, W, k, W + L.oXINIT);
         bump_select_serial(c, L, W);
         ASC(MPCB200_SC_DT) = c.dt_ref;
         ASC(MPCB200_SC_COLD) = 2.0;
@@ -173,21 +180,15 @@ int emu_eval(const Cfg* cp, double* W, double uprev_dt)
     for (int l = 0; l < 32; ++l)
     {
         evalacc_init(a[l]);
-        for (int k = l; k < N; k += 32) eval_stage(c, L, W, W, emu_kb(L, W), uprev_dt, k, a[l]);
+        for (int k = l; k < N; k += 32) eval_stage(c, L, W, W, uprev_dt, k, a[l]);
     }
     reduce_eval(a);
     int fin = 0;
     const double mu = eval_finish(c, L, W, a[0], true, &fin);
     if (fin) return 1;
-    for (int k = 0; k < N; ++k) eval_finalize_stage(L, W, emu_kb(L, W), k, mu);
+    for (int k = 0; k < N; ++k) eval_finalize_stage(L, W, k, mu);
     return 0;
 }
-
-struct EmuStep
-{
-    double* W; int oSTEP; int N;
-    void operator()(int k, int c, double v) const { W[oSTEP + c * N + k] = v; }
-};
 
 int emu_kkt(const Cfg* cp, double* W)
 {
@@ -196,26 +197,22 @@ int emu_kkt(const Cfg* cp, double* W)
     make_layout(cp, MAX_OBST, MAX_VP, L);
     const int N = L.N;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return 1;
-    PlainFeed feed{TileRec{emu_kb(L, W)}, TileRic{emu_rb(L, W)}};
-    EmuStep step{W, L.oSTEP, N};
-    const bool ext = c.variable_dt || c.xf_fixed[0] || c.xf_fixed[1] || c.xf_fixed[2];
     double ddt = 0.0, delta = 0.0;
     int nreg = 0, ok;
-    if (ext) ok = riccati_solve_lane<true>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), 0, MAX_INERTIA_TRIES, &ddt, &delta, &nreg);
-    else ok = riccati_solve_lane<false>(c, N, feed, step, true, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), 0, MAX_INERTIA_TRIES, &ddt, &delta, &nreg);
-    ASC(MPCB200_SC_NREG) += (double)nreg;
-    if (!ok && delta <= MAX_DELTA)
+    if (kkt_is_ext(c))
     {
-        ASC(MPCB200_SC_DELTA_LAST) = 3.0 * delta;
-        ASC(MPCB200_SC_DEFER) = 1.0;
-        return 0;
+        SerialWarp<true> ex;
+        kkt_warp_setup<true>(ex, c.variable_dt);
+        ok = kkt_warp_solve<true>(ex, c, N, W + L.oKKT, W + L.oMM, W + L.oSTEP, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
     }
-    if (!ok) { ASC(MPCB200_SC_STATUS) = (double)MPCB200_STATUS_NUMERICAL_ERROR; return 1; }
-    ASC(MPCB200_SC_DEFER) = 0.0;
-    ASC(MPCB200_SC_DDT) = ddt;
-    ASC(MPCB200_SC_DELTA) = delta;
-    ASC(MPCB200_SC_DELTA_LAST) = delta;
-    return 0;
+    else
+    {
+        SerialWarp<false> ex;
+        kkt_warp_setup<false>(ex, c.variable_dt);
+        ok = kkt_warp_solve<false>(ex, c, N, W + L.oKKT, W + L.oMM, W + L.oSTEP, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST), &ddt, &delta, &nreg);
+    }
+    kkt_store_outcome(W + L.oSCAL, ok, ddt, delta, nreg);
+    return ASC(MPCB200_SC_STATUS) >= 0.0 ? 1 : 0;
 }
 
 void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
@@ -234,7 +231,7 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
     {
         LsAcc t;
         lsacc_init(t);
-        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, W, emu_kb(L, W), uprev_dt, k, t, hist);
+        for (int k = l; k < N; k += 32) ls_stage_steps(c, L, W, W, uprev_dt, k, t, hist);
         a.a_d = fmin(a.a_d, t.a_d);
         a.dphi_bar += t.dphi_bar; a.curv += t.curv; a.dJ += t.dJ;
     }
@@ -266,6 +263,8 @@ void emu_linesearch(const Cfg* cp, double* W, double uprev_dt)
         ++nbt;
     }
     const double a_dual = a.a_d > alpha ? alpha : a.a_d;
+    if (is_midpoint(c))
+        for (int k = 0; k < N; ++k) ls_stage_midpoint_fix(c, L, W, k);
     for (int k = 0; k < N; ++k) ls_stage_update(c, L, W, W, uprev_dt, k, alpha, a_dual);
     if (c.variable_dt) ASC(MPCB200_SC_DT) = dt + alpha * ddt;
     ASC(MPCB200_SC_ALPHA) = alpha;

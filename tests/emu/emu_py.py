@@ -16,7 +16,7 @@ _LIB = None
 def build(force=False):
     srcs = [os.path.join(_DIR, "emu.cpp")] + [
         os.path.join(_DIR, "..", "..", "mpc_local_planner_b200", "csrc", f)
-        for f in ("mpc_core.h", "mpc_stage.h", "mpc_riccati_lane.h", "mpc_layout.h")]
+        for f in ("mpc_core.h", "mpc_stage.h", "mpc_riccati_warp.h", "mpc_layout.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(s) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _DIR, "-B", "libemu.so"], stdout=subprocess.DEVNULL)
 
@@ -86,8 +86,8 @@ class EmuInstance:
         off = self.L.emu_field_offset(C.byref(self.cfg), f, C.byref(cnt))
         if f == capi.F_SCAL:
             return self.W[off: off + cnt.value]
-        if f == capi.F_KKT:  # 32-instance interleaved tile: element (k, f) at off + (k*42 + f)*32; present [42][N] (copy)
-            idx = off + (np.arange(self.N)[None, :] * cnt.value + np.arange(cnt.value)[:, None]) * 32
+        if f == capi.F_KKT:  # stage records [k][43] (42 words + a zero word); present [42][N] (copy)
+            idx = off + np.arange(self.N)[None, :] * 43 + np.arange(cnt.value)[:, None]
             return self.W[idx]
         return self.W[off: off + cnt.value * self.N].reshape(cnt.value, self.N)
 

@@ -425,24 +425,26 @@ def test_golden_option_fixtures(cuda_lib, option):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("cid,B", [(2, 96), (3, 40)])
-def test_kkt_attempt_scheduling_does_not_change_results(cuda_lib, cid, B):
-    """Running the two regularisation attempts of an iteration side by side (small batches) or one after the other is
-    an execution choice only: statuses, iteration counts and controls are identical."""
+def test_fused_and_phased_solves_are_identical(cuda_lib, cid, B):
+    """One persistent kernel per solve (default) or one kernel launch per phase is an execution choice only: the same
+    device functions run in the same order, so statuses, iteration counts and controls are identical bit for bit."""
     cfg = configs.config_for(cid, tol=1e-8)
     data = _data(cid, B)
     outs = []
-    for mode in (1, 2):
+    for mode in (capi.SOLVE_FUSED, capi.SOLVE_PHASED):
         s = _solver(cfg, B)
-        s.set_option(capi.OPT_KKT_ATTEMPTS, mode)
+        s.set_option(capi.OPT_SOLVE_MODE, mode)
         outs.append(s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"]))
         s.close()
     a, b = outs
     np.testing.assert_array_equal(a["status"], b["status"])
     np.testing.assert_array_equal(a["iters"], b["iters"])
     np.testing.assert_array_equal(a["u_seq"], b["u_seq"])
+    np.testing.assert_array_equal(a["x_seq"], b["x_seq"])
     np.testing.assert_array_equal(a["dt"], b["dt"])
 
 
+@pytest.mark.gpu
 def test_resample_changes_the_horizon_of_warm_trajectories(cuda_lib, orc):
     """mpcb200_resample (resampleTrajectory, the operation behind grid adaptation): the warm trajectories of the batch after a
     horizon change against the oracle's restatement, and the warm solve at the new horizon."""

@@ -24,6 +24,10 @@ def run(cid, B, n=None):
     gbs = byts / ms / 1e6
     print("cfg %d N %3d B %6d  kkt %.4f ms  algorithmic %.1f MB  %.0f GB/s  = %.1f %% of HBM peak (%.0f GB/s)" % (cid, N, B, ms, byts / 1e6, gbs, 100 * gbs / peak, peak), flush=True)
     s.close()
+if "--quick" in sys.argv:
+    for B in (1024, 4096): run(2, B)
+    run(3, 1024)
+    sys.exit(0)
 print("# KKT kernel alone, batch sweep, cfg 2 (N=50)")
 for B in (1024, 2048, 4096, 8192, 16384, 32768, 65536): run(2, B)
 print("# BASELINE configs[4]: horizon sweep at B=2048 (cfg 5)")

@@ -1,4 +1,4 @@
-"""Small cold solves of every code path (batch with both KKT attempt schedules, streaming, line / moving obstacles, minimum time)
+"""Small cold solves of every code path (batch in both solve modes, queue, line / moving obstacles, minimum time)
 for compute-sanitizer:  compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
 import sys; sys.path.insert(0, '.')
 import numpy as np
@@ -7,9 +7,9 @@ for cid, B in ((2, 48), (3, 24), (4, 32)):
     cfg = configs.config_for(cid, tol=1e-6)
     cfg.max_iter = 30
     data = configs.generate(cid, B)
-    for mode in (1, 2):
+    for mode in (capi.SOLVE_FUSED, capi.SOLVE_PHASED):
         s = capi.BatchSolver(cfg, B)
-        s.set_option(capi.OPT_KKT_ATTEMPTS, mode)
+        s.set_option(capi.OPT_SOLVE_MODE, mode)
         out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
         s.close()
     s = capi.BatchSolver(cfg, 16)
