@@ -14,8 +14,10 @@
 
 #ifdef __CUDACC__
 #define HD __host__ __device__
+#define NOINL __noinline__   /* big leaf functions are real functions on the device: the solve kernel is bound by instruction fetch */
 #else
 #define HD
+#define NOINL
 #endif
 
 #include "../../include/mpcb200.h"
@@ -71,15 +73,20 @@ struct WsLayout
 typedef mpcb200_config Cfg;
 
 // ---- elementary functions ----
-HD inline double normalize_theta(double theta)
+HD NOINL inline double normalize_theta_wrap(double theta)
 {
     const double PI = 3.14159265358979323846;
-    if (theta >= -PI && theta < PI) return theta;
     double multiplier = floor(theta / (2.0 * PI));
     theta = theta - multiplier * 2.0 * PI;
     if (theta >= PI) theta -= 2.0 * PI;
     if (theta < -PI) theta += 2.0 * PI;
     return theta;
+}
+HD inline double normalize_theta(double theta)
+{
+    const double PI = 3.14159265358979323846;
+    if (theta >= -PI && theta < PI) return theta;
+    return normalize_theta_wrap(theta);
 }
 HD inline double interpolate_angle(double a1, double a2, double factor)
 {
@@ -87,7 +94,7 @@ HD inline double interpolate_angle(double a1, double a2, double factor)
 }
 
 // f(x,u) and derivatives wrt q = (theta, u0, u1): J[j*3+i] = df_j/dq_i, Hc = sum_j nu_j Hess f_j packed (tt,t0,t1,00,01,11)
-HD inline void dynamics_derivs(const Cfg& c, double th, double v, double w, const double* nu, double* f, double* J,
+HD NOINL inline void dynamics_derivs(const Cfg& c, double th, double v, double w, const double* nu, double* f, double* J,
                                        double* Hc, const double* sc = nullptr)
 {
 #pragma unroll
@@ -148,7 +155,7 @@ HD inline void dynamics_derivs(const Cfg& c, double th, double v, double w, cons
     }
 }
 
-HD inline void dynamics_value(const Cfg& c, double th, double v, double w, double* f)
+HD NOINL inline void dynamics_value(const Cfg& c, double th, double v, double w, double* f)
 {
     if (c.robot_type != MPCB200_ROBOT_KIN_BICYCLE)
     {
@@ -186,7 +193,7 @@ HD inline double footprint_distance(const Cfg& c, double px, double py, double p
 // footprint <-> obstacle POINT (wx, wy) (+ obstacle radius r_obst): the point is taken to the robot frame and the closest
 // footprint feature is differentiated through q = R(theta)'(w - p)
 template <bool WITH_GRAD, bool WITH_HESS>
-HD inline double footprint_distance_point(const Cfg& c, double px, double py, double s, double co, double wx, double wy, double r_obst,
+HD NOINL inline double footprint_distance_point(const Cfg& c, double px, double py, double s, double co, double wx, double wy, double r_obst,
                                           double* grad3, double* hess6)
 {
     const double ox = wx - px, oy = wy - py;
@@ -309,7 +316,7 @@ HD inline bool segments_intersect(double p1x, double p1y, double p2x, double p2y
 // smaller of (i) the footprint's distance to the two end points and (ii) the distance of the footprint's vertices /
 // circle centres to the interior of the segment.
 template <bool WITH_GRAD, bool WITH_HESS>
-HD inline double footprint_distance_line(const Cfg& c, double px, double py, double s, double co, const double* op, double* grad3, double* hess6)
+HD NOINL inline double footprint_distance_line(const Cfg& c, double px, double py, double s, double co, const double* op, double* grad3, double* hess6)
 {
     const double ax = op[0], ay = op[1], bx = op[2], by = op[3];
     double ux = bx - ax, uy = by - ay;
@@ -409,7 +416,7 @@ HD inline void obstacle_centroid(int obst_type, const double* op, double* cx, do
     else { *cx = op[0]; *cy = op[1]; }
 }
 
-HD inline int clip_bin(double ratio)  // bin j holds the ratios in (2^(-(j+1)/2), 2^(-j/2)]
+HD NOINL inline int clip_bin(double ratio)  // bin j holds the ratios in (2^(-(j+1)/2), 2^(-j/2)]
 {
     const int j = (int)floor(-2.0 * log2(ratio));
     return j < 0 ? 0 : (j >= CLIP_BINS ? CLIP_BINS - 1 : j);
@@ -546,7 +553,7 @@ HD inline double lin_row(const Cfg& c, int N, int k, int slot, double uk, double
 
 HD inline int hidx(int i, int j) { return i * 5 - (i * (i - 1)) / 2 + (j - i); }
 
-HD inline double scaled_error(double dual_inf, double prim_inf, double sl_max, double sl_min, double sum_nu,
+HD NOINL inline double scaled_error(double dual_inf, double prim_inf, double sl_max, double sl_min, double sum_nu,
                                                double sum_lam, int m_eq, int m_ineq, double mu)
 {
     double sd = (sum_nu + sum_lam) / (double)(m_eq + m_ineq > 0 ? m_eq + m_ineq : 1);

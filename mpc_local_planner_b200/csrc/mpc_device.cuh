@@ -12,7 +12,8 @@
 #include "mpc_layout.h"
 
 #define FULLMASK 0xffffffffu
-#define MAX_GROUP_WARPS 4   // warps of the CTA that owns one instance (lane per stage; longer horizons wrap)
+#define MAX_ROLE_WARPS 4    // warps per role: one lane per stage, longer horizons wrap
+#define MAX_GROUP_WARPS (2 * MAX_ROLE_WARPS)   // the CTA that owns an instance has two roles: base lanes and obstacle-row lanes
 
 // ---- warp reductions (fp64 via two 32-bit shuffles each) ------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)
@@ -330,24 +331,46 @@ struct CtaShared
     int fin, accept;
 };
 
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(FULLMASK, v, o); }
+// butterfly over the lanes, level by level for all fields (a loop over the levels: a fifth of the code of fifteen unrolled
+// reductions; per field the same order of operations)
 __device__ __forceinline__ void evalacc_warp_reduce(EvalAcc& a)
 {
-    a.dual_inf = warp_max(a.dual_inf); a.prim_inf = warp_max(a.prim_inf);
-    a.sl_max = warp_max(a.sl_max); a.sl_min = warp_min(a.sl_min);
-    a.sum_nu = warp_sum(a.sum_nu); a.sum_lam = warp_sum(a.sum_lam); a.inf1 = warp_sum(a.inf1); a.blog = warp_sum(a.blog);
-    a.gt0 = warp_sum(a.gt0); a.gt1 = warp_sum(a.gt1); a.gldt = warp_sum(a.gldt); a.htt = warp_sum(a.htt);
-    a.obj = warp_sum(a.obj); a.m_ineq = warp_sum(a.m_ineq); a.m_eq = warp_sum(a.m_eq);
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        a.dual_inf = fmax(a.dual_inf, shfl_xor_d(a.dual_inf, o)); a.prim_inf = fmax(a.prim_inf, shfl_xor_d(a.prim_inf, o));
+        a.sl_max = fmax(a.sl_max, shfl_xor_d(a.sl_max, o)); a.sl_min = fmin(a.sl_min, shfl_xor_d(a.sl_min, o));
+        a.sum_nu += shfl_xor_d(a.sum_nu, o); a.sum_lam += shfl_xor_d(a.sum_lam, o); a.inf1 += shfl_xor_d(a.inf1, o); a.blog += shfl_xor_d(a.blog, o);
+        a.gt0 += shfl_xor_d(a.gt0, o); a.gt1 += shfl_xor_d(a.gt1, o); a.gldt += shfl_xor_d(a.gldt, o); a.htt += shfl_xor_d(a.htt, o);
+        a.obj += shfl_xor_d(a.obj, o); a.m_ineq += shfl_xor_d(a.m_ineq, o); a.m_eq += shfl_xor_d(a.m_eq, o);
+    }
 }
 
 // ---- PHASE_EVAL (whole CTA, lane per stage): stage functions + derivatives -> condensed KKT records, KKT error,
 //      convergence test and barrier update.  Returns 1 (uniform) when the instance terminates. ----
+// roles = 1: a lane does all the work of its stages.  roles = 2: the CTA has two roles of nt/2 threads each, the base lanes
+// (dynamics, costs, linear rows, record) and the obstacle-row lanes of the same stages -- about half of the work of a stage
+// each; their partial sums meet in shared memory (eval_stage_merge).  Shorter chains per lane, more instructions in total.
 template <bool LINES>
-__device__ __forceinline__ int dev_eval(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt)
+__device__ __forceinline__ int dev_eval(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt, int roles)
 {
-    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5, nth = roles == 2 ? nt >> 1 : nt;
+    const int role = tid >= nth, kt = tid - role * nth;
     EvalAcc a;
     evalacc_init(a);
-    for (int k = tid; k < N; k += nt) eval_stage<LINES>(c, L, W, W, uprev_dt, k, a);
+    if (roles == 2)
+    {
+        if (role == 0)
+            for (int k = kt; k < N; k += nth) eval_stage_base<LINES>(c, L, W, W, uprev_dt, k, a);
+        else
+            for (int k = kt; k < N; k += nth) eval_stage_obst<LINES>(c, L, W, W, uprev_dt, k, a);
+        __syncthreads();
+    }
+    else
+        for (int k = kt; k < N; k += nth) { eval_stage_base<LINES>(c, L, W, W, uprev_dt, k, a); eval_stage_obst<LINES>(c, L, W, W, uprev_dt, k, a); }
+    if (role == 0)
+        for (int k = kt; k < N; k += nth) eval_stage_merge(c, L, W, k, a);
     evalacc_warp_reduce(a);
     if (lane == 0) sh.eacc[wid] = a;
     __syncthreads();
@@ -385,9 +408,10 @@ __device__ __forceinline__ void dev_kkt(const Cfg& c, const WsLayout& L, double*
 
 // ---- PHASE_LINESEARCH (whole CTA, lane per stage): step lengths, l1-merit backtracking, iterate update ----
 template <bool LINES>
-__device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt)
+__device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt, int roles)
 {
-    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5, nth = roles == 2 ? nt >> 1 : nt;
+    const int role = tid >= nth, kt = tid - role * nth, part = roles == 2 ? (role ? PART_OBST : PART_BASE) : PART_ALL;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;   // the KKT phase gave the instance up
     if (ASC(MPCB200_SC_DEFER) != 0.0)
     {
@@ -402,10 +426,10 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
     // histogram of the blocking step ratios (+ row count) -> threshold bin of the clipped rows -> primal step length
     for (int j = tid; j <= CLIP_BINS; j += nt) sh.hist[j] = 0;
     __syncthreads();
-    for (int k = tid; k < N; k += nt) ls_stage_steps(c, L, W, W, uprev_dt, k, a, sh.hist);
+    for (int k = kt; k < N; k += nth) ls_stage_steps(c, L, W, W, uprev_dt, k, a, sh.hist, part);
     __syncthreads();
     const int jt = clip_threshold_bin(sh.hist, sh.hist[CLIP_BINS]);  // same value in every thread
-    for (int k = tid; k < N; k += nt) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt));
+    for (int k = kt; k < N; k += nth) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt, part));
     a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
     a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
     if (lane == 0) sh.lacc[wid] = a;
@@ -436,11 +460,12 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
     __syncthreads();
     double alpha = sh.alpha;
     int nbt = 0;
+#pragma unroll 1
     for (int bt = 0; bt < MAX_BACKTRACK; ++bt)
     {
         TrialAcc t;
         t.obj = t.inf1 = t.blog = 0.0;
-        for (int k = tid; k < N; k += nt) ls_stage_trial<LINES>(c, L, W, W, uprev_dt, k, alpha, t);
+        for (int k = kt; k < N; k += nth) ls_stage_trial<LINES>(c, L, W, W, uprev_dt, k, alpha, t, part);
         t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
         if (lane == 0) sh.tr[wid] = t;
         __syncthreads();
@@ -462,7 +487,7 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
         for (int k = tid; k < N; k += nt) ls_stage_midpoint_fix(c, L, W, k);   // reads the old heading of stage k+1
     __syncthreads();
     const double a_dual = sh.a_dual;
-    for (int k = tid; k < N; k += nt) ls_stage_update(c, L, W, W, uprev_dt, k, alpha, a_dual);
+    for (int k = kt; k < N; k += nth) ls_stage_update(c, L, W, W, uprev_dt, k, alpha, a_dual, part);
     if (tid == 0)
     {
         if (c.variable_dt) ASC(MPCB200_SC_DT) = ASC(MPCB200_SC_DT) + alpha * ASC(MPCB200_SC_DDT);

@@ -33,6 +33,16 @@
 #define GNU(c_, k_) G[L.oNU + (c_) * N + (k_)]
 #define GS(c_, k_) G[L.oS + (c_) * N + (k_)]
 #define GLAM(c_, k_) G[L.oLAM + (c_) * N + (k_)]
+// partial sums of the evaluation (obstacle part of a stage's pose block, base part of its pose gradient): rows 5.. of the DS
+// area, which is free during the evaluation (rows 0..4 park the gradient parts until eval_finalize_stage)
+#define EPART(c_, k_) W[L.oDS + (5 + (c_)) * N + (k_)]
+#define EP_H 0
+#define EP_G0 6
+#define EP_G1 9
+#define EP_GL 12
+#define EP_HB 15
+#define EP_GLB 18
+#define EP_ROWS 21
 #define ASC(i_) W[L.oSCAL + (i_)]
 #define AIN(i_) W[L.oIN + (i_)]
 
@@ -62,14 +72,15 @@ HD inline void evalacc_merge(EvalAcc& a, const EvalAcc& b)
 // bookkeeping of one inequality row (owner side): errors + barrier terms.  The barrier term sum(log s) is accumulated
 // as a running product that is flushed through one log() every few rows (fp64 log costs ~60 instructions).
 struct RowProd { double p; int n; };
+HD NOINL inline double log_call(double x) { return log(x); }   // one copy of the fp64 logarithm instead of one per call site
 HD inline void rowprod_add(RowProd& rp, double s, double& blog)
 {
     rp.p *= s;
-    if (++rp.n >= 4) { blog += log(rp.p); rp.p = 1.0; rp.n = 0; }
+    if (++rp.n >= 4) { blog += log_call(rp.p); rp.p = 1.0; rp.n = 0; }
 }
 HD inline void rowprod_flush(RowProd& rp, double& blog)
 {
-    if (rp.n > 0) { blog += log(rp.p); rp.p = 1.0; rp.n = 0; }
+    if (rp.n > 0) { blog += log_call(rp.p); rp.p = 1.0; rp.n = 0; }
 }
 HD inline void row_stats(EvalAcc& acc, RowProd& rp, double r, double s, double lam)
 {
@@ -85,20 +96,32 @@ HD inline void row_stats(EvalAcc& acc, RowProd& rp, double r, double s, double l
 // One linear row (control bound / control-rate row) seen from stage k's control component I.
 //   g: row value, (s, lam): slack / multiplier, gmine: d g / d u_k[I], gdt: d g / d(dt), own: the row belongs to stage k
 //   (bookkeeping of errors and dt terms is done once, by the owner), gcross: d g / d u_{k-1}[I] (own rate rows only).
+// The arithmetic of a row is ONE function on the device (twelve call sites per stage): the products come back by value.
+struct LinTerms { double r, rs, c0g, rsg, lamg, sgg, sgt, sgc, c0t, rst, lamt, sgtt; };
+HD NOINL inline LinTerms lin_row_terms(double g, double s, double lam, double gmine, double gdt, double gcross)
+{
+    LinTerms t;
+    const double rs = 1.0 / s;
+    const double r = g + s, sig = lam * rs, c0 = sig * r;
+    t.r = r; t.rs = rs;
+    t.c0g = c0 * gmine; t.rsg = rs * gmine; t.lamg = lam * gmine;
+    t.sgg = sig * gmine * gmine; t.sgt = sig * gmine * gdt; t.sgc = sig * gmine * gcross;
+    t.c0t = c0 * gdt; t.rst = rs * gdt; t.lamt = lam * gdt; t.sgtt = sig * gdt * gdt;
+    return t;
+}
 template <int I>
 HD inline void lin_row_accum(double g, double s, double lam, double gmine, double gdt, bool own, double gcross, double* H, double* g0,
                              double* g1, double* GL, double* hb, double* Cc, EvalAcc& acc, RowProd& rp)
 {
-    const double rs = 1.0 / s;
-    const double r = g + s, sig = lam * rs, c0 = sig * r;
-    g0[3 + I] += c0 * gmine; g1[3 + I] += rs * gmine; GL[3 + I] += lam * gmine;
-    H[hidx(3 + I, 3 + I)] += sig * gmine * gmine;
-    hb[3 + I] += sig * gmine * gdt;
+    const LinTerms t = lin_row_terms(g, s, lam, gmine, gdt, gcross);
+    g0[3 + I] += t.c0g; g1[3 + I] += t.rsg; GL[3 + I] += t.lamg;
+    H[hidx(3 + I, 3 + I)] += t.sgg;
+    hb[3 + I] += t.sgt;
     if (own)
     {
-        Cc[I] += sig * gmine * gcross;
-        row_stats(acc, rp, r, s, lam);
-        acc.gt0 += c0 * gdt; acc.gt1 += rs * gdt; acc.gldt += lam * gdt; acc.htt += sig * gdt * gdt;
+        Cc[I] += t.sgc;
+        row_stats(acc, rp, t.r, s, lam);
+        acc.gt0 += t.c0t; acc.gt1 += t.rst; acc.gldt += t.lamt; acc.htt += t.sgtt;
     }
 }
 
@@ -140,7 +163,7 @@ HD inline void lin_rows_component(const Cfg& c, const WsLayout& L, const double*
 // coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
 // LINES = false compiles the rarely used obstacle kinds out (line obstacles, moving obstacles): see footprint_distance_sc
 template <bool LINES = true>
-HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, EvalAcc& acc)
+HD inline void eval_stage_base(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, EvalAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT);
@@ -390,6 +413,40 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
             }
         }
     }
+    rowprod_flush(rp, acc.blog);
+    // dual infeasibility over the free controls of this stage (the pose components wait for the obstacle rows: eval_stage_merge)
+    if (k <= N - 2) acc.dual_inf = fmax(acc.dual_inf, fmax(fabs(GL[3]), fabs(GL[4])));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) EPART(EP_GLB + i, k) = GL[i];
+    // store the record
+#pragma unroll
+    for (int i = 0; i < 15; ++i) AKKT(MPCB200_K_H + i, k) = H[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { ADS(i, k) = g0[i]; ASTEP(i, k) = g1[i]; AKKT(MPCB200_K_HB + i, k) = hb[i]; }  // g = g0 + mu g1 is stored by eval_finalize_stage
+    // (g0, g1 wait in the image -- DS / STEP are free during the evaluation -- so that the record is written exactly once)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { AKKT(MPCB200_K_A + i, k) = a3[i]; AKKT(MPCB200_K_E + i, k) = e[i]; AKKT(MPCB200_K_D + i, k) = dvec[i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) AKKT(MPCB200_K_B + i, k) = Bm[i];
+    AKKT(MPCB200_K_C + 0, k) = Cc[0];
+    AKKT(MPCB200_K_C + 1, k) = Cc[1];
+}
+
+// The obstacle rows of stage k (k = 1..N-2): row values and gradients for the line search (OG), their part of the pose block
+// of the record as 18 partial sums (EPART: H xx 6, g0 3, g1 3, GL 3, dt border 3) -- run by the lanes of the second role
+// beside eval_stage_base, added to the record by eval_stage_merge.
+template <bool LINES = true>
+HD inline void eval_stage_obst(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, EvalAcc& acc)
+{
+    const int N = L.N, K = L.K;
+    const double dt = ASC(MPCB200_SC_DT);
+    double H[15], g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, GL[3] = {0, 0, 0}, hb[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 15; ++i) H[i] = 0.0;
+    RowProd rp; rp.p = 1.0; rp.n = 0;
+    const double x[3] = {AX(0, k), AX(1, k), AX(2, k)};
+    double sc[2] = {0.0, 1.0};
+    if (k >= 1 && k <= N - 2 && K > 0) sincos(x[2], &sc[0], &sc[1]);
     // obstacle rows (k = 1..N-2); value and gradient are kept for the line-search kernel
     if (k >= 1 && k <= N - 2)
     {
@@ -430,27 +487,33 @@ HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G,
         }
     }
     rowprod_flush(rp, acc.blog);
-    // dual infeasibility over the free variables of this stage
+    int q = 0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 3; ++i)
     {
-        if (i < 3 && k == 0) continue;
-        if (i < 3 && k == N - 1 && c.xf_fixed[i]) continue;
-        if (i >= 3 && k == N - 1) continue;
-        acc.dual_inf = fmax(acc.dual_inf, fabs(GL[i]));
+#pragma unroll
+        for (int jj = i; jj < 3; ++jj, ++q) EPART(EP_H + q, k) = H[hidx(i, jj)];
+        EPART(EP_G0 + i, k) = g0[i]; EPART(EP_G1 + i, k) = g1[i]; EPART(EP_GL + i, k) = GL[i]; EPART(EP_HB + i, k) = hb[i];
     }
-    // store the record
+}
+
+// record of stage k = base part + obstacle part; dual infeasibility of the pose components
+HD inline void eval_stage_merge(const Cfg& c, const WsLayout& L, double* W, int k, EvalAcc& acc)
+{
+    const int N = L.N;
+    int q = 0;
 #pragma unroll
-    for (int i = 0; i < 15; ++i) AKKT(MPCB200_K_H + i, k) = H[i];
+    for (int i = 0; i < 3; ++i)
+    {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) { ADS(i, k) = g0[i]; ASTEP(i, k) = g1[i]; AKKT(MPCB200_K_HB + i, k) = hb[i]; }  // g = g0 + mu g1 is stored by eval_finalize_stage
-    // (g0, g1 wait in the image -- DS / STEP are free during the evaluation -- so that the record is written exactly once)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { AKKT(MPCB200_K_A + i, k) = a3[i]; AKKT(MPCB200_K_E + i, k) = e[i]; AKKT(MPCB200_K_D + i, k) = dvec[i]; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) AKKT(MPCB200_K_B + i, k) = Bm[i];
-    AKKT(MPCB200_K_C + 0, k) = Cc[0];
-    AKKT(MPCB200_K_C + 1, k) = Cc[1];
+        for (int jj = i; jj < 3; ++jj, ++q) AKKT(MPCB200_K_H + hidx(i, jj), k) += EPART(EP_H + q, k);
+        ADS(i, k) += EPART(EP_G0 + i, k);
+        ASTEP(i, k) += EPART(EP_G1 + i, k);
+        AKKT(MPCB200_K_HB + i, k) += EPART(EP_HB + i, k);
+        const double gl = EPART(EP_GLB + i, k) + EPART(EP_GL + i, k);
+        if (k == 0 || (k == N - 1 && c.xf_fixed[i])) continue;
+        acc.dual_inf = fmax(acc.dual_inf, fabs(gl));
+    }
 }
 
 // After the warp reduction: convergence test, monotone barrier update (Ipopt's Fiacco-McCormick rule), scalars.
@@ -519,7 +582,11 @@ HD inline void lsacc_init(LsAcc& a) { a.a_p = 1.0; a.a_d = 1.0; a.dphi_bar = a.c
 #else
 #define HIST_ADD(p_) (++*(p_))
 #endif
-HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, LsAcc& acc, int* hist)
+// part: PART_BASE = the linear rows, the terminal ball, the objective and curvature terms; PART_OBST = the obstacle rows
+#define PART_BASE 1
+#define PART_OBST 2
+#define PART_ALL 3
+HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, LsAcc& acc, int* hist, int part = PART_ALL)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT), mu = ASC(MPCB200_SC_MU), ddt = ASC(MPCB200_SC_DDT);
@@ -532,7 +599,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
     if (k <= N - 2) { du[0] = ASTEP(3, k); du[1] = ASTEP(4, k); }
     // rows: slack / multiplier steps.  Linear rows are re-evaluated (pure arithmetic); obstacle rows reuse the value and
     // gradient stored by the EVAL kernel at this very point.  r0 = g + s is kept for the analytic trial evaluation.
-    for (int sl = 0; sl < 8 + K; ++sl)
+    for (int sl = (part & PART_BASE) ? 0 : 8; sl < ((part & PART_OBST) ? 8 + K : 8); ++sl)
     {
         double g, gdz;
         if (sl == BALL_SLOT && k == N - 1 && ball_active(c))
@@ -575,6 +642,7 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         acc.dphi_bar += -mu * ds * rs;
         acc.curv += (lam * rs) * ds * ds;
     }
+    if (!(part & PART_BASE)) return;
     // directional derivative of the objective
     double dJ = 0.0;
     if (k <= N - 2)
@@ -647,13 +715,13 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
 }
 
 // primal step length: smallest step ratio over the rows of stage k that are not clipped (bins below jt)
-HD inline double ls_stage_ap(const WsLayout& L, const double* W, int k, int jt)
+HD inline double ls_stage_ap(const WsLayout& L, const double* W, int k, int jt, int part = PART_ALL)
 {
     const int N = L.N, RS = L.RS;
     const double mu = ASC(MPCB200_SC_MU);
     const double tau = (1.0 - mu > TAU_MIN) ? 1.0 - mu : TAU_MIN;
     double a_p = 1.0;
-    for (int sl = 0; sl < RS; ++sl)
+    for (int sl = (part & PART_BASE) ? 0 : 8; sl < ((part & PART_OBST) ? RS : 8); ++sl)
     {
         const double ds = ADS(sl, k);  // 0 for inactive rows
         if (!(ds < 0)) continue;
@@ -665,7 +733,7 @@ HD inline double ls_stage_ap(const WsLayout& L, const double* W, int k, int jt)
 
 // objective contribution of stage k at (x, u, dt): quadratic running cost (k <= N-2; dt-weighted in integral form), terminal
 // cost and minimum-time term (k = N-1), via-points attached to the stage.  u is read for k <= N-2 only.
-HD inline double stage_objective(const Cfg& c, const WsLayout& L, const double* W, int k, const double* x, const double* u, double dtt)
+HD NOINL inline double stage_objective(const Cfg& c, const WsLayout& L, const double* W, int k, const double* x, const double* u, double dtt)
 {
     const int N = L.N;
     const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
@@ -731,7 +799,7 @@ struct TrialAcc { double obj, inf1, blog; };
 // merit pieces of stage k at the trial point z + alpha dz, s + alpha ds.  Linear rows are exact in alpha:
 // g(alpha) + s(alpha) = (1 - alpha) r0, so only the dynamics defect, the objective and the obstacle rows are re-evaluated.
 template <bool LINES = true>
-HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, const double* G, double uprev_dt, int k, double alpha, TrialAcc& acc)
+HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, const double* G, double uprev_dt, int k, double alpha, TrialAcc& acc, int part = PART_ALL)
 {
     const int N = L.N, K = L.K;
     const double dtt = ASC(MPCB200_SC_DT) + (c.variable_dt ? alpha * ASC(MPCB200_SC_DDT) : 0.0);
@@ -739,7 +807,8 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
     const double xf[3] = {AIN(IN_XF), AIN(IN_XF + 1), AIN(IN_XF + 2)};
     double sc[2];
     sincos(x[2], &sc[0], &sc[1]);
-    if (k <= N - 2)
+    if (!(part & PART_BASE)) {}
+    else if (k <= N - 2)
     {
         const double u[2] = {AU(0, k) + alpha * ASTEP(3, k), AU(1, k) + alpha * ASTEP(4, k)};
         double f[3];
@@ -761,7 +830,7 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
     else acc.obj += stage_objective(c, L, W, k, x, nullptr, dtt);
     RowProd rp; rp.p = 1.0; rp.n = 0;
     const double oma = 1.0 - alpha;
-    for (int sl = 0; sl < 8; ++sl)
+    for (int sl = (part & PART_BASE) ? 0 : 8; sl < 8; ++sl)
     {
         if (!lin_row_active(c, N, k, sl, uprev_dt)) continue;
         const double s0 = AS(sl, k), ds = ADS(sl, k);
@@ -771,7 +840,7 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
         acc.inf1 += fabs(res);
         rowprod_add(rp, sn, acc.blog);
     }
-    if (k >= 1 && k <= N - 2)
+    if ((part & PART_OBST) && k >= 1 && k <= N - 2)
         for (int j = 0; j < K; ++j)
         {
             const int oi = (int)AOBS(j, k);
@@ -785,7 +854,7 @@ HD inline void ls_stage_trial(const Cfg& c, const WsLayout& L, const double* W, 
             acc.inf1 += fabs(c.min_obstacle_dist - dist + sn);
             rowprod_add(rp, sn, acc.blog);
         }
-    if (k == N - 1 && ball_active(c))
+    if ((part & PART_BASE) && k == N - 1 && ball_active(c))
     {
         double sn = AS(BALL_SLOT, k) + alpha * ADS(BALL_SLOT, k);
         if (sn < CLIP_FLOOR * AS(BALL_SLOT, k)) sn = CLIP_FLOOR * AS(BALL_SLOT, k);
@@ -812,21 +881,21 @@ HD inline void ls_stage_midpoint_fix(const Cfg& c, const WsLayout& L, double* W,
 }
 
 // accept the step: z, s, lambda, nu of stage k (reads and writes stage k only: safe to run lane-parallel in place)
-HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W, double* G, double uprev_dt, int k, double alpha, double a_dual)
+HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W, double* G, double uprev_dt, int k, double alpha, double a_dual, int part = PART_ALL)
 {
     const int N = L.N, K = L.K;
     const double mu = ASC(MPCB200_SC_MU);
     const double d0 = ASTEP(0, k), d1 = ASTEP(1, k), d2 = ASTEP(2, k);
     double nup[3] = {0.0, 0.0, 0.0};
     if (k <= N - 2) { nup[0] = ASTEP(5, k); nup[1] = ASTEP(6, k); nup[2] = ASTEP(7, k); }
-    GX(0, k) = AX(0, k) + alpha * d0; GX(1, k) = AX(1, k) + alpha * d1; GX(2, k) = AX(2, k) + alpha * d2;
-    if (k <= N - 2)
+    if (part & PART_BASE) { GX(0, k) = AX(0, k) + alpha * d0; GX(1, k) = AX(1, k) + alpha * d1; GX(2, k) = AX(2, k) + alpha * d2; }
+    if ((part & PART_BASE) && k <= N - 2)
     {
         GU(0, k) = AU(0, k) + alpha * ASTEP(3, k);
         GU(1, k) = AU(1, k) + alpha * ASTEP(4, k);
         for (int i = 0; i < 3; ++i) GNU(i, k) = ANU(i, k) + alpha * (nup[i] - ANU(i, k));
     }
-    for (int sl = 0; sl < 8 + K; ++sl)
+    for (int sl = (part & PART_BASE) ? 0 : 8; sl < ((part & PART_OBST) ? 8 + K : 8); ++sl)
     {
         bool act;
         if (sl < 8) act = lin_row_active(c, N, k, sl, uprev_dt) || (sl == BALL_SLOT && k == N - 1 && ball_active(c));
