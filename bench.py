@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the hot path (BASELINE.json metric) on N GPUs of one node.
 
-A "step" = one pass of the hot path over one batch of synthetic OCP instances: cold Controller::step for every
-instance of BASELINE config[1] (batch=1024 per GPU, unicycle quadratic-form, N=50, 5 circular obstacles).
+A "step" = one pass of the hot path over one batch of synthetic OCP instances: a cold Controller::step for every
+instance of the workload.  Default workload = BASELINE configs[1] (batch 1024 per GPU, unicycle quadratic-form, N=50,
+5 circular obstacles); `--config 3|4|5` measures BASELINE configs[2..4] through the same code.
 
   python bench.py --gpus 1 --steps K --warmup W                       (single GPU)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU)
   python bench.py --impl reference ...                                (CPU arm: the oracle port on the host cores)
 
-Rank 0 prints ONE JSON line.  `value` = whole-job converged solves/s with the inputs already resident in HBM;
-`e2e` = the same metric through the C-ABI call with pinned HOST buffers (H2D + D2H inside the timed region);
-`roofline` = the Riccati KKT kernel's algorithmic bytes / its CUDA-event time, against the measured HBM peak;
-`cpu_baseline` = the CPU oracle (port of the algorithm, test infrastructure) on a bounded sample of the workload.
+Rank 0 prints ONE JSON line.
+  value        whole-job converged solves/s, inputs already resident in HBM (mpcb200_solve_resident: ONE launch of the
+               persistent solve kernel per step, L2 flushed between steps, CUDA events on the work stream, max over ranks)
+  e2e          the same metric through mpcb200_step_batch with pinned HOST buffers (H2D + D2H inside the timed region)
+  roofline     the KKT factorisation kernel (kkt_warp_kernel): algorithmic bytes of SURVEY 8(d) x the instances of a launch
+               / its CUDA-event time, timed alone inside this run on the records of the batch, against the measured HBM peak
+  cpu_baseline the CPU oracle (plain-C port of the algorithm, test infrastructure) on a bounded sample of the workload
+  configs      driver-visible numbers for the other BASELINE configurations (cfg 3 and the horizon sweep at N=1 GPU;
+               cfg 4 = 16 384 via-point instances split over the ranks of this run: strong scaling over the driver's runs)
 """
 import argparse
 import json
@@ -26,12 +32,20 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "converged MPC solves/sec (N=50 unicycle quadratic-form OCP, 5 obstacles, batched)"
 UNIT = "solves/s"
-CONFIG_ID = 2
-BATCH_PER_GPU = 1024
-WORKLOAD = ("BASELINE configs[1]: batch=1024 per GPU, unicycle quadratic_form, N=50, fixed dt=0.3, 5 circular "
-            "obstacles, rate limits 0.2, tol 1e-6, max_iter 100, cold start")
+WORKLOADS = {
+    2: ("converged MPC solves/sec (N=50 unicycle quadratic-form OCP, 5 obstacles, batched)", 1024,
+        "BASELINE configs[1]: batch=1024 per GPU, unicycle quadratic_form, N=50, fixed dt=0.3, 5 circular obstacles, "
+        "rate limits 0.2, tol 1e-6, max_iter 100, cold start"),
+    3: ("converged MPC solves/sec (N=80 carlike minimum-time OCP, polygon footprint, batched)", 4096,
+        "BASELINE configs[2]: batch=4096 per GPU, simple_car (rear drive, L=0.4) minimum_time, N=80, free dt, polygon "
+        "footprint (9 vertices), 5 point/circle obstacles, tol 1e-6, max_iter 100, cold start"),
+    4: ("converged MPC solves/sec (N=50 unicycle quadratic-form OCP with via-points, batched)", 2048,
+        "BASELINE configs[3]: batch=2048 per GPU (16384 over 8), unicycle quadratic_form + via-point attraction, N=50, "
+        "5 circular obstacles, 2 via-points, tol 1e-6, max_iter 100, cold start"),
+    5: ("converged MPC solves/sec (unicycle quadratic-form OCP, horizon N, batched)", 2048,
+        "BASELINE configs[4]: batch=2048, unicycle quadratic_form, horizon N in {20,50,100,200}, 5 circular obstacles"),
+}
 
 
 def kkt_bytes_per_instance(cfg):
@@ -45,10 +59,36 @@ def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst: kernel timed alone)"
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_cores():
+    """Threads this process may really use: the affinity mask, capped by the cgroup CPU quota (cpu.max)."""
+    try:
+        n_aff = len(os.sched_getaffinity(0))
+    except Exception:
+        n_aff = os.cpu_count() or 1
+    quota = None
+    for p in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(p).read().split()
+            if p.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    n = n_aff
+    if quota is not None:
+        n = max(1, min(n_aff, int(quota + 0.5)))
+    return n, {"os_cpu_count": os.cpu_count(), "affinity": n_aff, "cgroup_quota": quota}
 
 
 class ClockSampler(threading.Thread):
@@ -110,7 +150,7 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_arm(cfg, data_fn, seconds_target, threads):
-    """The CPU oracle (port) on a bounded sample of the same workload, all host threads."""
+    """The CPU oracle (port) on a bounded sample of the same workload, on the host threads this process may use."""
     from oracle import oracle_py as orc
     orc.build()
     n = max(threads * 8, 32)
@@ -118,8 +158,7 @@ def cpu_arm(cfg, data_fn, seconds_target, threads):
     t = time.time()
     out = orc.step_batch(cfg, data, n_threads=threads)
     el = time.time() - t
-    # grow the sample towards the time target (bounded)
-    if el < seconds_target / 4:
+    if el < seconds_target / 4:   # grow the sample towards the time target (bounded)
         n2 = int(min(n * (seconds_target / 2) / max(el, 1e-3), 32768))
         data = data_fn(n2)
         t = time.time()
@@ -136,8 +175,11 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE configuration (SURVEY 8d numbering)")
+    ap.add_argument("--horizon", type=int, default=50, help="grid points N for --config 5")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the configuration's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the secondary blocks (cfg 3 / 4 / horizon sweep / queue)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -145,9 +187,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     from mpc_local_planner_b200 import capi, configs
-    cfg = configs.config_for(CONFIG_ID, tol=1e-6)
-    B = args.batch
-    threads = os.cpu_count() or 1
+    cid = args.config
+    metric, default_batch, workload = WORKLOADS[cid]
+    n_h = args.horizon if cid == 5 else None
+    cfg = configs.config_for(cid, n=n_h, tol=1e-6)
+    B = args.batch or default_batch
+    threads, cores_info = host_cores()
 
     # ------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -156,7 +201,7 @@ def main():
         from oracle import oracle_py as orc
         orc.build()
         sample = max(threads * 32, 256)
-        data = configs.generate(CONFIG_ID, sample)
+        data = configs.generate(cid, sample, n=n_h)
         for _ in range(max(args.warmup, 0)):
             orc.step_batch(cfg, data, n_threads=threads)
         t0 = time.time()
@@ -167,12 +212,13 @@ def main():
         el = time.time() - t0
         val = conv / el
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference arm = CPU oracle port of the same algorithm (the reference's "
-                       "control_box_rst + Ipopt stack cannot be built here: no ROS/Eigen/Ipopt, see DESIGN.md)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+            "config": {"workload": workload},
+            "note": "reference arm = CPU oracle port of the same algorithm (the reference's control_box_rst + Ipopt stack cannot "
+                    "be built here: no ROS/Eigen/Ipopt, see DESIGN.md)",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "cores_detail": cores_info, "kind": "port",
                              "sample": f"{sample} instances of the workload per step, {args.steps} steps"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -191,142 +237,233 @@ def main():
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
 
-    # weak scaling: rank r solves instances [r*B, (r+1)*B) of the same seeded stream
-    data = configs.generate(CONFIG_ID, B, first=rank * B)
-    solver = capi.BatchSolver(cfg, B, device=dev)
-    N = cfg.n
-
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # one CUDA stream carries the solver kernels, the L2 flush, the export of u* and the NCCL all-gather, so that
-    # CUDA events recorded on it bracket the timed region on the device
+    def reduce_max_sum(tmax, tsum):
+        """(max over ranks of tmax, sum over ranks of tsum); every rank calls it the same number of times"""
+        if dist is None:
+            return list(tmax), list(tsum)
+        a = torch.tensor(list(tmax), dtype=torch.float64, device=f"cuda:{dev}")
+        b = torch.tensor(list(tsum), dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        return [float(x) for x in a], [float(x) for x in b]
+
     stream = torch.cuda.Stream(device=dev)
-    solver.set_stream(stream.cuda_stream)
 
-    # all-gather buffers for u* (SURVEY 8e): every rank ends up with all optimal controls
-    send = torch.empty(B * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}")
-    recv = torch.empty(world * B * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}") if world > 1 else None
-
-    # The all-gather of step i runs beside the solve of step i+1 (async NCCL work; the work stream waits for it only before the
-    # send buffer is written again and at the end of the timed region), so the ranks are not re-synchronised on every step.
-    gather = {"work": None}
-
-    def gather_wait():
-        if gather["work"] is not None:
-            gather["work"].wait()   # device-side: the work stream waits for the collective
-            gather["work"] = None
-
-    def gather_controls():
-        if world > 1:
-            gather_wait()
-            solver.export_controls(send.data_ptr())
-            gather["work"] = dist.all_gather_into_tensor(recv, send, async_op=True)
-
-    def resident_step():
-        solver.flush_l2()  # working set (68 MB) < L2 (126 MB): evict between steps
-        solver.solve_resident(cold=True)
-        gather_controls()
-
-    def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize; returns the device time between CUDA events on the work stream
-        (the last all-gather included)."""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(steps):
-                last = fn()
-            gather_wait()
-            e1.record(stream)
-        barrier()
-        return e0.elapsed_time(e1) * 1e-3, last
-
-    solver.upload(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            resident_step()
-    torch.cuda.synchronize()
-    solver.stats_reset()
-    sampler = ClockSampler(dev)
-    sampler.start()
-    el, _ = timed(resident_step, args.steps)
-    sampler.stop_flag = True
-    st = solver.stats()
-    res = solver.fetch()
-    conv_local = int((res["status"] == 0).sum())
-    iters_mean = float(res["iters"].mean())
-    # per-phase device times: one extra, untimed step with every phase bracketed by events (the brackets cost stream time,
-    # so the timed region above only brackets the KKT phase)
-    solver.set_timing(0x1f)
-    solver.stats_reset()
-    with torch.cuda.stream(stream):
-        resident_step()
-    torch.cuda.synchronize()
-    st_all = solver.stats()
-    solver.set_timing(1 << capi.PHASE_KKT)
-
-    # ---- end-to-end through the C ABI with pinned host buffers ----
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t.numpy(), t
-    keep = []
-    hx0, k = pinned(data["x0"]); keep.append(k)
-    hxf, k = pinned(data["xf"]); keep.append(k)
-    hup, k = pinned(data["u_prev"]); keep.append(k)
-    oc, k = pinned(data["obstacles"][0]); keep.append(k)
-    ot, k = pinned(data["obstacles"][1]); keep.append(k)
-    op, k = pinned(data["obstacles"][2]); keep.append(k)
 
-    def e2e_step():
-        solver.reset()
-        solver.flush_l2()
-        out = solver.step(hx0, hxf, hup, data["u_prev_dt"], (oc, ot, op), None)  # H2D inputs, solve, D2H results
-        gather_controls()
-        return out
-    with torch.cuda.stream(stream):
-        for _ in range(2):
-            e2e_step()
-    torch.cuda.synchronize()
-    st0 = solver.stats()
-    e2e_steps = max(3, args.steps // 2)
-    el_e2e, out = timed(e2e_step, e2e_steps)
-    st1 = solver.stats()
-    conv_e2e = int((out["status"] == 0).sum())
+    def measure(cid_, cfg_, B_, steps, warmup, first, want_e2e, want_gather):
+        """K timed cold batch solves of one workload on this rank.  Returns a dict of local results."""
+        data = configs.generate(cid_, B_, first=first, n=cfg_.n if cid_ == 5 else None)
+        solver = capi.BatchSolver(cfg_, B_, device=dev)
+        solver.set_stream(stream.cuda_stream)
+        N = cfg_.n
+        send = torch.empty(B_ * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}")
+        recv = torch.empty(world * B_ * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}") if (world > 1 and want_gather) else None
+        # The all-gather of step i runs beside the solve of step i+1 (async NCCL work; the work stream waits for it only before
+        # the send buffer is written again and at the end of the timed region), so the ranks are not re-synchronised every step.
+        gather = {"work": None}
 
-    # ---- max over ranks / totals ----
-    if dist is not None:
-        t = torch.tensor([el, el_e2e], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        el, el_e2e = float(t[0]), float(t[1])
-        c = torch.tensor([conv_local, conv_e2e], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        conv_total, conv_e2e_total = int(c[0]), int(c[1])
-    else:
-        conv_total, conv_e2e_total = conv_local, conv_e2e
-    # ---- continuous batching: the K steps' instances as ONE queue through the same 1024-slot pool (mpcb200_solve_stream),
-    #      host buffers in, host buffers out.  Reported next to the per-batch numbers, not instead of them; a failure here
-    #      must never take the contract line down. ----
-    reps = args.steps
-    stream_err, el_stream, conv_stream = None, 1.0, 0
-    try:
-        tile = lambda a: np.ascontiguousarray(np.concatenate([a] * reps))
-        q = dict(x0=tile(data["x0"]), xf=tile(data["xf"]), u_prev=tile(data["u_prev"]), obstacles=tuple(tile(a) for a in data["obstacles"]))
-        with torch.cuda.stream(stream):  # warm-up with the full queue: the job-sized device arrays are allocated here
-            solver.solve_stream(q["x0"], q["xf"], q["u_prev"], data["u_prev_dt"], q["obstacles"], None)
+        def gather_wait():
+            if gather["work"] is not None:
+                gather["work"].wait()
+                gather["work"] = None
+
+        def gather_controls():
+            if recv is not None:
+                gather_wait()
+                solver.export_controls(send.data_ptr())
+                gather["work"] = dist.all_gather_into_tensor(recv, send, async_op=True)
+
+        def resident_step():
+            solver.flush_l2()   # the working set of a batch fits in the 126 MB L2: evict between steps
+            solver.solve_resident(cold=True)
+            gather_controls()
+
+        def timed(fn, n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                last = None
+                for _ in range(n):
+                    last = fn()
+                gather_wait()
+                e1.record(stream)
+            barrier()
+            return e0.elapsed_time(e1) * 1e-3, last
+
+        solver.upload(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                resident_step()
         torch.cuda.synchronize()
-        el_stream, sout = timed(lambda: solver.solve_stream(q["x0"], q["xf"], q["u_prev"], data["u_prev_dt"], q["obstacles"], None), 1)
-        conv_stream = int((sout["status"] == 0).sum())
-        if dist is not None:
-            t = torch.tensor([el_stream], dtype=torch.float64, device=f"cuda:{dev}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            c = torch.tensor([conv_stream], dtype=torch.float64, device=f"cuda:{dev}")
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            el_stream, conv_stream = float(t[0]), int(c[0])
-    except Exception as e:
-        stream_err = repr(e)
+        solver.stats_reset()
+        sampler = ClockSampler(dev)
+        sampler.start()
+        el, _ = timed(resident_step, steps)
+        sampler.stop_flag = True
+        st = solver.stats()
+        res = solver.fetch()
+        out = {"el": el, "conv": int((res["status"] == 0).sum()), "iters_mean": float(res["iters"].mean()), "stats": st,
+               "clocks": sampler.summary(), "solver": solver, "data": data, "timed": timed, "gather_controls": gather_controls}
+        if want_e2e:
+            keep = []
+            hin = {}
+            for k_ in ("x0", "xf", "u_prev"):
+                hin[k_], t_ = pinned(data[k_]); keep.append(t_)
+            ob = vp = None
+            if data["obstacles"] is not None:
+                ob = []
+                for a in data["obstacles"]:
+                    h_, t_ = pinned(a); ob.append(h_); keep.append(t_)
+                ob = tuple(ob)
+            if data["viapoints"] is not None:
+                vp = []
+                for a in data["viapoints"]:
+                    h_, t_ = pinned(a); vp.append(h_); keep.append(t_)
+                vp = tuple(vp)
+            hout = solver.alloc_outputs(B_, pin=lambda a: pinned(a))   # pinned result buffers, reused by every step
+
+            def e2e_step():
+                solver.reset()
+                solver.flush_l2()
+                o = solver.step(hin["x0"], hin["xf"], hin["u_prev"], data["u_prev_dt"], ob, vp, out=hout)  # H2D, solve, D2H
+                gather_controls()
+                return o
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    e2e_step()
+            torch.cuda.synchronize()
+            st0 = solver.stats()
+            e2e_steps = max(3, steps // 2)
+            el_e2e, o = timed(e2e_step, e2e_steps)
+            st1 = solver.stats()
+            out.update(el_e2e=el_e2e, e2e_steps=e2e_steps, conv_e2e=int((o["status"] == 0).sum()),
+                       h2d=(st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps, d2h=(st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps,
+                       keep=keep)
+        return out
+
+    # ================= the contract workload =================
+    m = measure(cid, cfg, B, args.steps, args.warmup, rank * B, True, True)
+    (el, el_e2e), (conv_total, conv_e2e_total) = reduce_max_sum([m["el"], m["el_e2e"]], [m["conv"], m["conv_e2e"]])
+    solver, st, N = m["solver"], m["stats"], cfg.n
+
+    # ---- roofline: the KKT kernel alone on the first-iteration records of this batch (every instance live), L2 flushed
+    #      between the launches, CUDA events on the work stream around each launch ----
+    peak, peak_src = hbm_peak()
+    bpi = kkt_bytes_per_instance(cfg)
+    solver.reset()
+    solver.set_option(capi.OPT_SOLVE_MODE, capi.SOLVE_PHASED)
+    solver.run_phase(capi.PHASE_INIT); solver.run_phase(capi.PHASE_ASSOCIATE); solver.run_phase(capi.PHASE_EVAL)
+    solver.stats_reset()
+    kkt_ms = solver.time_phase(capi.PHASE_KKT, reps=20, flush_l2=True)
+    stk = solver.stats()
+    sweeps = stk["kkt_sweeps"] / max(stk["kkt_instances"], 1)
+    solver.set_option(capi.OPT_SOLVE_MODE, capi.SOLVE_FUSED)
+    achieved = B * bpi / (kkt_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "kkt_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("batch") == B and tj.get("config") == cid:
+                traffic = int(tj["dram_bytes_per_launch"])   # ncu --set full on this kernel at this batch (cold caches)
+        except Exception:
+            traffic = None
+    # share of the solve the KKT phase takes (SM cycles counted by the persistent kernel itself)
+    ph = st["ms"]
+    ph_sum = sum(ph) if sum(ph) > 0 else 1.0
+    roofline = {"bound": "hbm", "kernel": "kkt_warp_kernel (warp-cooperative Riccati factorisation + solve, one warp per instance)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_instance": bpi, "instances_per_launch": B, "avg_launch_ms": kkt_ms,
+                "sweeps_per_instance": sweeps,
+                "how": "kernel timed alone in this run: 20 launches on the batch's first-iteration records, L2 flushed before each, "
+                       "CUDA events on the launching stream",
+                "in_solve": {"kkt_share_of_cta_time": ph[capi.PHASE_KKT] / ph_sum,
+                             "kkt_calls": st["kkt_instances"], "sweeps_per_call": st["kkt_sweeps"] / max(st["kkt_instances"], 1),
+                             "algorithmic_gbs_over_the_step": st["kkt_instances"] * bpi / el / 1e9,
+                             "note": "inside the persistent solve kernel the records never leave shared memory"}}
+
+    # ================= secondary blocks =================
+    extra = {}
+    err_flag = 0.0
+    if not args.no_extra_configs:
+        # (a) the K steps' instances as ONE queue through the persistent kernel (mpcb200_solve_stream), host buffers in and out
+        try:
+            reps = min(args.steps, 16)
+            data = m["data"]
+            tile = lambda a: np.ascontiguousarray(np.concatenate([a] * reps))
+            q = dict(x0=tile(data["x0"]), xf=tile(data["xf"]), u_prev=tile(data["u_prev"]),
+                     obstacles=tuple(tile(a) for a in data["obstacles"]) if data["obstacles"] is not None else None,
+                     viapoints=tuple(tile(a) for a in data["viapoints"]) if data["viapoints"] is not None else None)
+            with torch.cuda.stream(stream):
+                solver.solve_stream(q["x0"], q["xf"], q["u_prev"], data["u_prev_dt"], q["obstacles"], q["viapoints"])
+            torch.cuda.synchronize()
+            el_q, sout = m["timed"](lambda: solver.solve_stream(q["x0"], q["xf"], q["u_prev"], data["u_prev_dt"], q["obstacles"], q["viapoints"]), 1)
+            extra["_queue"] = (el_q, int((sout["status"] == 0).sum()), reps)
+        except Exception as e:   # never take the contract line down; the collectives below still run on every rank
+            extra["_queue"] = (1.0, 0, 0)
+            extra["queue_error"] = repr(e)
+            err_flag = 1.0
+    solver.close()
+    if not args.no_extra_configs:
+        (elq,), (convq,) = reduce_max_sum([extra["_queue"][0]], [extra["_queue"][1]])
+        reps = extra.pop("_queue")[2]
+        if reps:
+            extra["queue"] = {"value": convq / elq, "unit": UNIT, "instances_per_gpu": reps * B, "ms_per_batch": elq / reps * 1e3,
+                              "what": "the same instances as ONE queue of K x batch through the persistent kernel (mpcb200_solve_stream: "
+                                      "continuous batching), host buffers in and out; results are bit-identical to the batch solves"}
+        # (b) BASELINE configs[3]: 16 384 via-point instances split over the ranks of this run (strong scaling across runs)
+        try:
+            g = 16384
+            b4 = g // world
+            c4 = configs.config_for(4, tol=1e-6)
+            m4 = measure(4, c4, b4, 3, 3, rank * b4, False, True)
+            r4 = (m4["el"], m4["conv"])
+            m4["solver"].close()
+        except Exception as e:
+            r4 = (1.0, 0)
+            extra["cfg4_error"] = repr(e)
+        (el4,), (conv4,) = reduce_max_sum([r4[0]], [r4[1]])
+        extra["cfg4_global16384"] = {"value": conv4 * 3 / el4, "unit": UNIT, "global_batch": 16384, "batch_per_gpu": 16384 // world,
+                                     "ms_per_step": el4 / 3 * 1e3, "scaling": "strong", "converged_fraction": conv4 / 16384.0,
+                                     "workload": WORKLOADS[4][2]}
+        if world == 1 and cid == 2:
+            # (c) BASELINE configs[2] and the horizon sweep of configs[4], one GPU
+            try:
+                c3 = configs.config_for(3, tol=1e-6)
+                m3 = measure(3, c3, 4096, 3, 3, 0, False, False)
+                extra["cfg3_b4096"] = {"value": m3["conv"] * 3 / m3["el"], "unit": UNIT, "ms_per_step": m3["el"] / 3 * 1e3,
+                                       "converged_fraction": m3["conv"] / 4096.0, "workload": WORKLOADS[3][2]}
+                m3["solver"].close()
+                sweep = []
+                for n_ in (20, 50, 100, 200):
+                    c5 = configs.config_for(5, n=n_, tol=1e-6)
+                    d5 = configs.generate(5, 2048, n=n_)
+                    s5 = capi.BatchSolver(c5, 2048, device=dev)
+                    s5.set_stream(stream.cuda_stream)
+                    s5.upload(d5["x0"], d5["xf"], d5["u_prev"], d5["u_prev_dt"], d5["obstacles"], d5["viapoints"])
+                    s5.set_option(capi.OPT_SOLVE_MODE, capi.SOLVE_PHASED)
+                    s5.run_phase(capi.PHASE_INIT); s5.run_phase(capi.PHASE_ASSOCIATE); s5.run_phase(capi.PHASE_EVAL)
+                    ms5 = s5.time_phase(capi.PHASE_KKT, reps=10, flush_l2=True)
+                    s5.set_option(capi.OPT_SOLVE_MODE, capi.SOLVE_FUSED)
+                    s5.flush_l2()
+                    t5 = s5.solve_resident(cold=True)
+                    o5 = s5.fetch()
+                    gbs = 2048 * kkt_bytes_per_instance(c5) / (ms5 * 1e-3) / 1e9
+                    sweep.append({"n": n_, "kkt_ms": ms5, "kkt_gbs": gbs, "kkt_frac_of_hbm_peak": gbs / peak,
+                                  "solves_per_s": int((o5["status"] == 0).sum()) / t5})
+                    s5.close()
+                extra["cfg5_horizon_sweep_b2048"] = sweep
+            except Exception as e:
+                extra["cfg3_cfg5_error"] = repr(e)
 
     if rank != 0:
         if dist is not None:
@@ -334,53 +471,28 @@ def main():
         return 0
 
     value = conv_total * args.steps / el
-    e2e_value = conv_e2e_total * e2e_steps / el_e2e
-    # ---- roofline of the dominant kernel (Riccati KKT) from the CUDA-event times of the timed region ----
-    peak, peak_src = hbm_peak()
-    bpi = kkt_bytes_per_instance(cfg)
-    kkt_ms = st["ms"][capi.PHASE_KKT]
-    kkt_launches = max(st["launches"][capi.PHASE_KKT], 1)
-    units = st["kkt_instances"]
-    achieved = (units * bpi) / (kkt_ms * 1e-3) / 1e9 if kkt_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "kkt_traffic.json")
-    if os.path.exists(tp):
-        try:
-            ratio = json.load(open(tp)).get("traffic_over_algorithmic")
-            traffic = int(ratio * units * bpi / kkt_launches) if ratio else None  # DRAM bytes of the average launch (ncu ratio x algorithmic)
-        except Exception:
-            traffic = None
-    total_ms = el / args.steps * 1e3 * args.steps
-    roofline = {"bound": "hbm", "kernel": "kkt_kernel (Riccati factorisation + solve)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_instance": bpi, "instances_per_launch_avg": units / kkt_launches,
-                "avg_launch_ms": kkt_ms / kkt_launches, "share_of_step": kkt_ms / total_ms if total_ms > 0 else None,
-                "sweeps_per_instance": st["kkt_sweeps"] / max(units, 1)}
+    e2e_value = conv_e2e_total * m["e2e_steps"] / el_e2e
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "horizon_n": N,
+        "config": {"workload": workload, "config_id": cid, "batch_per_gpu": B, "global_batch": B * world, "horizon_n": N,
                    "parallelism": f"instances sharded over {world} GPU(s), NCCL all-gather of u* (step i) beside the solve of step i+1" if world > 1 else "1 GPU",
-                   "l2": "flushed between steps (working set 68 MB < 126 MB L2)",
-                   "converged_fraction": conv_total / float(B * world), "mean_ipm_iterations": iters_mean},
+                   "l2": "flushed between steps (a batch's working set fits in the 126 MB L2)",
+                   "converged_fraction": conv_total / float(B * world), "mean_ipm_iterations": m["iters_mean"],
+                   "solve": "one persistent kernel per step: a CTA owns an instance from the initial guess to convergence"},
         "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": (st1["h2d_bytes"] - st0["h2d_bytes"]) // e2e_steps,
-                "d2h_bytes_per_step": (st1["d2h_bytes"] - st0["d2h_bytes"]) // e2e_steps},
-        "streaming": {"error": stream_err} if stream_err else {"value": conv_stream / el_stream, "unit": UNIT, "queue_per_gpu": reps * B, "pool_slots_per_gpu": B,
-                      "ms_per_1024": el_stream / reps * 1e3,
-                      "what": "the same K x 1024 instances per GPU as ONE queue through the 1024-slot pool (mpcb200_solve_stream, "
-                              "continuous batching: a finished slot takes the next instance), host buffers in and out; per-instance "
-                              "results are bit-identical to the batch solves"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"])},
         "gpu_launches": int(st["launches_total"]),
-        "kernel_ms": dict(zip(["init", "associate", "eval", "kkt", "linesearch"], st_all["ms"])),
-        "timing": "CUDA events on the work stream around the K steps (max over ranks); kernel_ms from one extra step with all phases bracketed",
-        "clocks": sampler.summary(),
+        "kernel_ms": dict(zip(["init", "associate", "eval", "kkt", "linesearch"], [x / args.steps for x in st["ms"]])),
+        "kernel_ms_note": "mean time a CTA of the persistent solve kernel spends in each phase per step (SM cycle counters of the kernel)",
+        "timing": "CUDA events on the work stream around the K steps (max over ranks)",
+        "clocks": m["clocks"],
+        "configs": extra,
     }
     if not args.no_cpu_baseline and world == 1:
-        v, n, conv, secs = cpu_arm(cfg, lambda n: configs.generate(CONFIG_ID, n), 20.0, threads)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        v, n, conv, secs = cpu_arm(cfg, lambda n_: configs.generate(cid, n_, n=n_h), 20.0, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "cores_detail": cores_info, "kind": "port",
                                 "sample": f"{n} instances of the same workload ({conv} converged) in {secs:.1f} s, "
                                           "CPU oracle (same algorithm, plain C, one instance per thread)"}
     elif world > 1:

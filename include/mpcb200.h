@@ -353,9 +353,6 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
 #define MPCB200_OPT_SOLVE_MODE 3
 /* MPCB200_OPT_CTAS_PER_SM: cap on the CTAs of the solve kernel resident on one SM (0 = as many as fit; tuning / experiments). */
 #define MPCB200_OPT_CTAS_PER_SM 4
-/* MPCB200_OPT_ROLES: 1 (default) = one lane does all the work of a horizon stage; 2 = the obstacle rows of the stages get lanes of
-   their own (twice the threads per instance: shorter dependent chains, more instructions in total). */
-#define MPCB200_OPT_ROLES 5
 int mpcb200_set_option(mpcb200_handle* h, int option, int value);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */

@@ -31,7 +31,6 @@ F_X, F_U, F_NU, F_S, F_LAM, F_KKT, F_STEP, F_SCAL, F_OBSIDX = range(9)
 PHASE_INIT, PHASE_ASSOCIATE, PHASE_EVAL, PHASE_KKT, PHASE_LINESEARCH = range(5)
 OPT_SOLVE_MODE = 3
 OPT_CTAS_PER_SM = 4
-OPT_ROLES = 5
 SOLVE_FUSED, SOLVE_PHASED = 0, 1
 NUM_PHASES = 5
 K_H, K_G, K_A, K_B, K_E, K_C, K_HB, K_D = 0, 15, 20, 23, 29, 32, 34, 39
@@ -314,12 +313,27 @@ class BatchSolver:
         out["solve_time_s"] = t.value
         return out
 
-    def step(self, x0, xf, u_prev=None, u_prev_dt=0.0, obstacles=None, viapoints=None, x_init=None, reinit=None):
-        """Controller::step for a batch (host arrays in, host arrays out; copies inside the call)."""
-        B, x0, xf, u_prev, o, v, xi, keep = self._prep_inputs(x0, xf, u_prev, obstacles, viapoints, x_init)
+    def alloc_outputs(self, B, pin=None):
+        """Result buffers for step(..., out=...).  pin: optional callable array -> (pinned array, owner) (e.g. through
+        torch.Tensor.pin_memory): page-locked buffers take the device-to-host copies without a staging copy."""
         N = self.N
         out = dict(u_seq=np.empty((B, N, 2)), x_seq=np.empty((B, N, 3)), dt=np.empty(B),
                    status=np.empty(B, dtype=np.int32), kkt_err=np.empty(B), iters=np.empty(B, dtype=np.int32))
+        if pin is not None:
+            owners = []
+            for k in list(out):
+                out[k], owner = pin(out[k])
+                owners.append(owner)
+            out["_owners"] = owners
+        return out
+
+    def step(self, x0, xf, u_prev=None, u_prev_dt=0.0, obstacles=None, viapoints=None, x_init=None, reinit=None, out=None):
+        """Controller::step for a batch (host arrays in, host arrays out; copies inside the call).  out: buffers of
+        alloc_outputs() to write the results into (default: fresh arrays)."""
+        B, x0, xf, u_prev, o, v, xi, keep = self._prep_inputs(x0, xf, u_prev, obstacles, viapoints, x_init)
+        N = self.N
+        if out is None:
+            out = self.alloc_outputs(B)
         t = C.c_double(0.0)
         ri = None
         if reinit is not None:

@@ -12,8 +12,7 @@
 #include "mpc_layout.h"
 
 #define FULLMASK 0xffffffffu
-#define MAX_ROLE_WARPS 4    // warps per role: one lane per stage, longer horizons wrap
-#define MAX_GROUP_WARPS (2 * MAX_ROLE_WARPS)   // the CTA that owns an instance has two roles: base lanes and obstacle-row lanes
+#define MAX_GROUP_WARPS 4   // warps of the CTA that owns one instance (lane per stage; longer horizons wrap)
 
 // ---- warp reductions (fp64 via two 32-bit shuffles each) ------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v)
@@ -349,28 +348,13 @@ __device__ __forceinline__ void evalacc_warp_reduce(EvalAcc& a)
 
 // ---- PHASE_EVAL (whole CTA, lane per stage): stage functions + derivatives -> condensed KKT records, KKT error,
 //      convergence test and barrier update.  Returns 1 (uniform) when the instance terminates. ----
-// roles = 1: a lane does all the work of its stages.  roles = 2: the CTA has two roles of nt/2 threads each, the base lanes
-// (dynamics, costs, linear rows, record) and the obstacle-row lanes of the same stages -- about half of the work of a stage
-// each; their partial sums meet in shared memory (eval_stage_merge).  Shorter chains per lane, more instructions in total.
 template <bool LINES>
-__device__ __forceinline__ int dev_eval(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt, int roles)
+__device__ __forceinline__ int dev_eval(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt)
 {
-    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5, nth = roles == 2 ? nt >> 1 : nt;
-    const int role = tid >= nth, kt = tid - role * nth;
+    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     EvalAcc a;
     evalacc_init(a);
-    if (roles == 2)
-    {
-        if (role == 0)
-            for (int k = kt; k < N; k += nth) eval_stage_base<LINES>(c, L, W, W, uprev_dt, k, a);
-        else
-            for (int k = kt; k < N; k += nth) eval_stage_obst<LINES>(c, L, W, W, uprev_dt, k, a);
-        __syncthreads();
-    }
-    else
-        for (int k = kt; k < N; k += nth) { eval_stage_base<LINES>(c, L, W, W, uprev_dt, k, a); eval_stage_obst<LINES>(c, L, W, W, uprev_dt, k, a); }
-    if (role == 0)
-        for (int k = kt; k < N; k += nth) eval_stage_merge(c, L, W, k, a);
+    for (int k = tid; k < N; k += nt) eval_stage<LINES>(c, L, W, W, uprev_dt, k, a);
     evalacc_warp_reduce(a);
     if (lane == 0) sh.eacc[wid] = a;
     __syncthreads();
@@ -408,10 +392,9 @@ __device__ __forceinline__ void dev_kkt(const Cfg& c, const WsLayout& L, double*
 
 // ---- PHASE_LINESEARCH (whole CTA, lane per stage): step lengths, l1-merit backtracking, iterate update ----
 template <bool LINES>
-__device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt, int roles)
+__device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, CtaShared& sh, int tid, int nt)
 {
-    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5, nth = roles == 2 ? nt >> 1 : nt;
-    const int role = tid >= nth, kt = tid - role * nth, part = roles == 2 ? (role ? PART_OBST : PART_BASE) : PART_ALL;
+    const int N = L.N, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     if (ASC(MPCB200_SC_STATUS) >= 0.0) return;   // the KKT phase gave the instance up
     if (ASC(MPCB200_SC_DEFER) != 0.0)
     {
@@ -426,10 +409,10 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
     // histogram of the blocking step ratios (+ row count) -> threshold bin of the clipped rows -> primal step length
     for (int j = tid; j <= CLIP_BINS; j += nt) sh.hist[j] = 0;
     __syncthreads();
-    for (int k = kt; k < N; k += nth) ls_stage_steps(c, L, W, W, uprev_dt, k, a, sh.hist, part);
+    for (int k = tid; k < N; k += nt) ls_stage_steps(c, L, W, W, uprev_dt, k, a, sh.hist);
     __syncthreads();
     const int jt = clip_threshold_bin(sh.hist, sh.hist[CLIP_BINS]);  // same value in every thread
-    for (int k = kt; k < N; k += nth) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt, part));
+    for (int k = tid; k < N; k += nt) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt));
     a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
     a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
     if (lane == 0) sh.lacc[wid] = a;
@@ -465,7 +448,7 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
     {
         TrialAcc t;
         t.obj = t.inf1 = t.blog = 0.0;
-        for (int k = kt; k < N; k += nth) ls_stage_trial<LINES>(c, L, W, W, uprev_dt, k, alpha, t, part);
+        for (int k = tid; k < N; k += nt) ls_stage_trial<LINES>(c, L, W, W, uprev_dt, k, alpha, t);
         t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
         if (lane == 0) sh.tr[wid] = t;
         __syncthreads();
@@ -487,7 +470,7 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
         for (int k = tid; k < N; k += nt) ls_stage_midpoint_fix(c, L, W, k);   // reads the old heading of stage k+1
     __syncthreads();
     const double a_dual = sh.a_dual;
-    for (int k = kt; k < N; k += nth) ls_stage_update(c, L, W, W, uprev_dt, k, alpha, a_dual, part);
+    for (int k = tid; k < N; k += nt) ls_stage_update(c, L, W, W, uprev_dt, k, alpha, a_dual);
     if (tid == 0)
     {
         if (c.variable_dt) ASC(MPCB200_SC_DT) = ASC(MPCB200_SC_DT) + alpha * ASC(MPCB200_SC_DDT);

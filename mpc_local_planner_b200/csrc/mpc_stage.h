@@ -33,16 +33,6 @@
 #define GNU(c_, k_) G[L.oNU + (c_) * N + (k_)]
 #define GS(c_, k_) G[L.oS + (c_) * N + (k_)]
 #define GLAM(c_, k_) G[L.oLAM + (c_) * N + (k_)]
-// partial sums of the evaluation (obstacle part of a stage's pose block, base part of its pose gradient): rows 5.. of the DS
-// area, which is free during the evaluation (rows 0..4 park the gradient parts until eval_finalize_stage)
-#define EPART(c_, k_) W[L.oDS + (5 + (c_)) * N + (k_)]
-#define EP_H 0
-#define EP_G0 6
-#define EP_G1 9
-#define EP_GL 12
-#define EP_HB 15
-#define EP_GLB 18
-#define EP_ROWS 21
 #define ASC(i_) W[L.oSCAL + (i_)]
 #define AIN(i_) W[L.oIN + (i_)]
 
@@ -163,7 +153,7 @@ HD inline void lin_rows_component(const Cfg& c, const WsLayout& L, const double*
 // coefficient of mu is parked in STEP[0..4][k] until the barrier parameter is decided), error accumulators.
 // LINES = false compiles the rarely used obstacle kinds out (line obstacles, moving obstacles): see footprint_distance_sc
 template <bool LINES = true>
-HD inline void eval_stage_base(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, EvalAcc& acc)
+HD inline void eval_stage(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, EvalAcc& acc)
 {
     const int N = L.N, K = L.K;
     const double dt = ASC(MPCB200_SC_DT);
@@ -413,40 +403,6 @@ HD inline void eval_stage_base(const Cfg& c, const WsLayout& L, double* W, doubl
             }
         }
     }
-    rowprod_flush(rp, acc.blog);
-    // dual infeasibility over the free controls of this stage (the pose components wait for the obstacle rows: eval_stage_merge)
-    if (k <= N - 2) acc.dual_inf = fmax(acc.dual_inf, fmax(fabs(GL[3]), fabs(GL[4])));
-#pragma unroll
-    for (int i = 0; i < 3; ++i) EPART(EP_GLB + i, k) = GL[i];
-    // store the record
-#pragma unroll
-    for (int i = 0; i < 15; ++i) AKKT(MPCB200_K_H + i, k) = H[i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) { ADS(i, k) = g0[i]; ASTEP(i, k) = g1[i]; AKKT(MPCB200_K_HB + i, k) = hb[i]; }  // g = g0 + mu g1 is stored by eval_finalize_stage
-    // (g0, g1 wait in the image -- DS / STEP are free during the evaluation -- so that the record is written exactly once)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { AKKT(MPCB200_K_A + i, k) = a3[i]; AKKT(MPCB200_K_E + i, k) = e[i]; AKKT(MPCB200_K_D + i, k) = dvec[i]; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) AKKT(MPCB200_K_B + i, k) = Bm[i];
-    AKKT(MPCB200_K_C + 0, k) = Cc[0];
-    AKKT(MPCB200_K_C + 1, k) = Cc[1];
-}
-
-// The obstacle rows of stage k (k = 1..N-2): row values and gradients for the line search (OG), their part of the pose block
-// of the record as 18 partial sums (EPART: H xx 6, g0 3, g1 3, GL 3, dt border 3) -- run by the lanes of the second role
-// beside eval_stage_base, added to the record by eval_stage_merge.
-template <bool LINES = true>
-HD inline void eval_stage_obst(const Cfg& c, const WsLayout& L, double* W, double* G, double uprev_dt, int k, EvalAcc& acc)
-{
-    const int N = L.N, K = L.K;
-    const double dt = ASC(MPCB200_SC_DT);
-    double H[15], g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, GL[3] = {0, 0, 0}, hb[3] = {0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 15; ++i) H[i] = 0.0;
-    RowProd rp; rp.p = 1.0; rp.n = 0;
-    const double x[3] = {AX(0, k), AX(1, k), AX(2, k)};
-    double sc[2] = {0.0, 1.0};
-    if (k >= 1 && k <= N - 2 && K > 0) sincos(x[2], &sc[0], &sc[1]);
     // obstacle rows (k = 1..N-2); value and gradient are kept for the line-search kernel
     if (k >= 1 && k <= N - 2)
     {
@@ -487,33 +443,27 @@ HD inline void eval_stage_obst(const Cfg& c, const WsLayout& L, double* W, doubl
         }
     }
     rowprod_flush(rp, acc.blog);
-    int q = 0;
+    // dual infeasibility over the free variables of this stage
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 5; ++i)
     {
-#pragma unroll
-        for (int jj = i; jj < 3; ++jj, ++q) EPART(EP_H + q, k) = H[hidx(i, jj)];
-        EPART(EP_G0 + i, k) = g0[i]; EPART(EP_G1 + i, k) = g1[i]; EPART(EP_GL + i, k) = GL[i]; EPART(EP_HB + i, k) = hb[i];
+        if (i < 3 && k == 0) continue;
+        if (i < 3 && k == N - 1 && c.xf_fixed[i]) continue;
+        if (i >= 3 && k == N - 1) continue;
+        acc.dual_inf = fmax(acc.dual_inf, fabs(GL[i]));
     }
-}
-
-// record of stage k = base part + obstacle part; dual infeasibility of the pose components
-HD inline void eval_stage_merge(const Cfg& c, const WsLayout& L, double* W, int k, EvalAcc& acc)
-{
-    const int N = L.N;
-    int q = 0;
+    // store the record
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-    {
+    for (int i = 0; i < 15; ++i) AKKT(MPCB200_K_H + i, k) = H[i];
 #pragma unroll
-        for (int jj = i; jj < 3; ++jj, ++q) AKKT(MPCB200_K_H + hidx(i, jj), k) += EPART(EP_H + q, k);
-        ADS(i, k) += EPART(EP_G0 + i, k);
-        ASTEP(i, k) += EPART(EP_G1 + i, k);
-        AKKT(MPCB200_K_HB + i, k) += EPART(EP_HB + i, k);
-        const double gl = EPART(EP_GLB + i, k) + EPART(EP_GL + i, k);
-        if (k == 0 || (k == N - 1 && c.xf_fixed[i])) continue;
-        acc.dual_inf = fmax(acc.dual_inf, fabs(gl));
-    }
+    for (int i = 0; i < 5; ++i) { ADS(i, k) = g0[i]; ASTEP(i, k) = g1[i]; AKKT(MPCB200_K_HB + i, k) = hb[i]; }  // g = g0 + mu g1 is stored by eval_finalize_stage
+    // (g0, g1 wait in the image -- DS / STEP are free during the evaluation -- so that the record is written exactly once)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { AKKT(MPCB200_K_A + i, k) = a3[i]; AKKT(MPCB200_K_E + i, k) = e[i]; AKKT(MPCB200_K_D + i, k) = dvec[i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) AKKT(MPCB200_K_B + i, k) = Bm[i];
+    AKKT(MPCB200_K_C + 0, k) = Cc[0];
+    AKKT(MPCB200_K_C + 1, k) = Cc[1];
 }
 
 // After the warp reduction: convergence test, monotone barrier update (Ipopt's Fiacco-McCormick rule), scalars.

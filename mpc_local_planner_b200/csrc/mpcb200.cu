@@ -81,8 +81,8 @@ __device__ __forceinline__ void mark_invalid(const WsLayout& L, double* W)
 
 // ---- kernel: ONE PHASE of the solve for every instance of a batch (kernel-level API and the phased solve mode) ----
 template <bool LINES>
-__global__ void __maxnreg__(168) phase_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, double* ws, int B, int phase,
-                                                                       double uprev_dt, int force_cold, int first_outer, int* n_active, int img_words, int roles)
+__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) phase_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, double* ws, int B, int phase,
+                                                                       double uprev_dt, int force_cold, int first_outer, int* n_active, int img_words)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ CtaShared sh;
@@ -105,11 +105,11 @@ __global__ void __maxnreg__(168) phase_kernel(const __grid_constant__ Cfg c, con
         case MPCB200_PHASE_ASSOCIATE: if (wid == 0) dev_associate(c, L, W, uprev_dt, first_outer, lane); break;
         case MPCB200_PHASE_EVAL:
         {
-            const int fin = dev_eval<LINES>(c, L, W, uprev_dt, sh, tid, nt, roles);
+            const int fin = dev_eval<LINES>(c, L, W, uprev_dt, sh, tid, nt);
             if (!fin && n_active && tid == 0) atomicAdd(n_active, 1);
             break;
         }
-        case MPCB200_PHASE_LINESEARCH: dev_linesearch<LINES>(c, L, W, uprev_dt, sh, tid, nt, roles); break;
+        case MPCB200_PHASE_LINESEARCH: dev_linesearch<LINES>(c, L, W, uprev_dt, sh, tid, nt); break;
         default: break;
     }
     stage_out(Gp, W, L.oOTYPE, tid);   // everything but the inputs
@@ -169,12 +169,11 @@ struct FusedArgs
     int force_cold;
     double uprev_dt;
     int img_words;           // resident prefix
-    int roles;               // 1: a lane does all the work of its stages, 2: base lanes + obstacle-row lanes
     int* queue;              // next instance
     unsigned long long* counters;
 };
 template <bool LINES, bool EXT>
-__global__ void __maxnreg__(168) solve_fused_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, const __grid_constant__ FusedArgs a)
+__global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, const __grid_constant__ FusedArgs a)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ CtaShared sh;
@@ -224,7 +223,7 @@ __global__ void __maxnreg__(168) solve_fused_kernel(const __grid_constant__ Cfg 
                 TICK(MPCB200_PHASE_ASSOCIATE);
                 for (;;)
                 {
-                    const int fin = dev_eval<LINES>(c, L, W, a.uprev_dt, sh, tid, nt, a.roles);
+                    const int fin = dev_eval<LINES>(c, L, W, a.uprev_dt, sh, tid, nt);
                     TICK(MPCB200_PHASE_EVAL);
                     if (fin) break;
                     if (wid == 0) dev_kkt<EXT>(c, L, W, ex, &n_sweeps);
@@ -232,7 +231,7 @@ __global__ void __maxnreg__(168) solve_fused_kernel(const __grid_constant__ Cfg 
                     TICK(MPCB200_PHASE_KKT);
                     if (tid == 0) ++n_kkt;
                     if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // inertia correction failed: given up
-                    dev_linesearch<LINES>(c, L, W, a.uprev_dt, sh, tid, nt, a.roles);
+                    dev_linesearch<LINES>(c, L, W, a.uprev_dt, sh, tid, nt);
                     TICK(MPCB200_PHASE_LINESEARCH);
                     if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // jammed: given up
                 }
@@ -343,7 +342,6 @@ struct mpcb200_handle
     int has_lines;  // line obstacles in the batch, moving obstacles or midpoint differences: the kernels are launched with those (rarely used) paths compiled in
     double uprev_dt;
     int fused_grid;  // CTAs of the last fused launch
-    int roles;            // MPCB200_OPT_ROLES: 1 (default) or 2 roles of lanes per instance
     int max_ctas_per_sm;  // MPCB200_OPT_CTAS_PER_SM: cap on the resident CTAs per SM of the solve kernel (0 = what fits)
     mpcb200_stats stats;
     std::vector<cudaEvent_t> ev;  // pool of event pairs
@@ -446,7 +444,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
     h->n_cap = cfg->n; h->d_resample = nullptr; h->d_cm = nullptr; h->cm_cap = 0; h->costmap_ms = 0.0;
     h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0; h->has_lines = 0;
-    h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0; h->max_ctas_per_sm = 0; h->roles = 1;
+    h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0; h->max_ctas_per_sm = 0;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
         cudaError_t e_ = (call);                                                                                   \
@@ -549,7 +547,7 @@ static void ev_collect(mpcb200_handle* h)
 static int group_threads(const mpcb200_handle* h)
 {
     const int gw = (h->cfg.n + 31) / 32;
-    return h->roles * 32 * (gw < MAX_ROLE_WARPS ? gw : MAX_ROLE_WARPS);   // a lane per stage in each role
+    return 32 * (gw < MAX_GROUP_WARPS ? gw : MAX_GROUP_WARPS);   // a lane per stage
 }
 static int image_words(const mpcb200_handle* h) { return resident_words(h->L, h->has_obst ? h->obst_max : 0); }
 
@@ -566,8 +564,8 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
     }
     else if (phase >= 0 && phase < MPCB200_NUM_PHASES)
     {
-        if (h->has_lines) phase_kernel<true><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words, h->roles);
-        else phase_kernel<false><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words, h->roles);
+        if (h->has_lines) phase_kernel<true><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words);
+        else phase_kernel<false><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words);
     }
     else return set_err(h, MPCB200_E_INVALID, "unknown phase");
     if (timed) ev_end(h);
@@ -677,7 +675,7 @@ static int launch_fused(mpcb200_handle* h, int total, int queue_mode, int force_
 {
     FusedArgs a;
     a.ws = h->ws; a.in = in; a.out = out; a.total = total; a.queue_mode = queue_mode; a.force_cold = force_cold; a.uprev_dt = h->uprev_dt;
-    a.img_words = image_words(h); a.roles = h->roles; a.queue = h->d_queue; a.counters = h->d_counters;
+    a.img_words = image_words(h); a.queue = h->d_queue; a.counters = h->d_counters;
     const size_t smem = IMG_HEAD + (size_t)a.img_words * 8;
     if (smem > MAX_IMG_SMEM) return set_err(h, MPCB200_E_UNSUPPORTED, "the instance does not fit in shared memory");
     const int threads = group_threads(h);
@@ -1037,7 +1035,6 @@ extern "C" int mpcb200_set_option(mpcb200_handle* h, int option, int value)
     if (!h) return MPCB200_E_INVALID;
     if (option == MPCB200_OPT_SOLVE_MODE && value >= 0 && value <= 1) { h->solve_mode = value; return 0; }
     if (option == MPCB200_OPT_CTAS_PER_SM && value >= 0 && value <= 32) { h->max_ctas_per_sm = value; return 0; }
-    if (option == MPCB200_OPT_ROLES && (value == 1 || value == 2)) { h->roles = value; return 0; }
     return set_err(h, MPCB200_E_INVALID, "unknown option or value");
 }
 

@@ -180,7 +180,7 @@ int emu_eval(const Cfg* cp, double* W, double uprev_dt)
     for (int l = 0; l < 32; ++l)
     {
         evalacc_init(a[l]);
-        for (int k = l; k < N; k += 32) { eval_stage_base(c, L, W, W, uprev_dt, k, a[l]); eval_stage_obst(c, L, W, W, uprev_dt, k, a[l]); eval_stage_merge(c, L, W, k, a[l]); }
+        for (int k = l; k < N; k += 32) eval_stage(c, L, W, W, uprev_dt, k, a[l]);
     }
     reduce_eval(a);
     int fin = 0;
