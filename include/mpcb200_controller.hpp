@@ -245,7 +245,9 @@ class Controller
         {
             // success iff the solver status is Converged or EarlyTerminated
             _ocp_successful = (status == MPCB200_STATUS_CONVERGED || status == MPCB200_STATUS_MAX_ITER);
-            _grid_empty = false;
+            // a failed solve (numerical error, invalid input) leaves no trajectory to warm-start from: the device keeps the
+            // instance cold, and the grid counts as empty here (the reference's planner resets the controller after a failed step)
+            _grid_empty = !_ocp_successful;
             if (u_seq) fill(*u_seq, _u, 2, N, dt_out);
             if (x_seq) fill(*x_seq, _x, 3, N, dt_out);
             _last_dt = dt_out; _last_status = status; _last_iters = iters; _last_kkt = kkt; _last_solve_time = secs;

@@ -1136,8 +1136,10 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * 40);
     CostmapArgs a{maps->size_x, maps->size_y, maps->resolution, behind_robot_dist, d_cost, d_origin, d_pose};
     const dim3 grid_mark((unsigned)((W / 4 + 1 + 63) / 64), (unsigned)B), grid_emit((unsigned)((W + 127) / 128), (unsigned)B);
-    cudaEvent_t t0, t1;
-    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    cudaEvent_t t0 = h->t0, t1 = h->t1;
+    // slots behind count[b] are padding: zeroed, so that what goes back to the caller (and on into step_batch) is defined
+    CK(cudaMemsetAsync(d_type, 0, (size_t)B * M * 4, h->stream));
+    CK(cudaMemsetAsync(d_params, 0, (size_t)B * M * MPCB200_OBST_STRIDE * 8, h->stream));
     CK(cudaEventRecord(t0, h->stream));
     if (W % 4 == 0) costmap_mark_kernel<true><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
     else costmap_mark_kernel<false><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
@@ -1155,7 +1157,6 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, t0, t1));
     h->costmap_ms = ms;
-    cudaEventDestroy(t0); cudaEventDestroy(t1);
     return MPCB200_OK;
 }
 

@@ -93,24 +93,23 @@ def test_full_size_batches(cuda_lib, orc, cid, B, n):
     ref = orc.step_batch(cfg, subd, n_threads=8)
     both = (ref["status"] == 0) & (out["status"][pick] == 0)
     assert both.sum() >= 4
-    assert (ref["status"] == out["status"][pick]).mean() >= 0.75
+    assert (ref["status"] == out["status"][pick]).sum() >= 62   # of 64 (whole batches agree on >= 99.9 %: profiles/r2_parity_report.txt)
     du = np.abs(ref["u_seq"][both] - out["u_seq"][pick][both]).reshape(both.sum(), -1).max(axis=1)
     if cfg.variable_dt:
         # minimum-time optima need not be strict: the optimal time agrees everywhere, the controls on most instances
         assert np.abs(ref["dt"][both] - out["dt"][pick][both]).max() < 1e-5
-        assert (du < U_TOL).mean() >= 0.7
+        assert (du < U_TOL).mean() >= 0.8
     else:
         # tol 1e-6 here (BASELINE), so allow the distance two tol-1e-6 solutions of the same problem can have; on a rare
         # instance rounding differences between CPU and GPU send the two iterations to different local optima
         # (tools/parity_report.py: 1 in 1000 at N = 50)
-        assert (du < 1e-3).mean() >= 0.95 and (du < U_TOL).mean() >= 0.8
+        assert (du < 1e-3).mean() >= 0.97 and (du < U_TOL).mean() >= 0.9
     s.close()
 
 
 def test_machine_filling_batch_matches_small_batch(cuda_lib):
-    """A batch large enough to fill the SMs runs the regularisation attempts one after the other inside the KKT kernel
-    (small batches run them side by side): an execution choice only, the first 96 instances come out bit-identical to
-    a 96-instance batch."""
+    """A batch many times larger than the resident CTAs of the persistent solve kernel (every CTA works through dozens of
+    instances of the queue): the first 96 instances come out bit-identical to a 96-instance batch."""
     cfg = configs.config_for(2, tol=1e-6)
     base = configs.generate(2, 2048)
     B = 32768

@@ -75,12 +75,13 @@ def test_solve_parity(cuda_lib, orc, cid, B):
     s = _solver(cfg, B)
     out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], data["viapoints"])
     ref = orc.step_batch(cfg, data, n_threads=4)
-    # the status may differ on a marginal instance (e.g. converging at iteration 99 vs 101): allow a few
-    agree = (out["status"] == ref["status"]).mean()
+    # the status may differ on a marginal instance (e.g. converging at iteration 99 vs 101): at most one of these batches
+    # (whole batches of 1024 agree on every status: profiles/r2_parity_report.txt)
+    agree = (out["status"] == ref["status"]).sum()
     both = (out["status"] == 0) & (ref["status"] == 0)
     n_ref = max((ref["status"] == 0).sum(), 1)
-    assert agree >= 0.8, f"status agreement {agree}: gpu {out['status']} oracle {ref['status']}"
-    assert both.sum() >= 1 and both.sum() >= 0.75 * n_ref, f"gpu {out['status']} oracle {ref['status']}"
+    assert agree >= B - 1, f"status agreement {agree}/{B}: gpu {out['status']} oracle {ref['status']}"
+    assert both.sum() >= 1 and both.sum() >= n_ref - 1, f"gpu {out['status']} oracle {ref['status']}"
     du = np.abs(out["u_seq"][both] - ref["u_seq"][both]).max(axis=(1, 2))
     assert np.abs(out["dt"][both] - ref["dt"][both]).max() < 1e-6
     if cfg.variable_dt and B > 1:
@@ -89,7 +90,8 @@ def test_solve_parity(cuda_lib, orc, cid, B):
         assert (du < U_TOL).mean() >= 0.8, f"du {du}"
         both = both & (np.abs(out["u_seq"] - ref["u_seq"]).max(axis=(1, 2)) < U_TOL)
     else:
-        assert du.max() < U_TOL, f"du {du}"
+        assert (du < U_TOL).sum() >= len(du) - 1, f"du {du}"   # at most one instance in another local optimum (non-convex problem)
+        both = both & (np.abs(out["u_seq"] - ref["u_seq"]).max(axis=(1, 2)) < U_TOL)
     # (x wrapped) states agree too
     dx = out["x_seq"][both] - ref["x_seq"][both]
     dx[..., 2] = (dx[..., 2] + np.pi) % (2 * np.pi) - np.pi
