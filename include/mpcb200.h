@@ -149,6 +149,14 @@ typedef struct mpcb200_config {
        (N-1) dt to the quadratic control cost.  As in the reference it takes effect only with zero state weights Q and
        non-zero control weights R (and needs variable_dt); with any other weights the plain quadratic form is used. */
     int hybrid_cost_minimum_time;
+    /* Cold initial guess exactly as the reference builds it (full_discretization_grid_base_se2.cpp:192-239: states on the
+       straight line start -> goal or on the supplied plan, zero controls, dt = dt_ref): 1 switches the solver-side
+       preprocessing off -- no choice among bumped lines (initial_guess_bumps is ignored), no repair of poses that violate
+       obstacle rows, no control seeding.  Default 0: the preprocessing is ON, i.e. the default cold start is NOT the
+       reference's; it is the one that lets 99.7 % instead of ~60 % of the BASELINE instances converge within the
+       reference's 100 iterations (DESIGN.md "cold initial guess").  A locally convergent method inherits the homotopy class of
+       its starting point, so the two modes may return different local optima of the same problem. */
+    int reference_initial_guess;
 } mpcb200_config;
 
 /* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]). */
@@ -248,6 +256,21 @@ typedef struct mpcb200_costmaps {
 int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* robot_pose /*[B*3]*/,
                               double behind_robot_dist, int max_per_instance, int* count /*[B]*/, int* found /*[B] or NULL*/,
                               int* type /*[B*max]*/, double* params /*[B*max*MPCB200_OBST_STRIDE]*/);
+/*
+ * Footprint-vs-costmap feasibility of the planned poses for B robots: replaces Controller::isPoseTrajectoryFeasible
+ * (src/controller.cpp:859-917; caller src/mpc_local_planner_ros.cpp:414-428, which resets the planner on a rejection).
+ * The footprint polygon (footprint_xy: n_footprint points in the robot frame = costmap_2d's footprint spec; fewer than 3 points
+ * = "circular robot": only the centre cell is looked up) is laid over the robot's costmap at poses 0..look_ahead_idx of its
+ * trajectory (look_ahead_idx < 0 or >= n: all poses = collision_check_no_poses -1) and, wherever two consecutive poses are
+ * farther apart than inscribed_radius or turn by more than min_resolution_angular (collision_check_min_resolution_angular), at
+ * evenly spaced poses in between.  feasible[b] = 0 iff some footprint cost is -1 (a LETHAL cell under an edge, or the centre
+ * outside the map) -- exactly the reference's test (footprint vertices outside the map and unknown cells do not reject).
+ *   x_seq  [B][n_poses][3] host trajectories, or NULL: the trajectories of the last solve, read on the device (n = config.n).
+ * circumscribed_radius is accepted for signature parity (base_local_planner::CostmapModel::footprintCost ignores it too).
+ */
+int mpcb200_check_feasible(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* x_seq, int n_poses,
+                           const double* footprint_xy, int n_footprint, double inscribed_radius, double circumscribed_radius,
+                           double min_resolution_angular, int look_ahead_idx, unsigned char* feasible /*[B]*/);
 /* device time (ms, CUDA events around the three kernels) of the last mpcb200_costmap_obstacles call */
 double mpcb200_costmap_last_ms(const mpcb200_handle* h);
 

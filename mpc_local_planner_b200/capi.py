@@ -86,6 +86,7 @@ class Config(C.Structure):
         ("terminal_ball_gamma", C.c_double),
         ("cost_integration", C.c_int),
         ("hybrid_cost_minimum_time", C.c_int),
+        ("reference_initial_guess", C.c_int),
     ]
 
     def copy(self):
@@ -186,7 +187,7 @@ EXPORTS = [
     "mpcb200_default_config", "mpcb200_create", "mpcb200_step_batch", "mpcb200_reset", "mpcb200_destroy",
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
-    "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
+    "mpcb200_check_feasible", "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
     "mpcb200_resample", "mpcb200_get_horizon", "mpcb200_costmap_obstacles", "mpcb200_costmap_last_ms",
 ]
 
@@ -232,6 +233,7 @@ def load_library(path=None):
     lib.mpcb200_ws_read.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.mpcb200_ws_write.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.mpcb200_run_phase.argtypes = [vp, C.c_int, C.c_int]
+    lib.mpcb200_check_feasible.argtypes = [vp, C.c_int, C.POINTER(Costmaps), dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_ubyte)]
     lib.mpcb200_time_phase.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     lib.mpcb200_set_timing.argtypes = [vp, C.c_uint]
     lib.mpcb200_set_stream.argtypes = [vp, vp]
@@ -388,6 +390,21 @@ class BatchSolver:
         self._check(self.lib.mpcb200_costmap_obstacles(self.h, B, C.byref(m), _dp(pose), float(behind_robot_dist), M, _ip(count), _ip(found),
                                                        _ip(typ), _dp(par)), "mpcb200_costmap_obstacles")
         return (count, typ, par), found
+
+    def check_feasible(self, cost, origin, resolution, footprint, inscribed_radius, min_resolution_angular, look_ahead_idx=-1, x_seq=None,
+                       circumscribed_radius=0.0):
+        """isPoseTrajectoryFeasible for B robots: cost [B, size_y, size_x] uint8, origin [B, 2], footprint [n_fp, 2] (robot frame);
+        x_seq [B, n, 3] or None = the trajectories of the last solve on the device.  -> bool [B]"""
+        cost = np.ascontiguousarray(cost, dtype=np.uint8); origin = np.ascontiguousarray(origin, dtype=np.float64)
+        fp = np.ascontiguousarray(footprint, dtype=np.float64).reshape(-1, 2)
+        B = cost.shape[0]
+        m = Costmaps(cost.shape[2], cost.shape[1], float(resolution), _dp(origin), cost.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        xs = np.ascontiguousarray(x_seq, dtype=np.float64) if x_seq is not None else None
+        ok = np.zeros(B, dtype=np.uint8)
+        self._check(self.lib.mpcb200_check_feasible(self.h, B, C.byref(m), _dp(xs), xs.shape[1] if xs is not None else 0, _dp(fp), fp.shape[0],
+                                                    float(inscribed_radius), float(circumscribed_radius), float(min_resolution_angular),
+                                                    int(look_ahead_idx), ok.ctypes.data_as(C.POINTER(C.c_ubyte))), "mpcb200_check_feasible")
+        return ok.astype(bool)
 
     def costmap_last_ms(self):
         return float(self.lib.mpcb200_costmap_last_ms(self.h))

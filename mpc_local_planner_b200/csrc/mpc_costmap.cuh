@@ -138,3 +138,117 @@ __global__ void costmap_offsets_kernel(int size_x, int B, const int* colcount, i
     if (threadIdx.x == 0) { found[b] = carry; count[b] = carry < max_out ? carry : max_out; }
 }
 
+
+// ---- footprint-vs-costmap feasibility of a pose trajectory: Controller::isPoseTrajectoryFeasible (src/controller.cpp:859-917,
+//      called at src/mpc_local_planner_ros.cpp:414-428) for B robots.  One warp per robot, one lane per interval of the
+//      trajectory: the lane checks pose i and the poses interpolated between i and i+1 (accumulated step by step, as the
+//      reference does), every check rasterises the footprint edges over the robot's map (byte gathers).
+//      [EXT] CostmapModel::footprintCost / lineCost / pointCost, LineIterator, Costmap2D::worldToMap restated from upstream
+//      knowledge of ROS navigation (see oracle/mpc_oracle.c: orc_pose_trajectory_feasible). ----
+struct FeasArgs
+{
+    int size_x, size_y;
+    double resolution;
+    const unsigned char* cost;   // [B][size_y][size_x]
+    const double* origin;        // [B][2]
+    const double* xseq;          // [B][n][3]
+    int n;
+    const double* footprint;     // [n_fp][2], robot frame
+    int n_fp;
+    double inscribed_radius, min_resolution_angular;
+    int look_ahead_idx;
+};
+__device__ __forceinline__ bool feas_world_to_map(const FeasArgs& a, double ox, double oy, double wx, double wy, int* mx, int* my)
+{
+    if (wx < ox || wy < oy) return false;
+    *mx = (int)((wx - ox) / a.resolution);
+    *my = (int)((wy - oy) / a.resolution);
+    return *mx < a.size_x && *my < a.size_y;
+}
+__device__ __forceinline__ double feas_line_cost(const FeasArgs& a, const unsigned char* map, int x0, int x1, int y0, int y1)
+{
+    const int deltax = abs(x1 - x0), deltay = abs(y1 - y0);
+    int x = x0, y = y0, xinc1, xinc2, yinc1, yinc2, den, num, numadd, numpixels;
+    if (x1 >= x0) { xinc1 = 1; xinc2 = 1; } else { xinc1 = -1; xinc2 = -1; }
+    if (y1 >= y0) { yinc1 = 1; yinc2 = 1; } else { yinc1 = -1; yinc2 = -1; }
+    if (deltax >= deltay) { xinc1 = 0; yinc2 = 0; den = deltax; num = deltax / 2; numadd = deltay; numpixels = deltax; }
+    else { xinc2 = 0; yinc1 = 0; den = deltay; num = deltay / 2; numadd = deltax; numpixels = deltay; }
+    double line_cost = 0.0;
+    for (int cur = 0; cur <= numpixels; ++cur)
+    {
+        const unsigned char c = map[(size_t)y * a.size_x + x];
+        const double pc = c == 255 ? -2.0 : (c == 254 ? -1.0 : (double)c);
+        if (pc < 0) return pc;
+        if (line_cost < pc) line_cost = pc;
+        num += numadd;
+        if (num >= den) { num -= den; x += xinc1; y += yinc1; }
+        x += xinc2; y += yinc2;
+    }
+    return line_cost;
+}
+__device__ __forceinline__ double feas_footprint_cost(const FeasArgs& a, const unsigned char* map, double ox, double oy, double px, double py, double th)
+{
+    int cx, cy;
+    if (!feas_world_to_map(a, ox, oy, px, py, &cx, &cy)) return -1.0;
+    if (a.n_fp < 3)
+    {
+        const unsigned char c = map[(size_t)cy * a.size_x + cx];
+        if (c == 255) return -2.0;
+        if (c == 254 || c == 253) return -1.0;
+        return (double)c;
+    }
+    double si, co;
+    sincos(th, &si, &co);
+    double fc = 0.0;
+    for (int i = 0; i < a.n_fp; ++i)
+    {
+        const int j = (i + 1) % a.n_fp;
+        const double fix = a.footprint[2 * i], fiy = a.footprint[2 * i + 1], fjx = a.footprint[2 * j], fjy = a.footprint[2 * j + 1];
+        const double ax = px + (fix * co - fiy * si), ay = py + (fix * si + fiy * co);
+        const double bx = px + (fjx * co - fjy * si), by = py + (fjx * si + fjy * co);
+        int x0, y0, x1, y1;
+        if (!feas_world_to_map(a, ox, oy, ax, ay, &x0, &y0)) return -3.0;
+        if (!feas_world_to_map(a, ox, oy, bx, by, &x1, &y1)) return -3.0;
+        const double lc = feas_line_cost(a, map, x0, x1, y0, y1);
+        if (fc < lc) fc = lc;
+        if (lc < 0) return lc;
+    }
+    return fc;
+}
+__global__ void feasible_kernel(FeasArgs a, int B, unsigned char* feasible)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const unsigned char* map = a.cost + (size_t)b * a.size_x * a.size_y;
+    const double ox = a.origin[2 * b], oy = a.origin[2 * b + 1];
+    const double* xs = a.xseq + (size_t)b * a.n * 3;
+    int look = a.look_ahead_idx;
+    if (look < 0 || look >= a.n) look = a.n - 1;
+    bool ok = a.n >= 2;
+    for (int i = lane; i <= look && ok; i += 32)
+    {
+        const double px = xs[3 * i], py = xs[3 * i + 1], pth = xs[3 * i + 2];
+        if (feas_footprint_cost(a, map, ox, oy, px, py, pth) == -1.0) { ok = false; break; }
+        if (i < look)
+        {
+            const double delta_rot = normalize_theta(xs[3 * i + 5] - pth);
+            const double dx = xs[3 * i + 3] - px, dy = xs[3 * i + 4] - py;
+            const double dist = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            if (fabs(delta_rot) > a.min_resolution_angular || dist > a.inscribed_radius)
+            {
+                const double ca = ceil(fabs(delta_rot) / a.min_resolution_angular), cb = ceil(dist / a.inscribed_radius);
+                const int n_add = (int)(ca > cb ? ca : cb) - 1;
+                double ix = px, iy = py, ith = pth;
+                for (int step = 0; step < n_add; ++step)
+                {
+                    ix = ix + dx / (n_add + 1.0);
+                    iy = iy + dy / (n_add + 1.0);
+                    ith = normalize_theta(ith + delta_rot / (n_add + 1.0));
+                    if (feas_footprint_cost(a, map, ox, oy, ix, iy, ith) == -1.0) { ok = false; break; }
+                }
+            }
+        }
+    }
+    const bool all_ok = __all_sync(FULLMASK, ok) != 0;
+    if (lane == 0) feasible[b] = all_ok ? 1 : 0;
+}

@@ -224,7 +224,8 @@ __device__ __forceinline__ void dev_init(const Cfg& c, const WsLayout& L, double
 __device__ __forceinline__ void dev_associate(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int first_outer, int lane)
 {
     const int N = L.N;
-    const bool repair = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
+    const bool cold_pending = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
+    const bool repair = cold_pending && !c.reference_initial_guess;   // solver-side preprocessing of a cold guess (off: the reference's guess)
     __syncwarp();
     for (int k = lane; k < N; k += 32) associate_stage(c, L, W, k);
     // via-points: MinTimeViaPointsCost::update with findClosestPose (argmin over the grid, first minimum wins)
@@ -313,7 +314,7 @@ __device__ __forceinline__ void dev_associate(const Cfg& c, const WsLayout& L, d
         ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
         ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
         ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0; ASC(MPCB200_SC_DEFER) = 0.0;
-        if (repair) ASC(MPCB200_SC_COLD) = 0.0;
+        if (cold_pending) ASC(MPCB200_SC_COLD) = 0.0;
         ASC(MPCB200_SC_STATUS) = -1.0;
     }
     __syncwarp();

@@ -895,7 +895,7 @@ HD inline void init_cold_stage(const Cfg& c, const WsLayout& L, double* W, int k
 #define BUMP_MARGIN 0.05
 HD inline bool bump_enabled(const Cfg& c, const WsLayout& L, const double* W)
 {
-    return c.initial_guess_bumps > 0 && AIN(IN_HASXINIT) == 0.0 && (int)AIN(IN_NOBST) > 0;
+    return c.initial_guess_bumps > 0 && !c.reference_initial_guess && AIN(IN_HASXINIT) == 0.0 && (int)AIN(IN_NOBST) > 0;
 }
 HD inline bool bump_normal(const WsLayout& L, const double* W, double* nx, double* ny)
 {

@@ -318,7 +318,8 @@ struct mpcb200_handle
     int max_batch, device, B;
     int n_cap;                  // horizon the buffers were sized for at create (mpcb200_resample moves cfg.n within [3, n_cap])
     double* d_resample;         // scratch of mpcb200_resample, allocated on first use
-    void* d_cm; size_t cm_cap; double costmap_ms;  // scratch of mpcb200_costmap_obstacles (grown on demand), device ms of its last call
+    void* d_cm; size_t cm_cap; double costmap_ms;
+    void* d_fz; size_t fz_cap;   // scratch of mpcb200_check_feasible (maps, trajectories, footprint, flags)  // scratch of mpcb200_costmap_obstacles (grown on demand), device ms of its last call
     double* ws;
     int num_sms, clock_khz;
     int solve_mode;             // MPCB200_OPT_SOLVE_MODE: 0 fused persistent kernel (default), 1 one kernel per phase
@@ -442,7 +443,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     h->cfg = *cfg; h->max_batch = max_batch; h->device = device; h->B = 0; h->ws = nullptr; h->ev_used = 0;
     memset(&h->stats, 0, sizeof(h->stats));
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
-    h->n_cap = cfg->n; h->d_resample = nullptr; h->d_cm = nullptr; h->cm_cap = 0; h->costmap_ms = 0.0;
+    h->n_cap = cfg->n; h->d_resample = nullptr; h->d_cm = nullptr; h->cm_cap = 0; h->costmap_ms = 0.0; h->d_fz = nullptr; h->fz_cap = 0;
     h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0; h->has_lines = 0;
     h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0; h->max_ctas_per_sm = 0;
 #define CKC(call)                                                                                                  \
@@ -499,7 +500,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
                     h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_queue, h->d_flush, h->d_counters};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* sptrs[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
-                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_resample, h->d_cm};
+                     h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_resample, h->d_cm, h->d_fz};
     for (void* p : sptrs) if (p) cudaFree(p);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
@@ -1157,6 +1158,51 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, t0, t1));
     h->costmap_ms = ms;
+    return MPCB200_OK;
+}
+
+extern "C" int mpcb200_check_feasible(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* x_seq, int n_poses, const double* footprint_xy,
+                                      int n_footprint, double inscribed_radius, double circumscribed_radius, double min_resolution_angular,
+                                      int look_ahead_idx, unsigned char* feasible)
+{
+    (void)circumscribed_radius;   // CostmapModel::footprintCost does not use it either
+    if (!h) return MPCB200_E_INVALID;
+    if (B < 1 || !maps || !maps->cost || !maps->origin || !feasible || n_footprint < 0 || (n_footprint > 0 && !footprint_xy))
+        return set_err(h, MPCB200_E_INVALID, "check_feasible: B >= 1, maps, footprint and the output array are required");
+    if (maps->size_x < 1 || maps->size_y < 1 || !(maps->resolution > 0)) return set_err(h, MPCB200_E_INVALID, "check_feasible: bad map geometry");
+    if (!(inscribed_radius > 0) || !(min_resolution_angular > 0)) return set_err(h, MPCB200_E_INVALID, "check_feasible: inscribed_radius and min_resolution_angular must be > 0");
+    const int n = x_seq ? n_poses : h->cfg.n;
+    if (n < 1) return set_err(h, MPCB200_E_INVALID, "check_feasible: n_poses >= 1 required");
+    if (!x_seq && (h->B < B)) return set_err(h, MPCB200_E_INVALID, "check_feasible: no solved batch of this size on the device (pass x_seq)");
+    CK(cudaSetDevice(h->device));
+    const size_t W = (size_t)maps->size_x, H = (size_t)maps->size_y;
+    const size_t need = (size_t)B * n * 24 + (size_t)B * 16 + (size_t)(n_footprint > 0 ? n_footprint : 1) * 16 + (size_t)B * W * H + (size_t)B + 256;
+    if (need > h->fz_cap)
+    {
+        if (h->d_fz) cudaFree(h->d_fz);
+        h->d_fz = nullptr; h->fz_cap = 0;
+        CK(cudaMalloc(&h->d_fz, need));
+        h->fz_cap = need;
+    }
+    char* p = (char*)h->d_fz;
+    double* d_x = (double*)p; p += (size_t)B * n * 24;
+    double* d_origin = (double*)p; p += (size_t)B * 16;
+    double* d_fp = (double*)p; p += (size_t)(n_footprint > 0 ? n_footprint : 1) * 16;
+    unsigned char* d_cost = (unsigned char*)p; p += (size_t)B * W * H;
+    unsigned char* d_ok = (unsigned char*)p;
+    CK(cudaMemcpyAsync(d_cost, maps->cost, (size_t)B * W * H, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_origin, maps->origin, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
+    if (n_footprint > 0) CK(cudaMemcpyAsync(d_fp, footprint_xy, (size_t)n_footprint * 16, cudaMemcpyHostToDevice, h->stream));
+    if (x_seq) CK(cudaMemcpyAsync(d_x, x_seq, (size_t)B * n * 24, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * 16 + (size_t)n_footprint * 16 + (x_seq ? (size_t)B * n * 24 : 0));
+    FeasArgs a{maps->size_x, maps->size_y, maps->resolution, d_cost, d_origin, x_seq ? d_x : h->d_xseq, n, d_fp, n_footprint,
+               inscribed_radius, min_resolution_angular, look_ahead_idx};
+    feasible_kernel<<<grid_for(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, h->stream>>>(a, B, d_ok);
+    h->stats.launches_total += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(feasible, d_ok, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += B;
+    CK(cudaStreamSynchronize(h->stream));
     return MPCB200_OK;
 }
 

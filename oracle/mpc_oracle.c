@@ -743,7 +743,7 @@ void orc_init_cold(const orc_problem* p, const double* x_init, orc_ws* ws)
         ws->U[IX(1, k)] = 0.0;
     }
     ws->SCAL[MPCB200_SC_DT] = p->cfg->dt_ref;
-    const int nb = p->cfg->initial_guess_bumps;
+    const int nb = p->cfg->reference_initial_guess ? 0 : p->cfg->initial_guess_bumps;   /* reference guess: the straight line itself */
     if (!x_init && nb > 0 && p->n_obst > 0)
     {
         double nx = -(p->xf[1] - p->x0[1]), ny = p->xf[0] - p->x0[0];
@@ -796,6 +796,110 @@ int orc_costmap_obstacles(int size_x, int size_y, double resolution, const doubl
             ++found;
         }
     return found;
+}
+
+/*
+ * Controller::isPoseTrajectoryFeasible [R/src/controller.cpp:859-917], called by MpcLocalPlannerROS::computeVelocityCommands
+ * [R/src/mpc_local_planner_ros.cpp:414-428]: the footprint is laid over the costmap at the first look_ahead_idx + 1 poses of
+ * the trajectory and, where two consecutive poses are farther apart than the inscribed radius or turn more than
+ * min_resolution_collision_check_angular, at evenly spaced poses between them (the intermediate pose is ACCUMULATED step by
+ * step, :903-906).  Infeasible <=> some footprintCost == -1.
+ * [EXT] base_local_planner::CostmapModel::footprintCost / lineCost / pointCost and LineIterator, costmap_2d::Costmap2D::worldToMap
+ * (ROS navigation; not in /root/reference -- restated from upstream knowledge):
+ *   centre outside the map -> -1;  fewer than 3 footprint points: cost of the centre cell, LETHAL (254) or INSCRIBED (253) -> -1,
+ *   NO_INFORMATION (255) -> -2;  else every footprint edge (closing edge included) is rasterised with the Bresenham LineIterator:
+ *   a vertex outside the map -> -3 (NOT -1: such a pose passes the check), a LETHAL cell -> -1, a NO_INFORMATION cell -> -2.
+ * x_seq: [n][3] poses.  footprint: n_fp points (x, y) in the robot frame.  Returns 1 = feasible, 0 = not.
+ */
+static int orc_world_to_map(int size_x, int size_y, double res, const double* origin, double wx, double wy, int* mx, int* my)
+{
+    if (wx < origin[0] || wy < origin[1]) return 0;
+    *mx = (int)((wx - origin[0]) / res);
+    *my = (int)((wy - origin[1]) / res);
+    return *mx < size_x && *my < size_y;
+}
+static double orc_line_cost(int size_x, const unsigned char* cost, int x0, int x1, int y0, int y1)
+{
+    /* base_local_planner::LineIterator */
+    const int deltax = abs(x1 - x0), deltay = abs(y1 - y0);
+    int x = x0, y = y0, xinc1, xinc2, yinc1, yinc2, den, num, numadd, numpixels;
+    if (x1 >= x0) { xinc1 = 1; xinc2 = 1; } else { xinc1 = -1; xinc2 = -1; }
+    if (y1 >= y0) { yinc1 = 1; yinc2 = 1; } else { yinc1 = -1; yinc2 = -1; }
+    if (deltax >= deltay) { xinc1 = 0; yinc2 = 0; den = deltax; num = deltax / 2; numadd = deltay; numpixels = deltax; }
+    else { xinc2 = 0; yinc1 = 0; den = deltay; num = deltay / 2; numadd = deltax; numpixels = deltay; }
+    double line_cost = 0.0;
+    for (int cur = 0; cur <= numpixels; ++cur)
+    {
+        const unsigned char c = cost[(size_t)y * size_x + x];
+        const double pc = c == 255 ? -2.0 : (c == 254 ? -1.0 : (double)c);   /* pointCost */
+        if (pc < 0) return pc;
+        if (line_cost < pc) line_cost = pc;
+        num += numadd;
+        if (num >= den) { num -= den; x += xinc1; y += yinc1; }
+        x += xinc2; y += yinc2;
+    }
+    return line_cost;
+}
+static double orc_footprint_cost(int size_x, int size_y, double res, const double* origin, const unsigned char* cost, double px, double py,
+                                 double th, const double* fp, int n_fp)
+{
+    int cx, cy;
+    if (!orc_world_to_map(size_x, size_y, res, origin, px, py, &cx, &cy)) return -1.0;
+    if (n_fp < 3)
+    {
+        const unsigned char c = cost[(size_t)cy * size_x + cx];
+        if (c == 255) return -2.0;
+        if (c == 254 || c == 253) return -1.0;
+        return (double)c;
+    }
+    const double co = cos(th), si = sin(th);
+    double fc = 0.0;
+    for (int i = 0; i < n_fp; ++i)
+    {
+        const int j = (i + 1) % n_fp;   /* edges 0-1, 1-2, ..., then the closing edge last -> first */
+        const double ax = px + (fp[2 * i] * co - fp[2 * i + 1] * si), ay = py + (fp[2 * i] * si + fp[2 * i + 1] * co);
+        const double bx = px + (fp[2 * j] * co - fp[2 * j + 1] * si), by = py + (fp[2 * j] * si + fp[2 * j + 1] * co);
+        int x0, y0, x1, y1;
+        if (!orc_world_to_map(size_x, size_y, res, origin, ax, ay, &x0, &y0)) return -3.0;
+        if (!orc_world_to_map(size_x, size_y, res, origin, bx, by, &x1, &y1)) return -3.0;
+        const double lc = orc_line_cost(size_x, cost, x0, x1, y0, y1);
+        if (fc < lc) fc = lc;
+        if (lc < 0) return lc;
+    }
+    return fc;
+}
+int orc_pose_trajectory_feasible(int size_x, int size_y, double resolution, const double* origin, const unsigned char* cost,
+                                 const double* x_seq, int n, const double* footprint, int n_fp, double inscribed_radius,
+                                 double min_resolution_angular, int look_ahead_idx)
+{
+    if (n < 2) return 0;
+    if (look_ahead_idx < 0 || look_ahead_idx >= n) look_ahead_idx = n - 1;
+    for (int i = 0; i <= look_ahead_idx; ++i)
+    {
+        const double* p = x_seq + 3 * i;
+        if (orc_footprint_cost(size_x, size_y, resolution, origin, cost, p[0], p[1], p[2], footprint, n_fp) == -1.0) return 0;
+        if (i < look_ahead_idx)
+        {
+            const double* q = x_seq + 3 * (i + 1);
+            const double delta_rot = orc_normalize_theta(q[2] - p[2]);
+            const double dx = q[0] - p[0], dy = q[1] - p[1];
+            const double dist = sqrt(dx * dx + dy * dy);
+            if (fabs(delta_rot) > min_resolution_angular || dist > inscribed_radius)
+            {
+                const double a = ceil(fabs(delta_rot) / min_resolution_angular), b = ceil(dist / inscribed_radius);
+                const int n_add = (int)(a > b ? a : b) - 1;
+                double ix = p[0], iy = p[1], ith = p[2];
+                for (int step = 0; step < n_add; ++step)
+                {
+                    ix = ix + dx / (n_add + 1.0);
+                    iy = iy + dy / (n_add + 1.0);
+                    ith = orc_normalize_theta(ith + delta_rot / (n_add + 1.0));
+                    if (orc_footprint_cost(size_x, size_y, resolution, origin, cost, ix, iy, ith, footprint, n_fp) == -1.0) return 0;
+                }
+            }
+        }
+    }
+    return 1;
 }
 
 /*
@@ -2130,7 +2234,7 @@ int orc_step(const orc_problem* p, orc_ws* ws, const double* x_init, int reinit,
     for (int it = 0; it < outer; ++it)
     {
         orc_associate(p, ws);
-        if (it == 0 && is_cold)
+        if (it == 0 && is_cold && !p->cfg->reference_initial_guess)   /* solver-side preprocessing; off: the reference's guess */
         {
             orc_project_init(p, ws);
             orc_init_controls(p, ws);

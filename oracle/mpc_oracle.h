@@ -102,6 +102,10 @@ void orc_warm_shift(const orc_problem* p, orc_ws* ws);
 /* updateObstacleContainerWithCostmap for one robot: mpc_local_planner_ros.cpp:474-499 */
 int orc_costmap_obstacles(int size_x, int size_y, double resolution, const double* origin, const unsigned char* cost,
                           const double* robot_pose, double behind_dist, int max_out, double* xy);
+/* Controller::isPoseTrajectoryFeasible for one robot: controller.cpp:859-917 (+ [EXT] CostmapModel::footprintCost) */
+int orc_pose_trajectory_feasible(int size_x, int size_y, double resolution, const double* origin, const unsigned char* cost,
+                                 const double* x_seq, int n, const double* footprint, int n_fp, double inscribed_radius,
+                                 double min_resolution_angular, int look_ahead_idx);
 /* resampleTrajectory(n_new): full_discretization_grid_base_se2.cpp:440-524 */
 double orc_resample_trajectory(int n, const double* X, const double* U, double dt, int n_new, double* Xn, double* Un);
 /* a12/a11: obstacle + via-point association from the current trajectory */

@@ -60,6 +60,7 @@ def lib():
         L.orc_objective.argtypes = [C.POINTER(Problem), C.POINTER(Ws), dp, dp, C.c_double]
         L.orc_ws_alloc.restype = C.POINTER(Ws)
         L.orc_costmap_obstacles.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_ubyte), dp, C.c_double, C.c_int, dp]
+        L.orc_pose_trajectory_feasible.argtypes = [C.c_int, C.c_int, C.c_double, dp, C.POINTER(C.c_ubyte), dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_int]
         L.orc_resample_trajectory.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, dp, dp]
         L.orc_resample_trajectory.restype = C.c_double
         L.orc_ws_alloc.argtypes = [C.c_int, C.c_int]
@@ -190,6 +191,15 @@ def costmap_obstacles(cost, origin, resolution, robot_pose, behind_dist, max_out
     found = lib().orc_costmap_obstacles(cost.shape[1], cost.shape[0], float(resolution), _dp(origin),
                                         cost.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(pose), float(behind_dist), int(max_out), _dp(xy))
     return xy[: min(found, max_out)].copy(), found
+
+
+def pose_trajectory_feasible(cost, origin, resolution, x_seq, footprint, inscribed_radius, min_resolution_angular, look_ahead_idx=-1):
+    """isPoseTrajectoryFeasible for one robot: cost [size_y, size_x] uint8, x_seq [n, 3], footprint [n_fp, 2] -> bool"""
+    cost = np.ascontiguousarray(cost, dtype=np.uint8); origin = np.ascontiguousarray(origin, dtype=np.float64)
+    x_seq = np.ascontiguousarray(x_seq, dtype=np.float64); fp = np.ascontiguousarray(footprint, dtype=np.float64).reshape(-1, 2)
+    return bool(lib().orc_pose_trajectory_feasible(cost.shape[1], cost.shape[0], float(resolution), _dp(origin), cost.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                                   _dp(x_seq), x_seq.shape[0], _dp(fp), fp.shape[0], float(inscribed_radius),
+                                                   float(min_resolution_angular), int(look_ahead_idx)))
 
 
 def resample_trajectory(X, U, dt, n_new):

@@ -112,7 +112,8 @@ void emu_associate(const Cfg* cp, double* W, double uprev_dt, int first_outer)
     WsLayout L;
     make_layout(cp, MAX_OBST, MAX_VP, L);
     const int N = L.N;
-    const bool repair = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
+    const bool cold_pending = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
+    const bool repair = cold_pending && !c.reference_initial_guess;
     for (int k = 0; k < N; ++k) associate_stage(c, L, W, k);
     if (has_viapoints(c))
     {
@@ -158,7 +159,7 @@ void emu_associate(const Cfg* cp, double* W, double uprev_dt, int first_outer)
     ASC(MPCB200_SC_MU) = mu; ASC(MPCB200_SC_RHO) = 1.0; ASC(MPCB200_SC_DELTA) = 0.0; ASC(MPCB200_SC_DELTA_LAST) = 0.0;
     ASC(MPCB200_SC_ITER) = 0.0; ASC(MPCB200_SC_STATUS) = -1.0; ASC(MPCB200_SC_NREG) = 0.0; ASC(MPCB200_SC_NBT) = 0.0;
     ASC(MPCB200_SC_DDT) = 0.0; ASC(MPCB200_SC_ALPHA) = 0.0; ASC(MPCB200_SC_TINY) = 0.0; ASC(MPCB200_SC_DEFER) = 0.0;
-    if (repair) ASC(MPCB200_SC_COLD) = 0.0;
+    if (cold_pending) ASC(MPCB200_SC_COLD) = 0.0;
 }
 
 // lanes accumulate their own stages, then a tree reduction in the same xor order as the shuffles

@@ -176,3 +176,38 @@ def test_failed_instance_restarts_cold(cuda_lib):
         np.testing.assert_array_equal(out2["status"][failed], out["status"][failed])     # same cold solve, same outcome
         np.testing.assert_array_equal(out2["u_seq"][failed], out["u_seq"][failed])
     s.close()
+
+
+@pytest.mark.parametrize("footprint", ["polygon", "two_points"])
+def test_check_feasible_matches_the_oracle(cuda_lib, orc, footprint):
+    """mpcb200_check_feasible (Controller::isPoseTrajectoryFeasible, controller.cpp:859-917) for a batch of robots: accept /
+    reject byte for byte as the oracle's plain-C loop, on random maps, trajectories that turn and leave the map, both look-ahead
+    settings -- and on the trajectories of a solve that are still on the device."""
+    from tests.test_oracle_functions import _feasibility_cases
+    rng = np.random.default_rng(5)
+    fp = np.array(configs.CARLIKE_POLYGON) if footprint == "polygon" else np.array([[0.1, 0.0], [-0.1, 0.0]])
+    cases = _feasibility_cases(rng, 96)
+    cost = np.stack([c[0] for c in cases]); origin = np.stack([c[1] for c in cases]); xs = np.stack([c[2] for c in cases])
+    cfg = configs.cfg2(tol=1e-6)
+    s = capi.BatchSolver(cfg, 96, device=0)
+    for look in (-1, 5):
+        got = s.check_feasible(cost, origin, 0.05, fp, 0.18, 0.3, look, x_seq=xs)
+        want = np.array([orc.pose_trajectory_feasible(cost[b], origin[b], 0.05, xs[b], fp, 0.18, 0.3, look) for b in range(96)])
+        np.testing.assert_array_equal(got, want)
+        assert want.any() and not want.all()
+    # the trajectories of the last solve, checked where they are (device)
+    data = configs.generate(2, 96)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    H, W, res = 200, 200, 0.05
+    maps = np.zeros((96, H, W), dtype=np.uint8)
+    org = np.tile(np.array([-2.0, -5.0]), (96, 1))
+    cnt, typ, par = data["obstacles"]
+    for b in range(96):      # the obstacle centres of the instance as lethal cells
+        for j in range(cnt[b]):
+            mx, my = int((par[b, j, 0] - org[b, 0]) / res), int((par[b, j, 1] - org[b, 1]) / res)
+            if 0 <= mx < W and 0 <= my < H:
+                maps[b, my, mx] = 254
+    got = s.check_feasible(maps, org, res, fp, 0.18, 0.3, -1)
+    want = np.array([orc.pose_trajectory_feasible(maps[b], org[b], res, out["x_seq"][b], fp, 0.18, 0.3, -1) for b in range(96)])
+    np.testing.assert_array_equal(got, want)
+    s.close()

@@ -456,3 +456,198 @@ def test_costmap_obstacles_against_numpy(orc, W, H):
         xy3, found3 = orc.costmap_obstacles(cost, origin, res, pose, behind, max_out=3)
         assert found3 == found and len(xy3) == 3
         np.testing.assert_array_equal(xy3, xy[:3])
+
+
+# ---- the independent numpy restatement (tests/golden/ocp_numpy.py, written from the reference's lines without the oracle)
+#      against the oracle, function by function, on random iterates ----
+def _np_problem(cfg, data, b):
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import ocp_numpy as on
+    return on, on.problem_from_batch(cfg, data, b)
+
+
+@pytest.mark.parametrize("variant", ["cfg2", "cfg3_polygon", "cfg4_viapoints", "two_circles_lines", "line_footprint", "min_time_via_points_ordered", "midpoint"])
+def test_numpy_restatement_agrees_with_the_oracle(orc, variant):
+    """Association (StageInequalitySE2::update incl. the world-centroid side test), via-point association, obstacle rows,
+    control-rate rows (the oracle keeps them multiplied by dt), collocation defects (ditto) and the objective."""
+    rng = np.random.default_rng(11)
+    if variant == "cfg2":
+        cfg = configs.cfg2(n=20); data = configs.generate(5, 6, n=20)
+    elif variant == "cfg3_polygon":
+        cfg = configs.cfg3(n=16); data = configs.generate(3, 6, n=16)
+    elif variant == "cfg4_viapoints":
+        cfg = configs.cfg4(n=20); data = configs.generate(4, 6)
+    elif variant == "two_circles_lines":
+        cfg = configs.cfg2(n=16); cfg.footprint_type = capi.FOOTPRINT_TWO_CIRCLES; cfg.footprint_params[:] = [0.2, 0.12, 0.15, 0.1]
+        data = configs.with_line_obstacles(configs.generate(5, 6, n=16))
+    elif variant == "line_footprint":
+        cfg = configs.cfg2(n=16); cfg.footprint_type = capi.FOOTPRINT_LINE; cfg.footprint_params[:] = [-0.15, 0.0, 0.2, 0.0]
+        data = configs.with_line_obstacles(configs.generate(5, 6, n=16))
+    elif variant == "min_time_via_points_ordered":
+        cfg = configs.cfg1(); cfg.objective = capi.OBJ_MINIMUM_TIME_VIA_POINTS; cfg.vp_ordered = 1; cfg.vp_orientation_weight = 0.3
+        cfg.vp_position_weight = 1.5; cfg.du_lb[:] = [-0.3, -0.4]; cfg.du_ub[:] = [0.3, 0.4]; cfg.k_max_obstacles_per_stage = 5
+        data = configs.generate(4, 6)
+        vc, vp = data["viapoints"]; data["viapoints"] = (vc, vp[:, ::-1].copy())
+    else:
+        cfg = configs.cfg2(n=16); cfg.collocation = capi.COLLOC_MIDPOINT; data = configs.generate(5, 6, n=16)
+    cfg.reference_initial_guess = 1
+    N = cfg.n
+    for b in range(6):
+        on, p = _np_problem(cfg, data, b)
+        o = orc.instance_from_batch(cfg, data, b)
+        o.init_cold()
+        # a wiggled trajectory (so that sides, forced inclusions and the via-point association are not trivial)
+        X = o.arr("X"); U = o.arr("U")
+        X[:2, 1:N - 1] += rng.normal(0, 0.15, (2, N - 2)); X[2, 1:N - 1] += rng.normal(0, 0.4, N - 2)
+        U[:, :N - 1] = rng.uniform(-0.15, 0.25, (2, N - 1))
+        dt = float(o.arr("SCAL")[capi.SC_DT])
+        if cfg.variable_dt:
+            dt = 0.37; o.arr("SCAL")[capi.SC_DT] = dt
+        o.associate(); o.init_duals(); o.eval()
+        Xn = X.T.copy(); Un = U[:, :N - 1].T.copy()
+        # association: same obstacles per stage, same order
+        assoc = on.associate(cfg, Xn, p.ot, p.op, dt)
+        OBS = o.arr("OBSIDX")
+        for k in range(N):
+            mine = assoc[k]
+            theirs = [int(v) for v in OBS[:, k] if v >= 0]
+            assert mine == theirs, f"{variant} instance {b} stage {k}: numpy {mine} oracle {theirs}"
+        if p.vps:
+            assert on.associate_viapoints(cfg, Xn, p.vps) == list(o.vp_stage()), variant
+        # defects: oracle keeps e = x_k + dt f - x_{k+1} = -dt * (reference defect)
+        e_np = on.defects(cfg, Xn, Un, dt).reshape(N - 1, 3)
+        np.testing.assert_allclose(o.defects().T, -dt * e_np, atol=1e-12)
+        # rows: obstacle rows as they are, control-rate rows multiplied by the interval length
+        G = o.arr("G")
+        for k in range(1, N - 1):
+            for j, oi in enumerate(assoc[k]):
+                row = cfg.min_obstacle_dist - on.footprint_distance(cfg, Xn[k], p.ot[oi], p.op[oi], t=k * dt)
+                assert G[8 + j, k] == pytest.approx(row, abs=1e-12)
+        for k in range(N):
+            uk = Un[k] if k <= N - 2 else np.zeros(2)
+            um = Un[k - 1] if k >= 1 else data["u_prev"][b]
+            T = dt if k >= 1 else data["u_prev_dt"]
+            for i in range(2):
+                if cfg.du_lb[i] > -1e29:
+                    assert G[4 + 2 * i, k] == pytest.approx(T * (cfg.du_lb[i] - (uk[i] - um[i]) / T), abs=1e-12)
+                if cfg.du_ub[i] < 1e29:
+                    assert G[5 + 2 * i, k] == pytest.approx(T * ((uk[i] - um[i]) / T - cfg.du_ub[i]), abs=1e-12)
+        # objective
+        vp_stage = on.associate_viapoints(cfg, Xn, p.vps) if p.vps else []
+        f_np = on.objective(cfg, Xn, Un, dt, data["xf"][b], p.vps, vp_stage)
+        assert o.arr("SCAL")[capi.SC_OBJ] == pytest.approx(f_np, rel=1e-12, abs=1e-12)
+
+
+# ---- Controller::isPoseTrajectoryFeasible (controller.cpp:859-917): the oracle's C loop against a plain-Python restatement ----
+def _py_feasible(cost, origin, res, xs, fp, inscribed, min_ang, look):
+    H, W = cost.shape
+
+    def w2m(wx, wy):
+        if wx < origin[0] or wy < origin[1]:
+            return None
+        mx, my = int((wx - origin[0]) / res), int((wy - origin[1]) / res)
+        return (mx, my) if (mx < W and my < H) else None
+
+    def line_cost(x0, x1, y0, y1):
+        dx, dy = abs(x1 - x0), abs(y1 - y0)
+        x, y = x0, y0
+        xi1 = xi2 = 1 if x1 >= x0 else -1
+        yi1 = yi2 = 1 if y1 >= y0 else -1
+        if dx >= dy:
+            xi1 = 0; yi2 = 0; den = dx; num = dx // 2; numadd = dy; npx = dx
+        else:
+            xi2 = 0; yi1 = 0; den = dy; num = dy // 2; numadd = dx; npx = dy
+        lc = 0.0
+        for _ in range(npx + 1):
+            c = int(cost[y, x])
+            pc = -2.0 if c == 255 else (-1.0 if c == 254 else float(c))
+            if pc < 0:
+                return pc
+            lc = max(lc, pc)
+            num += numadd
+            if num >= den:
+                num -= den; x += xi1; y += yi1
+            x += xi2; y += yi2
+        return lc
+
+    def fcost(px, py, th):
+        c = w2m(px, py)
+        if c is None:
+            return -1.0
+        if len(fp) < 3:
+            v = int(cost[c[1], c[0]])
+            return -2.0 if v == 255 else (-1.0 if v in (254, 253) else float(v))
+        co, si = math.cos(th), math.sin(th)
+        pts = [(px + (fx * co - fy * si), py + (fx * si + fy * co)) for fx, fy in fp]
+        fc = 0.0
+        for i in range(len(pts)):
+            a, b = pts[i], pts[(i + 1) % len(pts)]
+            ca, cb = w2m(*a), w2m(*b)
+            if ca is None or cb is None:
+                return -3.0
+            lc = line_cost(ca[0], cb[0], ca[1], cb[1])
+            fc = max(fc, lc)
+            if lc < 0:
+                return lc
+        return fc
+
+    def norm(t):
+        if -math.pi <= t < math.pi:
+            return t
+        t = t - math.floor(t / (2 * math.pi)) * 2 * math.pi
+        if t >= math.pi:
+            t -= 2 * math.pi
+        if t < -math.pi:
+            t += 2 * math.pi
+        return t
+    n = len(xs)
+    if n < 2:
+        return False
+    if look < 0 or look >= n:
+        look = n - 1
+    for i in range(look + 1):
+        if fcost(*xs[i]) == -1.0:
+            return False
+        if i < look:
+            drot = norm(xs[i + 1][2] - xs[i][2]); dx = xs[i + 1][0] - xs[i][0]; dy = xs[i + 1][1] - xs[i][1]
+            dist = math.sqrt(dx * dx + dy * dy)
+            if abs(drot) > min_ang or dist > inscribed:
+                nadd = int(max(math.ceil(abs(drot) / min_ang), math.ceil(dist / inscribed))) - 1
+                ix, iy, ith = xs[i]
+                for _ in range(nadd):
+                    ix += dx / (nadd + 1.0); iy += dy / (nadd + 1.0); ith = norm(ith + drot / (nadd + 1.0))
+                    if fcost(ix, iy, ith) == -1.0:
+                        return False
+    return True
+
+
+def _feasibility_cases(rng, n_cases, W=80, H=70, res=0.05, n=14):
+    out = []
+    for c in range(n_cases):
+        cost = np.zeros((H, W), dtype=np.uint8)
+        cost[rng.random((H, W)) < 0.004] = 254
+        cost[rng.random((H, W)) < 0.01] = 255
+        cost[rng.random((H, W)) < 0.01] = 253
+        origin = rng.uniform(-1, 1, 2)
+        start = origin + rng.uniform(0.3, 0.8, 2)
+        goal = origin + np.array([W * res, H * res]) - rng.uniform(-0.2, 0.8, 2)   # sometimes leaves the map
+        t = np.linspace(0, 1, n)[:, None]
+        xy = start + t * (goal - start) + rng.normal(0, 0.02, (n, 2))
+        th = np.arctan2(goal[1] - start[1], goal[0] - start[0]) + np.cumsum(rng.normal(0, 0.25, n))
+        out.append((cost, origin, np.column_stack([xy, th])))
+    return out
+
+
+@pytest.mark.parametrize("footprint", ["polygon", "two_points"])
+def test_pose_trajectory_feasibility_against_python(orc, footprint):
+    rng = np.random.default_rng(5)
+    fp = np.array(configs.CARLIKE_POLYGON) if footprint == "polygon" else np.array([[0.1, 0.0], [-0.1, 0.0]])
+    seen = set()
+    for look in (-1, 5):
+        for cost, origin, xs in _feasibility_cases(rng, 40):
+            a = orc.pose_trajectory_feasible(cost, origin, 0.05, xs, fp, 0.18, 0.3, look)
+            b = _py_feasible(cost, origin, 0.05, [tuple(r) for r in xs], [tuple(p) for p in fp], 0.18, 0.3, look)
+            assert a == b
+            seen.add(a)
+    assert seen == {True, False}   # the cases exercise both outcomes
