@@ -279,6 +279,28 @@ void mpcb200_destroy(mpcb200_handle* h);
 /* Last error message of this handle (or of create() when h == NULL). Never NULL. */
 const char* mpcb200_last_error(const mpcb200_handle* h);
 
+/* ---- several devices of one node behind one handle ------------------------------------------------ */
+/*
+ * Instances are independent: the batch is cut into contiguous blocks, device r of the list solves instances
+ * [r ceil(B/G), (r+1) ceil(B/G)) with its own workspace on its own stream (one host thread per device inside the call), and ONE
+ * NCCL all-gather over NVLink / NVSwitch then leaves the packed optimal controls of the WHOLE batch on every device
+ * (mpcb200_multi_device_controls: [G][ceil(B/G)][N-1][2] doubles, the slots behind B unused).  No other collective.  Per instance
+ * the arithmetic is the single-device one: G-device results equal the 1-device results bit for bit.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2") when n_devices > 1; MPCB200_E_UNSUPPORTED if it cannot be loaded.
+ */
+typedef struct mpcb200_multi mpcb200_multi;
+int mpcb200_create_multi(const mpcb200_config* cfg, int max_batch_total, const int* devices, int n_devices, mpcb200_multi** out);
+/* same arguments as mpcb200_step_batch, for the whole batch; solve_time_s = the slowest device's device time */
+int mpcb200_step_batch_multi(mpcb200_multi* m, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                             const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init, const unsigned char* reinit,
+                             double* u_seq, double* x_seq, double* dt_out, int* status, double* kkt_err, int* iters, double* solve_time_s);
+/* the gathered controls on device `rank` of the list (device pointer) and their size in doubles */
+int mpcb200_multi_device_controls(mpcb200_multi* m, int rank, void** dev_ptr, long long* n_doubles);
+/* the single-device handle of device `rank` (reset, resample, options, statistics ...) */
+mpcb200_handle* mpcb200_multi_handle(mpcb200_multi* m, int rank);
+void mpcb200_destroy_multi(mpcb200_multi* m);
+const char* mpcb200_multi_last_error(const mpcb200_multi* m);
+
 /* ---- device-resident variant (inputs already in HBM; used by bench.py's kernel-only `value`) ----------- */
 
 /*

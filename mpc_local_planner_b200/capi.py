@@ -189,6 +189,8 @@ EXPORTS = [
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
     "mpcb200_check_feasible", "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
     "mpcb200_resample", "mpcb200_get_horizon", "mpcb200_costmap_obstacles", "mpcb200_costmap_last_ms",
+    "mpcb200_create_multi", "mpcb200_step_batch_multi", "mpcb200_multi_device_controls", "mpcb200_multi_handle",
+    "mpcb200_destroy_multi", "mpcb200_multi_last_error",
 ]
 
 
@@ -233,6 +235,15 @@ def load_library(path=None):
     lib.mpcb200_ws_read.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.mpcb200_ws_write.argtypes = [vp, C.c_int, C.c_int, dp]
     lib.mpcb200_run_phase.argtypes = [vp, C.c_int, C.c_int]
+    lib.mpcb200_create_multi.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.mpcb200_step_batch_multi.argtypes = lib.mpcb200_step_batch.argtypes
+    lib.mpcb200_multi_device_controls.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_longlong)]
+    lib.mpcb200_multi_handle.argtypes = [vp, C.c_int]
+    lib.mpcb200_multi_handle.restype = vp
+    lib.mpcb200_destroy_multi.argtypes = [vp]
+    lib.mpcb200_destroy_multi.restype = None
+    lib.mpcb200_multi_last_error.argtypes = [vp]
+    lib.mpcb200_multi_last_error.restype = C.c_char_p
     lib.mpcb200_check_feasible.argtypes = [vp, C.c_int, C.POINTER(Costmaps), dp, C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_ubyte)]
     lib.mpcb200_time_phase.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp]
     lib.mpcb200_set_timing.argtypes = [vp, C.c_uint]
@@ -476,3 +487,62 @@ class BatchSolver:
         n = C.c_longlong()
         self._check(self.lib.mpcb200_device_controls(self.h, C.byref(p), C.byref(n)), "mpcb200_device_controls")
         return p.value, n.value
+
+
+class MultiSolver:
+    """Several devices of one node behind one handle (mpcb200_create_multi): contiguous blocks of the batch per device, one NCCL
+    all-gather of the packed optimal controls."""
+
+    def __init__(self, cfg, max_batch_total, devices):
+        self.lib = load_library()
+        self.cfg = cfg.copy()
+        self.N = int(cfg.n)
+        self.devices = list(devices)
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = self.lib.mpcb200_create_multi(C.byref(self.cfg), int(max_batch_total), devs, len(self.devices), C.byref(h))
+        if rc != 0:
+            raise SolverError(f"mpcb200_create_multi failed ({rc}): {self.lib.mpcb200_multi_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpcb200_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, x0, xf, u_prev=None, u_prev_dt=0.0, obstacles=None, viapoints=None):
+        B, x0, xf, u_prev, o, v, xi, keep = BatchSolver._prep_inputs(x0, xf, u_prev, obstacles, viapoints, None)
+        N = self.N
+        out = dict(u_seq=np.empty((B, N, 2)), x_seq=np.empty((B, N, 3)), dt=np.empty(B),
+                   status=np.empty(B, dtype=np.int32), kkt_err=np.empty(B), iters=np.empty(B, dtype=np.int32))
+        t = C.c_double(0.0)
+        rc = self.lib.mpcb200_step_batch_multi(
+            self.h, B, _dp(x0), _dp(xf), _dp(u_prev), float(u_prev_dt), C.byref(o) if o else None, C.byref(v) if v else None, None, None,
+            _dp(out["u_seq"]), _dp(out["x_seq"]), _dp(out["dt"]), _ip(out["status"]), _dp(out["kkt_err"]), _ip(out["iters"]), C.byref(t))
+        if rc != 0:
+            raise SolverError(f"mpcb200_step_batch_multi failed ({rc}): {self.lib.mpcb200_multi_last_error(self.h).decode()}")
+        out["solve_time_s"] = t.value
+        self.B = B
+        return out
+
+    def gathered_controls(self, rank):
+        """the all-gathered packed controls on device `rank` as a host array [G, ceil(B/G), N-1, 2] (copied back for inspection)"""
+        p = C.c_void_p(); n = C.c_longlong()
+        rc = self.lib.mpcb200_multi_device_controls(self.h, rank, C.byref(p), C.byref(n))
+        if rc != 0:
+            raise SolverError("mpcb200_multi_device_controls failed")
+        import torch
+        G = len(self.devices)
+        per = n.value // (G * (self.N - 1) * 2)
+        host = np.empty(n.value)
+        cudart = torch.cuda.cudart()
+        with torch.cuda.device(self.devices[rank]):
+            err = cudart.cudaMemcpy(host.ctypes.data, p.value, n.value * 8, 2)   # cudaMemcpyDeviceToHost
+        assert int(err) == 0, err
+        return host.reshape(G, per, self.N - 1, 2)

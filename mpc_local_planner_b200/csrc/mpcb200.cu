@@ -1217,3 +1217,167 @@ extern "C" int mpcb200_flush_l2(mpcb200_handle* h)
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
+
+// =================================================================================================================
+// several devices of one node behind one handle: instances are independent, so the batch is cut into contiguous
+// blocks, one per device; every device solves its block with its own handle on its own stream (one host thread each), and ONE
+// NCCL all-gather over NVLink leaves the packed optimal controls of the whole batch on every device.  No other collective.
+// NCCL is loaded at run time (dlopen) when a multi-device handle is created: the single-device library has no NCCL dependency.
+// =================================================================================================================
+#include <dlfcn.h>
+#include <thread>
+
+struct NcclApi
+{
+    void* lib = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+#define MPC_NCCL_FLOAT64 8   /* ncclFloat64 / ncclDouble (nccl.h) */
+
+struct mpcb200_multi
+{
+    int n_dev = 0, max_per = 0, n = 0;
+    std::vector<int> devices;
+    std::vector<mpcb200_handle*> h;
+    std::vector<void*> comm;
+    std::vector<double*> d_all;      // per device: gathered packed controls [n_dev][max_per][N-1][2]
+    NcclApi nccl;
+    std::string err;
+};
+static std::string g_multi_err = "";
+static int multi_err(mpcb200_multi* m, int code, const std::string& msg) { if (m) m->err = msg; else g_multi_err = msg; return code; }
+
+static bool load_nccl(NcclApi& a, std::string& why)
+{
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (a.lib) break; }
+    if (!a.lib) { why = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : ""); return false; }
+#define NSYM(field, name) a.field = (decltype(a.field))dlsym(a.lib, name); if (!a.field) { why = std::string("NCCL symbol missing: ") + name; return false; }
+    NSYM(CommInitAll, "ncclCommInitAll") NSYM(CommDestroy, "ncclCommDestroy") NSYM(AllGather, "ncclAllGather")
+    NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd") NSYM(GetErrorString, "ncclGetErrorString")
+#undef NSYM
+    return true;
+}
+
+extern "C" void mpcb200_destroy_multi(mpcb200_multi* m)
+{
+    if (!m) return;
+    for (size_t r = 0; r < m->comm.size(); ++r) if (m->comm[r] && m->nccl.CommDestroy) m->nccl.CommDestroy(m->comm[r]);
+    for (size_t r = 0; r < m->d_all.size(); ++r) if (m->d_all[r]) { cudaSetDevice(m->devices[r]); cudaFree(m->d_all[r]); }
+    for (auto* h : m->h) if (h) mpcb200_destroy(h);
+    delete m;
+}
+
+extern "C" int mpcb200_create_multi(const mpcb200_config* cfg, int max_batch_total, const int* devices, int n_devices, mpcb200_multi** out)
+{
+    if (!cfg || !out || max_batch_total < 1 || !devices || n_devices < 1) return multi_err(nullptr, MPCB200_E_INVALID, "bad arguments");
+    mpcb200_multi* m = new mpcb200_multi();
+    m->n_dev = n_devices; m->n = cfg->n;
+    m->max_per = (max_batch_total + n_devices - 1) / n_devices;
+    m->devices.assign(devices, devices + n_devices);
+    m->h.assign(n_devices, nullptr); m->comm.assign(n_devices, nullptr); m->d_all.assign(n_devices, nullptr);
+    for (int r = 0; r < n_devices; ++r)
+    {
+        const int rc = mpcb200_create(cfg, m->max_per, devices[r], &m->h[r]);
+        if (rc) { const std::string e = mpcb200_last_error(nullptr); mpcb200_destroy_multi(m); return multi_err(nullptr, rc, e); }
+    }
+    if (n_devices > 1)
+    {
+        std::string why;
+        if (!load_nccl(m->nccl, why)) { mpcb200_destroy_multi(m); return multi_err(nullptr, MPCB200_E_UNSUPPORTED, why); }
+        const int nrc = m->nccl.CommInitAll(m->comm.data(), n_devices, devices);
+        if (nrc != 0) { const std::string e = std::string("ncclCommInitAll: ") + m->nccl.GetErrorString(nrc); mpcb200_destroy_multi(m); return multi_err(nullptr, MPCB200_E_CUDA, e); }
+    }
+    const size_t words = (size_t)n_devices * m->max_per * (cfg->n - 1) * 2;
+    for (int r = 0; r < n_devices; ++r)
+    {
+        if (cudaSetDevice(devices[r]) != cudaSuccess || cudaMalloc(&m->d_all[r], words * 8) != cudaSuccess)
+        { mpcb200_destroy_multi(m); return multi_err(nullptr, MPCB200_E_CUDA, "cudaMalloc of the gathered controls failed"); }
+    }
+    *out = m;
+    return MPCB200_OK;
+}
+
+extern "C" const char* mpcb200_multi_last_error(const mpcb200_multi* m) { return m ? m->err.c_str() : g_multi_err.c_str(); }
+extern "C" mpcb200_handle* mpcb200_multi_handle(mpcb200_multi* m, int rank) { return (m && rank >= 0 && rank < m->n_dev) ? m->h[rank] : nullptr; }
+extern "C" int mpcb200_multi_device_controls(mpcb200_multi* m, int rank, void** dev_ptr, long long* n_doubles)
+{
+    if (!m || rank < 0 || rank >= m->n_dev) return MPCB200_E_INVALID;
+    if (dev_ptr) *dev_ptr = m->d_all[rank];
+    if (n_doubles) *n_doubles = (long long)m->n_dev * m->max_per * (m->n - 1) * 2;
+    return MPCB200_OK;
+}
+
+extern "C" int mpcb200_step_batch_multi(mpcb200_multi* m, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                                        const mpcb200_obstacles* obst, const mpcb200_viapoints* vp, const double* x_init, const unsigned char* reinit,
+                                        double* u_seq, double* x_seq, double* dt_out, int* status, double* kkt_err, int* iters, double* solve_time_s)
+{
+    if (!m) return MPCB200_E_INVALID;
+    if (B < 1 || B > m->n_dev * m->max_per) return multi_err(m, MPCB200_E_INVALID, "batch size out of range");
+    const int G = m->n_dev, N = m->n;
+    const int per = (B + G - 1) / G;   // contiguous blocks: device r gets instances [r per, min((r+1) per, B))
+    std::vector<int> rcs(G, 0);
+    std::vector<double> secs(G, 0.0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < G; ++r)
+    {
+        const int b0 = r * per, nb = std::max(0, std::min(per, B - b0));
+        if (nb == 0) continue;
+        th.emplace_back([=, &rcs, &secs]() {
+            mpcb200_obstacles ob; mpcb200_viapoints vv;
+            const mpcb200_obstacles* pob = nullptr; const mpcb200_viapoints* pvp = nullptr;
+            if (obst && obst->count && obst->max_per_instance > 0)
+            {
+                const size_t M = (size_t)obst->max_per_instance;
+                ob.max_per_instance = obst->max_per_instance; ob.count = obst->count + b0; ob.type = obst->type + (size_t)b0 * M;
+                ob.params = obst->params + (size_t)b0 * M * MPCB200_OBST_STRIDE;
+                pob = &ob;
+            }
+            if (vp && vp->count && vp->max_per_instance > 0)
+            {
+                vv.max_per_instance = vp->max_per_instance; vv.count = vp->count + b0; vv.poses = vp->poses + (size_t)b0 * vp->max_per_instance * 3;
+                pvp = &vv;
+            }
+            rcs[r] = mpcb200_step_batch(m->h[r], nb, x0 + (size_t)b0 * 3, xf + (size_t)b0 * 3, u_prev ? u_prev + (size_t)b0 * 2 : nullptr, u_prev_dt, pob, pvp,
+                                        x_init ? x_init + (size_t)b0 * N * 3 : nullptr, reinit ? reinit + b0 : nullptr,
+                                        u_seq ? u_seq + (size_t)b0 * N * 2 : nullptr, x_seq ? x_seq + (size_t)b0 * N * 3 : nullptr, dt_out ? dt_out + b0 : nullptr,
+                                        status ? status + b0 : nullptr, kkt_err ? kkt_err + b0 : nullptr, iters ? iters + b0 : nullptr, &secs[r]);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int r = 0; r < G; ++r)
+        if (rcs[r]) return multi_err(m, rcs[r], std::string("device ") + std::to_string(m->devices[r]) + ": " + mpcb200_last_error(m->h[r]));
+    // ---- all-gather of the packed optimal controls: every device ends up with u* of every instance ----
+    const size_t count = (size_t)per * (N - 1) * 2;
+    if (G > 1)
+    {
+        int nrc = m->nccl.GroupStart();
+        for (int r = 0; r < G && nrc == 0; ++r)
+        {
+            cudaSetDevice(m->devices[r]);
+            nrc = m->nccl.AllGather(m->h[r]->d_upacked, m->d_all[r], count, MPC_NCCL_FLOAT64, m->comm[r], m->h[r]->stream);
+        }
+        const int erc = m->nccl.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        if (nrc != 0) return multi_err(m, MPCB200_E_CUDA, std::string("ncclAllGather: ") + m->nccl.GetErrorString(nrc));
+        for (int r = 0; r < G; ++r)
+        {
+            cudaSetDevice(m->devices[r]);
+            if (cudaStreamSynchronize(m->h[r]->stream) != cudaSuccess) return multi_err(m, MPCB200_E_CUDA, "stream synchronisation after the all-gather failed");
+        }
+    }
+    else
+    {
+        cudaSetDevice(m->devices[0]);
+        if (cudaMemcpyAsync(m->d_all[0], m->h[0]->d_upacked, count * 8, cudaMemcpyDeviceToDevice, m->h[0]->stream) != cudaSuccess ||
+            cudaStreamSynchronize(m->h[0]->stream) != cudaSuccess)
+            return multi_err(m, MPCB200_E_CUDA, "copy of the controls failed");
+    }
+    if (solve_time_s) { double mx = 0.0; for (double s_ : secs) mx = s_ > mx ? s_ : mx; *solve_time_s = mx; }
+    return MPCB200_OK;
+}

@@ -48,3 +48,11 @@ def test_no_cpu_fallback(cuda_lib):
     with pytest.raises(capi.SolverError) as ei:
         capi.BatchSolver(capi.default_config(), 4)
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+@pytest.mark.skipif(has_gpu(), reason="box has a GPU")
+def test_multi_device_handle_fails_loudly_without_gpu(cuda_lib):
+    from mpc_local_planner_b200 import capi, configs
+    with pytest.raises(capi.SolverError) as e:
+        capi.MultiSolver(configs.cfg2(), 64, [0, 1])
+    assert "no CPU fallback" in str(e.value)

@@ -211,3 +211,28 @@ def test_check_feasible_matches_the_oracle(cuda_lib, orc, footprint):
     want = np.array([orc.pose_trajectory_feasible(maps[b], org[b], res, out["x_seq"][b], fp, 0.18, 0.3, -1) for b in range(96)])
     np.testing.assert_array_equal(got, want)
     s.close()
+
+
+def test_multi_device_handle_equals_single_device(cuda_lib):
+    """mpcb200_create_multi / mpcb200_step_batch_multi: contiguous blocks over the devices, one NCCL all-gather of
+    u*.  The G-device results equal the 1-device results bit for bit, and every device holds the controls of all instances."""
+    import torch
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs at least two devices")
+    G = min(G, 8)
+    cfg = configs.cfg2(tol=1e-6)
+    B = 64 * G - 5          # ragged last block
+    data = configs.generate(2, B)
+    s = capi.BatchSolver(cfg, B, device=0)
+    one = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    s.close()
+    m = capi.MultiSolver(cfg, B, list(range(G)))
+    many = m.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    for k in ("status", "iters", "u_seq", "x_seq", "dt"):
+        np.testing.assert_array_equal(one[k], many[k])
+    per = (B + G - 1) // G
+    for rank in (0, G - 1):
+        g = m.gathered_controls(rank).reshape(G * per, cfg.n - 1, 2)[:B]
+        np.testing.assert_array_equal(g, one["u_seq"][:, :-1, :])
+    m.close()
