@@ -296,6 +296,8 @@ int mpcb200_step_batch_multi(mpcb200_multi* m, int B, const double* x0, const do
                              double* u_seq, double* x_seq, double* dt_out, int* status, double* kkt_err, int* iters, double* solve_time_s);
 /* the gathered controls on device `rank` of the list (device pointer) and their size in doubles */
 int mpcb200_multi_device_controls(mpcb200_multi* m, int rank, void** dev_ptr, long long* n_doubles);
+/* copy of that buffer to the host (n_doubles doubles) */
+int mpcb200_multi_fetch_controls(mpcb200_multi* m, int rank, double* host);
 /* the single-device handle of device `rank` (reset, resample, options, statistics ...) */
 mpcb200_handle* mpcb200_multi_handle(mpcb200_multi* m, int rank);
 void mpcb200_destroy_multi(mpcb200_multi* m);
@@ -333,7 +335,9 @@ int mpcb200_flush_l2(mpcb200_handle* h);
 #define MPCB200_F_KKT 5    /* 42 x N  condensed KKT stage records (see DESIGN.md "KKT record") */
 #define MPCB200_F_STEP 6   /* 8 x N   Newton step: dw (5), nu_plus (3) */
 #define MPCB200_F_SCAL 7   /* 24      per-instance scalars (see MPCB200_SC_*) */
-#define MPCB200_F_OBSIDX 8 /* K x N   associated obstacle index per row slot as double (-1 = empty) */
+#define MPCB200_F_OBSIDX 8 /* K x N   associated obstacle per row slot as double: its RESIDENT slot (-1 = empty); = its list index for
+                              lists of at most 64 obstacles */
+#define MPCB200_F_OBSGIDX 9 /* 64      list index of each resident obstacle (lists of more than 64 obstacles), -1 = free slot */
 #define MPCB200_KKT_WORDS 42
 /* offsets inside one KKT stage record (DESIGN.md "KKT record"); stage k = 0..N-2, terminal data at k = N-1 */
 #define MPCB200_K_H 0    /* 15: upper triangle (row-major) of the condensed 5x5 Hessian block of w_k = (x_k, u_k) */
@@ -368,6 +372,7 @@ int mpcb200_flush_l2(mpcb200_handle* h);
 #define MPCB200_SC_NBT 18    /* line-search backtracks so far */
 #define MPCB200_SC_COLD 19   /* 1 until the instance has been solved once (cold start pending) */
 #define MPCB200_SC_VALID 22   /* 1 = the inputs of the instance are finite (else status INVALID_INPUT, never iterated) */
+#define MPCB200_SC_OBST_DROPPED 23 /* long obstacle lists: selected obstacles that did not fit into the 64 resident slots */
 #define MPCB200_SC_DEFER 21  /* 1 = the KKT phase spent its factorisation budget: null step, regularisation resumes next iteration */
 #define MPCB200_SC_TINY 20   /* consecutive iterations with a step length below 1e-8 (2 => the instance is given up) */
 

@@ -27,7 +27,7 @@ FOOTPRINT_POINT, FOOTPRINT_CIRCULAR, FOOTPRINT_TWO_CIRCLES, FOOTPRINT_LINE, FOOT
 OBST_POINT, OBST_CIRCLE, OBST_LINE = 0, 1, 2
 STATUS_CONVERGED, STATUS_MAX_ITER, STATUS_NUMERICAL_ERROR, STATUS_INVALID_INPUT = 0, 1, 2, 3
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_NODEVICE = -1, -2, -3, -4, -5
-F_X, F_U, F_NU, F_S, F_LAM, F_KKT, F_STEP, F_SCAL, F_OBSIDX = range(9)
+F_X, F_U, F_NU, F_S, F_LAM, F_KKT, F_STEP, F_SCAL, F_OBSIDX, F_OBSGIDX = range(10)
 PHASE_INIT, PHASE_ASSOCIATE, PHASE_EVAL, PHASE_KKT, PHASE_LINESEARCH = range(5)
 OPT_SOLVE_MODE = 3
 OPT_CTAS_PER_SM = 4
@@ -35,7 +35,7 @@ SOLVE_FUSED, SOLVE_PHASED = 0, 1
 NUM_PHASES = 5
 K_H, K_G, K_A, K_B, K_E, K_C, K_HB, K_D = 0, 15, 20, 23, 29, 32, 34, 39
 (SC_DT, SC_MU, SC_RHO, SC_DELTA, SC_HTT, SC_GT, SC_DDT, SC_ERR0, SC_ERRMU, SC_ITER, SC_STATUS, SC_ALPHA, SC_OBJ,
- SC_INF, SC_DELTA_LAST, SC_NREG, SC_BLOG, SC_GLDT, SC_NBT, SC_COLD, SC_TINY, SC_DEFER, SC_VALID) = range(23)
+ SC_INF, SC_DELTA_LAST, SC_NREG, SC_BLOG, SC_GLDT, SC_NBT, SC_COLD, SC_TINY, SC_DEFER, SC_VALID, SC_OBST_DROPPED) = range(24)
 
 
 class Config(C.Structure):
@@ -189,7 +189,7 @@ EXPORTS = [
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
     "mpcb200_check_feasible", "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
     "mpcb200_resample", "mpcb200_get_horizon", "mpcb200_costmap_obstacles", "mpcb200_costmap_last_ms",
-    "mpcb200_create_multi", "mpcb200_step_batch_multi", "mpcb200_multi_device_controls", "mpcb200_multi_handle",
+    "mpcb200_create_multi", "mpcb200_step_batch_multi", "mpcb200_multi_device_controls", "mpcb200_multi_fetch_controls", "mpcb200_multi_handle",
     "mpcb200_destroy_multi", "mpcb200_multi_last_error",
 ]
 
@@ -238,6 +238,7 @@ def load_library(path=None):
     lib.mpcb200_create_multi.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     lib.mpcb200_step_batch_multi.argtypes = lib.mpcb200_step_batch.argtypes
     lib.mpcb200_multi_device_controls.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_longlong)]
+    lib.mpcb200_multi_fetch_controls.argtypes = [vp, C.c_int, dp]
     lib.mpcb200_multi_handle.argtypes = [vp, C.c_int]
     lib.mpcb200_multi_handle.restype = vp
     lib.mpcb200_destroy_multi.argtypes = [vp]
@@ -437,7 +438,7 @@ class BatchSolver:
     def ws_read(self, field, B=None):
         B = B or self.B
         cnt = self.ws_count(field)
-        shape = (B, cnt) if field == F_SCAL else (B, cnt, self.N)
+        shape = (B, cnt) if field in (F_SCAL, F_OBSGIDX) else (B, cnt, self.N)
         a = np.empty(shape)
         self._check(self.lib.mpcb200_ws_read(self.h, field, B, _dp(a)), "mpcb200_ws_read")
         return a
@@ -537,12 +538,9 @@ class MultiSolver:
         rc = self.lib.mpcb200_multi_device_controls(self.h, rank, C.byref(p), C.byref(n))
         if rc != 0:
             raise SolverError("mpcb200_multi_device_controls failed")
-        import torch
         G = len(self.devices)
         per = n.value // (G * (self.N - 1) * 2)
         host = np.empty(n.value)
-        cudart = torch.cuda.cudart()
-        with torch.cuda.device(self.devices[rank]):
-            err = cudart.cudaMemcpy(host.ctypes.data, p.value, n.value * 8, 2)   # cudaMemcpyDeviceToHost
-        assert int(err) == 0, err
+        if self.lib.mpcb200_multi_fetch_controls(self.h, rank, _dp(host)) != 0:
+            raise SolverError("mpcb200_multi_fetch_controls failed")
         return host.reshape(G, per, self.N - 1, 2)

@@ -35,7 +35,7 @@ struct WsLayout
     int oR0, oOG;            // row residuals at the current point (RS x N), obstacle row value + gradient (4K x N)
     int oKKT, oMM;           // condensed KKT stage records [k][RSTR]; stage matrices + gains of the KKT sweep [k][MSTR]
     int oIN;                 // x0(3) xf(3) u_prev(2) n_obst n_vp has_xinit reinit
-    int oOBST, oOTYPE, oVP, oXINIT;
+    int oOBST, oOTYPE, oVP, oXINIT, oOGIDX;
 };
 #define IN_X0 0
 #define IN_XF 3
@@ -44,6 +44,7 @@ struct WsLayout
 #define IN_NVP 9
 #define IN_HASXINIT 10
 #define IN_REINIT 11
+#define IN_NRES 12         /* obstacles in the resident list (= IN_NOBST unless the list stays in global memory) */
 #define IN_WORDS 16
 
 // solver constants (same values as the oracle)

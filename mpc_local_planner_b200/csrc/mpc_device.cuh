@@ -115,30 +115,40 @@ __device__ __forceinline__ bool scatter_one(const WsLayout& L, double* W, const 
     }
     if (lane < 2) { const double u = in.u_prev ? in.u_prev[src * 2 + lane] : 0.0; AIN(IN_UPREV + lane) = u; ok = ok && isfinite(u); }
     int nob = 0, nvp = 0;
-    if (in.obst_count) nob = min(max(in.obst_count[src], 0), min(in.obst_max, L.M));
+    const bool long_list = in.obst_max > L.M;   // the list stays in global memory, the association copies what it selects
+    if (in.obst_count) nob = min(max(in.obst_count[src], 0), in.obst_max);
     if (in.vp_count) nvp = min(max(in.vp_count[src], 0), min(in.vp_max, L.V));
     if (lane == 0)
     {
         AIN(IN_NOBST) = (double)nob; AIN(IN_NVP) = (double)nvp;
+        AIN(IN_NRES) = long_list ? 0.0 : (double)nob;
         AIN(IN_HASXINIT) = in.x_init ? 1.0 : 0.0;
         AIN(IN_REINIT) = (in.reinit && in.reinit[src]) ? 1.0 : 0.0;
     }
     for (int i = lane; i < nob * MPCB200_OBST_STRIDE; i += 32)
     {
         const double v = in.obst_params[src * in.obst_max * MPCB200_OBST_STRIDE + i];
-        W[L.oOBST + i] = v;
+        if (!long_list) W[L.oOBST + i] = v;
         ok = ok && isfinite(v);
     }
     for (int i = lane; i < nob; i += 32)
     {
         const int t = in.obst_type[src * in.obst_max + i];
-        W[L.oOTYPE + i] = (double)t;
+        if (!long_list) W[L.oOTYPE + i] = (double)t;
         ok = ok && t >= MPCB200_OBST_POINT && t <= MPCB200_OBST_LINE;
     }
     for (int i = lane; i < nvp * 3; i += 32) { const double v = in.vp_poses[src * in.vp_max * 3 + i]; W[L.oVP + i] = v; ok = ok && isfinite(v); }
     if (in.x_init && xinit_dst)
         for (int i = lane; i < 3 * N; i += 32) xinit_dst[i] = in.x_init[src * 3 * N + i];
     return __all_sync(FULLMASK, ok) != 0;
+}
+
+// the full obstacle list of instance `src`: the image (short lists) or the caller's arrays
+__device__ __forceinline__ ObstSrc obstacle_source(const WsLayout& L, const double* W, const InputPtrs& in, int64_t src)
+{
+    if (in.obst_count && in.obst_max > L.M)
+        return ObstSrc{in.obst_params + src * in.obst_max * MPCB200_OBST_STRIDE, nullptr, in.obst_type + src * in.obst_max};
+    return ObstSrc{W + L.oOBST, W + L.oOTYPE, nullptr};
 }
 
 // results of one instance into the compact output arrays (threads t, t + nt, ... of the owner)
@@ -171,7 +181,7 @@ __device__ __forceinline__ void gather_one(const WsLayout& L, const double* W, c
 
 // ---- PHASE_INIT (one warp): cold initial guess or warm-start shift ----------------------------------------
 // xinit: the instance's initial plan samples [N][3] (read when IN_HASXINIT)
-__device__ __forceinline__ void dev_init(const Cfg& c, const WsLayout& L, double* W, const double* xinit, int force_cold, int lane)
+__device__ __forceinline__ void dev_init(const Cfg& c, const WsLayout& L, double* W, const ObstSrc& os, const double* xinit, int force_cold, int lane)
 {
     const int N = L.N;
     const bool cold = force_cold || ASC(MPCB200_SC_COLD) != 0.0 || AIN(IN_REINIT) != 0.0;
@@ -189,7 +199,7 @@ __device__ __forceinline__ void dev_init(const Cfg& c, const WsLayout& L, double
             {
                 const double A = BUMP_STEP * (double)m;
                 double v = 0.0;
-                for (int k = lane; k < N; k += 32) v += bump_stage_violation(c, L, W, k, A, nx, ny);
+                for (int k = lane; k < N; k += 32) v += bump_stage_violation(c, L, W, os, k, A, nx, ny);
                 const double score = 1e-3 * fabs(A) + warp_sum(v);
                 if (bump_better(score, best)) { best = score; best_a = A; }
             }
@@ -221,13 +231,113 @@ __device__ __forceinline__ void dev_init(const Cfg& c, const WsLayout& L, double
 }
 
 // ---- PHASE_ASSOCIATE (one warp): obstacle / via-point association, initial-guess repair, dual initialisation ----
-__device__ __forceinline__ void dev_associate(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int first_outer, int lane)
+// Association over a LONG obstacle list (StageInequalitySE2::update, stage_inequality_se2.cpp:73-147, for the hundreds of point
+// obstacles of a raw costmap): the stages one after the other, the lanes over the obstacles of the list in global memory.  Per
+// stage the same selection as associate_stage -- forced inclusions in list order, then the nearest left and the nearest right
+// obstacle within the cut-off, into the K row slots with the same replacement rule -- and only the selected obstacles are copied
+// into the resident list (each once: `gidx` = list index of every resident slot; a full list drops and counts).
+__device__ __forceinline__ void kslot_insert(int* idx, double* dst, int& cnt, int KK, int j, double dist)
+{
+    if (cnt < KK) { idx[cnt] = j; dst[cnt] = dist; ++cnt; return; }
+    int far = 0;
+    for (int i = 1; i < KK; ++i)
+        if (dst[i] > dst[far]) far = i;
+    if (dist < dst[far]) { idx[far] = j; dst[far] = dist; }
+}
+__device__ __forceinline__ void dev_associate_list(const Cfg& c, const WsLayout& L, double* W, const ObstSrc& os, double* gidx /* [L.M] scratch */, int lane)
+{
+    const int N = L.N, K = L.K, KK = K < 16 ? K : 16;
+    const int nobst = (int)AIN(IN_NOBST);
+    int nres = 0, dropped = 0;
+    for (int i = lane; i < L.M; i += 32) gidx[i] = -1.0;
+    for (int k = lane; k < N; k += 32)
+        for (int j = 0; j < K; ++j) AOBS(j, k) = -1.0;
+    __syncwarp();
+    for (int k = 1; k <= N - 2 && K > 0; ++k)
+    {
+        const double px = AX(0, k), py = AX(1, k), pth = AX(2, k);
+        const double ox = cos(pth), oy = sin(pth);
+        int sidx[16]; double sdst[16]; int cnt = 0;
+        double lmin = 1e300, rmin = 1e300; int left = -1, right = -1;
+        for (int base = 0; base < nobst; base += 32)
+        {
+            const int j = base + lane;
+            double dist = 1e300; bool forced = false;
+            if (j < nobst)
+            {
+                double ob[5];
+                const double* op0 = os.p(j);
+                const int ot = os.type(j);
+                const double* op = obstacle_at(c, op0, k, ASC(MPCB200_SC_DT), ob);
+                dist = footprint_distance<false, false>(c, px, py, pth, ot, op, nullptr, nullptr);
+                forced = dist < c.force_inclusion_dist || obstacle_is_dynamic(c, op0);
+                if (!forced && !(dist > c.cutoff_dist))
+                {
+                    double ccx, ccy;
+                    obstacle_centroid(ot, op, &ccx, &ccy);
+                    if (ox * ccy - ccx * oy > 0) { if (dist < lmin) { lmin = dist; left = j; } }
+                    else { if (dist < rmin) { rmin = dist; right = j; } }
+                }
+            }
+            unsigned m = __ballot_sync(FULLMASK, forced);
+            while (m)   // forced inclusions in list order (uniform: every lane keeps the same slot list)
+            {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                kslot_insert(sidx, sdst, cnt, KK, base + src, __shfl_sync(FULLMASK, dist, src));
+            }
+        }
+        // nearest left / right over the lanes: smallest distance, the earliest obstacle on ties (the reference's strict <)
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const double ol = __shfl_xor_sync(FULLMASK, lmin, o); const int il = __shfl_xor_sync(FULLMASK, left, o);
+            if (il >= 0 && (left < 0 || ol < lmin || (ol == lmin && il < left))) { lmin = ol; left = il; }
+            const double orr = __shfl_xor_sync(FULLMASK, rmin, o); const int ir = __shfl_xor_sync(FULLMASK, right, o);
+            if (ir >= 0 && (right < 0 || orr < rmin || (orr == rmin && ir < right))) { rmin = orr; right = ir; }
+        }
+        if (left >= 0) kslot_insert(sidx, sdst, cnt, KK, left, lmin);
+        if (right >= 0) kslot_insert(sidx, sdst, cnt, KK, right, rmin);
+        // resident slots of the selected obstacles
+        for (int s_ = 0; s_ < cnt; ++s_)
+        {
+            const int g = sidx[s_];
+            int slot = -1;
+            for (int b0 = 0; b0 < L.M; b0 += 32)
+            {
+                const unsigned hit = __ballot_sync(FULLMASK, b0 + lane < nres && (int)gidx[b0 + lane] == g);
+                if (hit) { slot = b0 + __ffs(hit) - 1; break; }
+            }
+            if (slot < 0)
+            {
+                if (nres < L.M)
+                {
+                    slot = nres++;
+                    if (lane < MPCB200_OBST_STRIDE) W[L.oOBST + slot * MPCB200_OBST_STRIDE + lane] = os.p(g)[lane];
+                    if (lane == 0) { W[L.oOTYPE + slot] = (double)os.type(g); gidx[slot] = (double)g; }
+                    __syncwarp();
+                }
+                else ++dropped;
+            }
+            if (lane == 0 && slot >= 0) AOBS(s_, k) = (double)slot;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) { AIN(IN_NRES) = (double)nres; ASC(MPCB200_SC_OBST_DROPPED) = (double)dropped; }
+    __syncwarp();
+}
+
+// os / gidx: the instance's full obstacle list and, for a list in global memory (long_list), scratch for the list index of every
+// resident slot
+__device__ __forceinline__ void dev_associate(const Cfg& c, const WsLayout& L, double* W, double uprev_dt, int first_outer, int lane,
+                                              const ObstSrc& os, bool long_list, double* gidx)
 {
     const int N = L.N;
     const bool cold_pending = first_outer && ASC(MPCB200_SC_COLD) == 2.0;
     const bool repair = cold_pending && !c.reference_initial_guess;   // solver-side preprocessing of a cold guess (off: the reference's guess)
     __syncwarp();
-    for (int k = lane; k < N; k += 32) associate_stage(c, L, W, k);
+    if (long_list) dev_associate_list(c, L, W, os, gidx, lane);
+    else
+        for (int k = lane; k < N; k += 32) associate_stage(c, L, W, k);
     // via-points: MinTimeViaPointsCost::update with findClosestPose (argmin over the grid, first minimum wins)
     if (has_viapoints(c))
     {

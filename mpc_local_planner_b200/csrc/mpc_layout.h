@@ -3,7 +3,8 @@
 #include "mpc_core.h"
 #include "mpc_riccati_warp.h"
 
-#define MAX_OBST 64
+#define MAX_OBST 64          // obstacles resident per instance (the union of what the association selects along the horizon)
+#define MAX_OBST_LIST 2048   // obstacles per instance in the caller's list (kept in global memory beyond MAX_OBST)
 #define MAX_VP 8
 
 HD inline bool kkt_is_ext(const Cfg& c) { return c.variable_dt || c.xf_fixed[0] || c.xf_fixed[1] || c.xf_fixed[2]; }
@@ -43,6 +44,7 @@ static inline void make_layout(const mpcb200_config* c, int M, int V, WsLayout& 
     L.oOBST = take((M > 0 ? M : 1) * MPCB200_OBST_STRIDE);
     // ---- global memory only ----
     L.oXINIT = take(3 * N);
+    L.oOGIDX = take(M > 0 ? M : 1);   // list index of every resident obstacle (long lists; diagnostics and tests)
     L.stride = ((int64_t)o + 15) / 16 * 16;
 }
 // doubles of the resident prefix when m_used obstacles per instance are in use

@@ -14,6 +14,17 @@
 #pragma once
 #include "mpc_core.h"
 
+// Where the FULL obstacle list of an instance is read from: the resident image (lists of at most MAX_OBST obstacles are copied
+// there and list index = resident slot) or the caller's compact arrays in global memory (longer lists, e.g. the point obstacles of
+// a raw costmap: only the obstacles the association selects enter the image).
+struct ObstSrc
+{
+    const double* par;   // [n][MPCB200_OBST_STRIDE]
+    const double* td;    // types as doubles (image) ...
+    const int* ti;       // ... or as ints (compact input arrays)
+    HD int type(int j) const { return ti ? ti[j] : (int)td[j]; }
+    HD const double* p(int j) const { return par + (size_t)j * MPCB200_OBST_STRIDE; }
+};
 #define AX(c_, k_) W[L.oX + (c_) * N + (k_)]
 #define AU(c_, k_) W[L.oU + (c_) * N + (k_)]
 #define ANU(c_, k_) W[L.oNU + (c_) * N + (k_)]
@@ -906,7 +917,7 @@ HD inline bool bump_normal(const WsLayout& L, const double* W, double* nx, doubl
     return true;
 }
 HD inline double bump_offset(int N, int k, double A) { return A * sin(M_PI * (double)k / (double)(N - 1)); }
-HD inline double bump_stage_violation(const Cfg& c, const WsLayout& L, const double* W, int k, double A, double nx, double ny)
+HD inline double bump_stage_violation(const Cfg& c, const WsLayout& L, const double* W, const ObstSrc& os, int k, double A, double nx, double ny)
 {
     const int N = L.N;
     if (k < 1 || k > N - 2) return 0.0;
@@ -919,8 +930,8 @@ HD inline double bump_stage_violation(const Cfg& c, const WsLayout& L, const dou
     for (int j = 0; j < nobst; ++j)
     {
         double ob[5];
-        const double* op = obstacle_at(c, W + L.oOBST + j * MPCB200_OBST_STRIDE, k, c.dt_ref, ob);
-        const double d = footprint_distance_sc<false, false, true>(c, px, py, sn, cs, (int)W[L.oOTYPE + j], op, nullptr, nullptr);
+        const double* op = obstacle_at(c, os.p(j), k, c.dt_ref, ob);
+        const double d = footprint_distance_sc<false, false, true>(c, px, py, sn, cs, os.type(j), op, nullptr, nullptr);
         const double viol = c.min_obstacle_dist + BUMP_MARGIN - d;
         if (viol > 0.0) v += viol;
     }
@@ -946,7 +957,8 @@ HD inline void bump_select_serial(const Cfg& c, const WsLayout& L, double* W)
     {
         const double A = BUMP_STEP * (double)m;
         double score = 1e-3 * fabs(A);
-        for (int k = 1; k <= N - 2; ++k) score += bump_stage_violation(c, L, W, k, A, nx, ny);
+        const ObstSrc os{W + L.oOBST, W + L.oOTYPE, nullptr};
+        for (int k = 1; k <= N - 2; ++k) score += bump_stage_violation(c, L, W, os, k, A, nx, ny);
         if (bump_better(score, best)) { best = score; best_a = A; }
     }
     for (int k = 1; k <= N - 2; ++k) { const double o = bump_offset(N, k, best_a); AX(0, k) += o * nx; AX(1, k) += o * ny; }

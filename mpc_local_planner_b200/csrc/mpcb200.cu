@@ -82,7 +82,7 @@ __device__ __forceinline__ void mark_invalid(const WsLayout& L, double* W)
 // ---- kernel: ONE PHASE of the solve for every instance of a batch (kernel-level API and the phased solve mode) ----
 template <bool LINES>
 __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) phase_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, double* ws, int B, int phase,
-                                                                       double uprev_dt, int force_cold, int first_outer, int* n_active, int img_words)
+                                                                       double uprev_dt, int force_cold, int first_outer, int* n_active, int img_words, InputPtrs in)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ CtaShared sh;
@@ -101,8 +101,14 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) phase_kernel(const __
     stage_in(W, Gp, img_words, bar, 0, tid);
     switch (phase)
     {
-        case MPCB200_PHASE_INIT: if (wid == 0) dev_init(c, L, W, Gp + L.oXINIT, force_cold, lane); break;
-        case MPCB200_PHASE_ASSOCIATE: if (wid == 0) dev_associate(c, L, W, uprev_dt, first_outer, lane); break;
+        case MPCB200_PHASE_INIT: if (wid == 0) dev_init(c, L, W, obstacle_source(L, W, in, inst), Gp + L.oXINIT, force_cold, lane); break;
+        case MPCB200_PHASE_ASSOCIATE:
+            if (wid == 0)
+            {
+                const bool long_list = in.obst_count && in.obst_max > L.M;
+                dev_associate(c, L, W, uprev_dt, first_outer, lane, obstacle_source(L, W, in, inst), long_list, Gp + L.oOGIDX);
+            }
+            break;
         case MPCB200_PHASE_EVAL:
         {
             const int fin = dev_eval<LINES>(c, L, W, uprev_dt, sh, tid, nt);
@@ -112,7 +118,9 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) phase_kernel(const __
         case MPCB200_PHASE_LINESEARCH: dev_linesearch<LINES>(c, L, W, uprev_dt, sh, tid, nt); break;
         default: break;
     }
-    stage_out(Gp, W, L.oOTYPE, tid);   // everything but the inputs
+    // everything but the inputs -- except after the association over a long list, which fills the resident obstacles
+    const bool wrote_obstacles = phase == MPCB200_PHASE_ASSOCIATE && in.obst_count && in.obst_max > L.M;
+    stage_out(Gp, W, wrote_obstacles ? img_words : L.oOTYPE, tid);
 }
 
 // ---- kernel: PHASE_KKT -- one warp per instance: records HBM -> shared memory (one bulk-async copy), warp-cooperative
@@ -213,12 +221,20 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
         __syncthreads();
         if (s_valid)
         {
-            if (wid == 0) dev_init(c, L, W, a.in.x_init ? a.in.x_init + (int64_t)inst * 3 * N : nullptr, a.force_cold, lane);
+            const bool long_list = a.in.obst_count && a.in.obst_max > L.M;
+            const ObstSrc os = obstacle_source(L, W, a.in, inst);
+            double* gidx = W + L.oMM;   // scratch of the KKT / line-search phases, free while the association runs
+            if (wid == 0) dev_init(c, L, W, os, a.in.x_init ? a.in.x_init + (int64_t)inst * 3 * N : nullptr, a.force_cold, lane);
             __syncthreads();
             TICK(MPCB200_PHASE_INIT);
             for (int oi = 0; oi < outer; ++oi)
             {
-                if (wid == 0) dev_associate(c, L, W, a.uprev_dt, oi == 0, lane);
+                if (wid == 0)
+                {
+                    dev_associate(c, L, W, a.uprev_dt, oi == 0, lane, os, long_list, gidx);
+                    if (long_list && Gp)
+                        for (int i = lane; i < L.M; i += 32) Gp[L.oOGIDX + i] = gidx[i];
+                }
                 __syncthreads();
                 TICK(MPCB200_PHASE_ASSOCIATE);
                 for (;;)
@@ -336,6 +352,7 @@ struct mpcb200_handle
     cudaEvent_t poll_ev[2], t0, t1;
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
+    int d_obst_m, s_obst_m;   // obstacles per instance the staging arrays (batch / queue job) hold
     // queue job (mpcb200_solve_stream): inputs / outputs of the whole queue on the device (grown on demand)
     size_t stream_cap;
     double *s_x0, *s_xf, *s_uprev, *s_obst, *s_vp, *s_useq, *s_xseq, *s_dt, *s_kkt, *s_upacked;
@@ -462,6 +479,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_x0, B * 3 * 8)); CKC(cudaMalloc(&h->d_xf, B * 3 * 8)); CKC(cudaMalloc(&h->d_uprev, B * 2 * 8));
     CKC(cudaMalloc(&h->d_obst, B * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CKC(cudaMalloc(&h->d_obst_count, B * 4));
     CKC(cudaMalloc(&h->d_obst_type, B * MAX_OBST * 4));
+    h->d_obst_m = MAX_OBST; h->s_obst_m = 0;
     CKC(cudaMalloc(&h->d_vp, B * MAX_VP * 3 * 8)); CKC(cudaMalloc(&h->d_vp_count, B * 4));
     CKC(cudaMalloc(&h->d_xinit, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_reinit, B));
     CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
@@ -550,8 +568,9 @@ static int group_threads(const mpcb200_handle* h)
     const int gw = (h->cfg.n + 31) / 32;
     return 32 * (gw < MAX_GROUP_WARPS ? gw : MAX_GROUP_WARPS);   // a lane per stage
 }
-static int image_words(const mpcb200_handle* h) { return resident_words(h->L, h->has_obst ? h->obst_max : 0); }
+static int image_words(const mpcb200_handle* h) { return resident_words(h->L, h->has_obst ? (h->obst_max < h->L.M ? h->obst_max : h->L.M) : 0); }
 
+static InputPtrs batch_inputs(mpcb200_handle* h, bool with_uprev);
 static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int first_outer, int* n_active, bool timed)
 {
     const int img_words = image_words(h);
@@ -565,8 +584,8 @@ static int launch_phase(mpcb200_handle* h, int phase, int B, int force_cold, int
     }
     else if (phase >= 0 && phase < MPCB200_NUM_PHASES)
     {
-        if (h->has_lines) phase_kernel<true><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words);
-        else phase_kernel<false><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words);
+        if (h->has_lines) phase_kernel<true><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words, batch_inputs(h, true));
+        else phase_kernel<false><<<B, group_threads(h), img_smem, h->stream>>>(h->cfg, h->L, h->ws, B, phase, h->uprev_dt, force_cold, first_outer, n_active, img_words, batch_inputs(h, true));
     }
     else return set_err(h, MPCB200_E_INVALID, "unknown phase");
     if (timed) ev_end(h);
@@ -611,7 +630,7 @@ static int copy_inputs(mpcb200_handle* h, const Staging& d, size_t B, const doub
     h->has_obst = 0; h->obst_max = 0; h->has_lines = is_midpoint(h->cfg);  // the kernel variants with the rarely used paths compiled in
     if (obst && obst->count && obst->max_per_instance > 0)
     {
-        if (obst->max_per_instance > MAX_OBST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 64 obstacles per instance");
+        if (obst->max_per_instance > MAX_OBST_LIST) return set_err(h, MPCB200_E_UNSUPPORTED, "more than 2048 obstacles per instance");
         if (!obst->type || !obst->params) return set_err(h, MPCB200_E_INVALID, "obstacle types and parameters are required");
         const size_t M = (size_t)obst->max_per_instance;
         scan_obstacles(h, B, obst);
@@ -642,6 +661,24 @@ static int copy_inputs(mpcb200_handle* h, const Staging& d, size_t B, const doub
     in->reinit = h->has_reinit ? d.reinit : nullptr;
     return 0;
 }
+// obstacle lists longer than the resident list: the staging arrays grow to the list length on first use
+static int reserve_obstacles(mpcb200_handle* h, bool queue, size_t rows, const mpcb200_obstacles* obst)
+{
+    if (!obst || !obst->count || obst->max_per_instance <= 0 || obst->max_per_instance > MAX_OBST_LIST) return 0;
+    int& cap = queue ? h->s_obst_m : h->d_obst_m;
+    if (obst->max_per_instance <= cap) return 0;
+    double*& par = queue ? h->s_obst : h->d_obst;
+    int*& typ = queue ? h->s_obst_type : h->d_obst_type;
+    CK(cudaStreamSynchronize(h->stream));
+    if (par) cudaFree(par);
+    if (typ) cudaFree(typ);
+    par = nullptr; typ = nullptr; cap = 0;
+    const size_t M = (size_t)obst->max_per_instance;
+    CK(cudaMalloc(&par, rows * M * MPCB200_OBST_STRIDE * 8));
+    CK(cudaMalloc(&typ, rows * M * 4));
+    cap = (int)M;
+    return 0;
+}
 static Staging batch_staging(mpcb200_handle* h) { return Staging{h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_vp, h->d_xinit, h->d_obst_count, h->d_obst_type, h->d_vp_count, h->d_reinit}; }
 static InputPtrs batch_inputs(mpcb200_handle* h, bool with_uprev)
 {
@@ -660,7 +697,9 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
     CK(cudaSetDevice(h->device));
     InputPtrs in;
     if (!u_prev) CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
-    int rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit, &in);
+    int rc = reserve_obstacles(h, false, (size_t)h->max_batch, obst);
+    if (rc) return rc;
+    rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit, &in);
     if (rc) return rc;
     // the instance blocks get the inputs as well: the kernel-level API (phase kernels) works on the blocks
     in.u_prev = h->d_uprev;
@@ -799,10 +838,11 @@ static int stream_reserve(mpcb200_handle* h, size_t total)
     void* old[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
                    h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters};
     for (void* p : old) if (p) cudaFree(p);
-    h->stream_cap = 0;
+    h->stream_cap = 0; h->s_obst_m = 0;
     const size_t N = (size_t)h->n_cap, T = total;  // sized for the largest horizon the handle can be resampled to
     CK(cudaMalloc(&h->s_x0, T * 3 * 8)); CK(cudaMalloc(&h->s_xf, T * 3 * 8)); CK(cudaMalloc(&h->s_uprev, T * 2 * 8));
     CK(cudaMalloc(&h->s_obst, T * MAX_OBST * MPCB200_OBST_STRIDE * 8)); CK(cudaMalloc(&h->s_obst_count, T * 4)); CK(cudaMalloc(&h->s_obst_type, T * MAX_OBST * 4));
+    h->s_obst_m = MAX_OBST;
     CK(cudaMalloc(&h->s_vp, T * MAX_VP * 3 * 8)); CK(cudaMalloc(&h->s_vp_count, T * 4));
     CK(cudaMalloc(&h->s_useq, T * N * 2 * 8)); CK(cudaMalloc(&h->s_xseq, T * N * 3 * 8)); CK(cudaMalloc(&h->s_dt, T * 8)); CK(cudaMalloc(&h->s_kkt, T * 8));
     CK(cudaMalloc(&h->s_upacked, T * (N - 1) * 2 * 8)); CK(cudaMalloc(&h->s_status, T * 4)); CK(cudaMalloc(&h->s_iters, T * 4));
@@ -819,6 +859,7 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
     CK(cudaSetDevice(h->device));
     int rc = stream_reserve(h, (size_t)total);
     if (rc) return rc;
+    if ((rc = reserve_obstacles(h, true, h->stream_cap, obst))) return rc;
     const size_t T = (size_t)total, N = (size_t)h->cfg.n;
     InputPtrs in;
     Staging s{h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, nullptr, h->s_obst_count, h->s_obst_type, h->s_vp_count, nullptr};
@@ -860,6 +901,7 @@ extern "C" int mpcb200_step_batch(mpcb200_handle* h, int B, const double* x0, co
         // fused mode: the solve kernel reads the compact arrays itself, the blocks only carry the warm state
         InputPtrs in;
         if (!u_prev) CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
+        if ((rc = reserve_obstacles(h, false, (size_t)h->max_batch, obst))) return rc;
         if ((rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit, &in))) return rc;
         h->B = B;
     }
@@ -954,6 +996,7 @@ static int field_info(const mpcb200_handle* h, int field, int* off, int* cnt)
         case MPCB200_F_STEP: *off = L.oSTEP; *cnt = 8; return 0;
         case MPCB200_F_SCAL: *off = L.oSCAL; *cnt = MPCB200_SCAL_WORDS; return 0;
         case MPCB200_F_OBSIDX: *off = L.oOBS; *cnt = L.K > 0 ? L.K : 1; return 0;
+        case MPCB200_F_OBSGIDX: *off = L.oOGIDX; *cnt = L.M; return 0;
     }
     return -1;
 }
@@ -982,7 +1025,7 @@ extern "C" int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst)
                 for (int f = 0; f < KW; ++f) dst[((size_t)b * KW + f) * N + k] = tmp[((size_t)b * N + k) * RSTR + f];
         return 0;
     }
-    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * N;
+    const size_t words = (field == MPCB200_F_SCAL || field == MPCB200_F_OBSGIDX) ? (size_t)cnt : (size_t)cnt * N;
     CK(cudaMemcpy2DAsync(dst, words * 8, h->ws + off, (size_t)h->L.stride * 8, words * 8, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1005,7 +1048,7 @@ extern "C" int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const doubl
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
-    const size_t words = (field == MPCB200_F_SCAL) ? (size_t)cnt : (size_t)cnt * N;
+    const size_t words = (field == MPCB200_F_SCAL || field == MPCB200_F_OBSGIDX) ? (size_t)cnt : (size_t)cnt * N;
     CK(cudaMemcpy2DAsync(h->ws + off, (size_t)h->L.stride * 8, src, words * 8, words * 8, (size_t)B, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1108,9 +1151,10 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     CK(cudaSetDevice(h->device));
     const size_t W = (size_t)maps->size_x, H = (size_t)maps->size_y, M = (size_t)max_per_instance;
     const int nrb = (int)((H - 1 + 31) / 32);            // 32-row blocks of the rows the reference visits
-    const int Wp = (int)((W + 3) / 4 * 4);               // mask row pitch: four columns per marking thread
+    const int ncg = (int)((W + MARK_COLS - 1) / MARK_COLS); // 16-column groups per row
+    const int Wp = ncg * MARK_COLS;                      // mask row pitch: sixteen columns per marking thread
     const size_t mask_words = (size_t)B * nrb * Wp;
-    const size_t need = (size_t)B * W * H + (size_t)B * 5 * 8 + 2 * (size_t)B * W * 4 + 2 * (size_t)B * 4 + (size_t)B * M * (MPCB200_OBST_STRIDE * 8 + 4) +
+    const size_t need = (size_t)B * W * H + 16 + (size_t)B * 5 * 8 + 2 * (size_t)B * 4 + (size_t)B * M * (MPCB200_OBST_STRIDE * 8 + 4) +
                         mask_words * 4 + 512;
     if (need > h->cm_cap)
     {
@@ -1125,30 +1169,29 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     double* d_params = (double*)p; p += (size_t)B * M * MPCB200_OBST_STRIDE * 8;
     double* d_origin = (double*)p; p += (size_t)B * 2 * 8;
     double* d_pose = (double*)p; p += (size_t)B * 3 * 8;
-    int* d_colcount = (int*)p; p += (size_t)B * W * 4;
-    int* d_colstart = (int*)p; p += (size_t)B * W * 4;
     int* d_count = (int*)p; p += (size_t)B * 4;
     int* d_found = (int*)p; p += (size_t)B * 4;
     int* d_type = (int*)p; p += (size_t)B * M * 4;
-    unsigned char* d_cost = (unsigned char*)p;            // 4-byte aligned: everything before it is a multiple of 4 bytes
+    p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+    unsigned char* d_cost = (unsigned char*)p;            // 16-byte aligned (16-byte loads when size_x % 16 == 0)
     CK(cudaMemcpyAsync(d_cost, maps->cost, (size_t)B * W * H, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_origin, maps->origin, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_pose, robot_pose, (size_t)B * 24, cudaMemcpyHostToDevice, h->stream));
     h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * 40);
     CostmapArgs a{maps->size_x, maps->size_y, maps->resolution, behind_robot_dist, d_cost, d_origin, d_pose};
-    const dim3 grid_mark((unsigned)((W / 4 + 1 + 63) / 64), (unsigned)B), grid_emit((unsigned)((W + 127) / 128), (unsigned)B);
+    const dim3 grid_mark((unsigned)(((size_t)B * ncg * nrb + 255) / 256));
     cudaEvent_t t0 = h->t0, t1 = h->t1;
     // slots behind count[b] are padding: zeroed, so that what goes back to the caller (and on into step_batch) is defined
     CK(cudaMemsetAsync(d_type, 0, (size_t)B * M * 4, h->stream));
     CK(cudaMemsetAsync(d_params, 0, (size_t)B * M * MPCB200_OBST_STRIDE * 8, h->stream));
     CK(cudaEventRecord(t0, h->stream));
-    if (W % 4 == 0) costmap_mark_kernel<true><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
-    else costmap_mark_kernel<false><<<grid_mark, 64, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colcount);
-    costmap_offsets_kernel<<<B, 256, 0, h->stream>>>(maps->size_x, B, d_colcount, d_colstart, max_per_instance, d_count, d_found);
-    costmap_emit_kernel<<<grid_emit, 128, 0, h->stream>>>(a, B, nrb, Wp, d_mask, d_colstart, max_per_instance, d_params, d_type);
+    if (W % 16 == 0) costmap_mark_kernel<16><<<grid_mark, 256, 0, h->stream>>>(a, B, nrb, ncg, Wp, d_mask);
+    else if (W % 4 == 0) costmap_mark_kernel<4><<<grid_mark, 256, 0, h->stream>>>(a, B, nrb, ncg, Wp, d_mask);
+    else costmap_mark_kernel<1><<<grid_mark, 256, 0, h->stream>>>(a, B, nrb, ncg, Wp, d_mask);
+    costmap_emit_kernel<<<B, 256, 0, h->stream>>>(a, B, nrb, Wp, d_mask, max_per_instance, d_count, d_found, d_params, d_type);
     CK(cudaGetLastError());
     CK(cudaEventRecord(t1, h->stream));
-    h->stats.launches_total += 3;
+    h->stats.launches_total += 2;
     CK(cudaMemcpyAsync(count, d_count, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
     if (found) CK(cudaMemcpyAsync(found, d_found, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(type, d_type, (size_t)B * M * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1310,6 +1353,15 @@ extern "C" int mpcb200_multi_device_controls(mpcb200_multi* m, int rank, void** 
     if (!m || rank < 0 || rank >= m->n_dev) return MPCB200_E_INVALID;
     if (dev_ptr) *dev_ptr = m->d_all[rank];
     if (n_doubles) *n_doubles = (long long)m->n_dev * m->max_per * (m->n - 1) * 2;
+    return MPCB200_OK;
+}
+
+extern "C" int mpcb200_multi_fetch_controls(mpcb200_multi* m, int rank, double* host)
+{
+    if (!m || rank < 0 || rank >= m->n_dev || !host) return MPCB200_E_INVALID;
+    if (cudaSetDevice(m->devices[rank]) != cudaSuccess ||
+        cudaMemcpy(host, m->d_all[rank], (size_t)m->n_dev * m->max_per * (m->n - 1) * 16, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return multi_err(m, MPCB200_E_CUDA, "copy of the gathered controls failed");
     return MPCB200_OK;
 }
 

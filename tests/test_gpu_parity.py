@@ -182,10 +182,18 @@ def test_maximum_obstacle_count(cuda_lib, orc):
     both = out["status"] == 0
     assert both.sum() >= 3
     assert np.abs(out["u_seq"][both] - ref["u_seq"][both]).max() < U_TOL
-    with pytest.raises(capi.SolverError):  # 65 obstacles: over the capacity
-        s2 = _solver(cfg, B)
+    # the same 64 obstacles in a list with room for 80: the list stays in global memory, the result does not change
+    pad = 80
+    types2 = np.zeros((B, pad), dtype=np.int32); types2[:, :M] = types
+    params2 = np.zeros((B, pad, capi.OBST_STRIDE)); params2[:, :M] = params
+    s2 = _solver(cfg, B)
+    out2 = s2.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], (count, types2, params2))
+    np.testing.assert_array_equal(out2["status"], out["status"])
+    assert np.abs(out2["u_seq"][both] - out["u_seq"][both]).max() < 1e-9
+    with pytest.raises(capi.SolverError):  # the list capacity of the ABI
         s2.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"],
-                (np.full(B, 65, dtype=np.int32), np.zeros((B, 65), dtype=np.int32), np.zeros((B, 65, capi.OBST_STRIDE))))
+                (np.full(B, 2049, dtype=np.int32), np.zeros((B, 2049), dtype=np.int32), np.zeros((B, 2049, capi.OBST_STRIDE))))
+    s2.close()
 
 
 @pytest.mark.parametrize("cid,pool,total", [(2, 64, 300), (3, 32, 100), (4, 96, 96)])

@@ -236,3 +236,96 @@ def test_multi_device_handle_equals_single_device(cuda_lib):
         g = m.gathered_controls(rank).reshape(G * per, cfg.n - 1, 2)[:B]
         np.testing.assert_array_equal(g, one["u_seq"][:, :-1, :])
     m.close()
+
+
+def _costmap_scene(B, density, seed, ahead=3.0):
+    """robots on random costmaps, goals 3 m ahead, the cells around start and goal cleared"""
+    from test_oracle_functions import _random_costmap
+    rng = np.random.default_rng(seed)
+    W, H, res = 200, 160, 0.05
+    cost = np.stack([_random_costmap(rng, W, H, density) for _ in range(B)])
+    cost[:, :, W - 1] = 0; cost[:, H - 1, :] = 0
+    origin = rng.uniform(-3, 3, (B, 2))
+    pose = np.concatenate([origin + rng.uniform(2.5, 4.5, (B, 2)), rng.uniform(-np.pi, np.pi, (B, 1))], axis=1)
+    goal = pose.copy(); goal[:, 0] += ahead * np.cos(pose[:, 2]); goal[:, 1] += ahead * np.sin(pose[:, 2])
+    yy, xx = np.mgrid[0:H, 0:W]
+    for b in range(B):
+        cx, cy = origin[b, 0] + (xx + 0.5) * res, origin[b, 1] + (yy + 0.5) * res
+        for p in (pose[b], goal[b]):
+            cost[b][(cx - p[0]) ** 2 + (cy - p[1]) ** 2 < 0.7 ** 2] = 0
+    return cost, origin, res, pose, goal
+
+
+def test_long_obstacle_lists_stay_in_global_memory(cuda_lib, orc):
+    """SURVEY 8 f-1, second half: the raw costmap list of a robot (hundreds of point obstacles, far beyond the 64 resident
+    slots) goes into step() as it is.  The association runs over the list in global memory (StageInequalitySE2::update,
+    stage_inequality_se2.cpp:73-147) and only what it selects becomes resident: same rows per stage as the oracle's loop over the
+    full list, same cold start (the bumps look at the full list as well), same solves."""
+    B, M = 16, 512
+    cost, origin, res, pose, goal = _costmap_scene(B, 0.006, 11)
+    cfg = configs.cfg2(tol=1e-6)
+    s = capi.BatchSolver(cfg, B, device=0)
+    (count, typ, par), found = s.costmap_obstacles(cost, origin, res, pose, 0.3, M)
+    assert count.max() > 100 and (found <= M).all()
+    data = dict(x0=pose, xf=goal, u_prev=np.zeros((B, 2)), u_prev_dt=0.2, obstacles=(count, typ, par), viapoints=None)
+    s.upload(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    s.run_phase(capi.PHASE_INIT); s.run_phase(capi.PHASE_ASSOCIATE)
+    X, OBS, GIDX, SC = (s.ws_read(f) for f in (capi.F_X, capi.F_OBSIDX, capi.F_OBSGIDX, capi.F_SCAL))
+    rows = 0
+    for b in range(B):
+        o = orc.instance_from_batch(cfg, data, b)
+        o.init_cold(); o.associate()
+        want = o.arr("OBSIDX")
+        slot = OBS[b].astype(int)
+        got = np.where(slot >= 0, GIDX[b].astype(int)[np.clip(slot, 0, None)], -1)
+        np.testing.assert_array_equal(got, want.astype(int))
+        used = np.unique(slot[slot >= 0])
+        assert len(used) == (GIDX[b] >= 0).sum() and SC[b][capi.SC_OBST_DROPPED] == 0     # every resident slot is referenced, each obstacle once
+        assert len(np.unique(GIDX[b][GIDX[b] >= 0])) == len(used)
+        o.L.orc_project_init(orc.C.byref(o.p), o.ws)
+        np.testing.assert_allclose(X[b], o.arr("X"), rtol=0, atol=1e-12)
+        rows += (want >= 0).sum()
+    assert rows > 20 * B
+    s.close()
+    # whole solves, fused and phased
+    ref = orc.step_batch(cfg, data, n_threads=8)
+    for mode in (capi.SOLVE_FUSED, capi.SOLVE_PHASED):
+        s = capi.BatchSolver(cfg, B, device=0)
+        s.set_option(capi.OPT_SOLVE_MODE, mode)
+        out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+        assert (out["status"] == ref["status"]).mean() >= 0.8
+        both = (out["status"] == 0) & (ref["status"] == 0)
+        assert both.sum() >= B // 2
+        du = np.abs(out["u_seq"][both] - ref["u_seq"][both]).reshape(both.sum(), -1).max(axis=1)
+        assert (du < U_TOL).mean() >= 0.8
+        # a second, warm step with the same lists
+        out2 = s.step(out["x_seq"][:, 1], data["xf"], out["u_seq"][:, 0], 0.2, data["obstacles"], None)
+        assert (out2["status"][both] == 0).mean() >= 0.8
+        s.close()
+    # the queue entry point takes the same lists
+    s = capi.BatchSolver(cfg, B, device=0)
+    outq = s.solve_stream(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    both = (outq["status"] == 0) & (ref["status"] == 0)
+    assert both.sum() >= B // 2
+    s.close()
+
+
+def test_resident_list_overflow_is_counted(cuda_lib):
+    """a map so dense that the union of the selected obstacles exceeds the resident list: rows are dropped, counted, and the
+    solve still ends in a defined status"""
+    B, M = 4, 2048
+    cost, origin, res, pose, goal = _costmap_scene(B, 0.12, 12, ahead=4.5)
+    cfg = configs.cfg2(tol=1e-6)
+    cfg.k_max_obstacles_per_stage = 8
+    s = capi.BatchSolver(cfg, B, device=0)
+    (count, typ, par), found = s.costmap_obstacles(cost, origin, res, pose, 0.3, M)
+    assert count.max() > 1000
+    s.upload(pose, goal, None, 0.2, (count, typ, par), None)
+    s.run_phase(capi.PHASE_INIT); s.run_phase(capi.PHASE_ASSOCIATE)
+    SC, G, O = (s.ws_read(f) for f in (capi.F_SCAL, capi.F_OBSGIDX, capi.F_OBSIDX))
+    assert (SC[:, capi.SC_OBST_DROPPED] > 0).any()
+    full = SC[:, capi.SC_OBST_DROPPED] > 0
+    assert ((G >= 0).sum(axis=1)[full] == 64).all() and O.max() <= 63
+    out = s.step(pose, goal, None, 0.2, (count, typ, par), None)
+    assert np.isin(out["status"], [0, 1, 2]).all() and np.isfinite(out["u_seq"][out["status"] == 0]).all()
+    s.close()
