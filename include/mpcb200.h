@@ -159,7 +159,11 @@ typedef struct mpcb200_config {
     int reference_initial_guess;
 } mpcb200_config;
 
-/* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]). */
+/* Per-instance obstacle lists, fixed stride: instance b owns obstacles [b*max_per_instance, b*max_per_instance+count[b]).
+ * max_per_instance <= 2048.  Lists of up to 64 slots are resident with the instance; longer lists (the raw costmap lists of
+ * updateObstacleContainerWithCostmap) stay in these arrays on the device and the association (StageInequalitySE2::update,
+ * stage_inequality_se2.cpp:73-147) copies what it selects for some stage into the 64 resident slots.  A selection that does not
+ * fit any more is dropped and counted in MPCB200_SC_OBST_DROPPED (k_max_obstacles_per_stage x (n-2) <= 64 can never drop). */
 typedef struct mpcb200_obstacles {
     int max_per_instance;
     const int* count;      /* [B] */
@@ -245,7 +249,7 @@ int mpcb200_get_horizon(const mpcb200_handle* h, int* n, int* n_capacity);
  * AND farther than behind_robot_dist (costmap_obstacles_behind_robot_dist).  Order = the reference's push_back order
  * (mx outer, my inner).  Outputs in the layout of mpcb200_obstacles with max_per_instance slots per robot:
  * count[b] = obstacles written = min(found[b], max_per_instance); found[b] = cells that qualified (found > count: the list was
- * cut -- the solver takes at most 64 obstacles per instance in this round); velocities 0.
+ * cut); velocities 0.
  */
 typedef struct mpcb200_costmaps {
     int size_x, size_y;          /* cells: Costmap2D::getSizeInCellsX / Y */
@@ -256,6 +260,16 @@ typedef struct mpcb200_costmaps {
 int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* robot_pose /*[B*3]*/,
                               double behind_robot_dist, int max_per_instance, int* count /*[B]*/, int* found /*[B] or NULL*/,
                               int* type /*[B*max]*/, double* params /*[B*max*MPCB200_OBST_STRIDE]*/);
+
+/* One planning cycle from the costmaps for B robots: updateObstacleContainerWithCostmap (mpc_local_planner_ros.cpp:474-499, robot
+ * pose = x0) followed by Controller::step, as MpcLocalPlannerROS::computeVelocityCommands chains them (mpc_local_planner_ros.cpp:
+ * 330-412).  The obstacle lists never leave the device: maps H2D -> extraction into the batch's obstacle arrays -> association
+ * over the lists in global memory (up to 2048 per robot) -> solve.  obst_found[b] (optional) = cells that qualified; lists are cut
+ * at max_per_instance.  Other arguments and results as mpcb200_step_batch. */
+int mpcb200_step_batch_costmap(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                               const mpcb200_costmaps* maps, double behind_robot_dist, int max_per_instance, const mpcb200_viapoints* vp,
+                               const double* x_init, const unsigned char* reinit, double* u_seq, double* x_seq, double* dt_out, int* status,
+                               double* kkt_err, int* iters, int* obst_found, double* solve_time_s);
 /*
  * Footprint-vs-costmap feasibility of the planned poses for B robots: replaces Controller::isPoseTrajectoryFeasible
  * (src/controller.cpp:859-917; caller src/mpc_local_planner_ros.cpp:414-428, which resets the planner on a rejection).

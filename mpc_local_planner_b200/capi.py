@@ -188,7 +188,7 @@ EXPORTS = [
     "mpcb200_last_error", "mpcb200_upload_inputs", "mpcb200_solve_resident", "mpcb200_fetch_results",
     "mpcb200_device_controls", "mpcb200_ws_count", "mpcb200_ws_read", "mpcb200_ws_write", "mpcb200_run_phase",
     "mpcb200_check_feasible", "mpcb200_time_phase", "mpcb200_set_timing", "mpcb200_set_stream", "mpcb200_set_option", "mpcb200_solve_stream", "mpcb200_stats_get", "mpcb200_stats_reset", "mpcb200_export_controls", "mpcb200_flush_l2",
-    "mpcb200_resample", "mpcb200_get_horizon", "mpcb200_costmap_obstacles", "mpcb200_costmap_last_ms",
+    "mpcb200_resample", "mpcb200_get_horizon", "mpcb200_costmap_obstacles", "mpcb200_step_batch_costmap", "mpcb200_costmap_last_ms",
     "mpcb200_create_multi", "mpcb200_step_batch_multi", "mpcb200_multi_device_controls", "mpcb200_multi_fetch_controls", "mpcb200_multi_handle",
     "mpcb200_destroy_multi", "mpcb200_multi_last_error",
 ]
@@ -217,6 +217,8 @@ def load_library(path=None):
     lib.mpcb200_reset.argtypes = [vp, ucp, C.c_int]
     lib.mpcb200_resample.argtypes = [vp, C.c_int]
     lib.mpcb200_costmap_obstacles.argtypes = [vp, C.c_int, C.POINTER(Costmaps), dp, C.c_double, C.c_int, ip, ip, ip, dp]
+    lib.mpcb200_step_batch_costmap.argtypes = [vp, C.c_int, dp, dp, dp, C.c_double, C.POINTER(Costmaps), C.c_double, C.c_int, C.POINTER(ViaPoints),
+                                               dp, ucp, dp, dp, dp, ip, dp, ip, ip, dp]
     lib.mpcb200_costmap_last_ms.argtypes = [vp]
     lib.mpcb200_costmap_last_ms.restype = C.c_double
     lib.mpcb200_get_horizon.argtypes = [vp, ip, ip]
@@ -402,6 +404,28 @@ class BatchSolver:
         self._check(self.lib.mpcb200_costmap_obstacles(self.h, B, C.byref(m), _dp(pose), float(behind_robot_dist), M, _ip(count), _ip(found),
                                                        _ip(typ), _dp(par)), "mpcb200_costmap_obstacles")
         return (count, typ, par), found
+
+    def step_from_costmaps(self, x0, xf, cost, origin, resolution, behind_robot_dist, max_per_instance, u_prev=None, u_prev_dt=0.0,
+                           viapoints=None, x_init=None, reinit=None, out=None):
+        """One planning cycle from the costmaps (updateObstacleContainerWithCostmap with robot pose = x0, then Controller::step): the
+        obstacle lists stay on the device.  Returns step()'s dict plus obst_found [B]."""
+        B, x0, xf, u_prev, _, v, xi, keep = self._prep_inputs(x0, xf, u_prev, None, viapoints, x_init)
+        cost = np.ascontiguousarray(cost, dtype=np.uint8); origin = np.ascontiguousarray(origin, dtype=np.float64)
+        m = Costmaps(cost.shape[2], cost.shape[1], float(resolution), _dp(origin), cost.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        if out is None:
+            out = self.alloc_outputs(B)
+        found = np.zeros(B, dtype=np.int32)
+        t = C.c_double(0.0)
+        ri = np.ascontiguousarray(reinit, dtype=np.uint8) if reinit is not None else None
+        rc = self.lib.mpcb200_step_batch_costmap(
+            self.h, B, _dp(x0), _dp(xf), _dp(u_prev), float(u_prev_dt), C.byref(m), float(behind_robot_dist), int(max_per_instance),
+            C.byref(v) if v else None, _dp(xi), ri.ctypes.data_as(C.POINTER(C.c_ubyte)) if ri is not None else None,
+            _dp(out["u_seq"]), _dp(out["x_seq"]), _dp(out["dt"]), _ip(out["status"]), _dp(out["kkt_err"]), _ip(out["iters"]), _ip(found), C.byref(t))
+        self._check(rc, "mpcb200_step_batch_costmap")
+        out["solve_time_s"] = t.value
+        out["obst_found"] = found
+        self.B = B
+        return out
 
     def check_feasible(self, cost, origin, resolution, footprint, inscribed_radius, min_resolution_angular, look_ahead_idx=-1, x_seq=None,
                        circumscribed_radius=0.0):

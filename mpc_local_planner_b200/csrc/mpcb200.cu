@@ -349,7 +349,7 @@ struct mpcb200_handle
     int *d_status, *d_iters, *d_nactive, *d_queue;
     unsigned long long* d_counters;
     int* h_nactive;  // pinned, two poll slots
-    cudaEvent_t poll_ev[2], t0, t1;
+    cudaEvent_t poll_ev[2], t0, t1, c0, c1;   // t: around a solve, c: around the costmap kernels
     double* d_flush; size_t flush_n;
     int has_obst, has_vp, has_xinit, has_reinit, obst_max, vp_max;
     int d_obst_m, s_obst_m;   // obstacles per instance the staging arrays (batch / queue job) hold
@@ -495,7 +495,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     h->s_x0 = h->s_xf = h->s_uprev = h->s_obst = h->s_vp = h->s_useq = h->s_xseq = h->s_dt = h->s_kkt = h->s_upacked = nullptr;
     h->s_obst_count = h->s_obst_type = h->s_vp_count = h->s_status = h->s_iters = nullptr;
     CKC(cudaEventCreateWithFlags(&h->poll_ev[0], cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
-    CKC(cudaEventCreate(&h->t0)); CKC(cudaEventCreate(&h->t1));
+    CKC(cudaEventCreate(&h->t0)); CKC(cudaEventCreate(&h->t1)); CKC(cudaEventCreate(&h->c0)); CKC(cudaEventCreate(&h->c1));
     h->flush_n = (size_t)40 * 1024 * 1024;  // 320 MB > 126 MB L2
     CKC(cudaMalloc(&h->d_flush, h->flush_n * 8));
     CKC(cudaMemsetAsync(h->d_flush, 0, h->flush_n * 8, h->stream));
@@ -522,7 +522,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     for (void* p : sptrs) if (p) cudaFree(p);
     if (h->h_nactive) cudaFreeHost(h->h_nactive);
     for (auto& e : h->ev) cudaEventDestroy(e);
-    cudaEventDestroy(h->poll_ev[0]); cudaEventDestroy(h->poll_ev[1]); cudaEventDestroy(h->t0); cudaEventDestroy(h->t1);
+    cudaEventDestroy(h->poll_ev[0]); cudaEventDestroy(h->poll_ev[1]); cudaEventDestroy(h->t0); cudaEventDestroy(h->t1); cudaEventDestroy(h->c0); cudaEventDestroy(h->c1);
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -662,18 +662,18 @@ static int copy_inputs(mpcb200_handle* h, const Staging& d, size_t B, const doub
     return 0;
 }
 // obstacle lists longer than the resident list: the staging arrays grow to the list length on first use
-static int reserve_obstacles(mpcb200_handle* h, bool queue, size_t rows, const mpcb200_obstacles* obst)
+static int reserve_obstacles(mpcb200_handle* h, bool queue, size_t rows, int max_per_instance)
 {
-    if (!obst || !obst->count || obst->max_per_instance <= 0 || obst->max_per_instance > MAX_OBST_LIST) return 0;
+    if (max_per_instance <= 0 || max_per_instance > MAX_OBST_LIST) return 0;
     int& cap = queue ? h->s_obst_m : h->d_obst_m;
-    if (obst->max_per_instance <= cap) return 0;
+    if (max_per_instance <= cap) return 0;
     double*& par = queue ? h->s_obst : h->d_obst;
     int*& typ = queue ? h->s_obst_type : h->d_obst_type;
     CK(cudaStreamSynchronize(h->stream));
     if (par) cudaFree(par);
     if (typ) cudaFree(typ);
     par = nullptr; typ = nullptr; cap = 0;
-    const size_t M = (size_t)obst->max_per_instance;
+    const size_t M = (size_t)max_per_instance;
     CK(cudaMalloc(&par, rows * M * MPCB200_OBST_STRIDE * 8));
     CK(cudaMalloc(&typ, rows * M * 4));
     cap = (int)M;
@@ -697,7 +697,7 @@ static int upload_inputs(mpcb200_handle* h, int B, const double* x0, const doubl
     CK(cudaSetDevice(h->device));
     InputPtrs in;
     if (!u_prev) CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
-    int rc = reserve_obstacles(h, false, (size_t)h->max_batch, obst);
+    int rc = reserve_obstacles(h, false, (size_t)h->max_batch, (obst && obst->count) ? obst->max_per_instance : 0);
     if (rc) return rc;
     rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit, &in);
     if (rc) return rc;
@@ -859,7 +859,7 @@ extern "C" int mpcb200_solve_stream(mpcb200_handle* h, int total, const double* 
     CK(cudaSetDevice(h->device));
     int rc = stream_reserve(h, (size_t)total);
     if (rc) return rc;
-    if ((rc = reserve_obstacles(h, true, h->stream_cap, obst))) return rc;
+    if ((rc = reserve_obstacles(h, true, h->stream_cap, (obst && obst->count) ? obst->max_per_instance : 0))) return rc;
     const size_t T = (size_t)total, N = (size_t)h->cfg.n;
     InputPtrs in;
     Staging s{h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, nullptr, h->s_obst_count, h->s_obst_type, h->s_vp_count, nullptr};
@@ -901,7 +901,7 @@ extern "C" int mpcb200_step_batch(mpcb200_handle* h, int B, const double* x0, co
         // fused mode: the solve kernel reads the compact arrays itself, the blocks only carry the warm state
         InputPtrs in;
         if (!u_prev) CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
-        if ((rc = reserve_obstacles(h, false, (size_t)h->max_batch, obst))) return rc;
+        if ((rc = reserve_obstacles(h, false, (size_t)h->max_batch, (obst && obst->count) ? obst->max_per_instance : 0))) return rc;
         if ((rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, obst, vp, x_init, reinit, &in))) return rc;
         h->B = B;
     }
@@ -1140,15 +1140,15 @@ extern "C" int mpcb200_export_controls(mpcb200_handle* h, void* dst_dev)
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
-extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* robot_pose, double behind_robot_dist,
-                                         int max_per_instance, int* count, int* found, int* type, double* params)
+// costmap -> point obstacles on the device.  Poses come from the host (host_pose) or are already on the device (dev_pose: the x0 array
+// of a step); lists go to d_count / d_type / d_params ([B], [B][M], [B][M][7]; nullptr: scratch of this call).
+struct CostmapOut { int* count; int* found; int* type; double* params; };
+static int costmap_run(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* host_pose, const double* dev_pose, double behind_robot_dist,
+                       int max_per_instance, int* d_count, int* d_type, double* d_params, CostmapOut* out)
 {
-    if (!h) return MPCB200_E_INVALID;
-    if (B > 65535) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: at most 65535 robots per call");
-    if (B < 1 || !maps || !maps->cost || !maps->origin || !robot_pose || !count || !type || !params || max_per_instance < 1)
+    if (B < 1 || !maps || !maps->cost || !maps->origin || max_per_instance < 1)
         return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: B >= 1, maps, poses and output arrays are required");
     if (maps->size_x < 2 || maps->size_y < 2 || !(maps->resolution > 0)) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: maps of at least 2 x 2 cells with a positive resolution");
-    CK(cudaSetDevice(h->device));
     const size_t W = (size_t)maps->size_x, H = (size_t)maps->size_y, M = (size_t)max_per_instance;
     const int nrb = (int)((H - 1 + 31) / 32);            // 32-row blocks of the rows the reference visits
     const int ncg = (int)((W + MARK_COLS - 1) / MARK_COLS); // 16-column groups per row
@@ -1158,6 +1158,7 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
                         mask_words * 4 + 512;
     if (need > h->cm_cap)
     {
+        CK(cudaStreamSynchronize(h->stream));
         if (h->d_cm) cudaFree(h->d_cm);
         h->d_cm = nullptr; h->cm_cap = 0;
         CK(cudaMalloc(&h->d_cm, need));
@@ -1166,42 +1167,94 @@ extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200
     // carve the scratch: 16-byte aligned pieces first (mask rows are stored as uint4), then ints, then the maps
     char* p = (char*)h->d_cm;
     unsigned* d_mask = (unsigned*)p; p += mask_words * 4;
-    double* d_params = (double*)p; p += (size_t)B * M * MPCB200_OBST_STRIDE * 8;
+    double* s_params = (double*)p; p += (size_t)B * M * MPCB200_OBST_STRIDE * 8;
     double* d_origin = (double*)p; p += (size_t)B * 2 * 8;
     double* d_pose = (double*)p; p += (size_t)B * 3 * 8;
-    int* d_count = (int*)p; p += (size_t)B * 4;
+    int* s_count = (int*)p; p += (size_t)B * 4;
     int* d_found = (int*)p; p += (size_t)B * 4;
-    int* d_type = (int*)p; p += (size_t)B * M * 4;
+    int* s_type = (int*)p; p += (size_t)B * M * 4;
     p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
     unsigned char* d_cost = (unsigned char*)p;            // 16-byte aligned (16-byte loads when size_x % 16 == 0)
+    if (!d_count) d_count = s_count;
+    if (!d_type) d_type = s_type;
+    if (!d_params) d_params = s_params;
     CK(cudaMemcpyAsync(d_cost, maps->cost, (size_t)B * W * H, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_origin, maps->origin, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d_pose, robot_pose, (size_t)B * 24, cudaMemcpyHostToDevice, h->stream));
-    h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * 40);
-    CostmapArgs a{maps->size_x, maps->size_y, maps->resolution, behind_robot_dist, d_cost, d_origin, d_pose};
+    if (host_pose) CK(cudaMemcpyAsync(d_pose, host_pose, (size_t)B * 24, cudaMemcpyHostToDevice, h->stream));
+    h->stats.h2d_bytes += (long long)((size_t)B * W * H + (size_t)B * (host_pose ? 40 : 16));
+    CostmapArgs a{maps->size_x, maps->size_y, maps->resolution, behind_robot_dist, d_cost, d_origin, host_pose ? d_pose : dev_pose};
     const dim3 grid_mark((unsigned)(((size_t)B * ncg * nrb + 255) / 256));
-    cudaEvent_t t0 = h->t0, t1 = h->t1;
     // slots behind count[b] are padding: zeroed, so that what goes back to the caller (and on into step_batch) is defined
     CK(cudaMemsetAsync(d_type, 0, (size_t)B * M * 4, h->stream));
     CK(cudaMemsetAsync(d_params, 0, (size_t)B * M * MPCB200_OBST_STRIDE * 8, h->stream));
-    CK(cudaEventRecord(t0, h->stream));
+    CK(cudaEventRecord(h->c0, h->stream));
     if (W % 16 == 0) costmap_mark_kernel<16><<<grid_mark, 256, 0, h->stream>>>(a, B, nrb, ncg, Wp, d_mask);
     else if (W % 4 == 0) costmap_mark_kernel<4><<<grid_mark, 256, 0, h->stream>>>(a, B, nrb, ncg, Wp, d_mask);
     else costmap_mark_kernel<1><<<grid_mark, 256, 0, h->stream>>>(a, B, nrb, ncg, Wp, d_mask);
     costmap_emit_kernel<<<B, 256, 0, h->stream>>>(a, B, nrb, Wp, d_mask, max_per_instance, d_count, d_found, d_params, d_type);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(t1, h->stream));
+    CK(cudaEventRecord(h->c1, h->stream));
     h->stats.launches_total += 2;
-    CK(cudaMemcpyAsync(count, d_count, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (found) CK(cudaMemcpyAsync(found, d_found, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(type, d_type, (size_t)B * M * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(params, d_params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyDeviceToHost, h->stream));
+    out->count = d_count; out->found = d_found; out->type = d_type; out->params = d_params;
+    return 0;
+}
+
+extern "C" int mpcb200_costmap_obstacles(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* robot_pose, double behind_robot_dist,
+                                         int max_per_instance, int* count, int* found, int* type, double* params)
+{
+    if (!h) return MPCB200_E_INVALID;
+    if (!robot_pose || !count || !type || !params) return set_err(h, MPCB200_E_INVALID, "costmap_obstacles: B >= 1, maps, poses and output arrays are required");
+    CK(cudaSetDevice(h->device));
+    CostmapOut o;
+    int rc = costmap_run(h, B, maps, robot_pose, nullptr, behind_robot_dist, max_per_instance, nullptr, nullptr, nullptr, &o);
+    if (rc) return rc;
+    const size_t M = (size_t)max_per_instance;
+    CK(cudaMemcpyAsync(count, o.count, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (found) CK(cudaMemcpyAsync(found, o.found, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(type, o.type, (size_t)B * M * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(params, o.params, (size_t)B * M * MPCB200_OBST_STRIDE * 8, cudaMemcpyDeviceToHost, h->stream));
     h->stats.d2h_bytes += (long long)((size_t)B * 8 + (size_t)B * M * (4 + MPCB200_OBST_STRIDE * 8));
     CK(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, t0, t1));
+    CK(cudaEventElapsedTime(&ms, h->c0, h->c1));
     h->costmap_ms = ms;
     return MPCB200_OK;
+}
+
+// One planning cycle from the costmaps: MpcLocalPlannerROS::computeVelocityCommands' updateObstacleContainerWithCostmap
+// (mpc_local_planner_ros.cpp:474-499) followed by Controller::step, for B robots, without the obstacle lists leaving the device:
+// maps H2D -> mark / emit into the batch's obstacle arrays (robot pose = x0) -> association over the lists -> solve.
+extern "C" int mpcb200_step_batch_costmap(mpcb200_handle* h, int B, const double* x0, const double* xf, const double* u_prev, double u_prev_dt,
+                                          const mpcb200_costmaps* maps, double behind_robot_dist, int max_per_instance, const mpcb200_viapoints* vp,
+                                          const double* x_init, const unsigned char* reinit, double* u_seq, double* x_seq, double* dt_out, int* status,
+                                          double* kkt_err, int* iters, int* obst_found, double* solve_time_s)
+{
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (max_per_instance < 1 || max_per_instance > MAX_OBST_LIST) return set_err(h, MPCB200_E_UNSUPPORTED, "step_batch_costmap: 1..2048 obstacles per instance");
+    CK(cudaSetDevice(h->device));
+    // room for the lists in the batch's obstacle arrays
+    if ((rc = reserve_obstacles(h, false, (size_t)h->max_batch, max_per_instance))) return rc;
+    InputPtrs in;
+    if (!u_prev) CK(cudaMemsetAsync(h->d_uprev, 0, (size_t)B * 2 * 8, h->stream));
+    if ((rc = copy_inputs(h, batch_staging(h), (size_t)B, x0, xf, u_prev, u_prev_dt, nullptr, vp, x_init, reinit, &in))) return rc;
+    CostmapOut o;
+    if ((rc = costmap_run(h, B, maps, nullptr, h->d_x0, behind_robot_dist, max_per_instance, h->d_obst_count, h->d_obst_type, h->d_obst, &o))) return rc;
+    h->has_obst = 1; h->obst_max = max_per_instance;   // point obstacles only: no line-obstacle kernel variant needed
+    h->B = B;
+    if (h->solve_mode == 1)
+    {
+        in = batch_inputs(h, true);
+        scatter_inputs_kernel<<<grid_for(B, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, h->stream>>>(h->L, h->ws, B, in);
+        h->stats.launches_total += 1;
+        CK(cudaGetLastError());
+    }
+    if ((rc = solve_device(h, B, 0, solve_time_s))) return rc;
+    if (obst_found) CK(cudaMemcpyAsync(obst_found, o.found, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+    rc = fetch_results(h, B, u_seq, x_seq, dt_out, status, kkt_err, iters);
+    float ms = 0.f;
+    if (!rc && cudaEventElapsedTime(&ms, h->c0, h->c1) == cudaSuccess) h->costmap_ms = ms;
+    return rc;
 }
 
 extern "C" int mpcb200_check_feasible(mpcb200_handle* h, int B, const mpcb200_costmaps* maps, const double* x_seq, int n_poses, const double* footprint_xy,

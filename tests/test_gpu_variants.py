@@ -302,6 +302,16 @@ def test_long_obstacle_lists_stay_in_global_memory(cuda_lib, orc):
         out2 = s.step(out["x_seq"][:, 1], data["xf"], out["u_seq"][:, 0], 0.2, data["obstacles"], None)
         assert (out2["status"][both] == 0).mean() >= 0.8
         s.close()
+    # the chained entry point (maps in, controls out; the lists never leave the device) gives the same results bit for bit
+    s = capi.BatchSolver(cfg, B, device=0)
+    out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+    s.close()
+    s = capi.BatchSolver(cfg, B, device=0)
+    outc = s.step_from_costmaps(pose, goal, cost, origin, res, 0.3, M, u_prev=data["u_prev"], u_prev_dt=0.2)
+    np.testing.assert_array_equal(outc["obst_found"], found)
+    np.testing.assert_array_equal(outc["status"], out["status"])
+    np.testing.assert_array_equal(outc["u_seq"], out["u_seq"])
+    s.close()
     # the queue entry point takes the same lists
     s = capi.BatchSolver(cfg, B, device=0)
     outq = s.solve_stream(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
