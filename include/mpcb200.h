@@ -417,6 +417,10 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
 #define MPCB200_OPT_SOLVE_MODE 3
 /* MPCB200_OPT_CTAS_PER_SM: cap on the CTAs of the solve kernel resident on one SM (0 = as many as fit; tuning / experiments). */
 #define MPCB200_OPT_CTAS_PER_SM 4
+/* MPCB200_OPT_SM_PHASE_SYNC: the CTAs of the solve kernel that share an SM enter each phase of the iteration together
+   (instruction-cache locality; timing only).  -1 (default) = on when three or more CTAs fit on an SM, 0 = off, 1 = on with
+   gates before evaluation, KKT and line search, 2 = on with gates before KKT and line search only. */
+#define MPCB200_OPT_SM_PHASE_SYNC 5
 int mpcb200_set_option(mpcb200_handle* h, int option, int value);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */
@@ -427,6 +431,7 @@ typedef struct mpcb200_stats {
     long long h2d_bytes, d2h_bytes;
     long long kkt_instances; /* number of (instance, iteration) pairs the KKT phase actually factorised */
     long long kkt_sweeps;    /* backward sweeps incl. inertia-correction refactorisations */
+    double gate_ms;          /* mean time a CTA of the solve kernel waited for its SM neighbours (MPCB200_OPT_SM_PHASE_SYNC) */
 } mpcb200_stats;
 int mpcb200_stats_get(const mpcb200_handle* h, mpcb200_stats* out);
 int mpcb200_stats_reset(mpcb200_handle* h);

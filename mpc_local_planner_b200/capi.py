@@ -31,6 +31,7 @@ F_X, F_U, F_NU, F_S, F_LAM, F_KKT, F_STEP, F_SCAL, F_OBSIDX, F_OBSGIDX = range(1
 PHASE_INIT, PHASE_ASSOCIATE, PHASE_EVAL, PHASE_KKT, PHASE_LINESEARCH = range(5)
 OPT_SOLVE_MODE = 3
 OPT_CTAS_PER_SM = 4
+OPT_SM_PHASE_SYNC = 5
 SOLVE_FUSED, SOLVE_PHASED = 0, 1
 NUM_PHASES = 5
 K_H, K_G, K_A, K_B, K_E, K_C, K_HB, K_D = 0, 15, 20, 23, 29, 32, 34, 39
@@ -112,7 +113,7 @@ class ViaPoints(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("launches", C.c_longlong * NUM_PHASES), ("ms", C.c_double * NUM_PHASES),
                 ("launches_total", C.c_longlong), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
-                ("kkt_instances", C.c_longlong), ("kkt_sweeps", C.c_longlong)]
+                ("kkt_instances", C.c_longlong), ("kkt_sweeps", C.c_longlong), ("gate_ms", C.c_double)]
 
 
 def default_config():
@@ -496,7 +497,7 @@ class BatchSolver:
         self._check(self.lib.mpcb200_stats_get(self.h, C.byref(s)), "mpcb200_stats_get")
         return dict(launches=list(s.launches), ms=list(s.ms), launches_total=s.launches_total,
                     h2d_bytes=s.h2d_bytes, d2h_bytes=s.d2h_bytes, kkt_instances=s.kkt_instances,
-                    kkt_sweeps=s.kkt_sweeps)
+                    kkt_sweeps=s.kkt_sweeps, gate_ms=s.gate_ms)
 
     def stats_reset(self):
         self._check(self.lib.mpcb200_stats_reset(self.h), "mpcb200_stats_reset")

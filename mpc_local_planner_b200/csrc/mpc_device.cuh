@@ -251,7 +251,7 @@ __device__ __forceinline__ void dev_associate_list(const Cfg& c, const WsLayout&
     int nres = 0, dropped = 0;
     for (int i = lane; i < L.M; i += 32) gidx[i] = -1.0;
     for (int k = lane; k < N; k += 32)
-        for (int j = 0; j < K; ++j) AOBS(j, k) = -1.0;
+        for (int j = 0; j < K; ++j) AOBS(j, k) = -1;
     __syncwarp();
     for (int k = 1; k <= N - 2 && K > 0; ++k)
     {
@@ -318,7 +318,7 @@ __device__ __forceinline__ void dev_associate_list(const Cfg& c, const WsLayout&
                 }
                 else ++dropped;
             }
-            if (lane == 0 && slot >= 0) AOBS(s_, k) = (double)slot;
+            if (lane == 0 && slot >= 0) AOBS(s_, k) = (signed char)slot;
         }
     }
     __syncwarp();

@@ -23,7 +23,7 @@ static inline void make_layout(const mpcb200_config* c, int M, int V, WsLayout& 
     L.oIN = take(IN_WORDS);
     L.oX = take(3 * N); L.oU = take(2 * N); L.oNU = take(3 * N);
     L.oS = take(L.RS * N); L.oLAM = take(L.RS * N);
-    L.oOBS = take((L.K > 0 ? L.K : 1) * N);
+    L.oOBS = take(((L.K > 0 ? L.K : 1) * N + 7) / 8);   // one byte per (row slot, stage)
     L.oVPST = take(V > 0 ? V : 1);
     L.oVP = take((V > 0 ? V : 1) * 3);
     L.oSTEP = take(8 * N);

@@ -32,7 +32,8 @@ struct ObstSrc
 #define ALAM(c_, k_) W[L.oLAM + (c_) * N + (k_)]
 #define AKKT(c_, k_) W[L.oKKT + (k_) * RSTR + (c_)]  /* stage records [k][RSTR] (odd stride: lane-per-stage accesses without bank conflicts) */
 #define ASTEP(c_, k_) W[L.oSTEP + (c_) * N + (k_)]
-#define AOBS(c_, k_) W[L.oOBS + (c_) * N + (k_)]
+// associated obstacle per row slot: one signed byte per (slot, stage) -- the RESIDENT slot of the obstacle, -1 = empty
+#define AOBS(c_, k_) ((signed char*)(W + L.oOBS))[(c_) * N + (k_)]
 #define ADS(c_, k_) W[L.oDS + (c_) * N + (k_)]
 // W addresses the instance image: the leading part of the workspace (scalars, inputs, iterate, steps, obstacles), which the
 // eval / line-search kernels stage in shared memory; G always addresses the instance's workspace in global memory (fields
@@ -860,7 +861,7 @@ HD inline void ls_stage_update(const Cfg& c, const WsLayout& L, const double* W,
     {
         bool act;
         if (sl < 8) act = lin_row_active(c, N, k, sl, uprev_dt) || (sl == BALL_SLOT && k == N - 1 && ball_active(c));
-        else act = (k >= 1 && k <= N - 2) && AOBS(sl - 8, k) >= 0.0;
+        else act = (k >= 1 && k <= N - 2) && AOBS(sl - 8, k) >= 0;
         if (!act) continue;
         const double s0 = AS(sl, k), ds = ADS(sl, k), lam0 = ALAM(sl, k);
         const double rs = 1.0 / s0;
@@ -1046,7 +1047,7 @@ HD inline double resample_serial(int n, const double* Xo, const double* Uo, doub
 HD inline void associate_stage(const Cfg& c, const WsLayout& L, double* W, int k)
 {
     const int N = L.N, K = L.K;
-    for (int j = 0; j < K; ++j) AOBS(j, k) = -1.0;
+    for (int j = 0; j < K; ++j) AOBS(j, k) = -1;
     if (k < 1 || k > N - 2 || K <= 0) return;
     const double px = AX(0, k), py = AX(1, k), pth = AX(2, k);
     const double ox = cos(pth), oy = sin(pth);
@@ -1083,13 +1084,13 @@ HD inline void associate_stage(const Cfg& c, const WsLayout& L, double* W, int k
             }
             else dist = pass == 1 ? left_min : right_min;
             // insert into the K-slot list (append; when full replace the farthest if nearer)
-            if (cnt < KK) { AOBS(cnt, k) = (double)j; dists[cnt] = dist; ++cnt; }
+            if (cnt < KK) { AOBS(cnt, k) = (signed char)j; dists[cnt] = dist; ++cnt; }
             else
             {
                 int far = 0;
                 for (int i = 1; i < KK; ++i)
                     if (dists[i] > dists[far]) far = i;
-                if (dist < dists[far]) { AOBS(far, k) = (double)j; dists[far] = dist; }
+                if (dist < dists[far]) { AOBS(far, k) = (signed char)j; dists[far] = dist; }
             }
         }
     }
@@ -1279,7 +1280,7 @@ HD inline void auto_mu_stage(const Cfg& c, const WsLayout& L, const double* W, d
     int m = 0;
     for (int sl = 0; sl < 8; ++sl) m += lin_row_active(c, N, k, sl, uprev_dt) || (sl == BALL_SLOT && k == N - 1 && ball_active(c));
     if (k >= 1 && k <= N - 2)
-        for (int j = 0; j < K; ++j) m += AOBS(j, k) >= 0.0;
+        for (int j = 0; j < K; ++j) m += AOBS(j, k) >= 0;
     *rows += (double)m;
 }
 HD inline double auto_mu(double obj, double rows)

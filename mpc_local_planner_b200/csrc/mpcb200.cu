@@ -37,6 +37,7 @@
 #define CNT_CYC 2          // +phase: SM cycles CTAs spent in each phase of the fused kernel (thread 0's clock64)
 #define CNT_CYC_TOTAL 7    // SM cycles CTAs spent on instances in the fused kernel
 #define CNT_INST 8         // instances solved by the fused kernel
+#define CNT_GATE 9         // SM cycles CTAs waited at the phase gates (MPCB200_OPT_SM_PHASE_SYNC)
 #define CNT_WORDS 16
 
 // ---- kernel: inputs of a batch into the instance blocks (phased path; the fused kernel scatters into shared memory itself) ----
@@ -179,7 +180,55 @@ struct FusedArgs
     int img_words;           // resident prefix
     int* queue;              // next instance
     unsigned long long* counters;
+    unsigned long long* sm_sync;   // [SMs] phase alignment words (nullptr: off)
+    int sm_gates;                  // 3: gates before eval, KKT and line search; 2: before KKT and line search only
 };
+// ---- phase alignment of the CTAs that share an SM ---------------------------------------------------------------------------
+// The solve kernel's iteration is ~128 KB of straight fp64 code, four times the SM's instruction cache (32 KB): CTAs that sit on
+// the same SM in different phases evict each other's code and every warp streams its instructions from the GPC-level cache
+// (ncu: 40 % of the instruction-cache requests miss, `no_instruction` is the first stall reason).  The co-resident CTAs therefore
+// enter each phase of the iteration together: one word per SM in global memory -- generation | arrived | members -- is a barrier
+// with changing membership (a CTA is a member while it iterates, not while it sets up or writes back an instance).
+// The generation counts barriers; generation mod 3 is the phase the barrier opens (eval, KKT, line search): a CTA that arrives
+// out of step keeps arriving (and idles) until the generation matches its phase.  Timing only -- no data crosses CTAs.
+__device__ __forceinline__ unsigned sm_index() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define SMS_MEMBERS(w_) ((unsigned)((w_) & 0xFFFFull))
+#define SMS_ARRIVED(w_) ((unsigned)(((w_) >> 16) & 0xFFFFull))
+#define SMS_GEN(w_) ((unsigned)((w_) >> 32))
+#define SMS_PACK(g_, a_, m_) (((unsigned long long)(g_) << 32) | ((unsigned long long)(a_) << 16) | (unsigned long long)(m_))
+__device__ __forceinline__ void sms_join(unsigned long long* st) { atomicAdd(st, 1ull); }
+__device__ __forceinline__ void sms_leave(unsigned long long* st)
+{
+    unsigned long long old = *(volatile unsigned long long*)st, assumed;
+    do
+    {
+        assumed = old;
+        unsigned m = SMS_MEMBERS(assumed) - 1u, ar = SMS_ARRIVED(assumed), g = SMS_GEN(assumed);
+        if (ar > 0u && ar >= m) { ar = 0u; ++g; }   // the others were waiting for this CTA only
+        old = atomicCAS(st, assumed, SMS_PACK(g, ar, m));
+    } while (old != assumed);
+}
+__device__ __forceinline__ void sms_arrive(unsigned long long* st, unsigned phase, unsigned nph)
+{
+    for (;;)
+    {
+        unsigned long long old = *(volatile unsigned long long*)st, assumed;
+        unsigned g;
+        bool released;
+        do
+        {
+            assumed = old;
+            unsigned m = SMS_MEMBERS(assumed), ar = SMS_ARRIVED(assumed) + 1u;
+            g = SMS_GEN(assumed);
+            released = ar >= m;
+            old = atomicCAS(st, assumed, released ? SMS_PACK(g + 1u, 0u, m) : SMS_PACK(g, ar, m));
+        } while (old != assumed);
+        if (!released)
+            while (SMS_GEN(*(volatile unsigned long long*)st) == g) __nanosleep(32);
+        if (g % nph == phase) return;
+    }
+}
+
 template <bool LINES, bool EXT>
 __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, const __grid_constant__ FusedArgs a)
 {
@@ -197,6 +246,9 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
     __syncthreads();
     uint32_t parity = 0;
     unsigned long long cyc[MPCB200_NUM_PHASES] = {0, 0, 0, 0, 0}, cyc_total = 0, n_kkt = 0, n_sweeps = 0, n_inst = 0;
+    const unsigned nph = (unsigned)a.sm_gates;
+    unsigned long long gate_cyc = 0;   // waiting at the phase gates (included in the phase that follows the gate)
+    unsigned long long* sms = a.sm_sync ? a.sm_sync + sm_index() : nullptr;
     const int outer = c.outer_iterations > 0 ? c.outer_iterations : 1;
 #define TICK(p_) do { if (tid == 0) { const long long t_ = clock64(); cyc[p_] += (unsigned long long)(t_ - t_mark); t_mark = t_; } } while (0)
     for (;;)
@@ -237,20 +289,27 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
                 }
                 __syncthreads();
                 TICK(MPCB200_PHASE_ASSOCIATE);
+                if (sms && tid == 0) sms_join(sms);
+#define PHASE_GATE(p_) do { if (sms) { if (tid == 0) { const long long g0_ = clock64(); sms_arrive(sms, p_, nph); gate_cyc += (unsigned long long)(clock64() - g0_); } __syncthreads(); } } while (0)
                 for (;;)
                 {
+                    if (nph == 3u) PHASE_GATE(0u);
                     const int fin = dev_eval<LINES>(c, L, W, a.uprev_dt, sh, tid, nt);
                     TICK(MPCB200_PHASE_EVAL);
                     if (fin) break;
+                    PHASE_GATE(nph - 2u);
                     if (wid == 0) dev_kkt<EXT>(c, L, W, ex, &n_sweeps);
                     __syncthreads();
                     TICK(MPCB200_PHASE_KKT);
                     if (tid == 0) ++n_kkt;
                     if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // inertia correction failed: given up
+                    PHASE_GATE(nph - 1u);
                     dev_linesearch<LINES>(c, L, W, a.uprev_dt, sh, tid, nt);
                     TICK(MPCB200_PHASE_LINESEARCH);
                     if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // jammed: given up
                 }
+#undef PHASE_GATE
+                if (sms && tid == 0) sms_leave(sms);
             }
             // a failed solve leaves nothing to warm-start from
             if (tid == 0 && ASC(MPCB200_SC_STATUS) == (double)MPCB200_STATUS_NUMERICAL_ERROR) ASC(MPCB200_SC_COLD) = 1.0;
@@ -265,6 +324,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
     if (tid == 0 && a.counters)
     {
         for (int p = 0; p < MPCB200_NUM_PHASES; ++p) atomicAdd(a.counters + CNT_CYC + p, cyc[p]);
+        atomicAdd(a.counters + CNT_GATE, gate_cyc);
         atomicAdd(a.counters + CNT_CYC_TOTAL, cyc_total);
         atomicAdd(a.counters + CNT_KKT_INST, n_kkt);
         atomicAdd(a.counters + CNT_KKT_SWEEPS, n_sweeps);
@@ -360,6 +420,8 @@ struct mpcb200_handle
     int has_lines;  // line obstacles in the batch, moving obstacles or midpoint differences: the kernels are launched with those (rarely used) paths compiled in
     double uprev_dt;
     int fused_grid;  // CTAs of the last fused launch
+    int sm_phase_sync;    // MPCB200_OPT_SM_PHASE_SYNC: co-resident CTAs of the solve kernel enter the phases together
+    unsigned long long* d_smsync;
     int max_ctas_per_sm;  // MPCB200_OPT_CTAS_PER_SM: cap on the resident CTAs per SM of the solve kernel (0 = what fits)
     mpcb200_stats stats;
     std::vector<cudaEvent_t> ev;  // pool of event pairs
@@ -462,7 +524,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
     h->n_cap = cfg->n; h->d_resample = nullptr; h->d_cm = nullptr; h->cm_cap = 0; h->costmap_ms = 0.0; h->d_fz = nullptr; h->fz_cap = 0;
     h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0; h->has_lines = 0;
-    h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0; h->max_ctas_per_sm = 0;
+    h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0; h->max_ctas_per_sm = 0; h->sm_phase_sync = -1; h->d_smsync = nullptr;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
         cudaError_t e_ = (call);                                                                                   \
@@ -484,7 +546,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_xinit, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_reinit, B));
     CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
     CKC(cudaMalloc(&h->d_kkt, B * 8)); CKC(cudaMalloc(&h->d_upacked, B * (N - 1) * 2 * 8));
-    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8)); CKC(cudaMalloc(&h->d_queue, 4));
+    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8)); CKC(cudaMalloc(&h->d_queue, 4)); CKC(cudaMalloc(&h->d_smsync, 1024 * 8));
     CKC(cudaMalloc(&h->d_counters, CNT_WORDS * 8)); CKC(cudaMemsetAsync(h->d_counters, 0, CNT_WORDS * 8, h->stream));
     CKC(allow_smem(phase_kernel<false>)); CKC(allow_smem(phase_kernel<true>));
     CKC(allow_smem(kkt_warp_kernel<false>)); CKC(allow_smem(kkt_warp_kernel<true>));
@@ -515,7 +577,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->ws, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
-                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_queue, h->d_flush, h->d_counters};
+                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_queue, h->d_flush, h->d_counters, h->d_smsync};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* sptrs[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
                      h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_resample, h->d_cm, h->d_fz};
@@ -716,6 +778,7 @@ static int launch_fused(mpcb200_handle* h, int total, int queue_mode, int force_
     FusedArgs a;
     a.ws = h->ws; a.in = in; a.out = out; a.total = total; a.queue_mode = queue_mode; a.force_cold = force_cold; a.uprev_dt = h->uprev_dt;
     a.img_words = image_words(h); a.queue = h->d_queue; a.counters = h->d_counters;
+    a.sm_sync = nullptr; a.sm_gates = h->sm_phase_sync == 2 ? 2 : 3;
     const size_t smem = IMG_HEAD + (size_t)a.img_words * 8;
     if (smem > MAX_IMG_SMEM) return set_err(h, MPCB200_E_UNSUPPORTED, "the instance does not fit in shared memory");
     const int threads = group_threads(h);
@@ -728,6 +791,12 @@ static int launch_fused(mpcb200_handle* h, int total, int queue_mode, int force_
         if (h->max_ctas_per_sm > 0 && per_sm > h->max_ctas_per_sm) per_sm = h->max_ctas_per_sm;                                \
         const int grid = total < per_sm * h->num_sms ? total : per_sm * h->num_sms;                                            \
         h->fused_grid = grid;                                                                                                  \
+        /* phase alignment pays when several CTAs share an SM (auto: from three; measured, profiles/r2_phase_alignment.txt) */  \
+        if (h->sm_phase_sync > 0 || (h->sm_phase_sync < 0 && per_sm >= 3 && grid > h->num_sms))                                \
+        {                                                                                                                      \
+            a.sm_sync = h->d_smsync;                                                                                           \
+            CK(cudaMemsetAsync(h->d_smsync, 0, 1024 * 8, h->stream));                                                          \
+        }                                                                                                                      \
         CK(cudaMemsetAsync(h->d_queue, 0, 4, h->stream));                                                                      \
         solve_fused_kernel<LN, EX><<<grid, threads, smem, h->stream>>>(h->cfg, h->L, a);                                       \
     } while (0)
@@ -791,6 +860,7 @@ static int collect_fused_counters(mpcb200_handle* h)
     CK(cudaMemcpy(cnt, h->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
     const double per_cta = h->fused_grid > 0 ? 1.0 / ((double)h->fused_grid * (double)h->clock_khz) : 0.0;  // cycles -> ms per CTA
     for (int p = 0; p < MPCB200_NUM_PHASES; ++p) h->stats.ms[p] += (double)cnt[CNT_CYC + p] * per_cta;
+    h->stats.gate_ms += (double)cnt[CNT_GATE] * per_cta;
     h->stats.kkt_instances += (long long)cnt[CNT_KKT_INST];
     h->stats.kkt_sweeps += (long long)cnt[CNT_KKT_SWEEPS];
     h->stats.launches[MPCB200_PHASE_KKT] += (long long)cnt[CNT_KKT_INST];
@@ -1025,6 +1095,15 @@ extern "C" int mpcb200_ws_read(mpcb200_handle* h, int field, int B, double* dst)
                 for (int f = 0; f < KW; ++f) dst[((size_t)b * KW + f) * N + k] = tmp[((size_t)b * N + k) * RSTR + f];
         return 0;
     }
+    if (field == MPCB200_F_OBSIDX)
+    {   // device layout: one signed byte per (slot, stage); the API presents doubles [B][K][N]
+        const size_t nb = (size_t)cnt * N;
+        std::vector<signed char> tmp((size_t)B * nb);
+        CK(cudaMemcpy2DAsync(tmp.data(), nb, h->ws + off, (size_t)h->L.stride * 8, nb, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (size_t i = 0; i < tmp.size(); ++i) dst[i] = (double)tmp[i];
+        return 0;
+    }
     const size_t words = (field == MPCB200_F_SCAL || field == MPCB200_F_OBSGIDX) ? (size_t)cnt : (size_t)cnt * N;
     CK(cudaMemcpy2DAsync(dst, words * 8, h->ws + off, (size_t)h->L.stride * 8, words * 8, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1045,6 +1124,15 @@ extern "C" int mpcb200_ws_write(mpcb200_handle* h, int field, int B, const doubl
             for (int k = 0; k < N; ++k)
                 for (int f = 0; f < KW; ++f) tmp[((size_t)b * N + k) * RSTR + f] = src[((size_t)b * KW + f) * N + k];
         CK(cudaMemcpy2DAsync(h->ws + off, (size_t)h->L.stride * 8, tmp.data(), (size_t)N * RSTR * 8, (size_t)N * RSTR * 8, (size_t)B, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (field == MPCB200_F_OBSIDX)
+    {
+        const size_t nb = (size_t)cnt * N;
+        std::vector<signed char> tmp((size_t)B * nb);
+        for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = (signed char)src[i];
+        CK(cudaMemcpy2DAsync(h->ws + off, (size_t)h->L.stride * 8, tmp.data(), nb, nb, (size_t)B, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return 0;
     }
@@ -1079,6 +1167,7 @@ extern "C" int mpcb200_set_option(mpcb200_handle* h, int option, int value)
     if (!h) return MPCB200_E_INVALID;
     if (option == MPCB200_OPT_SOLVE_MODE && value >= 0 && value <= 1) { h->solve_mode = value; return 0; }
     if (option == MPCB200_OPT_CTAS_PER_SM && value >= 0 && value <= 32) { h->max_ctas_per_sm = value; return 0; }
+    if (option == MPCB200_OPT_SM_PHASE_SYNC && value >= -1 && value <= 2) { h->sm_phase_sync = value; return 0; }
     return set_err(h, MPCB200_E_INVALID, "unknown option or value");
 }
 

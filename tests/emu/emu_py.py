@@ -89,6 +89,8 @@ class EmuInstance:
         if f == capi.F_KKT:  # stage records [k][43] (42 words + a zero word); present [42][N] (copy)
             idx = off + np.arange(self.N)[None, :] * 43 + np.arange(cnt.value)[:, None]
             return self.W[idx]
+        if f == capi.F_OBSIDX:  # one signed byte per (slot, stage)
+            return self.W[off:].view(np.int8)[: cnt.value * self.N].reshape(cnt.value, self.N).astype(np.float64)
         return self.W[off: off + cnt.value * self.N].reshape(cnt.value, self.N)
 
     def init(self, force_cold=False):
