@@ -436,7 +436,21 @@ def main():
                                      "ms_per_step": el4 / 3 * 1e3, "scaling": "strong", "converged_fraction": conv4 / 16384.0,
                                      "workload": WORKLOADS[4][2]}
         if world == 1 and cid == 2:
-            # (c) BASELINE configs[2] and the horizon sweep of configs[4], one GPU
+            # (c) the cold start exactly as the reference builds it (config.reference_initial_guess = 1: straight line, zero
+            #     controls, no solver-side preprocessing), same instances: how many converge within the 100 iterations, how fast
+            try:
+                cr = configs.config_for(2, tol=1e-6)
+                cr.reference_initial_guess = 1
+                mr = measure(2, cr, B, 5, 3, 0, False, False)
+                extra["reference_initial_guess"] = {"value": mr["conv"] * 5 / mr["el"], "unit": UNIT, "ms_per_step": mr["el"] / 5 * 1e3,
+                                                    "converged_fraction": mr["conv"] / float(B), "mean_ipm_iterations": mr["iters_mean"],
+                                                    "what": "config.reference_initial_guess = 1 (the reference's initial guess, "
+                                                            "full_discretization_grid_base_se2.cpp:192-239); the headline uses the default 0 "
+                                                            "(bumped-line choice + repair of violated obstacle rows, DESIGN.md)"}
+                mr["solver"].close()
+            except Exception as e:
+                extra["reference_guess_error"] = repr(e)
+            # (d) BASELINE configs[2] and the horizon sweep of configs[4], one GPU
             try:
                 c3 = configs.config_for(3, tol=1e-6)
                 m3 = measure(3, c3, 4096, 3, 3, 0, False, False)
@@ -480,7 +494,9 @@ def main():
                    "parallelism": f"instances sharded over {world} GPU(s), NCCL all-gather of u* (step i) beside the solve of step i+1" if world > 1 else "1 GPU",
                    "l2": "flushed between steps (a batch's working set fits in the 126 MB L2)",
                    "converged_fraction": conv_total / float(B * world), "mean_ipm_iterations": m["iters_mean"],
-                   "solve": "one persistent kernel per step: a CTA owns an instance from the initial guess to convergence"},
+                   "solve": "one persistent kernel per step: a CTA owns an instance from the initial guess to convergence; the CTAs "
+                            "sharing an SM enter the phases of an iteration together (instruction-cache locality)",
+                   "gate_wait_ms_per_cta": m["stats"]["gate_ms"] / max(1, args.steps)},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"])},
         "gpu_launches": int(st["launches_total"]),
