@@ -52,6 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
+    __syncwarp();   // lanes may leave the spin in different turns: converge before any warp collective that follows
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
@@ -184,6 +185,7 @@ __device__ __forceinline__ void gather_one(const WsLayout& L, const double* W, c
 __device__ __forceinline__ void dev_init(const Cfg& c, const WsLayout& L, double* W, const ObstSrc& os, const double* xinit, int force_cold, int lane)
 {
     const int N = L.N;
+    __syncwarp();   // (see dev_kkt)
     const bool cold = force_cold || ASC(MPCB200_SC_COLD) != 0.0 || AIN(IN_REINIT) != 0.0;
     __syncwarp();
     if (cold)
@@ -466,6 +468,7 @@ __device__ __forceinline__ int dev_eval(const Cfg& c, const WsLayout& L, double*
     EvalAcc a;
     evalacc_init(a);
     for (int k = tid; k < N; k += nt) eval_stage<LINES>(c, L, W, W, uprev_dt, k, a);
+    __syncwarp();
     evalacc_warp_reduce(a);
     if (lane == 0) sh.eacc[wid] = a;
     __syncthreads();
@@ -488,6 +491,7 @@ __device__ __forceinline__ int dev_eval(const Cfg& c, const WsLayout& L, double*
 template <bool EXT>
 __device__ __forceinline__ void dev_kkt(const Cfg& c, const WsLayout& L, double* W, CudaWarp<EXT>& ex, unsigned long long* sweeps)
 {
+    __syncwarp();   // the warp enters its collectives converged, whatever thread-0-only code ran before
     double ddt = 0.0, delta = 0.0;
     int nreg = 0;
     const int ok = kkt_warp_solve<EXT>(ex, c, L.N, W + L.oKKT, W + L.oMM, W + L.oSTEP, ASC(MPCB200_SC_HTT), ASC(MPCB200_SC_GT), ASC(MPCB200_SC_DELTA_LAST),
@@ -524,6 +528,7 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
     __syncthreads();
     const int jt = clip_threshold_bin(sh.hist, sh.hist[CLIP_BINS]);  // same value in every thread
     for (int k = tid; k < N; k += nt) a.a_p = fmin(a.a_p, ls_stage_ap(L, W, k, jt));
+    __syncwarp();
     a.a_p = warp_min(a.a_p); a.a_d = warp_min(a.a_d);
     a.dphi_bar = warp_sum(a.dphi_bar); a.curv = warp_sum(a.curv); a.dJ = warp_sum(a.dJ);
     if (lane == 0) sh.lacc[wid] = a;
@@ -560,6 +565,7 @@ __device__ __forceinline__ void dev_linesearch(const Cfg& c, const WsLayout& L, 
         TrialAcc t;
         t.obj = t.inf1 = t.blog = 0.0;
         for (int k = tid; k < N; k += nt) ls_stage_trial<LINES>(c, L, W, W, uprev_dt, k, alpha, t);
+        __syncwarp();
         t.obj = warp_sum(t.obj); t.inf1 = warp_sum(t.inf1); t.blog = warp_sum(t.blog);
         if (lane == 0) sh.tr[wid] = t;
         __syncthreads();

@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
     unsigned long long gate_cyc = 0;   // waiting at the phase gates (included in the phase that follows the gate)
     unsigned long long* sms = a.sm_sync ? a.sm_sync + sm_index() : nullptr;
     const int outer = c.outer_iterations > 0 ? c.outer_iterations : 1;
-#define TICK(p_) do { if (tid == 0) { const long long t_ = clock64(); cyc[p_] += (unsigned long long)(t_ - t_mark); t_mark = t_; } } while (0)
+// Phase clocks: EVERY thread keeps them (thread 0's are reported).  Not `if (tid == 0)`: a thread-0-only block directly in front of
+// warp-collective code (shuffles, votes) made the compiler split the paths of thread 0 and of lanes 1..31 through the KKT phase in
+// one build variant -- lanes 1..31 ran their shuffles on the converged fast path, thread 0 waited in the collective slow path for
+// ever (found with cuda-gdb, profiles/r2_phase_alignment.txt).  Branch-free bookkeeping leaves nothing to split.
+#define TICK(p_) do { const long long t_ = clock64(); cyc[p_] += (unsigned long long)(t_ - t_mark); t_mark = t_; } while (0)
     for (;;)
     {
         if (tid == 0) s_inst = atomicAdd(a.queue, 1);
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
                 }
                 __syncthreads();
                 TICK(MPCB200_PHASE_ASSOCIATE);
-                if (sms && tid == 0) sms_join(sms);
+                if (sms) { if (tid == 0) sms_join(sms); __syncthreads(); }
 #define PHASE_GATE(p_) do { if (sms) { if (tid == 0) { const long long g0_ = clock64(); sms_arrive(sms, p_, nph); gate_cyc += (unsigned long long)(clock64() - g0_); } __syncthreads(); } } while (0)
                 for (;;)
                 {
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
                     if (wid == 0) dev_kkt<EXT>(c, L, W, ex, &n_sweeps);
                     __syncthreads();
                     TICK(MPCB200_PHASE_KKT);
-                    if (tid == 0) ++n_kkt;
+                    ++n_kkt;
                     if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // inertia correction failed: given up
                     PHASE_GATE(nph - 1u);
                     dev_linesearch<LINES>(c, L, W, a.uprev_dt, sh, tid, nt);
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
                     if (ASC(MPCB200_SC_STATUS) >= 0.0) break;   // jammed: given up
                 }
 #undef PHASE_GATE
-                if (sms && tid == 0) sms_leave(sms);
+                if (sms) { if (tid == 0) sms_leave(sms); __syncthreads(); }
             }
             // a failed solve leaves nothing to warm-start from
             if (tid == 0 && ASC(MPCB200_SC_STATUS) == (double)MPCB200_STATUS_NUMERICAL_ERROR) ASC(MPCB200_SC_COLD) = 1.0;
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
         gather_one(L, W, a.out, inst, tid, nt);
         if (!a.queue_mode) stage_out(Gp, W, L.oSTATE_END, tid);   // state (and what the kernel-level API reads back)
         else __syncthreads();
-        if (tid == 0) { cyc_total += (unsigned long long)(clock64() - t_begin); ++n_inst; }
+        cyc_total += (unsigned long long)(clock64() - t_begin); ++n_inst;
     }
 #undef TICK
     if (tid == 0 && a.counters)
