@@ -191,6 +191,7 @@ struct FusedArgs
 // with changing membership (a CTA is a member while it iterates, not while it sets up or writes back an instance).
 // The generation counts barriers; generation mod 3 is the phase the barrier opens (eval, KKT, line search): a CTA that arrives
 // out of step keeps arriving (and idles) until the generation matches its phase.  Timing only -- no data crosses CTAs.
+#define SMS_POLL_NS 128   // pause between two polls of the barrier word (the polling thread shares its scheduler with working warps)
 __device__ __forceinline__ unsigned sm_index() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #define SMS_MEMBERS(w_) ((unsigned)((w_) & 0xFFFFull))
 #define SMS_ARRIVED(w_) ((unsigned)(((w_) >> 16) & 0xFFFFull))
@@ -224,7 +225,7 @@ __device__ __forceinline__ void sms_arrive(unsigned long long* st, unsigned phas
             old = atomicCAS(st, assumed, released ? SMS_PACK(g + 1u, 0u, m) : SMS_PACK(g, ar, m));
         } while (old != assumed);
         if (!released)
-            while (SMS_GEN(*(volatile unsigned long long*)st) == g) __nanosleep(32);
+            while (SMS_GEN(*(volatile unsigned long long*)st) == g) __nanosleep(SMS_POLL_NS);
         if (g % nph == phase) return;
     }
 }
