@@ -599,8 +599,9 @@ HD inline void ls_stage_steps(const Cfg& c, const WsLayout& L, double* W, double
         ADS(sl, k) = ds;
         GR0(sl, k) = r0;
         HIST_ADD(hist + CLIP_BINS);
-        if (ds < 0 && -tau * s / ds < 1.0) HIST_ADD(hist + clip_bin(-tau * s / ds));
-        if (dl < 0) acc.a_d = fmin(acc.a_d, -tau * lam / dl);
+        // (cross-multiplied tests first: the fp64 divisions are paid by the blocking rows only)
+        if (ds < 0 && tau * s < -ds) { const double r = -tau * s / ds; if (r < 1.0) HIST_ADD(hist + clip_bin(r)); }
+        if (dl < 0 && tau * lam < -dl * acc.a_d) acc.a_d = fmin(acc.a_d, -tau * lam / dl);
         acc.dphi_bar += -mu * ds * rs;
         acc.curv += (lam * rs) * ds * ds;
     }
@@ -687,7 +688,9 @@ HD inline double ls_stage_ap(const WsLayout& L, const double* W, int k, int jt, 
     {
         const double ds = ADS(sl, k);  // 0 for inactive rows
         if (!(ds < 0)) continue;
-        const double r = -tau * AS(sl, k) / ds;
+        const double s0 = AS(sl, k);
+        if (!(tau * s0 < -ds * a_p)) continue;   // r >= a_p: not blocking (decided without the division)
+        const double r = -tau * s0 / ds;
         if (r < a_p && clip_bin(r) < jt) a_p = r;
     }
     return a_p;
