@@ -258,11 +258,12 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t.numpy(), t
 
-    def measure(cid_, cfg_, B_, steps, warmup, first, want_e2e, want_gather):
+    def measure(cid_, cfg_, B_, steps, warmup, first, want_e2e, want_gather, order_by_history=1):
         """K timed cold batch solves of one workload on this rank.  Returns a dict of local results."""
         data = configs.generate(cid_, B_, first=first, n=cfg_.n if cid_ == 5 else None)
         solver = capi.BatchSolver(cfg_, B_, device=dev)
         solver.set_stream(stream.cuda_stream)
+        solver.set_option(capi.OPT_ORDER_BY_HISTORY, order_by_history)
         N = cfg_.n
         send = torch.empty(B_ * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}")
         recv = torch.empty(world * B_ * (N - 1) * 2, dtype=torch.float64, device=f"cuda:{dev}") if (world > 1 and want_gather) else None
@@ -450,6 +451,16 @@ def main():
                 mr["solver"].close()
             except Exception as e:
                 extra["reference_guess_error"] = repr(e)
+            # (c2) the headline workload with the queue in index order (MPCB200_OPT_ORDER_BY_HISTORY = 0): every step of this bench solves
+            #      the SAME instances, so the default order -- longest first by the previous solve's iteration counts of the same slots --
+            #      is an exact hint here; in a fleet it is as good as a robot's difficulty persists from cycle to cycle
+            try:
+                mo = measure(2, configs.config_for(2, tol=1e-6), B, 10, 3, 0, False, False, order_by_history=0)
+                extra["index_order"] = {"value": mo["conv"] * 10 / mo["el"], "unit": UNIT, "ms_per_step": mo["el"] / 10 * 1e3,
+                                        "what": "same workload, queue in index order (no history)"}
+                mo["solver"].close()
+            except Exception as e:
+                extra["index_order_error"] = repr(e)
             # (d) BASELINE configs[2] and the horizon sweep of configs[4], one GPU
             try:
                 c3 = configs.config_for(3, tol=1e-6)
@@ -496,7 +507,9 @@ def main():
                    "converged_fraction": conv_total / float(B * world), "mean_ipm_iterations": m["iters_mean"],
                    "solve": "one persistent kernel per step: a CTA owns an instance from the initial guess to convergence; the CTAs "
                             "sharing an SM enter the phases of an iteration together (instruction-cache locality)",
-                   "gate_wait_ms_per_cta": m["stats"]["gate_ms"] / max(1, args.steps)},
+                   "gate_wait_ms_per_cta": m["stats"]["gate_ms"] / max(1, args.steps),
+                   "queue_order": "longest first by the iteration counts the same slots needed in the previous step (every step of the bench "
+                                  "solves the same instances: an exact hint; the warm-up steps build it); configs.index_order = without"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"])},
         "gpu_launches": int(st["launches_total"]),

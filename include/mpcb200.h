@@ -421,6 +421,10 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
    (instruction-cache locality; timing only).  -1 (default) = on when three or more CTAs fit on an SM, 0 = off, 1 = on with
    gates before evaluation, KKT and line search, 2 = on with gates before KKT and line search only. */
 #define MPCB200_OPT_SM_PHASE_SYNC 5
+/* MPCB200_OPT_ORDER_BY_HISTORY: 1 (default) = a batch solve takes its instances longest-first by the iteration counts the same
+   slots needed in the previous batch solve of this handle (a batch costs its slowest instance; a robot that was hard in the last
+   cycle tends to be hard in this one).  Order of execution only; 0 = index order. */
+#define MPCB200_OPT_ORDER_BY_HISTORY 6
 int mpcb200_set_option(mpcb200_handle* h, int option, int value);
 
 /* Counters accumulated since the last mpcb200_stats_reset: kernels launched, device ms per phase. */

@@ -32,6 +32,7 @@ PHASE_INIT, PHASE_ASSOCIATE, PHASE_EVAL, PHASE_KKT, PHASE_LINESEARCH = range(5)
 OPT_SOLVE_MODE = 3
 OPT_CTAS_PER_SM = 4
 OPT_SM_PHASE_SYNC = 5
+OPT_ORDER_BY_HISTORY = 6
 SOLVE_FUSED, SOLVE_PHASED = 0, 1
 NUM_PHASES = 5
 K_H, K_G, K_A, K_B, K_E, K_C, K_HB, K_D = 0, 15, 20, 23, 29, 32, 34, 39

@@ -179,6 +179,7 @@ struct FusedArgs
     double uprev_dt;
     int img_words;           // resident prefix
     int* queue;              // next instance
+    const int* order;        // queue position -> instance (nullptr: identity)
     unsigned long long* counters;
     unsigned long long* sm_sync;   // [SMs] phase alignment words (nullptr: off)
     int sm_gates;                  // 3: gates before eval, KKT and line search; 2: before KKT and line search only
@@ -230,6 +231,45 @@ __device__ __forceinline__ void sms_arrive(unsigned long long* st, unsigned phas
     }
 }
 
+// ---- kernel: queue order of a batch = longest first by the iteration counts of the PREVIOUS solve of the same slots ----
+// A batch costs its slowest instance: an instance that needs 100 iterations and is taken from the queue when the first slots free
+// up (2-3 ms into the step) ends 2-3 ms later than if it had been among the first.  Nothing predicts the iteration count of a cold
+// instance from its geometry (correlations < 0.2 on the BASELINE instances), but a robot that was hard in the last cycle tends to be
+// hard in this one, so the history is the hint.  Counting sort (descending, stable) by min(iters, 1023) in one CTA.
+__global__ void __launch_bounds__(1024) order_by_history_kernel(const int* __restrict__ prev_iters, int B, int* __restrict__ order)
+{
+    __shared__ int hist[1024];
+    __shared__ int warp_tot[32];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    hist[t] = 0;
+    __syncthreads();
+    for (int i = t; i < B; i += 1024) { int k = prev_iters[i]; k = k < 0 ? 0 : (k > 1023 ? 1023 : k); atomicAdd(&hist[1023 - k], 1); }
+    __syncthreads();
+    // exclusive scan of hist (bucket 0 = the longest)
+    const int v = hist[t];
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += warp_tot[w];
+    __syncthreads();
+    hist[t] = woff + incl - v;   // first position of bucket t
+    __syncthreads();
+    // stable placement: the thread that owns a bucket walks the instances in index order (buckets are few and short in practice;
+    // the walk is B loads per non-empty bucket owner -- done by the warps in parallel over the buckets)
+    if (v > 0)
+    {
+        int pos = hist[t];
+        const int key = 1023 - t;
+        for (int i = 0; i < B; ++i)
+        {
+            int k = prev_iters[i]; k = k < 0 ? 0 : (k > 1023 ? 1023 : k);
+            if (k == key) order[pos++] = i;
+        }
+    }
+}
+
 template <bool LINES, bool EXT>
 __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(const __grid_constant__ Cfg c, const __grid_constant__ WsLayout L, const __grid_constant__ FusedArgs a)
 {
@@ -258,7 +298,7 @@ __global__ void __launch_bounds__(MAX_GROUP_WARPS * 32, 3) solve_fused_kernel(co
 #define TICK(p_) do { const long long t_ = clock64(); cyc[p_] += (unsigned long long)(t_ - t_mark); t_mark = t_; } while (0)
     for (;;)
     {
-        if (tid == 0) s_inst = atomicAdd(a.queue, 1);
+        if (tid == 0) { const int q = atomicAdd(a.queue, 1); s_inst = (q < a.total && a.order) ? a.order[q] : q; }
         __syncthreads();
         const int inst = s_inst;
         if (inst >= a.total) break;
@@ -425,6 +465,9 @@ struct mpcb200_handle
     int has_lines;  // line obstacles in the batch, moving obstacles or midpoint differences: the kernels are launched with those (rarely used) paths compiled in
     double uprev_dt;
     int fused_grid;  // CTAs of the last fused launch
+    int order_by_history; // MPCB200_OPT_ORDER_BY_HISTORY: batch queue longest-first by the previous solve's iteration counts
+    int hist_B;           // batch size of the last batch solve whose iteration counts are in d_iters (0: none)
+    int *d_prev_iters, *d_order;
     int sm_phase_sync;    // MPCB200_OPT_SM_PHASE_SYNC: co-resident CTAs of the solve kernel enter the phases together
     unsigned long long* d_smsync;
     int max_ctas_per_sm;  // MPCB200_OPT_CTAS_PER_SM: cap on the resident CTAs per SM of the solve kernel (0 = what fits)
@@ -529,7 +572,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     make_layout(cfg, MAX_OBST, MAX_VP, h->L);
     h->n_cap = cfg->n; h->d_resample = nullptr; h->d_cm = nullptr; h->cm_cap = 0; h->costmap_ms = 0.0; h->d_fz = nullptr; h->fz_cap = 0;
     h->uprev_dt = 0.0; h->has_obst = h->has_vp = h->has_xinit = h->has_reinit = 0; h->obst_max = h->vp_max = 0; h->has_lines = 0;
-    h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0; h->max_ctas_per_sm = 0; h->sm_phase_sync = -1; h->d_smsync = nullptr;
+    h->solve_mode = 0; h->timing_mask = 1u << MPCB200_PHASE_KKT; h->fused_grid = 0; h->max_ctas_per_sm = 0; h->sm_phase_sync = -1; h->d_smsync = nullptr; h->order_by_history = 1; h->hist_B = 0; h->d_prev_iters = h->d_order = nullptr;
 #define CKC(call)                                                                                                  \
     do {                                                                                                           \
         cudaError_t e_ = (call);                                                                                   \
@@ -551,7 +594,7 @@ extern "C" int mpcb200_create(const mpcb200_config* cfg, int max_batch, int devi
     CKC(cudaMalloc(&h->d_xinit, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_reinit, B));
     CKC(cudaMalloc(&h->d_useq, B * N * 2 * 8)); CKC(cudaMalloc(&h->d_xseq, B * N * 3 * 8)); CKC(cudaMalloc(&h->d_dt, B * 8));
     CKC(cudaMalloc(&h->d_kkt, B * 8)); CKC(cudaMalloc(&h->d_upacked, B * (N - 1) * 2 * 8));
-    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8)); CKC(cudaMalloc(&h->d_queue, 4)); CKC(cudaMalloc(&h->d_smsync, 1024 * 8));
+    CKC(cudaMalloc(&h->d_status, B * 4)); CKC(cudaMalloc(&h->d_iters, B * 4)); CKC(cudaMalloc(&h->d_nactive, 8)); CKC(cudaMalloc(&h->d_queue, 4)); CKC(cudaMalloc(&h->d_smsync, 1024 * 8)); CKC(cudaMalloc(&h->d_prev_iters, B * 4)); CKC(cudaMalloc(&h->d_order, B * 4));
     CKC(cudaMalloc(&h->d_counters, CNT_WORDS * 8)); CKC(cudaMemsetAsync(h->d_counters, 0, CNT_WORDS * 8, h->stream));
     CKC(allow_smem(phase_kernel<false>)); CKC(allow_smem(phase_kernel<true>));
     CKC(allow_smem(kkt_warp_kernel<false>)); CKC(allow_smem(kkt_warp_kernel<true>));
@@ -582,7 +625,7 @@ extern "C" void mpcb200_destroy(mpcb200_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->ws, h->d_x0, h->d_xf, h->d_uprev, h->d_obst, h->d_obst_count, h->d_obst_type, h->d_vp, h->d_vp_count, h->d_xinit,
-                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_queue, h->d_flush, h->d_counters, h->d_smsync};
+                    h->d_reinit, h->d_useq, h->d_xseq, h->d_dt, h->d_kkt, h->d_upacked, h->d_status, h->d_iters, h->d_nactive, h->d_queue, h->d_flush, h->d_counters, h->d_smsync, h->d_prev_iters, h->d_order};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* sptrs[] = {h->s_x0, h->s_xf, h->s_uprev, h->s_obst, h->s_vp, h->s_useq, h->s_xseq, h->s_dt, h->s_kkt, h->s_upacked, h->s_obst_count,
                      h->s_obst_type, h->s_vp_count, h->s_status, h->s_iters, h->d_resample, h->d_cm, h->d_fz};
@@ -784,6 +827,16 @@ static int launch_fused(mpcb200_handle* h, int total, int queue_mode, int force_
     a.ws = h->ws; a.in = in; a.out = out; a.total = total; a.queue_mode = queue_mode; a.force_cold = force_cold; a.uprev_dt = h->uprev_dt;
     a.img_words = image_words(h); a.queue = h->d_queue; a.counters = h->d_counters;
     a.sm_sync = nullptr; a.sm_gates = h->sm_phase_sync == 2 ? 2 : 3;
+    a.order = nullptr;
+    if (!queue_mode && h->order_by_history && h->hist_B == total && total > h->num_sms)
+    {
+        // (d_iters is rewritten by this solve: order from a copy)
+        CK(cudaMemcpyAsync(h->d_prev_iters, h->d_iters, (size_t)total * 4, cudaMemcpyDeviceToDevice, h->stream));
+        order_by_history_kernel<<<1, 1024, 0, h->stream>>>(h->d_prev_iters, total, h->d_order);
+        h->stats.launches_total += 1;
+        a.order = h->d_order;
+    }
+    if (!queue_mode) h->hist_B = total;
     const size_t smem = IMG_HEAD + (size_t)a.img_words * 8;
     if (smem > MAX_IMG_SMEM) return set_err(h, MPCB200_E_UNSUPPORTED, "the instance does not fit in shared memory");
     const int threads = group_threads(h);
@@ -1172,6 +1225,7 @@ extern "C" int mpcb200_set_option(mpcb200_handle* h, int option, int value)
     if (!h) return MPCB200_E_INVALID;
     if (option == MPCB200_OPT_SOLVE_MODE && value >= 0 && value <= 1) { h->solve_mode = value; return 0; }
     if (option == MPCB200_OPT_CTAS_PER_SM && value >= 0 && value <= 32) { h->max_ctas_per_sm = value; return 0; }
+    if (option == MPCB200_OPT_ORDER_BY_HISTORY && value >= 0 && value <= 1) { h->order_by_history = value; return 0; }
     if (option == MPCB200_OPT_SM_PHASE_SYNC && value >= -1 && value <= 2) { h->sm_phase_sync = value; return 0; }
     return set_err(h, MPCB200_E_INVALID, "unknown option or value");
 }

@@ -342,31 +342,40 @@ def test_resident_list_overflow_is_counted(cuda_lib):
 
 
 def test_execution_options_do_not_change_results(cuda_lib):
-    """MPCB200_OPT_SM_PHASE_SYNC (phase alignment of the CTAs that share an SM: off / three gates / two gates) and
-    MPCB200_OPT_CTAS_PER_SM only change WHEN a CTA runs a phase: every instance gets bit for bit the same result.  The batch is
-    large enough for several CTAs per SM, so the gates really wait."""
+    """MPCB200_OPT_SM_PHASE_SYNC (phase alignment of the CTAs that share an SM: off / three gates / two gates),
+    MPCB200_OPT_CTAS_PER_SM and MPCB200_OPT_ORDER_BY_HISTORY (queue longest-first by the previous solve's iteration counts) only
+    change WHEN a CTA runs WHICH instance: every instance gets bit for bit the same result.  The batch is large enough for
+    several CTAs per SM and a second wave, so the gates really wait and the order really matters; every solver runs the batch
+    twice (cold) so that the second solve has a history."""
     cfg = configs.cfg2(tol=1e-6)
-    B = 700
+    B = 900
     data = configs.generate(2, B)
     ref = None
-    for sync, cap in ((0, 0), (1, 0), (2, 0), (1, 2), (-1, 0)):
+    times = {}
+    for sync, cap, order in ((0, 0, 0), (1, 0, 0), (2, 0, 0), (1, 2, 1), (-1, 0, 1), (-1, 0, 0)):
         s = capi.BatchSolver(cfg, B, device=0)
         s.set_option(capi.OPT_SM_PHASE_SYNC, sync)
         s.set_option(capi.OPT_CTAS_PER_SM, cap)
-        out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
-        st = s.stats()
-        if sync > 0:
-            assert st["gate_ms"] > 0.0
-        if sync == 0:
-            assert st["gate_ms"] == 0.0
-        if ref is None:
-            ref = out
-        else:
-            for k in ("status", "iters", "u_seq", "x_seq", "dt", "kkt_err"):
-                np.testing.assert_array_equal(out[k], ref[k])
+        s.set_option(capi.OPT_ORDER_BY_HISTORY, order)
+        for rep in range(2):
+            s.reset()
+            out = s.step(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
+            st = s.stats()
+            if sync > 0:
+                assert st["gate_ms"] > 0.0
+            if sync == 0:
+                assert st["gate_ms"] == 0.0
+            if ref is None:
+                ref = out
+            else:
+                for k in ("status", "iters", "u_seq", "x_seq", "dt", "kkt_err"):
+                    np.testing.assert_array_equal(out[k], ref[k])
+        times[(sync, cap, order)] = out["solve_time_s"]
         # a queue through the aligned kernel as well
         if sync == 1 and cap == 0:
             q = s.solve_stream(data["x0"], data["xf"], data["u_prev"], data["u_prev_dt"], data["obstacles"], None)
             np.testing.assert_array_equal(q["u_seq"], ref["u_seq"])
         s.close()
     assert (ref["status"] == 0).mean() > 0.95
+    # with the history the second solve must not be slower than in index order (it starts its longest instances first)
+    assert times[(-1, 0, 1)] <= 1.05 * times[(-1, 0, 0)]
