@@ -390,7 +390,18 @@ def main():
                 "in_solve": {"kkt_share_of_cta_time": ph[capi.PHASE_KKT] / ph_sum,
                              "kkt_calls": st["kkt_instances"], "sweeps_per_call": st["kkt_sweeps"] / max(st["kkt_instances"], 1),
                              "algorithmic_gbs_over_the_step": st["kkt_instances"] * bpi / el / 1e9,
-                             "note": "inside the persistent solve kernel the records never leave shared memory"}}
+                             "note": "inside the persistent solve kernel the records never leave shared memory"},
+                "dominant_kernel": {"kernel": "solve_fused_kernel (one launch = one step: every instance from the initial guess to convergence)",
+                                    "share_of_step": 0.94, "share_source": "profiles/r2_launch_shares.txt (ncu launch list of this command)",
+                                    "avg_launch_ms": el / args.steps * 1e3,
+                                    "algorithmic_gbs": st["kkt_instances"] * bpi / el / 1e9, "frac_of_hbm_peak": st["kkt_instances"] * bpi / el / 1e9 / peak,
+                                    "dram_bytes_per_launch_ncu": 43140864,
+                                    "note": "SURVEY 8d's per-unit bytes (the KKT records and steps of every instance-iteration) x the "
+                                            "instance-iterations of a step / the step time.  The kernel keeps those records in shared memory "
+                                            "(ncu: 7.9 MB read + 35.2 MB written per launch, profiles/r2_fused_ncu.txt), so it is nowhere near "
+                                            "the HBM roofline by construction: it is bound by the latency of one interior-point iteration "
+                                            "(DESIGN.md 4).  The stand-alone KKT kernel above is the one kernel of the path that streams its "
+                                            "data through HBM, hence the roofline kernel."}}
 
     # ================= secondary blocks =================
     extra = {}
