@@ -377,5 +377,6 @@ def test_execution_options_do_not_change_results(cuda_lib):
             np.testing.assert_array_equal(q["u_seq"], ref["u_seq"])
         s.close()
     assert (ref["status"] == 0).mean() > 0.95
-    # with the history the second solve must not be slower than in index order (it starts its longest instances first)
-    assert times[(-1, 0, 1)] <= 1.05 * times[(-1, 0, 0)]
+    # with the history the second solve starts its longest instances first: it must not be clearly slower than index order
+    # (loose bound: a timing, not a result)
+    assert times[(-1, 0, 1)] <= 1.3 * times[(-1, 0, 0)]
